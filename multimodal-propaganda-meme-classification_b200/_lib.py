@@ -1,0 +1,73 @@
+"""ctypes binding of libb200mm.so, the C-ABI CUDA library (declared in include/b200mm.h).
+
+There is no CPU or PyTorch fallback: if the library cannot be loaded, or an entry point returns a
+non-zero status, the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_longlong, c_void_p, c_float, c_ulonglong
+
+from . import _build
+
+_lib = None
+
+c_ptr = c_void_p
+
+# name -> argtypes (restype is always int: 0 = ok, >0 = cudaError_t, <0 = b200mm error)
+_SIGNATURES: dict[str, list] = {}
+
+
+def declare(name: str, argtypes: list) -> None:
+    _SIGNATURES[name] = argtypes
+
+
+class B200MMError(RuntimeError):
+    pass
+
+
+_ERRORS = {-1: "bad argument (shape/alignment contract)", -2: "CUDA driver entry point unavailable",
+           -3: "tensor map rejected by the driver", -4: "device is not sm_100 (B200)"}
+
+
+def load(build_if_needed: bool = True) -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if build_if_needed and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on the box and a stale .so: use what travelled with the repo
+            if not os.path.exists(path):
+                raise B200MMError(f"libb200mm.so missing and cannot be built: {e}") from e
+    if not os.path.exists(path):
+        raise B200MMError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(path)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        if rc > 0:
+            raise B200MMError(f"{name}: CUDA error {rc}")
+        raise B200MMError(f"{name}: {_ERRORS.get(rc, rc)}")
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)
+
+
+# ------------------------------------------------------------------ signatures (mirror include/b200mm.h)
+declare("b200mm_version", [])
+declare("b200mm_num_sms", [])
+declare("b200mm_gemm_bf16", [c_ptr, c_int, c_longlong, c_ptr, c_int, c_longlong, c_int, c_int, c_int, c_int,
+                             c_ptr, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong,
+                             c_int, c_int, c_ptr])

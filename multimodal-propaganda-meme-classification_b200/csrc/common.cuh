@@ -1,0 +1,47 @@
+// Host-side helpers shared by every translation unit of libb200mm: error plumbing, device
+// properties, and TMA tensor-map construction through the driver entry point (so the library
+// needs no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+
+#define B200MM_API extern "C" __attribute__((visibility("default")))
+
+// All C-ABI entry points return 0 on success or a cudaError_t / negative b200mm code.
+enum : int {
+  B200MM_OK = 0,
+  B200MM_ERR_BAD_ARG = -1,      // shape / alignment contract violated
+  B200MM_ERR_NO_DRIVER = -2,    // cuTensorMapEncodeTiled not resolvable
+  B200MM_ERR_TENSORMAP = -3,    // driver rejected the tensor map
+  B200MM_ERR_NOT_SM100 = -4,    // device is not compute capability 10.x
+};
+
+#define B200MM_CHECK_LAUNCH()                         \
+  do {                                                \
+    cudaError_t e__ = cudaGetLastError();             \
+    if (e__ != cudaSuccess) return static_cast<int>(e__); \
+  } while (0)
+
+namespace b200 {
+
+struct DeviceInfo {
+  int num_sms = 0;
+  int cc_major = 0;
+  bool ok = false;
+};
+const DeviceInfo& device_info();
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows `row_stride_bytes` apart,
+// box = box_inner x box_outer, SWIZZLE_128B (box_inner * 2 B must be <= 128 B), zero OOB fill.
+int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer);
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) {
+  return (a + b - 1) / b;
+}
+
+}  // namespace b200

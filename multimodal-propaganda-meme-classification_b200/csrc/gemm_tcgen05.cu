@@ -1,0 +1,375 @@
+// bf16 GEMM on the 5th-generation tensor cores: D[M,N] = A x B with fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer   : cp.async.bulk.tensor -> STAGES-deep smem ring (SWIZZLE_128B)
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warps 2..9  epilogue       : tcgen05.ld accumulator -> bias / GELU / dGELU / residual -> global
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Both operands may be K-major ("row-major with the reduction dim contiguous")
+// or MN-major (reduction dim strided) -- this is what lets the same kernel serve
+//   forward   Y  = X  W^T      (A K-major,  B K-major)      reference: nn.Linear / 1x1 conv / im2col conv
+//   dgrad     dX = dY W        (A K-major,  B MN-major)
+//   wgrad     dW = dY^T X      (A MN-major, B MN-major, split-K over the token dim, fp32 red.add)
+// without transposing anything in HBM.
+//
+// Replaces: the cuBLASLt calls behind
+// transformers/models/distilbert/modeling_distilbert.py q_lin/k_lin/v_lin/out_lin/lin1/lin2 and the
+// cuDNN convolutions behind torchvision/models/resnet.py, as driven by
+// example_scripts/Multimodal_example_task2C.txt:172-197.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;              // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_UMMA_K = 16;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
+constexpr int GEMM_SMEM_BUDGET = 200 * 1024;  // operand ring; barriers live behind it
+
+enum EpiMode : int {
+  EPI_STORE = 0,       // out = bf16(acc + bias + residual)
+  EPI_GELU = 1,        // out = bf16(z = acc + bias); out2 = bf16(gelu(z))
+  EPI_DGELU = 2,       // out = bf16(acc * gelu'(aux))
+  EPI_F32 = 3,         // out_f32 = acc + bias
+  EPI_F32_ATOMIC = 4,  // out_f32 += acc        (split-K partial sums)
+  EPI_RELU = 5,        // out = bf16(max(acc + bias + residual, 0))
+};
+
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;  // operand majorness flags (0 = K-major, 1 = MN-major)
+  int m_tiles, n_tiles, splits, k_iters, k_iters_per_split;
+  int epi;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  const __nv_bfloat16* aux;
+  long long ld_aux;
+  void* out;
+  long long ldc;
+  __nv_bfloat16* out2;
+  long long ld2;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : GEMM_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int num_work = tiles_mn * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w / tiles_mn;
+        const int t = w - split * tiles_mn;
+        const int m_blk = t / p.n_tiles;
+        const int n_blk = t - m_blk * p.n_tiles;
+        const int k_begin = split * p.k_iters_per_split;
+        const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + j * 64, kb * GEMM_BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * GEMM_BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, p.a_mn, p.b_mn);
+      // K-major: 16-element k step = 32 B inside the swizzle row; 8-row groups 1024 B apart.
+      // MN-major: 16-element k step = two 8-k-row groups = 2048 B; 64-wide MN atoms one 8 KB box apart.
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w / tiles_mn;
+        const int k_begin = split * p.k_iters_per_split;
+        const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;              // which half of the BN columns
+    constexpr int HALF_COLS = BN / 2;
+    constexpr int CHUNK = HALF_COLS < 32 ? HALF_COLS : 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int split = w / tiles_mn;
+      const int t = w - split * tiles_mn;
+      const int m_blk = t / p.n_tiles;
+      const int n_blk = t - m_blk * p.n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const long long row = static_cast<long long>(m_blk) * GEMM_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < HALF_COLS / CHUNK; ++c) {
+        const int col_in_tile = half * HALF_COLS + c * CHUNK;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + col_in_tile;
+        uint32_t v[32];
+        if constexpr (CHUNK == 32) {
+          tmem_ld32(taddr, v);
+        } else {
+          uint32_t v16[16];
+          tmem_ld16(taddr, v16);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v16[i];
+        }
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + col_in_tile;
+        if (row_ok && col0 < p.N) {
+#pragma unroll
+          for (int g = 0; g < CHUNK / 8; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= p.N) break;
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+            if (p.bias != nullptr && (p.epi != EPI_F32_ATOMIC)) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            if (p.epi == EPI_STORE || p.epi == EPI_RELU) {
+              if (p.residual != nullptr) {
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col));
+                const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
+                             r3 = unpack_bf16x2(r.w);
+                x[0] += r0.x; x[1] += r0.y; x[2] += r1.x; x[3] += r1.y;
+                x[4] += r2.x; x[5] += r2.y; x[6] += r3.x; x[7] += r3.y;
+              }
+              if (p.epi == EPI_RELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+              }
+              uint4 o;
+              o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+              o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col) = o;
+            } else if (p.epi == EPI_GELU) {
+              uint4 o;
+              o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+              o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col) = o;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+              o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+              o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(p.out2 + row * p.ld2 + col) = o;
+            } else if (p.epi == EPI_DGELU) {
+              const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.aux + row * p.ld_aux + col));
+              const float2 z0 = unpack_bf16x2(r.x), z1 = unpack_bf16x2(r.y), z2 = unpack_bf16x2(r.z),
+                           z3 = unpack_bf16x2(r.w);
+              x[0] *= gelu_erf_grad(z0.x); x[1] *= gelu_erf_grad(z0.y);
+              x[2] *= gelu_erf_grad(z1.x); x[3] *= gelu_erf_grad(z1.y);
+              x[4] *= gelu_erf_grad(z2.x); x[5] *= gelu_erf_grad(z2.y);
+              x[6] *= gelu_erf_grad(z3.x); x[7] *= gelu_erf_grad(z3.y);
+              uint4 o;
+              o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+              o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col) = o;
+            } else if (p.epi == EPI_F32) {
+              float* o = static_cast<float*>(p.out) + row * p.ldc + col;
+              *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            } else {  // EPI_F32_ATOMIC
+              float* o = static_cast<float*>(p.out) + row * p.ldc + col;
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(x[0]), "f"(x[1]), "f"(x[2]),
+                           "f"(x[3])
+                           : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 4), "f"(x[4]), "f"(x[5]),
+                           "f"(x[6]), "f"(x[7])
+                           : "memory");
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// D[M,N] = A x B (+ epilogue), bf16 operands, fp32 accumulate.
+//   a_mn == 0: A is stored [M, K] (row stride lda elements);  a_mn == 1: A is stored [K, M].
+//   b_mn == 0: B is stored [N, K] (row stride ldb elements);  b_mn == 1: B is stored [K, N].
+//   epi: EpiMode above.  splits > 1 requires epi == EPI_F32_ATOMIC (out must be pre-zeroed or hold the
+//   value to accumulate onto).  block_n in {0 (auto), 64, 128, 256}.
+// Contract: pointers 16-byte aligned, lda/ldb/ldc/... multiples of 8 elements, N % 8 == 0.
+B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb,
+                                int M, int N, int K, int epi, const float* bias, const void* residual,
+                                long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
+                                void* out2, long long ld2, int splits, int block_n, void* stream) {
+  const DeviceInfo& dev = device_info();
+  if (!dev.ok) return B200MM_ERR_NOT_SM100;
+  if (dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || (lda & 7) || (ldb & 7) || (ldc & 3)) return B200MM_ERR_BAD_ARG;
+  if (epi < EPI_STORE || epi > EPI_RELU) return B200MM_ERR_BAD_ARG;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && epi != EPI_F32_ATOMIC) return B200MM_ERR_BAD_ARG;
+  if (epi == EPI_GELU && out2 == nullptr) return B200MM_ERR_BAD_ARG;
+  if (epi == EPI_DGELU && aux == nullptr) return B200MM_ERR_BAD_ARG;
+
+  int bn = block_n;
+  if (bn == 0) bn = (N % 256 == 0 || N > 512) ? 256 : (N > 64 ? 128 : 64);
+  if (bn != 64 && bn != 128 && bn != 256) return B200MM_ERR_BAD_ARG;
+
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn ? 1 : 0;
+  p.b_mn = b_mn ? 1 : 0;
+  p.m_tiles = ceil_div(M, GEMM_BM);
+  p.n_tiles = ceil_div(N, bn);
+  p.k_iters = ceil_div(K, GEMM_BK);
+  if (splits > p.k_iters) splits = p.k_iters;
+  p.k_iters_per_split = ceil_div(p.k_iters, splits);
+  p.splits = ceil_div(p.k_iters, p.k_iters_per_split);
+  p.epi = epi;
+  p.bias = bias;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.ldr = ldr;
+  p.aux = static_cast<const __nv_bfloat16*>(aux);
+  p.ld_aux = ld_aux;
+  p.out = out;
+  p.ldc = ldc;
+  p.out2 = static_cast<__nv_bfloat16*>(out2);
+  p.ld2 = ld2;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, A, K, M, lda * 2, GEMM_BK, GEMM_BM);
+  else         rc = make_tmap_2d_bf16(&ta, A, M, K, lda * 2, 64, GEMM_BK);
+  if (rc) return rc;
+  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, B, K, N, ldb * 2, GEMM_BK, bn);
+  else         rc = make_tmap_2d_bf16(&tb, B, N, K, ldb * 2, 64, GEMM_BK);
+  if (rc) return rc;
+
+  const int num_work = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = num_work < dev.num_sms ? num_work : dev.num_sms;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch_gemm<64>(ta, tb, p, grid, s);
+    case 128: return launch_gemm<128>(ta, tb, p, grid, s);
+    default: return launch_gemm<256>(ta, tb, p, grid, s);
+  }
+}
