@@ -70,4 +70,41 @@ declare("b200mm_version", [])
 declare("b200mm_num_sms", [])
 declare("b200mm_gemm_bf16", [c_ptr, c_int, c_longlong, c_ptr, c_int, c_longlong, c_int, c_int, c_int, c_int,
                              c_ptr, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong,
-                             c_int, c_int, c_ptr])
+                             c_int, c_int, c_float, c_ulonglong, c_ptr])
+declare("b200mm_attention_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float, c_ulonglong, c_ptr])
+declare("b200mm_attention_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float,
+                                 c_ulonglong, c_ptr])
+declare("b200mm_layernorm_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_float, c_float,
+                                 c_ulonglong, c_ptr])
+declare("b200mm_embed_layernorm_fwd", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       c_int, c_int, c_float, c_float, c_ulonglong, c_ptr])
+declare("b200mm_layernorm_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int,
+                                 c_float, c_ulonglong, c_float, c_ulonglong, c_ptr])
+declare("b200mm_embedding_bwd", [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_int, c_int, c_ptr])
+declare("b200mm_mask_to_bias", [c_ptr, c_ptr, c_longlong, c_ptr])
+declare("b200mm_colsum_bf16", [c_ptr, c_longlong, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_head_loss", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_float, c_float, c_int,
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_sumsq_f32", [c_ptr, c_longlong, c_ptr, c_ptr])
+declare("b200mm_adam_step", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_longlong, c_float, c_float, c_float, c_float,
+                             c_float, c_int, c_ptr, c_float, c_float, c_ptr])
+declare("b200mm_cast_f32_to_bf16", [c_ptr, c_ptr, c_longlong, c_ptr])
+declare("b200mm_gather_rows", [c_ptr, c_ptr, c_int, c_int, c_longlong, c_longlong, c_float, c_ulonglong, c_ptr])
+declare("b200mm_scatter_rows", [c_ptr, c_ptr, c_longlong, c_int, c_longlong, c_longlong, c_float, c_ulonglong,
+                                c_ptr])
+declare("b200mm_batchnorm_fwd", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_float, c_float, c_int, c_ptr,
+                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_batchnorm_eval", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_float, c_int,
+                                  c_ptr, c_ptr])
+declare("b200mm_batchnorm_bwd", [c_ptr, c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr,
+                                 c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_maxpool3x3s2_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr])
+declare("b200mm_maxpool3x3s2_bwd", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_avgpool_fwd", [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_avgpool_bwd", [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_im2col_nhwc", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_col2im_nhwc", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_im2col_nchw_f32", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr,
+                                   c_ptr])
+declare("b200mm_subsample_nhwc", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_upsample_add_nhwc", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])

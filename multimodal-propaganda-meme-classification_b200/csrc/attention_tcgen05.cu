@@ -1,0 +1,457 @@
+// Fused multi-head self-attention (head_dim 64, S <= 128) forward and backward on tcgen05 + TMA.
+//
+// One CTA (128 threads) handles one (batch, head) at a time, persistently:
+//   forward :  S = Q K^T (tcgen05.mma, fp32 in TMEM) -> scale + additive key-padding bias -> softmax in
+//              registers (thread r owns query row r: TMEM lane r) -> Philox dropout -> P (bf16) staged in
+//              128B-swizzled smem -> O = P V (tcgen05.mma) -> 1/rowsum -> global.  LSE kept for backward.
+//   backward:  recompute S and dP = dO V^T on the tensor core, P = exp(S - LSE), dS = P o (dP - delta),
+//              then dV = P^T dO, dK = dS^T Q, dQ = dS K -- the transposed operands are the SAME smem tiles
+//              read through MN-major UMMA descriptors, nothing is transposed in memory.
+// Q/K/V are read straight out of the fused-QKV projection output [B*S, 3*D] (and dQ/dK/dV written into
+// the matching [B*S, 3*D] gradient) with 3-D TMA boxes, so no head-major re-layout pass exists.
+//
+// Replaces: transformers/models/distilbert/modeling_distilbert.py:126-151
+// (eager_attention_forward: softmax(QK^T * d^-1/2 + mask) -> dropout -> @V) and its autograd backward.
+#include "common.cuh"
+#include "device_utils.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int ATT_T = 128;   // query / key tile (== max sequence length of this kernel)
+constexpr int ATT_D = 64;    // head dim
+constexpr int ATT_TILE_BYTES = ATT_T * ATT_D * 2;  // 16 KB: one [128 x 64] bf16 tile, 128B rows
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnParams {
+  int B, H, S, D;  // D = H * 64
+  float scale_log2;      // head_dim^-1/2 * log2(e)
+  float scale;           // head_dim^-1/2
+  float p_drop;
+  uint32_t drop_threshold;
+  float inv_keep;
+  unsigned long long seed;
+  const float* key_bias;  // [B, S] additive bias (0 / -inf for padded keys) or nullptr
+  __nv_bfloat16* out;     // fwd: O [B*S, D]
+  float* lse;             // [B, H, S] natural-log LSE of the scaled+biased scores
+  const __nv_bfloat16* o_in;   // bwd: O
+  const __nv_bfloat16* do_in;  // bwd: dO [B*S, D]
+  __nv_bfloat16* dqkv;         // bwd: [B*S, 3D]
+};
+
+// byte offset of 16-byte chunk `chunk` (0..7) of row `r` inside a [rows x 64] bf16 SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int chunk) { return r * 128 + ((chunk ^ (r & 7)) << 4); }
+
+// write 32 consecutive bf16 of row r (columns c0..c0+31, c0 % 32 == 0) into a [128 x 128] tile stored as two
+// [128 x 64] swizzled blocks
+__device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c0, const float (&x)[32]) {
+  uint8_t* blk = tile + (c0 >> 6) * ATT_TILE_BYTES;
+  const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    o.x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
+    o.y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
+    o.z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
+    o.w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
+    *reinterpret_cast<uint4*>(blk + sw128_off(r, chunk0 + q)) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_TILE_BYTES;
+  uint8_t* sP = sV + ATT_TILE_BYTES;  // 32 KB
+  float* sBias = reinterpret_cast<float*>(sP + 2 * ATT_TILE_BYTES);
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + ATT_T);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_S = tmem, t_O = tmem + 128;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+
+  uint32_t load_phase = 0;
+  const int items = p.B * p.H;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / p.H, h = item - b * p.H;
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, 3 * ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tma_qkv, bar_load, h * ATT_D, 0, b);
+      tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, 0, b);
+      tma_load_3d(sV, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, 0, b);
+    }
+    sBias[tid] = tid < p.S ? (p.key_bias ? p.key_bias[b * p.S + tid] * LOG2E : 0.f) : -INFINITY;
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar_load, load_phase);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(t_S, umma_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024), umma_desc_sw128(smem_u32(sK) + k * 32, 16, 1024),
+                  idesc_s, k > 0);
+      umma_commit(bar_mma);
+    }
+    load_phase ^= 1;
+    mbar_wait(bar_mma, 0);
+    tc_fence_after_sync();
+
+    // ---- softmax over the 128 key columns of this thread's query row
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_S + lane_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[c * 32 + i]));
+    }
+    if (mx == -INFINITY) mx = 0.f;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_S + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      float x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        x[i] = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[c * 32 + i]) - mx);
+        sum += x[i];
+      }
+      if (use_drop) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint64_t gidx = (static_cast<uint64_t>(item) * ATT_T + tid) * 32 + c * 8 + g;
+          const uint32_t keep = dropout_keep4(p.seed, gidx, p.drop_threshold);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[g * 4 + i] = (keep >> i) & 1 ? x[g * 4 + i] * p.inv_keep : 0.f;
+        }
+      }
+      store_row32_sw128(sP, tid, c * 32, x);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(t_O,
+                  umma_desc_sw128(smem_u32(sP) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 1);
+    tc_fence_after_sync();
+
+    const float inv_sum = 1.f / sum;
+    const bool row_ok = tid < p.S;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.S + tid) * p.D + h * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_O + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv_sum, __uint_as_float(v[q * 8 + 1]) * inv_sum);
+          o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv_sum, __uint_as_float(v[q * 8 + 3]) * inv_sum);
+          o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv_sum, __uint_as_float(v[q * 8 + 5]) * inv_sum);
+          o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv_sum, __uint_as_float(v[q * 8 + 7]) * inv_sum);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = o;
+        }
+      }
+    }
+    if (row_ok && p.lse) p.lse[static_cast<long long>(item) * p.S + tid] = (mx + log2f(sum)) * LN2;
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_TILE_BYTES;
+  uint8_t* sdO = sV + ATT_TILE_BYTES;
+  uint8_t* sP = sdO + ATT_TILE_BYTES;       // 32 KB, P (dropped) as bf16
+  uint8_t* sdS = sP + 2 * ATT_TILE_BYTES;   // 32 KB, dS * scale as bf16
+  float* sBias = reinterpret_cast<float*>(sdS + 2 * ATT_TILE_BYTES);
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + ATT_T);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_S = tmem, t_dP = tmem + 128;               // phase 1
+  const uint32_t t_dV = tmem, t_dK = tmem + 64, t_dQ = tmem + 128;  // phase 2 (reuses the columns)
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);  // A^T (MN-major) x B (MN-major)
+  const uint32_t idesc_nt = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+
+  uint32_t load_phase = 0;
+  const int items = p.B * p.H;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / p.H, h = item - b * p.H;
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, 4 * ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tma_qkv, bar_load, h * ATT_D, 0, b);
+      tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, 0, b);
+      tma_load_3d(sV, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, 0, b);
+      tma_load_3d(sdO, &tma_do, bar_load, h * ATT_D, 0, b);
+    }
+    sBias[tid] = tid < p.S ? (p.key_bias ? p.key_bias[b * p.S + tid] * LOG2E : 0.f) : -INFINITY;
+    // delta_r = sum_d dO[r,d] * O[r,d]; lse of this query row (rows beyond S contribute nothing)
+    const bool row_ok = tid < p.S;
+    float delta = 0.f, lse_l2 = INFINITY;
+    if (row_ok) {
+      const long long off = (static_cast<long long>(b) * p.S + tid) * p.D + h * ATT_D;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float a[8], g[8];
+        load8(p.o_in + off + q * 8, a);
+        load8(p.do_in + off + q * 8, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) delta = fmaf(a[i], g[i], delta);
+      }
+      lse_l2 = p.lse[static_cast<long long>(item) * p.S + tid] * LOG2E;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar_load, load_phase);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(t_S, umma_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024), umma_desc_sw128(smem_u32(sK) + k * 32, 16, 1024),
+                  idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(t_dP, umma_desc_sw128(smem_u32(sdO) + k * 32, 16, 1024),
+                  umma_desc_sw128(smem_u32(sV) + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit(bar_mma);
+    }
+    load_phase ^= 1;
+    mbar_wait(bar_mma, 0);
+    tc_fence_after_sync();
+
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t vs[32], vp[32];
+      tmem_ld32(t_S + lane_addr + c * 32, vs);
+      tmem_ld32(t_dP + lane_addr + c * 32, vp);
+      tmem_ld_wait();
+      float pd[32], ds[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float prob = exp2f(fmaf(__uint_as_float(vs[i]), p.scale_log2, sBias[c * 32 + i]) - lse_l2);
+        pd[i] = prob;
+        ds[i] = __uint_as_float(vp[i]);
+      }
+      if (use_drop) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint64_t gidx = (static_cast<uint64_t>(item) * ATT_T + tid) * 32 + c * 8 + g;
+          const uint32_t keep = dropout_keep4(p.seed, gidx, p.drop_threshold);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float m = (keep >> i) & 1 ? p.inv_keep : 0.f;
+            const float prob = pd[g * 4 + i];
+            pd[g * 4 + i] = prob * m;                                         // dropped probs (for dV)
+            ds[g * 4 + i] = prob * (ds[g * 4 + i] * m - delta) * p.scale;     // dS
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ds[i] = pd[i] * (ds[i] - delta) * p.scale;
+      }
+      store_row32_sw128(sP, tid, c * 32, pd);
+      store_row32_sw128(sdS, tid, c * 32, ds);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+      // dV[key, d] = sum_q P[q, key] dO[q, d]     A = P^T: MN-major (64-key atoms = the two blocks), K = query rows
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(t_dV, umma_desc_sw128(smem_u32(sP) + k * 2048, ATT_TILE_BYTES, 1024),
+                  umma_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024), idesc_tt, k > 0);
+      // dK[key, d] = sum_q dS[q, key] Q[q, d]
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(t_dK, umma_desc_sw128(smem_u32(sdS) + k * 2048, ATT_TILE_BYTES, 1024),
+                  umma_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024), idesc_tt, k > 0);
+      // dQ[q, d] = sum_key dS[q, key] K[key, d]   A = dS K-major, B = K MN-major
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(t_dQ, umma_desc_sw128(smem_u32(sdS) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_nt, k > 0);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 1);
+    tc_fence_after_sync();
+
+    __nv_bfloat16* grow = p.dqkv + (static_cast<long long>(b) * p.S + tid) * (3 * p.D) + h * ATT_D;
+#pragma unroll 1
+    for (int which = 0; which < 3; ++which) {
+      const uint32_t t_src = which == 0 ? t_dQ : (which == 1 ? t_dK : t_dV);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_src + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(grow + which * p.D + c * 32 + q * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+constexpr int ATT_FWD_SMEM = 5 * ATT_TILE_BYTES + ATT_T * 4 + 64 + 1024;
+constexpr int ATT_BWD_SMEM = 8 * ATT_TILE_BYTES + ATT_T * 4 + 64 + 1024;
+
+static int fill_params(AttnParams& p, int B, int H, int S, float p_drop, unsigned long long seed,
+                       const float* key_bias) {
+  if (B <= 0 || H <= 0 || S <= 0 || S > ATT_T || p_drop < 0.f || p_drop >= 1.f) return B200MM_ERR_BAD_ARG;
+  p.B = B; p.H = H; p.S = S; p.D = H * ATT_D;
+  p.scale = 0.125f;  // 64^-1/2
+  p.scale_log2 = p.scale * LOG2E;
+  p.p_drop = p_drop;
+  p.drop_threshold = dropout_threshold(p_drop);
+  p.inv_keep = 1.f / (1.f - p_drop);
+  p.seed = seed;
+  p.key_bias = key_bias;
+  return B200MM_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// O[B*S, H*64] = softmax(Q K^T / 8 + key_bias) (dropout) V, Q/K/V = column blocks of qkv [B*S, 3*H*64].
+// lse [B,H,S] (fp32) is written when non-null (required for the backward).  S <= 128.
+B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
+                                    float p_drop, unsigned long long seed, void* stream) {
+  const DeviceInfo& dev = device_info();
+  if (!dev.ok || dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
+  AttnParams p{};
+  int rc = fill_params(p, B, H, S, p_drop, seed, key_bias);
+  if (rc) return rc;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  CUtensorMap tq;
+  const uint64_t row = static_cast<uint64_t>(3) * p.D * 2;
+  rc = make_tmap_3d_bf16(&tq, qkv, 3 * p.D, S, B, row, row * S, ATT_D, ATT_T);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int items = B * H;
+  const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
+  attn_fwd_kernel<<<grid, 128, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// dqkv [B*S, 3*H*64] <- gradients of Q, K, V given dO, using O and the saved LSE.
+B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, const void* out, const void* dout,
+                                    const float* lse, void* dqkv, int B, int H, int S, float p_drop,
+                                    unsigned long long seed, void* stream) {
+  const DeviceInfo& dev = device_info();
+  if (!dev.ok || dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
+  AttnParams p{};
+  int rc = fill_params(p, B, H, S, p_drop, seed, key_bias);
+  if (rc) return rc;
+  if (lse == nullptr) return B200MM_ERR_BAD_ARG;
+  p.lse = const_cast<float*>(lse);
+  p.o_in = static_cast<const __nv_bfloat16*>(out);
+  p.do_in = static_cast<const __nv_bfloat16*>(dout);
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  CUtensorMap tq, td;
+  const uint64_t row = static_cast<uint64_t>(3) * p.D * 2;
+  rc = make_tmap_3d_bf16(&tq, qkv, 3 * p.D, S, B, row, row * S, ATT_D, ATT_T);
+  if (rc) return rc;
+  const uint64_t orow = static_cast<uint64_t>(p.D) * 2;
+  rc = make_tmap_3d_bf16(&td, dout, p.D, S, B, orow, orow * S, ATT_D, ATT_T);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const int items = B * H;
+  const int grid = items < dev.num_sms ? items : dev.num_sms;
+  attn_bwd_kernel<<<grid, 128, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}

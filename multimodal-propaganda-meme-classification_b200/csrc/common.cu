@@ -49,6 +49,23 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
   return r == CUDA_SUCCESS ? B200MM_OK : B200MM_ERR_TENSORMAP;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return B200MM_ERR_NO_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15) || box0 * 2 > 128 ||
+      box1 > 256)
+    return B200MM_ERR_BAD_ARG;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200MM_OK : B200MM_ERR_TENSORMAP;
+}
+
 }  // namespace b200
 
 B200MM_API int b200mm_version() { return 100; }

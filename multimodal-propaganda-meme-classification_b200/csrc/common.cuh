@@ -39,6 +39,10 @@ const DeviceInfo& device_info();
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer);
 
+// 3-D bf16 tensor map over [d2][d1][d0] (d0 contiguous), box = box0 x box1 x 1, SWIZZLE_128B.
+int make_tmap_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
   return (a + b - 1) / b;

@@ -1,0 +1,665 @@
+// Image-tower kernels that surround the implicit-GEMM convolutions (all NHWC bf16, HBM-bound, 16-byte
+// accesses over the channel dim): train-mode BatchNorm (+ReLU, +residual) forward/backward, max / average
+// pooling, and the im2col / col2im lowering that turns 3x3 and 7x7 convolutions into the tcgen05 GEMM.
+//
+// Replaces: torchvision/models/resnet.py:197-206 (stem), :108-163 (Bottleneck),
+// :266-280 (_forward_impl) -- cuDNN convolution / batch-norm and ATen pooling -- and their backward passes.
+#include "common.cuh"
+#include "device_utils.cuh"
+
+namespace b200 {
+
+static int grid_for(long long work_items, int threads) {
+  const DeviceInfo& dev = device_info();
+  const long long max_ctas = static_cast<long long>(dev.num_sms > 0 ? dev.num_sms : 148) * 8;
+  const long long want = ceil_div(work_items, static_cast<long long>(threads));
+  return static_cast<int>(want < 1 ? 1 : (want > max_ctas ? max_ctas : want));
+}
+
+// ------------------------------------------------------------------ BatchNorm2d (training mode)
+// Layout: x [M = N*H*W, C]; G = C/8 channel groups (power of two, <= 256); a CTA of 256 threads covers
+// 256/G rows per pass, thread (ty, g) owns channels g*8..g*8+7.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta, float* __restrict__ sum,
+                float* __restrict__ sumsq) {
+  __shared__ float red[2][256][8];
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r0 + ty; r < r1; r += rpp) {
+    float v[8];
+    load8(x + r * C + g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += v[i];
+      q[i] = fmaf(v[i], v[i], q[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[0][threadIdx.x][i] = s[i];
+    red[1][threadIdx.x][i] = q[i];
+  }
+  __syncthreads();
+  if (ty == 0) {
+    for (int t = 1; t < rpp; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += red[0][t * G + g][i];
+        q[i] += red[1][t * G + g][i];
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(sum + g * 8 + i, s[i]);
+      atomicAdd(sumsq + g * 8 + i, q[i]);
+    }
+  }
+}
+
+// out = act(x * scale + shift (+ residual)); CTA 0 also records mean / rstd and updates the running statistics
+// (momentum update with the unbiased variance, as nn.BatchNorm2d does).
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual, long long M, int C,
+                int rows_per_cta, const float* __restrict__ sum, const float* __restrict__ sumsq,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum, int relu,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = g * 8 + i;
+    const float mean = sum[c] / M;
+    const float var = fmaxf(sumsq[c] / M - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    sc[i] = gamma[c] * rstd;
+    sh[i] = beta[c] - mean * sc[i];
+    if (blockIdx.x == 0 && ty == 0) {
+      mean_out[c] = mean;
+      rstd_out[c] = rstd;
+      if (running_mean != nullptr) {
+        const float unbiased = M > 1 ? var * (static_cast<float>(M) / static_cast<float>(M - 1)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  for (long long r = r0 + ty; r < r1; r += rpp) {
+    float v[8];
+    load8(x + r * C + g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+    if (residual != nullptr) {
+      float rv[8];
+      load8(residual + r * C + g * 8, rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += rv[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    store8(out + r * C + g * 8, v);
+  }
+}
+
+// eval-mode BN: running statistics instead of batch statistics
+__global__ void __launch_bounds__(256)
+bn_eval_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual, long long M, int C,
+               int rows_per_cta, const float* __restrict__ running_mean, const float* __restrict__ running_var,
+               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+               __nv_bfloat16* __restrict__ out) {
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = g * 8 + i;
+    sc[i] = gamma[c] * rsqrtf(running_var[c] + eps);
+    sh[i] = beta[c] - running_mean[c] * sc[i];
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  for (long long r = r0 + ty; r < r1; r += rpp) {
+    float v[8];
+    load8(x + r * C + g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+    if (residual != nullptr) {
+      float rv[8];
+      load8(residual + r * C + g * 8, rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += rv[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    store8(out + r * C + g * 8, v);
+  }
+}
+
+// backward pass 1: dbeta = sum dz, dgamma = sum dz * xhat, dz = dout o (out > 0) when relu
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                     const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, int relu,
+                     float* __restrict__ dgamma_sum, float* __restrict__ dbeta_sum) {
+  __shared__ float red[2][256][8];
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
+  float mu[8], rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = mean[g * 8 + i];
+    rs[i] = rstd[g * 8 + i];
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r0 + ty; r < r1; r += rpp) {
+    float d[8], xv[8];
+    load8(dout + r * C + g * 8, d);
+    load8(x + r * C + g * 8, xv);
+    if (relu) {
+      float o[8];
+      load8(out + r * C + g * 8, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sb[i] += d[i];
+      sg[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], sg[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[0][threadIdx.x][i] = sg[i];
+    red[1][threadIdx.x][i] = sb[i];
+  }
+  __syncthreads();
+  if (ty == 0) {
+    for (int t = 1; t < rpp; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sg[i] += red[0][t * G + g][i];
+        sb[i] += red[1][t * G + g][i];
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(dgamma_sum + g * 8 + i, sg[i]);
+      atomicAdd(dbeta_sum + g * 8 + i, sb[i]);
+    }
+  }
+}
+
+// backward pass 2: dx = gamma * rstd * (dz - dbeta/M - xhat * dgamma/M); optional dz copy for the identity branch;
+// CTA 0 accumulates the parameter gradients.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                    const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    int relu, const float* __restrict__ dgamma_sum, const float* __restrict__ dbeta_sum,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
+  float mu[8], rs[8], k0[8], k1[8], k2[8];
+  const float invM = 1.f / static_cast<float>(M);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = g * 8 + i;
+    mu[i] = mean[c];
+    rs[i] = rstd[c];
+    const float dg = dgamma_sum[c], db = dbeta_sum[c];
+    k0[i] = gamma[c] * rs[i];
+    k1[i] = db * invM;
+    k2[i] = dg * invM;
+    if (blockIdx.x == 0 && ty == 0) {
+      dgamma[c] += dg;
+      dbeta[c] += db;
+    }
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  for (long long r = r0 + ty; r < r1; r += rpp) {
+    float d[8], xv[8];
+    load8(dout + r * C + g * 8, d);
+    load8(x + r * C + g * 8, xv);
+    if (relu) {
+      float o[8];
+      load8(out + r * C + g * 8, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    }
+    if (dz_out != nullptr) store8(dz_out + r * C + g * 8, d);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = k0[i] * (d[i] - k1[i] - (xv[i] - mu[i]) * rs[i] * k2[i]);
+    store8(dx + r * C + g * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------ pooling
+// 3x3 / stride 2 / pad 1 max pooling; argmax (0..8, first maximum in (kh,kw) scan order like ATen) kept for bwd
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int Ho, int Wo,
+                   __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ argmax) {
+  const int G = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long t = i / G;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho * 2 - 1 + kh;
+      if (hi < 0 || hi >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo * 2 - 1 + kw;
+        if (wi < 0 || wi >= W) continue;
+        float v[8];
+        load8(x + ((static_cast<long long>(n) * H + hi) * W + wi) * C + g * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (v[k] > best[k]) { best[k] = v[k]; arg[k] = kh * 3 + kw; }
+      }
+    }
+    const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C + g * 8;
+    store8(out + o, best);
+    uint2 a;
+    a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+    a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+    *reinterpret_cast<uint2*>(argmax + o) = a;
+  }
+}
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax, int N, int H, int W,
+                   int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  const int G = C >> 3;
+  const long long total = static_cast<long long>(N) * H * W * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long t = i / G;
+    const int wi = static_cast<int>(t % W); t /= W;
+    const int hi = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int kh = 0; kh < 3; ++kh) {
+      const int th = hi + 1 - kh;
+      if (th < 0 || (th & 1) || (th >> 1) >= Ho) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tw = wi + 1 - kw;
+        if (tw < 0 || (tw & 1) || (tw >> 1) >= Wo) continue;
+        const long long o = ((static_cast<long long>(n) * Ho + (th >> 1)) * Wo + (tw >> 1)) * C + g * 8;
+        const uint2 a = *reinterpret_cast<const uint2*>(argmax + o);
+        float d[8];
+        load8(dout + o, d);
+        const int code = kh * 3 + kw;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int ak = ((k < 4 ? a.x : a.y) >> ((k & 3) * 8)) & 0xff;
+          if (ak == code) acc[k] += d[k];
+        }
+      }
+    }
+    store8(dx + ((static_cast<long long>(n) * H + hi) * W + wi) * C + g * 8, acc);
+  }
+}
+
+// global average pool [N, HW, C] -> [N, C] and its backward
+__global__ void __launch_bounds__(256)
+avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int HW, int C, __nv_bfloat16* __restrict__ out) {
+  const int G = C >> 3;
+  const long long total = static_cast<long long>(N) * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    const long long n = i / G;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < HW; ++p) {
+      float v[8];
+      load8(x + (n * HW + p) * C + g * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+    const float inv = 1.f / HW;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= inv;
+    store8(out + n * C + g * 8, acc);
+  }
+}
+__global__ void __launch_bounds__(256)
+avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int N, int HW, int C, __nv_bfloat16* __restrict__ dx) {
+  const int G = C >> 3;
+  const long long total = static_cast<long long>(N) * HW * G;
+  const float inv = 1.f / HW;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    const long long n = i / G / HW;
+    float v[8];
+    load8(dout + n * C + g * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= inv;
+    store8(dx + (i / G) * C + g * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------ im2col / col2im (NHWC)
+// cols[m, (kh*KW + kw)*C + c] = x[n, ho*stride - pad + kh, wo*stride - pad + kw, c]  (0 outside)
+__global__ void __launch_bounds__(256)
+im2col_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+              int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
+  const int G = C >> 3;
+  const int taps = KH * KW;
+  const long long total = static_cast<long long>(N) * Ho * Wo * taps * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long t = i / G;
+    const int tap = static_cast<int>(t % taps); t /= taps;  // t = output pixel index m
+    const long long m = t;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    const int hi = ho * stride - pad + tap / KW, wi = wo * stride - pad + tap % KW;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+      v = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + hi) * W + wi) * C + g * 8);
+    *reinterpret_cast<uint4*>(cols + (m * taps + tap) * C + g * 8) = v;
+  }
+}
+// dx[n,hi,wi,c] = sum over taps of dcols[m(ho,wo), tap, c] (+ addend)
+__global__ void __launch_bounds__(256)
+col2im_kernel(const __nv_bfloat16* __restrict__ dcols, const __nv_bfloat16* __restrict__ addend, int N, int H, int W,
+              int C, int KH, int KW, int stride, int pad, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  const int G = C >> 3;
+  const int taps = KH * KW;
+  const long long total = static_cast<long long>(N) * H * W * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long t = i / G;
+    const long long pix = t;
+    const int wi = static_cast<int>(t % W); t /= W;
+    const int hi = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (addend != nullptr) load8(addend + pix * C + g * 8, acc);
+    for (int kh = 0; kh < KH; ++kh) {
+      const int th = hi + pad - kh;
+      if (th < 0 || th % stride || th / stride >= Ho) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int tw = wi + pad - kw;
+        if (tw < 0 || tw % stride || tw / stride >= Wo) continue;
+        const long long m = (static_cast<long long>(n) * Ho + th / stride) * Wo + tw / stride;
+        float v[8];
+        load8(dcols + (m * taps + kh * KW + kw) * C + g * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      }
+    }
+    store8(dx + pix * C + g * 8, acc);
+  }
+}
+// Stem lowering straight from the fp32 NCHW image the reference's DataLoader yields:
+// cols[m, (kh*KW+kw)*Cin + c] (row length Kp >= KH*KW*Cin, zero padded)
+__global__ void __launch_bounds__(256)
+im2col_nchw_f32_kernel(const float* __restrict__ img, int N, int Cin, int H, int W, int KH, int KW, int stride,
+                       int pad, int Ho, int Wo, int Kp, __nv_bfloat16* __restrict__ cols) {
+  const int chunks = Kp >> 3;
+  const int K = KH * KW * Cin;
+  const long long total = static_cast<long long>(N) * Ho * Wo * chunks;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % chunks);
+    long long t = i / chunks;
+    const long long m = t;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int kk = ch * 8 + k;
+      float val = 0.f;
+      if (kk < K) {
+        const int c = kk % Cin, tap = kk / Cin;
+        const int hi = ho * stride - pad + tap / KW, wi = wo * stride - pad + tap % KW;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
+          val = __ldg(img + ((static_cast<long long>(n) * Cin + c) * H + hi) * W + wi);
+      }
+      v[k] = val;
+    }
+    store8(cols + m * Kp + ch * 8, v);
+  }
+}
+// spatial subsampling for stride-2 1x1 convolutions: out[n,ho,wo,:] = x[n,ho*s,wo*s,:]; and its transpose (zero fill)
+__global__ void __launch_bounds__(256)
+subsample_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int stride, int Ho, int Wo,
+                 __nv_bfloat16* __restrict__ out) {
+  const int G = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long t = i / G;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    *reinterpret_cast<uint4*>(out + (i / G) * C + g * 8) = *reinterpret_cast<const uint4*>(
+        x + ((static_cast<long long>(n) * H + ho * stride) * W + wo * stride) * C + g * 8);
+  }
+}
+// dx[n,hi,wi,:] = addend[n,hi,wi,:] + (hi,wi on the stride grid ? dsub[n,hi/s,wi/s,:] : 0)
+__global__ void __launch_bounds__(256)
+upsample_add_kernel(const __nv_bfloat16* __restrict__ dsub, const __nv_bfloat16* __restrict__ addend, int N, int H,
+                    int W, int C, int stride, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  const int G = C >> 3;
+  const long long total = static_cast<long long>(N) * H * W * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long t = i / G;
+    const int wi = static_cast<int>(t % W); t /= W;
+    const int hi = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (addend != nullptr) load8(addend + (i / G) * C + g * 8, acc);
+    if (hi % stride == 0 && wi % stride == 0 && hi / stride < Ho && wi / stride < Wo) {
+      float v[8];
+      load8(dsub + ((static_cast<long long>(n) * Ho + hi / stride) * Wo + wi / stride) * C + g * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+    store8(dx + (i / G) * C + g * 8, acc);
+  }
+}
+
+static bool bn_shape_ok(long long M, int C) {
+  const int G = C >> 3;
+  return M > 0 && C >= 8 && (C & 7) == 0 && G <= 256 && (G & (G - 1)) == 0;
+}
+static int bn_rows_per_cta(long long M, int C, int* grid) {
+  const DeviceInfo& dev = device_info();
+  const int rpp = 256 / (C >> 3);
+  const long long target = static_cast<long long>(dev.num_sms > 0 ? dev.num_sms : 148) * 8;
+  long long rows = ceil_div(M, target);
+  rows = ceil_div(rows, static_cast<long long>(rpp)) * rpp;
+  *grid = static_cast<int>(ceil_div(M, rows));
+  return static_cast<int>(rows);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// Training-mode BatchNorm over x [M, C] (NHWC flattened): out = act(BN(x) (+ residual)).
+// scratch: fp32 [2*C] workspace (zeroed here).  mean_out / rstd_out: fp32 [C] saved for the backward.
+// running_mean / running_var (nullable) receive the momentum update.
+B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long long M, int C, const float* gamma,
+                                    const float* beta, float eps, float momentum, int relu, void* out, float* mean_out,
+                                    float* rstd_out, float* running_mean, float* running_var, float* scratch,
+                                    void* stream) {
+  if (!bn_shape_ok(M, C)) return B200MM_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * C, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int grid;
+  const int rows = bn_rows_per_cta(M, C, &grid);
+  bn_stats_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), M, C, rows, scratch, scratch + C);
+  B200MM_CHECK_LAUNCH();
+  bn_apply_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+                                       static_cast<const __nv_bfloat16*>(residual), M, C, rows, scratch, scratch + C,
+                                       gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out,
+                                       rstd_out, running_mean, running_var);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+B200MM_API int b200mm_batchnorm_eval(const void* x, const void* residual, long long M, int C, const float* gamma,
+                                     const float* beta, const float* running_mean, const float* running_var, float eps,
+                                     int relu, void* out, void* stream) {
+  if (!bn_shape_ok(M, C)) return B200MM_ERR_BAD_ARG;
+  int grid;
+  const int rows = bn_rows_per_cta(M, C, &grid);
+  bn_eval_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, running_mean,
+      running_var, gamma, beta, eps, relu, static_cast<__nv_bfloat16*>(out));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// BatchNorm backward.  dout: gradient w.r.t. the (post-activation) output; out: that output (ReLU mask; may be null
+// when relu == 0); x: the BN input.  dx: gradient w.r.t. x; dz_out (nullable): gradient w.r.t. the pre-activation
+// sum, i.e. what flows into the residual branch.  dgamma / dbeta accumulate.
+B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const void* x, long long M, int C,
+                                    const float* mean, const float* rstd, const float* gamma, int relu, void* dx,
+                                    void* dz_out, float* dgamma, float* dbeta, float* scratch, void* stream) {
+  if (!bn_shape_ok(M, C) || (relu && out == nullptr)) return B200MM_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * C, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int grid;
+  const int rows = bn_rows_per_cta(M, C, &grid);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dout),
+                                            static_cast<const __nv_bfloat16*>(out),
+                                            static_cast<const __nv_bfloat16*>(x), M, C, rows, mean, rstd, relu,
+                                            scratch, scratch + C);
+  B200MM_CHECK_LAUNCH();
+  bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(
+      static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out),
+      static_cast<const __nv_bfloat16*>(x), M, C, rows, mean, rstd, gamma, relu, scratch, scratch + C,
+      static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dz_out), dgamma, dbeta);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+B200MM_API int b200mm_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, void* argmax,
+                                       void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) return B200MM_ERR_BAD_ARG;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool_fwd_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * (C >> 3), 256), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), N, H, W, C, Ho, Wo,
+                                                            static_cast<__nv_bfloat16*>(out),
+                                                            static_cast<uint8_t*>(argmax));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_maxpool3x3s2_bwd(const void* dout, const void* argmax, int N, int H, int W, int C, void* dx,
+                                       void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) return B200MM_ERR_BAD_ARG;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool_bwd_kernel<<<grid_for(static_cast<long long>(N) * H * W * (C >> 3), 256), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dout),
+                                                            static_cast<const uint8_t*>(argmax), N, H, W, C, Ho, Wo,
+                                                            static_cast<__nv_bfloat16*>(dx));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_avgpool_fwd(const void* x, int N, int HW, int C, void* out, void* stream) {
+  if (N <= 0 || HW <= 0 || C <= 0 || (C & 7)) return B200MM_ERR_BAD_ARG;
+  avgpool_fwd_kernel<<<grid_for(static_cast<long long>(N) * (C >> 3), 256), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), N, HW, C,
+                                                            static_cast<__nv_bfloat16*>(out));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_avgpool_bwd(const void* dout, int N, int HW, int C, void* dx, void* stream) {
+  if (N <= 0 || HW <= 0 || C <= 0 || (C & 7)) return B200MM_ERR_BAD_ARG;
+  avgpool_bwd_kernel<<<grid_for(static_cast<long long>(N) * HW * (C >> 3), 256), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dout), N, HW, C,
+                                                            static_cast<__nv_bfloat16*>(dx));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+B200MM_API int b200mm_im2col_nhwc(const void* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                                  void* cols, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || KH <= 0 || KW <= 0 || stride <= 0 || pad < 0)
+    return B200MM_ERR_BAD_ARG;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  im2col_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * KH * KW * (C >> 3), 256), 256, 0,
+                  static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), N, H, W, C, KH, KW, stride,
+                                                       pad, Ho, Wo, static_cast<__nv_bfloat16*>(cols));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_col2im_nhwc(const void* dcols, const void* addend, int N, int H, int W, int C, int KH, int KW,
+                                  int stride, int pad, void* dx, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || KH <= 0 || KW <= 0 || stride <= 0 || pad < 0)
+    return B200MM_ERR_BAD_ARG;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  col2im_kernel<<<grid_for(static_cast<long long>(N) * H * W * (C >> 3), 256), 256, 0,
+                  static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dcols),
+                                                       static_cast<const __nv_bfloat16*>(addend), N, H, W, C, KH, KW,
+                                                       stride, pad, Ho, Wo, static_cast<__nv_bfloat16*>(dx));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_im2col_nchw_f32(const float* img, int N, int Cin, int H, int W, int KH, int KW, int stride,
+                                      int pad, int Kp, void* cols, void* stream) {
+  if (N <= 0 || Cin <= 0 || H <= 0 || W <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || pad < 0 || (Kp & 7) ||
+      Kp < KH * KW * Cin)
+    return B200MM_ERR_BAD_ARG;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  im2col_nchw_f32_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * (Kp >> 3), 256), 256, 0,
+                           static_cast<cudaStream_t>(stream)>>>(img, N, Cin, H, W, KH, KW, stride, pad, Ho, Wo, Kp,
+                                                                static_cast<__nv_bfloat16*>(cols));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_subsample_nhwc(const void* x, int N, int H, int W, int C, int stride, void* out, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || stride <= 0) return B200MM_ERR_BAD_ARG;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  subsample_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * (C >> 3), 256), 256, 0,
+                     static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), N, H, W, C, stride, Ho,
+                                                          Wo, static_cast<__nv_bfloat16*>(out));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_upsample_add_nhwc(const void* dsub, const void* addend, int N, int H, int W, int C, int stride,
+                                        void* dx, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || stride <= 0) return B200MM_ERR_BAD_ARG;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  upsample_add_kernel<<<grid_for(static_cast<long long>(N) * H * W * (C >> 3), 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dsub),
+                                                             static_cast<const __nv_bfloat16*>(addend), N, H, W, C,
+                                                             stride, Ho, Wo, static_cast<__nv_bfloat16*>(dx));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}

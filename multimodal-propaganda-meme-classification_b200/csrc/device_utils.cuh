@@ -1,0 +1,83 @@
+// Device-side helpers shared by the non-GEMM kernels: warp/block reductions, Philox counter RNG,
+// 16-byte vector <-> bf16x8 conversion.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace b200 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10: stateless counter RNG so that forward and backward (and every data-parallel replica,
+// given its own seed) regenerate identical dropout masks from (seed, element index).
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = 0x1BD11BDAu, c3 = 0x5851F42Du;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask for 4 consecutive elements: bit i set = element kept. threshold = p_drop * 2^32.
+__device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t group_idx, uint32_t threshold) {
+  const uint4 r = philox4x32(seed, group_idx);
+  return (r.x >= threshold ? 1u : 0u) | (r.y >= threshold ? 2u : 0u) | (r.z >= threshold ? 4u : 0u) |
+         (r.w >= threshold ? 8u : 0u);
+}
+__host__ __device__ inline uint32_t dropout_threshold(float p) {
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(t);
+}
+
+__device__ __forceinline__ float2 unpack_bf16x2_dev(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_dev(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct alignas(16) bf16x8 {
+  uint32_t u[4];
+};
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&x)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+    const float2 f = __bfloat1622float2(v);
+    x[2 * i] = f.x;
+    x[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&x)[8]) {
+  uint4 o;
+  uint32_t* u = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    u[i] = *reinterpret_cast<uint32_t*>(&v);
+  }
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+}  // namespace b200

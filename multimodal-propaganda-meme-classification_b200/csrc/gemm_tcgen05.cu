@@ -17,6 +17,7 @@
 // cuDNN convolutions behind torchvision/models/resnet.py, as driven by
 // example_scripts/Multimodal_example_task2C.txt:172-197.
 #include "common.cuh"
+#include "device_utils.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -51,6 +52,11 @@ struct GemmParams {
   long long ldc;
   __nv_bfloat16* out2;
   long long ld2;
+  // EPI_STORE only: inverted dropout on (acc + bias) before the residual add, mask keyed by (seed, row * N + col)
+  float p_drop;
+  uint32_t drop_threshold;
+  float inv_keep;
+  unsigned long long seed;
 };
 
 template <int BN>
@@ -222,6 +228,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
             }
             if (p.epi == EPI_STORE || p.epi == EPI_RELU) {
+              if (p.p_drop > 0.f) {
+                const uint64_t gi = static_cast<uint64_t>(row * p.N + col) >> 2;
+                const uint32_t k0 = dropout_keep4(p.seed, gi, p.drop_threshold);
+                const uint32_t k1 = dropout_keep4(p.seed, gi + 1, p.drop_threshold);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  x[i] = (k0 >> i) & 1 ? x[i] * p.inv_keep : 0.f;
+                  x[4 + i] = (k1 >> i) & 1 ? x[4 + i] * p.inv_keep : 0.f;
+                }
+              }
               if (p.residual != nullptr) {
                 const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col));
                 const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
@@ -314,12 +330,13 @@ using namespace b200;
 //   a_mn == 0: A is stored [M, K] (row stride lda elements);  a_mn == 1: A is stored [K, M].
 //   b_mn == 0: B is stored [N, K] (row stride ldb elements);  b_mn == 1: B is stored [K, N].
 //   epi: EpiMode above.  splits > 1 requires epi == EPI_F32_ATOMIC (out must be pre-zeroed or hold the
-//   value to accumulate onto).  block_n in {0 (auto), 64, 128, 256}.
+//   value to accumulate onto).  block_n in {0 (auto), 64, 128, 256}.  p_drop/seed: EPI_STORE dropout (see GemmParams).
 // Contract: pointers 16-byte aligned, lda/ldb/ldc/... multiples of 8 elements, N % 8 == 0.
 B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb,
                                 int M, int N, int K, int epi, const float* bias, const void* residual,
                                 long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
-                                void* out2, long long ld2, int splits, int block_n, void* stream) {
+                                void* out2, long long ld2, int splits, int block_n, float p_drop,
+                                unsigned long long seed, void* stream) {
   const DeviceInfo& dev = device_info();
   if (!dev.ok) return B200MM_ERR_NOT_SM100;
   if (dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
@@ -354,6 +371,11 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
   p.ldc = ldc;
   p.out2 = static_cast<__nv_bfloat16*>(out2);
   p.ld2 = ld2;
+  if (p_drop < 0.f || p_drop >= 1.f) return B200MM_ERR_BAD_ARG;
+  p.p_drop = (epi == EPI_STORE) ? p_drop : 0.f;
+  p.drop_threshold = dropout_threshold(p_drop);
+  p.inv_keep = 1.f / (1.f - p_drop);
+  p.seed = seed;
 
   CUtensorMap ta, tb;
   int rc;

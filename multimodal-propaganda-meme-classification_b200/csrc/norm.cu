@@ -1,0 +1,343 @@
+// LayerNorm / embedding kernels of the text tower (HBM-bound; one warp per token row, 16-byte accesses,
+// warp-shuffle reductions, fp32 statistics).
+//
+// Replaces:
+//   transformers/models/distilbert/modeling_distilbert.py:96-122  Embeddings (word + position -> LN -> dropout)
+//   ...:257, :261  sa_layer_norm / output_layer_norm  (the residual add is fused into the producing GEMM epilogue)
+// and their autograd backward passes.
+#include "common.cuh"
+#include "device_utils.cuh"
+
+namespace b200 {
+
+constexpr int LN_WARPS = 8;
+constexpr int LN_MAX_CHUNKS = 8;  // per lane: 8 chunks x 8 elements x 32 lanes -> D <= 2048
+
+struct DropSpec {
+  float p;
+  uint32_t threshold;
+  float inv_keep;
+  unsigned long long seed;
+};
+static DropSpec make_drop(float p, unsigned long long seed) {
+  DropSpec d;
+  d.p = p;
+  d.threshold = dropout_threshold(p);
+  d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  d.seed = seed;
+  return d;
+}
+// keep-scale for the 8 consecutive elements starting at flat index `idx` (idx % 8 == 0)
+__device__ __forceinline__ void drop_scale8(const DropSpec& d, long long idx, float (&s)[8]) {
+  const uint32_t k0 = dropout_keep4(d.seed, static_cast<uint64_t>(idx >> 2), d.threshold);
+  const uint32_t k1 = dropout_keep4(d.seed, static_cast<uint64_t>(idx >> 2) + 1, d.threshold);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s[i] = (k0 >> i) & 1 ? d.inv_keep : 0.f;
+    s[4 + i] = (k1 >> i) & 1 ? d.inv_keep : 0.f;
+  }
+}
+
+// y = LN(x) * gamma + beta, optional dropout on y.  Stats saved for the backward.
+// EMBED: x is not read from memory but formed as word[ids[row]] + pos[row % S] (fp32 tables) and also
+// written out (bf16) as the saved LayerNorm input.
+template <bool EMBED>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ ids,
+                     const float* __restrict__ word, const float* __restrict__ pos, int S, int vocab,
+                     __nv_bfloat16* __restrict__ x_saved, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int M, int D, float eps, DropSpec drop) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp;
+  if (row >= M) return;
+  const int chunks = D >> 3;
+  float v[LN_MAX_CHUNKS][8];
+  float sum = 0.f;
+  const float* wrow = nullptr;
+  const float* prow = nullptr;
+  if constexpr (EMBED) {
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    wrow = word + id * D;
+    prow = pos + static_cast<long long>(row % S) * D;
+  }
+#pragma unroll
+  for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
+    const int c = lane + j * 32;
+    if (c < chunks) {
+      if constexpr (EMBED) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(wrow + c * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(wrow + c * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(prow + c * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(prow + c * 8 + 4));
+        v[j][0] = a0.x + b0.x; v[j][1] = a0.y + b0.y; v[j][2] = a0.z + b0.z; v[j][3] = a0.w + b0.w;
+        v[j][4] = a1.x + b1.x; v[j][5] = a1.y + b1.y; v[j][6] = a1.z + b1.z; v[j][7] = a1.w + b1.w;
+        store8(x_saved + row * D + c * 8, v[j]);
+        // statistics are taken on the bf16-rounded values: that is what the backward will see
+        load8(x_saved + row * D + c * 8, v[j]);
+      } else {
+        load8(x + row * D + c * 8, v[j]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[j][i];
+    }
+  }
+  const float mean = warp_sum(sum) / D;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
+    const int c = lane + j * 32;
+    if (c < chunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[j][i] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / D + eps);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
+    const int c = lane + j * 32;
+    if (c < chunks) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c * 8 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+      if (drop.p > 0.f) {
+        float s[8];
+        drop_scale8(drop, row * D + c * 8, s);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= s[i];
+      }
+      store8(y + row * D + c * 8, o);
+    }
+  }
+}
+
+// dx = LN backward; optional dropout mask on the incoming dy (in_drop: the mask that was applied to the LN output
+// in the forward) and optional second output dx2 = dropout-masked dx (out_drop: the mask that was applied to the
+// GEMM branch feeding this LN's input).  dgamma/dbeta are accumulated with fp32 atomics (pre-zeroed by caller
+// or holding the gradient to accumulate onto).
+template <int NC>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                     __nv_bfloat16* __restrict__ dx2, float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                     int D, int rows_per_cta, DropSpec in_drop, DropSpec out_drop) {
+  extern __shared__ float red[];  // [LN_WARPS][2][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = D >> 3;
+  float ag[NC][8], ab[NC][8];
+#pragma unroll
+  for (int j = 0; j < NC; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ag[j][i] = ab[j][i] = 0.f;
+
+  const long long row_begin = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long row_end = min(row_begin + rows_per_cta, static_cast<long long>(M));
+  for (long long row = row_begin + warp; row < row_end; row += LN_WARPS) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float g_dy[NC][8], xh[NC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = lane + j * 32;
+      if (c < chunks) {
+        float d[8], xv[8];
+        load8(dy + row * D + c * 8, d);
+        load8(x + row * D + c * 8, xv);
+        if (in_drop.p > 0.f) {
+          float s[8];
+          drop_scale8(in_drop, row * D + c * 8, s);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] *= s[i];
+        }
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = (xv[i] - mean) * rstd;
+          xh[j][i] = h;
+          ag[j][i] = fmaf(d[i], h, ag[j][i]);
+          ab[j][i] += d[i];
+          const float dg = d[i] * g[i];
+          g_dy[j][i] = dg;
+          s1 += dg;
+          s2 = fmaf(dg, h, s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = lane + j * 32;
+      if (c < chunks) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (g_dy[j][i] - s1 - xh[j][i] * s2);
+        store8(dx + row * D + c * 8, o);
+        if (dx2 != nullptr) {
+          float s[8];
+          drop_scale8(out_drop, row * D + c * 8, s);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] *= s[i];
+          store8(dx2 + row * D + c * 8, o);
+        }
+      }
+    }
+  }
+  // cross-warp reduction of the column sums, then one atomic per column per CTA
+  float* rg = red + warp * 2 * D;
+  float* rb = rg + D;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    const int c = lane + j * 32;
+    if (c < chunks) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rg[c * 8 + i] = ag[j][i];
+        rb[c * 8 + i] = ab[j][i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < D; col += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) {
+      sg += red[w * 2 * D + col];
+      sb += red[w * 2 * D + D + col];
+    }
+    atomicAdd(dgamma + col, sg);
+    atomicAdd(dbeta + col, sb);
+  }
+}
+
+// Embedding backward: scatter-add d(word+pos sum) rows into the fp32 gradient tables.
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const long long* __restrict__ ids, int S, int vocab,
+                     float* __restrict__ dword, float* __restrict__ dpos, int M, int D) {
+  const int chunks = D >> 2;
+  const long long total = static_cast<long long>(M) * chunks;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / chunks;
+    const int c = static_cast<int>(i - row * chunks) * 4;
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const uint2 r = *reinterpret_cast<const uint2*>(dx + row * D + c);
+    const float2 a = unpack_bf16x2_dev(r.x), b = unpack_bf16x2_dev(r.y);
+    float* w = dword + id * D + c;
+    float* q = dpos + static_cast<long long>(row % S) * D + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(w), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+  }
+}
+
+// attention_mask (int64, 1 = real token) -> additive key bias (0 / -inf), as HF builds it
+// (modeling_distilbert.py:415-419 create_bidirectional_mask)
+__global__ void mask_to_bias_kernel(const long long* __restrict__ mask, float* __restrict__ bias, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) bias[i] = mask[i] != 0 ? 0.f : -INFINITY;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static bool ln_shape_ok(int M, int D) { return M > 0 && D > 0 && (D & 7) == 0 && D <= LN_MAX_CHUNKS * 256; }
+
+// y[M,D] = dropout(LayerNorm(x[M,D])) ; saves mean/rstd (fp32 [M]).
+B200MM_API int b200mm_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                    float* rstd, int M, int D, float eps, float p_drop, unsigned long long seed,
+                                    void* stream) {
+  if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
+  layernorm_fwd_kernel<false><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, 1, 1, nullptr, gamma, beta,
+      static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// Embeddings: x_saved = bf16(word[ids] + pos[t]); y = dropout(LayerNorm(x_saved)).  ids int64 [M = B*S].
+B200MM_API int b200mm_embed_layernorm_fwd(const long long* ids, const float* word, const float* pos, int S, int vocab,
+                                          const float* gamma, const float* beta, void* x_saved, void* y, float* mean,
+                                          float* rstd, int M, int D, float eps, float p_drop, unsigned long long seed,
+                                          void* stream) {
+  if (!ln_shape_ok(M, D) || S <= 0 || vocab <= 0) return B200MM_ERR_BAD_ARG;
+  layernorm_fwd_kernel<true><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      nullptr, ids, word, pos, S, vocab, static_cast<__nv_bfloat16*>(x_saved), gamma, beta,
+      static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// LayerNorm backward.  dx2 (nullable) receives dx with the (p_out, seed_out) dropout mask applied.
+B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                                    const float* gamma, void* dx, void* dx2, float* dgamma, float* dbeta, int M, int D,
+                                    float p_in, unsigned long long seed_in, float p_out, unsigned long long seed_out,
+                                    void* stream) {
+  if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
+  const DeviceInfo& dev = device_info();
+  const int target_ctas = dev.num_sms > 0 ? dev.num_sms * 4 : 592;
+  int rows_per_cta = ceil_div(M, target_ctas);
+  rows_per_cta = ceil_div(rows_per_cta, LN_WARPS) * LN_WARPS;
+  const int grid = ceil_div(M, rows_per_cta);
+  const size_t smem = static_cast<size_t>(LN_WARPS) * 2 * D * sizeof(float);
+  const int nc = ceil_div(D, 256);
+#define LAUNCH_LN_BWD(NC)                                                                                          \
+  do {                                                                                                             \
+    static bool configured = false;                                                                                \
+    if (!configured) {                                                                                             \
+      cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           LN_WARPS * 2 * NC * 256 * 4);                                           \
+      if (e != cudaSuccess) return static_cast<int>(e);                                                            \
+      configured = true;                                                                                           \
+    }                                                                                                              \
+    layernorm_bwd_kernel<NC><<<grid, LN_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                    \
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd, gamma,            \
+        static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dx2), dgamma, dbeta, M, D, rows_per_cta,      \
+        make_drop(p_in, seed_in), make_drop(dx2 ? p_out : 0.f, seed_out));                                         \
+  } while (0)
+  if (nc <= 1) LAUNCH_LN_BWD(1);
+  else if (nc == 2) LAUNCH_LN_BWD(2);
+  else if (nc == 3) LAUNCH_LN_BWD(3);
+  else if (nc == 4) LAUNCH_LN_BWD(4);
+  else LAUNCH_LN_BWD(8);
+#undef LAUNCH_LN_BWD
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// dword[ids[m]] += dx[m], dpos[m % S] += dx[m]   (fp32 tables, accumulate)
+B200MM_API int b200mm_embedding_bwd(const void* dx, const long long* ids, int S, int vocab, float* dword, float* dpos,
+                                    int M, int D, void* stream) {
+  if (M <= 0 || D <= 0 || (D & 3) || S <= 0) return B200MM_ERR_BAD_ARG;
+  const long long total = static_cast<long long>(M) * (D >> 2);
+  const int grid = static_cast<int>(total / 256 > 148 * 16 ? 148 * 16 : ceil_div(total, 256LL));
+  embedding_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dx), ids, S, vocab, dword, dpos, M, D);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+B200MM_API int b200mm_mask_to_bias(const long long* mask, float* bias, long long n, void* stream) {
+  if (n <= 0) return B200MM_ERR_BAD_ARG;
+  mask_to_bias_kernel<<<static_cast<int>(ceil_div(n, 256LL)), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, bias, n);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}

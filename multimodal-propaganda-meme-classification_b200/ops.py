@@ -1,0 +1,329 @@
+"""Torch-tensor front end of the C-ABI kernels (device pointers + sizes go down, nothing else).
+
+Every function launches on torch's current CUDA stream and allocates its outputs with ``torch.empty`` (the
+caching allocator), so a whole step is CUDA-graph capturable.  There is no CPU path: tensors must live on
+a CUDA device and libb200mm.so must load, otherwise these raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+EPI_STORE, EPI_GELU, EPI_DGELU, EPI_F32, EPI_F32_ATOMIC, EPI_RELU = range(6)
+LOSS_CE, LOSS_FOCAL, LOSS_EXTERNAL = 0, 1, 2
+
+_num_sms = None
+
+
+def num_sms() -> int:
+    global _num_sms
+    if _num_sms is None:
+        _num_sms = _lib.load().b200mm_num_sms() or 148
+    return _num_sms
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.B200MMError(f"{name} must be a CUDA tensor (b200mm has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        raise ValueError(f"{name}: innermost dimension must be contiguous")
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residual=None, aux=None, out2=None,
+             splits=1, block_n=0, p_drop=0.0, seed=0):
+    """D[M,N] = A x B (+epilogue). A: [M,K] (a_mn False) or [K,M] (a_mn True); B: [N,K] or [K,N]."""
+    _lib.call("b200mm_gemm_bf16", _p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, epi,
+              _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
+              _p(aux), aux.stride(0) if aux is not None else 0, _p(out), out.stride(0),
+              _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed), _s())
+    return out
+
+
+def linear_fwd(x, w, bias=None, *, residual=None, out=None, relu=False, p_drop=0.0, seed=0):
+    """y = x @ w.T + bias (+dropout) (+residual) (relu).  x [M,K] bf16, w [N,K] bf16, bias fp32 [N]."""
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=bf16)
+    return gemm_raw(x, False, w, False, M, N, K, out, epi=EPI_RELU if relu else EPI_STORE, bias=bias,
+                    residual=residual, p_drop=p_drop, seed=seed)
+
+
+def linear_gelu_fwd(x, w, bias):
+    """z = x @ w.T + bias ; a = gelu(z) (exact erf).  Returns (z, a), both bf16 [M,N]."""
+    M, K = x.shape
+    N = w.shape[0]
+    z = torch.empty(M, N, device=x.device, dtype=bf16)
+    a = torch.empty(M, N, device=x.device, dtype=bf16)
+    gemm_raw(x, False, w, False, M, N, K, z, epi=EPI_GELU, bias=bias, out2=a)
+    return z, a
+
+
+def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None):
+    """dx = dy @ w (+residual), or dx = (dy @ w) * gelu'(gelu_z).  dy [M,N], w [N,K] -> dx [M,K]."""
+    M, N = dy.shape
+    K = w.shape[1]
+    if out is None:
+        out = torch.empty(M, K, device=dy.device, dtype=bf16)
+    if gelu_z is not None:
+        return gemm_raw(dy, False, w, True, M, K, N, out, epi=EPI_DGELU, aux=gelu_z)
+    return gemm_raw(dy, False, w, True, M, K, N, out, epi=EPI_STORE, residual=residual)
+
+
+def _wgrad_splits(n_out, k_out, m_red):
+    tiles = ((n_out + 127) // 128) * ((k_out + 255) // 256)
+    k_iters = (m_red + 63) // 64
+    want = max(1, (2 * num_sms() + tiles - 1) // tiles)
+    return max(1, min(want, k_iters // 4 if k_iters >= 8 else 1))
+
+
+def linear_wgrad(dy, x, dw):
+    """dw[N,K] (fp32) += dy[M,N].T @ x[M,K]   (split-K over M, fp32 red.add accumulation)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    return gemm_raw(dy, True, x, True, N, K, M, dw, epi=EPI_F32_ATOMIC, splits=_wgrad_splits(N, K, M))
+
+
+def colsum(x, out):
+    """out[N] (fp32) += x[M,N].sum(0)"""
+    M, N = x.shape
+    _lib.call("b200mm_colsum_bf16", _p(x), x.stride(0), M, N, _p(out), _s())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def mask_to_bias(mask):
+    """int64 attention_mask (1 = token) -> fp32 additive key bias (0 / -inf)."""
+    _chk(mask, torch.int64, "attention_mask")
+    mask = mask.contiguous()
+    bias = torch.empty(mask.shape, device=mask.device, dtype=f32)
+    _lib.call("b200mm_mask_to_bias", _p(mask), _p(bias), mask.numel(), _s())
+    return bias
+
+
+def attention_fwd(qkv, key_bias, B, H, S, *, p_drop=0.0, seed=0, need_lse=True):
+    out = torch.empty(B * S, H * 64, device=qkv.device, dtype=bf16)
+    lse = torch.empty(B, H, S, device=qkv.device, dtype=f32) if need_lse else None
+    _lib.call("b200mm_attention_fwd", _p(qkv), _p(key_bias), _p(out), _p(lse), B, H, S, float(p_drop), int(seed), _s())
+    return out, lse
+
+
+def attention_bwd(qkv, key_bias, out, dout, lse, B, H, S, *, p_drop=0.0, seed=0):
+    dqkv = torch.empty_like(qkv)
+    _lib.call("b200mm_attention_bwd", _p(qkv), _p(key_bias), _p(out), _p(dout), _p(lse), _p(dqkv), B, H, S,
+              float(p_drop), int(seed), _s())
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------------- norms / embeddings
+def layernorm_fwd(x, gamma, beta, eps, *, p_drop=0.0, seed=0):
+    M, D = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=f32)
+    rstd = torch.empty(M, device=x.device, dtype=f32)
+    _lib.call("b200mm_layernorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, D, float(eps),
+              float(p_drop), int(seed), _s())
+    return y, mean, rstd
+
+
+def embed_layernorm_fwd(ids, word, pos, gamma, beta, eps, *, p_drop=0.0, seed=0):
+    B, S = ids.shape
+    V, D = word.shape
+    M = B * S
+    x_saved = torch.empty(M, D, device=ids.device, dtype=bf16)
+    y = torch.empty(M, D, device=ids.device, dtype=bf16)
+    mean = torch.empty(M, device=ids.device, dtype=f32)
+    rstd = torch.empty(M, device=ids.device, dtype=f32)
+    _lib.call("b200mm_embed_layernorm_fwd", _p(ids), _p(word), _p(pos), S, V, _p(gamma), _p(beta), _p(x_saved), _p(y),
+              _p(mean), _p(rstd), M, D, float(eps), float(p_drop), int(seed), _s())
+    return y, x_saved, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
+    """Returns (dx, dx_masked) where dx_masked is None unless p_out > 0."""
+    M, D = x.shape
+    dx = torch.empty_like(x)
+    dx2 = torch.empty_like(x) if p_out > 0 else None
+    _lib.call("b200mm_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dx2), _p(dgamma),
+              _p(dbeta), M, D, float(p_in), int(seed_in), float(p_out), int(seed_out), _s())
+    return dx, dx2
+
+
+def embedding_bwd(dx, ids, dword, dpos):
+    B, S = ids.shape
+    V, D = dword.shape
+    _lib.call("b200mm_embedding_bwd", _p(dx), _p(ids), S, V, _p(dword), _p(dpos), B * S, D, _s())
+
+
+def gather_rows(x, rows, stride_rows, offset_rows, *, p_drop=0.0, seed=0):
+    D = x.shape[1]
+    out = torch.empty(rows, D, device=x.device, dtype=bf16)
+    _lib.call("b200mm_gather_rows", _p(x), _p(out), rows, D, stride_rows, offset_rows, float(p_drop), int(seed), _s())
+    return out
+
+
+def scatter_rows(dpooled, M, stride_rows, offset_rows, *, p_drop=0.0, seed=0):
+    D = dpooled.shape[1]
+    dx = torch.empty(M, D, device=dpooled.device, dtype=bf16)
+    _lib.call("b200mm_scatter_rows", _p(dpooled), _p(dx), M, D, stride_rows, offset_rows, float(p_drop), int(seed),
+              _s())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------- head / loss / optim
+def head_loss(feat, W, bias, labels, *, loss_kind=LOSS_CE, alpha=0.25, gamma=2.0, train=True, dW=None, dbias=None,
+              dlogits=None):
+    """Output layer + loss (+ its backward when train).  Returns (logits fp32 [B,C], loss_sum fp32 [1],
+    correct int32 [1], dfeat bf16 [B,F] | None)."""
+    B, F = feat.shape
+    C = W.shape[0]
+    dev = feat.device
+    logits = torch.empty(B, C, device=dev, dtype=f32)
+    loss = torch.zeros(1, device=dev, dtype=f32)
+    correct = torch.zeros(1, device=dev, dtype=torch.int32)
+    dfeat = torch.empty(B, F, device=dev, dtype=bf16) if train else None
+    _lib.call("b200mm_head_loss", _p(feat), _p(W), _p(bias), _p(labels), B, F, C, loss_kind, float(alpha),
+              float(gamma), int(train), _p(dlogits), _p(logits), _p(loss), _p(correct), _p(dfeat), _p(dW), _p(dbias),
+              _s())
+    return logits, loss, correct, dfeat
+
+
+def sumsq(g, out):
+    _lib.call("b200mm_sumsq_f32", _p(g), g.numel(), _p(out), _s())
+    return out
+
+
+def adam_step(p, g, m, v, shadow, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1, gradsq=None,
+              max_norm=0.0, grad_scale=1.0):
+    _lib.call("b200mm_adam_step", _p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), float(lr), float(beta1),
+              float(beta2), float(eps), float(weight_decay), int(step), _p(gradsq), float(max_norm),
+              float(grad_scale), _s())
+
+
+def cast_to_bf16(x, y):
+    _lib.call("b200mm_cast_f32_to_bf16", _p(x), _p(y), x.numel(), _s())
+    return y
+
+
+# ----------------------------------------------------------------------------------------------- image tower pieces
+class BNScratch:
+    """fp32 [2*C] workspace shared by every BatchNorm launch of one device."""
+    _buf = {}
+
+    @classmethod
+    def get(cls, device, C):
+        key = (device.index, torch.cuda.current_stream().cuda_stream)
+        b = cls._buf.get(key)
+        if b is None or b.numel() < 2 * C:
+            b = torch.empty(max(2 * C, 8192), device=device, dtype=f32)
+            cls._buf[key] = b
+        return b
+
+
+def batchnorm_fwd(x, gamma, beta, running_mean, running_var, *, residual=None, relu=True, eps=1e-5, momentum=0.1):
+    M, C = x.shape
+    out = torch.empty_like(x)
+    mean = torch.empty(C, device=x.device, dtype=f32)
+    rstd = torch.empty(C, device=x.device, dtype=f32)
+    _lib.call("b200mm_batchnorm_fwd", _p(x), _p(residual), M, C, _p(gamma), _p(beta), float(eps), float(momentum),
+              int(relu), _p(out), _p(mean), _p(rstd), _p(running_mean), _p(running_var),
+              _p(BNScratch.get(x.device, C)), _s())
+    return out, mean, rstd
+
+
+def batchnorm_eval(x, gamma, beta, running_mean, running_var, *, residual=None, relu=True, eps=1e-5):
+    M, C = x.shape
+    out = torch.empty_like(x)
+    _lib.call("b200mm_batchnorm_eval", _p(x), _p(residual), M, C, _p(gamma), _p(beta), _p(running_mean),
+              _p(running_var), float(eps), int(relu), _p(out), _s())
+    return out
+
+
+def batchnorm_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=True, need_dz=False):
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    dz = torch.empty_like(x) if need_dz else None
+    _lib.call("b200mm_batchnorm_bwd", _p(dout), _p(out), _p(x), M, C, _p(mean), _p(rstd), _p(gamma), int(relu),
+              _p(dx), _p(dz), _p(dgamma), _p(dbeta), _p(BNScratch.get(x.device, C)), _s())
+    return dx, dz
+
+
+def maxpool_fwd(x, N, H, W, C):
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(N * Ho * Wo, C, device=x.device, dtype=bf16)
+    arg = torch.empty(N * Ho * Wo, C, device=x.device, dtype=torch.uint8)
+    _lib.call("b200mm_maxpool3x3s2_fwd", _p(x), N, H, W, C, _p(out), _p(arg), _s())
+    return out, arg, Ho, Wo
+
+
+def maxpool_bwd(dout, arg, N, H, W, C):
+    dx = torch.empty(N * H * W, C, device=dout.device, dtype=bf16)
+    _lib.call("b200mm_maxpool3x3s2_bwd", _p(dout), _p(arg), N, H, W, C, _p(dx), _s())
+    return dx
+
+
+def avgpool_fwd(x, N, HW, C):
+    out = torch.empty(N, C, device=x.device, dtype=bf16)
+    _lib.call("b200mm_avgpool_fwd", _p(x), N, HW, C, _p(out), _s())
+    return out
+
+
+def avgpool_bwd(dout, N, HW, C):
+    dx = torch.empty(N * HW, C, device=dout.device, dtype=bf16)
+    _lib.call("b200mm_avgpool_bwd", _p(dout), N, HW, C, _p(dx), _s())
+    return dx
+
+
+def conv_out_hw(H, W, k, stride, pad):
+    return (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+
+
+def im2col(x, N, H, W, C, k, stride, pad):
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    cols = torch.empty(N * Ho * Wo, k * k * C, device=x.device, dtype=bf16)
+    _lib.call("b200mm_im2col_nhwc", _p(x), N, H, W, C, k, k, stride, pad, _p(cols), _s())
+    return cols, Ho, Wo
+
+
+def col2im(dcols, N, H, W, C, k, stride, pad, addend=None):
+    dx = torch.empty(N * H * W, C, device=dcols.device, dtype=bf16)
+    _lib.call("b200mm_col2im_nhwc", _p(dcols), _p(addend), N, H, W, C, k, k, stride, pad, _p(dx), _s())
+    return dx
+
+
+def im2col_nchw_f32(img, k, stride, pad, Kp):
+    _chk(img, f32, "pixel_values")
+    img = img.contiguous()
+    N, Cin, H, W = img.shape
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    cols = torch.empty(N * Ho * Wo, Kp, device=img.device, dtype=bf16)
+    _lib.call("b200mm_im2col_nchw_f32", _p(img), N, Cin, H, W, k, k, stride, pad, Kp, _p(cols), _s())
+    return cols, Ho, Wo
+
+
+def subsample(x, N, H, W, C, stride):
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty(N * Ho * Wo, C, device=x.device, dtype=bf16)
+    _lib.call("b200mm_subsample_nhwc", _p(x), N, H, W, C, stride, _p(out), _s())
+    return out, Ho, Wo
+
+
+def upsample_add(dsub, addend, N, H, W, C, stride):
+    dx = torch.empty(N * H * W, C, device=dsub.device, dtype=bf16)
+    _lib.call("b200mm_upsample_add_nhwc", _p(dsub), _p(addend), N, H, W, C, stride, _p(dx), _s())
+    return dx

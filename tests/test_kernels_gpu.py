@@ -1,0 +1,398 @@
+"""Per-kernel parity on the B200: every C-ABI kernel vs a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+bf16 = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from b200mm import ops as o
+    return o
+
+
+# ------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 768, 768), (1000, 512, 200), (130, 64, 152), (256, 1000, 2048)])
+def test_gemm_forward_epilogues(ops, cuda_device, M, N, K):
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device=cuda_device).to(bf16)
+    w = torch.randn(N, K, device=cuda_device).to(bf16)
+    b = torch.randn(N, device=cuda_device)
+    res = torch.randn(M, N, device=cuda_device).to(bf16)
+    ref = x.float() @ w.float().t() + b
+    assert rel(ops.linear_fwd(x, w, b), ref) < 1e-2
+    assert rel(ops.linear_fwd(x, w, b, residual=res), ref + res.float()) < 1e-2
+    assert rel(ops.linear_fwd(x, w, b, relu=True), torch.relu(ref)) < 1e-2
+    xs = (x.float() * 0.05).to(bf16)
+    refs = xs.float() @ w.float().t() + b
+    z, a = ops.linear_gelu_fwd(xs, w, b)
+    assert rel(z, refs) < 1e-2 and rel(a, F.gelu(refs)) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (4096, 768, 3072), (1000, 512, 200)])
+def test_gemm_dgrad_wgrad(ops, cuda_device, M, N, K):
+    torch.manual_seed(1)
+    x = torch.randn(M, K, device=cuda_device).to(bf16)
+    w = torch.randn(N, K, device=cuda_device).to(bf16)
+    dy = torch.randn(M, N, device=cuda_device).to(bf16)
+    res = torch.randn(M, K, device=cuda_device).to(bf16)
+    assert rel(ops.linear_dgrad(dy, w), dy.float() @ w.float()) < 1e-2
+    assert rel(ops.linear_dgrad(dy, w, residual=res), dy.float() @ w.float() + res.float()) < 1e-2
+    z = torch.randn(M, K, device=cuda_device).to(bf16)
+    zf = z.float().requires_grad_(True)
+    F.gelu(zf).sum().backward()
+    assert rel(ops.linear_dgrad(dy, w, gelu_z=z), (dy.float() @ w.float()) * zf.grad) < 1e-2
+    dw = torch.ones(N, K, device=cuda_device)
+    ops.linear_wgrad(dy, x, dw)
+    assert rel(dw, dy.float().t() @ x.float() + 1.0) < 1e-3
+    db = torch.zeros(N, device=cuda_device)
+    ops.colsum(dy, db)
+    assert rel(db, dy.float().sum(0)) < 1e-3
+
+
+def test_gemm_dropout_epilogue(ops, cuda_device):
+    torch.manual_seed(2)
+    M, N, K = 512, 768, 256
+    x = torch.randn(M, K, device=cuda_device).to(bf16)
+    w = torch.randn(N, K, device=cuda_device).to(bf16)
+    ref = x.float() @ w.float().t()
+    y = ops.linear_fwd(x, w, None, p_drop=0.25, seed=77).float()
+    kept = y != 0
+    frac = kept.float().mean().item()
+    assert abs(frac - 0.75) < 0.01
+    assert rel(y[kept], (ref / 0.75)[kept]) < 1e-2
+    # the LayerNorm backward regenerates the same mask from (seed, row * N + col)
+    g = torch.ones(N, device=cuda_device)
+    xin = torch.randn(M, N, device=cuda_device).to(bf16)
+    _, mean, rstd = ops.layernorm_fwd(xin, g, torch.zeros_like(g), 1e-5)
+    dg, db = torch.zeros_like(g), torch.zeros_like(g)
+    dx, dxm = ops.layernorm_bwd(torch.randn(M, N, device=cuda_device).to(bf16), xin, mean, rstd, g, dg, db,
+                                p_out=0.25, seed_out=77)
+    assert torch.equal(dxm.float() != 0, kept | (dx.float() == 0) & (dxm.float() != 0)) or \
+        ((dxm.float() != 0) == (kept & (dx.float() != 0))).all()
+
+
+# ------------------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, key_bias, B, H, S):
+    D = H * 64
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0
+    if key_bias is not None:
+        s = s + key_bias.view(B, 1, 1, S)
+    p = torch.softmax(s, -1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * S, D)
+
+
+@pytest.mark.parametrize("B,H,S", [(2, 2, 128), (3, 12, 128), (2, 4, 64), (2, 3, 100)])
+def test_attention_fwd_bwd(ops, cuda_device, B, H, S):
+    torch.manual_seed(3)
+    D = H * 64
+    qkv = torch.randn(B * S, 3 * D, device=cuda_device).to(bf16)
+    lengths = torch.randint(4, S + 1, (B,), device=cuda_device)
+    lengths[0] = S
+    mask = (torch.arange(S, device=cuda_device)[None] < lengths[:, None]).long()
+    bias = ops.mask_to_bias(mask)
+    out, lse = ops.attention_fwd(qkv, bias, B, H, S)
+    qf = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qf, bias, B, H, S)
+    assert rel(out, ref) < 1e-2
+    dout = torch.randn(B * S, D, device=cuda_device).to(bf16)
+    ref.backward(dout.float())
+    dqkv = ops.attention_bwd(qkv, bias, out, dout, lse, B, H, S)
+    assert rel(dqkv, qf.grad) < 2e-2
+
+
+def test_attention_dropout_is_consistent(ops, cuda_device):
+    """With p > 0 the forward is an unbiased estimate of the p = 0 output and the backward uses the same mask:
+    checked through the directional derivative d<O, dO>/d eps along a random direction."""
+    torch.manual_seed(4)
+    B, H, S = 2, 2, 128
+    D = H * 64
+    qkv = (torch.randn(B * S, 3 * D, device=cuda_device) * 0.5).to(bf16)
+    o0, _ = ops.attention_fwd(qkv, None, B, H, S)
+    acc = torch.zeros_like(o0, dtype=torch.float32)
+    n = 64
+    for i in range(n):
+        o, _ = ops.attention_fwd(qkv, None, B, H, S, p_drop=0.1, seed=1000 + i)
+        acc += o.float()
+    assert rel(acc / n, o0) < 0.06
+    out, lse = ops.attention_fwd(qkv, None, B, H, S, p_drop=0.1, seed=5)
+    out2, _ = ops.attention_fwd(qkv, None, B, H, S, p_drop=0.1, seed=5)
+    assert torch.equal(out, out2)
+    dout = torch.randn(B * S, D, device=cuda_device).to(bf16)
+    dqkv = ops.attention_bwd(qkv, None, out, dout, lse, B, H, S, p_drop=0.1, seed=5).float()
+    direction = torch.randn_like(dqkv)
+    eps = 0.05
+    op, _ = ops.attention_fwd((qkv.float() + eps * direction).to(bf16), None, B, H, S, p_drop=0.1, seed=5)
+    om, _ = ops.attention_fwd((qkv.float() - eps * direction).to(bf16), None, B, H, S, p_drop=0.1, seed=5)
+    fd = ((op.float() - om.float()) * dout.float()).sum().item() / (2 * eps)
+    an = (dqkv * direction).sum().item()
+    assert abs(fd - an) / (abs(an) + 1e-6) < 0.1
+
+
+# ------------------------------------------------------------------------------------------------- LayerNorm / embeddings
+@pytest.mark.parametrize("M,D", [(64, 128), (1000, 768), (300, 1024), (96, 2048)])
+def test_layernorm_fwd_bwd(ops, cuda_device, M, D):
+    torch.manual_seed(5)
+    x = torch.randn(M, D, device=cuda_device).to(bf16)
+    g = torch.randn(D, device=cuda_device)
+    b = torch.randn(D, device=cuda_device)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12)
+    xf = x.float().requires_grad_(True)
+    gf = g.clone().requires_grad_(True)
+    bf = b.clone().requires_grad_(True)
+    ref = F.layer_norm(xf, (D,), gf, bf, 1e-12)
+    assert rel(y, ref) < 1e-2
+    dy = torch.randn(M, D, device=cuda_device).to(bf16)
+    ref.backward(dy.float())
+    dg = torch.zeros(D, device=cuda_device)
+    db = torch.zeros(D, device=cuda_device)
+    dx, dx2 = ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db)
+    assert dx2 is None
+    assert rel(dx, xf.grad) < 1e-2
+    assert rel(dg, gf.grad) < 1e-2 and rel(db, bf.grad) < 1e-2
+
+
+def test_embedding_fwd_bwd(ops, cuda_device):
+    torch.manual_seed(6)
+    B, S, V, D = 4, 32, 500, 128
+    ids = torch.randint(0, V, (B, S), device=cuda_device)
+    word = torch.randn(V, D, device=cuda_device)
+    pos = torch.randn(64, D, device=cuda_device)
+    g = torch.rand(D, device=cuda_device) + 0.5
+    b = torch.randn(D, device=cuda_device)
+    y, xs, mean, rstd = ops.embed_layernorm_fwd(ids, word, pos, g, b, 1e-12)
+    ref_x = word[ids] + pos[:S][None]
+    assert rel(xs, ref_x.view(B * S, D)) < 1e-2
+    assert rel(y, F.layer_norm(ref_x, (D,), g, b, 1e-12).view(B * S, D)) < 1e-2
+    dx = torch.randn(B * S, D, device=cuda_device).to(bf16)
+    dword = torch.zeros(V, D, device=cuda_device)
+    dpos = torch.zeros(64, D, device=cuda_device)
+    ops.embedding_bwd(dx, ids, dword, dpos)
+    ref_w = torch.zeros(V, D, device=cuda_device).index_add_(0, ids.view(-1), dx.float())
+    ref_p = torch.zeros(64, D, device=cuda_device)
+    ref_p[:S] = dx.float().view(B, S, D).sum(0)
+    assert rel(dword, ref_w) < 1e-5 and rel(dpos, ref_p) < 1e-5
+
+
+def test_gather_scatter_rows(ops, cuda_device):
+    torch.manual_seed(7)
+    B, S, D = 5, 16, 64
+    h = torch.randn(B * S, D, device=cuda_device).to(bf16)
+    last = ops.gather_rows(h, B, S, S - 1)
+    assert torch.equal(last, h.view(B, S, D)[:, -1])
+    cls = ops.gather_rows(h, B, S, 0)
+    assert torch.equal(cls, h.view(B, S, D)[:, 0])
+    d = torch.randn(B, D, device=cuda_device).to(bf16)
+    dx = ops.scatter_rows(d, B * S, S, S - 1).view(B, S, D)
+    assert torch.equal(dx[:, -1], d) and dx[:, :-1].abs().sum().item() == 0
+    dropped = ops.gather_rows(h, B, S, S - 1, p_drop=0.3, seed=9).float()
+    back = ops.scatter_rows(torch.ones(B, D, device=cuda_device).to(bf16), B * S, S, S - 1, p_drop=0.3, seed=9)
+    assert torch.equal(dropped != 0, (back.view(B, S, D)[:, -1].float() != 0) & (last.float() != 0))
+
+
+# ------------------------------------------------------------------------------------------------- BatchNorm / pools / conv lowering
+@pytest.mark.parametrize("M,C,relu,use_res", [(4096, 64, True, False), (1568, 256, True, True), (392, 2048, False, False)])
+def test_batchnorm_fwd_bwd(ops, cuda_device, M, C, relu, use_res):
+    torch.manual_seed(8)
+    x = (torch.randn(M, C, device=cuda_device) * 2 + 0.5).to(bf16)
+    res = torch.randn(M, C, device=cuda_device).to(bf16) if use_res else None
+    g = torch.rand(C, device=cuda_device) + 0.5
+    b = torch.randn(C, device=cuda_device)
+    rm = torch.zeros(C, device=cuda_device)
+    rv = torch.ones(C, device=cuda_device)
+    out, mean, rstd = ops.batchnorm_fwd(x, g, b, rm, rv, residual=res, relu=relu)
+    xf = x.float().requires_grad_(True)
+    gf = g.clone().requires_grad_(True)
+    bf = b.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+    ref = F.batch_norm(xf, rm2, rv2, gf, bf, True, 0.1, 1e-5)
+    resf = res.float().requires_grad_(True) if use_res else None
+    if use_res:
+        ref = ref + resf
+    if relu:
+        ref = torch.relu(ref)
+    assert rel(out, ref) < 1e-2
+    assert rel(rm, rm2) < 1e-3 and rel(rv, rv2) < 1e-3
+    dout = torch.randn(M, C, device=cuda_device).to(bf16)
+    ref.backward(dout.float())
+    dg, db = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+    dx, dz = ops.batchnorm_bwd(dout, out, x, mean, rstd, g, dg, db, relu=relu, need_dz=use_res)
+    assert rel(dx, xf.grad) < 2e-2
+    assert rel(dg, gf.grad) < 2e-2 and rel(db, bf.grad) < 2e-2
+    if use_res:
+        assert rel(dz, resf.grad) < 2e-2
+    ev = ops.batchnorm_eval(x, g, b, rm2, rv2, residual=res, relu=relu)
+    ref_ev = F.batch_norm(x.float(), rm2, rv2, g, b, False, 0.1, 1e-5)
+    if use_res:
+        ref_ev = ref_ev + res.float()
+    if relu:
+        ref_ev = torch.relu(ref_ev)
+    assert rel(ev, ref_ev) < 1e-2
+
+
+def _nhwc(x):  # NCHW fp32 -> [N*H*W, C] bf16
+    N, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(N * H * W, C).to(bf16)
+
+
+def _nchw(x, N, H, W):
+    return x.float().view(N, H, W, -1).permute(0, 3, 1, 2)
+
+
+def test_pools(ops, cuda_device):
+    torch.manual_seed(9)
+    N, C, H, W = 3, 64, 18, 18
+    x = torch.randn(N, C, H, W, device=cuda_device).to(bf16).float()
+    out, arg, Ho, Wo = ops.maxpool_fwd(_nhwc(x), N, H, W, C)
+    xf = x.clone().requires_grad_(True)
+    ref = F.max_pool2d(xf, 3, 2, 1)
+    assert (Ho, Wo) == tuple(ref.shape[2:])
+    assert torch.equal(_nchw(out, N, Ho, Wo), ref.detach())
+    dout = torch.randn_like(ref).to(bf16).float()
+    ref.backward(dout)
+    dx = ops.maxpool_bwd(_nhwc(dout), arg, N, H, W, C)
+    assert rel(_nchw(dx, N, H, W), xf.grad) < 1e-2
+    a = ops.avgpool_fwd(_nhwc(x), N, H * W, C)
+    assert rel(a, x.mean((2, 3))) < 1e-2
+    d = torch.randn(N, C, device=cuda_device).to(bf16)
+    da = ops.avgpool_bwd(d, N, H * W, C)
+    assert rel(_nchw(da, N, H, W), (d.float() / (H * W))[:, :, None, None].expand(N, C, H, W)) < 1e-2
+
+
+@pytest.mark.parametrize("k,stride,pad,Cin,Cout,H", [(3, 1, 1, 64, 64, 14), (3, 2, 1, 128, 128, 16), (1, 1, 0, 64, 256, 8)])
+def test_conv_as_gemm(ops, cuda_device, k, stride, pad, Cin, Cout, H):
+    torch.manual_seed(10)
+    N, W = 4, H
+    x = torch.randn(N, Cin, H, W, device=cuda_device).to(bf16).float()
+    w = (torch.randn(Cout, Cin, k, k, device=cuda_device) * 0.05).to(bf16).float()
+    xf = x.clone().requires_grad_(True)
+    wf = w.clone().requires_grad_(True)
+    ref = F.conv2d(xf, wf, None, stride, pad)
+    w_ohwi = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).to(bf16).contiguous()
+    xn = _nhwc(x)
+    if k == 1:
+        cols, Ho, Wo = xn, H, W
+    else:
+        cols, Ho, Wo = ops.im2col(xn, N, H, W, Cin, k, stride, pad)
+    y = ops.linear_fwd(cols, w_ohwi)
+    assert rel(_nchw(y, N, Ho, Wo), ref) < 1e-2
+    dy = torch.randn_like(ref).to(bf16).float()
+    ref.backward(dy)
+    dyn = _nhwc(dy)
+    dw = torch.zeros(Cout, k * k * Cin, device=cuda_device)
+    ops.linear_wgrad(dyn, cols, dw)
+    assert rel(dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2), wf.grad) < 1e-2
+    dcols = ops.linear_dgrad(dyn, w_ohwi)
+    dx = dcols if k == 1 else ops.col2im(dcols, N, H, W, Cin, k, stride, pad)
+    assert rel(_nchw(dx, N, H, W), xf.grad) < 2e-2
+
+
+def test_stem_lowering_and_subsample(ops, cuda_device):
+    torch.manual_seed(11)
+    N, H, W = 2, 32, 32
+    img = torch.randn(N, 3, H, W, device=cuda_device)
+    w = (torch.randn(64, 3, 7, 7, device=cuda_device) * 0.05).to(bf16).float()
+    ref = F.conv2d(img.to(bf16).float(), w, None, 2, 3)
+    Kp = 152
+    cols, Ho, Wo = ops.im2col_nchw_f32(img, 7, 2, 3, Kp)
+    wp = torch.zeros(64, Kp, device=cuda_device, dtype=bf16)
+    wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).to(bf16)
+    y = ops.linear_fwd(cols, wp)
+    assert rel(_nchw(y, N, Ho, Wo), ref) < 1e-2
+    x = torch.randn(N, 64, 8, 8, device=cuda_device).to(bf16).float()
+    sub, ho, wo = ops.subsample(_nhwc(x), N, 8, 8, 64, 2)
+    assert torch.equal(_nchw(sub, N, ho, wo), x[:, :, ::2, ::2])
+    add = torch.randn(N, 64, 8, 8, device=cuda_device).to(bf16).float()
+    up = ops.upsample_add(sub, _nhwc(add), N, 8, 8, 64, 2)
+    ref_up = add.clone()
+    ref_up[:, :, ::2, ::2] += x[:, :, ::2, ::2]
+    assert rel(_nchw(up, N, 8, 8), ref_up) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------- head / loss / optimizer
+def test_head_cross_entropy(ops, cuda_device):
+    torch.manual_seed(12)
+    B, Fd, C = 37, 512, 2
+    feat = torch.randn(B, Fd, device=cuda_device).to(bf16)
+    W = torch.randn(C, Fd, device=cuda_device) * 0.05
+    b = torch.randn(C, device=cuda_device)
+    labels = torch.randint(0, C, (B,), device=cuda_device)
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    logits, loss, correct, dfeat = ops.head_loss(feat, W, b, labels, dW=dW, dbias=db)
+    ff = feat.float().requires_grad_(True)
+    Wf = W.clone().requires_grad_(True)
+    bf = b.clone().requires_grad_(True)
+    ref_logits = ff @ Wf.t() + bf
+    ref_loss = F.cross_entropy(ref_logits, labels)
+    ref_loss.backward()
+    assert rel(logits, ref_logits) < 1e-5
+    assert abs(loss.item() - ref_loss.item()) < 1e-5
+    assert correct.item() == (ref_logits.argmax(1) == labels).sum().item()
+    assert rel(dfeat, ff.grad) < 1e-2 and rel(dW, Wf.grad) < 1e-4 and rel(db, bf.grad) < 1e-4
+    # external-dlogits path == what autograd of an arbitrary criterion would hand back
+    dlog = torch.autograd.grad(F.cross_entropy(ref_logits.detach().requires_grad_(True), labels),
+                               [], allow_unused=True) if False else None
+    lg = ref_logits.detach().requires_grad_(True)
+    F.cross_entropy(lg, labels).backward()
+    dW2, db2 = torch.zeros_like(W), torch.zeros_like(b)
+    _, _, _, dfeat2 = ops.head_loss(feat, W, b, None, loss_kind=ops.LOSS_EXTERNAL, dW=dW2, dbias=db2,
+                                    dlogits=lg.grad.contiguous())
+    assert rel(dfeat2, ff.grad) < 1e-2 and rel(dW2, Wf.grad) < 1e-4
+
+
+def test_head_focal(ops, cuda_device):
+    from torchvision.ops import sigmoid_focal_loss
+    torch.manual_seed(13)
+    B, Fd = 64, 512
+    feat = torch.randn(B, Fd, device=cuda_device).to(bf16)
+    W = torch.randn(1, Fd, device=cuda_device) * 0.1
+    b = torch.randn(1, device=cuda_device)
+    labels = torch.randint(0, 2, (B,), device=cuda_device)
+    dW, db = torch.zeros_like(W), torch.zeros_like(b)
+    logits, loss, correct, dfeat = ops.head_loss(feat, W, b, labels, loss_kind=ops.LOSS_FOCAL, alpha=0.25, gamma=2.0,
+                                                 dW=dW, dbias=db)
+    ff = feat.float().requires_grad_(True)
+    Wf = W.clone().requires_grad_(True)
+    ref_logits = (ff @ Wf.t() + b).squeeze(1)
+    ref = sigmoid_focal_loss(ref_logits, labels.float(), alpha=0.25, gamma=2.0, reduction="mean")
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert rel(dfeat, ff.grad) < 1e-2 and rel(dW, Wf.grad) < 1e-4
+
+
+def test_adam_matches_torch(ops, cuda_device):
+    torch.manual_seed(14)
+    n = 4096 * 33
+    p = torch.randn(n, device=cuda_device)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=2e-5)
+    m, v = torch.zeros(n, device=cuda_device), torch.zeros(n, device=cuda_device)
+    shadow = torch.empty(n, device=cuda_device, dtype=bf16)
+    for step in range(1, 6):
+        g = torch.randn(n, device=cuda_device) * (0.1 if step % 2 else 10)
+        ref_p.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, shadow, lr=2e-5, step=step)
+    assert (p - ref_p.detach()).abs().max().item() < 1e-6
+    assert torch.equal(shadow, p.to(bf16))
+    # clipping: same as clip_grad_norm_ followed by Adam
+    g = torch.randn(n, device=cuda_device) * 3
+    ref_p.grad = g.clone()
+    torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+    opt.step()
+    sq = torch.zeros(1, device=cuda_device)
+    ops.sumsq(g, sq)
+    assert abs(sq.item() - (g.double() ** 2).sum().item()) / sq.item() < 1e-4
+    ops.adam_step(p, g, m, v, shadow, lr=2e-5, step=6, gradsq=sq, max_norm=1.0)
+    assert (p - ref_p.detach()).abs().max().item() < 1e-6
