@@ -1,0 +1,118 @@
+/*
+ * libb200mm -- C ABI of the B200-native (sm_100a) kernels behind the task-2C multimodal classifier hot path.
+ *
+ * The reference (KevinMathewT/multimodal-propaganda-meme-classification) is pure Python: it has no FFI of its own.
+ * Its hot path bottoms out in ATen / cuBLASLt / cuDNN calls made by transformers and torchvision; each entry point
+ * below names the reference call site(s) it replaces.  Paths are relative to the reference repository;
+ * `$TF` = transformers/models/distilbert/modeling_distilbert.py, `$TV` = torchvision/models/resnet.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (CUDA), plain sizes, no torch types, no ownership transfer;
+ *   - `stream` is a cudaStream_t; all work is enqueued asynchronously on it (CUDA-graph capturable);
+ *   - return value: 0 = ok, > 0 = cudaError_t, < 0 = B200MM_ERR_* below; nothing throws across the boundary;
+ *   - bf16 matrices are row-major with the innermost dimension contiguous; `ld*` are row strides in ELEMENTS;
+ *   - alignment contract: bf16 pointers 16-byte aligned, row strides multiples of 8 elements.
+ * There is no CPU implementation behind any of these symbols.
+ */
+#ifndef B200MM_H_
+#define B200MM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MM_OK 0
+#define B200MM_ERR_BAD_ARG (-1)   /* shape / alignment contract violated */
+#define B200MM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled could not be resolved */
+#define B200MM_ERR_TENSORMAP (-3) /* the driver rejected a TMA tensor map */
+#define B200MM_ERR_NOT_SM100 (-4) /* current device is not compute capability 10.x */
+
+int b200mm_version(void);
+int b200mm_num_sms(void);
+
+/* ---- tcgen05 / TMA bf16 GEMM with fused epilogues ---------------------------------------------------------------
+ * D[M,N] = A x B, fp32 accumulation in TMEM.  a_mn = 0: A stored [M,K]; 1: A stored [K,M].  b_mn = 0: B stored
+ * [N,K]; 1: B stored [K,N].  epi: 0 store bf16 (acc + bias, dropout(p_drop, seed), + residual) | 1 GELU: out = z,
+ * out2 = gelu(z) | 2 dGELU: out = acc * gelu'(aux) | 3 fp32 store | 4 fp32 atomic accumulate (split-K) | 5 ReLU.
+ * Replaces: nn.Linear forward/backward behind q_lin/k_lin/v_lin/out_lin ($TF:187-189, :206), lin1/GELU/lin2
+ * ($TF:223-227), the fusion head (example_scripts/Multimodal_example_task2C.txt:179, :184, :193), torchvision's
+ * fc ($TV:206, :278) and every convolution of ResNet-50 ($TV:197, :118-130 via conv1x1 / conv3x3) as implicit GEMM. */
+int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, int M, int N,
+                     int K, int epi, const float* bias, const void* residual, long long ldr, const void* aux,
+                     long long ld_aux, void* out, long long ldc, void* out2, long long ld2, int splits, int block_n,
+                     float p_drop, unsigned long long seed, void* stream);
+
+/* ---- fused attention (head_dim 64, S <= 128) -------------------------------------------------------------------
+ * out[B*S, H*64] = softmax(Q K^T / 8 + key_bias) (dropout) V with Q|K|V = column blocks of qkv [B*S, 3*H*64].
+ * Replaces $TF:126-151 (eager_attention_forward) and its autograd backward. */
+int b200mm_attention_fwd(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
+                         float p_drop, unsigned long long seed, void* stream);
+int b200mm_attention_bwd(const void* qkv, const float* key_bias, const void* out, const void* dout, const float* lse,
+                         void* dqkv, int B, int H, int S, float p_drop, unsigned long long seed, void* stream);
+/* int64 attention_mask (1 = token) -> additive fp32 key bias 0 / -inf  ($TF:415-419) */
+int b200mm_mask_to_bias(const long long* mask, float* bias, long long n, void* stream);
+
+/* ---- LayerNorm / embeddings ($TF:96-122 Embeddings, :257 sa_layer_norm, :261 output_layer_norm) -------------- */
+int b200mm_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                         int M, int D, float eps, float p_drop, unsigned long long seed, void* stream);
+int b200mm_embed_layernorm_fwd(const long long* ids, const float* word, const float* pos, int S, int vocab,
+                               const float* gamma, const float* beta, void* x_saved, void* y, float* mean,
+                               float* rstd, int M, int D, float eps, float p_drop, unsigned long long seed,
+                               void* stream);
+int b200mm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                         void* dx, void* dx2, float* dgamma, float* dbeta, int M, int D, float p_in,
+                         unsigned long long seed_in, float p_out, unsigned long long seed_out, void* stream);
+int b200mm_embedding_bwd(const void* dx, const long long* ids, int S, int vocab, long long padding_idx, float* dword,
+                         float* dpos, int M, int D, void* stream);
+/* pooled token: out[i,:] = dropout(x[i*stride_rows + offset_rows, :])  (h[:, -1, :] + bert_drop,
+ * example_scripts/Multimodal_example_task2C.txt:178) and its backward scatter */
+int b200mm_gather_rows(const void* x, void* out, int rows, int D, long long stride_rows, long long offset_rows,
+                       float p_drop, unsigned long long seed, void* stream);
+int b200mm_scatter_rows(const void* dpooled, void* dx, long long M, int D, long long stride_rows,
+                        long long offset_rows, float p_drop, unsigned long long seed, void* stream);
+
+/* ---- image tower support: BatchNorm2d (training / eval), pooling, conv lowering ($TV:108-163, :197-206, :266-280) */
+int b200mm_batchnorm_fwd(const void* x, const void* residual, long long M, int C, const float* gamma,
+                         const float* beta, float eps, float momentum, int relu, void* out, float* mean_out,
+                         float* rstd_out, float* running_mean, float* running_var, float* scratch, void* stream);
+int b200mm_batchnorm_eval(const void* x, const void* residual, long long M, int C, const float* gamma,
+                          const float* beta, const float* running_mean, const float* running_var, float eps, int relu,
+                          void* out, void* stream);
+int b200mm_batchnorm_bwd(const void* dout, const void* out, const void* x, long long M, int C, const float* mean,
+                         const float* rstd, const float* gamma, int relu, void* dx, void* dz_out, float* dgamma,
+                         float* dbeta, float* scratch, void* stream);
+int b200mm_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, void* argmax, void* stream);
+int b200mm_maxpool3x3s2_bwd(const void* dout, const void* argmax, int N, int H, int W, int C, void* dx, void* stream);
+int b200mm_avgpool_fwd(const void* x, int N, int HW, int C, void* out, void* stream);
+int b200mm_avgpool_bwd(const void* dout, int N, int HW, int C, void* dx, void* stream);
+int b200mm_im2col_nhwc(const void* x, int N, int H, int W, int C, int KH, int KW, int stride, int pad, void* cols,
+                       void* stream);
+int b200mm_col2im_nhwc(const void* dcols, const void* addend, int N, int H, int W, int C, int KH, int KW, int stride,
+                       int pad, void* dx, void* stream);
+int b200mm_im2col_nchw_f32(const float* img, int N, int Cin, int H, int W, int KH, int KW, int stride, int pad,
+                           int Kp, void* cols, void* stream);
+int b200mm_subsample_nhwc(const void* x, int N, int H, int W, int C, int stride, void* out, void* stream);
+int b200mm_upsample_add_nhwc(const void* dsub, const void* addend, int N, int H, int W, int C, int stride, void* dx,
+                             void* stream);
+
+/* ---- head + loss, optimizer --------------------------------------------------------------------------------------
+ * output layer fused with the loss: example_scripts/Multimodal_example_task2C.txt:195 (output_fc) + :214, :248
+ * (nn.CrossEntropyLoss); loss_kind 1 = torchvision.ops.sigmoid_focal_loss (Multimodal_example_task2C.py:167);
+ * loss_kind 2 = backward only, from an external dL/dlogits. */
+int b200mm_head_loss(const void* feat, const float* W, const float* bias, const long long* labels, int B, int F,
+                     int C, int loss_kind, float alpha, float gamma, int train, const float* dlogits_in,
+                     float* logits, float* loss_sum, int* correct, void* dfeat, float* dW, float* dbias,
+                     void* stream);
+int b200mm_colsum_bf16(const void* x, long long ld, int M, int N, float* out, void* stream);
+/* optim.Adam(...).step() (example_scripts/Multimodal_example_task2C.txt:217, :249) + clip_grad_norm_
+ * (Multimodal_example_task2C.py:713-715) over a flat fp32 parameter range, refreshing the bf16 shadow */
+int b200mm_sumsq_f32(const float* g, long long n, float* out, void* stream);
+int b200mm_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, const float* gradsq,
+                     float max_norm, float grad_scale, void* stream);
+int b200mm_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MM_H_ */

@@ -1,6 +1,33 @@
 """b200mm: B200-native (sm_100a) train/infer engine for the task-2C late-fusion propaganda-meme classifier.
 
 Import as ``b200mm`` (a shim at the repo root maps that name onto this directory, whose name follows the
-reference repository and is not a valid Python identifier).
+reference repository and is not a valid Python identifier).  Public surface = the reference's own:
+
+    MultimodalClassifier(num_classes)            example_scripts/Multimodal_example_task2C.txt:152-197
+    train / test / evaluate                       ...txt:200-242, 259-280
+    CrossEntropyLoss, FusedAdam                   ...txt:248-249
+    ensemble.*                                    example_scripts/combine_preds.py
 """
 __version__ = "0.1.0"
+
+_LAZY = {
+    "MultimodalClassifier": ("model", "MultimodalClassifier"),
+    "TextConfig": ("text_tower", "TextConfig"),
+    "ImageConfig": ("image_tower", "ImageConfig"),
+    "FusedAdam": ("optim", "FusedAdam"),
+    "get_linear_schedule_with_warmup": ("optim", "get_linear_schedule_with_warmup"),
+    "CrossEntropyLoss": ("loop", "CrossEntropyLoss"),
+    "SigmoidFocalLoss": ("loop", "SigmoidFocalLoss"),
+    "train": ("loop", "train"),
+    "test": ("loop", "test"),
+    "evaluate": ("loop", "evaluate"),
+    "predict": ("loop", "predict"),
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        mod, attr = _LAZY[name]
+        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+    raise AttributeError(name)

@@ -53,7 +53,13 @@ def load(build_if_needed: bool = True) -> ctypes.CDLL:
     return lib
 
 
+# kernels launched through this module since the counter was last reset (bench.py's gpu_launches)
+LAUNCHES = [0]
+_KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0}
+
+
 def call(name: str, *args) -> None:
+    LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
     rc = getattr(load(), name)(*args)
     if rc != 0:
         if rc > 0:
@@ -80,7 +86,7 @@ declare("b200mm_embed_layernorm_fwd", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr,
                                        c_int, c_int, c_float, c_float, c_ulonglong, c_ptr])
 declare("b200mm_layernorm_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int,
                                  c_float, c_ulonglong, c_float, c_ulonglong, c_ptr])
-declare("b200mm_embedding_bwd", [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_int, c_int, c_ptr])
+declare("b200mm_embedding_bwd", [c_ptr, c_ptr, c_int, c_int, c_longlong, c_ptr, c_ptr, c_int, c_int, c_ptr])
 declare("b200mm_mask_to_bias", [c_ptr, c_ptr, c_longlong, c_ptr])
 declare("b200mm_colsum_bf16", [c_ptr, c_longlong, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_head_loss", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_float, c_float, c_int,

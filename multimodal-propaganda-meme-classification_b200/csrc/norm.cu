@@ -230,7 +230,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 // Embedding backward: scatter-add d(word+pos sum) rows into the fp32 gradient tables.
 __global__ void __launch_bounds__(256)
 embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const long long* __restrict__ ids, int S, int vocab,
-                     float* __restrict__ dword, float* __restrict__ dpos, int M, int D) {
+                     long long padding_idx, float* __restrict__ dword, float* __restrict__ dpos, int M, int D) {
   const int chunks = D >> 2;
   const long long total = static_cast<long long>(M) * chunks;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -243,7 +243,9 @@ embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const long long* __re
     const float2 a = unpack_bf16x2_dev(r.x), b = unpack_bf16x2_dev(r.y);
     float* w = dword + id * D + c;
     float* q = dpos + static_cast<long long>(row % S) * D + c;
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(w), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    // nn.Embedding(padding_idx=pad_token_id): the pad row never receives a gradient (modeling_distilbert.py:86)
+    if (ids[row] != padding_idx)
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(w), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
   }
 }
@@ -323,14 +325,14 @@ B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* 
   return B200MM_OK;
 }
 
-// dword[ids[m]] += dx[m], dpos[m % S] += dx[m]   (fp32 tables, accumulate)
-B200MM_API int b200mm_embedding_bwd(const void* dx, const long long* ids, int S, int vocab, float* dword, float* dpos,
-                                    int M, int D, void* stream) {
+// dword[ids[m]] += dx[m] (skipped where ids[m] == padding_idx; pass -1 for none), dpos[m % S] += dx[m]
+B200MM_API int b200mm_embedding_bwd(const void* dx, const long long* ids, int S, int vocab, long long padding_idx,
+                                    float* dword, float* dpos, int M, int D, void* stream) {
   if (M <= 0 || D <= 0 || (D & 3) || S <= 0) return B200MM_ERR_BAD_ARG;
   const long long total = static_cast<long long>(M) * (D >> 2);
   const int grid = static_cast<int>(total / 256 > 148 * 16 ? 148 * 16 : ceil_div(total, 256LL));
   embedding_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dx), ids, S, vocab, dword, dpos, M, D);
+      static_cast<const __nv_bfloat16*>(dx), ids, S, vocab, padding_idx, dword, dpos, M, D);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

@@ -1,0 +1,215 @@
+"""Image tower: torchvision-style ResNet (Bottleneck, v1.5) with explicit forward / backward on the sm_100a
+kernels.  Activations are NHWC bf16 token matrices [N*H*W, C]; every convolution is the tcgen05 GEMM
+(1x1: directly on the activation matrix; 3x3 / 7x7: on an im2col lowering); BatchNorm runs in training mode
+with per-replica batch statistics exactly like the reference.
+
+Mirrors ``self.resnet(image)`` of example_scripts/Multimodal_example_task2C.txt:164, :183 ->
+torchvision/models/resnet.py:108-163 (Bottleneck), :197-213 (stem, init), :266-280 (_forward_impl).
+The 1000-way ImageNet ``fc`` is kept, as the reference keeps it (.txt:164-165).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .params import ParamStore
+
+STEM_K = 7 * 7 * 3
+STEM_KP = 152  # K padded to a multiple of 8 elements (TMA row stride must be a multiple of 16 bytes)
+
+
+@dataclass
+class ImageConfig:
+    layers: tuple = (3, 4, 6, 3)   # ResNet-50
+    width: int = 64
+    num_outputs: int = 1000
+    bn_eps: float = 1e-5
+    bn_momentum: float = 0.1
+    prefix: str = "resnet"
+
+
+class _Conv:
+    """One conv (+ its BatchNorm): parameter views and geometry."""
+
+    def __init__(self, name, bn_name, cin, cout, k, stride, pad):
+        self.name, self.bn_name = name, bn_name
+        self.cin, self.cout, self.k, self.stride, self.pad = cin, cout, k, stride, pad
+        self.kdim = STEM_KP if cin == 3 else k * k * cin
+
+
+class ImageTower:
+    def __init__(self, cfg: ImageConfig, store: ParamStore):
+        self.cfg = cfg
+        self.store = store
+        p = cfg.prefix
+        self.stem = _Conv(f"{p}.conv1", f"{p}.bn1", 3, cfg.width, 7, 2, 3)
+        self.blocks = []
+        inplanes = cfg.width
+        for li, nblocks in enumerate(cfg.layers):
+            planes = cfg.width * (2 ** li)
+            for bi in range(nblocks):
+                stride = 2 if (li > 0 and bi == 0) else 1
+                base = f"{p}.layer{li + 1}.{bi}"
+                blk = {
+                    "c1": _Conv(f"{base}.conv1", f"{base}.bn1", inplanes, planes, 1, 1, 0),
+                    "c2": _Conv(f"{base}.conv2", f"{base}.bn2", planes, planes, 3, stride, 1),
+                    "c3": _Conv(f"{base}.conv3", f"{base}.bn3", planes, planes * 4, 1, 1, 0),
+                    "ds": None,
+                    "stride": stride,
+                }
+                if stride != 1 or inplanes != planes * 4:
+                    blk["ds"] = _Conv(f"{base}.downsample.0", f"{base}.downsample.1", inplanes, planes * 4, 1, stride, 0)
+                self.blocks.append(blk)
+                inplanes = planes * 4
+        self.feat_dim = inplanes
+        self._convs = [self.stem] + [c for b in self.blocks for c in (b["c1"], b["c2"], b["c3"], b["ds"]) if c]
+        self._saved = None
+        self.buffers = None
+        self.capture = None   # set to a list to record every block's output (per-layer parity checks)
+
+    # ------------------------------------------------------------------ parameters
+    def register_noshadow(self):
+        st = self.store
+        for c in self._convs:
+            st.add(f"{c.bn_name}.weight", (c.cout,), shadow=False)
+            st.add(f"{c.bn_name}.bias", (c.cout,), shadow=False)
+        st.add(f"{self.cfg.prefix}.fc.bias", (self.cfg.num_outputs,), shadow=False)
+
+    def register_shadowed(self):
+        st = self.store
+        for c in self._convs:
+            st.add(f"{c.name}.weight", (c.cout, c.kdim))   # OHWI flattened: [Cout, kh*kw*Cin] (stem padded to 152)
+        st.add(f"{self.cfg.prefix}.fc.weight", (self.cfg.num_outputs, self.feat_dim))
+
+    def bind(self):
+        st = self.store
+        dev = st.device
+        # running statistics live outside the optimizer's flat buffer
+        total = sum(2 * c.cout for c in self._convs)
+        self.buffers = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for c in self._convs:
+            c.w, c.dw = st.s(f"{c.name}.weight"), st.g(f"{c.name}.weight")
+            c.g, c.dg = st.p(f"{c.bn_name}.weight"), st.g(f"{c.bn_name}.weight")
+            c.b, c.db = st.p(f"{c.bn_name}.bias"), st.g(f"{c.bn_name}.bias")
+            c.rm = self.buffers[off:off + c.cout]
+            c.rv = self.buffers[off + c.cout:off + 2 * c.cout]
+            c.rv.fill_(1.0)
+            off += 2 * c.cout
+        p = self.cfg.prefix
+        self.fc_w, self.dfc_w = st.s(f"{p}.fc.weight"), st.g(f"{p}.fc.weight")
+        self.fc_b, self.dfc_b = st.p(f"{p}.fc.bias"), st.g(f"{p}.fc.bias")
+        self.num_batches_tracked = 0
+
+    def init_parameters(self, generator=None):
+        """torchvision init (resnet.py:208-213): kaiming_normal_(fan_out, relu) convs, BN = (1, 0); nn.Linear default
+        (kaiming_uniform a=sqrt(5)) for fc."""
+        st = self.store
+        for c in self._convs:
+            w = st.p(f"{c.name}.weight")
+            std = (2.0 / (c.cout * c.k * c.k)) ** 0.5
+            w.normal_(0.0, std, generator=generator)
+            if c.cin == 3:
+                w[:, STEM_K:].zero_()
+            st.p(f"{c.bn_name}.weight").fill_(1.0)
+            st.p(f"{c.bn_name}.bias").zero_()
+        p = self.cfg.prefix
+        bound = 1.0 / (self.feat_dim ** 0.5)
+        st.p(f"{p}.fc.weight").uniform_(-bound, bound, generator=generator)
+        st.p(f"{p}.fc.bias").uniform_(-bound, bound, generator=generator)
+
+    # ------------------------------------------------------------------ building blocks
+    def _bn(self, c, x, training, residual=None, relu=True):
+        cfg = self.cfg
+        if training:
+            return ops.batchnorm_fwd(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps,
+                                     momentum=cfg.bn_momentum)
+        return ops.batchnorm_eval(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps), None, None
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, image: torch.Tensor, *, training: bool):
+        """image: fp32 NCHW [N, 3, H, W] (what the reference's transforms produce). Returns bf16 [N, 1000]."""
+        N, Cin, H, W = image.shape
+        assert Cin == 3
+        sv = {"N": N, "blocks": []} if training else None
+        st = self.stem
+        cols, H1, W1 = ops.im2col_nchw_f32(image, 7, 2, 3, STEM_KP)
+        c0 = ops.linear_fwd(cols, st.w)
+        a0, m0, r0 = self._bn(st, c0, training)
+        x, arg, H2, W2 = ops.maxpool_fwd(a0, N, H1, W1, st.cout)
+        if training:
+            sv["stem"] = (cols, c0, a0, m0, r0, arg, H1, W1)
+        Hc, Wc = H2, W2
+        for blk in self.blocks:
+            c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
+            y1 = ops.linear_fwd(x, c1.w)
+            a1, m1, r1 = self._bn(c1, y1, training)
+            cols2, Ho, Wo = ops.im2col(a1, N, Hc, Wc, c2.cin, 3, stride, 1)
+            y2 = ops.linear_fwd(cols2, c2.w)
+            a2, m2, r2 = self._bn(c2, y2, training)
+            y3 = ops.linear_fwd(a2, c3.w)
+            xs = yd = md = rd = None
+            if ds is not None:
+                xs = x if stride == 1 else ops.subsample(x, N, Hc, Wc, ds.cin, stride)[0]
+                yd = ops.linear_fwd(xs, ds.w)
+                idn, md, rd = self._bn(ds, yd, training, relu=False)
+            else:
+                idn = x
+            out, m3, r3 = self._bn(c3, y3, training, residual=idn, relu=True)
+            if training:
+                sv["blocks"].append((x, y1, a1, m1, r1, cols2, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hc, Wc,
+                                     Ho, Wo))
+            x, Hc, Wc = out, Ho, Wo
+            if self.capture is not None:
+                self.capture.append((x, N, Hc, Wc))
+        pooled = ops.avgpool_fwd(x, N, Hc * Wc, self.feat_dim)
+        logits = ops.linear_fwd(pooled, self.fc_w, self.fc_b)
+        if training:
+            sv["tail"] = (pooled, Hc, Wc)
+            self.num_batches_tracked += 1
+        self._saved = sv
+        return logits
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dlogits: torch.Tensor):
+        """dlogits: bf16 [N, 1000]. Accumulates parameter gradients (the image itself needs none)."""
+        sv = self._saved
+        assert sv is not None, "backward() without a training-mode forward()"
+        N = sv["N"]
+        pooled, Hc, Wc = sv["tail"]
+        ops.linear_wgrad(dlogits, pooled, self.dfc_w)
+        ops.colsum(dlogits, self.dfc_b)
+        dpooled = ops.linear_dgrad(dlogits, self.fc_w)
+        d_out = ops.avgpool_bwd(dpooled, N, Hc * Wc, self.feat_dim)
+        for blk, s in zip(reversed(self.blocks), reversed(sv["blocks"])):
+            c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
+            x, y1, a1, m1, r1, cols2, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hi, Wi, Ho, Wo = s
+            # out = relu(bn3(y3) + idn)
+            d_y3, dz = ops.batchnorm_bwd(d_out, out, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, need_dz=True)
+            ops.linear_wgrad(d_y3, a2, c3.dw)
+            d_a2 = ops.linear_dgrad(d_y3, c3.w)
+            d_y2, _ = ops.batchnorm_bwd(d_a2, a2, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True)
+            ops.linear_wgrad(d_y2, cols2, c2.dw)
+            d_cols2 = ops.linear_dgrad(d_y2, c2.w)
+            d_a1 = ops.col2im(d_cols2, N, Hi, Wi, c2.cin, 3, stride, 1)
+            d_y1, _ = ops.batchnorm_bwd(d_a1, a1, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True)
+            ops.linear_wgrad(d_y1, x, c1.dw)
+            if ds is None:
+                d_out = ops.linear_dgrad(d_y1, c1.w, residual=dz)          # identity branch folded into the epilogue
+            else:
+                d_yd, _ = ops.batchnorm_bwd(dz, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=False)
+                ops.linear_wgrad(d_yd, xs, ds.dw)
+                d_x1 = ops.linear_dgrad(d_y1, c1.w)
+                if stride == 1:
+                    d_out = ops.linear_dgrad(d_yd, ds.w, residual=d_x1)
+                else:
+                    d_xs = ops.linear_dgrad(d_yd, ds.w)
+                    d_out = ops.upsample_add(d_xs, d_x1, N, Hi, Wi, ds.cin, stride)
+        cols, c0, a0, m0, r0, arg, H1, W1 = sv["stem"]
+        st = self.stem
+        d_a0 = ops.maxpool_bwd(d_out, arg, N, H1, W1, st.cout)
+        d_c0, _ = ops.batchnorm_bwd(d_a0, a0, c0, m0, r0, st.g, st.dg, st.db, relu=True)
+        ops.linear_wgrad(d_c0, cols, st.dw)
+        self._saved = None

@@ -44,9 +44,41 @@ def _chk(t: torch.Tensor, dtype, name="tensor"):
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
+_gemm_profile = None   # when a list: (start_event, end_event, flops) per GEMM launch (see profile_gemm)
+
+
+def profile_gemm(step_fn, steps: int = 2):
+    """Time every GEMM launch of ``steps`` calls of ``step_fn`` with CUDA events on the launching stream.
+    Returns (GEMM milliseconds per step, GEMM FLOPs per step, GEMM launches per step)."""
+    global _gemm_profile
+    torch.cuda.synchronize()
+    _gemm_profile = []
+    try:
+        for _ in range(steps):
+            step_fn()
+        torch.cuda.synchronize()
+        rec = _gemm_profile
+    finally:
+        _gemm_profile = None
+    ms = sum(a.elapsed_time(b) for a, b, _ in rec)
+    fl = sum(f for _, _, f in rec)
+    return ms / steps, fl / steps, len(rec) // steps
+
+
 def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residual=None, aux=None, out2=None,
              splits=1, block_n=0, p_drop=0.0, seed=0):
     """D[M,N] = A x B (+epilogue). A: [M,K] (a_mn False) or [K,M] (a_mn True); B: [N,K] or [K,N]."""
+    if _gemm_profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call("b200mm_gemm_bf16", _p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, epi,
+                  _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
+                  _p(aux), aux.stride(0) if aux is not None else 0, _p(out), out.stride(0),
+                  _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed),
+                  _s())
+        e1.record()
+        _gemm_profile.append((e0, e1, 2.0 * M * N * K))
+        return out
     _lib.call("b200mm_gemm_bf16", _p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, epi,
               _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
               _p(aux), aux.stride(0) if aux is not None else 0, _p(out), out.stride(0),
@@ -164,10 +196,10 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, p_in=0.0, seed_in=
     return dx, dx2
 
 
-def embedding_bwd(dx, ids, dword, dpos):
+def embedding_bwd(dx, ids, dword, dpos, padding_idx=-1):
     B, S = ids.shape
     V, D = dword.shape
-    _lib.call("b200mm_embedding_bwd", _p(dx), _p(ids), S, V, _p(dword), _p(dpos), B * S, D, _s())
+    _lib.call("b200mm_embedding_bwd", _p(dx), _p(ids), S, V, int(padding_idx), _p(dword), _p(dpos), B * S, D, _s())
 
 
 def gather_rows(x, rows, stride_rows, offset_rows, *, p_drop=0.0, seed=0):

@@ -1,0 +1,82 @@
+"""``FusedAdam``: torch.optim.Adam semantics (reference: optim.Adam(model.parameters(), lr=2e-5),
+example_scripts/Multimodal_example_task2C.txt:249; HEAD script param groups + clip_grad_norm_,
+Multimodal_example_task2C.py:168, :645-664, :713-715) as ONE streaming kernel per contiguous parameter range:
+read p, g, m, v (fp32), write p, m, v and the bf16 shadow the GEMMs consume -- 30 B / parameter of HBM traffic,
+nothing else.  Optional global-norm clipping is folded in (a sum-of-squares pre-pass, then the clip factor is
+applied inside the Adam kernel; no separate scaling pass over the gradients).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = max_grad_norm
+        stores = {id(getattr(p, "_b200mm_store", None)): getattr(p, "_b200mm_store", None)
+                  for g in self.param_groups for p in g["params"]}
+        if len(stores) != 1 or None in stores.values():
+            raise ValueError("FusedAdam drives the parameters of exactly one b200mm model")
+        self.store = next(iter(stores.values()))
+        self.model = self.store.owner
+        n = self.store.numel
+        self.exp_avg = torch.zeros(n, device=self.store.device, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=self.store.device, dtype=torch.float32)
+        self._gradsq = torch.zeros(1, device=self.store.device, dtype=torch.float32)
+        self._step = 0
+        self.last_grad_norm = None
+        # contiguous element ranges per param group (alignment padding between parameters is all-zero: safe to sweep)
+        self._ranges = []
+        for gi, g in enumerate(self.param_groups):
+            spans = sorted((p._b200mm_offset, p._b200mm_offset + p._b200mm_padded) for p in g["params"])
+            merged = []
+            for a, b in spans:
+                if merged and merged[-1][1] == a:
+                    merged[-1][1] = b
+                else:
+                    merged.append([a, b])
+            self._ranges.append(merged)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.model.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        assert closure is None
+        st = self.store
+        self._step += 1
+        sync = getattr(self.model, "grad_sync", None)
+        if sync is not None:
+            grad_scale = grad_scale * sync.finish()     # summed gradients -> mean, folded into the Adam kernel
+        gradsq = None
+        if self.max_grad_norm is not None:
+            self._gradsq.zero_()
+            ops.sumsq(st.grad, self._gradsq)
+            gradsq = self._gradsq
+            self.last_grad_norm = self._gradsq   # device scalar (squared norm); .sqrt().item() when logging
+        s0 = st.shadow_start
+        for g, ranges in zip(self.param_groups, self._ranges):
+            b1, b2 = g["betas"]
+            for a, b in ranges:
+                # split at the shadow boundary: embedding tables / norm params have no bf16 shadow
+                for lo, hi, sh in ((a, min(b, s0), False), (max(a, s0), b, True)):
+                    if hi <= lo:
+                        continue
+                    ops.adam_step(st.master[lo:hi], st.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                                  st.shadow[lo:hi] if sh else None, lr=g["lr"], beta1=b1, beta2=b2, eps=g["eps"],
+                                  weight_decay=g["weight_decay"], step=self._step, gradsq=gradsq,
+                                  max_norm=self.max_grad_norm or 0.0, grad_scale=grad_scale)
+        self.model._shadow_fresh = True
+
+
+def get_linear_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, last_epoch=-1):
+    """Same schedule as transformers.get_linear_schedule_with_warmup (used at Multimodal_example_task2C.py:172-174)."""
+    def lr_lambda(step):
+        if step < num_warmup_steps:
+            return float(step) / float(max(1, num_warmup_steps))
+        return max(0.0, float(num_training_steps - step) / float(max(1, num_training_steps - num_warmup_steps)))
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, lr_lambda, last_epoch)

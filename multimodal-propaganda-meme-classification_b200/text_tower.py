@@ -34,6 +34,7 @@ class TextConfig:
     dropout: float = 0.1
     attention_dropout: float = 0.1
     layer_norm_eps: float = 1e-12
+    pad_token_id: int = 0      # nn.Embedding(padding_idx=pad_token_id): no gradient for the pad row
     prefix: str = "bert"
 
 
@@ -51,6 +52,7 @@ class TextTower:
         self.cfg = cfg
         self.store = store
         self._saved = None
+        self.capture = None   # set to a list to record the embedding output and every layer's output
 
     # ------------------------------------------------------------------ parameter registration (reference key names)
     def register_noshadow(self):
@@ -141,6 +143,8 @@ class TextTower:
                                                            c.layer_norm_eps, p_drop=pd, seed=s_emb)
         saved = {"ids": ids, "key_bias": key_bias, "B": B, "S": S, "emb": (x_emb, e_mean, e_rstd, pd, s_emb),
                  "layers": []} if training else None
+        if self.capture is not None:
+            self.capture.append(x)
         for li, L in enumerate(self.layers):
             s_att, s_ffn = _mix(seed, step, li, 1), _mix(seed, step, li, 2)
             qkv = ops.linear_fwd(x, L["wqkv"], L["bqkv"])
@@ -153,6 +157,8 @@ class TextTower:
             if training:
                 saved["layers"].append((x, qkv, ctx, lse, y_pre, m1, r1, y, z, a, o_pre, m2, r2, pa, s_att, pd, s_ffn))
             x = out
+            if self.capture is not None:
+                self.capture.append(x)
         self._saved = saved
         return x
 
@@ -188,5 +194,5 @@ class TextTower:
             d_out = ops.linear_dgrad(dqkv, L["wqkv"], residual=d_ypre)     # + residual path of LN1's input
         x_emb, e_mean, e_rstd, pd, s_emb = sv["emb"]
         d_emb, _ = ops.layernorm_bwd(d_out, x_emb, e_mean, e_rstd, self.eg, self.deg, self.deb, p_in=pd, seed_in=s_emb)
-        ops.embedding_bwd(d_emb, sv["ids"], self.dword, self.dpos)
+        ops.embedding_bwd(d_emb, sv["ids"], self.dword, self.dpos, padding_idx=self.cfg.pad_token_id)
         self._saved = None

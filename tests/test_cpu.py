@@ -1,0 +1,281 @@
+"""CPU-side tests (run with -m "not gpu"): the oracle against the committed golden vectors, the host logic
+(TSV schema, fold ensembling, parameter store, gradient-bucket planning incl. a 2-rank gloo run) and the C-ABI
+library's load / export contract.  No compute kernel is called here."""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------------------- oracle pinning
+def test_oracle_matches_committed_golden():
+    """oracle/reference_model.py reproduces the vectors committed by tests/golden/make_golden.py."""
+    import torch.nn as nn
+    from oracle import reference_model as R
+    fx = torch.load(os.path.join(GOLD, "oracle_tiny_golden.pt"))
+    cfg = R.TowerConfig.tiny()
+    torch.manual_seed(42)
+    torch.set_num_threads(1)
+    m = R.zero_dropout(R.MultimodalClassifier(2, cfg))
+    m.train()
+    data = R.synthetic_batch(8, 32, cfg)
+    assert data["text"].sum() == fx["text_ids_sum"] and data["text_mask"].sum() == fx["mask_sum"]
+    assert torch.equal(data["label"], fx["labels"])
+    out = m(data["text"], data["image"], data["text_mask"])
+    loss = nn.CrossEntropyLoss()(out, data["label"])
+    loss.backward()
+    assert torch.allclose(out.detach(), fx["logits"], rtol=1e-4, atol=1e-5)
+    assert abs(loss.item() - fx["loss"].item()) < 1e-5
+    assert torch.allclose(m.output_fc.weight.grad, fx["grad_output_fc"], rtol=1e-3, atol=1e-6)
+    assert abs(m.bert.transformer.layer[0].attention.q_lin.weight.grad.norm().item() - fx["grad_q0_norm"].item()) \
+        < 1e-3 * fx["grad_q0_norm"].item()
+    assert abs(m.resnet.conv1.weight.grad.norm().item() - fx["grad_conv1_norm"].item()) \
+        < 1e-3 * fx["grad_conv1_norm"].item()
+
+
+def test_oracle_is_the_reference_graph():
+    """Structure pinned to the reference module (example_scripts/Multimodal_example_task2C.txt:152-197):
+    parameter count of configs 1-2 (161.72 M) and the last-token pooling quirk."""
+    from oracle import reference_model as R
+    m = R.MultimodalClassifier(2, R.TowerConfig.tiny())
+    names = dict(m.named_parameters())
+    for k in ("bert_fc.weight", "resnet_fc.weight", "fusion_fc.weight", "output_fc.weight"):
+        assert k in names
+    assert names["resnet_fc.weight"].shape == (512, 1000) and names["fusion_fc.weight"].shape == (512, 1024)
+    # full-size parameter count without allocating it: build on the meta device
+    with torch.device("meta"):
+        full = R.MultimodalClassifier(2)
+    assert sum(p.numel() for p in full.parameters()) == 161_723_178
+    # h[:, -1, :] pooling: changing a token in the LAST position changes the text feature even when it is padding
+    m = R.zero_dropout(m).eval()
+    d = R.synthetic_batch(2, 16, R.TowerConfig.tiny())
+    with torch.no_grad():
+        a = m(d["text"], d["image"], d["text_mask"])
+        t2 = d["text"].clone()
+        t2[:, -1] = 7
+        b = m(t2, d["image"], d["text_mask"])
+    assert not torch.allclose(a[1], b[1])
+
+
+# ------------------------------------------------------------------------------------------------- ensembling tail
+def _load_combine_fixture():
+    with open(os.path.join(GOLD, "combine_preds_golden.json")) as f:
+        fx = json.load(f)
+    rank = {int(k): v for k, v in fx["sorted_rank"].items()}
+    # ids whose lexicographic order equals the order of the original dataset paths (pandas groupby sorts by id)
+    name = {k: f"id{rank[k]:05d}" for k in rank}
+    gold = {name[int(k)]: ("propaganda" if v else "not_propaganda") for k, v in fx["gold"].items()}
+    folds = [([name[i] for i in fo["idx"]], [float(p) for p in fo["prob_repr"]]) for fo in fx["folds"]]
+    return fx, gold, folds
+
+
+def test_combine_preds_known_answer():
+    """Reproduces, bit for bit in float64, what the reference's own script prints on its committed fold TSVs."""
+    from b200mm import ensemble
+    fx, gold, folds = _load_combine_fixture()
+    got = []
+    for ids, probs in folds:
+        t, f1, _ = ensemble.threshold_optimization(ids, np.array(probs), gold)
+        got.append((t, f1))
+    ids, mean = ensemble.average_probability([f[0] for f in folds], [f[1] for f in folds])
+    t, f1, labels = ensemble.threshold_optimization(ids, mean, gold)
+    got.append((t, f1))
+    assert len(fx["pairs_threshold_f1"]) == 6
+    for (gt, gf), (rt, rf) in zip(got, fx["pairs_threshold_f1"]):
+        assert gt == rt and abs(gf - rf) < 1e-12
+    assert abs(got[-1][0] - 0.42424242424242425) < 1e-15 and abs(got[-1][1] - 0.647887323943662) < 1e-12
+    assert len(labels) == 312
+
+
+def test_ensemble_matches_pandas_sklearn_oracle():
+    """Random folds: numpy implementation == the pandas/sklearn restatement of combine_preds (oracle/ensemble.py)."""
+    pd = pytest.importorskip("pandas")
+    from b200mm import ensemble
+    from oracle import ensemble as O
+    rng = np.random.default_rng(0)
+    ids = [f"data/x/{i:04d}.jpg" for i in range(200)]
+    gold = {i: ("propaganda" if rng.random() < 0.3 else "not_propaganda") for i in ids}
+    folds = []
+    for k in range(5):
+        perm = rng.permutation(len(ids))
+        folds.append(([ids[j] for j in perm], rng.random(len(ids)).astype(np.float32).astype(np.float64)[perm]))
+    dfs = [pd.DataFrame({"id": f[0], "prob": f[1]}) for f in folds]
+    labels_df = pd.DataFrame({"id": list(gold), "class_label": list(gold.values())})
+    avg = O.average_probability(dfs)
+    gi, gm = ensemble.average_probability([f[0] for f in folds], [f[1] for f in folds])
+    assert list(avg["id"]) == gi
+    assert np.allclose(avg["prob"].values, gm, rtol=0, atol=1e-15)
+    _, t_ref, f_ref = O.threshold_optimization(avg, labels_df)
+    t, f, lab = ensemble.threshold_optimization(gi, gm, gold)
+    assert t == t_ref and abs(f - f_ref) < 1e-12
+    mv = O.majority_voting(dfs)  # the reference votes row-by-row (pd.concat aligns on the row index, not on id)
+    assert list(mv["label"]) == ensemble.majority_voting([f[1] for f in folds])
+
+
+def test_scorer_known_answer_and_roc_threshold():
+    from sklearn.metrics import roc_curve
+    from b200mm import ensemble
+    with open(os.path.join(GOLD, "scorer_golden.json")) as f:
+        fx = json.load(f)
+    gold = np.array(fx["gold"])
+    pred = np.array([fx["pred"][str(i)] for i in range(len(gold))])
+    assert abs(ensemble.macro_f1(gold, pred) - fx["f1_macro"]) < 1e-12       # scorer/task2.py:109
+    assert abs((gold == pred).mean() - fx["acc"]) < 1e-12
+    rng = np.random.default_rng(1)
+    y = (rng.random(300) < 0.3).astype(int)
+    p = np.clip(rng.normal(0.4 + 0.2 * y, 0.2), 0, 1).astype(np.float32).astype(np.float64)
+    fpr, tpr, thr = roc_curve(y, p)                                          # Multimodal_example_task2C.py:819-822
+    assert ensemble.roc_optimal_threshold(y, p) == thr[np.argmax(tpr - fpr)]
+
+
+# ------------------------------------------------------------------------------------------------- TSV contract
+def test_tsv_schema_roundtrip(tmp_path):
+    from b200mm import tsv
+    ids = ["data/arabic_memes_fb_insta_pinterest/Instagram/IMAGES/a/1.jpg", "data/x/y_z/2.png"]
+    p32 = np.array([0.37347766757011414, 0.8171256780624390], dtype=np.float32)
+    path = tmp_path / "task2C_kevinmathew_probs_fold_0.tsv"
+    tsv.write_prob_tsv(path, ids, ["not_propaganda", "propaganda"], p32, "run-1")
+    lines = path.read_text().split("\n")
+    assert lines[0] == "id\tlabel\tprob\trun_id"
+    assert lines[1].split("\t")[2] == "0.37347766757011414"      # float repr of the fp32 value, as the reference prints
+    i2, l2, pr, r2 = tsv.read_prob_tsv(path)
+    assert i2 == ids and l2 == ["not_propaganda", "propaganda"] and r2 == ["run-1", "run-1"]
+    assert np.array_equal(np.array(pr, dtype=np.float32), p32)
+    lab = tmp_path / "task2C_TeamName.tsv"
+    tsv.write_label_tsv(lab, ids, ["propaganda", "not_propaganda"], "DistilBERT-ResNet")
+    assert tsv.check_label_tsv(lab)
+    lab.write_text("id\tlabel\trun_id\nbad line\n")
+    assert not tsv.check_label_tsv(lab)
+
+
+# ------------------------------------------------------------------------------------------------- C ABI contract
+def test_library_builds_loads_and_exports_header_symbols():
+    from b200mm import _build, _lib
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "b200mm.h")) as f:
+        declared = set(re.findall(r"\bint\s+(b200mm_\w+)\s*\(", f.read()))
+    assert len(declared) >= 29
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(_lib.exported_symbols())          # ctypes table mirrors the header exactly
+    assert lib.b200mm_version() >= 100
+    # sm_100a SASS with tcgen05 / TMA instructions is really in the shipped object
+    out = os.popen(f"cuobjdump -sass {path} 2>/dev/null | grep -c -E 'UTCHMMA|UTMALDG|LDTM'").read().strip()
+    if out:
+        assert int(out) > 0
+
+
+def test_no_cpu_fallback():
+    """The product path fails loudly without CUDA; it never routes through the oracle."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import b200mm
+    from b200mm import _lib
+    with pytest.raises(_lib.B200MMError):
+        b200mm.MultimodalClassifier(2)
+    src = ""
+    pkg = os.path.join(ROOT, "multimodal-propaganda-meme-classification_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src += open(os.path.join(pkg, fn)).read()
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+# ------------------------------------------------------------------------------------------------- parameter store / DP plan
+def _fake_store():
+    from b200mm.params import ParamStore
+    st = ParamStore("cpu")
+    st.add("bert.embeddings.word_embeddings.weight", (100, 16), shadow=False)
+    st.add("bert.layer.bias", (48,), shadow=False)
+    st.add("resnet.bn1.weight", (64,), shadow=False)
+    st.add("output_fc.bias", (2,), shadow=False)
+    st.add("bert.layer.q.weight", (16, 16))
+    st.add("bert.layer.k.weight", (16, 16))
+    st.add("resnet.conv1.weight", (64, 152))
+    st.add("fusion_fc.weight", (512, 1024))
+    st.finalize()
+    return st
+
+
+def test_param_store_layout_and_bucket_plan():
+    from b200mm.ddp import GradSync
+    st = _fake_store()
+    offs = [st.specs[n].offset for n in st.names()]
+    assert offs == sorted(offs) and all(o % 64 == 0 for o in offs)
+    assert st.shadow_start == st.specs["bert.layer.q.weight"].offset
+    qk = st.span(st.master, "bert.layer.q.weight", "bert.layer.k.weight", (32, 16))
+    qk.fill_(3.0)
+    assert st.p("bert.layer.k.weight").eq(3).all() and st.p("resnet.conv1.weight").eq(0).all()
+    gs = GradSync(st, bucket_elems=4096)
+    cov = gs.covered()
+    assert cov[0][0] == 0 and cov[-1][1] == st.numel
+    assert all(a[1] == b[0] for a, b in zip(cov, cov[1:]))                   # exact, gap-free, non-overlapping cover
+    assert all(b - a <= 4096 for a, b in cov)
+    text = gs.phases["text"]
+    spec = st.specs
+    assert text[0][0] == spec["bert.embeddings.word_embeddings.weight"].offset
+    assert any(a <= spec["bert.layer.k.weight"].offset < b for a, b in text)
+    assert not any(a <= spec["resnet.conv1.weight"].offset < b for a, b in text)
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200mm.ddp import GradSync
+    st = _fake_store()
+    torch.manual_seed(100 + rank)
+    st.master.normal_()
+    gs = GradSync(st, bucket_elems=10000)
+    gs.broadcast_parameters()
+    torch.manual_seed(7 + rank)
+    st.grad.normal_()
+    local = st.grad.clone()
+    gs.ready("text")
+    gs.ready("rest")
+    scale = gs.finish()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = torch.allclose(st.grad * scale, sum(gathered) / world, atol=1e-6)
+    ref = st.master.clone()
+    dist.broadcast(ref, src=0)
+    ok = ok and torch.equal(ref, st.master)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference prints one JSON line with the keys the driver reads (tiny run)."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-batch", "2", "--seq", "16"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0

@@ -180,6 +180,12 @@ def test_embedding_fwd_bwd(ops, cuda_device):
     dpos = torch.zeros(64, D, device=cuda_device)
     ops.embedding_bwd(dx, ids, dword, dpos)
     ref_w = torch.zeros(V, D, device=cuda_device).index_add_(0, ids.view(-1), dx.float())
+    pad = int(ids[0, 0])
+    dword_p = torch.zeros(V, D, device=cuda_device)
+    ops.embedding_bwd(dx, ids, dword_p, torch.zeros(64, D, device=cuda_device), padding_idx=pad)
+    ref_wp = ref_w.clone()
+    ref_wp[pad] = 0
+    assert rel(dword_p, ref_wp) < 1e-5 and dword_p[pad].abs().sum().item() == 0
     ref_p = torch.zeros(64, D, device=cuda_device)
     ref_p[:S] = dx.float().view(B, S, D).sum(0)
     assert rel(dword, ref_w) < 1e-5 and rel(dpos, ref_p) < 1e-5
