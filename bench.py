@@ -144,7 +144,7 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=dev)
     import b200mm
     from b200mm import _lib, ops
-    from oracle import reference_model as R   # synthetic-input generator only (shared with the oracle)
+    from b200mm.synth import synthetic_batch
 
     B, S = args.batch, args.seq
     model = b200mm.MultimodalClassifier(2, device=dev, seed=42)
@@ -154,7 +154,7 @@ def run_engine(args):
     crit = b200mm.CrossEntropyLoss()
     opt = b200mm.FusedAdam(model.parameters(), lr=2e-5)
 
-    host = R.synthetic_batch(B, S, seed=1234 + rank)
+    host = synthetic_batch(B, S, seed=1234 + rank)
     host = {k: v.pin_memory() for k, v in host.items()}
     devd = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -228,6 +228,7 @@ def run_engine(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import reference_model as R      # cpu_baseline leg: the one place this arm touches the oracle
         r = R.cpu_train_throughput(batch=args.cpu_batch, seq_len=S, steps=3, warmup=1)
         cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                "sample": f"3 steps of batch {args.cpu_batch} (BASELINE config 1) after 1 warm-up, fp32 torch CPU, "

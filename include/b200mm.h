@@ -71,7 +71,8 @@ int b200mm_gather_rows(const void* x, void* out, int rows, int D, long long stri
 int b200mm_scatter_rows(const void* dpooled, void* dx, long long M, int D, long long stride_rows,
                         long long offset_rows, float p_drop, unsigned long long seed, void* stream);
 
-/* ---- image tower support: BatchNorm2d (training / eval), pooling, conv lowering ($TV:108-163, :197-206, :266-280) */
+/* ---- image tower support: BatchNorm2d (training / eval), pooling, conv lowering ($TV:108-163, :197-206, :266-280)
+ * `scratch`: fp32 workspace of at least 18*C + 32 floats, zeroed by the call itself. */
 int b200mm_batchnorm_fwd(const void* x, const void* residual, long long M, int C, const float* gamma,
                          const float* beta, float eps, float momentum, int relu, void* out, float* mean_out,
                          float* rstd_out, float* running_mean, float* running_var, float* scratch, void* stream);

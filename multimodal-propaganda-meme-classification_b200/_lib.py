@@ -58,9 +58,22 @@ LAUNCHES = [0]
 _KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0}
 
 
-def call(name: str, *args) -> None:
+# optional per-call CUDA-event profile of a real (pipelined, warm-L2) run: PROFILE = [] enables it;
+# entries are (name, key, start_event, end_event).  See scripts/profile_step.py.
+PROFILE = None
+
+
+def call(name: str, *args, key=None) -> None:
     LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
-    rc = getattr(load(), name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args)
+        e1.record()
+        PROFILE.append((name, key, e0, e1))
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != 0:
         if rc > 0:
             raise B200MMError(f"{name}: CUDA error {rc}")

@@ -34,17 +34,23 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                      uint32_t box_inner, uint32_t box_outer) {
+                      uint32_t box_inner, uint32_t box_outer, uint32_t swizzle_bytes) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return B200MM_ERR_NO_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_bytes & 15) || box_inner * 2 > 128 || box_outer > 256)
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_bytes & 15) || box_inner * 2 > swizzle_bytes ||
+      box_outer > 256 || (swizzle_bytes != 128 && swizzle_bytes != 64))
     return B200MM_ERR_BAD_ARG;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
+  // 256-byte L2 promotion only when rows are 256-byte aligned: with e.g. the stem's 304-byte rows it makes every
+  // 128-byte box row fetch 256 bytes (2.5x DRAM over-fetch, measured 608 us instead of ~220 us on the stem GEMM)
+  const CUtensorMapL2promotion promo =
+      (row_stride_bytes % 256 == 0) ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? B200MM_OK : B200MM_ERR_TENSORMAP;
 }

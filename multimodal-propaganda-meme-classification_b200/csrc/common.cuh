@@ -37,7 +37,7 @@ const DeviceInfo& device_info();
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows `row_stride_bytes` apart,
 // box = box_inner x box_outer, SWIZZLE_128B (box_inner * 2 B must be <= 128 B), zero OOB fill.
 int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                      uint32_t box_inner, uint32_t box_outer);
+                      uint32_t box_inner, uint32_t box_outer, uint32_t swizzle_bytes = 128);
 
 // 3-D bf16 tensor map over [d2][d1][d0] (d0 contiguous), box = box0 x box1 x 1, SWIZZLE_128B.
 int make_tmap_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,

@@ -16,46 +16,85 @@ static int grid_for(long long work_items, int threads) {
   return static_cast<int>(want < 1 ? 1 : (want > max_ctas ? max_ctas : want));
 }
 
-// ------------------------------------------------------------------ BatchNorm2d (training mode)
-// Layout: x [M = N*H*W, C]; G = C/8 channel groups (power of two, <= 256); a CTA of 256 threads covers
-// 256/G rows per pass, thread (ty, g) owns channels g*8..g*8+7.
-__global__ void __launch_bounds__(256)
-bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta, float* __restrict__ sum,
-                float* __restrict__ sumsq) {
-  __shared__ float red[2][256][8];
-  const int G = C >> 3;
-  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
-  const long long r1 = min(r0 + rows_per_cta, M);
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r0 + ty; r < r1; r += rpp) {
-    float v[8];
-    load8(x + r * C + g * 8, v);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i] += v[i];
-      q[i] = fmaf(v[i], v[i], q[i]);
-    }
-  }
+// Column-reduction epilogue shared by the BatchNorm reductions.  Thread (ty, g) holds partial sums a[8], b[8] of
+// channels g*8..g*8+7.  (1) CTA-level reduction over ty in shared memory; (2) one fp32 atomic per channel and CTA
+// into one of BN_REPLICAS replica rows (CTA index mod R) -- spreading the same-address traffic that otherwise
+// saturates a handful of L2 atomic units (measured: 45 % of the kernel with a single row, 1184 CTAs);
+// (3) the last CTA to finish (ticket counter) sums the replicas into the final row.
+// scratch layout (floats): [R][2C] replicas | [2C] final | 1 ticket counter (all zeroed by the caller).
+constexpr int BN_REPLICAS = 8;
+__device__ __forceinline__ void column_reduce_finish(float (&red)[2][256][8], float (&a)[8], float (&b)[8], int G,
+                                                     int g, int ty, int rpp, int C, float* __restrict__ scratch) {
+  __shared__ unsigned int s_ticket;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    red[0][threadIdx.x][i] = s[i];
-    red[1][threadIdx.x][i] = q[i];
+    red[0][threadIdx.x][i] = a[i];
+    red[1][threadIdx.x][i] = b[i];
   }
   __syncthreads();
   if (ty == 0) {
     for (int t = 1; t < rpp; ++t)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        s[i] += red[0][t * G + g][i];
-        q[i] += red[1][t * G + g][i];
+        a[i] += red[0][t * G + g][i];
+        b[i] += red[1][t * G + g][i];
       }
+    float* rep = scratch + static_cast<size_t>(blockIdx.x % BN_REPLICAS) * 2 * C;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(sum + g * 8 + i, s[i]);
-      atomicAdd(sumsq + g * 8 + i, q[i]);
+      atomicAdd(rep + g * 8 + i, a[i]);
+      atomicAdd(rep + C + g * 8 + i, b[i]);
     }
   }
+  __threadfence();
+  __syncthreads();
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + static_cast<size_t>(BN_REPLICAS + 1) * 2 * C);
+  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1) {
+    __threadfence();
+    float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < BN_REPLICAS; ++r) t += __ldcg(scratch + static_cast<size_t>(r) * 2 * C + c);
+      fin[c] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm2d (training mode)
+// Layout: x [M = N*H*W, C]; G = C/8 channel groups (power of two, <= 256); a CTA of 256 threads covers
+// 256/G rows per pass, thread (ty, g) owns channels g*8..g*8+7.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
+                float* __restrict__ scratch) {
+  __shared__ float red[2][256][8];
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr int U = 8;  // independent 16-byte loads in flight per thread (the loop is latency-bound otherwise)
+  for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * rpp;
+      raw[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(x + rr * C + g * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v[8];
+      unpack8(raw[u], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += v[i];
+        q[i] = fmaf(v[i], v[i], q[i]);
+      }
+    }
+  }
+  column_reduce_finish(red, s, q, G, g, ty, rpp, C, scratch);
 }
 
 // out = act(x * scale + shift (+ residual)); CTA 0 also records mean / rstd and updates the running statistics
@@ -145,11 +184,11 @@ bn_eval_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 }
 
 // backward pass 1: dbeta = sum dz, dgamma = sum dz * xhat, dz = dout o (out > 0) when relu
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu,
-                     float* __restrict__ dgamma_sum, float* __restrict__ dbeta_sum) {
+                     float* __restrict__ scratch) {
   __shared__ float red[2][256][8];
   const int G = C >> 3;
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
@@ -162,46 +201,42 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
   float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r0 + ty; r < r1; r += rpp) {
-    float d[8], xv[8];
-    load8(dout + r * C + g * 8, d);
-    load8(x + r * C + g * 8, xv);
-    if (relu) {
-      float o[8];
-      load8(out + r * C + g * 8, o);
+  constexpr int U = 4;
+  for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
+    uint4 rd[U], rx[U], ro[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * rpp;
+      const bool ok = rr < r1;
+      const long long off = rr * C + g * 8;
+      rd[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dout + off)) : make_uint4(0, 0, 0, 0);
+      rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
+      ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sb[i] += d[i];
-      sg[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], sg[i]);
-    }
-  }
+    for (int u = 0; u < U; ++u) {
+      float d[8], xv[8];
+      unpack8(rd[u], d);
+      unpack8(rx[u], xv);
+      if (relu) {
+        float o[8];
+        unpack8(ro[u], o);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    red[0][threadIdx.x][i] = sg[i];
-    red[1][threadIdx.x][i] = sb[i];
-  }
-  __syncthreads();
-  if (ty == 0) {
-    for (int t = 1; t < rpp; ++t)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sg[i] += red[0][t * G + g][i];
-        sb[i] += red[1][t * G + g][i];
+        for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
       }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(dgamma_sum + g * 8 + i, sg[i]);
-      atomicAdd(dbeta_sum + g * 8 + i, sb[i]);
+      for (int i = 0; i < 8; ++i) {
+        sb[i] += d[i];
+        sg[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], sg[i]);
+      }
     }
   }
+  column_reduce_finish(red, sg, sb, G, g, ty, rpp, C, scratch);
 }
 
 // backward pass 2: dx = gamma * rstd * (dz - dbeta/M - xhat * dgamma/M); optional dz copy for the identity branch;
 // CTA 0 accumulates the parameter gradients.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                     const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -228,21 +263,37 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
-  for (long long r = r0 + ty; r < r1; r += rpp) {
-    float d[8], xv[8];
-    load8(dout + r * C + g * 8, d);
-    load8(x + r * C + g * 8, xv);
-    if (relu) {
-      float o[8];
-      load8(out + r * C + g * 8, o);
+  constexpr int U = 2;
+  for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
+    uint4 rd[U], rx[U], ro[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * rpp;
+      const bool ok = rr < r1;
+      const long long off = rr * C + g * 8;
+      rd[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dout + off)) : make_uint4(0, 0, 0, 0);
+      rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
+      ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
     }
-    if (dz_out != nullptr) store8(dz_out + r * C + g * 8, d);
-    float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = k0[i] * (d[i] - k1[i] - (xv[i] - mu[i]) * rs[i] * k2[i]);
-    store8(dx + r * C + g * 8, o);
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * rpp;
+      if (rr >= r1) break;
+      float d[8], xv[8];
+      unpack8(rd[u], d);
+      unpack8(rx[u], xv);
+      if (relu) {
+        float o[8];
+        unpack8(ro[u], o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+      }
+      if (dz_out != nullptr) store8(dz_out + rr * C + g * 8, d);
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = k0[i] * (d[i] - k1[i] - (xv[i] - mu[i]) * rs[i] * k2[i]);
+      store8(dx + rr * C + g * 8, o);
+    }
   }
 }
 
@@ -366,21 +417,30 @@ im2col_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, i
               int Ho, int Wo, __nv_bfloat16* __restrict__ cols) {
   const int G = C >> 3;
   const int taps = KH * KW;
-  const long long total = static_cast<long long>(N) * Ho * Wo * taps * G;
+  const long long total = static_cast<long long>(N) * Ho * Wo * G;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(i % G);
     long long t = i / G;
-    const int tap = static_cast<int>(t % taps); t /= taps;  // t = output pixel index m
     const long long m = t;
     const int wo = static_cast<int>(t % Wo); t /= Wo;
     const int ho = static_cast<int>(t % Ho);
     const int n = static_cast<int>(t / Ho);
-    const int hi = ho * stride - pad + tap / KW, wi = wo * stride - pad + tap % KW;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-      v = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + hi) * W + wi) * C + g * 8);
-    *reinterpret_cast<uint4*>(cols + (m * taps + tap) * C + g * 8) = v;
+    // all taps of this (pixel, 8-channel chunk): the loads are independent, issue them before the stores
+    for (int tap0 = 0; tap0 < taps; tap0 += 9) {
+      uint4 v[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int tap = tap0 + j;
+        const int hi = ho * stride - pad + tap / KW, wi = wo * stride - pad + tap % KW;
+        v[j] = make_uint4(0, 0, 0, 0);
+        if (tap < taps && hi >= 0 && hi < H && wi >= 0 && wi < W)
+          v[j] = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + hi) * W + wi) * C + g * 8));
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        if (tap0 + j < taps) *reinterpret_cast<uint4*>(cols + (m * taps + tap0 + j) * C + g * 8) = v[j];
+    }
   }
 }
 // dx[n,hi,wi,c] = sum over taps of dcols[m(ho,wo), tap, c] (+ addend)
@@ -400,17 +460,26 @@ col2im_kernel(const __nv_bfloat16* __restrict__ dcols, const __nv_bfloat16* __re
     const int n = static_cast<int>(t / H);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (addend != nullptr) load8(addend + pix * C + g * 8, acc);
-    for (int kh = 0; kh < KH; ++kh) {
-      const int th = hi + pad - kh;
-      if (th < 0 || th % stride || th / stride >= Ho) continue;
-      for (int kw = 0; kw < KW; ++kw) {
-        const int tw = wi + pad - kw;
-        if (tw < 0 || tw % stride || tw / stride >= Wo) continue;
-        const long long m = (static_cast<long long>(n) * Ho + th / stride) * Wo + tw / stride;
-        float v[8];
-        load8(dcols + (m * taps + kh * KW + kw) * C + g * 8, v);
+    for (int tap0 = 0; tap0 < taps; tap0 += 9) {
+      uint4 v[9];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      for (int j = 0; j < 9; ++j) {
+        const int tap = tap0 + j;
+        const int kh = tap / KW, kw = tap - kh * KW;
+        const int th = hi + pad - kh, tw = wi + pad - kw;
+        v[j] = make_uint4(0, 0, 0, 0);
+        if (tap < taps && th >= 0 && tw >= 0 && th % stride == 0 && tw % stride == 0 && th / stride < Ho &&
+            tw / stride < Wo) {
+          const long long m = (static_cast<long long>(n) * Ho + th / stride) * Wo + tw / stride;
+          v[j] = __ldg(reinterpret_cast<const uint4*>(dcols + (m * taps + tap) * C + g * 8));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        float f[8];
+        unpack8(v[j], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
       }
     }
     store8(dx + pix * C + g * 8, acc);
@@ -494,10 +563,12 @@ static bool bn_shape_ok(long long M, int C) {
   const int G = C >> 3;
   return M > 0 && C >= 8 && (C & 7) == 0 && G <= 256 && (G & (G - 1)) == 0;
 }
-static int bn_rows_per_cta(long long M, int C, int* grid) {
+// floats of scratch a BatchNorm launch needs: replicas + final row + ticket (rounded up)
+static size_t bn_scratch_floats(int C) { return static_cast<size_t>(BN_REPLICAS + 1) * 2 * C + 32; }
+static int bn_rows_per_cta(long long M, int C, int* grid, int ctas_per_sm = 8) {
   const DeviceInfo& dev = device_info();
   const int rpp = 256 / (C >> 3);
-  const long long target = static_cast<long long>(dev.num_sms > 0 ? dev.num_sms : 148) * 8;
+  const long long target = static_cast<long long>(dev.num_sms > 0 ? dev.num_sms : 148) * ctas_per_sm;
   long long rows = ceil_div(M, target);
   rows = ceil_div(rows, static_cast<long long>(rpp)) * rpp;
   *grid = static_cast<int>(ceil_div(M, rows));
@@ -509,7 +580,7 @@ static int bn_rows_per_cta(long long M, int C, int* grid) {
 using namespace b200;
 
 // Training-mode BatchNorm over x [M, C] (NHWC flattened): out = act(BN(x) (+ residual)).
-// scratch: fp32 [2*C] workspace (zeroed here).  mean_out / rstd_out: fp32 [C] saved for the backward.
+// scratch: fp32 workspace of at least 18*C + 32 floats (zeroed here).  mean_out / rstd_out: fp32 [C] saved for the backward.
 // running_mean / running_var (nullable) receive the momentum update.
 B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long long M, int C, const float* gamma,
                                     const float* beta, float eps, float momentum, int relu, void* out, float* mean_out,
@@ -517,14 +588,16 @@ B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long lo
                                     void* stream) {
   if (!bn_shape_ok(M, C)) return B200MM_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * C, s);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * bn_scratch_floats(C), s);
   if (e != cudaSuccess) return static_cast<int>(e);
-  int grid;
+  int grid, rgrid;
   const int rows = bn_rows_per_cta(M, C, &grid);
-  bn_stats_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), M, C, rows, scratch, scratch + C);
+  const int rrows = bn_rows_per_cta(M, C, &rgrid, 3);   // reductions: fewer, fatter CTAs (8 loads in flight / thread)
+  const float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;
+  bn_stats_kernel<<<rgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), M, C, rrows, scratch);
   B200MM_CHECK_LAUNCH();
   bn_apply_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
-                                       static_cast<const __nv_bfloat16*>(residual), M, C, rows, scratch, scratch + C,
+                                       static_cast<const __nv_bfloat16*>(residual), M, C, rows, fin, fin + C,
                                        gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out,
                                        rstd_out, running_mean, running_var);
   B200MM_CHECK_LAUNCH();
@@ -552,18 +625,20 @@ B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const voi
                                     void* dz_out, float* dgamma, float* dbeta, float* scratch, void* stream) {
   if (!bn_shape_ok(M, C) || (relu && out == nullptr)) return B200MM_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * C, s);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * bn_scratch_floats(C), s);
   if (e != cudaSuccess) return static_cast<int>(e);
-  int grid;
+  int grid, rgrid;
   const int rows = bn_rows_per_cta(M, C, &grid);
-  bn_bwd_reduce_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dout),
-                                            static_cast<const __nv_bfloat16*>(out),
-                                            static_cast<const __nv_bfloat16*>(x), M, C, rows, mean, rstd, relu,
-                                            scratch, scratch + C);
+  const int rrows = bn_rows_per_cta(M, C, &rgrid, 2);
+  const float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;
+  bn_bwd_reduce_kernel<<<rgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dout),
+                                             static_cast<const __nv_bfloat16*>(out),
+                                             static_cast<const __nv_bfloat16*>(x), M, C, rrows, mean, rstd, relu,
+                                             scratch);
   B200MM_CHECK_LAUNCH();
   bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(
       static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out),
-      static_cast<const __nv_bfloat16*>(x), M, C, rows, mean, rstd, gamma, relu, scratch, scratch + C,
+      static_cast<const __nv_bfloat16*>(x), M, C, rows, mean, rstd, gamma, relu, fin, fin + C,
       static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dz_out), dgamma, dbeta);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
@@ -613,7 +688,7 @@ B200MM_API int b200mm_im2col_nhwc(const void* x, int N, int H, int W, int C, int
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || KH <= 0 || KW <= 0 || stride <= 0 || pad < 0)
     return B200MM_ERR_BAD_ARG;
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  im2col_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * KH * KW * (C >> 3), 256), 256, 0,
+  im2col_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * (C >> 3), 256), 256, 0,
                   static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), N, H, W, C, KH, KW, stride,
                                                        pad, Ho, Wo, static_cast<__nv_bfloat16*>(cols));
   B200MM_CHECK_LAUNCH();

@@ -69,6 +69,16 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&x)[8]) {
     x[2 * i + 1] = f.y;
   }
 }
+__device__ __forceinline__ void unpack8(const uint4& r, float (&x)[8]) {
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+    const float2 f = __bfloat1622float2(v);
+    x[2 * i] = f.x;
+    x[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&x)[8]) {
   uint4 o;
   uint32_t* u = reinterpret_cast<uint32_t*>(&o);

@@ -82,7 +82,8 @@ def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residu
     _lib.call("b200mm_gemm_bf16", _p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, epi,
               _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
               _p(aux), aux.stride(0) if aux is not None else 0, _p(out), out.stride(0),
-              _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed), _s())
+              _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed), _s(),
+              key=(M, N, K, int(a_mn), int(b_mn), epi, splits))
     return out
 
 
@@ -254,15 +255,15 @@ def cast_to_bf16(x, y):
 
 # ----------------------------------------------------------------------------------------------- image tower pieces
 class BNScratch:
-    """fp32 [2*C] workspace shared by every BatchNorm launch of one device."""
+    """fp32 workspace (>= 18*C + 32 floats) shared by every BatchNorm launch of one device/stream."""
     _buf = {}
 
     @classmethod
     def get(cls, device, C):
         key = (device.index, torch.cuda.current_stream().cuda_stream)
         b = cls._buf.get(key)
-        if b is None or b.numel() < 2 * C:
-            b = torch.empty(max(2 * C, 8192), device=device, dtype=f32)
+        if b is None or b.numel() < 18 * C + 32:
+            b = torch.empty(max(18 * C + 32, 18 * 2048 + 32), device=device, dtype=f32)
             cls._buf[key] = b
         return b
 

@@ -1,0 +1,52 @@
+"""Micro-benchmark of individual ops at config-2 shapes (for ncu captures and quick A/B timing)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from b200mm import ops
+dev = torch.device("cuda:0")
+bf = torch.bfloat16
+which = sys.argv[1:] or ["bn", "col2im", "gemm"]
+def timeit(name, fn, bytes_=None, flops=None, iters=10):
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    for _ in range(2): fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()   # evict L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    s = f"{name:44s} {ms*1e3:8.1f} us"
+    if bytes_: s += f"  {bytes_/ms/1e6:7.0f} GB/s"
+    if flops: s += f"  {flops/ms/1e9:7.0f} TF/s"
+    print(s, flush=True)
+if "bn" in which:
+    for (M, C) in [(802816, 64), (802816, 256), (200704, 512), (50176, 1024), (12544, 2048)]:
+        x = torch.randn(M, C, device=dev).to(bf); g = torch.ones(C, device=dev); b = torch.zeros(C, device=dev)
+        rm = torch.zeros(C, device=dev); rv = torch.ones(C, device=dev)
+        out, mean, rstd = ops.batchnorm_fwd(x, g, b, rm, rv)
+        timeit(f"bn_fwd  [{M},{C}]", lambda: ops.batchnorm_fwd(x, g, b, rm, rv), bytes_=3 * M * C * 2)
+        dout = torch.randn(M, C, device=dev).to(bf); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
+        timeit(f"bn_bwd  [{M},{C}]", lambda: ops.batchnorm_bwd(dout, out, x, mean, rstd, g, dg, db), bytes_=7 * M * C * 2)
+if "col2im" in which:
+    for (N, H, C, s) in [(256, 56, 64, 1), (256, 56, 128, 2), (256, 14, 256, 1)]:
+        Ho = H // s
+        dcols = torch.randn(N * Ho * Ho, 9 * C, device=dev).to(bf)
+        x = torch.randn(N * H * H, C, device=dev).to(bf)
+        timeit(f"col2im N{N} H{H} C{C} s{s}", lambda: ops.col2im(dcols, N, H, H, C, 3, s, 1), bytes_=dcols.numel() * 2 + N * H * H * C * 2)
+        timeit(f"im2col N{N} H{H} C{C} s{s}", lambda: ops.im2col(x, N, H, H, C, 3, s, 1), bytes_=dcols.numel() * 2 + N * H * H * C * 2)
+    img = torch.randn(256, 3, 224, 224, device=dev)
+    timeit("im2col_nchw stem", lambda: ops.im2col_nchw_f32(img, 7, 2, 3, 152), bytes_=img.numel() * 4 + 256 * 112 * 112 * 152 * 2)
+    a0 = torch.randn(256 * 112 * 112, 64, device=dev).to(bf)
+    timeit("maxpool_fwd", lambda: ops.maxpool_fwd(a0, 256, 112, 112, 64), bytes_=a0.numel() * 2 * 1.375)
+if "gemm" in which:
+    for (M, N, K, b_mn, epi) in [(32768, 3072, 768, 0, 1), (32768, 3072, 768, 1, 2), (32768, 2304, 768, 0, 0), (32768, 768, 768, 0, 0),
+                                 (802816, 256, 64, 0, 0), (802816, 576, 64, 1, 0), (802816, 64, 576, 0, 0), (200704, 1152, 128, 1, 0),
+                                 (3211264, 64, 152, 0, 0), (50176, 2304, 256, 1, 0), (8192, 8192, 8192, 0, 0)]:
+        A = torch.randn(M, K, device=dev).to(bf)
+        Bm = torch.randn(N, K, device=dev).to(bf) if not b_mn else torch.randn(K, N, device=dev).to(bf)
+        out = torch.empty(M, N, device=dev, dtype=bf); out2 = torch.empty(M, N, device=dev, dtype=bf) if epi == 1 else None
+        aux = torch.randn(M, N, device=dev).to(bf) if epi == 2 else None
+        bias = torch.zeros(N, device=dev)
+        timeit(f"gemm M{M} N{N} K{K} b_mn{b_mn} epi{epi}", lambda: ops.gemm_raw(A, False, Bm, bool(b_mn), M, N, K, out, epi=epi, bias=bias, aux=aux, out2=out2),
+               flops=2.0 * M * N * K, bytes_=2.0 * (M * K + N * K + M * N * (2 if epi == 1 else 1) + (M * N if epi == 2 else 0)))

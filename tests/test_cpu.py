@@ -279,3 +279,32 @@ def test_bench_reference_arm_contract():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ------------------------------------------------------------------------------------------------- bf16 emulation oracle
+def test_bf16_emulation_oracle_rounds_only_inside_context():
+    """oracle/bf16_emulation.py: hooks are installed only inside the context, weights become bf16-representable,
+    and the emulated forward stays within bf16-level distance of the fp32 one for the shallow tiny network."""
+    from oracle import bf16_emulation as E
+    from oracle import reference_model as R
+    cfg = R.TowerConfig.tiny()
+    torch.manual_seed(0)
+    m = R.zero_dropout(R.MultimodalClassifier(2, cfg)).eval()
+    E.round_gemm_weights_(m)
+    w = m.resnet.layer1[0].conv1.weight
+    assert torch.equal(w, w.to(torch.bfloat16).float())
+    assert not torch.equal(m.output_fc.weight, m.output_fc.weight.to(torch.bfloat16).float())   # stays fp32
+    d = R.synthetic_batch(4, 16, cfg)
+    with torch.no_grad():
+        a = m(d["text"], d["image"], d["text_mask"])
+        with E.bf16_storage(m):
+            b = m(d["text"], d["image"], d["text_mask"])
+        c = m(d["text"], d["image"], d["text_mask"])
+    assert torch.equal(a, c)                       # hooks removed
+    err = ((a - b).norm() / a.norm()).item()
+    assert 0 < err < 3e-2
+    # gradients flow through the rounding (straight-through)
+    m.train()
+    with E.bf16_storage(m):
+        m(d["text"], d["image"], d["text_mask"]).sum().backward()
+    assert m.resnet.conv1.weight.grad is not None and m.bert.embeddings.word_embeddings.weight.grad is not None
