@@ -444,6 +444,52 @@ im2col_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, i
   }
 }
 // dx[n,hi,wi,c] = sum over taps of dcols[m(ho,wo), tap, c] (+ addend)
+// 3x3 / pad 1 fast path, stride as a template parameter (no integer divisions in the tap loop), all 9 gathers of a
+// thread issued before the first use.
+template <int STRIDE>
+__global__ void __launch_bounds__(256, 3)
+col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcols, const __nv_bfloat16* __restrict__ addend, int N, int H,
+                 int W, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  const int G = C >> 3;
+  const long long total = static_cast<long long>(N) * H * W * G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long t = i / G;
+    const long long pix = t;
+    const int wi = static_cast<int>(t % W); t /= W;
+    const int hi = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    const long long img_base = static_cast<long long>(n) * Ho * Wo;
+    uint4 v[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int th = hi + 1 - kh;
+      const bool hok = th >= 0 && (STRIDE == 1 || (th & 1) == 0) && (th / STRIDE) < Ho;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tw = wi + 1 - kw;
+        const bool ok = hok && tw >= 0 && (STRIDE == 1 || (tw & 1) == 0) && (tw / STRIDE) < Wo;
+        v[kh * 3 + kw] = make_uint4(0, 0, 0, 0);
+        if (ok) {
+          const long long m = img_base + static_cast<long long>(th / STRIDE) * Wo + tw / STRIDE;
+          v[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(dcols + (m * 9 + kh * 3 + kw) * C + g * 8));
+        }
+      }
+    }
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (addend != nullptr) load8(addend + pix * C + g * 8, acc);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      float f[8];
+      unpack8(v[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+    store8(dx + pix * C + g * 8, acc);
+  }
+}
+// generic fallback (any kernel size / stride / padding)
 __global__ void __launch_bounds__(256)
 col2im_kernel(const __nv_bfloat16* __restrict__ dcols, const __nv_bfloat16* __restrict__ addend, int N, int H, int W,
               int C, int KH, int KW, int stride, int pad, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
@@ -460,61 +506,67 @@ col2im_kernel(const __nv_bfloat16* __restrict__ dcols, const __nv_bfloat16* __re
     const int n = static_cast<int>(t / H);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (addend != nullptr) load8(addend + pix * C + g * 8, acc);
-    for (int tap0 = 0; tap0 < taps; tap0 += 9) {
-      uint4 v[9];
+    for (int kh = 0; kh < KH; ++kh) {
+      const int th = hi + pad - kh;
+      if (th < 0 || th % stride || th / stride >= Ho) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int tw = wi + pad - kw;
+        if (tw < 0 || tw % stride || tw / stride >= Wo) continue;
+        const long long m = (static_cast<long long>(n) * Ho + th / stride) * Wo + tw / stride;
+        float v[8];
+        load8(dcols + (m * taps + kh * KW + kw) * C + g * 8, v);
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        const int tap = tap0 + j;
-        const int kh = tap / KW, kw = tap - kh * KW;
-        const int th = hi + pad - kh, tw = wi + pad - kw;
-        v[j] = make_uint4(0, 0, 0, 0);
-        if (tap < taps && th >= 0 && tw >= 0 && th % stride == 0 && tw % stride == 0 && th / stride < Ho &&
-            tw / stride < Wo) {
-          const long long m = (static_cast<long long>(n) * Ho + th / stride) * Wo + tw / stride;
-          v[j] = __ldg(reinterpret_cast<const uint4*>(dcols + (m * taps + tap) * C + g * 8));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        float f[8];
-        unpack8(v[j], f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
       }
     }
     store8(dx + pix * C + g * 8, acc);
   }
 }
 // Stem lowering straight from the fp32 NCHW image the reference's DataLoader yields:
-// cols[m, (kh*KW+kw)*Cin + c] (row length Kp >= KH*KW*Cin, zero padded)
+// cols[m, (kh*KW+kw)*Cin + c] (row length Kp >= KH*KW*Cin, zero padded).
+// One CTA per output row (n, ho): the KH x Cin input rows it needs are staged in shared memory with coalesced reads
+// (as bf16), then the Wo x Kp output row block -- contiguous in memory -- is written with 16-byte stores.
 __global__ void __launch_bounds__(256)
 im2col_nchw_f32_kernel(const float* __restrict__ img, int N, int Cin, int H, int W, int KH, int KW, int stride,
                        int pad, int Ho, int Wo, int Kp, __nv_bfloat16* __restrict__ cols) {
-  const int chunks = Kp >> 3;
+  extern __shared__ uint8_t smem_raw[];
+  const int Wp = W + 2 * pad;
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [KH][Cin][Wp]
+  int* lut = reinterpret_cast<int*>(smem_raw + ((static_cast<size_t>(KH) * Cin * Wp * 2 + 15) & ~size_t(15)));  // [Kp]
+  const int n = blockIdx.x / Ho, ho = blockIdx.x - n * Ho;
   const int K = KH * KW * Cin;
-  const long long total = static_cast<long long>(N) * Ho * Wo * chunks;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int ch = static_cast<int>(i % chunks);
-    long long t = i / chunks;
-    const long long m = t;
-    const int wo = static_cast<int>(t % Wo); t /= Wo;
-    const int ho = static_cast<int>(t % Ho);
-    const int n = static_cast<int>(t / Ho);
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int kk = ch * 8 + k;
-      float val = 0.f;
-      if (kk < K) {
-        const int c = kk % Cin, tap = kk / Cin;
-        const int hi = ho * stride - pad + tap / KW, wi = wo * stride - pad + tap % KW;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W)
-          val = __ldg(img + ((static_cast<long long>(n) * Cin + c) * H + hi) * W + wi);
-      }
-      v[k] = val;
+  for (int idx = threadIdx.x; idx < KH * Cin * Wp; idx += blockDim.x) {
+    const int wp = idx % Wp;
+    const int c = (idx / Wp) % Cin;
+    const int kh = idx / (Wp * Cin);
+    const int hi = ho * stride - pad + kh, wi = wp - pad;
+    float v = 0.f;
+    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(img + ((static_cast<long long>(n) * Cin + c) * H + hi) * W + wi);
+    tile[idx] = __float2bfloat16(v);
+  }
+  for (int kk = threadIdx.x; kk < Kp; kk += blockDim.x) {
+    int off = -1;
+    if (kk < K) {
+      const int c = kk % Cin, tap = kk / Cin;
+      off = ((tap / KW) * Cin + c) * Wp + tap % KW;
     }
-    store8(cols + m * Kp + ch * 8, v);
+    lut[kk] = off;
+  }
+  __syncthreads();
+  const int chunks = Kp >> 3;
+  __nv_bfloat16* out = cols + (static_cast<long long>(n) * Ho + ho) * Wo * Kp;
+  for (int idx = threadIdx.x; idx < Wo * chunks; idx += blockDim.x) {
+    const int wo = idx / chunks, ch = idx - wo * chunks;
+    const int base = wo * stride;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int o0 = lut[ch * 8 + 2 * k], o1 = lut[ch * 8 + 2 * k + 1];
+      const uint16_t lo = o0 >= 0 ? *reinterpret_cast<const uint16_t*>(tile + o0 + base) : uint16_t(0);
+      const uint16_t hi = o1 >= 0 ? *reinterpret_cast<const uint16_t*>(tile + o1 + base) : uint16_t(0);
+      w[k] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<long long>(wo) * Kp + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 // spatial subsampling for stride-2 1x1 convolutions: out[n,ho,wo,:] = x[n,ho*s,wo*s,:]; and its transpose (zero fill)
@@ -699,10 +751,17 @@ B200MM_API int b200mm_col2im_nhwc(const void* dcols, const void* addend, int N, 
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || KH <= 0 || KW <= 0 || stride <= 0 || pad < 0)
     return B200MM_ERR_BAD_ARG;
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  col2im_kernel<<<grid_for(static_cast<long long>(N) * H * W * (C >> 3), 256), 256, 0,
-                  static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dcols),
-                                                       static_cast<const __nv_bfloat16*>(addend), N, H, W, C, KH, KW,
-                                                       stride, pad, Ho, Wo, static_cast<__nv_bfloat16*>(dx));
+  const int grid = grid_for(static_cast<long long>(N) * H * W * (C >> 3), 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* dc = static_cast<const __nv_bfloat16*>(dcols);
+  const __nv_bfloat16* ad = static_cast<const __nv_bfloat16*>(addend);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dx);
+  if (KH == 3 && KW == 3 && pad == 1 && stride == 1)
+    col2im3x3_kernel<1><<<grid, 256, 0, s>>>(dc, ad, N, H, W, C, Ho, Wo, o);
+  else if (KH == 3 && KW == 3 && pad == 1 && stride == 2)
+    col2im3x3_kernel<2><<<grid, 256, 0, s>>>(dc, ad, N, H, W, C, Ho, Wo, o);
+  else
+    col2im_kernel<<<grid, 256, 0, s>>>(dc, ad, N, H, W, C, KH, KW, stride, pad, Ho, Wo, o);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -712,9 +771,10 @@ B200MM_API int b200mm_im2col_nchw_f32(const float* img, int N, int Cin, int H, i
       Kp < KH * KW * Cin)
     return B200MM_ERR_BAD_ARG;
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  im2col_nchw_f32_kernel<<<grid_for(static_cast<long long>(N) * Ho * Wo * (Kp >> 3), 256), 256, 0,
-                           static_cast<cudaStream_t>(stream)>>>(img, N, Cin, H, W, KH, KW, stride, pad, Ho, Wo, Kp,
-                                                                static_cast<__nv_bfloat16*>(cols));
+  const size_t smem = ((static_cast<size_t>(KH) * Cin * (W + 2 * pad) * 2 + 15) & ~size_t(15)) + sizeof(int) * Kp;
+  if (smem > 48 * 1024) return B200MM_ERR_BAD_ARG;
+  im2col_nchw_f32_kernel<<<N * Ho, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      img, N, Cin, H, W, KH, KW, stride, pad, Ho, Wo, Kp, static_cast<__nv_bfloat16*>(cols));
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

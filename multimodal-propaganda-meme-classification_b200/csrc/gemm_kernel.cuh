@@ -1,0 +1,381 @@
+// bf16 GEMM on the 5th-generation tensor cores: D[M,N] = A x B with fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer   : cp.async.bulk.tensor -> STAGES-deep smem ring (SWIZZLE_128B)
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warps 2..9  epilogue       : tcgen05.ld accumulator -> bias / GELU / dGELU / residual -> global
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Both operands may be K-major ("row-major with the reduction dim contiguous")
+// or MN-major (reduction dim strided) -- this is what lets the same kernel serve
+//   forward   Y  = X  W^T      (A K-major,  B K-major)      reference: nn.Linear / 1x1 conv / im2col conv
+//   dgrad     dX = dY W        (A K-major,  B MN-major)
+//   wgrad     dW = dY^T X      (A MN-major, B MN-major, split-K over the token dim, fp32 red.add)
+// without transposing anything in HBM.
+//
+// Replaces: the cuBLASLt calls behind
+// transformers/models/distilbert/modeling_distilbert.py q_lin/k_lin/v_lin/out_lin/lin1/lin2 and the
+// cuDNN convolutions behind torchvision/models/resnet.py, as driven by
+// example_scripts/Multimodal_example_task2C.txt:172-197.
+#pragma once
+#include "common.cuh"
+#include "device_utils.cuh"
+#include "ptx.cuh"
+#include "gemm_params.cuh"
+
+namespace b200 {
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  // ring depth that fits next to `nbuf` staging boxes per epilogue warp and the barrier block
+  static constexpr int stages_for(int nbuf) {
+    const int avail = GEMM_SMEM_TOTAL - GEMM_EPI_WARPS * nbuf * GEMM_BOX_BYTES - 512;
+    const int s = avail / STAGE_BYTES;
+    return s > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : s;
+  }
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  const int STAGES = p.num_stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (STAGE_BYTES is a multiple of 1024)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_WARPS * p.nbuf * GEMM_BOX_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int num_work = tiles_mn * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w / tiles_mn;
+        const int t = w - split * tiles_mn;
+        const int m_blk = t / p.n_tiles;
+        const int n_blk = t - m_blk * p.n_tiles;
+        const int k_begin = split * p.k_iters_per_split;
+        const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < GEMM_BM / 64; ++j)
+              tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + j * 64, kb * GEMM_BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * GEMM_BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, p.a_mn, p.b_mn);
+      // K-major: 16-element k step = 32 B inside the swizzle row; 8-row groups 1024 B apart.
+      // MN-major: 16-element k step = two 8-k-row groups = 2048 B; 64-wide MN atoms one 8 KB box apart.
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w / tiles_mn;
+        const int k_begin = split * p.k_iters_per_split;
+        const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    // bf16 outputs: TMEM -> registers -> (bias / activation / residual) -> 128B-swizzled smem box -> TMA store
+    // (fully coalesced global writes, rows/columns beyond M/N clipped by the tensor map).
+    // fp32 outputs (wgrad): direct vector stores / red.global.add straight from registers.
+    // The mode is a template parameter: one lean instruction stream per epilogue (the all-modes-in-one version was
+    // 4096 SASS instructions, missed the instruction cache and issue-bound the short-K convolution GEMMs).
+    const int ew = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = ew >> 2;              // which half of the BN columns
+    constexpr int HALF_COLS = BN / 2;
+    constexpr bool BF16_OUT = EPI != EPI_F32 && EPI != EPI_F32_ATOMIC;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    const bool has_bias = p.bias != nullptr;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int split = w / tiles_mn;
+      const int t = w - split * tiles_mn;
+      const int m_blk = t / p.n_tiles;
+      const int n_blk = t - m_blk * p.n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const long long row = static_cast<long long>(m_blk) * GEMM_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      if constexpr (BF16_OUT) {
+        constexpr int BOX_W = HALF_COLS < 64 ? HALF_COLS : 64;   // columns per staged box: 64 (SW128) or 32 (SW64)
+        constexpr int BOXES = HALF_COLS / BOX_W;
+        constexpr int CHUNKS_PER_BOX = BOX_W / 32;
+        constexpr int PASSES = EPI == EPI_GELU ? 2 : 1;
+        uint8_t* stage_base = staging + ew * (p.nbuf * GEMM_BOX_BYTES);
+        const __nv_bfloat16* res_row = nullptr;
+        if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP)
+          if (p.residual != nullptr && row_ok) res_row = p.residual + row * p.ldr;
+        const __nv_bfloat16* aux_row = nullptr;
+        if constexpr (EPI == EPI_DGELU)
+          if (row_ok) aux_row = p.aux + row * p.ld_aux;
+#pragma unroll 1
+        for (int b = 0; b < BOXES; ++b) {
+          const int box_col_in_tile = half * HALF_COLS + b * BOX_W;
+          const int box_col0 = n_blk * BN + box_col_in_tile;
+          if (box_col0 >= p.N) break;
+#pragma unroll 1
+          for (int pass = 0; pass < PASSES; ++pass) {
+            // the store issued from this buffer `nbuf` boxes ago has left shared memory
+            if (lane == 0) {
+              if (p.nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+            }
+            __syncwarp();
+            uint8_t* stage_buf = stage_base + buf * GEMM_BOX_BYTES;
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS_PER_BOX; ++c) {
+              uint32_t v[32];
+              tmem_ld32(t_base + box_col_in_tile + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const int col = box_col0 + c * 32 + g * 8;
+                const bool col_ok = col < p.N;
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+                if (has_bias && col_ok) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                  x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                  x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                }
+                if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP) {
+                  if constexpr (EPI == EPI_STORE_DROP) {
+                    const uint64_t gi = static_cast<uint64_t>(row * p.N + col) >> 2;
+                    const uint32_t k0 = dropout_keep4(p.seed, gi, p.drop_threshold);
+                    const uint32_t k1 = dropout_keep4(p.seed, gi + 1, p.drop_threshold);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      x[i] = (k0 >> i) & 1 ? x[i] * p.inv_keep : 0.f;
+                      x[4 + i] = (k1 >> i) & 1 ? x[4 + i] * p.inv_keep : 0.f;
+                    }
+                  }
+                  if (res_row != nullptr && col_ok) {
+                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(res_row + col));
+                    const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
+                                 r3 = unpack_bf16x2(r.w);
+                    x[0] += r0.x; x[1] += r0.y; x[2] += r1.x; x[3] += r1.y;
+                    x[4] += r2.x; x[5] += r2.y; x[6] += r3.x; x[7] += r3.y;
+                  }
+                  if constexpr (EPI == EPI_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+                  }
+                }
+                if constexpr (EPI == EPI_DGELU) {
+                  if (aux_row != nullptr && col_ok) {
+                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(aux_row + col));
+                    const float2 z0 = unpack_bf16x2(r.x), z1 = unpack_bf16x2(r.y), z2 = unpack_bf16x2(r.z),
+                                 z3 = unpack_bf16x2(r.w);
+                    x[0] *= gelu_erf_grad(z0.x); x[1] *= gelu_erf_grad(z0.y);
+                    x[2] *= gelu_erf_grad(z1.x); x[3] *= gelu_erf_grad(z1.y);
+                    x[4] *= gelu_erf_grad(z2.x); x[5] *= gelu_erf_grad(z2.y);
+                    x[6] *= gelu_erf_grad(z3.x); x[7] *= gelu_erf_grad(z3.y);
+                  }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
+                o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
+                if constexpr (EPI == EPI_GELU) {
+                  if (pass == 1) {
+                    // activation of the STORED (bf16-rounded) pre-activation: forward and backward see the same z
+                    const float2 z0 = unpack_bf16x2(o.x), z1 = unpack_bf16x2(o.y), z2 = unpack_bf16x2(o.z),
+                                 z3 = unpack_bf16x2(o.w);
+                    o.x = pack_bf16x2(gelu_erf(z0.x), gelu_erf(z0.y));
+                    o.y = pack_bf16x2(gelu_erf(z1.x), gelu_erf(z1.y));
+                    o.z = pack_bf16x2(gelu_erf(z2.x), gelu_erf(z2.y));
+                    o.w = pack_bf16x2(gelu_erf(z3.x), gelu_erf(z3.y));
+                  }
+                }
+                const int cc = c * 4 + g;  // 16-byte chunk index inside the staged row
+                const uint32_t off = BOX_W == 64 ? lane * 128 + ((cc ^ (lane & 7)) << 4)
+                                                 : lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4);
+                *reinterpret_cast<uint4*>(stage_buf + off) = o;
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(pass == 0 ? &tma_out : &tma_out2, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
+              tma_store_commit();
+            }
+            if (++buf == p.nbuf) buf = 0;
+          }
+        }
+      } else {
+        constexpr int CHUNK = HALF_COLS < 32 ? HALF_COLS : 32;
+#pragma unroll 1
+        for (int c = 0; c < HALF_COLS / CHUNK; ++c) {
+          const int col_in_tile = half * HALF_COLS + c * CHUNK;
+          uint32_t v[32];
+          tmem_ld32(t_base + col_in_tile, v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BN + col_in_tile;
+          if (row_ok && col0 < p.N) {
+#pragma unroll
+            for (int g = 0; g < CHUNK / 8; ++g) {
+              const int col = col0 + g * 8;
+              if (col >= p.N) break;
+              float x[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
+              float* o = static_cast<float*>(p.out) + row * p.ldc + col;
+              if constexpr (EPI == EPI_F32) {
+                if (has_bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                  x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                  x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                }
+                *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              } else {  // EPI_F32_ATOMIC
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(x[0]), "f"(x[1]), "f"(x[2]),
+                             "f"(x[3])
+                             : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 4), "f"(x[4]), "f"(x[5]),
+                             "f"(x[6]), "f"(x[7])
+                             : "memory");
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (BF16_OUT) {
+      if (lane == 0) tma_store_wait<0>();   // smem must outlive the last bulk store
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// Launch one (BN, EPI) instantiation.  Shared memory split: `stages` ring slots + `nbuf` staging boxes per epilogue warp.
+template <int BN, int EPI>
+static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                            GemmParams p, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GEMM_SMEM_TOTAL + 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  // long-K tiles live in the main loop: deepest ring, one staging box; short-K tiles are store-bound: two boxes
+  const int k_per_tile = p.k_iters_per_split;
+  p.nbuf = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 0 : (k_per_tile >= 8 ? 1 : 2);   // fp32 modes do not stage
+  p.num_stages = Cfg::stages_for(p.nbuf);
+  static_assert(GemmCfg<BN>::stages_for(2) >= 2, "ring too shallow");
+  gemm_bf16_kernel<BN, EPI><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL + 1024, stream>>>(ta, tb, to, to2, p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? B200MM_OK : static_cast<int>(e);
+}
+
+template <int BN>
+int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                   const GemmParams& p, int grid, cudaStream_t stream) {
+  switch (p.epi) {
+    case EPI_STORE:
+      if (p.p_drop > 0.f) return launch_gemm_inst<BN, EPI_STORE_DROP>(ta, tb, to, to2, p, grid, stream);
+      return launch_gemm_inst<BN, EPI_STORE>(ta, tb, to, to2, p, grid, stream);
+    case EPI_GELU: return launch_gemm_inst<BN, EPI_GELU>(ta, tb, to, to2, p, grid, stream);
+    case EPI_DGELU: return launch_gemm_inst<BN, EPI_DGELU>(ta, tb, to, to2, p, grid, stream);
+    case EPI_F32: return launch_gemm_inst<BN, EPI_F32>(ta, tb, to, to2, p, grid, stream);
+    case EPI_F32_ATOMIC: return launch_gemm_inst<BN, EPI_F32_ATOMIC>(ta, tb, to, to2, p, grid, stream);
+    default: return launch_gemm_inst<BN, EPI_RELU>(ta, tb, to, to2, p, grid, stream);
+  }
+}
+
+}  // namespace b200

@@ -16,364 +16,19 @@
 // transformers/models/distilbert/modeling_distilbert.py q_lin/k_lin/v_lin/out_lin/lin1/lin2 and the
 // cuDNN convolutions behind torchvision/models/resnet.py, as driven by
 // example_scripts/Multimodal_example_task2C.txt:172-197.
-#include "common.cuh"
+#include "gemm_params.cuh"
 #include "device_utils.cuh"
-#include "ptx.cuh"
 
 namespace b200 {
-
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;              // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
-constexpr int GEMM_STAGE_BUFS = 2;  // staging boxes per epilogue warp: a TMA store is never waited on by the next box
-constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGE_BUFS * 4096;  // box = [32 rows x 64 cols] bf16
-constexpr int GEMM_SMEM_BUDGET = 227 * 1024 - GEMM_STAGING_BYTES - 2048;  // operand ring
-
-enum EpiMode : int {
-  EPI_STORE = 0,       // out = bf16(acc + bias + residual)
-  EPI_GELU = 1,        // out = bf16(z = acc + bias); out2 = bf16(gelu(z))
-  EPI_DGELU = 2,       // out = bf16(acc * gelu'(aux))
-  EPI_F32 = 3,         // out_f32 = acc + bias
-  EPI_F32_ATOMIC = 4,  // out_f32 += acc        (split-K partial sums)
-  EPI_RELU = 5,        // out = bf16(max(acc + bias + residual, 0))
-};
-
-struct GemmParams {
-  int M, N, K;
-  int a_mn, b_mn;  // operand majorness flags (0 = K-major, 1 = MN-major)
-  int m_tiles, n_tiles, splits, k_iters, k_iters_per_split;
-  int epi;
-  const float* bias;
-  const __nv_bfloat16* residual;
-  long long ldr;
-  const __nv_bfloat16* aux;
-  long long ld_aux;
-  void* out;
-  long long ldc;
-  __nv_bfloat16* out2;
-  long long ld2;
-  // EPI_STORE only: inverted dropout on (acc + bias) before the residual add, mask keyed by (seed, row * N + col)
-  float p_drop;
-  uint32_t drop_threshold;
-  float inv_keep;
-  unsigned long long seed;
-};
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = GEMM_SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : GEMM_SMEM_BUDGET / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
-                 const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (STAGE_BYTES is a multiple of 1024)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + GEMM_STAGING_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int tiles_mn = p.m_tiles * p.n_tiles;
-  const int num_work = tiles_mn * p.splits;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int split = w / tiles_mn;
-        const int t = w - split * tiles_mn;
-        const int m_blk = t / p.n_tiles;
-        const int n_blk = t - m_blk * p.n_tiles;
-        const int k_begin = split * p.k_iters_per_split;
-        const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
-        for (int kb = k_begin; kb < k_end; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
-          } else {
-#pragma unroll
-            for (int j = 0; j < GEMM_BM / 64; ++j)
-              tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + j * 64, kb * GEMM_BK);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
-          } else {
-#pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n_blk * BN + j * 64, kb * GEMM_BK);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, p.a_mn, p.b_mn);
-      // K-major: 16-element k step = 32 B inside the swizzle row; 8-row groups 1024 B apart.
-      // MN-major: 16-element k step = two 8-k-row groups = 2048 B; 64-wide MN atoms one 8 KB box apart.
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
-      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int split = w / tiles_mn;
-        const int k_begin = split * p.k_iters_per_split;
-        const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = k_begin; kb < k_end; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = umma_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps
-    // bf16 outputs: TMEM -> registers -> (bias / activation / residual) -> 128B-swizzled smem box -> TMA store
-    // (fully coalesced global writes, rows/columns beyond M/N clipped by the tensor map).
-    // fp32 outputs (wgrad): direct vector stores / red.global.add straight from registers.
-    const int ew = warp - 2;
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;              // which half of the BN columns
-    constexpr int HALF_COLS = BN / 2;
-    constexpr int BOX_W = HALF_COLS < 64 ? HALF_COLS : 64;   // columns per staged box: 64 (SW128) or 32 (SW64)
-    constexpr int BOXES = HALF_COLS / BOX_W;
-    constexpr int CHUNKS_PER_BOX = BOX_W / 32;
-    uint8_t* stage_base = staging + ew * (GEMM_STAGE_BUFS * 4096);
-    int buf = 0;
-    const bool bf16_out = p.epi != EPI_F32 && p.epi != EPI_F32_ATOMIC;
-    const int passes = p.epi == EPI_GELU ? 2 : 1;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int split = w / tiles_mn;
-      const int t = w - split * tiles_mn;
-      const int m_blk = t / p.n_tiles;
-      const int n_blk = t - m_blk * p.n_tiles;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after_sync();
-      const long long row = static_cast<long long>(m_blk) * GEMM_BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      if (bf16_out) {
-#pragma unroll 1
-        for (int b = 0; b < BOXES; ++b) {
-          const int box_col_in_tile = half * HALF_COLS + b * BOX_W;
-          const int box_col0 = n_blk * BN + box_col_in_tile;
-          if (box_col0 >= p.N) break;
-#pragma unroll 1
-          for (int pass = 0; pass < passes; ++pass) {
-            // the store issued from this buffer GEMM_STAGE_BUFS boxes ago has left shared memory
-            if (lane == 0) tma_store_wait_read<GEMM_STAGE_BUFS - 1>();
-            __syncwarp();
-            uint8_t* stage_buf = stage_base + buf * 4096;
-#pragma unroll
-            for (int c = 0; c < CHUNKS_PER_BOX; ++c) {
-              uint32_t v[32];
-              tmem_ld32(t_base + box_col_in_tile + c * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const int col = box_col0 + c * 32 + g * 8;
-                const bool col_ok = col < p.N;
-                float x[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
-                if (p.bias != nullptr && col_ok) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                  x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                  x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                }
-                if (p.epi == EPI_STORE || p.epi == EPI_RELU) {
-                  if (p.p_drop > 0.f) {
-                    const uint64_t gi = static_cast<uint64_t>(row * p.N + col) >> 2;
-                    const uint32_t k0 = dropout_keep4(p.seed, gi, p.drop_threshold);
-                    const uint32_t k1 = dropout_keep4(p.seed, gi + 1, p.drop_threshold);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      x[i] = (k0 >> i) & 1 ? x[i] * p.inv_keep : 0.f;
-                      x[4 + i] = (k1 >> i) & 1 ? x[4 + i] * p.inv_keep : 0.f;
-                    }
-                  }
-                  if (p.residual != nullptr && row_ok && col_ok) {
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col));
-                    const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
-                                 r3 = unpack_bf16x2(r.w);
-                    x[0] += r0.x; x[1] += r0.y; x[2] += r1.x; x[3] += r1.y;
-                    x[4] += r2.x; x[5] += r2.y; x[6] += r3.x; x[7] += r3.y;
-                  }
-                  if (p.epi == EPI_RELU) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-                  }
-                } else if (p.epi == EPI_DGELU) {
-                  if (row_ok && col_ok) {
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.aux + row * p.ld_aux + col));
-                    const float2 z0 = unpack_bf16x2(r.x), z1 = unpack_bf16x2(r.y), z2 = unpack_bf16x2(r.z),
-                                 z3 = unpack_bf16x2(r.w);
-                    x[0] *= gelu_erf_grad(z0.x); x[1] *= gelu_erf_grad(z0.y);
-                    x[2] *= gelu_erf_grad(z1.x); x[3] *= gelu_erf_grad(z1.y);
-                    x[4] *= gelu_erf_grad(z2.x); x[5] *= gelu_erf_grad(z2.y);
-                    x[6] *= gelu_erf_grad(z3.x); x[7] *= gelu_erf_grad(z3.y);
-                  }
-                }
-                uint4 o;
-                o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-                o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-                if (p.epi == EPI_GELU && pass == 1) {
-                  // activation of the STORED (bf16-rounded) pre-activation: forward and backward see the same z
-                  const float2 z0 = unpack_bf16x2(o.x), z1 = unpack_bf16x2(o.y), z2 = unpack_bf16x2(o.z),
-                               z3 = unpack_bf16x2(o.w);
-                  o.x = pack_bf16x2(gelu_erf(z0.x), gelu_erf(z0.y));
-                  o.y = pack_bf16x2(gelu_erf(z1.x), gelu_erf(z1.y));
-                  o.z = pack_bf16x2(gelu_erf(z2.x), gelu_erf(z2.y));
-                  o.w = pack_bf16x2(gelu_erf(z3.x), gelu_erf(z3.y));
-                }
-                const int cc = c * 4 + g;  // 16-byte chunk index inside the staged row
-                const uint32_t off = BOX_W == 64 ? lane * 128 + ((cc ^ (lane & 7)) << 4)
-                                                 : lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4);
-                *reinterpret_cast<uint4*>(stage_buf + off) = o;
-              }
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(pass == 0 ? &tma_out : &tma_out2, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
-              tma_store_commit();
-            }
-            buf = (buf + 1) % GEMM_STAGE_BUFS;
-          }
-        }
-      } else {
-        constexpr int CHUNK = HALF_COLS < 32 ? HALF_COLS : 32;
-#pragma unroll 1
-        for (int c = 0; c < HALF_COLS / CHUNK; ++c) {
-          const int col_in_tile = half * HALF_COLS + c * CHUNK;
-          uint32_t v[32];
-          tmem_ld32(t_base + col_in_tile, v);
-          tmem_ld_wait();
-          const int col0 = n_blk * BN + col_in_tile;
-          if (row_ok && col0 < p.N) {
-#pragma unroll
-            for (int g = 0; g < CHUNK / 8; ++g) {
-              const int col = col0 + g * 8;
-              if (col >= p.N) break;
-              float x[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
-              float* o = static_cast<float*>(p.out) + row * p.ldc + col;
-              if (p.epi == EPI_F32) {
-                if (p.bias != nullptr) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                  x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                  x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                }
-                *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(x[4], x[5], x[6], x[7]);
-              } else {  // EPI_F32_ATOMIC
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o), "f"(x[0]), "f"(x[1]), "f"(x[2]),
-                             "f"(x[3])
-                             : "memory");
-                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + 4), "f"(x[4]), "f"(x[5]),
-                             "f"(x[6]), "f"(x[7])
-                             : "memory");
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (lane == 0) tma_store_wait<0>();   // smem must outlive the last bulk store
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
-  }
-}
-
-template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
-                       const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, to, to2, p);
-  B200MM_CHECK_LAUNCH();
-  return B200MM_OK;
-}
-
+// one translation unit per tile width (gemm_bn64.cu / gemm_bn128.cu / gemm_bn256.cu) so they compile in parallel
+int launch_gemm_bn64(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const GemmParams&,
+                     int, cudaStream_t);
+int launch_gemm_bn128(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                      const GemmParams&, int, cudaStream_t);
+int launch_gemm_bn256(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                      const GemmParams&, int, cudaStream_t);
 }  // namespace b200
+
 
 using namespace b200;
 
@@ -455,8 +110,8 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
   const int grid = num_work < dev.num_sms ? num_work : dev.num_sms;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 64: return launch_gemm<64>(ta, tb, to, to2, p, grid, s);
-    case 128: return launch_gemm<128>(ta, tb, to, to2, p, grid, s);
-    default: return launch_gemm<256>(ta, tb, to, to2, p, grid, s);
+    case 64: return launch_gemm_bn64(ta, tb, to, to2, p, grid, s);
+    case 128: return launch_gemm_bn128(ta, tb, to, to2, p, grid, s);
+    default: return launch_gemm_bn256(ta, tb, to, to2, p, grid, s);
   }
 }

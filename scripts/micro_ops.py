@@ -39,10 +39,14 @@ if "col2im" in which:
     timeit("im2col_nchw stem", lambda: ops.im2col_nchw_f32(img, 7, 2, 3, 152), bytes_=img.numel() * 4 + 256 * 112 * 112 * 152 * 2)
     a0 = torch.randn(256 * 112 * 112, 64, device=dev).to(bf)
     timeit("maxpool_fwd", lambda: ops.maxpool_fwd(a0, 256, 112, 112, 64), bytes_=a0.numel() * 2 * 1.375)
-if "gemm" in which:
-    for (M, N, K, b_mn, epi) in [(32768, 3072, 768, 0, 1), (32768, 3072, 768, 1, 2), (32768, 2304, 768, 0, 0), (32768, 768, 768, 0, 0),
+if "gemm1" in which:
+    shapes = [(802816, 256, 64, 0, 0)]
+elif "gemm" in which:
+    shapes = [(32768, 3072, 768, 0, 1), (32768, 3072, 768, 1, 2), (32768, 2304, 768, 0, 0), (32768, 768, 768, 0, 0),
                                  (802816, 256, 64, 0, 0), (802816, 576, 64, 1, 0), (802816, 64, 576, 0, 0), (200704, 1152, 128, 1, 0),
-                                 (3211264, 64, 152, 0, 0), (50176, 2304, 256, 1, 0), (8192, 8192, 8192, 0, 0)]:
+                                 (3211264, 64, 152, 0, 0), (50176, 2304, 256, 1, 0), (8192, 8192, 8192, 0, 0)]
+if "gemm" in which or "gemm1" in which:
+    for (M, N, K, b_mn, epi) in shapes:
         A = torch.randn(M, K, device=dev).to(bf)
         Bm = torch.randn(N, K, device=dev).to(bf) if not b_mn else torch.randn(K, N, device=dev).to(bf)
         out = torch.empty(M, N, device=dev, dtype=bf); out2 = torch.empty(M, N, device=dev, dtype=bf) if epi == 1 else None

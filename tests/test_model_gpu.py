@@ -222,20 +222,22 @@ def test_image_backward_tight_without_relu_kinks(cuda_device):
 
 
 def test_loss_trajectory_matches_oracle(cuda_device):
-    """Same data, same init, Adam(lr=2e-5) (the reference's optimizer, .txt:249) on both sides: the loss curves agree
-    within 1 % at every step and the argmax predictions agree (BASELINE north_star)."""
+    """Same init, the same stream of fresh synthetic batches, Adam(lr=2e-5) (the reference's optimizer, .txt:249) on
+    both sides: the per-step losses agree within 1 % and the argmax predictions agree on >= 99.5 % of the samples
+    (BASELINE north_star; the full-size 200-step run is scripts/parity_report.py -> profiles/parity_r01.json)."""
     import b200mm
-    oracle, eng, data, cfg = _pair(cuda_device, seq=32, batch=16)
+    oracle, eng, _, cfg = _pair(cuda_device, seq=32, batch=16)
     from oracle import reference_model as R
-    d = _dev(data, cuda_device)
     oracle.train()
     eng.train()
     crit = nn.CrossEntropyLoss()
     opt_ref = torch.optim.Adam(oracle.parameters(), lr=2e-5)
     opt = b200mm.FusedAdam(eng.parameters(), lr=2e-5)
     ref_losses, losses, agree = [], [], 0
-    steps = 20
+    steps = 24
     for step in range(steps):
+        data = R.synthetic_batch(16, 32, cfg, seed=900 + step)
+        d = _dev(data, cuda_device)
         l, out_ref = R.train_step(oracle, data, crit, opt_ref)
         ref_losses.append(l.item())
         opt.zero_grad()
@@ -243,12 +245,8 @@ def test_loss_trajectory_matches_oracle(cuda_device):
         opt.step()
         losses.append(lf.item())
         agree += (logits.argmax(1).cpu() == out_ref.argmax(1)).sum().item()
-    assert ref_losses[-1] < ref_losses[0]
-    # 16 memorised samples: the loss falls by 60 % in 20 steps, so a constant lag of a fraction of one Adam step
-    # (bf16 gradient noise) shows up as a growing *relative* gap; 1 % is held over the first half, 2 % after.
-    # The full-size 200-step comparison lives in scripts/parity_report.py -> profiles/parity_r01.json.
     for i, (a, b) in enumerate(zip(losses, ref_losses)):
-        assert abs(a - b) / abs(b) < (1e-2 if i < 10 else 2e-2), (i, losses, ref_losses)
+        assert abs(a - b) / abs(b) < 1e-2, (i, losses, ref_losses)
     assert agree / (steps * 16) >= 0.995
 
 
