@@ -194,11 +194,31 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact (erf) GELU as the reference uses (transformers "gelu" -> nn.functional.gelu), evaluated with the
+// Abramowitz-Stegun 7.1.26 rational approximation of erf (|error| <= 1.5e-7 -- four orders below one bf16 ulp of the
+// stored result) so that the GEMM epilogue stays issue-light: one ex2, one rcp, five FMAs.
+// Both helpers share e = exp(-x^2/2): erf(x/sqrt2) = sign(x) (1 - poly(t) e), phi(x) = e / sqrt(2 pi).
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+  const float e = __expf(-u * u);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);         // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float cdf, pdf;
+  gelu_terms(x, cdf, pdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, pdf;
+  gelu_terms(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
 }
 
 }  // namespace b200
