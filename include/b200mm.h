@@ -42,6 +42,17 @@ int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int 
                      long long ld_aux, void* out, long long ldc, void* out2, long long ld2, int splits, int block_n,
                      float p_drop, unsigned long long seed, void* stream);
 
+/* Implicit-GEMM convolution on the same kernel: the activation operand is gathered from NHWC memory by im2col-mode
+ * TMA loads (no im2col matrix exists).  x: bf16 [N,H,W,C], C % 64 == 0; w: bf16 OHWI-flattened [Cout, k*k*C].
+ * conv_fwd also serves the stride-1 data gradient (call it on dY with the weight from conv_weight_rotate).
+ * Replaces conv3x3 of torchvision/models/resnet.py:19-31, :118-130 (cuDNN fprop / dgrad / wgrad). */
+int b200mm_conv_fwd(const void* x, int N, int H, int W, int C, const void* w, int Cout, int ksize, int stride, int pad,
+                    int epi, const float* bias, const void* residual, long long ldr, void* out, long long ldc,
+                    void* stream);
+int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x, int N, int H, int W, int C, int Cout, int ksize,
+                      int stride, int pad, float* dw, int splits, void* stream);
+int b200mm_conv_weight_rotate(const void* w, void* w_rot, int Cout, int Cin, int ksize, void* stream);
+
 /* ---- fused attention (head_dim 64, S <= 128) -------------------------------------------------------------------
  * out[B*S, H*64] = softmax(Q K^T / 8 + key_bias) (dropout) V with Q|K|V = column blocks of qkv [B*S, 3*H*64].
  * Replaces $TF:126-151 (eager_attention_forward) and its autograd backward. */

@@ -90,6 +90,11 @@ declare("b200mm_num_sms", [])
 declare("b200mm_gemm_bf16", [c_ptr, c_int, c_longlong, c_ptr, c_int, c_longlong, c_int, c_int, c_int, c_int,
                              c_ptr, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong,
                              c_int, c_int, c_float, c_ulonglong, c_ptr])
+declare("b200mm_conv_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
+                            c_longlong, c_ptr, c_longlong, c_ptr])
+declare("b200mm_conv_wgrad", [c_ptr, c_longlong, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr,
+                              c_int, c_ptr])
+declare("b200mm_conv_weight_rotate", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr])
 declare("b200mm_attention_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float, c_ulonglong, c_ptr])
 declare("b200mm_attention_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float,
                                  c_ulonglong, c_ptr])

@@ -43,6 +43,11 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 int make_tmap_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
 
+// im2col-mode bf16 tensor map over an NHWC activation [N][H][W][C]: square k x k window, symmetric padding,
+// traversal stride `stride`; each load delivers pixels_per_column pixels x 64 channels, SWIZZLE_128B.
+int make_tmap_im2col_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W, int C, int ksize, int stride, int pad,
+                          uint32_t pixels_per_column);
+
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) {
   return (a + b - 1) / b;

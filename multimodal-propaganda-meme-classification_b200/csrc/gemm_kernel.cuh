@@ -91,19 +91,57 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int n_blk = t - m_blk * p.n_tiles;
         const int k_begin = split * p.k_iters_per_split;
         const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
+        int a_n0 = 0, a_p0 = 0, a_q0 = 0;   // first output pixel of this M tile (im2col A operand)
+        if (p.a_im2col) {
+          const int pq = p.conv_P * p.conv_Q;
+          const int m0 = m_blk * GEMM_BM;
+          a_n0 = m0 / pq;
+          const int r0 = m0 - a_n0 * pq;
+          a_p0 = r0 / p.conv_Q;
+          a_q0 = r0 - a_p0 * p.conv_Q;
+        }
         for (int kb = k_begin; kb < k_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (!p.a_mn) {
+          if (p.b_im2col) {
+            // wgrad: only the 64-column atoms that exist (N = taps * C may end inside the tile) are loaded
+            int atoms = (p.N - n_blk * BN + 63) / 64;
+            atoms = atoms > BN / 64 ? BN / 64 : atoms;
+            mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + atoms * 8192);
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          }
+          if (p.a_im2col) {
+            const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+            const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
+            tma_load_im2col_4d(sa, &tma_a, &full_bar[stage], cb * 64, a_q0 * p.conv_stride - p.conv_pad,
+                               a_p0 * p.conv_stride - p.conv_pad, a_n0, static_cast<uint16_t>(kw),
+                               static_cast<uint16_t>(kh));
+          } else if (!p.a_mn) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
           } else {
 #pragma unroll
             for (int j = 0; j < GEMM_BM / 64; ++j)
               tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + j * 64, kb * GEMM_BK);
           }
-          if (!p.b_mn) {
+          if (p.b_im2col) {
+            const int pq = p.conv_P * p.conv_Q;
+            const int pix = kb * GEMM_BK;                 // first output pixel of this reduction block
+            const int n0 = pix / pq, r0 = pix - n0 * pq;
+            const int p0 = r0 / p.conv_Q, q0 = r0 - p0 * p.conv_Q;
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              const int col = n_blk * BN + j * 64;
+              if (col < p.N) {
+                const int tap = col / p.conv_C, c0 = col - tap * p.conv_C;
+                const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
+                tma_load_im2col_4d(sb + j * 8192, &tma_b, &full_bar[stage], c0, q0 * p.conv_stride - p.conv_pad,
+                                   p0 * p.conv_stride - p.conv_pad, n0, static_cast<uint16_t>(kw),
+                                   static_cast<uint16_t>(kh));
+              }
+            }
+          } else if (!p.b_mn) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           } else {
 #pragma unroll

@@ -42,6 +42,11 @@ struct GemmParams {
   uint32_t drop_threshold;
   float inv_keep;
   unsigned long long seed;
+  // implicit-GEMM convolution: an operand gathered by TMA im2col loads from an NHWC activation instead of a matrix.
+  //   a_im2col: A tile = 128 output pixels x 64 channels of tap (kb / cblocks)            (forward / stride-1 dgrad)
+  //   b_im2col: B atom = 64 pixels (reduction dim) x 64 channels of tap (col / conv_C)     (wgrad)
+  int a_im2col, b_im2col;
+  int conv_C, conv_KW, conv_stride, conv_pad, conv_P, conv_Q, conv_cblocks;
   int num_stages;  // smem ring depth (runtime: deep ring for long-K tiles, ...)
   int nbuf;        // ... or two epilogue staging boxes per warp for short-K, store-heavy tiles
 };

@@ -32,27 +32,35 @@ int launch_gemm_bn256(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&
 
 using namespace b200;
 
-// D[M,N] = A x B (+ epilogue), bf16 operands, fp32 accumulate.
-//   a_mn == 0: A is stored [M, K] (row stride lda elements);  a_mn == 1: A is stored [K, M].
-//   b_mn == 0: B is stored [N, K] (row stride ldb elements);  b_mn == 1: B is stored [K, N].
-//   epi: EpiMode above.  splits > 1 requires epi == EPI_F32_ATOMIC (out must be pre-zeroed or hold the
-//   value to accumulate onto).  block_n in {0 (auto), 64, 128, 256}.  p_drop/seed: EPI_STORE dropout (see GemmParams).
-// Contract: pointers 16-byte aligned, lda/ldb/ldc/... multiples of 8 elements, N % 8 == 0.
-B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb,
-                                int M, int N, int K, int epi, const float* bias, const void* residual,
-                                long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
-                                void* out2, long long ld2, int splits, int block_n, float p_drop,
-                                unsigned long long seed, void* stream) {
+namespace {
+
+// Where an operand comes from: a matrix (tiled TMA loads, K-major or MN-major) or an NHWC activation gathered with
+// im2col-mode TMA loads (implicit-GEMM convolution).
+struct Operand {
+  const void* ptr = nullptr;
+  int mn = 0;           // matrix: 0 = K-major ([rows, K]), 1 = MN-major ([K, rows])
+  long long ld = 0;     // matrix: row stride in elements
+  int im2col = 0;       // 1: ptr is an NHWC activation, geometry in ConvGeom
+};
+struct ConvGeom {
+  int N = 0, H = 0, W = 0, C = 0, ksize = 0, stride = 1, pad = 0, P = 0, Q = 0;
+};
+
+int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int N, int K, int epi, const float* bias,
+             const void* residual, long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
+             void* out2, long long ld2, int splits, int block_n, float p_drop, unsigned long long seed, void* stream) {
   const DeviceInfo& dev = device_info();
   if (!dev.ok) return B200MM_ERR_NOT_SM100;
   if (dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
-  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || (lda & 7) || (ldb & 7) || (ldc & 3)) return B200MM_ERR_BAD_ARG;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || (ldc & 3)) return B200MM_ERR_BAD_ARG;
+  if ((!A.im2col && (A.ld & 7)) || (!B.im2col && (B.ld & 7))) return B200MM_ERR_BAD_ARG;
   if (epi != EPI_F32 && epi != EPI_F32_ATOMIC && ((ldc & 7) || (epi == EPI_GELU && (ld2 & 7)))) return B200MM_ERR_BAD_ARG;
   if (epi < EPI_STORE || epi > EPI_RELU) return B200MM_ERR_BAD_ARG;
   if (splits < 1) splits = 1;
   if (splits > 1 && epi != EPI_F32_ATOMIC) return B200MM_ERR_BAD_ARG;
   if (epi == EPI_GELU && out2 == nullptr) return B200MM_ERR_BAD_ARG;
   if (epi == EPI_DGELU && aux == nullptr) return B200MM_ERR_BAD_ARG;
+  if ((A.im2col || B.im2col) && (cg.C % 64 != 0 || cg.ksize < 1)) return B200MM_ERR_BAD_ARG;
 
   int bn = block_n;
   if (bn == 0) bn = (N % 256 == 0 || N > 512) ? 256 : (N > 64 ? 128 : 64);
@@ -60,8 +68,12 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
 
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.a_mn = a_mn ? 1 : 0;
-  p.b_mn = b_mn ? 1 : 0;
+  p.a_mn = A.im2col ? 0 : (A.mn ? 1 : 0);
+  p.b_mn = B.im2col ? 1 : (B.mn ? 1 : 0);
+  p.a_im2col = A.im2col;
+  p.b_im2col = B.im2col;
+  p.conv_C = cg.C; p.conv_KW = cg.ksize; p.conv_stride = cg.stride; p.conv_pad = cg.pad;
+  p.conv_P = cg.P; p.conv_Q = cg.Q; p.conv_cblocks = cg.C / 64;
   p.m_tiles = ceil_div(M, GEMM_BM);
   p.n_tiles = ceil_div(N, bn);
   p.k_iters = ceil_div(K, GEMM_BK);
@@ -86,15 +98,17 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
 
   CUtensorMap ta, tb;
   int rc;
-  if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, A, K, M, lda * 2, GEMM_BK, GEMM_BM);
-  else         rc = make_tmap_2d_bf16(&ta, A, M, K, lda * 2, 64, GEMM_BK);
+  if (A.im2col)   rc = make_tmap_im2col_bf16(&ta, A.ptr, cg.N, cg.H, cg.W, cg.C, cg.ksize, cg.stride, cg.pad, GEMM_BM);
+  else if (!A.mn) rc = make_tmap_2d_bf16(&ta, A.ptr, K, M, A.ld * 2, GEMM_BK, GEMM_BM);
+  else            rc = make_tmap_2d_bf16(&ta, A.ptr, M, K, A.ld * 2, 64, GEMM_BK);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, B, K, N, ldb * 2, GEMM_BK, bn);
-  else         rc = make_tmap_2d_bf16(&tb, B, N, K, ldb * 2, 64, GEMM_BK);
+  if (B.im2col)   rc = make_tmap_im2col_bf16(&tb, B.ptr, cg.N, cg.H, cg.W, cg.C, cg.ksize, cg.stride, cg.pad, GEMM_BK);
+  else if (!B.mn) rc = make_tmap_2d_bf16(&tb, B.ptr, K, N, B.ld * 2, GEMM_BK, bn);
+  else            rc = make_tmap_2d_bf16(&tb, B.ptr, N, K, B.ld * 2, 64, GEMM_BK);
   if (rc) return rc;
 
   // output maps for the TMA-store epilogue (bf16 modes): box = [32 rows x 64 cols] SW128, or x 32 cols SW64 for BN=64
-  CUtensorMap to = ta, to2 = ta;
+  CUtensorMap to = tb, to2 = tb;
   if (epi != EPI_F32 && epi != EPI_F32_ATOMIC) {
     const uint32_t box_w = bn == 64 ? 32 : 64;
     rc = make_tmap_2d_bf16(&to, out, N, M, ldc * 2, box_w, 32, box_w * 2);
@@ -114,4 +128,93 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
     case 128: return launch_gemm_bn128(ta, tb, to, to2, p, grid, s);
     default: return launch_gemm_bn256(ta, tb, to, to2, p, grid, s);
   }
+}
+
+// w_rot[ci][k-1-kh][k-1-kw][co] = w[co][kh][kw][ci]: the weight of the transposed (data-gradient) convolution
+__global__ void __launch_bounds__(256)
+rotate_conv_weight_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ w_rot, int Cout, int Cin,
+                          int taps) {
+  const long long total = static_cast<long long>(Cout) * taps * Cin;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % Cout);           // fastest index of the OUTPUT (coalesced writes)
+    long long t = i / Cout;
+    const int tap = static_cast<int>(t % taps);
+    const int ci = static_cast<int>(t / taps);
+    w_rot[i] = w[(static_cast<long long>(co) * taps + (taps - 1 - tap)) * Cin + ci];
+  }
+}
+
+}  // namespace
+
+// D[M,N] = A x B (+ epilogue), bf16 operands, fp32 accumulate.
+//   a_mn == 0: A is stored [M, K] (row stride lda elements);  a_mn == 1: A is stored [K, M].
+//   b_mn == 0: B is stored [N, K] (row stride ldb elements);  b_mn == 1: B is stored [K, N].
+//   epi: EpiMode above.  splits > 1 requires epi == EPI_F32_ATOMIC (out must be pre-zeroed or hold the
+//   value to accumulate onto).  block_n in {0 (auto), 64, 128, 256}.  p_drop/seed: EPI_STORE dropout (see GemmParams).
+// Contract: pointers 16-byte aligned, lda/ldb/ldc/... multiples of 8 elements, N % 8 == 0.
+B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb,
+                                int M, int N, int K, int epi, const float* bias, const void* residual,
+                                long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
+                                void* out2, long long ld2, int splits, int block_n, float p_drop,
+                                unsigned long long seed, void* stream) {
+  Operand a, b;
+  a.ptr = A; a.mn = a_mn; a.ld = lda;
+  b.ptr = B; b.mn = b_mn; b.ld = ldb;
+  return run_gemm(a, b, ConvGeom{}, M, N, K, epi, bias, residual, ldr, aux, ld_aux, out, ldc, out2, ld2, splits,
+                  block_n, p_drop, seed, stream);
+}
+
+// Implicit-GEMM convolution forward (square k x k window, symmetric padding): out[N*P*Q, Cout] = conv(x, w) with
+// x an NHWC bf16 activation [N,H,W,C] (C % 64 == 0) gathered by TMA im2col loads -- no im2col matrix in memory --
+// and w the OHWI-flattened weight [Cout, k*k*C].  epi / bias / residual as in b200mm_gemm_bf16 (bf16 output modes).
+// The stride-1 data gradient is the same call on dY with the rotated weight (b200mm_conv_weight_rotate).
+// Replaces torchvision conv3x3 (torchvision/models/resnet.py:19-31, :118-130) forward / dgrad.
+B200MM_API int b200mm_conv_fwd(const void* x, int N, int H, int W, int C, const void* w, int Cout, int ksize,
+                               int stride, int pad, int epi, const float* bias, const void* residual, long long ldr,
+                               void* out, long long ldc, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || ksize <= 0 || stride <= 0 || pad < 0)
+    return B200MM_ERR_BAD_ARG;
+  ConvGeom cg;
+  cg.N = N; cg.H = H; cg.W = W; cg.C = C; cg.ksize = ksize; cg.stride = stride; cg.pad = pad;
+  cg.P = (H + 2 * pad - ksize) / stride + 1;
+  cg.Q = (W + 2 * pad - ksize) / stride + 1;
+  Operand a, b;
+  a.ptr = x; a.im2col = 1;
+  b.ptr = w; b.mn = 0; b.ld = static_cast<long long>(ksize) * ksize * C;
+  const long long M = static_cast<long long>(N) * cg.P * cg.Q;
+  if (M > 0x7fffffffLL) return B200MM_ERR_BAD_ARG;
+  return run_gemm(a, b, cg, static_cast<int>(M), Cout, ksize * ksize * C, epi, bias, residual, ldr, nullptr, 0, out,
+                  ldc, nullptr, 0, 1, 0, 0.f, 0, stream);
+}
+
+// Implicit-GEMM weight gradient: dw[Cout, k*k*C] (fp32) += dy[N*P*Q, Cout]^T x im2col(x); the im2col operand is
+// gathered by TMA, the reduction over output pixels is split across CTAs (fp32 red.global.add).
+B200MM_API int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x, int N, int H, int W, int C, int Cout,
+                                 int ksize, int stride, int pad, float* dw, int splits, void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || ksize <= 0 || stride <= 0 || pad < 0)
+    return B200MM_ERR_BAD_ARG;
+  ConvGeom cg;
+  cg.N = N; cg.H = H; cg.W = W; cg.C = C; cg.ksize = ksize; cg.stride = stride; cg.pad = pad;
+  cg.P = (H + 2 * pad - ksize) / stride + 1;
+  cg.Q = (W + 2 * pad - ksize) / stride + 1;
+  const long long pixels = static_cast<long long>(N) * cg.P * cg.Q;
+  if (pixels > 0x7fffffffLL) return B200MM_ERR_BAD_ARG;
+  Operand a, b;
+  a.ptr = dy; a.mn = 1; a.ld = ld_dy;     // stored [pixels, Cout] = [K, M]
+  b.ptr = x; b.im2col = 1;
+  const int ncols = ksize * ksize * C;
+  return run_gemm(a, b, cg, Cout, ncols, static_cast<int>(pixels), EPI_F32_ATOMIC, nullptr, nullptr, 0, nullptr, 0,
+                  dw, ncols, nullptr, 0, splits, 0, 0.f, 0, stream);
+}
+
+// w [Cout, k, k, Cin] -> w_rot [Cin, k, k, Cout] with both spatial axes flipped (bf16)
+B200MM_API int b200mm_conv_weight_rotate(const void* w, void* w_rot, int Cout, int Cin, int ksize, void* stream) {
+  if (Cout <= 0 || Cin <= 0 || ksize <= 0) return B200MM_ERR_BAD_ARG;
+  const long long total = static_cast<long long>(Cout) * ksize * ksize * Cin;
+  const int grid = static_cast<int>(total / 256 > 1184 ? 1184 : ceil_div(total, 256LL));
+  rotate_conv_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(w_rot), Cout, Cin, ksize * ksize);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
 }

@@ -130,7 +130,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
 // GEMM branch feeding this LN's input).  dgamma/dbeta are accumulated with fp32 atomics (pre-zeroed by caller
 // or holding the gradient to accumulate onto).
 template <int NC>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, NC <= 3 ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
@@ -295,7 +295,9 @@ B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* 
                                     void* stream) {
   if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
   const DeviceInfo& dev = device_info();
-  const int target_ctas = dev.num_sms > 0 ? dev.num_sms * 4 : 592;
+  // two resident CTAs per SM, one wave: every CTA ends with 2*D fp32 atomics onto the same 2*D addresses, so the
+  // CTA count is kept at the residency limit (4x fewer atomics than 4 CTAs/SM, same bandwidth)
+  const int target_ctas = dev.num_sms > 0 ? dev.num_sms * 2 : 296;
   int rows_per_cta = ceil_div(M, target_ctas);
   rows_per_cta = ceil_div(rows_per_cta, LN_WARPS) * LN_WARPS;
   const int grid = ceil_div(M, rows_per_cta);

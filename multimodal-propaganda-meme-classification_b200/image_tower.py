@@ -1,6 +1,7 @@
 """Image tower: torchvision-style ResNet (Bottleneck, v1.5) with explicit forward / backward on the sm_100a
 kernels.  Activations are NHWC bf16 token matrices [N*H*W, C]; every convolution is the tcgen05 GEMM
-(1x1: directly on the activation matrix; 3x3 / 7x7: on an im2col lowering); BatchNorm runs in training mode
+(1x1: directly on the activation matrix; 3x3: implicit GEMM, the activation operand gathered by im2col-mode TMA
+loads; 7x7 stem and the three stride-2 data gradients: explicit im2col / col2im); BatchNorm runs in training mode
 with per-replica batch statistics exactly like the reference.
 
 Mirrors ``self.resnet(image)`` of example_scripts/Multimodal_example_task2C.txt:164, :183 ->
@@ -146,8 +147,7 @@ class ImageTower:
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
             y1 = ops.linear_fwd(x, c1.w)
             a1, m1, r1 = self._bn(c1, y1, training)
-            cols2, Ho, Wo = ops.im2col(a1, N, Hc, Wc, c2.cin, 3, stride, 1)
-            y2 = ops.linear_fwd(cols2, c2.w)
+            y2, Ho, Wo = ops.conv_fwd(a1, N, Hc, Wc, c2.cin, c2.w, 3, stride, 1)      # implicit GEMM (TMA im2col)
             a2, m2, r2 = self._bn(c2, y2, training)
             y3 = ops.linear_fwd(a2, c3.w)
             xs = yd = md = rd = None
@@ -159,7 +159,7 @@ class ImageTower:
                 idn = x
             out, m3, r3 = self._bn(c3, y3, training, residual=idn, relu=True)
             if training:
-                sv["blocks"].append((x, y1, a1, m1, r1, cols2, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hc, Wc,
+                sv["blocks"].append((x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hc, Wc,
                                      Ho, Wo))
             x, Hc, Wc = out, Ho, Wo
             if self.capture is not None:
@@ -185,15 +185,20 @@ class ImageTower:
         d_out = ops.avgpool_bwd(dpooled, N, Hc * Wc, self.feat_dim)
         for blk, s in zip(reversed(self.blocks), reversed(sv["blocks"])):
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
-            x, y1, a1, m1, r1, cols2, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hi, Wi, Ho, Wo = s
+            x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hi, Wi, Ho, Wo = s
             # out = relu(bn3(y3) + idn)
             d_y3, dz = ops.batchnorm_bwd(d_out, out, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, need_dz=True)
             ops.linear_wgrad(d_y3, a2, c3.dw)
             d_a2 = ops.linear_dgrad(d_y3, c3.w)
             d_y2, _ = ops.batchnorm_bwd(d_a2, a2, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True)
-            ops.linear_wgrad(d_y2, cols2, c2.dw)
-            d_cols2 = ops.linear_dgrad(d_y2, c2.w)
-            d_a1 = ops.col2im(d_cols2, N, Hi, Wi, c2.cin, 3, stride, 1)
+            ops.conv_wgrad(d_y2, a1, N, Hi, Wi, c2.cin, 3, stride, 1, c2.dw)
+            if stride == 1:
+                # data gradient = the same implicit-GEMM convolution applied to dY with the rotated weight
+                w_rot = ops.conv_weight_rotate(c2.w, c2.cout, c2.cin, 3)
+                d_a1, _, _ = ops.conv_fwd(d_y2, N, Ho, Wo, c2.cout, w_rot, 3, 1, 1)
+            else:
+                d_cols2 = ops.linear_dgrad(d_y2, c2.w)
+                d_a1 = ops.col2im(d_cols2, N, Hi, Wi, c2.cin, 3, stride, 1)
             d_y1, _ = ops.batchnorm_bwd(d_a1, a1, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True)
             ops.linear_wgrad(d_y1, x, c1.dw)
             if ds is None:

@@ -132,6 +132,35 @@ def linear_wgrad(dy, x, dw):
     return gemm_raw(dy, True, x, True, N, K, M, dw, epi=EPI_F32_ATOMIC, splits=_wgrad_splits(N, K, M))
 
 
+def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False, out=None):
+    """Implicit-GEMM convolution: x NHWC bf16 [N*H*W, C] (C % 64 == 0), w [Cout, k*k*C] -> ([N*P*Q, Cout], P, Q)."""
+    Cout = w.shape[0]
+    P, Q = conv_out_hw(H, W, ksize, stride, pad)
+    if out is None:
+        out = torch.empty(N * P * Q, Cout, device=x.device, dtype=bf16)
+    _lib.call("b200mm_conv_fwd", _p(x), N, H, W, C, _p(w), Cout, ksize, stride, pad, EPI_RELU if relu else EPI_STORE,
+              None, _p(residual), residual.stride(0) if residual is not None else 0, _p(out), out.stride(0), _s(),
+              key=("conv_fwd", N * P * Q, Cout, ksize * ksize * C, stride))
+    return out, P, Q
+
+
+def conv_wgrad(dy, x, N, H, W, C, ksize, stride, pad, dw):
+    """dw[Cout, k*k*C] (fp32) += dy[N*P*Q, Cout]^T im2col(x)  -- im2col operand gathered by TMA."""
+    Cout = dy.shape[1]
+    pixels = dy.shape[0]
+    _lib.call("b200mm_conv_wgrad", _p(dy), dy.stride(0), _p(x), N, H, W, C, Cout, ksize, stride, pad, _p(dw),
+              _wgrad_splits(Cout, ksize * ksize * C, pixels), _s(),
+              key=("conv_wgrad", Cout, ksize * ksize * C, pixels, stride))
+    return dw
+
+
+def conv_weight_rotate(w, Cout, Cin, ksize, out=None):
+    if out is None:
+        out = torch.empty(Cin, ksize * ksize * Cout, device=w.device, dtype=bf16)
+    _lib.call("b200mm_conv_weight_rotate", _p(w), _p(out), Cout, Cin, ksize, _s())
+    return out
+
+
 def colsum(x, out):
     """out[N] (fp32) += x[M,N].sum(0)"""
     M, N = x.shape

@@ -39,9 +39,14 @@ for k, v in sorted(by_fn.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:32s} n={v[0]//STEPS:4d} {v[1]/STEPS:8.3f} ms")
     rep["ops"][k] = {"calls": v[0] // STEPS, "ms": v[1] / STEPS}
 print("GEMM by shape (M,N,K,a_mn,b_mn,epi,splits):")
-for k, v in sorted(by_gemm.items(), key=lambda kv: -kv[1][1])[:45]:
-    M, N, K = k[:3]; fl = 2.0 * M * N * K * v[0]
-    by = 2.0 * (M * K + N * K + M * N * (2 if k[5] in (3, 4) else 1))
+for k, v in sorted(by_gemm.items(), key=lambda kv: -kv[1][1])[:60]:
+    if isinstance(k[0], str):
+        M, N, K = k[1:4]
+        by = 2.0 * (M * N + N * K + M * K / 9.0) if k[0] == "conv_fwd" else 2.0 * (K * M + K * N / 9.0 + 2 * M * N)
+    else:
+        M, N, K = k[:3]
+        by = 2.0 * (M * K + N * K + M * N * (2 if k[5] in (3, 4) else 1))
+    fl = 2.0 * M * N * K * v[0]
     print(f"  {str(k):46s} n={v[0]//STEPS:3d} {v[1]/STEPS:7.3f} ms  {fl/v[1]/1e9:7.0f} TF/s  {by*v[0]/v[1]/1e6:7.0f} GB/s")
     rep["gemm"].append({"key": list(k), "calls": v[0] // STEPS, "ms": v[1] / STEPS, "tflops": fl / v[1] / 1e9, "gbs": by * v[0] / v[1] / 1e6})
 os.makedirs("profiles", exist_ok=True)

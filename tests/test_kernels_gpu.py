@@ -402,3 +402,33 @@ def test_adam_matches_torch(ops, cuda_device):
     assert abs(sq.item() - (g.double() ** 2).sum().item()) / sq.item() < 1e-4
     ops.adam_step(p, g, m, v, shadow, lr=2e-5, step=6, gradsq=sq, max_norm=1.0)
     assert (p - ref_p.detach()).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------- implicit-GEMM convolution
+@pytest.mark.parametrize("N,H,Cin,Cout,stride", [(4, 14, 64, 64, 1), (2, 16, 128, 128, 2), (8, 28, 128, 256, 1),
+                                                   (3, 7, 512, 512, 1), (5, 56, 64, 64, 1)])
+def test_implicit_gemm_conv3x3(ops, cuda_device, N, H, Cin, Cout, stride):
+    """TMA-im2col convolution (no lowering matrix in memory): forward, stride-1 data gradient through the rotated
+    weight, and the weight gradient, all vs F.conv2d / autograd."""
+    torch.manual_seed(20)
+    W = H
+    x = torch.randn(N, Cin, H, W, device=cuda_device).to(bf16).float()
+    w = (torch.randn(Cout, Cin, 3, 3, device=cuda_device) * 0.05).to(bf16).float()
+    xf = x.clone().requires_grad_(True)
+    wf = w.clone().requires_grad_(True)
+    ref = F.conv2d(xf, wf, None, stride, 1)
+    w_ohwi = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).to(bf16).contiguous()
+    xn = _nhwc(x)
+    y, P, Q = ops.conv_fwd(xn, N, H, W, Cin, w_ohwi, 3, stride, 1)
+    assert (P, Q) == tuple(ref.shape[2:])
+    assert rel(_nchw(y, N, P, Q), ref) < 1e-2
+    dy = torch.randn_like(ref).to(bf16).float()
+    ref.backward(dy)
+    dyn = _nhwc(dy)
+    dw = torch.zeros(Cout, 9 * Cin, device=cuda_device)
+    ops.conv_wgrad(dyn, xn, N, H, W, Cin, 3, stride, 1, dw)
+    assert rel(dw.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2), wf.grad) < 1e-2
+    if stride == 1:
+        w_rot = ops.conv_weight_rotate(w_ohwi, Cout, Cin, 3)
+        dx, _, _ = ops.conv_fwd(dyn, N, P, Q, Cout, w_rot, 3, 1, 1)
+        assert rel(_nchw(dx, N, H, W), xf.grad) < 1e-2
