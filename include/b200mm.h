@@ -53,7 +53,7 @@ int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x, int N, int
                       int stride, int pad, float* dw, int splits, void* stream);
 int b200mm_conv_weight_rotate(const void* w, void* w_rot, int Cout, int Cin, int ksize, void* stream);
 
-/* ---- fused attention (head_dim 64, S <= 128) -------------------------------------------------------------------
+/* ---- fused attention (head_dim 64, S <= 512) -------------------------------------------------------------------
  * out[B*S, H*64] = softmax(Q K^T / 8 + key_bias) (dropout) V with Q|K|V = column blocks of qkv [B*S, 3*H*64].
  * Replaces $TF:126-151 (eager_attention_forward) and its autograd backward. */
 int b200mm_attention_fwd(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
@@ -106,6 +106,12 @@ int b200mm_im2col_nchw_f32(const float* img, int N, int Cin, int H, int W, int K
 int b200mm_subsample_nhwc(const void* x, int N, int H, int W, int C, int stride, void* out, void* stream);
 int b200mm_upsample_add_nhwc(const void* dsub, const void* addend, int N, int H, int W, int C, int stride, void* dx,
                              void* stream);
+
+/* ---- image preprocessing: uint8 HWC -> Resize(shorter side, antialiased bilinear) -> CenterCrop -> /255 -> Normalize ->
+ * fp32 NCHW, fused (example_scripts/Multimodal_example_task2C.txt:37-41 transforms).  `images`: device array of n device
+ * pointers; mean3/std3: HOST arrays of 3 floats. */
+int b200mm_preprocess_u8(const void* images, const int* heights, const int* widths, int n, int resize, int crop,
+                         const float* mean3, const float* std3, float* out, void* stream);
 
 /* ---- head + loss, optimizer --------------------------------------------------------------------------------------
  * output layer fused with the loss: example_scripts/Multimodal_example_task2C.txt:195 (output_fc) + :214, :248

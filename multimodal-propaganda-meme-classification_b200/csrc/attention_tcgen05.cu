@@ -1,4 +1,4 @@
-// Fused multi-head self-attention (head_dim 64, S <= 128) forward and backward on tcgen05 + TMA.
+// Fused multi-head self-attention (head_dim 64, S <= 512) forward and backward on tcgen05 + TMA.
 //
 // One CTA (128 threads) handles one (batch, head) at a time, persistently:
 //   forward :  S = Q K^T (tcgen05.mma, fp32 in TMEM) -> scale + additive key-padding bias -> softmax in
@@ -373,12 +373,387 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------ S > 128
+// Longer sequences (the reference pads to 512 tokens, example_scripts/Multimodal_example_task2C.txt:14) run the same
+// tile maths over several 128-key tiles.  Forward: two passes over the key tiles (pass 1: row maxima; pass 2:
+// P = exp(S - max), O += P V accumulated in TMEM) -- no rescaling of the accumulator is ever needed.  Backward: the
+// saved LSE makes every (query tile, key tile) pair independent, so one CTA owns a key tile and accumulates dK / dV
+// over the query tiles in TMEM, another owns a query tile and accumulates dQ over the key tiles: no atomics.
+constexpr int ATT_MAX_S = 512;
+
+__device__ __forceinline__ uint64_t drop_group(int bh, int s_pad, int qrow, int key) {
+  return ((static_cast<uint64_t>(bh) * s_pad + qrow) * s_pad + key) >> 2;
+}
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_TILE_BYTES;
+  uint8_t* sP = sV + ATT_TILE_BYTES;  // 32 KB
+  float* sBias = reinterpret_cast<float*>(sP + 2 * ATT_TILE_BYTES);   // [ATT_MAX_S]
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + ATT_MAX_S);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_S = tmem, t_O = tmem + 128;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+  const int nt = (p.S + ATT_T - 1) / ATT_T;
+  const int s_pad = nt * ATT_T;
+
+  uint32_t ph_load = 0, ph_mma = 0;
+  const int items = p.B * p.H * nt;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int qi = item % nt, bh = item / nt;
+    const int b = bh / p.H, h = bh - b * p.H;
+    const int q0 = qi * ATT_T;
+    __syncthreads();   // previous item's readers of sBias are done
+    for (int k = tid; k < s_pad; k += 128)
+      sBias[k] = k < p.S ? (p.key_bias ? p.key_bias[b * p.S + k] * LOG2E : 0.f) : -INFINITY;
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &tma_qkv, bar_load, h * ATT_D, q0, b);
+    }
+    __syncthreads();
+    mbar_wait(bar_load, ph_load);
+    ph_load ^= 1;
+
+    // ---- pass 1: row maxima over all key tiles
+    float mx = -INFINITY;
+    for (int j = 0; j < nt; ++j) {
+      if (tid == 0) {
+        mbar_expect_tx(bar_load, ATT_TILE_BYTES);
+        tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, j * ATT_T, b);
+        mbar_wait(bar_load, ph_load);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(t_S, umma_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(bar_mma);
+      }
+      ph_load ^= 1;
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_S + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[j * ATT_T + c * 32 + i]));
+      }
+      tc_fence_before_sync();
+      __syncthreads();   // everybody has read S (and sK is free) before the next tile overwrites them
+    }
+    if (mx == -INFINITY) mx = 0.f;
+
+    // ---- pass 2: P = exp2(S - max), O += P V
+    float sum = 0.f;
+    for (int j = 0; j < nt; ++j) {
+      if (tid == 0) {
+        mbar_expect_tx(bar_load, 2 * ATT_TILE_BYTES);
+        tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, j * ATT_T, b);
+        tma_load_3d(sV, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, j * ATT_T, b);
+        mbar_wait(bar_load, ph_load);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(t_S, umma_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(bar_mma);
+      }
+      ph_load ^= 1;
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_S + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          x[i] = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[j * ATT_T + c * 32 + i]) - mx);
+          sum += x[i];
+        }
+        if (use_drop) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t keep = dropout_keep4(p.seed, drop_group(bh, s_pad, q0 + tid, j * ATT_T + c * 32 + g * 4),
+                                                p.drop_threshold);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[g * 4 + i] = (keep >> i) & 1 ? x[g * 4 + i] * p.inv_keep : 0.f;
+          }
+        }
+        store_row32_sw128(sP, tid, c * 32, x);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(t_O, umma_desc_sw128(smem_u32(sP) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, ph_mma);   // P V done: sP / sK / sV may be overwritten
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+    }
+
+    const float inv_sum = 1.f / sum;
+    const bool row_ok = q0 + tid < p.S;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.S + q0 + tid) * p.D + h * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_O + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv_sum, __uint_as_float(v[q * 8 + 1]) * inv_sum);
+          o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv_sum, __uint_as_float(v[q * 8 + 3]) * inv_sum);
+          o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv_sum, __uint_as_float(v[q * 8 + 5]) * inv_sum);
+          o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv_sum, __uint_as_float(v[q * 8 + 7]) * inv_sum);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = o;
+        }
+      }
+    }
+    if (row_ok && p.lse) p.lse[static_cast<long long>(bh) * p.S + q0 + tid] = (mx + log2f(sum)) * LN2;
+    tc_fence_before_sync();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+// kind 0: one key tile j, loop over query tiles -> dK_j, dV_j.   kind 1: one query tile i, loop over key tiles -> dQ_i.
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                      const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_TILE_BYTES;
+  uint8_t* sdO = sV + ATT_TILE_BYTES;
+  uint8_t* sP = sdO + ATT_TILE_BYTES;
+  uint8_t* sdS = sP + 2 * ATT_TILE_BYTES;
+  float* sBias = reinterpret_cast<float*>(sdS + 2 * ATT_TILE_BYTES);  // [128]: bias of the current key tile
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + ATT_T);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_S = tmem, t_dP = tmem + 128, t_A = tmem + 256, t_B = tmem + 320;  // A: dV or dQ, B: dK
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);
+  const uint32_t idesc_nt = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+  const int nt = (p.S + ATT_T - 1) / ATT_T;
+  const int s_pad = nt * ATT_T;
+
+  uint32_t ph_load = 0, ph_mma = 0;
+  const int per_kind = p.B * p.H * nt;
+  for (int item = blockIdx.x; item < 2 * per_kind; item += gridDim.x) {
+    const int kind = item / per_kind;
+    const int rest = item - kind * per_kind;
+    const int fixed = rest % nt, bh = rest / nt;      // fixed = key tile (kind 0) or query tile (kind 1)
+    const int b = bh / p.H, h = bh - b * p.H;
+    for (int it = 0; it < nt; ++it) {
+      const int qi = kind == 0 ? it : fixed;
+      const int kj = kind == 0 ? fixed : it;
+      const int q0 = qi * ATT_T, k0 = kj * ATT_T;
+      __syncthreads();
+      sBias[tid] = k0 + tid < p.S ? (p.key_bias ? p.key_bias[b * p.S + k0 + tid] * LOG2E : 0.f) : -INFINITY;
+      if (tid == 0) {
+        mbar_expect_tx(bar_load, 4 * ATT_TILE_BYTES);
+        tma_load_3d(sQ, &tma_qkv, bar_load, h * ATT_D, q0, b);
+        tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, k0, b);
+        tma_load_3d(sV, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, k0, b);
+        tma_load_3d(sdO, &tma_do, bar_load, h * ATT_D, q0, b);
+      }
+      const bool qrow_ok = q0 + tid < p.S;
+      float delta = 0.f, lse_l2 = INFINITY;
+      if (qrow_ok) {
+        const long long off = (static_cast<long long>(b) * p.S + q0 + tid) * p.D + h * ATT_D;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float a[8], g[8];
+          load8(p.o_in + off + q * 8, a);
+          load8(p.do_in + off + q * 8, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) delta = fmaf(a[i], g[i], delta);
+        }
+        lse_l2 = p.lse[static_cast<long long>(bh) * p.S + q0 + tid] * LOG2E;
+      }
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(bar_load, ph_load);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(t_S, umma_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(t_dP, umma_desc_sw128(smem_u32(sdO) + k * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sV) + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(bar_mma);
+      }
+      ph_load ^= 1;
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t vs[32], vp[32];
+        tmem_ld32(t_S + lane_addr + c * 32, vs);
+        tmem_ld32(t_dP + lane_addr + c * 32, vp);
+        tmem_ld_wait();
+        float pd[32], ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pd[i] = exp2f(fmaf(__uint_as_float(vs[i]), p.scale_log2, sBias[c * 32 + i]) - lse_l2);
+          ds[i] = __uint_as_float(vp[i]);
+        }
+        if (use_drop) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t keep =
+                dropout_keep4(p.seed, drop_group(bh, s_pad, q0 + tid, k0 + c * 32 + g * 4), p.drop_threshold);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float m = (keep >> i) & 1 ? p.inv_keep : 0.f;
+              const float prob = pd[g * 4 + i];
+              pd[g * 4 + i] = prob * m;
+              ds[g * 4 + i] = prob * (ds[g * 4 + i] * m - delta) * p.scale;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ds[i] = pd[i] * (ds[i] - delta) * p.scale;
+        }
+        if (kind == 0) store_row32_sw128(sP, tid, c * 32, pd);
+        store_row32_sw128(sdS, tid, c * 32, ds);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t accum = it > 0 ? 1u : 0u;
+        if (kind == 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dV_j += P^T dO_i
+            umma_bf16(t_A, umma_desc_sw128(smem_u32(sP) + k * 2048, ATT_TILE_BYTES, 1024),
+                      umma_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024), idesc_tt, (accum || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dK_j += dS^T Q_i
+            umma_bf16(t_B, umma_desc_sw128(smem_u32(sdS) + k * 2048, ATT_TILE_BYTES, 1024),
+                      umma_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024), idesc_tt, (accum || k > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // dQ_i += dS K_j
+            umma_bf16(t_A, umma_desc_sw128(smem_u32(sdS) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                      umma_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_nt, (accum || k > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, ph_mma);   // operands in smem are free again
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+    }
+    // ---- store the accumulated tile(s): rows = keys (kind 0) or queries (kind 1) of the fixed tile
+    const int r0 = fixed * ATT_T;
+    const bool row_ok = r0 + tid < p.S;
+    __nv_bfloat16* grow = p.dqkv + (static_cast<long long>(b) * p.S + r0 + tid) * (3 * p.D) + h * ATT_D;
+    const int nout = kind == 0 ? 2 : 1;
+#pragma unroll 1
+    for (int which = 0; which < nout; ++which) {
+      // kind 0: which 0 -> dV (column block 2), which 1 -> dK (block 1); kind 1: dQ (block 0)
+      const uint32_t t_src = which == 0 ? t_A : t_B;
+      const int blk = kind == 0 ? (which == 0 ? 2 : 1) : 0;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_src + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(grow + blk * p.D + c * 32 + q * 8) = o;
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+constexpr int ATT_FWD_MULTI_SMEM = 5 * ATT_TILE_BYTES + ATT_MAX_S * 4 + 64 + 1024;
+
 constexpr int ATT_FWD_SMEM = 5 * ATT_TILE_BYTES + ATT_T * 4 + 64 + 1024;
 constexpr int ATT_BWD_SMEM = 8 * ATT_TILE_BYTES + ATT_T * 4 + 64 + 1024;
 
 static int fill_params(AttnParams& p, int B, int H, int S, float p_drop, unsigned long long seed,
                        const float* key_bias) {
-  if (B <= 0 || H <= 0 || S <= 0 || S > ATT_T || p_drop < 0.f || p_drop >= 1.f) return B200MM_ERR_BAD_ARG;
+  if (B <= 0 || H <= 0 || S <= 0 || S > 512 || p_drop < 0.f || p_drop >= 1.f) return B200MM_ERR_BAD_ARG;
   p.B = B; p.H = H; p.S = S; p.D = H * ATT_D;
   p.scale = 0.125f;  // 64^-1/2
   p.scale_log2 = p.scale * LOG2E;
@@ -395,7 +770,7 @@ static int fill_params(AttnParams& p, int B, int H, int S, float p_drop, unsigne
 using namespace b200;
 
 // O[B*S, H*64] = softmax(Q K^T / 8 + key_bias) (dropout) V, Q/K/V = column blocks of qkv [B*S, 3*H*64].
-// lse [B,H,S] (fp32) is written when non-null (required for the backward).  S <= 128.
+// lse [B,H,S] (fp32) is written when non-null (required for the backward).  S <= 512 (multi-tile kernels above 128).
 B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
                                     float p_drop, unsigned long long seed, void* stream) {
   const DeviceInfo& dev = device_info();
@@ -413,7 +788,16 @@ B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(attn_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_MULTI_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
+  }
+  if (S > ATT_T) {
+    const int items = B * H * ceil_div(S, ATT_T);
+    const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
+    attn_fwd_multi_kernel<<<grid, 128, ATT_FWD_MULTI_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p);
+    B200MM_CHECK_LAUNCH();
+    return B200MM_OK;
   }
   const int items = B * H;
   const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
@@ -447,7 +831,16 @@ B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, cons
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(attn_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
+  }
+  if (S > ATT_T) {
+    const int items = 2 * B * H * ceil_div(S, ATT_T);
+    const int grid = items < dev.num_sms ? items : dev.num_sms;
+    attn_bwd_multi_kernel<<<grid, 128, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
+    B200MM_CHECK_LAUNCH();
+    return B200MM_OK;
   }
   const int items = B * H;
   const int grid = items < dev.num_sms ? items : dev.num_sms;

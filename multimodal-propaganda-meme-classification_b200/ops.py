@@ -47,9 +47,10 @@ def _chk(t: torch.Tensor, dtype, name="tensor"):
 _gemm_profile = None   # when a list: (start_event, end_event, flops) per GEMM launch (see profile_gemm)
 
 
-def profile_gemm(step_fn, steps: int = 2):
-    """Time every GEMM launch of ``steps`` calls of ``step_fn`` with CUDA events on the launching stream.
-    Returns (GEMM milliseconds per step, GEMM FLOPs per step, GEMM launches per step)."""
+def profile_gemm(step_fn, steps: int = 2, ridge: float = 208.0):
+    """Time every tcgen05 GEMM launch (plain and implicit-conv) of ``steps`` calls of ``step_fn`` with CUDA events on
+    the launching stream.  Returns (ms per step, FLOPs per step, launches per step, per-roofline detail): launches whose
+    algorithmic intensity (FLOP / byte of operands + output) is below ``ridge`` are HBM-bound, the rest tensor-bound."""
     global _gemm_profile
     torch.cuda.synchronize()
     _gemm_profile = []
@@ -60,9 +61,19 @@ def profile_gemm(step_fn, steps: int = 2):
         rec = _gemm_profile
     finally:
         _gemm_profile = None
-    ms = sum(a.elapsed_time(b) for a, b, _ in rec)
-    fl = sum(f for _, _, f in rec)
-    return ms / steps, fl / steps, len(rec) // steps
+    ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+    fl = sum(f for _, _, f, _ in rec)
+    # split by the roofline that bounds each launch: arithmetic intensity above / below the ridge point
+    split = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}
+    for a, b, f, by in rec:
+        k = "tensor" if f / by >= ridge else "hbm"
+        split[k][0] += a.elapsed_time(b)
+        split[k][1] += f
+        split[k][2] += by
+        split[k][3] += 1
+    detail = {k: {"ms": v[0] / steps, "flops": v[1] / steps, "bytes": v[2] / steps, "launches": v[3] // steps}
+              for k, v in split.items()}
+    return ms / steps, fl / steps, len(rec) // steps, detail
 
 
 def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residual=None, aux=None, out2=None,
@@ -77,7 +88,10 @@ def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residu
                   _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed),
                   _s())
         e1.record()
-        _gemm_profile.append((e0, e1, 2.0 * M * N * K))
+        nbytes = 2.0 * (M * K + N * K) + M * N * (8.0 if epi in (EPI_F32, EPI_F32_ATOMIC) else (4.0 if epi == EPI_GELU else 2.0))
+        if residual is not None or aux is not None:
+            nbytes += 2.0 * M * N
+        _gemm_profile.append((e0, e1, 2.0 * M * N * K, nbytes))
         return out
     _lib.call("b200mm_gemm_bf16", _p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, epi,
               _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
@@ -138,9 +152,17 @@ def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False,
     P, Q = conv_out_hw(H, W, ksize, stride, pad)
     if out is None:
         out = torch.empty(N * P * Q, Cout, device=x.device, dtype=bf16)
+    prof = _gemm_profile
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("b200mm_conv_fwd", _p(x), N, H, W, C, _p(w), Cout, ksize, stride, pad, EPI_RELU if relu else EPI_STORE,
               None, _p(residual), residual.stride(0) if residual is not None else 0, _p(out), out.stride(0), _s(),
               key=("conv_fwd", N * P * Q, Cout, ksize * ksize * C, stride))
+    if prof is not None:
+        e1.record()
+        M_, K_ = N * P * Q, ksize * ksize * C
+        prof.append((e0, e1, 2.0 * M_ * Cout * K_, 2.0 * (N * H * W * C + Cout * K_ + M_ * Cout)))
     return out, P, Q
 
 
@@ -148,9 +170,17 @@ def conv_wgrad(dy, x, N, H, W, C, ksize, stride, pad, dw):
     """dw[Cout, k*k*C] (fp32) += dy[N*P*Q, Cout]^T im2col(x)  -- im2col operand gathered by TMA."""
     Cout = dy.shape[1]
     pixels = dy.shape[0]
+    prof = _gemm_profile
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("b200mm_conv_wgrad", _p(dy), dy.stride(0), _p(x), N, H, W, C, Cout, ksize, stride, pad, _p(dw),
               _wgrad_splits(Cout, ksize * ksize * C, pixels), _s(),
               key=("conv_wgrad", Cout, ksize * ksize * C, pixels, stride))
+    if prof is not None:
+        e1.record()
+        K_ = ksize * ksize * C
+        prof.append((e0, e1, 2.0 * pixels * Cout * K_, 2.0 * (pixels * Cout + N * H * W * C) + 8.0 * Cout * K_))
     return dw
 
 
@@ -389,3 +419,31 @@ def upsample_add(dsub, addend, N, H, W, C, stride):
     dx = torch.empty(N * H * W, C, device=dsub.device, dtype=bf16)
     _lib.call("b200mm_upsample_add_nhwc", _p(dsub), _p(addend), N, H, W, C, stride, _p(dx), _s())
     return dx
+
+
+# ----------------------------------------------------------------------------------------------- preprocessing
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def preprocess_u8(images, *, resize=256, crop=224, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """images: list of uint8 CUDA tensors [H, W, 3] (decoded, any size).  Returns fp32 [n, 3, crop, crop] exactly as
+    Resize(resize) -> CenterCrop(crop) -> ToTensor -> Normalize(mean, std) would (antialiased bilinear)."""
+    import ctypes
+    n = len(images)
+    dev = images[0].device
+    imgs = [im.contiguous() for im in images]
+    for im in imgs:
+        _chk(im, torch.uint8, "image")
+        if im.dim() != 3 or im.shape[2] != 3:
+            raise ValueError("images must be [H, W, 3] uint8")
+    ptrs = torch.tensor([im.data_ptr() for im in imgs], dtype=torch.int64).to(dev)
+    hs = torch.tensor([im.shape[0] for im in imgs], dtype=torch.int32).to(dev)
+    ws = torch.tensor([im.shape[1] for im in imgs], dtype=torch.int32).to(dev)
+    out = torch.empty(n, 3, crop, crop, device=dev, dtype=f32)
+    m = (ctypes.c_float * 3)(*mean)
+    s = (ctypes.c_float * 3)(*std)
+    _lib.call("b200mm_preprocess_u8", _p(ptrs), _p(hs), _p(ws), n, resize, crop, ctypes.cast(m, ctypes.c_void_p),
+              ctypes.cast(s, ctypes.c_void_p), _p(out), _s())
+    out._keepalive = imgs
+    return out

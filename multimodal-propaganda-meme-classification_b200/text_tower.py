@@ -129,8 +129,8 @@ class TextTower:
         """ids, mask: int64 [B, S].  Returns the last hidden state as a bf16 [B*S, D] token matrix."""
         c = self.cfg
         B, S = ids.shape
-        if S > 128:
-            raise NotImplementedError("attention kernel currently covers sequence lengths up to 128")
+        if S > 512:
+            raise NotImplementedError("attention kernels cover sequence lengths up to 512 (the reference's maximum)")
         if S > c.max_position_embeddings:
             raise ValueError("sequence longer than the position table")
         ids = ids.contiguous()

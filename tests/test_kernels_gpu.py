@@ -93,7 +93,8 @@ def _attn_ref(qkv, key_bias, B, H, S):
     return (p @ v).permute(0, 2, 1, 3).reshape(B * S, D)
 
 
-@pytest.mark.parametrize("B,H,S", [(2, 2, 128), (3, 12, 128), (2, 4, 64), (2, 3, 100)])
+@pytest.mark.parametrize("B,H,S", [(2, 2, 128), (3, 12, 128), (2, 4, 64), (2, 3, 100), (2, 2, 256), (2, 3, 197),
+                                   (1, 4, 512), (2, 2, 300)])
 def test_attention_fwd_bwd(ops, cuda_device, B, H, S):
     torch.manual_seed(3)
     D = H * 64
@@ -432,3 +433,20 @@ def test_implicit_gemm_conv3x3(ops, cuda_device, N, H, Cin, Cout, stride):
         w_rot = ops.conv_weight_rotate(w_ohwi, Cout, Cin, 3)
         dx, _, _ = ops.conv_fwd(dyn, N, P, Q, Cout, w_rot, 3, 1, 1)
         assert rel(_nchw(dx, N, H, W), xf.grad) < 1e-2
+
+
+def test_preprocess_u8_matches_torch_transforms(ops, cuda_device):
+    """uint8 HWC -> Resize(256) -> CenterCrop(224) -> /255 -> Normalize, vs torch's antialiased bilinear resize."""
+    torch.manual_seed(30)
+    sizes = [(300, 400), (768, 512), (224, 224), (1000, 333), (257, 900)]
+    imgs = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device=cuda_device) for h, w in sizes]
+    out = ops.preprocess_u8(imgs)
+    mean = torch.tensor(ops.IMAGENET_MEAN, device=cuda_device).view(3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD, device=cuda_device).view(3, 1, 1)
+    for k, (im, (h, w)) in enumerate(zip(imgs, sizes)):
+        nh, nw = (256, int(256 * w / h)) if h <= w else (int(256 * h / w), 256)
+        x = im.permute(2, 0, 1).float().unsqueeze(0)
+        r = F.interpolate(x, size=(nh, nw), mode="bilinear", antialias=True, align_corners=False)[0]
+        top, left = int(round((nh - 224) / 2.0)), int(round((nw - 224) / 2.0))
+        ref = (r[:, top:top + 224, left:left + 224] / 255.0 - mean) / std
+        assert (out[k] - ref).abs().max().item() < 2e-4, (k, (out[k] - ref).abs().max().item())
