@@ -22,6 +22,9 @@ _LAZY = {
     "test": ("loop", "test"),
     "evaluate": ("loop", "evaluate"),
     "predict": ("loop", "predict"),
+    "seed_everything": ("loop_head", "seed_everything"),
+    "stratified_kfold": ("loop_head", "stratified_kfold"),
+    "get_params": ("loop_head", "get_params"),
 }
 
 

@@ -38,14 +38,14 @@ class _EngineFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dlogits):
-        ctx.model._engine_backward_from_dlogits(dlogits.contiguous())
+        ctx.model._engine_backward_from_dlogits(dlogits.reshape(dlogits.shape[0], -1).contiguous())
         return torch.zeros((), device=dlogits.device), None, None, None, None
 
 
 class MultimodalClassifier(nn.Module):
     def __init__(self, num_classes: int = 2, *, text_config: TextConfig | None = None,
                  image_config: ImageConfig | None = None, device=None, head_dropout: float = 0.3,
-                 pooling: str = POOL_LAST, seed: int = 42, init: bool = True):
+                 pooling: str = POOL_LAST, seed: int = 42, init: bool = True, squeeze_output: bool = False):
         super().__init__()
         if not torch.cuda.is_available():
             raise _lib.B200MMError("b200mm needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -54,6 +54,7 @@ class MultimodalClassifier(nn.Module):
         self.num_classes = num_classes
         self.head_dropout = head_dropout       # self.bert_drop = nn.Dropout(0.3), .txt:160
         self.pooling = pooling                 # 'last' = bert_output[0][:, -1, :], .txt:178 ; 'cls' = HEAD script
+        self.squeeze_output = squeeze_output   # single-logit head: return [B] like output.squeeze_(1) (HEAD :683)
         self.seed = seed
         self._step = 0
         self.tcfg = text_config or TextConfig()
@@ -276,8 +277,10 @@ class MultimodalClassifier(nn.Module):
         if text is None or image is None or mask is None:
             raise TypeError("forward(text, image, mask) / forward(input_ids=, attention_mask=, pixel_values=)")
         if self.training and torch.is_grad_enabled():
-            return _EngineFunction.apply(self._anchor, self, text, image, mask)
-        return self._engine_forward(text, image, mask, training=False)
+            out = _EngineFunction.apply(self._anchor, self, text, image, mask)
+        else:
+            out = self._engine_forward(text, image, mask, training=False)
+        return out.squeeze(1) if (self.squeeze_output and self.num_classes == 1) else out
 
     def eval_step_fused(self, text, image, mask, labels, *, loss_kind=ops.LOSS_CE, alpha=0.25, gamma=2.0):
         """Eval-mode forward with output_fc + loss + accuracy count fused. Returns (logits, loss_sum, correct)."""

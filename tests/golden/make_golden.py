@@ -95,7 +95,25 @@ def oracle_golden():
     print("oracle tiny loss:", loss.item())
 
 
+def kfold_golden():
+    """Labels of the reference's train split + sklearn's StratifiedKFold(5, shuffle=True, random_state=42) folds, the
+    split the HEAD script draws at Multimodal_example_task2C.py:115-128 (fold sizes 1714/1715)."""
+    import numpy as np
+    from sklearn.model_selection import StratifiedKFold
+    d = json.load(open(os.path.join(REF, "data/arabic_memes_propaganda_araieval_24_train.json")))
+    labels = [1 if x["class_label"] == "propaganda" else 0 for x in d]
+    skf = StratifiedKFold(5, shuffle=True, random_state=42)
+    splits = list(skf.split(np.zeros(len(labels)), labels))
+    json.dump({"source": "data/arabic_memes_propaganda_araieval_24_train.json class_label (1 = propaganda), file order; "
+                         "sklearn StratifiedKFold(5, shuffle=True, random_state=42)",
+               "labels_bits": "".join(map(str, labels)), "fold_sizes": [(len(a), len(b)) for a, b in splits],
+               "first_val_indices": [b[:5].tolist() for a, b in splits]},
+              open(os.path.join(HERE, "kfold_golden.json"), "w"))
+    print("kfold:", [(len(a), len(b)) for a, b in splits])
+
+
 if __name__ == "__main__":
+    kfold_golden()
     combine_preds_golden()
     scorer_golden()
     oracle_golden()

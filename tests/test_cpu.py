@@ -308,3 +308,39 @@ def test_bf16_emulation_oracle_rounds_only_inside_context():
     with E.bf16_storage(m):
         m(d["text"], d["image"], d["text_mask"]).sum().backward()
     assert m.resnet.conv1.weight.grad is not None and m.bert.embeddings.word_embeddings.weight.grad is not None
+
+
+# ------------------------------------------------------------------------------------------------- HEAD-style loop pieces
+def test_stratified_kfold_known_answer_and_sklearn():
+    from b200mm.loop_head import stratified_kfold
+    with open(os.path.join(GOLD, "kfold_golden.json")) as f:
+        fx = json.load(f)
+    labels = [int(c) for c in fx["labels_bits"]]
+    assert len(labels) == 2143 and sum(labels) == 603                       # SURVEY.md §8d train prior
+    folds = list(stratified_kfold(labels, 5, 42))
+    assert [(len(a), len(b)) for a, b in folds] == [tuple(x) for x in fx["fold_sizes"]]
+    assert [b[:5].tolist() for a, b in folds] == fx["first_val_indices"]
+    from sklearn.model_selection import StratifiedKFold
+    rng = np.random.default_rng(3)
+    y = rng.integers(0, 3, 517)
+    ref = list(StratifiedKFold(4, shuffle=True, random_state=7).split(np.zeros(len(y)), y))
+    mine = list(stratified_kfold(y, 4, 7))
+    for (ra, rb), (ma, mb) in zip(ref, mine):
+        assert np.array_equal(ra, ma) and np.array_equal(rb, mb)
+
+
+def test_warmup_schedule_matches_transformers():
+    from transformers import get_linear_schedule_with_warmup as ref_sched
+    from b200mm.optim import get_linear_schedule_with_warmup
+    lrs = []
+    for mk in (ref_sched, get_linear_schedule_with_warmup):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([p], lr=1e-5)
+        sch = mk(opt, num_warmup_steps=8, num_training_steps=80)
+        cur = []
+        for _ in range(80):
+            opt.step()
+            sch.step()
+            cur.append(sch.get_last_lr()[0])
+        lrs.append(cur)
+    assert np.allclose(lrs[0], lrs[1], rtol=0, atol=1e-15)

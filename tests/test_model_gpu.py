@@ -279,3 +279,82 @@ def test_reference_loop_api(cuda_device, tmp_path):
     rows = b200mm.evaluate(eng, loader, cuda_device, out_path=str(out))
     assert len(rows) == 8 and tsv.check_label_tsv(str(out))
     assert out.read_text().splitlines()[0] == "id\tlabel\trun_id"
+
+
+def test_long_sequence_forward_matches_oracle(cuda_device):
+    """Sequences beyond one 128-token tile go through the multi-tile attention kernels (the reference pads to 512)."""
+    import b200mm
+    from oracle import reference_model as R
+    cfg = R.TowerConfig.tiny(max_position_embeddings=512)
+    torch.manual_seed(5)
+    oracle = R.zero_dropout(R.MultimodalClassifier(2, cfg))
+    tcfg = b200mm.TextConfig(vocab_size=cfg.vocab_size, max_position_embeddings=512, dim=cfg.dim,
+                             n_layers=cfg.n_layers, n_heads=cfg.n_heads, hidden_dim=cfg.hidden_dim, dropout=0.0,
+                             attention_dropout=0.0)
+    eng = b200mm.MultimodalClassifier(2, text_config=tcfg, image_config=b200mm.ImageConfig(layers=cfg.resnet_layers),
+                                      head_dropout=0.0, device=cuda_device)
+    eng.load_reference_state_dict(oracle.state_dict())
+    oracle.train()
+    eng.train()
+    for S in (200, 512):
+        data = R.synthetic_batch(4, S, cfg, seed=S)
+        d = _dev(data, cuda_device)
+        ref = oracle(data["text"], data["image"], data["text_mask"]).detach()
+        crit = nn.CrossEntropyLoss()
+        eng.zero_grad()
+        logits, loss, _ = eng.train_step_fused(d["text"], d["image"], d["text_mask"], d["label"])
+        assert rel(logits, ref) < 2e-2
+        assert abs(loss.item() - crit(ref, data["label"]).item()) / loss.item() < 1e-2
+        assert torch.isfinite(eng.store.grad).all()
+
+
+def test_head_style_loop_api(cuda_device, tmp_path):
+    """HEAD script's API on the engine: single-logit focal head, param groups, warm-up schedule, clipping, ROC
+    threshold, both TSVs (Multimodal_example_task2C.py:645-664, 689-879)."""
+    import b200mm
+    from b200mm import loop_head, tsv
+    from oracle import reference_model as R
+    cfg = R.TowerConfig.tiny()
+    tcfg = b200mm.TextConfig(vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings,
+                             dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, hidden_dim=cfg.hidden_dim)
+    loop_head.seed_everything(42)
+    eng = b200mm.MultimodalClassifier(1, text_config=tcfg, image_config=b200mm.ImageConfig(layers=cfg.resnet_layers),
+                                      device=cuda_device, squeeze_output=True, pooling="cls")
+    data = R.synthetic_batch(48, 32, cfg)
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, idx):
+            self.idx = list(idx)
+
+        def __len__(self):
+            return len(self.idx)
+
+        def __getitem__(self, k):
+            i = self.idx[k]
+            return {"id": f"data/x/img_{i}.jpg", "text": data["text"][i], "text_mask": data["text_mask"][i],
+                    "image": data["image"][i], "label": data["label"][i]}
+
+    tr, va = next(iter(loop_head.stratified_kfold(data["label"].numpy(), 3, 42)))
+    train_loader = torch.utils.data.DataLoader(DS(tr), batch_size=8, shuffle=True)
+    val_loader = torch.utils.data.DataLoader(DS(va), batch_size=8)
+    crit = b200mm.SigmoidFocalLoss(alpha=0.25, gamma=2.0)
+    opt = b200mm.FusedAdam(loop_head.get_params(eng, 1e-5), lr=1e-5, max_grad_norm=10.0)
+    assert [g["lr"] for g in opt.param_groups] == pytest.approx([1e-5, 0.8e-5, 0.8e-5])
+    sched = b200mm.get_linear_schedule_with_warmup(opt, 1, 2 * len(train_loader))
+    lines, state = [], {}
+    out = eng(data["text"][:4].to(cuda_device), data["image"][:4].to(cuda_device),
+              data["text_mask"][:4].to(cuda_device))
+    assert out.shape == (4,)
+    for epoch in range(2):
+        loss, acc = loop_head.train(eng, train_loader, crit, opt, sched, cuda_device, epoch, test_loader=val_loader,
+                                    state=state, evaluate_kwargs={"fold": 3, "out_dir": str(tmp_path)},
+                                    log=lines.append)
+        assert loss > 0 and 0 <= acc <= 1
+    t_loss, t_acc, t_f1, thr = loop_head.test(eng, val_loader, crit, cuda_device, 1, log=lines.append)
+    assert 0 <= t_f1 <= 1 and 0 <= t_acc <= 1
+    assert any(l.startswith(" TEST | Epoch") for l in lines) and "best_macro_f1" in state
+    f_lab = tmp_path / "task2C_kevinmathew.tsv"
+    f_prob = tmp_path / "task2C_kevinmathew_probs_fold_3.tsv"
+    assert tsv.check_label_tsv(str(f_lab))
+    ids, labels, probs, _ = tsv.read_prob_tsv(str(f_prob))
+    assert len(ids) == len(va) and all(0.0 <= p <= 1.0 for p in probs)
