@@ -63,18 +63,31 @@ int b200mm_attention_bwd(const void* qkv, const float* key_bias, const void* out
 /* int64 attention_mask (1 = token) -> additive fp32 key bias 0 / -inf  ($TF:415-419) */
 int b200mm_mask_to_bias(const long long* mask, float* bias, long long n, void* stream);
 
-/* ---- LayerNorm / embeddings ($TF:96-122 Embeddings, :257 sa_layer_norm, :261 output_layer_norm) -------------- */
+/* ---- LayerNorm / embeddings ($TF:96-122 Embeddings, :257 sa_layer_norm, :261 output_layer_norm; BERT / XLM-R
+ * variants: transformers/models/bert/modeling_bert.py:53-113, xlm_roberta/modeling_xlm_roberta.py:56-159;
+ * ViT token assembly: transformers/models/vit/modeling_vit.py ViTEmbeddings.forward) --------------------------- */
 int b200mm_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                          int M, int D, float eps, float p_drop, unsigned long long seed, void* stream);
-int b200mm_embed_layernorm_fwd(const long long* ids, const float* word, const float* pos, int S, int vocab,
-                               const float* gamma, const float* beta, void* x_saved, void* y, float* mean,
-                               float* rstd, int M, int D, float eps, float p_drop, unsigned long long seed,
-                               void* stream);
+/* x_saved = bf16(word[ids] + pos[pos_ids ? pos_ids[m] : m % S] (+ type_row)); y = dropout(LN(x_saved)).
+ * pos_ids: nullable int32 [M] (RoBERTa-style); type_row: nullable fp32 [D] = token_type_embeddings[0]. */
+int b200mm_embed_layernorm_fwd(const long long* ids, const float* word, const float* pos, const int* pos_ids,
+                               const float* type_row, int S, int vocab, const float* gamma, const float* beta,
+                               void* x_saved, void* y, float* mean, float* rstd, int M, int D, float eps,
+                               float p_drop, unsigned long long seed, void* stream);
+/* addend (nullable bf16 [M,D]) is added to dx only: the residual-stream gradient of a pre-LN (ViT) block. */
 int b200mm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                         void* dx, void* dx2, float* dgamma, float* dbeta, int M, int D, float p_in,
-                         unsigned long long seed_in, float p_out, unsigned long long seed_out, void* stream);
-int b200mm_embedding_bwd(const void* dx, const long long* ids, int S, int vocab, long long padding_idx, float* dword,
-                         float* dpos, int M, int D, void* stream);
+                         const void* addend, void* dx, void* dx2, float* dgamma, float* dbeta, int M, int D,
+                         float p_in, unsigned long long seed_in, float p_out, unsigned long long seed_out,
+                         void* stream);
+int b200mm_embedding_bwd(const void* dx, const long long* ids, const int* pos_ids, long long pos_padding_idx, int S,
+                         int vocab, long long padding_idx, float* dword, float* dpos, int M, int D, void* stream);
+/* RoBERTa / XLM-R position ids: out[b,s] = cumsum(ids != pad)[b,s] * (ids[b,s] != pad) + pad  (int32 [B*S]) */
+int b200mm_position_ids(const long long* ids, long long pad_id, int B, int S, int* out, void* stream);
+/* ViT: tokens[B*(P+1), D] = [cls | patch[B*P, D]] + pos[(P+1), D]; backward: dpatch copy, dpos / dcls sums (+=) */
+int b200mm_vit_assemble_fwd(const void* patch, const float* cls, const float* pos, void* x, int B, int P, int D,
+                            void* stream);
+int b200mm_vit_assemble_bwd(const void* dx, void* dpatch, float* dcls, float* dpos, int B, int P, int D,
+                            void* stream);
 /* pooled token: out[i,:] = dropout(x[i*stride_rows + offset_rows, :])  (h[:, -1, :] + bert_drop,
  * example_scripts/Multimodal_example_task2C.txt:178) and its backward scatter */
 int b200mm_gather_rows(const void* x, void* out, int rows, int D, long long stride_rows, long long offset_rows,

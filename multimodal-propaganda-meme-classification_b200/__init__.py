@@ -14,6 +14,7 @@ _LAZY = {
     "MultimodalClassifier": ("model", "MultimodalClassifier"),
     "TextConfig": ("text_tower", "TextConfig"),
     "ImageConfig": ("image_tower", "ImageConfig"),
+    "ViTConfig": ("vit_tower", "ViTConfig"),
     "FusedAdam": ("optim", "FusedAdam"),
     "get_linear_schedule_with_warmup": ("optim", "get_linear_schedule_with_warmup"),
     "CrossEntropyLoss": ("loop", "CrossEntropyLoss"),

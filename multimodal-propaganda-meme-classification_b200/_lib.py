@@ -101,11 +101,15 @@ declare("b200mm_attention_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int
                                  c_ulonglong, c_ptr])
 declare("b200mm_layernorm_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_float, c_float,
                                  c_ulonglong, c_ptr])
-declare("b200mm_embed_layernorm_fwd", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                       c_int, c_int, c_float, c_float, c_ulonglong, c_ptr])
-declare("b200mm_layernorm_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int,
+declare("b200mm_embed_layernorm_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       c_ptr, c_ptr, c_int, c_int, c_float, c_float, c_ulonglong, c_ptr])
+declare("b200mm_layernorm_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int,
                                  c_float, c_ulonglong, c_float, c_ulonglong, c_ptr])
-declare("b200mm_embedding_bwd", [c_ptr, c_ptr, c_int, c_int, c_longlong, c_ptr, c_ptr, c_int, c_int, c_ptr])
+declare("b200mm_embedding_bwd", [c_ptr, c_ptr, c_ptr, c_longlong, c_int, c_int, c_longlong, c_ptr, c_ptr, c_int,
+                                 c_int, c_ptr])
+declare("b200mm_position_ids", [c_ptr, c_longlong, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_vit_assemble_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr])
+declare("b200mm_vit_assemble_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr])
 declare("b200mm_mask_to_bias", [c_ptr, c_ptr, c_longlong, c_ptr])
 declare("b200mm_colsum_bf16", [c_ptr, c_longlong, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_head_loss", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_float, c_float, c_int,

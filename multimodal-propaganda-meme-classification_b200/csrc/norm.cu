@@ -44,7 +44,8 @@ __device__ __forceinline__ void drop_scale8(const DropSpec& d, long long idx, fl
 template <bool EMBED>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ ids,
-                     const float* __restrict__ word, const float* __restrict__ pos, int S, int vocab,
+                     const float* __restrict__ word, const float* __restrict__ pos, const int* __restrict__ pos_ids,
+                     const float* __restrict__ type_row, int S, int vocab,
                      __nv_bfloat16* __restrict__ x_saved, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, int D, float eps, DropSpec drop) {
@@ -60,7 +61,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
     long long id = ids[row];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     wrow = word + id * D;
-    prow = pos + static_cast<long long>(row % S) * D;
+    // BERT-family position ids are 0..S-1; RoBERTa / XLM-R derive them from the pad pattern (pos_ids)
+    prow = pos + static_cast<long long>(pos_ids != nullptr ? pos_ids[row] : row % S) * D;
   }
 #pragma unroll
   for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
@@ -73,6 +75,12 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
         const float4 b1 = __ldg(reinterpret_cast<const float4*>(prow + c * 8 + 4));
         v[j][0] = a0.x + b0.x; v[j][1] = a0.y + b0.y; v[j][2] = a0.z + b0.z; v[j][3] = a0.w + b0.w;
         v[j][4] = a1.x + b1.x; v[j][5] = a1.y + b1.y; v[j][6] = a1.z + b1.z; v[j][7] = a1.w + b1.w;
+        if (type_row != nullptr) {   // token_type_embeddings[0] (all segment ids are 0 on this path)
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(type_row + c * 8));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(type_row + c * 8 + 4));
+          v[j][0] += t0.x; v[j][1] += t0.y; v[j][2] += t0.z; v[j][3] += t0.w;
+          v[j][4] += t1.x; v[j][5] += t1.y; v[j][6] += t1.z; v[j][7] += t1.w;
+        }
         store8(x_saved + row * D + c * 8, v[j]);
         // statistics are taken on the bf16-rounded values: that is what the backward will see
         load8(x_saved + row * D + c * 8, v[j]);
@@ -133,9 +141,9 @@ template <int NC>
 __global__ void __launch_bounds__(LN_WARPS * 32, NC <= 3 ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
-                     __nv_bfloat16* __restrict__ dx2, float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
-                     int D, int rows_per_cta, DropSpec in_drop, DropSpec out_drop) {
+                     const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ addend,
+                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx2, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int M, int D, int rows_per_cta, DropSpec in_drop, DropSpec out_drop) {
   extern __shared__ float red[];  // [LN_WARPS][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = D >> 3;
@@ -189,7 +197,15 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = rstd * (g_dy[j][i] - s1 - xh[j][i] * s2);
-        store8(dx + row * D + c * 8, o);
+        if (addend != nullptr) {   // pre-LN blocks: the residual stream's gradient joins here (dx2 stays LN-only)
+          float a[8], t[8];
+          load8(addend + row * D + c * 8, a);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = o[i] + a[i];
+          store8(dx + row * D + c * 8, t);
+        } else {
+          store8(dx + row * D + c * 8, o);
+        }
         if (dx2 != nullptr) {
           float s[8];
           drop_scale8(out_drop, row * D + c * 8, s);
@@ -229,7 +245,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 
 // Embedding backward: scatter-add d(word+pos sum) rows into the fp32 gradient tables.
 __global__ void __launch_bounds__(256)
-embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const long long* __restrict__ ids, int S, int vocab,
+embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const long long* __restrict__ ids,
+                     const int* __restrict__ pos_ids, long long pos_padding_idx, int S, int vocab,
                      long long padding_idx, float* __restrict__ dword, float* __restrict__ dpos, int M, int D) {
   const int chunks = D >> 2;
   const long long total = static_cast<long long>(M) * chunks;
@@ -242,11 +259,97 @@ embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const long long* __re
     const uint2 r = *reinterpret_cast<const uint2*>(dx + row * D + c);
     const float2 a = unpack_bf16x2_dev(r.x), b = unpack_bf16x2_dev(r.y);
     float* w = dword + id * D + c;
-    float* q = dpos + static_cast<long long>(row % S) * D + c;
+    const long long pid = pos_ids != nullptr ? pos_ids[row] : row % S;
+    float* q = dpos + pid * D + c;
     // nn.Embedding(padding_idx=pad_token_id): the pad row never receives a gradient (modeling_distilbert.py:86)
     if (ids[row] != padding_idx)
       asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(w), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    // RoBERTa's position table is nn.Embedding(padding_idx=pad): its pad row gets no gradient either
+    if (pid != pos_padding_idx)
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(q), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+  }
+}
+
+// RoBERTa / XLM-R position ids (transformers/models/xlm_roberta/modeling_xlm_roberta.py
+// create_position_ids_from_input_ids): pos = cumsum(ids != pad) * (ids != pad) + pad.  One warp per sequence.
+__global__ void __launch_bounds__(128)
+position_ids_kernel(const long long* __restrict__ ids, long long pad_id, int B, int S, int* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 4 + warp;
+  if (b >= B) return;
+  int carry = 0;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + lane;
+    const int real = (s < S && ids[static_cast<long long>(b) * S + s] != pad_id) ? 1 : 0;
+    int scan = real;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, scan, o);
+      if (lane >= o) scan += t;
+    }
+    if (s < S) out[static_cast<long long>(b) * S + s] = real ? carry + scan + static_cast<int>(pad_id) : static_cast<int>(pad_id);
+    carry += __shfl_sync(0xffffffffu, scan, 31);
+  }
+}
+
+// ViT token assembly (transformers/models/vit/modeling_vit.py ViTEmbeddings.forward):
+//   x[b, 0] = cls + pos[0];  x[b, 1 + i] = patch[b, i] + pos[1 + i]      (fp32 cls / pos, bf16 tokens)
+__global__ void __launch_bounds__(256)
+vit_assemble_fwd_kernel(const __nv_bfloat16* __restrict__ patch, const float* __restrict__ cls,
+                        const float* __restrict__ pos, __nv_bfloat16* __restrict__ x, int B, int P, int D) {
+  const int chunks = D >> 3;
+  const long long total = static_cast<long long>(B) * (P + 1) * chunks;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / chunks;
+    const int c = static_cast<int>(i - row * chunks) * 8;
+    const int b = static_cast<int>(row / (P + 1)), t = static_cast<int>(row - static_cast<long long>(b) * (P + 1));
+    float v[8];
+    if (t == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = cls[c + k];
+    } else {
+      load8(patch + (static_cast<long long>(b) * P + (t - 1)) * D + c, v);
+    }
+    const float* pr = pos + static_cast<long long>(t) * D + c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += pr[k];
+    store8(x + row * D + c, v);
+  }
+}
+
+// backward of the assembly: dpatch[b, i] = dx[b, 1 + i];  dpos[t] += sum_b dx[b, t];  dcls += sum_b dx[b, 0].
+// One CTA per token position t, thread = 8 channels, loop over the batch (coalesced 16-byte reads).
+__global__ void __launch_bounds__(256)
+vit_assemble_bwd_kernel(const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dpatch,
+                        float* __restrict__ dcls, float* __restrict__ dpos, int B, int P, int D) {
+  const int t = blockIdx.x;
+  for (int c = threadIdx.x * 8; c < D; c += blockDim.x * 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    constexpr int U = 4;
+    for (int b0 = 0; b0 < B; b0 += U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        raw[u] = (b0 + u) < B ? __ldg(reinterpret_cast<const uint4*>(
+                                    dx + (static_cast<long long>(b0 + u) * (P + 1) + t) * D + c))
+                              : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (b0 + u >= B) break;
+        if (t > 0)
+          *reinterpret_cast<uint4*>(dpatch + (static_cast<long long>(b0 + u) * P + (t - 1)) * D + c) = raw[u];
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      dpos[static_cast<long long>(t) * D + c + k] += acc[k];
+      if (t == 0) dcls[c + k] += acc[k];
+    }
   }
 }
 
@@ -269,28 +372,32 @@ B200MM_API int b200mm_layernorm_fwd(const void* x, const float* gamma, const flo
                                     void* stream) {
   if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
   layernorm_fwd_kernel<false><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, 1, 1, nullptr, gamma, beta,
+      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, nullptr, 1, 1, nullptr, gamma, beta,
       static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed));
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
 
-// Embeddings: x_saved = bf16(word[ids] + pos[t]); y = dropout(LayerNorm(x_saved)).  ids int64 [M = B*S].
-B200MM_API int b200mm_embed_layernorm_fwd(const long long* ids, const float* word, const float* pos, int S, int vocab,
+// Embeddings: x_saved = bf16(word[ids] + pos[pos_ids ? pos_ids[m] : m % S] (+ type_row)); y = dropout(LN(x_saved)).
+// ids int64 [M = B*S]; pos_ids (nullable) int32 [M]; type_row (nullable) fp32 [D] = token_type_embeddings[0].
+B200MM_API int b200mm_embed_layernorm_fwd(const long long* ids, const float* word, const float* pos,
+                                          const int* pos_ids, const float* type_row, int S, int vocab,
                                           const float* gamma, const float* beta, void* x_saved, void* y, float* mean,
                                           float* rstd, int M, int D, float eps, float p_drop, unsigned long long seed,
                                           void* stream) {
   if (!ln_shape_ok(M, D) || S <= 0 || vocab <= 0) return B200MM_ERR_BAD_ARG;
   layernorm_fwd_kernel<true><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, ids, word, pos, S, vocab, static_cast<__nv_bfloat16*>(x_saved), gamma, beta,
+      nullptr, ids, word, pos, pos_ids, type_row, S, vocab, static_cast<__nv_bfloat16*>(x_saved), gamma, beta,
       static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed));
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
 
-// LayerNorm backward.  dx2 (nullable) receives dx with the (p_out, seed_out) dropout mask applied.
+// LayerNorm backward.  dx2 (nullable) receives the LN gradient with the (p_out, seed_out) dropout mask applied;
+// addend (nullable, bf16 [M,D]) is added to dx only (pre-LN residual stream).
 B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
-                                    const float* gamma, void* dx, void* dx2, float* dgamma, float* dbeta, int M, int D,
+                                    const float* gamma, const void* addend, void* dx, void* dx2, float* dgamma,
+                                    float* dbeta, int M, int D,
                                     float p_in, unsigned long long seed_in, float p_out, unsigned long long seed_out,
                                     void* stream) {
   if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
@@ -314,7 +421,8 @@ B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* 
     }                                                                                                              \
     layernorm_bwd_kernel<NC><<<grid, LN_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                    \
         static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd, gamma,            \
-        static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dx2), dgamma, dbeta, M, D, rows_per_cta,      \
+        static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(dx),                                \
+        static_cast<__nv_bfloat16*>(dx2), dgamma, dbeta, M, D, rows_per_cta,                                       \
         make_drop(p_in, seed_in), make_drop(dx2 ? p_out : 0.f, seed_out));                                         \
   } while (0)
   if (nc <= 1) LAUNCH_LN_BWD(1);
@@ -327,14 +435,16 @@ B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* 
   return B200MM_OK;
 }
 
-// dword[ids[m]] += dx[m] (skipped where ids[m] == padding_idx; pass -1 for none), dpos[m % S] += dx[m]
-B200MM_API int b200mm_embedding_bwd(const void* dx, const long long* ids, int S, int vocab, long long padding_idx,
+// dword[ids[m]] += dx[m] (skipped where ids[m] == padding_idx; pass -1 for none);
+// dpos[pos_ids ? pos_ids[m] : m % S] += dx[m] (skipped where that index == pos_padding_idx; -1 for none)
+B200MM_API int b200mm_embedding_bwd(const void* dx, const long long* ids, const int* pos_ids,
+                                    long long pos_padding_idx, int S, int vocab, long long padding_idx,
                                     float* dword, float* dpos, int M, int D, void* stream) {
   if (M <= 0 || D <= 0 || (D & 3) || S <= 0) return B200MM_ERR_BAD_ARG;
   const long long total = static_cast<long long>(M) * (D >> 2);
   const int grid = static_cast<int>(total / 256 > 148 * 16 ? 148 * 16 : ceil_div(total, 256LL));
   embedding_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dx), ids, S, vocab, padding_idx, dword, dpos, M, D);
+      static_cast<const __nv_bfloat16*>(dx), ids, pos_ids, pos_padding_idx, S, vocab, padding_idx, dword, dpos, M, D);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -342,6 +452,35 @@ B200MM_API int b200mm_embedding_bwd(const void* dx, const long long* ids, int S,
 B200MM_API int b200mm_mask_to_bias(const long long* mask, float* bias, long long n, void* stream) {
   if (n <= 0) return B200MM_ERR_BAD_ARG;
   mask_to_bias_kernel<<<static_cast<int>(ceil_div(n, 256LL)), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, bias, n);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// pos_ids[B*S] (int32) = cumsum(ids != pad) * (ids != pad) + pad   (RoBERTa / XLM-R position ids)
+B200MM_API int b200mm_position_ids(const long long* ids, long long pad_id, int B, int S, int* out, void* stream) {
+  if (B <= 0 || S <= 0) return B200MM_ERR_BAD_ARG;
+  position_ids_kernel<<<ceil_div(B, 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(ids, pad_id, B, S, out);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// ViT embeddings: tokens[B*(P+1), D] = [cls | patch rows] + pos   and the backward of that assembly.
+B200MM_API int b200mm_vit_assemble_fwd(const void* patch, const float* cls, const float* pos, void* x, int B, int P,
+                                       int D, void* stream) {
+  if (B <= 0 || P <= 0 || D <= 0 || (D & 7)) return B200MM_ERR_BAD_ARG;
+  const long long total = static_cast<long long>(B) * (P + 1) * (D >> 3);
+  const int grid = static_cast<int>(total / 256 > 148 * 16 ? 148 * 16 : ceil_div(total, 256LL));
+  vit_assemble_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(patch), cls, pos, static_cast<__nv_bfloat16*>(x), B, P, D);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+B200MM_API int b200mm_vit_assemble_bwd(const void* dx, void* dpatch, float* dcls, float* dpos, int B, int P, int D,
+                                       void* stream) {
+  if (B <= 0 || P <= 0 || D <= 0 || (D & 7)) return B200MM_ERR_BAD_ARG;
+  const int threads = D / 8 < 256 ? ((D / 8 + 31) / 32) * 32 : 256;
+  vit_assemble_bwd_kernel<<<P + 1, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dpatch), dcls, dpos, B, P, D);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

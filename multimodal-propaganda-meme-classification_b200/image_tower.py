@@ -29,6 +29,7 @@ class ImageConfig:
     bn_eps: float = 1e-5
     bn_momentum: float = 0.1
     prefix: str = "resnet"
+    arch: str = "resnet"
 
 
 class _Conv:
@@ -65,7 +66,9 @@ class ImageTower:
                 self.blocks.append(blk)
                 inplanes = planes * 4
         self.feat_dim = inplanes
+        self.out_dim = cfg.num_outputs   # the 1000-way ImageNet fc is kept (.txt:164-165)
         self._convs = [self.stem] + [c for b in self.blocks for c in (b["c1"], b["c2"], b["c3"], b["ds"]) if c]
+        self._conv_by_weight = {c.name + ".weight": c for c in self._convs}
         self._saved = None
         self.buffers = None
         self.capture = None   # set to a list to record every block's output (per-layer parity checks)
@@ -121,6 +124,34 @@ class ImageTower:
         st.p(f"{p}.fc.weight").uniform_(-bound, bound, generator=generator)
         st.p(f"{p}.fc.bias").uniform_(-bound, bound, generator=generator)
 
+    # ------------------------------------------------------------------ state-dict layout exchange (see model.py)
+    def import_param(self, name: str, src: torch.Tensor, dst: torch.Tensor) -> None:
+        """torch layout -> engine layout: conv OIHW -> OHWI-flattened (stem K padded 147 -> 152)."""
+        if src.dim() == 4:
+            co, ci, kh, kw = src.shape
+            flat = src.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+            dst.zero_()
+            dst[:, :flat.shape[1]].copy_(flat)
+        else:
+            dst.copy_(src.view(dst.shape))
+
+    def export_param(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        c = self._conv_by_weight.get(name)
+        if c is None:
+            return t
+        return t[:, :c.k * c.k * c.cin].reshape(c.cout, c.k, c.k, c.cin).permute(0, 3, 1, 2).contiguous()
+
+    def load_buffers(self, sd: dict) -> None:
+        for c in self._convs:
+            c.rm.copy_(sd[f"{c.bn_name}.running_mean"])
+            c.rv.copy_(sd[f"{c.bn_name}.running_var"])
+
+    def export_buffers(self, out: dict) -> None:
+        for c in self._convs:
+            out[f"{c.bn_name}.running_mean"] = c.rm.clone()
+            out[f"{c.bn_name}.running_var"] = c.rv.clone()
+            out[f"{c.bn_name}.num_batches_tracked"] = torch.tensor(self.num_batches_tracked)
+
     # ------------------------------------------------------------------ building blocks
     def _bn(self, c, x, training, residual=None, relu=True):
         cfg = self.cfg
@@ -130,8 +161,9 @@ class ImageTower:
         return ops.batchnorm_eval(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps), None, None
 
     # ------------------------------------------------------------------ forward
-    def forward(self, image: torch.Tensor, *, training: bool):
-        """image: fp32 NCHW [N, 3, H, W] (what the reference's transforms produce). Returns bf16 [N, 1000]."""
+    def forward(self, image: torch.Tensor, *, training: bool, seed: int = 0, step: int = 0):
+        """image: fp32 NCHW [N, 3, H, W] (what the reference's transforms produce). Returns bf16 [N, 1000].
+        (seed / step: unused -- the ResNet has no dropout; kept for the tower interface shared with ViTTower.)"""
         N, Cin, H, W = image.shape
         assert Cin == 3
         sv = {"N": N, "blocks": []} if training else None

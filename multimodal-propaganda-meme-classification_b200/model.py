@@ -20,9 +20,10 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .image_tower import STEM_K, ImageConfig, ImageTower
+from .image_tower import ImageConfig, ImageTower
 from .params import ParamStore
 from .text_tower import TextConfig, TextTower, _mix
+from .vit_tower import ViTConfig, ViTTower
 
 POOL_LAST, POOL_CLS = "last", "cls"
 
@@ -44,8 +45,8 @@ class _EngineFunction(torch.autograd.Function):
 
 class MultimodalClassifier(nn.Module):
     def __init__(self, num_classes: int = 2, *, text_config: TextConfig | None = None,
-                 image_config: ImageConfig | None = None, device=None, head_dropout: float = 0.3,
-                 pooling: str = POOL_LAST, seed: int = 42, init: bool = True, squeeze_output: bool = False):
+                 image_config: ImageConfig | ViTConfig | None = None, device=None, head_dropout: float = 0.3,
+                 pooling: str | None = None, seed: int = 42, init: bool = True, squeeze_output: bool = False):
         super().__init__()
         if not torch.cuda.is_available():
             raise _lib.B200MMError("b200mm needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -53,17 +54,21 @@ class MultimodalClassifier(nn.Module):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.num_classes = num_classes
         self.head_dropout = head_dropout       # self.bert_drop = nn.Dropout(0.3), .txt:160
-        self.pooling = pooling                 # 'last' = bert_output[0][:, -1, :], .txt:178 ; 'cls' = HEAD script
+        self.tcfg = text_config or TextConfig()
+        self.icfg = image_config or ImageConfig()
+        if pooling is None:     # 'last' = bert_output[0][:, -1, :], .txt:178 ; 'cls' = HEAD script (.py:359-360)
+            pooling = POOL_LAST if self.tcfg.arch == "distilbert" else POOL_CLS
+        if pooling not in (POOL_LAST, POOL_CLS):
+            raise ValueError(f"Unsupported pooling method: {pooling}")     # HEAD script :352
+        self.pooling = pooling
         self.squeeze_output = squeeze_output   # single-logit head: return [B] like output.squeeze_(1) (HEAD :683)
         self.seed = seed
         self._step = 0
-        self.tcfg = text_config or TextConfig()
-        self.icfg = image_config or ImageConfig()
         with torch.cuda.device(self.device):
             st = ParamStore(self.device)
             self.store = st
             self.text = TextTower(self.tcfg, st)
-            self.img = ImageTower(self.icfg, st)
+            self.img = ViTTower(self.icfg, st) if self.icfg.arch == "vit" else ImageTower(self.icfg, st)
             D = self.tcfg.dim
             # --- shadow-less (fp32-read) parameters first
             self.text.register_noshadow()
@@ -75,7 +80,7 @@ class MultimodalClassifier(nn.Module):
             self.text.register_shadowed()
             self.img.register_shadowed()
             st.add("bert_fc.weight", (512, D))                          # .txt:161
-            st.add("resnet_fc.weight", (512, self.icfg.num_outputs))    # .txt:165
+            st.add("resnet_fc.weight", (512, self.img.out_dim))         # .txt:165 (1000 for the ResNet, dim for ViT)
             st.add("fusion_fc.weight", (512, 1024))                     # .txt:168
             st.finalize()
             self.text.bind()
@@ -133,7 +138,7 @@ class MultimodalClassifier(nn.Module):
         self.text.init_parameters(g)
         self.img.init_parameters(g)
         st = self.store
-        for name, fan_in in (("bert_fc", self.tcfg.dim), ("resnet_fc", self.icfg.num_outputs), ("fusion_fc", 1024),
+        for name, fan_in in (("bert_fc", self.tcfg.dim), ("resnet_fc", self.img.out_dim), ("fusion_fc", 1024),
                              ("output_fc", 512)):
             bound = 1.0 / (fan_in ** 0.5)   # nn.Linear default init
             st.p(f"{name}.weight").uniform_(-bound, bound, generator=g)
@@ -144,23 +149,21 @@ class MultimodalClassifier(nn.Module):
     @torch.no_grad()
     def load_reference_state_dict(self, sd: dict):
         """Copy weights from the reference/oracle module's ``state_dict()`` (torch layouts) into the engine layout:
-        conv OIHW -> OHWI-flattened (stem K padded 147 -> 152); everything else is a straight copy."""
+        conv OIHW -> OHWI-flattened (K zero-padded to a multiple of 8); everything else is a straight copy.  Keys
+        the engine does not hold (BERT ``pooler.*``, which the path never reads; ``position_ids`` buffers) are
+        ignored."""
         st = self.store
         used = set()
+        img_prefix = self.icfg.prefix + "."
         for name in st.names():
             dst = st.p(name)
             src = sd[name].to(self.device, torch.float32)
             used.add(name)
-            if src.dim() == 4:
-                co, ci, kh, kw = src.shape
-                flat = src.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
-                dst.zero_()
-                dst[:, :flat.shape[1]].copy_(flat)
+            if name.startswith(img_prefix):
+                self.img.import_param(name, src, dst)
             else:
                 dst.copy_(src.view(dst.shape))
-        for c in self.img._convs:
-            c.rm.copy_(sd[f"{c.bn_name}.running_mean"])
-            c.rv.copy_(sd[f"{c.bn_name}.running_var"])
+        self.img.load_buffers(sd)
         st.refresh_shadow()
         return used
 
@@ -171,22 +174,16 @@ class MultimodalClassifier(nn.Module):
 
     @torch.no_grad()
     def reference_state_dict(self, _grads: bool = False) -> dict:
-        """Inverse of ``load_reference_state_dict``: a state dict the reference module can ``load_state_dict``."""
+        """Inverse of ``load_reference_state_dict``: a state dict the reference module can ``load_state_dict``
+        (``strict=False`` for BERT-family towers, whose unused pooler the engine does not carry)."""
         st = self.store
         out = {}
-        conv = {c.name + ".weight": c for c in self.img._convs}
+        img_prefix = self.icfg.prefix + "."
         for name in st.names():
             t = (st.g(name) if _grads else st.p(name)).detach().clone()
-            if name in conv:
-                c = conv[name]
-                t = t[:, :c.k * c.k * c.cin].reshape(c.cout, c.k, c.k, c.cin).permute(0, 3, 1, 2).contiguous()
-            out[name] = t
-        if _grads:
-            return out
-        for c in self.img._convs:
-            out[f"{c.bn_name}.running_mean"] = c.rm.clone()
-            out[f"{c.bn_name}.running_var"] = c.rv.clone()
-            out[f"{c.bn_name}.num_batches_tracked"] = torch.tensor(self.img.num_batches_tracked)
+            out[name] = self.img.export_param(name, t) if name.startswith(img_prefix) else t
+        if not _grads:
+            self.img.export_buffers(out)
         return out
 
     def state_dict(self, *args, **kwargs):
@@ -205,7 +202,7 @@ class MultimodalClassifier(nn.Module):
         s_head = _mix(self.seed, self._step, 254, 0)
         pd = self.head_dropout if training else 0.0
         pooled = ops.gather_rows(h, B, S, off, p_drop=pd, seed=s_head)                             # bert_drop(h[:, -1])
-        r1000 = self.img.forward(image, training=training)                                         # [B, 1000]
+        r1000 = self.img.forward(image, training=training, seed=self.seed, step=self._step)        # [B, 1000 | dim]
         cat = torch.empty(B, 1024, device=self.device, dtype=torch.bfloat16)
         ops.linear_fwd(pooled, st.s("bert_fc.weight"), st.p("bert_fc.bias"), out=cat[:, :512])      # .txt:179
         ops.linear_fwd(r1000, st.s("resnet_fc.weight"), st.p("resnet_fc.bias"), out=cat[:, 512:])   # .txt:184, 190
@@ -265,7 +262,7 @@ class MultimodalClassifier(nn.Module):
         """One process per GPU: broadcast rank 0's parameters / BN buffers and all-reduce gradients every step."""
         from .ddp import GradSync
         self.grad_sync = GradSync(self.store, group, bucket_elems)
-        self.grad_sync.broadcast_parameters([self.img.buffers])
+        self.grad_sync.broadcast_parameters([self.img.buffers] if self.img.buffers is not None else [])
         self.store.refresh_shadow()
         return self.grad_sync
 

@@ -233,7 +233,7 @@ def layernorm_fwd(x, gamma, beta, eps, *, p_drop=0.0, seed=0):
     return y, mean, rstd
 
 
-def embed_layernorm_fwd(ids, word, pos, gamma, beta, eps, *, p_drop=0.0, seed=0):
+def embed_layernorm_fwd(ids, word, pos, gamma, beta, eps, *, p_drop=0.0, seed=0, pos_ids=None, type_row=None):
     B, S = ids.shape
     V, D = word.shape
     M = B * S
@@ -241,25 +241,53 @@ def embed_layernorm_fwd(ids, word, pos, gamma, beta, eps, *, p_drop=0.0, seed=0)
     y = torch.empty(M, D, device=ids.device, dtype=bf16)
     mean = torch.empty(M, device=ids.device, dtype=f32)
     rstd = torch.empty(M, device=ids.device, dtype=f32)
-    _lib.call("b200mm_embed_layernorm_fwd", _p(ids), _p(word), _p(pos), S, V, _p(gamma), _p(beta), _p(x_saved), _p(y),
+    _lib.call("b200mm_embed_layernorm_fwd", _p(ids), _p(word), _p(pos), _p(pos_ids), _p(type_row), S, V, _p(gamma),
+              _p(beta), _p(x_saved), _p(y),
               _p(mean), _p(rstd), M, D, float(eps), float(p_drop), int(seed), _s())
     return y, x_saved, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0):
-    """Returns (dx, dx_masked) where dx_masked is None unless p_out > 0."""
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, *, p_in=0.0, seed_in=0, p_out=0.0, seed_out=0,
+                  addend=None):
+    """Returns (dx, dx_masked) where dx_masked is None unless p_out > 0.  ``addend`` (bf16 [M,D]) is added to dx
+    only (the residual-stream gradient of a pre-LN block)."""
     M, D = x.shape
     dx = torch.empty_like(x)
     dx2 = torch.empty_like(x) if p_out > 0 else None
-    _lib.call("b200mm_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dx2), _p(dgamma),
+    _lib.call("b200mm_layernorm_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(addend), _p(dx), _p(dx2),
+              _p(dgamma),
               _p(dbeta), M, D, float(p_in), int(seed_in), float(p_out), int(seed_out), _s())
     return dx, dx2
 
 
-def embedding_bwd(dx, ids, dword, dpos, padding_idx=-1):
+def embedding_bwd(dx, ids, dword, dpos, padding_idx=-1, *, pos_ids=None, pos_padding_idx=-1):
     B, S = ids.shape
     V, D = dword.shape
-    _lib.call("b200mm_embedding_bwd", _p(dx), _p(ids), S, V, int(padding_idx), _p(dword), _p(dpos), B * S, D, _s())
+    _lib.call("b200mm_embedding_bwd", _p(dx), _p(ids), _p(pos_ids), int(pos_padding_idx), S, V, int(padding_idx),
+              _p(dword), _p(dpos), B * S, D, _s())
+
+
+def position_ids(ids, pad_id):
+    """RoBERTa / XLM-R position ids (int32 [B, S]): cumsum(ids != pad) * (ids != pad) + pad."""
+    _chk(ids, torch.int64, "input_ids")
+    B, S = ids.shape
+    out = torch.empty(B, S, device=ids.device, dtype=torch.int32)
+    _lib.call("b200mm_position_ids", _p(ids), int(pad_id), B, S, _p(out), _s())
+    return out
+
+
+def vit_assemble_fwd(patch, cls, pos, B, P):
+    D = patch.shape[1]
+    x = torch.empty(B * (P + 1), D, device=patch.device, dtype=bf16)
+    _lib.call("b200mm_vit_assemble_fwd", _p(patch), _p(cls), _p(pos), _p(x), B, P, D, _s())
+    return x
+
+
+def vit_assemble_bwd(dx, dcls, dpos, B, P):
+    D = dx.shape[1]
+    dpatch = torch.empty(B * P, D, device=dx.device, dtype=bf16)
+    _lib.call("b200mm_vit_assemble_bwd", _p(dx), _p(dpatch), _p(dcls), _p(dpos), B, P, D, _s())
+    return dpatch
 
 
 def gather_rows(x, rows, stride_rows, offset_rows, *, p_drop=0.0, seed=0):

@@ -47,12 +47,52 @@ class TowerConfig:
     resnet_width: int = 64
     image_size: int = 224
     num_classes: int = 2
+    # --- BASELINE configs 3-5 / HEAD-script towers (same head, towers swapped)
+    text_arch: str = "distilbert"        # 'distilbert' | 'bert' | 'roberta' (RoBERTa / XLM-R)
+    layer_norm_eps: float = 1e-12
+    pad_token_id: int = 0
+    type_vocab_size: int = 2
+    pooling: str = "last"                # 'last' = h[:, -1] (.txt:178) ; 'cls' = h[:, 0] (HEAD .py:359-360)
+    image_arch: str = "resnet"           # 'resnet' | 'vit'
+    vit_patch: int = 16
+    vit_dim: int = 768
+    vit_layers: int = 12
+    vit_heads: int = 12
+    vit_hidden: int = 3072
 
     @staticmethod
     def tiny(**kw) -> "TowerConfig":
         """A small instance of the same graph for fast CPU/GPU parity tests."""
         base = dict(vocab_size=1024, max_position_embeddings=128, dim=128, n_layers=2, n_heads=2,
                     hidden_dim=256, resnet_layers=(1, 1, 1, 1), image_size=64)
+        base.update(kw)
+        return TowerConfig(**base)
+
+    @staticmethod
+    def vit_b16_bert_base(**kw) -> "TowerConfig":
+        """BASELINE configs 3 / 5: ViT-B/16 + BERT-base (AraBERT-shaped, vocab 64000), CLS pooling."""
+        base = dict(vocab_size=64000, n_layers=12, text_arch="bert", pooling="cls", image_arch="vit")
+        base.update(kw)
+        return TowerConfig(**base)
+
+    @staticmethod
+    def vit_l14_xlmr_large(**kw) -> "TowerConfig":
+        """BASELINE config 4: ViT-L/14 + XLM-R-large."""
+        base = dict(vocab_size=250002, max_position_embeddings=514, dim=1024, n_layers=24, n_heads=16,
+                    hidden_dim=4096, text_arch="roberta", layer_norm_eps=1e-5, pad_token_id=1, type_vocab_size=1,
+                    pooling="cls", image_arch="vit", vit_patch=14, vit_dim=1024, vit_layers=24, vit_heads=16,
+                    vit_hidden=4096)
+        base.update(kw)
+        return TowerConfig(**base)
+
+    @staticmethod
+    def tiny_vit_bert(text_arch: str = "bert", **kw) -> "TowerConfig":
+        """Small instance of the config-3/4/5 graph (ViT + BERT / RoBERTa-style text tower)."""
+        rob = text_arch == "roberta"
+        base = dict(vocab_size=1024, max_position_embeddings=130, dim=128, n_layers=2, n_heads=2, hidden_dim=256,
+                    text_arch=text_arch, layer_norm_eps=1e-5 if rob else 1e-12, pad_token_id=1 if rob else 0,
+                    type_vocab_size=1 if rob else 2, pooling="cls", image_arch="vit", image_size=64, vit_patch=16,
+                    vit_dim=128, vit_layers=2, vit_heads=2, vit_hidden=256)
         base.update(kw)
         return TowerConfig(**base)
 
@@ -65,6 +105,43 @@ def build_distilbert(cfg: TowerConfig, eager: bool = True):
     if eager:
         hf._attn_implementation = "eager"
     return DistilBertModel(hf)
+
+
+def build_bert(cfg: TowerConfig, eager: bool = True):
+    """BERT-base / AraBERT (HEAD script ``AutoModel.from_pretrained(text_model)``, Multimodal_example_task2C.py:317)
+    or RoBERTa / XLM-R (``caption_text_model``, :337; BASELINE config 4) from config -- random init, no network."""
+    if cfg.text_arch == "bert":
+        from transformers import BertConfig as C, BertModel as M
+    else:
+        from transformers import XLMRobertaConfig as C, XLMRobertaModel as M
+    hf = C(vocab_size=cfg.vocab_size, hidden_size=cfg.dim, num_hidden_layers=cfg.n_layers,
+           num_attention_heads=cfg.n_heads, intermediate_size=cfg.hidden_dim,
+           max_position_embeddings=cfg.max_position_embeddings, hidden_dropout_prob=cfg.dropout,
+           attention_probs_dropout_prob=cfg.attention_dropout, layer_norm_eps=cfg.layer_norm_eps,
+           pad_token_id=cfg.pad_token_id, type_vocab_size=cfg.type_vocab_size)
+    if eager:
+        hf._attn_implementation = "eager"
+    return M(hf)
+
+
+def build_text(cfg: TowerConfig, eager: bool = True):
+    return build_distilbert(cfg, eager) if cfg.text_arch == "distilbert" else build_bert(cfg, eager)
+
+
+def build_vit(cfg: TowerConfig, eager: bool = True):
+    """transformers ViTModel without pooler: CLS token, pre-LN blocks, final LayerNorm (what the reference's
+    commented ``vit_base_patch16_224`` / ``ViTModel`` lines point at; Multimodal_example_task2C.py:82,
+    mm_model_mm_example_task2C.py:66-67)."""
+    from transformers import ViTConfig, ViTModel
+    hf = ViTConfig(hidden_size=cfg.vit_dim, num_hidden_layers=cfg.vit_layers, num_attention_heads=cfg.vit_heads,
+                   intermediate_size=cfg.vit_hidden, image_size=cfg.image_size, patch_size=cfg.vit_patch)
+    if eager:
+        hf._attn_implementation = "eager"
+    return ViTModel(hf, add_pooling_layer=False)
+
+
+def build_image(cfg: TowerConfig):
+    return build_resnet(cfg) if cfg.image_arch == "resnet" else build_vit(cfg)
 
 
 def build_resnet(cfg: TowerConfig):
@@ -80,19 +157,23 @@ class MultimodalClassifier(nn.Module):
         super().__init__()
         cfg = cfg or TowerConfig()
         self.cfg = cfg
-        self.bert = build_distilbert(cfg)                      # .txt:158
+        self.bert = build_text(cfg)                            # .txt:158
         self.bert_drop = nn.Dropout(cfg.head_dropout)          # .txt:160
         self.bert_fc = nn.Linear(cfg.dim, 512)                 # .txt:161
-        self.resnet = build_resnet(cfg)                        # .txt:164
-        self.resnet_fc = nn.Linear(1000, 512)                  # .txt:165
+        self.resnet = build_image(cfg)                         # .txt:164
+        self.resnet_fc = nn.Linear(1000 if cfg.image_arch == "resnet" else cfg.vit_dim, 512)   # .txt:165
         self.fusion_fc = nn.Linear(1024, 512)                  # .txt:168
         self.output_fc = nn.Linear(512, num_classes)           # .txt:170
 
     def forward(self, text, image, mask):
         bert_output = self.bert(text, attention_mask=mask, return_dict=False)   # .txt:175
-        bert_output = self.bert_drop(bert_output[0][:, -1, :])                  # .txt:178 (LAST position)
+        tok = -1 if self.cfg.pooling == "last" else 0                           # HEAD script pools CLS (.py:359-360)
+        bert_output = self.bert_drop(bert_output[0][:, tok, :])                 # .txt:178 (LAST position)
         bert_output = self.bert_fc(bert_output)                                 # .txt:179
-        resnet_output = self.resnet(image)                                      # .txt:183
+        if self.cfg.image_arch == "resnet":
+            resnet_output = self.resnet(image)                                  # .txt:183
+        else:
+            resnet_output = self.resnet(pixel_values=image).last_hidden_state[:, 0]   # ViT CLS feature
         resnet_output = self.resnet_fc(resnet_output)                           # .txt:184
         features = torch.cat((bert_output, resnet_output), dim=1)               # .txt:190
         features = self.fusion_fc(features)                                     # .txt:193
@@ -104,7 +185,7 @@ def zero_dropout(model: nn.Module) -> nn.Module:
     for m in model.modules():
         if isinstance(m, nn.Dropout):
             m.p = 0.0
-    if hasattr(model, "bert"):
+    if hasattr(model, "bert") and hasattr(model.bert, "transformer"):
         for layer in model.bert.transformer.layer:
             att = layer.attention
             if hasattr(att, "dropout") and isinstance(att.dropout, nn.Dropout):
@@ -128,7 +209,7 @@ def synthetic_batch(batch: int, seq_len: int, cfg: TowerConfig | None = None, se
     lengths[0] = seq_len
     pos = torch.arange(seq_len).unsqueeze(0)
     mask = (pos < lengths.unsqueeze(1)).long()
-    ids = ids * mask + PAD_ID * (1 - mask)
+    ids = ids * mask + cfg.pad_token_id * (1 - mask)
     labels = (torch.rand(batch, generator=g) < TRAIN_PRIOR).long()
     return {"text": ids.to(device), "text_mask": mask.to(device), "image": image.to(device),
             "label": labels.to(device)}

@@ -11,7 +11,7 @@ bf16 = torch.bfloat16
 
 
 def rel(a, b):
-    a, b = a.float(), b.float()
+    a, b = a.float().cpu(), b.float().cpu()
     return ((a - b).norm() / (b.norm() + 1e-12)).item()
 
 
@@ -450,3 +450,90 @@ def test_preprocess_u8_matches_torch_transforms(ops, cuda_device):
         top, left = int(round((nh - 224) / 2.0)), int(round((nw - 224) / 2.0))
         ref = (r[:, top:top + 224, left:left + 224] / 255.0 - mean) / std
         assert (out[k] - ref).abs().max().item() < 2e-4, (k, (out[k] - ref).abs().max().item())
+
+
+# ------------------------------------------------------------------ BERT / RoBERTa / ViT support kernels
+def test_position_ids_match_transformers(ops, cuda_device):
+    """RoBERTa / XLM-R position ids: cumsum(ids != pad) * (ids != pad) + pad
+    (transformers/models/xlm_roberta/modeling_xlm_roberta.py create_position_ids_from_input_ids)."""
+    g = torch.Generator().manual_seed(3)
+    B, S, pad = 7, 77, 1
+    ids = torch.randint(2, 500, (B, S), generator=g)
+    lens = torch.randint(1, S + 1, (B,), generator=g)
+    ids[torch.arange(S).unsqueeze(0) >= lens.unsqueeze(1)] = pad
+    ids[2, 5] = pad        # a pad in the middle of real tokens
+    mask = ids.ne(pad).int()
+    ref = (torch.cumsum(mask, dim=1) * mask).long() + pad
+    got = ops.position_ids(ids.to(cuda_device), pad)
+    assert torch.equal(got.cpu().long(), ref)
+
+
+def test_embedding_variants_fwd_bwd(ops, cuda_device):
+    """word + pos[pos_ids] + type[0] -> LN, and the matching scatter-add backward with both padding rows skipped."""
+    g = torch.Generator().manual_seed(5)
+    B, S, V, D, pad = 4, 24, 300, 128, 1
+    ids = torch.randint(2, V, (B, S), generator=g)
+    ids[:, 18:] = pad
+    word = torch.randn(V, D, generator=g)
+    pos = torch.randn(S + 2, D, generator=g)
+    typ = torch.randn(D, generator=g)
+    gamma, beta = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g)
+    dev = cuda_device
+    pos_ids = ops.position_ids(ids.to(dev), pad)
+    y, x_saved, mean, rstd = ops.embed_layernorm_fwd(ids.to(dev), word.to(dev), pos.to(dev), gamma.to(dev),
+                                                     beta.to(dev), 1e-5, pos_ids=pos_ids, type_row=typ.to(dev))
+    x_ref = word[ids] + pos[pos_ids.cpu().long()] + typ
+    y_ref = torch.nn.functional.layer_norm(x_ref, (D,), gamma, beta, 1e-5)
+    assert rel(x_saved.view(B, S, D), x_ref) < 5e-3
+    assert rel(y.view(B, S, D), y_ref) < 1e-2
+    dx = torch.randn(B * S, D, generator=g).to(dev).to(torch.bfloat16)
+    dword = torch.zeros(V, D, device=dev)
+    dpos = torch.zeros(S + 2, D, device=dev)
+    ops.embedding_bwd(dx, ids.to(dev), dword, dpos, padding_idx=pad, pos_ids=pos_ids, pos_padding_idx=pad)
+    dxf = dx.float().cpu().view(B, S, D)
+    dword_ref = torch.zeros(V, D).index_add_(0, ids.flatten(), dxf.view(-1, D))
+    dword_ref[pad] = 0
+    dpos_ref = torch.zeros(S + 2, D).index_add_(0, pos_ids.cpu().long().flatten(), dxf.view(-1, D))
+    dpos_ref[pad] = 0
+    assert rel(dword, dword_ref) < 1e-5 and rel(dpos, dpos_ref) < 1e-5
+
+
+def test_layernorm_bwd_addend(ops, cuda_device):
+    """pre-LN residual: dx = LN_bwd(dy) + addend."""
+    g = torch.Generator().manual_seed(9)
+    M, D = 300, 256
+    dev = cuda_device
+    x = torch.randn(M, D, generator=g).to(dev).to(torch.bfloat16)
+    dy = torch.randn(M, D, generator=g).to(dev).to(torch.bfloat16)
+    add = torch.randn(M, D, generator=g).to(dev).to(torch.bfloat16)
+    gamma = (torch.rand(D, generator=g) + 0.5).to(dev)
+    beta = torch.zeros(D, device=dev)
+    y, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-6)
+    dg0, db0 = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    dx0, _ = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg0, db0)
+    dg1, db1 = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    dx1, _ = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg1, db1, addend=add)
+    xr = x.float().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (D,), gamma, beta, 1e-6).backward(dy.float())
+    assert rel(dx0, xr.grad) < 1e-2
+    assert rel(dx1, xr.grad + add.float()) < 1e-2
+    assert torch.equal(dg0, dg1) or rel(dg0, dg1) < 1e-6
+
+
+def test_vit_assemble_fwd_bwd(ops, cuda_device):
+    g = torch.Generator().manual_seed(11)
+    B, P, D = 5, 16, 128
+    dev = cuda_device
+    patch = torch.randn(B * P, D, generator=g).to(dev).to(torch.bfloat16)
+    cls = torch.randn(D, generator=g).to(dev)
+    pos = torch.randn(P + 1, D, generator=g).to(dev)
+    x = ops.vit_assemble_fwd(patch, cls, pos, B, P)
+    ref = torch.cat([cls.view(1, 1, D).expand(B, 1, D), patch.float().view(B, P, D)], 1) + pos.view(1, P + 1, D)
+    assert rel(x.view(B, P + 1, D), ref) < 5e-3
+    dx = torch.randn(B * (P + 1), D, generator=g).to(dev).to(torch.bfloat16)
+    dcls = torch.zeros(D, device=dev)
+    dpos = torch.zeros(P + 1, D, device=dev)
+    dpatch = ops.vit_assemble_bwd(dx, dcls, dpos, B, P)
+    dxf = dx.float().view(B, P + 1, D)
+    assert torch.equal(dpatch.view(B, P, D), dx.view(B, P + 1, D)[:, 1:])
+    assert rel(dpos, dxf.sum(0)) < 1e-5 and rel(dcls, dxf[:, 0].sum(0)) < 1e-5

@@ -358,3 +358,112 @@ def test_head_style_loop_api(cuda_device, tmp_path):
     assert tsv.check_label_tsv(str(f_lab))
     ids, labels, probs, _ = tsv.read_prob_tsv(str(f_prob))
     assert len(ids) == len(va) and all(0.0 <= p <= 1.0 for p in probs)
+
+
+# ------------------------------------------------------------------ BASELINE configs 3-5: ViT + BERT / XLM-R towers
+def _pair_vit(cuda_device, text_arch="bert", seq=32, batch=8, seed=7):
+    """Engine / oracle pair of the config-3/4/5 graph (ViT image tower + BERT- or RoBERTa-style text tower, CLS
+    pooling) at a small size.  Parity for these towers is pinned by the in-repo oracle only."""
+    import b200mm
+    from oracle import reference_model as R
+    cfg = R.TowerConfig.tiny_vit_bert(text_arch)
+    torch.manual_seed(seed)
+    oracle = R.zero_dropout(R.MultimodalClassifier(2, cfg))
+    with torch.no_grad():   # library init leaves biases / LN at (0 / 1, 0): randomise so every term is exercised
+        for n, p in oracle.named_parameters():
+            if n.endswith(".bias") or "LayerNorm.weight" in n or "layernorm" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    tcfg = b200mm.TextConfig(vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings,
+                             dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, hidden_dim=cfg.hidden_dim,
+                             dropout=0.0, attention_dropout=0.0, layer_norm_eps=cfg.layer_norm_eps,
+                             pad_token_id=cfg.pad_token_id, arch=text_arch, type_vocab_size=cfg.type_vocab_size)
+    vcfg = b200mm.ViTConfig(image_size=cfg.image_size, patch_size=cfg.vit_patch, dim=cfg.vit_dim,
+                            n_layers=cfg.vit_layers, n_heads=cfg.vit_heads, hidden_dim=cfg.vit_hidden)
+    eng = b200mm.MultimodalClassifier(2, text_config=tcfg, image_config=vcfg, head_dropout=0.0, device=cuda_device)
+    assert eng.pooling == "cls"
+    eng.load_reference_state_dict(oracle.state_dict())
+    data = R.synthetic_batch(batch, seq, cfg)
+    return oracle, eng, data, cfg
+
+
+@pytest.mark.parametrize("text_arch", ["bert", "roberta"])
+def test_vit_text_variants_forward_and_layers(cuda_device, text_arch):
+    oracle, eng, data, cfg = _pair_vit(cuda_device, text_arch)
+    d = _dev(data, cuda_device)
+    # state-dict round trip (the engine does not carry the unused pooler / position_ids buffers)
+    sd, ref_sd = eng.reference_state_dict(), oracle.state_dict()
+    for k, v in ref_sd.items():
+        if "pooler" in k or k.endswith("position_ids") or k.endswith("token_type_ids"):
+            continue
+        assert k in sd, k
+        assert torch.equal(sd[k].cpu().view(v.shape), v), k
+    oracle.train()
+    eng.train()
+    ref_text, ref_img = [], []
+    hooks = [oracle.bert.embeddings.register_forward_hook(lambda m, i, o: ref_text.append(o.detach()))]
+    for layer in oracle.bert.encoder.layer:
+        hooks.append(layer.register_forward_hook(
+            lambda m, i, o: ref_text.append((o[0] if isinstance(o, tuple) else o).detach())))
+    hooks.append(oracle.resnet.embeddings.register_forward_hook(lambda m, i, o: ref_img.append(o.detach())))
+    for layer in oracle.resnet.encoder.layer:
+        hooks.append(layer.register_forward_hook(
+            lambda m, i, o: ref_img.append((o[0] if isinstance(o, tuple) else o).detach())))
+    ref = oracle(data["text"], data["image"], data["text_mask"]).detach()
+    for h in hooks:
+        h.remove()
+    eng.text.capture, eng.img.capture = [], []
+    with torch.no_grad():
+        got = eng._engine_forward(d["text"], d["image"], d["text_mask"], training=True)
+    B, S = data["text"].shape
+    assert len(eng.text.capture) == len(ref_text) and len(eng.img.capture) == len(ref_img)
+    for g_, r_ in zip(eng.text.capture, ref_text):
+        assert rel(g_.view(B, S, -1), r_) < 2e-2
+    for g_, r_ in zip(eng.img.capture, ref_img):
+        assert rel(g_.view(B, r_.shape[1], -1), r_) < 2e-2
+    assert rel(got, ref) < 2e-2
+    eng.text.capture = eng.img.capture = None
+    oracle.eval()
+    eng.eval()
+    assert rel(eng(d["text"], d["image"], d["text_mask"]), oracle(data["text"], data["image"], data["text_mask"])) < 2e-2
+
+
+@pytest.mark.parametrize("text_arch", ["bert", "roberta"])
+def test_vit_text_variants_backward_and_trajectory(cuda_device, text_arch):
+    import b200mm
+    oracle, eng, data, cfg = _pair_vit(cuda_device, text_arch, batch=16)
+    d = _dev(data, cuda_device)
+    oracle.train()
+    eng.train()
+    crit = nn.CrossEntropyLoss()
+    oracle.zero_grad()
+    loss_ref = crit(oracle(data["text"], data["image"], data["text_mask"]), data["label"])
+    loss_ref.backward()
+    eng.zero_grad()
+    _, loss, _ = eng.train_step_fused(d["text"], d["image"], d["text_mask"], d["label"])
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-2
+    grads = eng.reference_grad_dict()
+    worst = {}
+    for n, p in oracle.named_parameters():
+        if p.grad is None:        # pooler.dense.*: never reached (SURVEY.md §5)
+            assert "pooler" in n, n
+            continue
+        g = grads[n].cpu().view(p.grad.shape)
+        if p.grad.norm() < 1e-7:
+            continue
+        worst[n] = (rel(g, p.grad), _cos(g, p.grad))
+    bad = {n: v for n, v in worst.items() if v[0] > 6e-2 or v[1] < 0.995}
+    assert not bad, bad
+    # pad rows of the embedding tables never receive a gradient (nn.Embedding(padding_idx=...))
+    assert grads["bert.embeddings.word_embeddings.weight"][cfg.pad_token_id].abs().max() == 0
+    # short optimisation trajectory: same Adam recipe on both sides
+    opt_ref = torch.optim.Adam(oracle.parameters(), lr=2e-5)
+    opt = b200mm.FusedAdam(eng.parameters(), lr=2e-5)
+    for _ in range(5):
+        opt_ref.zero_grad()
+        l_ref = crit(oracle(data["text"], data["image"], data["text_mask"]), data["label"])
+        l_ref.backward()
+        opt_ref.step()
+        opt.zero_grad()
+        _, l, _ = eng.train_step_fused(d["text"], d["image"], d["text_mask"], d["label"])
+        opt.step()
+        assert abs(l.item() - l_ref.item()) / l_ref.item() < 2e-2
