@@ -23,6 +23,34 @@ sys.path.insert(0, ROOT)
 GFLOP_TRAIN_PER_SAMPLE = 57.8   # 3 x (8.18 ResNet-50 + 11.17 DistilBERT-S128) dense GFLOP
 METRIC = "train samples/s (224px img + 128-tok text)"
 
+# The headline (default) workload is BASELINE configs[1]; --config 3 / 4 / 5 run the other configurations of
+# BASELINE.json ("same head, towers swapped") for the record -- the driver only runs the default.
+# gflop = dense train GFLOP / sample (fwd x 3) resp. forward GFLOP / ensembled sample for config 5.
+WORKLOADS = {
+    2: dict(name="ResNet-50 + DistilBERT-multilingual late fusion train step (fwd + CE + bwd + Adam), "
+                 "BASELINE configs[1]", batch=256, seq=128, gflop=57.8),
+    3: dict(name="ViT-B/16 + BERT-base (vocab 64000) late fusion train step (fwd + CE + bwd + Adam), "
+                 "BASELINE configs[2]", batch=256, seq=128, gflop=172.2),
+    4: dict(name="ViT-L/14 + XLM-R-large late fusion train step (fwd + CE + bwd + Adam), seq 256, "
+                 "BASELINE configs[3]", batch=64, seq=256, gflop=969.0),
+    5: dict(name="5-fold ensemble inference (5 x ViT-B/16 + BERT-base forward, mean prob), BASELINE configs[4]",
+            batch=1024, seq=128, gflop=287.4),
+}
+
+
+def build_model(config: int, dev, seed: int = 42, num_classes: int = 2):
+    import b200mm
+    if config == 2:
+        return b200mm.MultimodalClassifier(num_classes, device=dev, seed=seed), dict(vocab_size=119547, pad_id=0)
+    if config in (3, 5):
+        t = b200mm.TextConfig.bert_base()
+        v = b200mm.ViTConfig.vit_b16()
+    else:
+        t = b200mm.TextConfig.xlmr_large()
+        v = b200mm.ViTConfig.vit_l14()
+    m = b200mm.MultimodalClassifier(num_classes, text_config=t, image_config=v, device=dev, seed=seed)
+    return m, dict(vocab_size=t.vocab_size, pad_id=t.pad_token_id)
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -30,8 +58,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
-    ap.add_argument("--seq", type=int, default=128)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS),
+                    help="BASELINE.json configuration (1-based; default 2 = the headline)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = the configuration's)")
+    ap.add_argument("--seq", type=int, default=0)
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the CPU reference step (BASELINE config 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -130,6 +160,108 @@ def run_reference(args):
     }), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------- config 5
+def run_ensemble(args, dev, world, rank):
+    """BASELINE configs[4]: 5-fold ensemble inference.  Five fold-models (same architecture, different weights) are
+    resident on every GPU; a step = the five eval-mode forward passes over one batch, sigmoid of the single logit
+    (HEAD script, Multimodal_example_task2C.py:808-810, 843-851) and the per-id mean over folds
+    (combine_preds.py:29-31).  Samples are sharded across ranks; value = ensembled samples/s."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import b200mm
+    from b200mm import _lib, ensemble
+    from b200mm.synth import synthetic_batch
+    B, S, wl = args.batch, args.seq, WORKLOADS[5]
+    folds = 5
+    models = []
+    for k in range(folds):
+        t, v = b200mm.TextConfig.bert_base(), b200mm.ViTConfig.vit_b16()
+        m = b200mm.MultimodalClassifier(1, text_config=t, image_config=v, device=dev, seed=42 + k, pooling="cls",
+                                        squeeze_output=True)
+        m.eval()
+        models.append(m)
+    host = synthetic_batch(B, S, seed=1234 + rank, vocab_size=64000)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    devd = {k: v.to(dev) for k, v in host.items()}
+    ids = [f"img_{rank}_{i}" for i in range(B)]
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("text", "text_mask", "image"))
+    logits_dev = torch.empty(folds, B, device=dev, dtype=torch.float32)
+    logits_host = torch.empty(folds, B, dtype=torch.float32).pin_memory()
+
+    def forward_all(d):
+        with torch.no_grad():
+            for k, m in enumerate(models):
+                logits_dev[k].copy_(m(d["text"], d["image"], d["text_mask"]))
+
+    def step_resident():
+        forward_all(devd)
+
+    def step_e2e():
+        d = {k: host[k].to(dev, non_blocking=True) for k in ("text", "text_mask", "image")}
+        forward_all(d)
+        logits_host.copy_(logits_dev, non_blocking=False)
+        probs = 1.0 / (1.0 + np.exp(-logits_host.numpy().astype(np.float64)))
+        _, mean_prob = ensemble.average_probability([ids] * folds, list(probs))
+        return int((mean_prob > 0.5).sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    _lib.LAUNCHES[0] = 0
+    ms = timed(step_resident, args.steps) / args.steps
+    launches = _lib.LAUNCHES[0]
+    clocks = sampler.stop()
+    value = world * B / (ms * 1e-3)
+    pk = peaks()
+    tfl = value / world * wl["gflop"] / 1e3
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05+TMA)", "achieved": tfl,
+                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tfl / pk["bf16_tflops_sustained"],
+                "traffic": None, "peak_source": pk["source"],
+                "note": "whole-forward dense FLOPs (5 x 57.5 GFLOP per ensembled sample) / step time"}
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ms_e = timed(step_e2e, args.steps) / args.steps
+        e2e = {"value": world * B / (ms_e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": folds * B * 4 * world, "ms_per_step": ms_e}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "ensembled inference samples/s (5 folds, 224px img + 128-tok text)", "value": value,
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "seq_len": S,
+                       "image": "3x224x224", "parallelism": f"dp{world}", "folds": folds,
+                       "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)"},
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------- engine arm
 def run_engine(args):
     import torch
@@ -147,14 +279,17 @@ def run_engine(args):
     from b200mm.synth import synthetic_batch
 
     B, S = args.batch, args.seq
-    model = b200mm.MultimodalClassifier(2, device=dev, seed=42)
+    wl = WORKLOADS[args.config]
+    if args.config == 5:
+        return run_ensemble(args, dev, world, rank)
+    model, synth_kw = build_model(args.config, dev)
     if world > 1:
         model.enable_data_parallel()
     model.train()
     crit = b200mm.CrossEntropyLoss()
     opt = b200mm.FusedAdam(model.parameters(), lr=2e-5)
 
-    host = synthetic_batch(B, S, seed=1234 + rank)
+    host = synthetic_batch(B, S, seed=1234 + rank, **synth_kw)
     host = {k: v.pin_memory() for k, v in host.items()}
     devd = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -226,8 +361,8 @@ def run_engine(args):
                                        "achieved_gbs": h["bytes"] / (h["ms"] * 1e-3) / 1e9 if h["ms"] else None,
                                        "frac_of_hbm_peak": (h["bytes"] / (h["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"])
                                        if h["ms"] else None, "ridge_flop_per_byte": ridge},
-                "whole_step_tflops": value / world * GFLOP_TRAIN_PER_SAMPLE / 1e3,
-                "whole_step_frac_of_peak": value / world * GFLOP_TRAIN_PER_SAMPLE / 1e3 / pk["bf16_tflops_sustained"]}
+                "whole_step_tflops": value / world * wl["gflop"] / 1e3,
+                "whole_step_frac_of_peak": value / world * wl["gflop"] / 1e3 / pk["bf16_tflops_sustained"]}
 
     e2e = None
     if not args.no_e2e:
@@ -238,7 +373,7 @@ def run_engine(args):
                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:
         from oracle import reference_model as R      # cpu_baseline leg: the one place this arm touches the oracle
         r = R.cpu_train_throughput(batch=args.cpu_batch, seq_len=S, steps=3, warmup=1)
         cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
@@ -249,9 +384,7 @@ def run_engine(args):
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ResNet-50 + DistilBERT-multilingual late fusion train step "
-                                   "(fwd + CE + bwd + Adam), BASELINE configs[1]",
-                       "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "image": "3x224x224",
+            "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "image": "3x224x224",
                        "parallelism": f"dp{world}", "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                        "dropout": "on (0.1 / 0.1 / 0.3, Philox)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -262,6 +395,8 @@ def run_engine(args):
 
 if __name__ == "__main__":
     a = parse()
+    a.batch = a.batch or WORKLOADS[a.config]["batch"]
+    a.seq = a.seq or WORKLOADS[a.config]["seq"]
     if a.impl == "reference":
         run_reference(a)
     else:

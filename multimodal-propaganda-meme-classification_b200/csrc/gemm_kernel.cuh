@@ -204,6 +204,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
+    int sv_tile = -1, sv_box = -1;   // which (tile, box) the prefetched side-input registers hold
+    // geometry of one staged epilogue box (bf16 outputs)
+    constexpr int BOX_W = HALF_COLS < 64 ? HALF_COLS : 64;   // columns per staged box: 64 (SW128) or 32 (SW64)
+    constexpr int BOXES = HALF_COLS / BOX_W;
+    // Side input of the epilogue (residual for the store modes, the saved pre-activation for dGELU): one
+    // [32 rows x BOX_W cols] box per staged output box.  It is read with fully coalesced 16-byte loads (a row
+    // segment per 8 / 4 lanes), one box AHEAD of its use so the HBM latency hides under the previous box, and
+    // handed to the row-owning lanes through the staging buffer the output is about to overwrite.  (The earlier
+    // per-lane row-strided __ldg pattern missed the 28 KB L1 left next to 227 KB of shared memory and made the
+    // dGELU / residual epilogues latency-bound.)
+    // Only dGELU takes this path: for the residual of the store modes the plain per-lane loads measured faster on the
+    // short-K convolution GEMMs (241 vs 283 us at [802816 x 256 x 64]) and equal on the long-K ones, and keeping
+    // them out keeps the store kernels' instruction stream short (they are I-cache sensitive).
+    constexpr bool HAS_SIDE = EPI == EPI_DGELU;
+    constexpr int CPR = BOX_W / 8;            // 16-byte chunks per box row
+    constexpr int RPP = 32 / CPR;             // rows covered by the warp per load pass
+    constexpr int SIDE_REGS = 32 / RPP;       // passes (uint4 registers) per box
+    const __nv_bfloat16* side = nullptr;
+    long long side_ld = 0;
+    if constexpr (EPI == EPI_DGELU) { side = p.aux; side_ld = p.ld_aux; }
+    uint4 sv[SIDE_REGS];
+    // tile coordinates advance by a constant (gridDim.x tiles) per round: no integer divisions on the prefetch path
+    // (side inputs exist only for the bf16 store modes, which never split K: tile index == w)
+    const int step_m = static_cast<int>(gridDim.x) / p.n_tiles, step_n = static_cast<int>(gridDim.x) % p.n_tiles;
+    auto advance = [&](int& mb, int& nb) {
+      mb += step_m;
+      nb += step_n;
+      if (nb >= p.n_tiles) { nb -= p.n_tiles; ++mb; }
+    };
+    auto side_fetch = [&](int mb, int nb, int b) {
+      const int col = nb * BN + half * HALF_COLS + b * BOX_W + (lane % CPR) * 8;
+      const long long r0 = static_cast<long long>(mb) * GEMM_BM + quarter * 32 + lane / CPR;
+      const __nv_bfloat16* src = side + r0 * side_ld + col;
+#pragma unroll
+      for (int j = 0; j < SIDE_REGS; ++j) {
+        sv[j] = (r0 + j * RPP < p.M && col < p.N)
+                    ? ldg_stream_v4(src + static_cast<long long>(j * RPP) * side_ld)
+                    : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
     const bool has_bias = p.bias != nullptr;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int split = w / tiles_mn;
@@ -216,17 +256,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const bool row_ok = row < p.M;
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if constexpr (BF16_OUT) {
-        constexpr int BOX_W = HALF_COLS < 64 ? HALF_COLS : 64;   // columns per staged box: 64 (SW128) or 32 (SW64)
-        constexpr int BOXES = HALF_COLS / BOX_W;
         constexpr int CHUNKS_PER_BOX = BOX_W / 32;
         constexpr int PASSES = EPI == EPI_GELU ? 2 : 1;
         uint8_t* stage_base = staging + ew * (p.nbuf * GEMM_BOX_BYTES);
         const __nv_bfloat16* res_row = nullptr;
         if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP)
           if (p.residual != nullptr && row_ok) res_row = p.residual + row * p.ldr;
-        const __nv_bfloat16* aux_row = nullptr;
-        if constexpr (EPI == EPI_DGELU)
-          if (row_ok) aux_row = p.aux + row * p.ld_aux;
+        if constexpr (HAS_SIDE) {
+          if (side != nullptr && (sv_tile != w || sv_box != 0)) { side_fetch(m_blk, n_blk, 0); sv_tile = w; sv_box = 0; }
+        }
 #pragma unroll 1
         for (int b = 0; b < BOXES; ++b) {
           const int box_col_in_tile = half * HALF_COLS + b * BOX_W;
@@ -240,6 +278,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             __syncwarp();
             uint8_t* stage_buf = stage_base + buf * GEMM_BOX_BYTES;
+            if constexpr (HAS_SIDE) {
+              if (side != nullptr) {
+#pragma unroll
+                for (int j = 0; j < SIDE_REGS; ++j) {
+                  const int r = j * RPP + lane / CPR, ch = lane % CPR;
+                  const uint32_t off = BOX_W == 64 ? r * 128 + ((ch ^ (r & 7)) << 4)
+                                                   : r * 64 + ((ch ^ ((r >> 1) & 3)) << 4);
+                  *reinterpret_cast<uint4*>(stage_buf + off) = sv[j];
+                }
+                // next box of this tile, or the first box of this CTA's next tile
+                const bool more = b + 1 < BOXES && n_blk * BN + half * HALF_COLS + (b + 1) * BOX_W < p.N;
+                int m1 = m_blk, n1 = n_blk;
+                advance(m1, n1);
+                {
+                  // ... and pull this box of the tile two rounds ahead into L2 (one 128-byte line per lane = one
+                  // box row): the register prefetch above then hits L2 instead of waiting ~2 us on HBM.
+                  int m2 = m1, n2 = n1;
+                  advance(m2, n2);
+                  const long long r = static_cast<long long>(m2) * GEMM_BM + quarter * 32 + lane;
+                  const int col = n2 * BN + box_col_in_tile;
+                  if (w + 2 * static_cast<int>(gridDim.x) < num_work && r < p.M && col < p.N)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(side + r * side_ld + col));
+                }
+                if (more) { side_fetch(m_blk, n_blk, b + 1); sv_tile = w; sv_box = b + 1; }
+                else if (w + static_cast<int>(gridDim.x) < num_work) {
+                  side_fetch(m1, n1, 0); sv_tile = w + gridDim.x; sv_box = 0;
+                }
+                __syncwarp();
+              }
+            }
 #pragma unroll 1
             for (int c = 0; c < CHUNKS_PER_BOX; ++c) {
               uint32_t v[32];
@@ -270,6 +338,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                   }
                   if (res_row != nullptr && col_ok) {
+                    // (row-strided per lane: relies on L1 to serve the other 16-byte pieces of each 128-byte line)
                     const uint4 r = __ldg(reinterpret_cast<const uint4*>(res_row + col));
                     const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
                                  r3 = unpack_bf16x2(r.w);
@@ -282,8 +351,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   }
                 }
                 if constexpr (EPI == EPI_DGELU) {
-                  if (aux_row != nullptr && col_ok) {
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(aux_row + col));
+                  if (col_ok) {
+                    const int scc = c * 4 + g;
+                    const uint4 r = *reinterpret_cast<const uint4*>(
+                        stage_buf + (BOX_W == 64 ? lane * 128 + ((scc ^ (lane & 7)) << 4)
+                                                 : lane * 64 + ((scc ^ ((lane >> 1) & 3)) << 4)));
                     const float2 z0 = unpack_bf16x2(r.x), z1 = unpack_bf16x2(r.y), z2 = unpack_bf16x2(r.z),
                                  z3 = unpack_bf16x2(r.w);
                     x[0] *= gelu_erf_grad(z0.x); x[1] *= gelu_erf_grad(z0.y);

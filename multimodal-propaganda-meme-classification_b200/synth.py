@@ -10,7 +10,8 @@ PAD_ID = 0
 TRAIN_PRIOR = 603 / 2143
 
 
-def synthetic_batch(batch: int, seq_len: int, *, vocab_size: int = 119547, image_size: int = 224, seed: int = 1234):
+def synthetic_batch(batch: int, seq_len: int, *, vocab_size: int = 119547, image_size: int = 224, seed: int = 1234,
+                    pad_id: int = PAD_ID):
     g = torch.Generator().manual_seed(seed)
     image = torch.randn(batch, 3, image_size, image_size, generator=g)
     lo = min(1000, vocab_size // 2)
@@ -19,6 +20,6 @@ def synthetic_batch(batch: int, seq_len: int, *, vocab_size: int = 119547, image
     lengths[0] = seq_len
     pos = torch.arange(seq_len).unsqueeze(0)
     mask = (pos < lengths.unsqueeze(1)).long()
-    ids = ids * mask + PAD_ID * (1 - mask)
+    ids = ids * mask + pad_id * (1 - mask)
     labels = (torch.rand(batch, generator=g) < TRAIN_PRIOR).long()
     return {"text": ids, "text_mask": mask, "image": image, "label": labels}

@@ -39,7 +39,18 @@ if "col2im" in which:
     timeit("im2col_nchw stem", lambda: ops.im2col_nchw_f32(img, 7, 2, 3, 152), bytes_=img.numel() * 4 + 256 * 112 * 112 * 152 * 2)
     a0 = torch.randn(256 * 112 * 112, 64, device=dev).to(bf)
     timeit("maxpool_fwd", lambda: ops.maxpool_fwd(a0, 256, 112, 112, 64), bytes_=a0.numel() * 2 * 1.375)
-if "gemm1" in which:
+if "gemm_dgelu" in which:
+    shapes = [(32768, 3072, 768, 1, 2)]
+    which.append("gemm")
+elif "gemm_res" in which:
+    shapes = [(802816, 256, 64, 1, 7)]
+    which.append("gemm")
+elif "gemmx" in which:
+    shapes = [(32768, 3072, 768, 1, 0), (32768, 3072, 768, 0, 2), (32768, 3072, 768, 1, 2), (32768, 3072, 768, 0, 0),
+              (32768, 3072, 768, 0, 1), (32768, 768, 768, 0, 0), (32768, 768, 768, 0, 7), (32768, 768, 3072, 0, 7),
+              (802816, 256, 64, 1, 0), (802816, 256, 64, 1, 7)]
+    which.append("gemm")
+elif "gemm1" in which:
     shapes = [(802816, 256, 64, 0, 0)]
 elif "gemm" in which:
     shapes = [(32768, 3072, 768, 0, 1), (32768, 3072, 768, 1, 2), (32768, 2304, 768, 0, 0), (32768, 768, 768, 0, 0),
@@ -47,10 +58,13 @@ elif "gemm" in which:
                                  (3211264, 64, 152, 0, 0), (50176, 2304, 256, 1, 0), (8192, 8192, 8192, 0, 0)]
 if "gemm" in which or "gemm1" in which:
     for (M, N, K, b_mn, epi) in shapes:
+        res = None
+        if epi == 7:     # plain store + residual
+            epi, res = 0, torch.randn(M, N, device=dev).to(bf)
         A = torch.randn(M, K, device=dev).to(bf)
         Bm = torch.randn(N, K, device=dev).to(bf) if not b_mn else torch.randn(K, N, device=dev).to(bf)
         out = torch.empty(M, N, device=dev, dtype=bf); out2 = torch.empty(M, N, device=dev, dtype=bf) if epi == 1 else None
         aux = torch.randn(M, N, device=dev).to(bf) if epi == 2 else None
-        bias = torch.zeros(N, device=dev)
-        timeit(f"gemm M{M} N{N} K{K} b_mn{b_mn} epi{epi}", lambda: ops.gemm_raw(A, False, Bm, bool(b_mn), M, N, K, out, epi=epi, bias=bias, aux=aux, out2=out2),
+        bias = torch.zeros(N, device=dev) if epi != 2 else None   # dgrad epilogues carry no bias
+        timeit(f"gemm M{M} N{N} K{K} b_mn{b_mn} epi{epi}{'+res' if res is not None else ''}", lambda: ops.gemm_raw(A, False, Bm, bool(b_mn), M, N, K, out, epi=epi, bias=bias, aux=aux, out2=out2, residual=res),
                flops=2.0 * M * N * K, bytes_=2.0 * (M * K + N * K + M * N * (2 if epi == 1 else 1) + (M * N if epi == 2 else 0)))

@@ -1,4 +1,4 @@
-"""Per-op CUDA-event profile of the real (pipelined, warm-L2) config-2 train step.
+"""Per-op CUDA-event profile of the real (pipelined, warm-L2) train step (PCFG = BASELINE config, default 2).
 Aggregates by C-ABI entry point, and by shape for the GEMM.  Writes profiles/step_profile_<tag>.json."""
 import json, os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,11 +6,14 @@ import torch, b200mm
 from b200mm import _lib
 from b200mm.synth import synthetic_batch
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-B = int(os.environ.get("PB", 256))
+import bench
+CFG = int(os.environ.get("PCFG", 2))
+B = int(os.environ.get("PB", bench.WORKLOADS[CFG]["batch"]))
+S = bench.WORKLOADS[CFG]["seq"]
 dev = torch.device("cuda:0")
-model = b200mm.MultimodalClassifier(2, device=dev); model.train()
+model, synth_kw = bench.build_model(CFG, dev); model.train()
 opt = b200mm.FusedAdam(model.parameters(), lr=2e-5)
-d = {k: v.to(dev) for k, v in synthetic_batch(B, 128).items()}
+d = {k: v.to(dev) for k, v in synthetic_batch(B, S, **synth_kw).items()}
 def step():
     opt.zero_grad(); model.train_step_fused(d["text"], d["image"], d["text_mask"], d["label"]); opt.step()
 for _ in range(3): step()
@@ -34,7 +37,7 @@ for name, key, a, b in rec:
     if key is not None: by_gemm[key][0] += 1; by_gemm[key][1] += ms
 tot = sum(v[1] for v in by_fn.values()) / STEPS
 print(f"step {plain:.2f} ms (with events {prof_ms:.2f} ms); sum of op times {tot:.2f} ms")
-rep = {"batch": B, "ms_per_step": plain, "ms_per_step_profiled": prof_ms, "ops": {}, "gemm": []}
+rep = {"config": CFG, "batch": B, "ms_per_step": plain, "ms_per_step_profiled": prof_ms, "ops": {}, "gemm": []}
 for k, v in sorted(by_fn.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:32s} n={v[0]//STEPS:4d} {v[1]/STEPS:8.3f} ms")
     rep["ops"][k] = {"calls": v[0] // STEPS, "ms": v[1] / STEPS}
