@@ -300,12 +300,20 @@ def run_engine(args):
         opt.step()
         return loss
 
+    # end-to-end: the package's own input path (b200mm.loop.DevicePrefetcher, what b200mm.train() iterates): every
+    # step's batch is copied host -> device from pinned memory (on a side stream, one batch ahead of the compute)
+    # and the step's loss / correct count are read back, as the reference loop does (.txt:206-211, 218-220)
+    from b200mm.loop import DevicePrefetcher
+
+    def endless():
+        while True:
+            yield host
+
+    e2e_iter = iter(DevicePrefetcher(endless(), dev))
+
     def step_e2e():
         opt.zero_grad()
-        t = host["text"].to(dev, non_blocking=True)
-        i = host["image"].to(dev, non_blocking=True)
-        m = host["text_mask"].to(dev, non_blocking=True)
-        l = host["label"].to(dev, non_blocking=True)
+        t, i, m, l, _ = next(e2e_iter)
         _, loss, ok = model.train_step_fused(t, i, m, l)
         opt.step()
         return loss.item(), ok.item()        # the reference's per-step D2H reads (.txt:218-220)

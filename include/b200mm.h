@@ -40,7 +40,10 @@ int b200mm_num_sms(void);
 int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, int M, int N,
                      int K, int epi, const float* bias, const void* residual, long long ldr, const void* aux,
                      long long ld_aux, void* out, long long ldc, void* out2, long long ld2, int splits, int block_n,
-                     float p_drop, unsigned long long seed, void* stream);
+                     float p_drop, unsigned long long seed, float* col_stats, void* stream);
+/* col_stats (nullable; epi 0 without bias / residual / dropout): fp32 [2N], col_stats[n] += sum_m out[m,n],
+ * col_stats[N+n] += sum_m out[m,n]^2 over the STORED bf16 values -- the train-mode BatchNorm statistics of a
+ * convolution output come out of the convolution's own epilogue (feeds b200mm_batchnorm_fwd_stats). */
 
 /* Implicit-GEMM convolution on the same kernel: the activation operand is gathered from NHWC memory by im2col-mode
  * TMA loads (no im2col matrix exists).  x: bf16 [N,H,W,C], C % 64 == 0; w: bf16 OHWI-flattened [Cout, k*k*C].
@@ -48,7 +51,7 @@ int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int 
  * Replaces conv3x3 of torchvision/models/resnet.py:19-31, :118-130 (cuDNN fprop / dgrad / wgrad). */
 int b200mm_conv_fwd(const void* x, int N, int H, int W, int C, const void* w, int Cout, int ksize, int stride, int pad,
                     int epi, const float* bias, const void* residual, long long ldr, void* out, long long ldc,
-                    void* stream);
+                    float* col_stats, void* stream);
 int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x, int N, int H, int W, int C, int Cout, int ksize,
                       int stride, int pad, float* dw, int splits, void* stream);
 int b200mm_conv_weight_rotate(const void* w, void* w_rot, int Cout, int Cin, int ksize, void* stream);
@@ -100,12 +103,18 @@ int b200mm_scatter_rows(const void* dpooled, void* dx, long long M, int D, long 
 int b200mm_batchnorm_fwd(const void* x, const void* residual, long long M, int C, const float* gamma,
                          const float* beta, float eps, float momentum, int relu, void* out, float* mean_out,
                          float* rstd_out, float* running_mean, float* running_var, float* scratch, void* stream);
+/* one-pass variant: col_stats = [sum(C) | sum of squares(C)] accumulated by the producing convolution's epilogue */
+int b200mm_batchnorm_fwd_stats(const void* x, const void* residual, long long M, int C, const float* col_stats,
+                               const float* gamma, const float* beta, float eps, float momentum, int relu, void* out,
+                               float* mean_out, float* rstd_out, float* running_mean, float* running_var,
+                               void* stream);
 int b200mm_batchnorm_eval(const void* x, const void* residual, long long M, int C, const float* gamma,
                           const float* beta, const float* running_mean, const float* running_var, float eps, int relu,
                           void* out, void* stream);
+/* relu != 0 with out == NULL: the ReLU mask is recomputed from x (needs beta; only valid without a residual) */
 int b200mm_batchnorm_bwd(const void* dout, const void* out, const void* x, long long M, int C, const float* mean,
-                         const float* rstd, const float* gamma, int relu, void* dx, void* dz_out, float* dgamma,
-                         float* dbeta, float* scratch, void* stream);
+                         const float* rstd, const float* gamma, const float* beta, int relu, void* dx, void* dz_out,
+                         float* dgamma, float* dbeta, float* scratch, void* stream);
 int b200mm_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, void* argmax, void* stream);
 int b200mm_maxpool3x3s2_bwd(const void* dout, const void* argmax, int N, int H, int W, int C, void* dx, void* stream);
 int b200mm_avgpool_fwd(const void* x, int N, int HW, int C, void* out, void* stream);

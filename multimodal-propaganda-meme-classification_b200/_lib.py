@@ -89,9 +89,9 @@ declare("b200mm_version", [])
 declare("b200mm_num_sms", [])
 declare("b200mm_gemm_bf16", [c_ptr, c_int, c_longlong, c_ptr, c_int, c_longlong, c_int, c_int, c_int, c_int,
                              c_ptr, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong,
-                             c_int, c_int, c_float, c_ulonglong, c_ptr])
+                             c_int, c_int, c_float, c_ulonglong, c_ptr, c_ptr])
 declare("b200mm_conv_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
-                            c_longlong, c_ptr, c_longlong, c_ptr])
+                            c_longlong, c_ptr, c_longlong, c_ptr, c_ptr])
 declare("b200mm_conv_wgrad", [c_ptr, c_longlong, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr,
                               c_int, c_ptr])
 declare("b200mm_conv_weight_rotate", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr])
@@ -123,10 +123,12 @@ declare("b200mm_scatter_rows", [c_ptr, c_ptr, c_longlong, c_int, c_longlong, c_l
                                 c_ptr])
 declare("b200mm_batchnorm_fwd", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_float, c_float, c_int, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_batchnorm_fwd_stats", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_float, c_float, c_int,
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_batchnorm_eval", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_float, c_int,
                                   c_ptr, c_ptr])
-declare("b200mm_batchnorm_bwd", [c_ptr, c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr,
-                                 c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_batchnorm_bwd", [c_ptr, c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
+                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_maxpool3x3s2_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr])
 declare("b200mm_maxpool3x3s2_bwd", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_avgpool_fwd", [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr])

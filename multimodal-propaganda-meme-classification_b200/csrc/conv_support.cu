@@ -115,7 +115,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
     const float var = fmaxf(sumsq[c] / M - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
     sc[i] = gamma[c] * rstd;
-    sh[i] = beta[c] - mean * sc[i];
+    sh[i] = fmaf(-mean, sc[i], beta[c]);   // explicit fma: the backward recomputes the ReLU mask with the same ops
     if (blockIdx.x == 0 && ty == 0) {
       mean_out[c] = mean;
       rstd_out[c] = rstd;
@@ -128,22 +128,32 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
-  for (long long r = r0 + ty; r < r1; r += rpp) {
-    float v[8];
-    load8(x + r * C + g * 8, v);
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread and stream (the loop is latency-bound otherwise)
+  for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
+    uint4 rx[U], rr[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
-    if (residual != nullptr) {
-      float rv[8];
-      load8(residual + r * C + g * 8, rv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += rv[i];
+    for (int u = 0; u < U; ++u) {
+      const long long row = r + static_cast<long long>(u) * rpp;
+      const bool ok = row < r1;
+      rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + row * C + g * 8)) : make_uint4(0, 0, 0, 0);
+      rr[u] = (ok && residual != nullptr) ? __ldg(reinterpret_cast<const uint4*>(residual + row * C + g * 8))
+                                          : make_uint4(0, 0, 0, 0);
     }
-    if (relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const long long row = r + static_cast<long long>(u) * rpp;
+      if (row >= r1) break;
+      float v[8], rv[8];
+      unpack8(rx[u], v);
+      unpack8(rr[u], rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]) + rv[i];
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      store8(out + row * C + g * 8, v);
     }
-    store8(out + r * C + g * 8, v);
   }
 }
 
@@ -164,44 +174,62 @@ bn_eval_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
-  for (long long r = r0 + ty; r < r1; r += rpp) {
-    float v[8];
-    load8(x + r * C + g * 8, v);
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread and stream (the loop is latency-bound otherwise)
+  for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
+    uint4 rx[U], rr[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
-    if (residual != nullptr) {
-      float rv[8];
-      load8(residual + r * C + g * 8, rv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += rv[i];
+    for (int u = 0; u < U; ++u) {
+      const long long row = r + static_cast<long long>(u) * rpp;
+      const bool ok = row < r1;
+      rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + row * C + g * 8)) : make_uint4(0, 0, 0, 0);
+      rr[u] = (ok && residual != nullptr) ? __ldg(reinterpret_cast<const uint4*>(residual + row * C + g * 8))
+                                          : make_uint4(0, 0, 0, 0);
     }
-    if (relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const long long row = r + static_cast<long long>(u) * rpp;
+      if (row >= r1) break;
+      float v[8], rv[8];
+      unpack8(rx[u], v);
+      unpack8(rr[u], rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]) + rv[i];
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      store8(out + row * C + g * 8, v);
     }
-    store8(out + r * C + g * 8, v);
   }
 }
 
 // backward pass 1: dbeta = sum dz, dgamma = sum dz * xhat, dz = dout o (out > 0) when relu
+template <bool HAS_OUT>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                      const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu,
-                     float* __restrict__ scratch) {
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scratch) {
   __shared__ float red[2][256][8];
   const int G = C >> 3;
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
-  float mu[8], rs[8];
+  // out == nullptr with relu: the mask is recomputed from x with the forward's own fma (saves one full read of the
+  // activation; only possible when no residual entered the ReLU)
+  const bool recompute = relu && !HAS_OUT;
+  float mu[8], rs[8], sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     mu[i] = mean[g * 8 + i];
     rs[i] = rstd[g * 8 + i];
+    sc[i] = recompute ? gamma[g * 8 + i] * rs[i] : 0.f;
+    sh[i] = recompute ? fmaf(-mu[i], sc[i], beta[g * 8 + i]) : 0.f;
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
   float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  constexpr int U = 4;
+  // bytes in flight per SM decide the bandwidth of these streaming passes: with two input streams instead of three
+  // the unroll goes up so that the same ~100 KB stay outstanding
+  constexpr int U = HAS_OUT ? 4 : 6;
   for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
     uint4 rd[U], rx[U], ro[U];
 #pragma unroll
@@ -211,14 +239,18 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
       const long long off = rr * C + g * 8;
       rd[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dout + off)) : make_uint4(0, 0, 0, 0);
       rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
-      ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
+      if constexpr (HAS_OUT)
+        ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float d[8], xv[8];
       unpack8(rd[u], d);
       unpack8(rx[u], xv);
-      if (relu) {
+      if (recompute) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(xv[i], sc[i], sh[i]) > 0.f ? d[i] : 0.f;
+      } else if (HAS_OUT && relu) {
         float o[8];
         unpack8(ro[u], o);
 #pragma unroll
@@ -236,17 +268,20 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
 
 // backward pass 2: dx = gamma * rstd * (dz - dbeta/M - xhat * dgamma/M); optional dz copy for the identity branch;
 // CTA 0 accumulates the parameter gradients.
-__global__ void __launch_bounds__(256, 3)
+template <bool HAS_OUT>
+__global__ void __launch_bounds__(256, HAS_OUT ? 3 : 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
                     const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                    int relu, const float* __restrict__ dgamma_sum, const float* __restrict__ dbeta_sum,
+                    const float* __restrict__ beta, int relu, const float* __restrict__ dgamma_sum,
+                    const float* __restrict__ dbeta_sum,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
   const int G = C >> 3;
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
-  float mu[8], rs[8], k0[8], k1[8], k2[8];
+  float mu[8], rs[8], k0[8], k1[8], k2[8], sh[8];
   const float invM = 1.f / static_cast<float>(M);
+  const bool recompute = relu && !HAS_OUT;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = g * 8 + i;
@@ -254,6 +289,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
     rs[i] = rstd[c];
     const float dg = dgamma_sum[c], db = dbeta_sum[c];
     k0[i] = gamma[c] * rs[i];
+    sh[i] = recompute ? fmaf(-mu[i], k0[i], beta[c]) : 0.f;
     k1[i] = db * invM;
     k2[i] = dg * invM;
     if (blockIdx.x == 0 && ty == 0) {
@@ -263,7 +299,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
-  constexpr int U = 2;
+  constexpr int U = HAS_OUT ? 2 : 6;   // 3 CTAs x 2 x 3 streams, or 2 CTAs x 6 x 2 streams of 16-byte loads in flight
   for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
     uint4 rd[U], rx[U], ro[U];
 #pragma unroll
@@ -273,7 +309,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
       const long long off = rr * C + g * 8;
       rd[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dout + off)) : make_uint4(0, 0, 0, 0);
       rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
-      ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
+      if constexpr (HAS_OUT)
+        ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -282,7 +319,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
       float d[8], xv[8];
       unpack8(rd[u], d);
       unpack8(rx[u], xv);
-      if (relu) {
+      if (recompute) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(xv[i], k0[i], sh[i]) > 0.f ? d[i] : 0.f;
+      } else if (HAS_OUT && relu) {
         float o[8];
         unpack8(ro[u], o);
 #pragma unroll
@@ -656,6 +696,23 @@ B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long lo
   return B200MM_OK;
 }
 
+// Same, with the column statistics already accumulated by the producing convolution's epilogue
+// (b200mm_gemm_bf16 / b200mm_conv_fwd col_stats): col_stats = [sum(C) | sum of squares(C)], fp32.  One pass over x.
+B200MM_API int b200mm_batchnorm_fwd_stats(const void* x, const void* residual, long long M, int C,
+                                          const float* col_stats, const float* gamma, const float* beta, float eps,
+                                          float momentum, int relu, void* out, float* mean_out, float* rstd_out,
+                                          float* running_mean, float* running_var, void* stream) {
+  if (!bn_shape_ok(M, C) || col_stats == nullptr) return B200MM_ERR_BAD_ARG;
+  int grid;
+  const int rows = bn_rows_per_cta(M, C, &grid);
+  bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, col_stats,
+      col_stats + C, gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out, rstd_out,
+      running_mean, running_var);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
 B200MM_API int b200mm_batchnorm_eval(const void* x, const void* residual, long long M, int C, const float* gamma,
                                      const float* beta, const float* running_mean, const float* running_var, float eps,
                                      int relu, void* out, void* stream) {
@@ -671,11 +728,13 @@ B200MM_API int b200mm_batchnorm_eval(const void* x, const void* residual, long l
 
 // BatchNorm backward.  dout: gradient w.r.t. the (post-activation) output; out: that output (ReLU mask; may be null
 // when relu == 0); x: the BN input.  dx: gradient w.r.t. x; dz_out (nullable): gradient w.r.t. the pre-activation
-// sum, i.e. what flows into the residual branch.  dgamma / dbeta accumulate.
+// sum, i.e. what flows into the residual branch.  dgamma / dbeta accumulate.  With relu != 0 and out == nullptr the
+// ReLU mask is recomputed from x, mean, rstd, gamma and beta (valid only if no residual was added before the ReLU).
 B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const void* x, long long M, int C,
-                                    const float* mean, const float* rstd, const float* gamma, int relu, void* dx,
-                                    void* dz_out, float* dgamma, float* dbeta, float* scratch, void* stream) {
-  if (!bn_shape_ok(M, C) || (relu && out == nullptr)) return B200MM_ERR_BAD_ARG;
+                                    const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                    int relu, void* dx, void* dz_out, float* dgamma, float* dbeta, float* scratch,
+                                    void* stream) {
+  if (!bn_shape_ok(M, C) || (relu && out == nullptr && beta == nullptr)) return B200MM_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * bn_scratch_floats(C), s);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -683,15 +742,22 @@ B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const voi
   const int rows = bn_rows_per_cta(M, C, &grid);
   const int rrows = bn_rows_per_cta(M, C, &rgrid, 2);
   const float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;
-  bn_bwd_reduce_kernel<<<rgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dout),
-                                             static_cast<const __nv_bfloat16*>(out),
-                                             static_cast<const __nv_bfloat16*>(x), M, C, rrows, mean, rstd, relu,
-                                             scratch);
+  const __nv_bfloat16* dout_ = static_cast<const __nv_bfloat16*>(dout);
+  const __nv_bfloat16* out_ = static_cast<const __nv_bfloat16*>(out);
+  const __nv_bfloat16* x_ = static_cast<const __nv_bfloat16*>(x);
+  if (out != nullptr)
+    bn_bwd_reduce_kernel<true><<<rgrid, 256, 0, s>>>(dout_, out_, x_, M, C, rrows, mean, rstd, relu, gamma, beta, scratch);
+  else
+    bn_bwd_reduce_kernel<false><<<rgrid, 256, 0, s>>>(dout_, out_, x_, M, C, rrows, mean, rstd, relu, gamma, beta, scratch);
   B200MM_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(
-      static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out),
-      static_cast<const __nv_bfloat16*>(x), M, C, rows, mean, rstd, gamma, relu, fin, fin + C,
-      static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dz_out), dgamma, dbeta);
+  if (out != nullptr)
+    bn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(dout_, out_, x_, M, C, rows, mean, rstd, gamma, beta, relu, fin,
+                                                   fin + C, static_cast<__nv_bfloat16*>(dx),
+                                                   static_cast<__nv_bfloat16*>(dz_out), dgamma, dbeta);
+  else
+    bn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(dout_, out_, x_, M, C, rows, mean, rstd, gamma, beta, relu, fin,
+                                                    fin + C, static_cast<__nv_bfloat16*>(dx),
+                                                    static_cast<__nv_bfloat16*>(dz_out), dgamma, dbeta);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

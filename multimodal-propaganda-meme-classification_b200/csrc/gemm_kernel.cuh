@@ -245,11 +245,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     };
     const bool has_bias = p.bias != nullptr;
+    // EPI_STORE_STATS: per-lane running column sums (two adjacent columns per staged box), flushed with fp32
+    // reductions when the CTA moves to another column block and at the end
+    float st_s[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, st_q[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    int st_nblk = -1;
+    auto stats_flush = [&]() {
+      if (st_nblk < 0) return;
+      if (BOX_W == 32 && lane >= 16) return;
+#pragma unroll
+      for (int b = 0; b < BOXES; ++b) {
+        const int col = st_nblk * BN + half * HALF_COLS + b * BOX_W + 2 * (BOX_W == 64 ? lane : (lane & 15));
+        if (col < p.N) {
+          asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p.col_stats + col), "f"(st_s[b][0]), "f"(st_s[b][1]) : "memory");
+          asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p.col_stats + p.N + col), "f"(st_q[b][0]), "f"(st_q[b][1]) : "memory");
+        }
+        st_s[b][0] = st_s[b][1] = st_q[b][0] = st_q[b][1] = 0.f;
+      }
+    };
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int split = w / tiles_mn;
       const int t = w - split * tiles_mn;
       const int m_blk = t / p.n_tiles;
       const int n_blk = t - m_blk * p.n_tiles;
+      if constexpr (EPI == EPI_STORE_STATS) {
+        if (n_blk != st_nblk) { stats_flush(); st_nblk = n_blk; }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
       const long long row = static_cast<long long>(m_blk) * GEMM_BM + quarter * 32 + lane;
@@ -320,11 +340,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[g * 8 + i]);
-                if (has_bias && col_ok) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                  x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                  x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                if constexpr (EPI != EPI_STORE_STATS && EPI != EPI_DGELU) {   // conv outputs / dgrads carry no bias
+                  if (has_bias && col_ok) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+                    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                  }
                 }
                 if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP) {
                   if constexpr (EPI == EPI_STORE_DROP) {
@@ -390,6 +412,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               tma_store_2d(pass == 0 ? &tma_out : &tma_out2, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
               tma_store_commit();
             }
+            if constexpr (EPI == EPI_STORE_STATS) {
+              // column sums over the 32 staged rows: lane l owns the 4-byte word (2 columns) l of every row --
+              // conflict-free under either swizzle; rows past M were zero-filled by TMA and add nothing
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+              if constexpr (BOX_W == 64) {
+                const uint32_t cc = lane >> 2, wo = (lane & 3) * 4;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                  const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                      stage_buf + r * 128 + ((cc ^ (r & 7)) << 4) + wo));
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                }
+              } else {
+                const uint32_t w16 = lane & 15, cc = w16 >> 2, wo = (w16 & 3) * 4, rb = (lane >> 4) * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const uint32_t r = rb + i;
+                  const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                      stage_buf + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4) + wo));
+                  s0 += f.x; s1 += f.y;
+                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                }
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+              }
+#pragma unroll
+              for (int bb = 0; bb < BOXES; ++bb) {
+                if (bb == b) { st_s[bb][0] += s0; st_s[bb][1] += s1; st_q[bb][0] += q0; st_q[bb][1] += q1; }
+              }
+            }
             if (++buf == p.nbuf) buf = 0;
           }
         }
@@ -437,6 +490,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if constexpr (EPI == EPI_STORE_STATS) stats_flush();
     if constexpr (BF16_OUT) {
       if (lane == 0) tma_store_wait<0>();   // smem must outlive the last bulk store
     }
@@ -478,6 +532,7 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
                    const GemmParams& p, int grid, cudaStream_t stream) {
   switch (p.epi) {
     case EPI_STORE:
+      if (p.col_stats != nullptr) return launch_gemm_inst<BN, EPI_STORE_STATS>(ta, tb, to, to2, p, grid, stream);
       if (p.p_drop > 0.f) return launch_gemm_inst<BN, EPI_STORE_DROP>(ta, tb, to, to2, p, grid, stream);
       return launch_gemm_inst<BN, EPI_STORE>(ta, tb, to, to2, p, grid, stream);
     case EPI_GELU: return launch_gemm_inst<BN, EPI_GELU>(ta, tb, to, to2, p, grid, stream);

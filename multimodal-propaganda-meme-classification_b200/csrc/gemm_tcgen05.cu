@@ -48,7 +48,8 @@ struct ConvGeom {
 
 int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int N, int K, int epi, const float* bias,
              const void* residual, long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
-             void* out2, long long ld2, int splits, int block_n, float p_drop, unsigned long long seed, void* stream) {
+             void* out2, long long ld2, int splits, int block_n, float p_drop, unsigned long long seed,
+             float* col_stats, void* stream) {
   const DeviceInfo& dev = device_info();
   if (!dev.ok) return B200MM_ERR_NOT_SM100;
   if (dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
@@ -59,7 +60,10 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   if (splits < 1) splits = 1;
   if (splits > 1 && epi != EPI_F32_ATOMIC) return B200MM_ERR_BAD_ARG;
   if (epi == EPI_GELU && out2 == nullptr) return B200MM_ERR_BAD_ARG;
-  if (epi == EPI_DGELU && aux == nullptr) return B200MM_ERR_BAD_ARG;
+  if (epi == EPI_DGELU && (aux == nullptr || bias != nullptr)) return B200MM_ERR_BAD_ARG;
+  // column statistics ride on the plain store epilogue only (convolution outputs: no bias, residual or dropout)
+  if (col_stats != nullptr && (epi != EPI_STORE || bias != nullptr || residual != nullptr || p_drop > 0.f))
+    return B200MM_ERR_BAD_ARG;
   if ((A.im2col || B.im2col) && (cg.C % 64 != 0 || cg.ksize < 1)) return B200MM_ERR_BAD_ARG;
 
   int bn = block_n;
@@ -90,6 +94,7 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   p.ldc = ldc;
   p.out2 = static_cast<__nv_bfloat16*>(out2);
   p.ld2 = ld2;
+  p.col_stats = col_stats;
   if (p_drop < 0.f || p_drop >= 1.f) return B200MM_ERR_BAD_ARG;
   p.p_drop = (epi == EPI_STORE) ? p_drop : 0.f;
   p.drop_threshold = dropout_threshold(p_drop);
@@ -152,17 +157,19 @@ rotate_conv_weight_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __
 //   b_mn == 0: B is stored [N, K] (row stride ldb elements);  b_mn == 1: B is stored [K, N].
 //   epi: EpiMode above.  splits > 1 requires epi == EPI_F32_ATOMIC (out must be pre-zeroed or hold the
 //   value to accumulate onto).  block_n in {0 (auto), 64, 128, 256}.  p_drop/seed: EPI_STORE dropout (see GemmParams).
+//   col_stats (nullable, epi 0 without bias/residual/dropout): fp32 [2N], col_stats[n] += sum_m out[m,n] and
+//   col_stats[N + n] += sum_m out[m,n]^2 over the stored bf16 values -- the BatchNorm statistics of a conv output.
 // Contract: pointers 16-byte aligned, lda/ldb/ldc/... multiples of 8 elements, N % 8 == 0.
 B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb,
                                 int M, int N, int K, int epi, const float* bias, const void* residual,
                                 long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
                                 void* out2, long long ld2, int splits, int block_n, float p_drop,
-                                unsigned long long seed, void* stream) {
+                                unsigned long long seed, float* col_stats, void* stream) {
   Operand a, b;
   a.ptr = A; a.mn = a_mn; a.ld = lda;
   b.ptr = B; b.mn = b_mn; b.ld = ldb;
   return run_gemm(a, b, ConvGeom{}, M, N, K, epi, bias, residual, ldr, aux, ld_aux, out, ldc, out2, ld2, splits,
-                  block_n, p_drop, seed, stream);
+                  block_n, p_drop, seed, col_stats, stream);
 }
 
 // Implicit-GEMM convolution forward (square k x k window, symmetric padding): out[N*P*Q, Cout] = conv(x, w) with
@@ -172,7 +179,7 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
 // Replaces torchvision conv3x3 (torchvision/models/resnet.py:19-31, :118-130) forward / dgrad.
 B200MM_API int b200mm_conv_fwd(const void* x, int N, int H, int W, int C, const void* w, int Cout, int ksize,
                                int stride, int pad, int epi, const float* bias, const void* residual, long long ldr,
-                               void* out, long long ldc, void* stream) {
+                               void* out, long long ldc, float* col_stats, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || ksize <= 0 || stride <= 0 || pad < 0)
     return B200MM_ERR_BAD_ARG;
   ConvGeom cg;
@@ -185,7 +192,7 @@ B200MM_API int b200mm_conv_fwd(const void* x, int N, int H, int W, int C, const 
   const long long M = static_cast<long long>(N) * cg.P * cg.Q;
   if (M > 0x7fffffffLL) return B200MM_ERR_BAD_ARG;
   return run_gemm(a, b, cg, static_cast<int>(M), Cout, ksize * ksize * C, epi, bias, residual, ldr, nullptr, 0, out,
-                  ldc, nullptr, 0, 1, 0, 0.f, 0, stream);
+                  ldc, nullptr, 0, 1, 0, 0.f, 0, col_stats, stream);
 }
 
 // Implicit-GEMM weight gradient: dw[Cout, k*k*C] (fp32) += dy[N*P*Q, Cout]^T x im2col(x); the im2col operand is
@@ -205,7 +212,7 @@ B200MM_API int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x,
   b.ptr = x; b.im2col = 1;
   const int ncols = ksize * ksize * C;
   return run_gemm(a, b, cg, Cout, ncols, static_cast<int>(pixels), EPI_F32_ATOMIC, nullptr, nullptr, 0, nullptr, 0,
-                  dw, ncols, nullptr, 0, splits, 0, 0.f, 0, stream);
+                  dw, ncols, nullptr, 0, splits, 0, 0.f, 0, nullptr, stream);
 }
 
 // w [Cout, k, k, Cin] -> w_rot [Cin, k, k, Cout] with both spatial axes flipped (bf16)

@@ -69,6 +69,11 @@ class ImageTower:
         self.out_dim = cfg.num_outputs   # the 1000-way ImageNet fc is kept (.txt:164-165)
         self._convs = [self.stem] + [c for b in self.blocks for c in (b["c1"], b["c2"], b["c3"], b["ds"]) if c]
         self._conv_by_weight = {c.name + ".weight": c for c in self._convs}
+        off = 0
+        for c in self._convs:
+            c.stats_off = off
+            off += 2 * c.cout
+        self._stats_total, self._stats = off, None
         self._saved = None
         self.buffers = None
         self.capture = None   # set to a list to record every block's output (per-layer parity checks)
@@ -153,11 +158,19 @@ class ImageTower:
             out[f"{c.bn_name}.num_batches_tracked"] = torch.tensor(self.num_batches_tracked)
 
     # ------------------------------------------------------------------ building blocks
+    def _stats_begin(self, training):
+        """One zeroed fp32 arena per step: [2*cout] column sums / sums of squares per convolution, filled by the
+        convolutions' own epilogues (so BatchNorm never re-reads its input for the statistics)."""
+        self._stats = torch.zeros(self._stats_total, device=self.store.device, dtype=torch.float32) if training else None
+
+    def _stats_of(self, c):
+        return None if self._stats is None else self._stats[c.stats_off:c.stats_off + 2 * c.cout]
+
     def _bn(self, c, x, training, residual=None, relu=True):
         cfg = self.cfg
         if training:
             return ops.batchnorm_fwd(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps,
-                                     momentum=cfg.bn_momentum)
+                                     momentum=cfg.bn_momentum, col_stats=self._stats_of(c))
         return ops.batchnorm_eval(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps), None, None
 
     # ------------------------------------------------------------------ forward
@@ -168,8 +181,9 @@ class ImageTower:
         assert Cin == 3
         sv = {"N": N, "blocks": []} if training else None
         st = self.stem
+        self._stats_begin(training)
         cols, H1, W1 = ops.im2col_nchw_f32(image, 7, 2, 3, STEM_KP)
-        c0 = ops.linear_fwd(cols, st.w)
+        c0 = ops.linear_fwd(cols, st.w, col_stats=self._stats_of(st))
         a0, m0, r0 = self._bn(st, c0, training)
         x, arg, H2, W2 = ops.maxpool_fwd(a0, N, H1, W1, st.cout)
         if training:
@@ -177,15 +191,16 @@ class ImageTower:
         Hc, Wc = H2, W2
         for blk in self.blocks:
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
-            y1 = ops.linear_fwd(x, c1.w)
+            y1 = ops.linear_fwd(x, c1.w, col_stats=self._stats_of(c1))
             a1, m1, r1 = self._bn(c1, y1, training)
-            y2, Ho, Wo = ops.conv_fwd(a1, N, Hc, Wc, c2.cin, c2.w, 3, stride, 1)      # implicit GEMM (TMA im2col)
+            y2, Ho, Wo = ops.conv_fwd(a1, N, Hc, Wc, c2.cin, c2.w, 3, stride, 1,      # implicit GEMM (TMA im2col)
+                                      col_stats=self._stats_of(c2))
             a2, m2, r2 = self._bn(c2, y2, training)
-            y3 = ops.linear_fwd(a2, c3.w)
+            y3 = ops.linear_fwd(a2, c3.w, col_stats=self._stats_of(c3))
             xs = yd = md = rd = None
             if ds is not None:
                 xs = x if stride == 1 else ops.subsample(x, N, Hc, Wc, ds.cin, stride)[0]
-                yd = ops.linear_fwd(xs, ds.w)
+                yd = ops.linear_fwd(xs, ds.w, col_stats=self._stats_of(ds))
                 idn, md, rd = self._bn(ds, yd, training, relu=False)
             else:
                 idn = x
@@ -222,7 +237,7 @@ class ImageTower:
             d_y3, dz = ops.batchnorm_bwd(d_out, out, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, need_dz=True)
             ops.linear_wgrad(d_y3, a2, c3.dw)
             d_a2 = ops.linear_dgrad(d_y3, c3.w)
-            d_y2, _ = ops.batchnorm_bwd(d_a2, a2, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True)
+            d_y2, _ = ops.batchnorm_bwd(d_a2, None, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, beta=c2.b)
             ops.conv_wgrad(d_y2, a1, N, Hi, Wi, c2.cin, 3, stride, 1, c2.dw)
             if stride == 1:
                 # data gradient = the same implicit-GEMM convolution applied to dY with the rotated weight
@@ -231,7 +246,7 @@ class ImageTower:
             else:
                 d_cols2 = ops.linear_dgrad(d_y2, c2.w)
                 d_a1 = ops.col2im(d_cols2, N, Hi, Wi, c2.cin, 3, stride, 1)
-            d_y1, _ = ops.batchnorm_bwd(d_a1, a1, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True)
+            d_y1, _ = ops.batchnorm_bwd(d_a1, None, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True, beta=c1.b)
             ops.linear_wgrad(d_y1, x, c1.dw)
             if ds is None:
                 d_out = ops.linear_dgrad(d_y1, c1.w, residual=dz)          # identity branch folded into the epilogue
@@ -247,6 +262,6 @@ class ImageTower:
         cols, c0, a0, m0, r0, arg, H1, W1 = sv["stem"]
         st = self.stem
         d_a0 = ops.maxpool_bwd(d_out, arg, N, H1, W1, st.cout)
-        d_c0, _ = ops.batchnorm_bwd(d_a0, a0, c0, m0, r0, st.g, st.dg, st.db, relu=True)
+        d_c0, _ = ops.batchnorm_bwd(d_a0, None, c0, m0, r0, st.g, st.dg, st.db, relu=True, beta=st.b)
         ops.linear_wgrad(d_c0, cols, st.dw)
         self._saved = None

@@ -54,6 +54,50 @@ def _to_device(data, device):
     return text, image, mask, labels
 
 
+class DevicePrefetcher:
+    """Iterates a loader of the reference's batch dicts and yields (text, image, mask, labels, batch) already on the
+    device, copying batch i+1 on a side stream while step i computes (the reference does the copy synchronously at
+    the top of every step, .txt:206-211; its loop is input-bound).  The overlap needs pinned host
+    tensors (``DataLoader(pin_memory=True)``); pageable ones are copied the way the reference copies them."""
+
+    def __init__(self, loader, device, pin: bool = False):
+        self.loader, self.device, self.pin = loader, torch.device(device), pin
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def _stage(self, data):
+        out = {}
+        with torch.cuda.stream(self.stream):
+            for k in ("text", "image", "text_mask", "label"):
+                if k in data:
+                    t = data[k]
+                    if self.pin and not t.is_cuda and not t.is_pinned():
+                        t = t.pin_memory()
+                    out[k] = t.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return out, ev, data
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev, raw = nxt
+            try:
+                nxt = self._stage(next(it))      # issue the next copy before this step's kernels are queued
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for t in cur.values():
+                t.record_stream(torch.cuda.current_stream(self.device))
+            yield cur["text"], cur["image"], cur["text_mask"], cur.get("label"), raw
+
+    def __len__(self):
+        return len(self.loader)
+
+
 def _fused(criterion):
     return isinstance(criterion, (CrossEntropyLoss, SigmoidFocalLoss))
 
@@ -64,9 +108,8 @@ def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_
     correct = 0
     n = 0
     fused = _fused(criterion) and hasattr(model, "train_step_fused")
-    for data in train_loader:
+    for text, image, mask, labels, data in DevicePrefetcher(train_loader, device):
         optimizer.zero_grad()
-        text, image, mask, labels = _to_device(data, device)
         if fused:
             _, loss, ok = model.train_step_fused(text, image, mask, labels, loss_kind=criterion.loss_kind,
                                                  alpha=criterion.alpha, gamma=criterion.gamma)

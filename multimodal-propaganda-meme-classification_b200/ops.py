@@ -77,7 +77,7 @@ def profile_gemm(step_fn, steps: int = 2, ridge: float = 208.0):
 
 
 def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residual=None, aux=None, out2=None,
-             splits=1, block_n=0, p_drop=0.0, seed=0):
+             splits=1, block_n=0, p_drop=0.0, seed=0, col_stats=None):
     """D[M,N] = A x B (+epilogue). A: [M,K] (a_mn False) or [K,M] (a_mn True); B: [N,K] or [K,N]."""
     if _gemm_profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -86,7 +86,7 @@ def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residu
                   _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
                   _p(aux), aux.stride(0) if aux is not None else 0, _p(out), out.stride(0),
                   _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed),
-                  _s())
+                  _p(col_stats), _s())
         e1.record()
         nbytes = 2.0 * (M * K + N * K) + M * N * (8.0 if epi in (EPI_F32, EPI_F32_ATOMIC) else (4.0 if epi == EPI_GELU else 2.0))
         if residual is not None or aux is not None:
@@ -96,19 +96,20 @@ def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residu
     _lib.call("b200mm_gemm_bf16", _p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, epi,
               _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
               _p(aux), aux.stride(0) if aux is not None else 0, _p(out), out.stride(0),
-              _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed), _s(),
-              key=(M, N, K, int(a_mn), int(b_mn), epi, splits))
+              _p(out2), out2.stride(0) if out2 is not None else 0, splits, block_n, float(p_drop), int(seed),
+              _p(col_stats), _s(), key=(M, N, K, int(a_mn), int(b_mn), epi, splits))
     return out
 
 
-def linear_fwd(x, w, bias=None, *, residual=None, out=None, relu=False, p_drop=0.0, seed=0):
-    """y = x @ w.T + bias (+dropout) (+residual) (relu).  x [M,K] bf16, w [N,K] bf16, bias fp32 [N]."""
+def linear_fwd(x, w, bias=None, *, residual=None, out=None, relu=False, p_drop=0.0, seed=0, col_stats=None):
+    """y = x @ w.T + bias (+dropout) (+residual) (relu).  x [M,K] bf16, w [N,K] bf16, bias fp32 [N].
+    col_stats (fp32 [2N], pre-zeroed): also accumulate sum / sum of squares of every output column (BatchNorm)."""
     M, K = x.shape
     N = w.shape[0]
     if out is None:
         out = torch.empty(M, N, device=x.device, dtype=bf16)
     return gemm_raw(x, False, w, False, M, N, K, out, epi=EPI_RELU if relu else EPI_STORE, bias=bias,
-                    residual=residual, p_drop=p_drop, seed=seed)
+                    residual=residual, p_drop=p_drop, seed=seed, col_stats=col_stats)
 
 
 def linear_gelu_fwd(x, w, bias):
@@ -146,7 +147,7 @@ def linear_wgrad(dy, x, dw):
     return gemm_raw(dy, True, x, True, N, K, M, dw, epi=EPI_F32_ATOMIC, splits=_wgrad_splits(N, K, M))
 
 
-def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False, out=None):
+def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False, out=None, col_stats=None):
     """Implicit-GEMM convolution: x NHWC bf16 [N*H*W, C] (C % 64 == 0), w [Cout, k*k*C] -> ([N*P*Q, Cout], P, Q)."""
     Cout = w.shape[0]
     P, Q = conv_out_hw(H, W, ksize, stride, pad)
@@ -157,8 +158,8 @@ def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False,
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.call("b200mm_conv_fwd", _p(x), N, H, W, C, _p(w), Cout, ksize, stride, pad, EPI_RELU if relu else EPI_STORE,
-              None, _p(residual), residual.stride(0) if residual is not None else 0, _p(out), out.stride(0), _s(),
-              key=("conv_fwd", N * P * Q, Cout, ksize * ksize * C, stride))
+              None, _p(residual), residual.stride(0) if residual is not None else 0, _p(out), out.stride(0),
+              _p(col_stats), _s(), key=("conv_fwd", N * P * Q, Cout, ksize * ksize * C, stride))
     if prof is not None:
         e1.record()
         M_, K_ = N * P * Q, ksize * ksize * C
@@ -355,11 +356,19 @@ class BNScratch:
         return b
 
 
-def batchnorm_fwd(x, gamma, beta, running_mean, running_var, *, residual=None, relu=True, eps=1e-5, momentum=0.1):
+def batchnorm_fwd(x, gamma, beta, running_mean, running_var, *, residual=None, relu=True, eps=1e-5, momentum=0.1,
+                  col_stats=None):
+    """Train-mode BatchNorm.  col_stats (fp32 [2C] = sums | sums of squares, from the producing convolution's
+    epilogue): skip the statistics pass."""
     M, C = x.shape
     out = torch.empty_like(x)
     mean = torch.empty(C, device=x.device, dtype=f32)
     rstd = torch.empty(C, device=x.device, dtype=f32)
+    if col_stats is not None:
+        _lib.call("b200mm_batchnorm_fwd_stats", _p(x), _p(residual), M, C, _p(col_stats), _p(gamma), _p(beta),
+                  float(eps), float(momentum), int(relu), _p(out), _p(mean), _p(rstd), _p(running_mean),
+                  _p(running_var), _s())
+        return out, mean, rstd
     _lib.call("b200mm_batchnorm_fwd", _p(x), _p(residual), M, C, _p(gamma), _p(beta), float(eps), float(momentum),
               int(relu), _p(out), _p(mean), _p(rstd), _p(running_mean), _p(running_var),
               _p(BNScratch.get(x.device, C)), _s())
@@ -374,11 +383,13 @@ def batchnorm_eval(x, gamma, beta, running_mean, running_var, *, residual=None, 
     return out
 
 
-def batchnorm_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=True, need_dz=False):
+def batchnorm_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=True, need_dz=False, beta=None):
+    """out=None with relu: the ReLU mask is recomputed from x (pass beta; only valid without a residual)."""
     M, C = x.shape
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if need_dz else None
-    _lib.call("b200mm_batchnorm_bwd", _p(dout), _p(out), _p(x), M, C, _p(mean), _p(rstd), _p(gamma), int(relu),
+    _lib.call("b200mm_batchnorm_bwd", _p(dout), _p(out), _p(x), M, C, _p(mean), _p(rstd), _p(gamma), _p(beta),
+              int(relu),
               _p(dx), _p(dz), _p(dgamma), _p(dbeta), _p(BNScratch.get(x.device, C)), _s())
     return dx, dz
 

@@ -14,7 +14,7 @@ def gemm(A, a_mn, B, b_mn, M, N, K, epi=0, bias=None, residual=None, aux=None, o
     L.call("b200mm_gemm_bf16", P(A), a_mn, A.stride(0), P(B), b_mn, B.stride(0), M, N, K, epi,
            P(bias), P(residual), residual.stride(0) if residual is not None else 0,
            P(aux), aux.stride(0) if aux is not None else 0, P(out), out.stride(0),
-           P(out2), out2.stride(0) if out2 is not None else 0, splits, bn, 0.0, 0, stream)
+           P(out2), out2.stride(0) if out2 is not None else 0, splits, bn, 0.0, 0, None, stream)
 
 
 def rel(a, b):

@@ -28,6 +28,9 @@ if "bn" in which:
         timeit(f"bn_fwd  [{M},{C}]", lambda: ops.batchnorm_fwd(x, g, b, rm, rv), bytes_=3 * M * C * 2)
         dout = torch.randn(M, C, device=dev).to(bf); dg = torch.zeros(C, device=dev); db = torch.zeros(C, device=dev)
         timeit(f"bn_bwd  [{M},{C}]", lambda: ops.batchnorm_bwd(dout, out, x, mean, rstd, g, dg, db), bytes_=7 * M * C * 2)
+        timeit(f"bn_bwd  [{M},{C}] mask from x", lambda: ops.batchnorm_bwd(dout, None, x, mean, rstd, g, dg, db, beta=b), bytes_=5 * M * C * 2)
+        st = torch.zeros(2 * C, device=dev); st[:C] = x.float().sum(0); st[C:] = (x.float() ** 2).sum(0)
+        timeit(f"bn_fwd  [{M},{C}] given stats", lambda: ops.batchnorm_fwd(x, g, b, rm, rv, col_stats=st), bytes_=2 * M * C * 2)
 if "col2im" in which:
     for (N, H, C, s) in [(256, 56, 64, 1), (256, 56, 128, 2), (256, 14, 256, 1)]:
         Ho = H // s

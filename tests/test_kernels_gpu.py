@@ -239,6 +239,12 @@ def test_batchnorm_fwd_bwd(ops, cuda_device, M, C, relu, use_res):
     assert rel(dg, gf.grad) < 2e-2 and rel(db, bf.grad) < 2e-2
     if use_res:
         assert rel(dz, resf.grad) < 2e-2
+    if relu and not use_res:
+        # ReLU mask recomputed from x instead of read from the saved output: same gradients up to the summation
+        # order of the column reductions (the two variants unroll differently)
+        dg2, db2 = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+        dx2, _ = ops.batchnorm_bwd(dout, None, x, mean, rstd, g, dg2, db2, relu=True, beta=b)
+        assert rel(dg2, dg) < 1e-5 and rel(db2, db) < 1e-5 and rel(dx2, dx) < 1e-3
     ev = ops.batchnorm_eval(x, g, b, rm2, rv2, residual=res, relu=relu)
     ref_ev = F.batch_norm(x.float(), rm2, rv2, g, b, False, 0.1, 1e-5)
     if use_res:
@@ -246,6 +252,31 @@ def test_batchnorm_fwd_bwd(ops, cuda_device, M, C, relu, use_res):
     if relu:
         ref_ev = torch.relu(ref_ev)
     assert rel(ev, ref_ev) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 64, 152), (3000, 256, 64), (1000, 512, 256), (777, 2048, 512), (5000, 128, 1152)])
+def test_gemm_column_statistics_feed_batchnorm(ops, cuda_device, M, N, K):
+    """The convolution epilogue's column sums (over the stored bf16 outputs) and the one-pass BatchNorm they feed,
+    against the separate statistics pass and against F.batch_norm."""
+    torch.manual_seed(21)
+    x = torch.randn(M, K, device=cuda_device).to(bf16)
+    w = (torch.randn(N, K, device=cuda_device) / K ** 0.5).to(bf16)
+    stats = torch.zeros(2 * N, device=cuda_device)
+    y = ops.linear_fwd(x, w, col_stats=stats)
+    y_plain = ops.linear_fwd(x, w)
+    assert torch.equal(y, y_plain)
+    yf = y.float()
+    assert rel(stats[:N], yf.sum(0)) < 1e-4 and rel(stats[N:], (yf * yf).sum(0)) < 1e-4
+    g = torch.rand(N, device=cuda_device) + 0.5
+    b = torch.randn(N, device=cuda_device)
+    rm, rv = torch.zeros(N, device=cuda_device), torch.ones(N, device=cuda_device)
+    rm2, rv2 = torch.zeros(N, device=cuda_device), torch.ones(N, device=cuda_device)
+    out, mean, rstd = ops.batchnorm_fwd(y, g, b, rm, rv, col_stats=stats)
+    out2, mean2, rstd2 = ops.batchnorm_fwd(y, g, b, rm2, rv2)
+    assert rel(mean, mean2) < 1e-4 and rel(rstd, rstd2) < 1e-4 and rel(out, out2) < 5e-3
+    assert rel(rm, rm2) < 1e-4 and rel(rv, rv2) < 1e-4
+    ref = torch.relu(F.batch_norm(yf, None, None, g, b, True, 0.1, 1e-5))
+    assert rel(out, ref) < 1e-2
 
 
 def _nhwc(x):  # NCHW fp32 -> [N*H*W, C] bf16
