@@ -144,6 +144,28 @@ int b200mm_head_loss(const void* feat, const float* W, const float* bias, const 
                      float* logits, float* loss_sum, int* correct, void* dfeat, float* dW, float* dbias,
                      void* stream);
 int b200mm_colsum_bf16(const void* x, long long ld, int M, int N, float* out, void* stream);
+/* ---- HEAD-script head (example_scripts/Multimodal_example_task2C.py:476-499 ConcatAttention3, :571-574 fine_tune,
+ * :599-601 text_fc, :641-643 output_fc, :167 sigmoid_focal_loss): small batch-dimension kernels ------------------- */
+/* BatchNorm1d (+ReLU) over x[B,C] (bf16, or fp32 when x_f32 != 0); train: batch statistics (saved in mean/rstd,
+ * folded into running_*); out / dx are bf16. */
+int b200mm_bn1d_fwd(const void* x, int x_f32, long long ldx, int B, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, int relu, int train, void* out, long long ldo, float* mean, float* rstd,
+                    float* running_mean, float* running_var, void* stream);
+int b200mm_bn1d_bwd(const void* dout, long long ldd, const void* out, long long ldo, const void* x, int x_f32,
+                    long long ldx, int B, int C, const float* mean, const float* rstd, const float* gamma, int relu, void* dx,
+                    long long lddx, float* dgamma, float* dbeta, void* stream);
+/* y = softmax(a, dim=1) * x (weights w kept in fp32); backward: da, and dx_direct = dy * w */
+int b200mm_softmax_gate_fwd(const void* a, const void* x, int B, int C, float* w, void* y, void* stream);
+int b200mm_softmax_gate_bwd(const void* dy, const float* w, const void* x, int B, int C, void* da, void* dx_direct,
+                            void* stream);
+int b200mm_relu_bwd(const void* dy, const void* y, long long n, void* dx, void* stream);
+/* Linear(F,1) + BatchNorm1d(1) + sigmoid focal loss (+ backward), one CTA, B <= 4096; loss / correct accumulate. */
+int b200mm_head_bn_focal(const void* feat, const float* W, const float* bias, const float* bn_gamma,
+                         const float* bn_beta, float* running_mean, float* running_var, const long long* labels, int B,
+                         int F, float eps, float momentum, float alpha, float gamma, int train, int bn_train,
+                         const float* dlogits_in, float* logits, float* loss, int* correct, void* dfeat, float* dW,
+                         float* dbias, float* dg, float* dbeta, void* stream);
+
 /* optim.Adam(...).step() (example_scripts/Multimodal_example_task2C.txt:217, :249) + clip_grad_norm_
  * (Multimodal_example_task2C.py:713-715) over a flat fp32 parameter range, refreshing the bf16 shadow */
 int b200mm_sumsq_f32(const float* g, long long n, float* out, void* stream);

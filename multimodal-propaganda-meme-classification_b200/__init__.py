@@ -12,6 +12,7 @@ __version__ = "0.1.0"
 
 _LAZY = {
     "MultimodalClassifier": ("model", "MultimodalClassifier"),
+    "MultimodalClassifierHEAD": ("head_model", "MultimodalClassifierHEAD"),
     "TextConfig": ("text_tower", "TextConfig"),
     "ImageConfig": ("image_tower", "ImageConfig"),
     "ViTConfig": ("vit_tower", "ViTConfig"),

@@ -139,3 +139,13 @@ declare("b200mm_im2col_nchw_f32", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_i
                                    c_ptr])
 declare("b200mm_subsample_nhwc", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_upsample_add_nhwc", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_bn1d_fwd", [c_ptr, c_int, c_longlong, c_int, c_int, c_ptr, c_ptr, c_float, c_float, c_int, c_int, c_ptr,
+                            c_longlong, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_bn1d_bwd", [c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_int, c_longlong, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                            c_int, c_ptr, c_longlong, c_ptr, c_ptr, c_ptr])
+declare("b200mm_softmax_gate_fwd", [c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr])
+declare("b200mm_softmax_gate_bwd", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr])
+declare("b200mm_relu_bwd", [c_ptr, c_ptr, c_longlong, c_ptr, c_ptr])
+declare("b200mm_head_bn_focal", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_float,
+                                 c_float, c_float, c_float, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                 c_ptr, c_ptr, c_ptr, c_ptr])

@@ -25,11 +25,17 @@ STEM_KP = 152  # K padded to a multiple of 8 elements (TMA row stride must be a 
 class ImageConfig:
     layers: tuple = (3, 4, 6, 3)   # ResNet-50
     width: int = 64
-    num_outputs: int = 1000
+    block: str = "bottleneck"      # 'bottleneck' (ResNet-50/101/152) | 'basic' (ResNet-18/34, the HEAD script's tower)
+    num_outputs: int = 1000        # 0: no fc, the pooled feature is returned (timm reset_classifier(0))
     bn_eps: float = 1e-5
     bn_momentum: float = 0.1
     prefix: str = "resnet"
     arch: str = "resnet"
+
+    @staticmethod
+    def resnet18(**kw) -> "ImageConfig":
+        """timm.create_model('resnet18') + reset_classifier(0) (Multimodal_example_task2C.py:84, 569-570)."""
+        return ImageConfig(layers=(2, 2, 2, 2), block="basic", num_outputs=0, **kw)
 
 
 class _Conv:
@@ -49,24 +55,36 @@ class ImageTower:
         self.stem = _Conv(f"{p}.conv1", f"{p}.bn1", 3, cfg.width, 7, 2, 3)
         self.blocks = []
         inplanes = cfg.width
+        if cfg.block not in ("bottleneck", "basic"):
+            raise ValueError(f"unknown ResNet block {cfg.block!r}")
+        self.basic = cfg.block == "basic"
+        expansion = 1 if self.basic else 4
         for li, nblocks in enumerate(cfg.layers):
             planes = cfg.width * (2 ** li)
             for bi in range(nblocks):
                 stride = 2 if (li > 0 and bi == 0) else 1
                 base = f"{p}.layer{li + 1}.{bi}"
-                blk = {
-                    "c1": _Conv(f"{base}.conv1", f"{base}.bn1", inplanes, planes, 1, 1, 0),
-                    "c2": _Conv(f"{base}.conv2", f"{base}.bn2", planes, planes, 3, stride, 1),
-                    "c3": _Conv(f"{base}.conv3", f"{base}.bn3", planes, planes * 4, 1, 1, 0),
-                    "ds": None,
-                    "stride": stride,
-                }
-                if stride != 1 or inplanes != planes * 4:
-                    blk["ds"] = _Conv(f"{base}.downsample.0", f"{base}.downsample.1", inplanes, planes * 4, 1, stride, 0)
+                if self.basic:     # torchvision BasicBlock (resnet.py:59-105): 3x3 (stride) -> 3x3
+                    blk = {
+                        "c1": _Conv(f"{base}.conv1", f"{base}.bn1", inplanes, planes, 3, stride, 1),
+                        "c2": _Conv(f"{base}.conv2", f"{base}.bn2", planes, planes, 3, 1, 1),
+                        "c3": None, "ds": None, "stride": stride,
+                    }
+                else:
+                    blk = {
+                        "c1": _Conv(f"{base}.conv1", f"{base}.bn1", inplanes, planes, 1, 1, 0),
+                        "c2": _Conv(f"{base}.conv2", f"{base}.bn2", planes, planes, 3, stride, 1),
+                        "c3": _Conv(f"{base}.conv3", f"{base}.bn3", planes, planes * 4, 1, 1, 0),
+                        "ds": None,
+                        "stride": stride,
+                    }
+                if stride != 1 or inplanes != planes * expansion:
+                    blk["ds"] = _Conv(f"{base}.downsample.0", f"{base}.downsample.1", inplanes, planes * expansion, 1,
+                                      stride, 0)
                 self.blocks.append(blk)
-                inplanes = planes * 4
+                inplanes = planes * expansion
         self.feat_dim = inplanes
-        self.out_dim = cfg.num_outputs   # the 1000-way ImageNet fc is kept (.txt:164-165)
+        self.out_dim = cfg.num_outputs or inplanes   # the 1000-way ImageNet fc is kept (.txt:164-165) unless 0
         self._convs = [self.stem] + [c for b in self.blocks for c in (b["c1"], b["c2"], b["c3"], b["ds"]) if c]
         self._conv_by_weight = {c.name + ".weight": c for c in self._convs}
         off = 0
@@ -84,13 +102,15 @@ class ImageTower:
         for c in self._convs:
             st.add(f"{c.bn_name}.weight", (c.cout,), shadow=False)
             st.add(f"{c.bn_name}.bias", (c.cout,), shadow=False)
-        st.add(f"{self.cfg.prefix}.fc.bias", (self.cfg.num_outputs,), shadow=False)
+        if self.cfg.num_outputs:
+            st.add(f"{self.cfg.prefix}.fc.bias", (self.cfg.num_outputs,), shadow=False)
 
     def register_shadowed(self):
         st = self.store
         for c in self._convs:
             st.add(f"{c.name}.weight", (c.cout, c.kdim))   # OHWI flattened: [Cout, kh*kw*Cin] (stem padded to 152)
-        st.add(f"{self.cfg.prefix}.fc.weight", (self.cfg.num_outputs, self.feat_dim))
+        if self.cfg.num_outputs:
+            st.add(f"{self.cfg.prefix}.fc.weight", (self.cfg.num_outputs, self.feat_dim))
 
     def bind(self):
         st = self.store
@@ -108,8 +128,9 @@ class ImageTower:
             c.rv.fill_(1.0)
             off += 2 * c.cout
         p = self.cfg.prefix
-        self.fc_w, self.dfc_w = st.s(f"{p}.fc.weight"), st.g(f"{p}.fc.weight")
-        self.fc_b, self.dfc_b = st.p(f"{p}.fc.bias"), st.g(f"{p}.fc.bias")
+        if self.cfg.num_outputs:
+            self.fc_w, self.dfc_w = st.s(f"{p}.fc.weight"), st.g(f"{p}.fc.weight")
+            self.fc_b, self.dfc_b = st.p(f"{p}.fc.bias"), st.g(f"{p}.fc.bias")
         self.num_batches_tracked = 0
 
     def init_parameters(self, generator=None):
@@ -125,9 +146,10 @@ class ImageTower:
             st.p(f"{c.bn_name}.weight").fill_(1.0)
             st.p(f"{c.bn_name}.bias").zero_()
         p = self.cfg.prefix
-        bound = 1.0 / (self.feat_dim ** 0.5)
-        st.p(f"{p}.fc.weight").uniform_(-bound, bound, generator=generator)
-        st.p(f"{p}.fc.bias").uniform_(-bound, bound, generator=generator)
+        if self.cfg.num_outputs:
+            bound = 1.0 / (self.feat_dim ** 0.5)
+            st.p(f"{p}.fc.weight").uniform_(-bound, bound, generator=generator)
+            st.p(f"{p}.fc.bias").uniform_(-bound, bound, generator=generator)
 
     # ------------------------------------------------------------------ state-dict layout exchange (see model.py)
     def import_param(self, name: str, src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -191,6 +213,24 @@ class ImageTower:
         Hc, Wc = H2, W2
         for blk in self.blocks:
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
+            if self.basic:
+                y1, Ho, Wo = ops.conv_fwd(x, N, Hc, Wc, c1.cin, c1.w, 3, stride, 1, col_stats=self._stats_of(c1))
+                a1, m1, r1 = self._bn(c1, y1, training)
+                y2, _, _ = ops.conv_fwd(a1, N, Ho, Wo, c2.cin, c2.w, 3, 1, 1, col_stats=self._stats_of(c2))
+                xs = yd = md = rd = None
+                if ds is not None:
+                    xs = x if stride == 1 else ops.subsample(x, N, Hc, Wc, ds.cin, stride)[0]
+                    yd = ops.linear_fwd(xs, ds.w, col_stats=self._stats_of(ds))
+                    idn, md, rd = self._bn(ds, yd, training, relu=False)
+                else:
+                    idn = x
+                out, m2, r2 = self._bn(c2, y2, training, residual=idn, relu=True)
+                if training:
+                    sv["blocks"].append((x, y1, a1, m1, r1, y2, m2, r2, xs, yd, md, rd, out, Hc, Wc, Ho, Wo))
+                x, Hc, Wc = out, Ho, Wo
+                if self.capture is not None:
+                    self.capture.append((x, N, Hc, Wc))
+                continue
             y1 = ops.linear_fwd(x, c1.w, col_stats=self._stats_of(c1))
             a1, m1, r1 = self._bn(c1, y1, training)
             y2, Ho, Wo = ops.conv_fwd(a1, N, Hc, Wc, c2.cin, c2.w, 3, stride, 1,      # implicit GEMM (TMA im2col)
@@ -212,7 +252,7 @@ class ImageTower:
             if self.capture is not None:
                 self.capture.append((x, N, Hc, Wc))
         pooled = ops.avgpool_fwd(x, N, Hc * Wc, self.feat_dim)
-        logits = ops.linear_fwd(pooled, self.fc_w, self.fc_b)
+        logits = ops.linear_fwd(pooled, self.fc_w, self.fc_b) if self.cfg.num_outputs else pooled
         if training:
             sv["tail"] = (pooled, Hc, Wc)
             self.num_batches_tracked += 1
@@ -226,12 +266,41 @@ class ImageTower:
         assert sv is not None, "backward() without a training-mode forward()"
         N = sv["N"]
         pooled, Hc, Wc = sv["tail"]
-        ops.linear_wgrad(dlogits, pooled, self.dfc_w)
-        ops.colsum(dlogits, self.dfc_b)
-        dpooled = ops.linear_dgrad(dlogits, self.fc_w)
+        if self.cfg.num_outputs:
+            ops.linear_wgrad(dlogits, pooled, self.dfc_w)
+            ops.colsum(dlogits, self.dfc_b)
+            dpooled = ops.linear_dgrad(dlogits, self.fc_w)
+        else:
+            dpooled = dlogits.contiguous()
         d_out = ops.avgpool_bwd(dpooled, N, Hc * Wc, self.feat_dim)
         for blk, s in zip(reversed(self.blocks), reversed(sv["blocks"])):
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
+            if self.basic:
+                x, y1, a1, m1, r1, y2, m2, r2, xs, yd, md, rd, out, Hi, Wi, Ho, Wo = s
+                # out = relu(bn2(y2) + idn)
+                d_y2, dz = ops.batchnorm_bwd(d_out, out, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, need_dz=True)
+                ops.conv_wgrad(d_y2, a1, N, Ho, Wo, c2.cin, 3, 1, 1, c2.dw)
+                d_a1, _, _ = ops.conv_fwd(d_y2, N, Ho, Wo, c2.cout, ops.conv_weight_rotate(c2.w, c2.cout, c2.cin, 3),
+                                          3, 1, 1)
+                d_y1, _ = ops.batchnorm_bwd(d_a1, None, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True, beta=c1.b)
+                ops.conv_wgrad(d_y1, x, N, Hi, Wi, c1.cin, 3, stride, 1, c1.dw)
+                if ds is None:      # stride 1: data gradient + identity branch in one epilogue
+                    d_out, _, _ = ops.conv_fwd(d_y1, N, Ho, Wo, c1.cout,
+                                               ops.conv_weight_rotate(c1.w, c1.cout, c1.cin, 3), 3, 1, 1, residual=dz)
+                else:
+                    d_yd, _ = ops.batchnorm_bwd(dz, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=False)
+                    ops.linear_wgrad(d_yd, xs, ds.dw)
+                    d_xs = ops.linear_dgrad(d_yd, ds.w)
+                    if stride == 1:
+                        d_x1, _, _ = ops.conv_fwd(d_y1, N, Ho, Wo, c1.cout,
+                                                  ops.conv_weight_rotate(c1.w, c1.cout, c1.cin, 3), 3, 1, 1,
+                                                  residual=d_xs)
+                        d_out = d_x1
+                    else:
+                        d_cols = ops.linear_dgrad(d_y1, c1.w)
+                        d_x1 = ops.col2im(d_cols, N, Hi, Wi, c1.cin, 3, stride, 1)
+                        d_out = ops.upsample_add(d_xs, d_x1, N, Hi, Wi, ds.cin, stride)
+                continue
             x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hi, Wi, Ho, Wo = s
             # out = relu(bn3(y3) + idn)
             d_y3, dz = ops.batchnorm_bwd(d_out, out, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, need_dz=True)

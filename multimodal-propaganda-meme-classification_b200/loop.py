@@ -54,6 +54,14 @@ def _to_device(data, device):
     return text, image, mask, labels
 
 
+def _extra_inputs(data, device):
+    """The HEAD script's batches also carry the BLIP caption tokens (Multimodal_example_task2C.py:293-303, 706-708):
+    returned as extra positional inputs of the model when present."""
+    if "caption_text" not in data:
+        return ()
+    return (data["caption_text"].to(device, non_blocking=True), data["caption_text_mask"].to(device, non_blocking=True))
+
+
 class DevicePrefetcher:
     """Iterates a loader of the reference's batch dicts and yields (text, image, mask, labels, batch) already on the
     device, copying batch i+1 on a side stream while step i computes (the reference does the copy synchronously at

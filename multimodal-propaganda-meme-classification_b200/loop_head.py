@@ -9,8 +9,9 @@
     evaluate(model, test_loader, threshold, device)  -> task2C_<team>.tsv + task2C_<team>_probs_fold_<k>.tsv  :837-879
 
 with a single-logit head + sigmoid focal loss (``MultimodalClassifier(num_classes=1, squeeze_output=True)`` and
-``SigmoidFocalLoss``; :167, :641-643).  The towers are the engine's two (text + image); the script's third
-(caption) tower and its BatchNorm1d / ConcatAttention head variants are listed as "next" in DESIGN.md.
+``SigmoidFocalLoss``; :167, :641-643) on the two-tower model, or with the script's own three-tower model
+(``b200mm.MultimodalClassifierHEAD``: caption tower, BatchNorm1d projection heads, ConcatAttention3; batches then
+also carry ``caption_text`` / ``caption_text_mask``, :293-303).
 
 What is deliberately NOT reproduced: clipping before un-scaling under AMP (:712-717) --
 the engine is bf16 with fp32 master weights and needs no loss scaling, so ``scaler`` is accepted and ignored and the
@@ -25,7 +26,7 @@ import numpy as np
 import torch
 
 from . import ensemble
-from .loop import ID2L, SigmoidFocalLoss, _fused, _to_device
+from .loop import ID2L, SigmoidFocalLoss, _extra_inputs, _fused, _to_device
 from .tsv import write_label_tsv, write_prob_tsv
 
 
@@ -64,6 +65,8 @@ def stratified_kfold(labels, n_splits: int = 5, seed: int = 42):
 def get_params(model, lr: float):
     """Three param groups as in the HEAD script (:645-664): everything else @ lr, text tower @ 0.8 lr, image tower
     @ 0.8 lr (engine names: ``bert.*`` is the text tower, ``resnet.*`` the image tower)."""
+    if hasattr(model, "get_params"):      # the three-tower HEAD model carries the reference's own method
+        return model.get_params(lr)
     text, image, other = [], [], []
     for name, p in model.named_parameters():
         (text if name.startswith("bert.") else image if name.startswith("resnet.") else other).append(p)
@@ -82,12 +85,13 @@ def test(model, test_loader, criterion, device, epoch=0, log=print):
     with torch.no_grad():
         for batch_idx, data in enumerate(test_loader, 1):
             text, image, mask, labels = _to_device(data, device)
+            extra = _extra_inputs(data, device)
             if fused:
-                output, loss, _ = model.eval_step_fused(text, image, mask, labels, loss_kind=criterion.loss_kind,
+                output, loss, _ = model.eval_step_fused(text, image, mask, *extra, labels, loss_kind=criterion.loss_kind,
                                                         alpha=criterion.alpha, gamma=criterion.gamma)
                 loss_v = loss.item()
             else:
-                output = model(text, image, mask)
+                output = model(text, image, mask, *extra)
                 loss_v = criterion(output, labels.float()).item()
             test_loss += loss_v * labels.size(0)
             n += labels.size(0)
@@ -118,7 +122,7 @@ def evaluate(model, test_loader, t_optimal_threshold, device, *, fold=0, team_na
     with torch.no_grad():
         for data in test_loader:
             text, image, mask, _ = _to_device(data, device)
-            probs.append(_probs(model(text, image, mask)).cpu())
+            probs.append(_probs(model(text, image, mask, *_extra_inputs(data, device))).cpu())
             ids.extend(list(data["id"]))
     probs = torch.cat(probs).numpy() if probs else np.zeros(0, dtype=np.float32)
     labels = [ID2L[int(p > t_optimal_threshold)] for p in probs]
@@ -143,13 +147,14 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
     for batch_idx, data in enumerate(train_loader, 1):
         optimizer.zero_grad()
         text, image, mask, labels = _to_device(data, device)
+        extra = _extra_inputs(data, device)
         if fused:
-            output, loss, ok = model.train_step_fused(text, image, mask, labels, loss_kind=criterion.loss_kind,
+            output, loss, ok = model.train_step_fused(text, image, mask, *extra, labels, loss_kind=criterion.loss_kind,
                                                       alpha=criterion.alpha, gamma=criterion.gamma)
             optimizer.step()
             loss_v, ok_v = loss.item(), ok.item()
         else:
-            output = model(text, image, mask)
+            output = model(text, image, mask, *extra)
             loss = criterion(output, labels.float() if output.dim() == 1 else labels)
             loss.backward()
             optimizer.step()

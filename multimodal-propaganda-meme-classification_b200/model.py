@@ -32,15 +32,15 @@ class _EngineFunction(torch.autograd.Function):
     """Single autograd node: forward = engine forward, backward = engine backward (grads written in place)."""
 
     @staticmethod
-    def forward(ctx, anchor, model, text, image, mask):
-        ctx.model = model
-        logits = model._engine_forward(text, image, mask, training=True)
+    def forward(ctx, anchor, model, *inputs):
+        ctx.model, ctx.n_inputs = model, len(inputs)
+        logits = model._engine_forward(*inputs, training=True)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         ctx.model._engine_backward_from_dlogits(dlogits.reshape(dlogits.shape[0], -1).contiguous())
-        return torch.zeros((), device=dlogits.device), None, None, None, None
+        return (torch.zeros((), device=dlogits.device), None) + (None,) * ctx.n_inputs
 
 
 class MultimodalClassifier(nn.Module):

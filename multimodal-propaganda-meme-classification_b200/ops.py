@@ -112,6 +112,14 @@ def linear_fwd(x, w, bias=None, *, residual=None, out=None, relu=False, p_drop=0
                     residual=residual, p_drop=p_drop, seed=seed, col_stats=col_stats)
 
 
+def linear_fwd_f32(x, w, bias=None):
+    """y = x @ w.T + bias with an fp32 result (for the rare spot where bf16 storage would lose the signal)."""
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=x.device, dtype=f32)
+    return gemm_raw(x, False, w, False, M, N, K, out, epi=EPI_F32, bias=bias)
+
+
 def linear_gelu_fwd(x, w, bias):
     """z = x @ w.T + bias ; a = gelu(z) (exact erf).  Returns (z, a), both bf16 [M,N]."""
     M, K = x.shape
@@ -321,6 +329,69 @@ def head_loss(feat, W, bias, labels, *, loss_kind=LOSS_CE, alpha=0.25, gamma=2.0
     _lib.call("b200mm_head_loss", _p(feat), _p(W), _p(bias), _p(labels), B, F, C, loss_kind, float(alpha),
               float(gamma), int(train), _p(dlogits), _p(logits), _p(loss), _p(correct), _p(dfeat), _p(dW), _p(dbias),
               _s())
+    return logits, loss, correct, dfeat
+
+
+# ----------------------------------------------------------------------------------------------- HEAD-script head
+def bn1d_fwd(x, gamma, beta, running_mean, running_var, *, relu=False, train=True, eps=1e-5, momentum=0.1, out=None):
+    """BatchNorm1d (+ReLU) over x [B, C] bf16 (may be a column slice).  Returns (out, mean, rstd)."""
+    B, C = x.shape
+    if out is None:
+        out = torch.empty(B, C, device=x.device, dtype=bf16)
+    mean = torch.empty(C, device=x.device, dtype=f32) if train else None
+    rstd = torch.empty(C, device=x.device, dtype=f32) if train else None
+    _lib.call("b200mm_bn1d_fwd", _p(x), int(x.dtype == f32), x.stride(0), B, C, _p(gamma), _p(beta), float(eps), float(momentum), int(relu),
+              int(train), _p(out), out.stride(0), _p(mean), _p(rstd), _p(running_mean), _p(running_var), _s())
+    return out, mean, rstd
+
+
+def bn1d_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=False):
+    B, C = x.shape
+    dx = torch.empty(B, C, device=x.device, dtype=bf16)
+    _lib.call("b200mm_bn1d_bwd", _p(dout), dout.stride(0), _p(out), out.stride(0) if out is not None else 0, _p(x),
+              int(x.dtype == f32), x.stride(0), B, C, _p(mean), _p(rstd), _p(gamma), int(relu), _p(dx), dx.stride(0), _p(dgamma),
+              _p(dbeta), _s())
+    return dx
+
+
+def softmax_gate_fwd(a, x):
+    """y = softmax(a, dim=1) * x.  Returns (y bf16, w fp32)."""
+    B, C = a.shape
+    w = torch.empty(B, C, device=a.device, dtype=f32)
+    y = torch.empty(B, C, device=a.device, dtype=bf16)
+    _lib.call("b200mm_softmax_gate_fwd", _p(a), _p(x), B, C, _p(w), _p(y), _s())
+    return y, w
+
+
+def softmax_gate_bwd(dy, w, x):
+    """Returns (da, dx_direct)."""
+    B, C = w.shape
+    da = torch.empty(B, C, device=w.device, dtype=bf16)
+    dxd = torch.empty(B, C, device=w.device, dtype=bf16)
+    _lib.call("b200mm_softmax_gate_bwd", _p(dy), _p(w), _p(x), B, C, _p(da), _p(dxd), _s())
+    return da, dxd
+
+
+def relu_bwd(dy, y):
+    dx = torch.empty_like(y)
+    _lib.call("b200mm_relu_bwd", _p(dy), _p(y), y.numel(), _p(dx), _s())
+    return dx
+
+
+def head_bn_focal(feat, W, bias, bn_g, bn_b, running_mean, running_var, labels, *, alpha=0.25, gamma=2.0, train=True,
+                  bn_train=True, eps=1e-5, momentum=0.1, dlogits=None, dW=None, dbias=None, dg=None, dbeta=None):
+    """Linear(F,1) + BatchNorm1d(1) + sigmoid focal loss (+ backward when train).
+    Returns (logits fp32 [B], loss fp32 [1], correct int32 [1], dfeat bf16 [B,F] | None)."""
+    B, F = feat.shape
+    dev = feat.device
+    logits = torch.empty(B, device=dev, dtype=f32)
+    loss = torch.zeros(1, device=dev, dtype=f32)
+    correct = torch.zeros(1, device=dev, dtype=torch.int32)
+    dfeat = torch.empty(B, F, device=dev, dtype=bf16) if train else None
+    _lib.call("b200mm_head_bn_focal", _p(feat), _p(W), _p(bias), _p(bn_g), _p(bn_b), _p(running_mean),
+              _p(running_var), _p(labels), B, F, float(eps), float(momentum), float(alpha), float(gamma), int(train),
+              int(bn_train), _p(dlogits), _p(logits), _p(loss), _p(correct), _p(dfeat), _p(dW), _p(dbias), _p(dg),
+              _p(dbeta), _s())
     return logits, loss, correct, dfeat
 
 

@@ -307,3 +307,70 @@ def cpu_train_throughput(batch: int = 16, seq_len: int = 128, steps: int = 3, wa
     med = sorted(times)[len(times) // 2]
     return {"samples_per_s": batch / med, "best_s": best, "median_s": med, "cores": threads,
             "batch": batch, "seq_len": seq_len, "steps": steps}
+
+
+# ------------------------------------------------------------------------------------------------- HEAD-script model
+class LLMWithClassificationHead(nn.Module):
+    """Reference: example_scripts/Multimodal_example_task2C.py:307-360, ``pooling_type="cls"`` (the only one the
+    script selects, :589-591, :603-605); ``AutoModel.from_pretrained`` -> from-config random init."""
+
+    def __init__(self, model: nn.Module):
+        super().__init__()
+        self.model = model
+
+    def forward(self, input_ids, attention_mask):
+        return self.model(input_ids=input_ids, attention_mask=attention_mask).last_hidden_state[:, 0]   # :359-360
+
+
+class ConcatAttention3(nn.Module):
+    """Reference: :476-499."""
+
+    def __init__(self, input_dim, attention_dim):
+        super().__init__()
+        self.attention_layer = nn.Sequential(nn.Linear(input_dim, input_dim), nn.BatchNorm1d(input_dim), nn.ReLU(),
+                                             nn.Softmax(dim=1))
+        self.reduce = nn.Sequential(nn.Linear(input_dim, attention_dim), nn.BatchNorm1d(attention_dim), nn.ReLU())
+
+    def forward(self, text_features, image_features, caption_features):
+        x = torch.cat((text_features, image_features, caption_features), dim=1)
+        return self.reduce(self.attention_layer(x) * x)
+
+
+class CustomDenseNet161(nn.Module):
+    """Reference: :562-585 -- timm ``resnet18`` with ``reset_classifier(0)`` (timm is not installed here; timm's
+    ResNet-18 is torchvision's BasicBlock ResNet with the same state-dict keys) + ``fine_tune`` MLP."""
+
+    def __init__(self, layers=(2, 2, 2, 2)):
+        super().__init__()
+        from torchvision.models.resnet import BasicBlock, ResNet
+        self.image_model = ResNet(BasicBlock, list(layers), num_classes=1000)
+        self.image_model.fc = nn.Identity()                       # reset_classifier(0)
+        self.fine_tune = nn.Sequential(nn.Linear(512, 512), nn.ReLU(inplace=True), nn.Dropout(p=0.35),
+                                       nn.Linear(512, 512))
+
+    def forward(self, x):
+        return self.fine_tune(self.image_model(x))
+
+
+class MultimodalClassifierHEAD(nn.Module):
+    """Reference: :587-685 with ``fusion_method="concatenation"`` (same attribute names / state-dict keys)."""
+
+    def __init__(self, text_cfg: TowerConfig, caption_cfg: TowerConfig, resnet_layers=(2, 2, 2, 2)):
+        super().__init__()
+        self.text_model = LLMWithClassificationHead(build_text(text_cfg))
+        self.text_dropout = nn.Dropout(0.3)
+        self.text_fc = nn.Sequential(nn.Linear(text_cfg.dim, 512), nn.BatchNorm1d(512), nn.ReLU())
+        self.caption_text_model = LLMWithClassificationHead(build_text(caption_cfg))
+        self.caption_text_dropout = nn.Dropout(0.3)
+        self.caption_text_fc = nn.Sequential(nn.Linear(caption_cfg.dim, 512), nn.BatchNorm1d(512), nn.ReLU())
+        self.image_model = CustomDenseNet161(resnet_layers)
+        self.fusion_layer = ConcatAttention3(3 * 512, 512)
+        self.output_fc = nn.Sequential(nn.Linear(512, 1), nn.BatchNorm1d(1))
+
+    def forward(self, text, image, mask, caption_text, caption_text_mask):
+        t = self.text_fc(self.text_dropout(self.text_model(text, attention_mask=mask)))
+        c = self.caption_text_fc(self.caption_text_dropout(
+            self.caption_text_model(caption_text, attention_mask=caption_text_mask)))
+        i = self.image_model(image)
+        out = self.output_fc(self.fusion_layer(t, i, c))
+        return out.squeeze(1)

@@ -71,3 +71,25 @@ if "gemm" in which or "gemm1" in which:
         bias = torch.zeros(N, device=dev) if epi != 2 else None   # dgrad epilogues carry no bias
         timeit(f"gemm M{M} N{N} K{K} b_mn{b_mn} epi{epi}{'+res' if res is not None else ''}", lambda: ops.gemm_raw(A, False, Bm, bool(b_mn), M, N, K, out, epi=epi, bias=bias, aux=aux, out2=out2, residual=res),
                flops=2.0 * M * N * K, bytes_=2.0 * (M * K + N * K + M * N * (2 if epi == 1 else 1) + (M * N if epi == 2 else 0)))
+if "attn" in which:
+    for (B, H, S) in [(256, 12, 128), (256, 12, 197)]:
+        qkv = torch.randn(B * S, 3 * H * 64, device=dev).to(bf)
+        mask = torch.ones(B, S, dtype=torch.int64, device=dev)
+        kb = ops.mask_to_bias(mask)
+        for pdrop in (0.0, 0.1):
+            out, lse = ops.attention_fwd(qkv, kb, B, H, S, p_drop=pdrop, seed=1)
+            dout = torch.randn_like(out)
+            fl = 4.0 * S * S * 64 * B * H
+            timeit(f"attn_fwd B{B} H{H} S{S} p{pdrop}", lambda: ops.attention_fwd(qkv, kb, B, H, S, p_drop=pdrop, seed=1),
+                   flops=fl, bytes_=qkv.numel() * 2 + out.numel() * 2)
+            timeit(f"attn_bwd B{B} H{H} S{S} p{pdrop}", lambda: ops.attention_bwd(qkv, kb, out, dout, lse, B, H, S, p_drop=pdrop, seed=1),
+                   flops=2.5 * fl, bytes_=2 * qkv.numel() * 2 + 2 * out.numel() * 2)
+if "ln" in which:
+    for (M, D) in [(32768, 768), (50432, 768), (16384, 1024)]:
+        x = torch.randn(M, D, device=dev).to(bf); g = torch.ones(D, device=dev); b = torch.zeros(D, device=dev)
+        y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-12)
+        dy = torch.randn_like(x); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
+        timeit(f"ln_fwd [{M},{D}]", lambda: ops.layernorm_fwd(x, g, b, 1e-12), bytes_=2 * M * D * 2)
+        timeit(f"ln_bwd [{M},{D}]", lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db), bytes_=3 * M * D * 2)
+        timeit(f"ln_bwd [{M},{D}] +addend", lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, dg, db, addend=dy), bytes_=4 * M * D * 2)
+        timeit(f"colsum [{M},{D}]", lambda: ops.colsum(dy, db), bytes_=M * D * 2)

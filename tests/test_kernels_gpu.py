@@ -568,3 +568,80 @@ def test_vit_assemble_fwd_bwd(ops, cuda_device):
     dxf = dx.float().view(B, P + 1, D)
     assert torch.equal(dpatch.view(B, P, D), dx.view(B, P + 1, D)[:, 1:])
     assert rel(dpos, dxf.sum(0)) < 1e-5 and rel(dcls, dxf[:, 0].sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------ HEAD-script head kernels
+@pytest.mark.parametrize("B,C", [(16, 512), (37, 1536), (8, 8)])
+def test_bn1d_fwd_bwd(ops, cuda_device, B, C):
+    torch.manual_seed(31)
+    dev = cuda_device
+    x = (torch.randn(B, C, device=dev) * 1.5 + 0.3).to(bf16)
+    g = torch.rand(C, device=dev) + 0.5
+    b = torch.randn(C, device=dev) * 0.3
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    out, mean, rstd = ops.bn1d_fwd(x, g, b, rm, rv, relu=True, train=True)
+    xf = x.float().requires_grad_(True)
+    gf, bf_ = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    ref = torch.relu(F.batch_norm(xf, rm2, rv2, gf, bf_, True, 0.1, 1e-5))
+    assert rel(out, ref) < 1e-2 and rel(rm, rm2) < 1e-4 and rel(rv, rv2) < 1e-4
+    dout = torch.randn(B, C, device=dev).to(bf16)
+    ref.backward(dout.float())
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    dx = ops.bn1d_bwd(dout, out, x, mean, rstd, g, dg, db, relu=True)
+    assert rel(dx, xf.grad) < 3e-2 and rel(dg, gf.grad) < 2e-2 and rel(db, bf_.grad) < 2e-2
+    ev, _, _ = ops.bn1d_fwd(x, g, b, rm2, rv2, relu=True, train=False)
+    assert rel(ev, torch.relu(F.batch_norm(x.float(), rm2, rv2, g, b, False, 0.1, 1e-5))) < 1e-2
+
+
+def test_softmax_gate_and_relu_bwd(ops, cuda_device):
+    torch.manual_seed(32)
+    dev = cuda_device
+    B, C = 19, 1536
+    a = torch.relu(torch.randn(B, C, device=dev)).to(bf16)
+    x = torch.randn(B, C, device=dev).to(bf16)
+    y, w = ops.softmax_gate_fwd(a, x)
+    af, xf = a.float().requires_grad_(True), x.float().requires_grad_(True)
+    ref = torch.softmax(af, 1) * xf
+    assert rel(y, ref) < 1e-2 and rel(w, torch.softmax(a.float(), 1)) < 1e-4
+    dy = torch.randn(B, C, device=dev).to(bf16)
+    ref.backward(dy.float())
+    da, dxd = ops.softmax_gate_bwd(dy, w, x)
+    assert rel(da, af.grad) < 2e-2 and rel(dxd, xf.grad) < 1e-2
+    yv = torch.randn(B, C, device=dev).to(bf16)
+    assert torch.equal(ops.relu_bwd(dy, yv), torch.where(yv.float() > 0, dy, torch.zeros_like(dy)))
+
+
+@pytest.mark.parametrize("B", [16, 300])
+def test_head_bn_focal(ops, cuda_device, B):
+    """Linear(512,1) + BatchNorm1d(1) + sigmoid_focal_loss, fused, against torch / torchvision."""
+    from torchvision.ops import sigmoid_focal_loss
+    torch.manual_seed(33)
+    dev = cuda_device
+    Fdim = 512
+    feat = torch.randn(B, Fdim, device=dev).to(bf16)
+    W = (torch.randn(1, Fdim, device=dev) / Fdim ** 0.5)
+    bias = torch.randn(1, device=dev)
+    g, be = torch.tensor([1.3], device=dev), torch.tensor([-0.2], device=dev)
+    rm, rv = torch.zeros(1, device=dev), torch.ones(1, device=dev)
+    labels = (torch.rand(B, device=dev) < 0.3).long()
+    dW, dbias, dg, dbe = (torch.zeros(1, Fdim, device=dev), torch.zeros(1, device=dev), torch.zeros(1, device=dev),
+                          torch.zeros(1, device=dev))
+    logits, loss, correct, dfeat = ops.head_bn_focal(feat, W, bias, g, be, rm, rv, labels, train=True, bn_train=True,
+                                                     dW=dW, dbias=dbias, dg=dg, dbeta=dbe)
+    ff = feat.float().requires_grad_(True)
+    Wf, bf_, gf, bef = (t.clone().requires_grad_(True) for t in (W, bias, g, be))
+    rm2, rv2 = torch.zeros(1, device=dev), torch.ones(1, device=dev)
+    z = ff @ Wf.t() + bf_
+    yref = F.batch_norm(z, rm2, rv2, gf, bef, True, 0.1, 1e-5).squeeze(1)
+    lref = sigmoid_focal_loss(yref, labels.float(), alpha=0.25, gamma=2.0, reduction="mean")
+    lref.backward()
+    assert rel(logits, yref) < 1e-4 and abs(loss.item() - lref.item()) / lref.item() < 1e-4
+    assert correct.item() == ((torch.sigmoid(yref) > 0.5) == (labels != 0)).sum().item()
+    assert rel(dfeat, ff.grad) < 1e-2 and rel(dW, Wf.grad) < 1e-3 and rel(dg, gf.grad) < 1e-3
+    assert abs(dbe.item() - bef.grad.item()) < 1e-5 + 1e-3 * abs(bef.grad.item())
+    assert rel(rm, rm2) < 1e-5 and rel(rv, rv2) < 1e-5
+    # eval statistics, no backward
+    lg2, loss2, _, _ = ops.head_bn_focal(feat, W, bias, g, be, rm2, rv2, labels, train=False, bn_train=False)
+    y2 = F.batch_norm(feat.float() @ W.t() + bias, rm2, rv2, g, be, False, 0.1, 1e-5).squeeze(1)
+    assert rel(lg2, y2) < 1e-4

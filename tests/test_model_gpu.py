@@ -468,3 +468,118 @@ def test_vit_text_variants_backward_and_trajectory(cuda_device, text_arch):
         _, l, _ = eng.train_step_fused(d["text"], d["image"], d["text_mask"], d["label"])
         opt.step()
         assert abs(l.item() - l_ref.item()) / l_ref.item() < 2e-2
+
+
+# ------------------------------------------------------------------ HEAD script's three-tower model
+def _pair_head(cuda_device, batch=16, seq=24, seed=11):
+    import b200mm
+    from oracle import reference_model as R
+    tc, cc = R.TowerConfig.tiny_vit_bert("bert"), R.TowerConfig.tiny_vit_bert("roberta")
+    torch.manual_seed(seed)
+    oracle = R.zero_dropout(R.MultimodalClassifierHEAD(tc, cc, (1, 1, 1, 1)))
+    with torch.no_grad():
+        for n, p in oracle.named_parameters():
+            if n.endswith(".bias") or "LayerNorm.weight" in n:
+                p.add_(0.1 * torch.randn_like(p))
+
+    def tcfg(c, arch):
+        return b200mm.TextConfig(vocab_size=c.vocab_size, max_position_embeddings=c.max_position_embeddings, dim=c.dim,
+                                 n_layers=c.n_layers, n_heads=c.n_heads, hidden_dim=c.hidden_dim, dropout=0.0,
+                                 attention_dropout=0.0, layer_norm_eps=c.layer_norm_eps, pad_token_id=c.pad_token_id,
+                                 arch=arch, type_vocab_size=c.type_vocab_size)
+    eng = b200mm.MultimodalClassifierHEAD("concatenation", text_config=tcfg(tc, "bert"),
+                                          caption_config=tcfg(cc, "roberta"),
+                                          image_config=b200mm.ImageConfig(layers=(1, 1, 1, 1), block="basic",
+                                                                          num_outputs=0),
+                                          device=cuda_device, text_dropout=0.0, image_dropout=0.0)
+    eng.load_reference_state_dict(oracle.state_dict())
+    d1, d2 = R.synthetic_batch(batch, seq, tc), R.synthetic_batch(batch, seq, cc, seed=77)
+    data = {"text": d1["text"], "text_mask": d1["text_mask"], "image": d1["image"], "label": d1["label"],
+            "caption_text": d2["text"], "caption_text_mask": d2["text_mask"]}
+    return oracle, eng, data
+
+
+def test_head_three_tower_model_matches_oracle(cuda_device):
+    from torchvision.ops import sigmoid_focal_loss
+    import b200mm
+    with pytest.raises(ValueError):
+        b200mm.MultimodalClassifierHEAD("mca", device=cuda_device)
+    oracle, eng, data = _pair_head(cuda_device)
+    d = _dev(data, cuda_device)
+    args = ("text", "image", "text_mask", "caption_text", "caption_text_mask")
+    oracle.train()
+    eng.train()
+    ref = oracle(*[data[k] for k in args])
+    loss_ref = sigmoid_focal_loss(ref, data["label"].float(), alpha=0.25, gamma=2.0, reduction="mean")
+    oracle.zero_grad()
+    loss_ref.backward()
+    eng.zero_grad()
+    logits, loss, _ = eng.train_step_fused(*[d[k] for k in args], d["label"])
+    assert logits.shape == ref.shape and rel(logits, ref.detach()) < 3e-2
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 2e-2
+    grads = eng.reference_grad_dict()
+    bad = {}
+    for n, p in oracle.named_parameters():
+        if p.grad is None:
+            continue
+        # a bias directly in front of a train-mode BatchNorm (text_fc.0.bias, the towers' last LayerNorm bias, ...)
+        # has an exactly-zero gradient in theory: what autograd returns there is rounding noise -- skip by magnitude
+        scale = oracle.get_parameter(n.rsplit(".", 1)[0] + ".weight").grad.abs().max().item() if n.endswith(".bias") \
+            and not n.endswith("LayerNorm.bias") else None
+        if p.grad.abs().max().item() < 1e-7 or (scale is not None and p.grad.abs().max().item() < 1e-3 * scale):
+            continue
+        g = grads[n].cpu().view(p.grad.shape)
+        tol_cos = 0.9 if n.startswith("image_model.image_model") else 0.98    # ReLU-mask flips behind bf16 rounding
+        if _cos(g, p.grad) < tol_cos:
+            bad[n] = (_cos(g, p.grad), p.grad.abs().max().item(), g.abs().max().item())
+    assert not bad, bad
+    # param groups of the reference (:645-664): the caption tower lands in the 0.8 x lr "text_model" group
+    groups = eng.get_params(1e-5)
+    names = {id(p): n for n, p in eng.named_parameters()}
+    assert any(names[id(p)].startswith("caption_text_model.") for p in groups[1]["params"])
+    assert all("fusion_layer" in names[id(p)] or names[id(p)].split(".")[0] in ("text_fc", "caption_text_fc",
+               "output_fc") for p in groups[0]["params"])
+    # eval mode (running statistics everywhere) after both sides took the same train-mode pass
+    oracle.eval()
+    eng.eval()
+    ref_e = oracle(*[data[k] for k in args]).detach()
+    got_e = eng(*[d[k] for k in args])
+    assert rel(got_e, ref_e) < 3e-2
+
+
+def test_head_three_tower_loop_api(cuda_device, tmp_path):
+    """train / test / evaluate of the HEAD script (:689-879) driving the three-tower model end to end."""
+    import b200mm
+    from b200mm import loop_head, tsv
+    _, eng, data = _pair_head(cuda_device, batch=32)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 32
+
+        def __getitem__(self, i):
+            out = {k: v[i] for k, v in data.items()}
+            out["id"] = f"data/x/img_{i}.jpg"
+            return out
+
+    loader = torch.utils.data.DataLoader(DS(), batch_size=8)
+    crit = b200mm.SigmoidFocalLoss(alpha=0.25, gamma=2.0)
+    opt = b200mm.FusedAdam(loop_head.get_params(eng, 1e-5), lr=1e-5, max_grad_norm=10.0)
+    assert [g["lr"] for g in opt.param_groups] == pytest.approx([1e-5, 0.8e-5, 0.8e-5])
+    sched = b200mm.get_linear_schedule_with_warmup(opt, 1, 2 * len(loader))
+    lines, state = [], {}
+    for epoch in range(2):
+        loss, acc = loop_head.train(eng, loader, crit, opt, sched, cuda_device, epoch, test_loader=loader, state=state,
+                                    evaluate_kwargs={"fold": 1, "out_dir": str(tmp_path)}, log=lines.append)
+        assert loss > 0 and 0 <= acc <= 1
+    t_loss, t_acc, t_f1, thr = loop_head.test(eng, loader, crit, cuda_device, 1, log=lines.append)
+    assert 0 <= t_f1 <= 1
+    ids, labels, probs, _ = tsv.read_prob_tsv(str(tmp_path / "task2C_kevinmathew_probs_fold_1.tsv"))
+    assert len(ids) == 32 and all(0.0 <= p <= 1.0 for p in probs)
+    # generic path: torch criterion + loss.backward() through the autograd node
+    eng.train()
+    eng.zero_grad()
+    d = _dev(data, cuda_device)
+    out = eng(d["text"][:8], d["image"][:8], d["text_mask"][:8], d["caption_text"][:8], d["caption_text_mask"][:8])
+    crit(out, d["label"][:8]).backward()
+    assert torch.isfinite(eng.store.grad).all() and eng.store.grad.abs().sum() > 0
