@@ -41,8 +41,8 @@ __device__ __forceinline__ void drop_scale8(const DropSpec& d, long long idx, fl
 // y = LN(x) * gamma + beta, optional dropout on y.  Stats saved for the backward.
 // EMBED: x is not read from memory but formed as word[ids[row]] + pos[row % S] (fp32 tables) and also
 // written out (bf16) as the saved LayerNorm input.
-template <bool EMBED>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+template <bool EMBED, int NC>
+__global__ void __launch_bounds__(LN_WARPS * 32, NC <= 2 ? 6 : (NC <= 4 ? 4 : 2))
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ ids,
                      const float* __restrict__ word, const float* __restrict__ pos, const int* __restrict__ pos_ids,
                      const float* __restrict__ type_row, int S, int vocab,
@@ -53,7 +53,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp;
   if (row >= M) return;
   const int chunks = D >> 3;
-  float v[LN_MAX_CHUNKS][8];
+  float v[NC][8];   // registers (and with them the rows in flight per SM) scale with D
   float sum = 0.f;
   const float* wrow = nullptr;
   const float* prow = nullptr;
@@ -65,7 +65,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
     prow = pos + static_cast<long long>(pos_ids != nullptr ? pos_ids[row] : row % S) * D;
   }
 #pragma unroll
-  for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
+  for (int j = 0; j < NC; ++j) {
     const int c = lane + j * 32;
     if (c < chunks) {
       if constexpr (EMBED) {
@@ -94,7 +94,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
   const float mean = warp_sum(sum) / D;
   float sq = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
+  for (int j = 0; j < NC; ++j) {
     const int c = lane + j * 32;
     if (c < chunks) {
 #pragma unroll
@@ -110,7 +110,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
     rstd_out[row] = rstd;
   }
 #pragma unroll
-  for (int j = 0; j < LN_MAX_CHUNKS; ++j) {
+  for (int j = 0; j < NC; ++j) {
     const int c = lane + j * 32;
     if (c < chunks) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8));
@@ -155,8 +155,25 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 
   const long long row_begin = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long row_end = min(row_begin + rows_per_cta, static_cast<long long>(M));
+  // software pipeline: the next row's dy / x are in flight while this row's two warp reductions run
+  uint4 nd[NC], nx[NC];
+  auto fetch = [&](long long r) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = lane + j * 32;
+      if (c < chunks) {
+        nd[j] = __ldg(reinterpret_cast<const uint4*>(dy + r * D + c * 8));
+        nx[j] = __ldg(reinterpret_cast<const uint4*>(x + r * D + c * 8));
+      }
+    }
+  };
+  if (row_begin + warp < row_end) fetch(row_begin + warp);
   for (long long row = row_begin + warp; row < row_end; row += LN_WARPS) {
     const float mean = mean_in[row], rstd = rstd_in[row];
+    uint4 cd[NC], cx[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) { cd[j] = nd[j]; cx[j] = nx[j]; }
+    if (row + LN_WARPS < row_end) fetch(row + LN_WARPS);
     float g_dy[NC][8], xh[NC][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -164,8 +181,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       const int c = lane + j * 32;
       if (c < chunks) {
         float d[8], xv[8];
-        load8(dy + row * D + c * 8, d);
-        load8(x + row * D + c * 8, xv);
+        unpack8(cd[j], d);
+        unpack8(cx[j], xv);
         if (in_drop.p > 0.f) {
           float s[8];
           drop_scale8(in_drop, row * D + c * 8, s);
@@ -371,9 +388,17 @@ B200MM_API int b200mm_layernorm_fwd(const void* x, const float* gamma, const flo
                                     float* rstd, int M, int D, float eps, float p_drop, unsigned long long seed,
                                     void* stream) {
   if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
-  layernorm_fwd_kernel<false><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, nullptr, 1, 1, nullptr, gamma, beta,
-      static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed));
+#define LAUNCH_LN_FWD(NC)                                                                                           \
+  layernorm_fwd_kernel<false, NC><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(  \
+      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, nullptr, 1, 1, nullptr, gamma, beta, \
+      static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed))
+  const int nc = ceil_div(D, 256);
+  if (nc <= 1) LAUNCH_LN_FWD(1);
+  else if (nc == 2) LAUNCH_LN_FWD(2);
+  else if (nc == 3) LAUNCH_LN_FWD(3);
+  else if (nc == 4) LAUNCH_LN_FWD(4);
+  else LAUNCH_LN_FWD(8);
+#undef LAUNCH_LN_FWD
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -386,9 +411,17 @@ B200MM_API int b200mm_embed_layernorm_fwd(const long long* ids, const float* wor
                                           float* rstd, int M, int D, float eps, float p_drop, unsigned long long seed,
                                           void* stream) {
   if (!ln_shape_ok(M, D) || S <= 0 || vocab <= 0) return B200MM_ERR_BAD_ARG;
-  layernorm_fwd_kernel<true><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, ids, word, pos, pos_ids, type_row, S, vocab, static_cast<__nv_bfloat16*>(x_saved), gamma, beta,
-      static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed));
+#define LAUNCH_LN_EMB(NC)                                                                                          \
+  layernorm_fwd_kernel<true, NC><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(  \
+      nullptr, ids, word, pos, pos_ids, type_row, S, vocab, static_cast<__nv_bfloat16*>(x_saved), gamma, beta,     \
+      static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed))
+  const int nc = ceil_div(D, 256);
+  if (nc <= 1) LAUNCH_LN_EMB(1);
+  else if (nc == 2) LAUNCH_LN_EMB(2);
+  else if (nc == 3) LAUNCH_LN_EMB(3);
+  else if (nc == 4) LAUNCH_LN_EMB(4);
+  else LAUNCH_LN_EMB(8);
+#undef LAUNCH_LN_EMB
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
