@@ -107,14 +107,16 @@ int b200mm_batchnorm_fwd(const void* x, const void* residual, long long M, int C
 int b200mm_batchnorm_fwd_stats(const void* x, const void* residual, long long M, int C, const float* col_stats,
                                const float* gamma, const float* beta, float eps, float momentum, int relu, void* out,
                                float* mean_out, float* rstd_out, float* running_mean, float* running_var,
-                               void* stream);
+                               unsigned char* relu_mask, void* stream);
+/* relu_mask (nullable, [M, C/8] bytes): 1 bit per element = (pre-ReLU value > 0), all the backward needs of the output */
 int b200mm_batchnorm_eval(const void* x, const void* residual, long long M, int C, const float* gamma,
                           const float* beta, const float* running_mean, const float* running_var, float eps, int relu,
                           void* out, void* stream);
-/* relu != 0 with out == NULL: the ReLU mask is recomputed from x (needs beta; only valid without a residual) */
+/* ReLU mask source, in order of preference: relu_mask (1 bit / element from b200mm_batchnorm_fwd_stats), the saved
+ * output `out`, or -- both NULL -- recomputed from x (needs beta; only valid without a residual). */
 int b200mm_batchnorm_bwd(const void* dout, const void* out, const void* x, long long M, int C, const float* mean,
-                         const float* rstd, const float* gamma, const float* beta, int relu, void* dx, void* dz_out,
-                         float* dgamma, float* dbeta, float* scratch, void* stream);
+                         const float* rstd, const float* gamma, const float* beta, const unsigned char* relu_mask,
+                         int relu, void* dx, void* dz_out, float* dgamma, float* dbeta, float* scratch, void* stream);
 int b200mm_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, void* argmax, void* stream);
 int b200mm_maxpool3x3s2_bwd(const void* dout, const void* argmax, int N, int H, int W, int C, void* dx, void* stream);
 int b200mm_avgpool_fwd(const void* x, int N, int HW, int C, void* out, void* stream);

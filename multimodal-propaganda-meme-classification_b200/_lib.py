@@ -124,11 +124,11 @@ declare("b200mm_scatter_rows", [c_ptr, c_ptr, c_longlong, c_int, c_longlong, c_l
 declare("b200mm_batchnorm_fwd", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_float, c_float, c_int, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_batchnorm_fwd_stats", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_float, c_float, c_int,
-                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_batchnorm_eval", [c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_float, c_int,
                                   c_ptr, c_ptr])
-declare("b200mm_batchnorm_bwd", [c_ptr, c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
-                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_batchnorm_bwd", [c_ptr, c_ptr, c_ptr, c_longlong, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
+                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_maxpool3x3s2_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr])
 declare("b200mm_maxpool3x3s2_bwd", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_avgpool_fwd", [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr])

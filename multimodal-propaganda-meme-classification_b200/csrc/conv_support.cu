@@ -104,7 +104,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
                 int rows_per_cta, const float* __restrict__ sum, const float* __restrict__ sumsq,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum, int relu,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                float* __restrict__ running_mean, float* __restrict__ running_var) {
+                float* __restrict__ running_mean, float* __restrict__ running_var,
+                unsigned char* __restrict__ relu_mask) {
   const int G = C >> 3;
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
   float sc[8], sh[8];
@@ -149,6 +150,12 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]) + rv[i];
       if (relu) {
+        if (relu_mask != nullptr) {   // 1 bit per element: what the backward needs of a residual BatchNorm's output
+          unsigned int m = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m |= (v[i] > 0.f ? 1u : 0u) << i;
+          relu_mask[row * G + g] = static_cast<unsigned char>(m);
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
       }
@@ -204,9 +211,10 @@ bn_eval_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 }
 
 // backward pass 1: dbeta = sum dz, dgamma = sum dz * xhat, dz = dout o (out > 0) when relu
-template <bool HAS_OUT>
+template <int MASK_SRC>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                     const unsigned char* __restrict__ relu_mask,
                      const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scratch) {
@@ -215,7 +223,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
   // out == nullptr with relu: the mask is recomputed from x with the forward's own fma (saves one full read of the
   // activation; only possible when no residual entered the ReLU)
-  const bool recompute = relu && !HAS_OUT;
+  constexpr bool HAS_OUT = MASK_SRC == 1;
+  const bool recompute = relu && MASK_SRC == 0;
   float mu[8], rs[8], sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -232,6 +241,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
   constexpr int U = HAS_OUT ? 4 : 6;
   for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
     uint4 rd[U], rx[U], ro[U];
+    unsigned int rm[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + static_cast<long long>(u) * rpp;
@@ -241,13 +251,17 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
       rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
       if constexpr (HAS_OUT)
         ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
+      if constexpr (MASK_SRC == 2) rm[u] = ok ? __ldg(relu_mask + rr * G + g) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float d[8], xv[8];
       unpack8(rd[u], d);
       unpack8(rx[u], xv);
-      if (recompute) {
+      if constexpr (MASK_SRC == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = (rm[u] >> i) & 1u ? d[i] : 0.f;
+      } else if (recompute) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = fmaf(xv[i], sc[i], sh[i]) > 0.f ? d[i] : 0.f;
       } else if (HAS_OUT && relu) {
@@ -268,9 +282,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
 
 // backward pass 2: dx = gamma * rstd * (dz - dbeta/M - xhat * dgamma/M); optional dz copy for the identity branch;
 // CTA 0 accumulates the parameter gradients.
-template <bool HAS_OUT>
-__global__ void __launch_bounds__(256, HAS_OUT ? 3 : 2)
+template <int MASK_SRC>
+__global__ void __launch_bounds__(256, MASK_SRC == 1 ? 3 : 2)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                    const unsigned char* __restrict__ relu_mask,
                     const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, int relu, const float* __restrict__ dgamma_sum,
@@ -281,7 +296,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
   float mu[8], rs[8], k0[8], k1[8], k2[8], sh[8];
   const float invM = 1.f / static_cast<float>(M);
-  const bool recompute = relu && !HAS_OUT;
+  constexpr bool HAS_OUT = MASK_SRC == 1;
+  const bool recompute = relu && MASK_SRC == 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = g * 8 + i;
@@ -299,9 +315,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
-  constexpr int U = HAS_OUT ? 2 : 6;   // 3 CTAs x 2 x 3 streams, or 2 CTAs x 6 x 2 streams of 16-byte loads in flight
+  constexpr int U = HAS_OUT ? 2 : (MASK_SRC == 2 ? 4 : 6);   // 16-byte loads in flight: 3 CTAs x 2 x 3 streams, or 2 CTAs x 4..6 x 2
   for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
     uint4 rd[U], rx[U], ro[U];
+    unsigned int rm[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + static_cast<long long>(u) * rpp;
@@ -311,6 +328,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
       rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
       if constexpr (HAS_OUT)
         ro[u] = (ok && relu) ? __ldg(reinterpret_cast<const uint4*>(out + off)) : make_uint4(0, 0, 0, 0);
+      if constexpr (MASK_SRC == 2) rm[u] = ok ? __ldg(relu_mask + rr * G + g) : 0u;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -319,7 +337,10 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
       float d[8], xv[8];
       unpack8(rd[u], d);
       unpack8(rx[u], xv);
-      if (recompute) {
+      if constexpr (MASK_SRC == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = (rm[u] >> i) & 1u ? d[i] : 0.f;
+      } else if (recompute) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = fmaf(xv[i], k0[i], sh[i]) > 0.f ? d[i] : 0.f;
       } else if (HAS_OUT && relu) {
@@ -691,7 +712,7 @@ B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long lo
   bn_apply_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
                                        static_cast<const __nv_bfloat16*>(residual), M, C, rows, fin, fin + C,
                                        gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out,
-                                       rstd_out, running_mean, running_var);
+                                       rstd_out, running_mean, running_var, nullptr);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -701,14 +722,15 @@ B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long lo
 B200MM_API int b200mm_batchnorm_fwd_stats(const void* x, const void* residual, long long M, int C,
                                           const float* col_stats, const float* gamma, const float* beta, float eps,
                                           float momentum, int relu, void* out, float* mean_out, float* rstd_out,
-                                          float* running_mean, float* running_var, void* stream) {
+                                          float* running_mean, float* running_var, unsigned char* relu_mask,
+                                          void* stream) {
   if (!bn_shape_ok(M, C) || col_stats == nullptr) return B200MM_ERR_BAD_ARG;
   int grid;
   const int rows = bn_rows_per_cta(M, C, &grid);
   bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, col_stats,
       col_stats + C, gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out, rstd_out,
-      running_mean, running_var);
+      running_mean, running_var, relu_mask);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -732,9 +754,10 @@ B200MM_API int b200mm_batchnorm_eval(const void* x, const void* residual, long l
 // ReLU mask is recomputed from x, mean, rstd, gamma and beta (valid only if no residual was added before the ReLU).
 B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const void* x, long long M, int C,
                                     const float* mean, const float* rstd, const float* gamma, const float* beta,
-                                    int relu, void* dx, void* dz_out, float* dgamma, float* dbeta, float* scratch,
-                                    void* stream) {
-  if (!bn_shape_ok(M, C) || (relu && out == nullptr && beta == nullptr)) return B200MM_ERR_BAD_ARG;
+                                    const unsigned char* relu_mask, int relu, void* dx, void* dz_out, float* dgamma,
+                                    float* dbeta, float* scratch, void* stream) {
+  if (!bn_shape_ok(M, C) || (relu && out == nullptr && beta == nullptr && relu_mask == nullptr))
+    return B200MM_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * bn_scratch_floats(C), s);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -745,20 +768,21 @@ B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const voi
   const __nv_bfloat16* dout_ = static_cast<const __nv_bfloat16*>(dout);
   const __nv_bfloat16* out_ = static_cast<const __nv_bfloat16*>(out);
   const __nv_bfloat16* x_ = static_cast<const __nv_bfloat16*>(x);
-  if (out != nullptr)
-    bn_bwd_reduce_kernel<true><<<rgrid, 256, 0, s>>>(dout_, out_, x_, M, C, rrows, mean, rstd, relu, gamma, beta, scratch);
-  else
-    bn_bwd_reduce_kernel<false><<<rgrid, 256, 0, s>>>(dout_, out_, x_, M, C, rrows, mean, rstd, relu, gamma, beta, scratch);
-  B200MM_CHECK_LAUNCH();
-  if (out != nullptr)
-    bn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(dout_, out_, x_, M, C, rows, mean, rstd, gamma, beta, relu, fin,
-                                                   fin + C, static_cast<__nv_bfloat16*>(dx),
-                                                   static_cast<__nv_bfloat16*>(dz_out), dgamma, dbeta);
-  else
-    bn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(dout_, out_, x_, M, C, rows, mean, rstd, gamma, beta, relu, fin,
-                                                    fin + C, static_cast<__nv_bfloat16*>(dx),
-                                                    static_cast<__nv_bfloat16*>(dz_out), dgamma, dbeta);
-  B200MM_CHECK_LAUNCH();
+  __nv_bfloat16* dx_ = static_cast<__nv_bfloat16*>(dx);
+  __nv_bfloat16* dz_ = static_cast<__nv_bfloat16*>(dz_out);
+#define BN_BWD(SRC)                                                                                                 \
+  do {                                                                                                              \
+    bn_bwd_reduce_kernel<SRC><<<rgrid, 256, 0, s>>>(dout_, out_, relu_mask, x_, M, C, rrows, mean, rstd, relu, gamma, \
+                                                    beta, scratch);                                                 \
+    B200MM_CHECK_LAUNCH();                                                                                          \
+    bn_bwd_apply_kernel<SRC><<<grid, 256, 0, s>>>(dout_, out_, relu_mask, x_, M, C, rows, mean, rstd, gamma, beta,   \
+                                                  relu, fin, fin + C, dx_, dz_, dgamma, dbeta);                     \
+    B200MM_CHECK_LAUNCH();                                                                                          \
+  } while (0)
+  if (relu && relu_mask != nullptr) BN_BWD(2);
+  else if (relu && out != nullptr) BN_BWD(1);
+  else BN_BWD(0);
+#undef BN_BWD
   return B200MM_OK;
 }
 

@@ -188,12 +188,15 @@ class ImageTower:
     def _stats_of(self, c):
         return None if self._stats is None else self._stats[c.stats_off:c.stats_off + 2 * c.cout]
 
-    def _bn(self, c, x, training, residual=None, relu=True):
+    def _bn(self, c, x, training, residual=None, relu=True, want_mask=False):
+        """want_mask: also return the 1-bit ReLU mask (4th value) -- what the backward of a residual BatchNorm reads
+        instead of the full output tensor."""
         cfg = self.cfg
         if training:
             return ops.batchnorm_fwd(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps,
-                                     momentum=cfg.bn_momentum, col_stats=self._stats_of(c))
-        return ops.batchnorm_eval(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps), None, None
+                                     momentum=cfg.bn_momentum, col_stats=self._stats_of(c), want_mask=want_mask)
+        out = ops.batchnorm_eval(x, c.g, c.b, c.rm, c.rv, residual=residual, relu=relu, eps=cfg.bn_eps)
+        return (out, None, None, None) if want_mask else (out, None, None)
 
     # ------------------------------------------------------------------ forward
     def forward(self, image: torch.Tensor, *, training: bool, seed: int = 0, step: int = 0):
@@ -224,9 +227,9 @@ class ImageTower:
                     idn, md, rd = self._bn(ds, yd, training, relu=False)
                 else:
                     idn = x
-                out, m2, r2 = self._bn(c2, y2, training, residual=idn, relu=True)
+                out, m2, r2, msk = self._bn(c2, y2, training, residual=idn, relu=True, want_mask=True)
                 if training:
-                    sv["blocks"].append((x, y1, a1, m1, r1, y2, m2, r2, xs, yd, md, rd, out, Hc, Wc, Ho, Wo))
+                    sv["blocks"].append((x, y1, a1, m1, r1, y2, m2, r2, xs, yd, md, rd, msk, Hc, Wc, Ho, Wo))
                 x, Hc, Wc = out, Ho, Wo
                 if self.capture is not None:
                     self.capture.append((x, N, Hc, Wc))
@@ -244,9 +247,9 @@ class ImageTower:
                 idn, md, rd = self._bn(ds, yd, training, relu=False)
             else:
                 idn = x
-            out, m3, r3 = self._bn(c3, y3, training, residual=idn, relu=True)
+            out, m3, r3, msk = self._bn(c3, y3, training, residual=idn, relu=True, want_mask=True)
             if training:
-                sv["blocks"].append((x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hc, Wc,
+                sv["blocks"].append((x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, msk, Hc, Wc,
                                      Ho, Wo))
             x, Hc, Wc = out, Ho, Wo
             if self.capture is not None:
@@ -276,9 +279,10 @@ class ImageTower:
         for blk, s in zip(reversed(self.blocks), reversed(sv["blocks"])):
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
             if self.basic:
-                x, y1, a1, m1, r1, y2, m2, r2, xs, yd, md, rd, out, Hi, Wi, Ho, Wo = s
+                x, y1, a1, m1, r1, y2, m2, r2, xs, yd, md, rd, msk, Hi, Wi, Ho, Wo = s
                 # out = relu(bn2(y2) + idn)
-                d_y2, dz = ops.batchnorm_bwd(d_out, out, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, need_dz=True)
+                d_y2, dz = ops.batchnorm_bwd(d_out, None, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, need_dz=True,
+                                             mask=msk)
                 ops.conv_wgrad(d_y2, a1, N, Ho, Wo, c2.cin, 3, 1, 1, c2.dw)
                 d_a1, _, _ = ops.conv_fwd(d_y2, N, Ho, Wo, c2.cout, ops.conv_weight_rotate(c2.w, c2.cout, c2.cin, 3),
                                           3, 1, 1)
@@ -301,9 +305,10 @@ class ImageTower:
                         d_x1 = ops.col2im(d_cols, N, Hi, Wi, c1.cin, 3, stride, 1)
                         d_out = ops.upsample_add(d_xs, d_x1, N, Hi, Wi, ds.cin, stride)
                 continue
-            x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, out, Hi, Wi, Ho, Wo = s
+            x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, msk, Hi, Wi, Ho, Wo = s
             # out = relu(bn3(y3) + idn)
-            d_y3, dz = ops.batchnorm_bwd(d_out, out, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, need_dz=True)
+            d_y3, dz = ops.batchnorm_bwd(d_out, None, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, need_dz=True,
+                                         mask=msk)
             ops.linear_wgrad(d_y3, a2, c3.dw)
             d_a2 = ops.linear_dgrad(d_y3, c3.w)
             d_y2, _ = ops.batchnorm_bwd(d_a2, None, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, beta=c2.b)

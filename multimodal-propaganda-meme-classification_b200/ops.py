@@ -428,7 +428,7 @@ class BNScratch:
 
 
 def batchnorm_fwd(x, gamma, beta, running_mean, running_var, *, residual=None, relu=True, eps=1e-5, momentum=0.1,
-                  col_stats=None):
+                  col_stats=None, want_mask=False):
     """Train-mode BatchNorm.  col_stats (fp32 [2C] = sums | sums of squares, from the producing convolution's
     epilogue): skip the statistics pass."""
     M, C = x.shape
@@ -436,10 +436,12 @@ def batchnorm_fwd(x, gamma, beta, running_mean, running_var, *, residual=None, r
     mean = torch.empty(C, device=x.device, dtype=f32)
     rstd = torch.empty(C, device=x.device, dtype=f32)
     if col_stats is not None:
+        # want_mask: also emit the 1-bit ReLU mask [M, C/8] (returned as a 4th value) for the backward
+        mask = torch.empty(M, C // 8, device=x.device, dtype=torch.uint8) if (want_mask and relu) else None
         _lib.call("b200mm_batchnorm_fwd_stats", _p(x), _p(residual), M, C, _p(col_stats), _p(gamma), _p(beta),
                   float(eps), float(momentum), int(relu), _p(out), _p(mean), _p(rstd), _p(running_mean),
-                  _p(running_var), _s())
-        return out, mean, rstd
+                  _p(running_var), _p(mask), _s())
+        return (out, mean, rstd, mask) if want_mask else (out, mean, rstd)
     _lib.call("b200mm_batchnorm_fwd", _p(x), _p(residual), M, C, _p(gamma), _p(beta), float(eps), float(momentum),
               int(relu), _p(out), _p(mean), _p(rstd), _p(running_mean), _p(running_var),
               _p(BNScratch.get(x.device, C)), _s())
@@ -454,13 +456,14 @@ def batchnorm_eval(x, gamma, beta, running_mean, running_var, *, residual=None, 
     return out
 
 
-def batchnorm_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=True, need_dz=False, beta=None):
-    """out=None with relu: the ReLU mask is recomputed from x (pass beta; only valid without a residual)."""
+def batchnorm_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=True, need_dz=False, beta=None, mask=None):
+    """ReLU mask: ``mask`` (1 bit / element, from batchnorm_fwd(want_mask=True)), else ``out``, else recomputed from x
+    (pass beta; only valid without a residual)."""
     M, C = x.shape
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if need_dz else None
     _lib.call("b200mm_batchnorm_bwd", _p(dout), _p(out), _p(x), M, C, _p(mean), _p(rstd), _p(gamma), _p(beta),
-              int(relu),
+              _p(mask), int(relu),
               _p(dx), _p(dz), _p(dgamma), _p(dbeta), _p(BNScratch.get(x.device, C)), _s())
     return dx, dz
 

@@ -245,6 +245,20 @@ def test_batchnorm_fwd_bwd(ops, cuda_device, M, C, relu, use_res):
         dg2, db2 = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
         dx2, _ = ops.batchnorm_bwd(dout, None, x, mean, rstd, g, dg2, db2, relu=True, beta=b)
         assert rel(dg2, dg) < 1e-5 and rel(db2, db) < 1e-5 and rel(dx2, dx) < 1e-3
+    if relu:
+        # 1-bit ReLU mask written by the statistics-fed forward, read by the backward instead of the output tensor
+        st = torch.zeros(2 * C, device=cuda_device)
+        st[:C], st[C:] = x.float().sum(0), (x.float() ** 2).sum(0)
+        rm3, rv3 = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+        out3, mean3, rstd3, msk = ops.batchnorm_fwd(x, g, b, rm3, rv3, residual=res, relu=True, col_stats=st,
+                                                    want_mask=True)
+        bits = ((msk.unsqueeze(-1) >> torch.arange(8, device=cuda_device, dtype=torch.uint8)) & 1).view(M, C).bool()
+        assert torch.equal(bits, out3 > 0)
+        dg3, db3 = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+        dx3, dz3 = ops.batchnorm_bwd(dout, None, x, mean3, rstd3, g, dg3, db3, relu=True, need_dz=use_res, mask=msk)
+        assert rel(dx3, xf.grad) < 2e-2 and rel(dg3, gf.grad) < 2e-2 and rel(db3, bf.grad) < 2e-2
+        if use_res:
+            assert rel(dz3, resf.grad) < 2e-2
     ev = ops.batchnorm_eval(x, g, b, rm2, rv2, residual=res, relu=relu)
     ref_ev = F.batch_norm(x.float(), rm2, rv2, g, b, False, 0.1, 1e-5)
     if use_res:
