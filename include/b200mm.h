@@ -41,7 +41,9 @@ int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int 
                      int K, int epi, const float* bias, const void* residual, long long ldr, const void* aux,
                      long long ld_aux, void* out, long long ldc, void* out2, long long ld2, int splits, int block_n,
                      float p_drop, unsigned long long seed, float* col_stats, void* stream);
-/* col_stats (nullable; epi 0 without bias / residual / dropout): fp32 [2N], col_stats[n] += sum_m out[m,n],
+/* residual == out (same pointer and stride, epi 0, no dropout): out += A x B (+ bias) in place -- the epilogue issues
+ * TMA reduce-add stores, the add happens in L2 (bf16), the SM never loads the residual.
+ * col_stats (nullable; epi 0 without bias / residual / dropout): fp32 [2N], col_stats[n] += sum_m out[m,n],
  * col_stats[N+n] += sum_m out[m,n]^2 over the STORED bf16 values -- the train-mode BatchNorm statistics of a
  * convolution output come out of the convolution's own epilogue (feeds b200mm_batchnorm_fwd_stats). */
 

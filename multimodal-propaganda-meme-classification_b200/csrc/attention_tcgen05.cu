@@ -40,6 +40,13 @@ struct AttnParams {
   __nv_bfloat16* dqkv;         // bwd: [B*S, 3D]
 };
 
+// exp2 on the special-function unit (inputs are <= 0 here; ex2.approx maps -inf to +0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // byte offset of 16-byte chunk `chunk` (0..7) of row `r` inside a [rows x 64] bf16 SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int chunk) { return r * 128 + ((chunk ^ (r & 7)) << 4); }
 
@@ -746,6 +753,172 @@ attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------ 128 < S <= 384, forward
+// All score tiles of a query tile stay in TMEM (NT x 128 columns; NT = ceil(S / 128) <= 3), so the forward is ONE pass:
+// Q, every K tile and every V tile arrive with one TMA wave, S_j = Q K_j^T for all j is issued back to back, the exact
+// row maximum is taken over the NT x 128 columns, then P_j = exp2(S_j - max) and O += P_j V_j per key tile.  O
+// accumulates in the first 64 columns of S_0 (already consumed when the first P V is issued) and P reuses Q's shared
+// memory, which keeps the CTA at NT*32 + 32 KB of shared memory and NT*128 TMEM columns: 2 CTAs / SM for the ViT
+// lengths (197, 257 -> NT = 2, 3).  Replaces the two-pass kernel above for these lengths (that one recomputed Q K^T
+// and reloaded K per pass: 299 us -> see profiles/ for the measured time at B=256, H=12, S=197).
+template <int NT>
+__global__ void __launch_bounds__(128, NT <= 2 ? 2 : 1)
+attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQP = smem;                              // Q [128 x 64] first, then P [128 x 128] (two swizzled blocks)
+  uint8_t* sK = sQP + 2 * ATT_TILE_BYTES;           // NT tiles
+  uint8_t* sV = sK + NT * ATT_TILE_BYTES;           // NT tiles
+  float* sBias = reinterpret_cast<float*>(sV + NT * ATT_TILE_BYTES);   // [NT * 128]
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + NT * ATT_T);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  constexpr int TMEM_COLS = NT == 1 ? 128 : (NT == 2 ? 256 : 512);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_O = tmem;   // aliases columns 0..63 of S_0
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+  const int nt = (p.S + ATT_T - 1) / ATT_T;      // query tiles per head (== NT key tiles)
+  const int s_pad = nt * ATT_T;
+
+  uint32_t ph_load = 0, ph_mma = 0;
+  const int items = p.B * p.H * nt;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int qi = item % nt, bh = item / nt;
+    const int b = bh / p.H, h = bh - b * p.H;
+    const int q0 = qi * ATT_T;
+    tc_fence_before_sync();
+    __syncthreads();   // previous item: everybody has read O / sBias, the tensor core is done with sQP / sK / sV
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, (1 + 2 * NT) * ATT_TILE_BYTES);
+      tma_load_3d(sQP, &tma_qkv, bar_load, h * ATT_D, q0, b);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        tma_load_3d(sK + j * ATT_TILE_BYTES, &tma_qkv, bar_load, p.D + h * ATT_D, j * ATT_T, b);
+        tma_load_3d(sV + j * ATT_TILE_BYTES, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, j * ATT_T, b);
+      }
+    }
+    for (int k = tid; k < NT * ATT_T; k += 128)
+      sBias[k] = k < p.S ? (p.key_bias ? p.key_bias[b * p.S + k] * LOG2E : 0.f) : -INFINITY;
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar_load, ph_load);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + j * ATT_T, umma_desc_sw128(smem_u32(sQP) + k * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sK + j * ATT_TILE_BYTES) + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit(bar_mma);
+    }
+    ph_load ^= 1;
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after_sync();
+
+    // ---- exact row maximum over all NT x 128 key columns (TMEM reads only)
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < NT * 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_addr + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[c * 32 + i]));
+    }
+    if (mx == -INFINITY) mx = 0.f;
+
+    // ---- P_j = exp2(S_j - max) -> shared memory -> O += P_j V_j
+    float sum = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + j * ATT_T + c * 32, v);
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          x[i] = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[j * ATT_T + c * 32 + i]) - mx);
+          sum += x[i];
+        }
+        if (use_drop) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t keep = dropout_keep4(p.seed, drop_group(bh, s_pad, q0 + tid, j * ATT_T + c * 32 + g * 4),
+                                                p.drop_threshold);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[g * 4 + i] = (keep >> i) & 1 ? x[g * 4 + i] * p.inv_keep : 0.f;
+          }
+        }
+        store_row32_sw128(sQP, tid, c * 32, x);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();   // P_j complete in shared memory; every thread has finished reading S_j from TMEM
+      if (tid == 0) {
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(t_O, umma_desc_sw128(smem_u32(sQP) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(smem_u32(sV + j * ATT_TILE_BYTES) + k * 2048, 8192, 1024), idesc_o,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, ph_mma);   // P V_j done: the P buffer may be overwritten / O may be read
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+    }
+
+    const float inv_sum = 1.f / sum;
+    const bool row_ok = q0 + tid < p.S;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.S + q0 + tid) * p.D + h * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_O + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv_sum, __uint_as_float(v[q * 8 + 1]) * inv_sum);
+          o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv_sum, __uint_as_float(v[q * 8 + 3]) * inv_sum);
+          o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv_sum, __uint_as_float(v[q * 8 + 5]) * inv_sum);
+          o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv_sum, __uint_as_float(v[q * 8 + 7]) * inv_sum);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = o;
+        }
+      }
+    }
+    if (row_ok && p.lse) p.lse[static_cast<long long>(bh) * p.S + q0 + tid] = (mx + log2f(sum)) * LN2;
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+template <int NT>
+constexpr int att_fwd_tmem_smem() { return (2 + 2 * NT) * ATT_TILE_BYTES + NT * ATT_T * 4 + 64 + 1024; }
+
 constexpr int ATT_FWD_MULTI_SMEM = 5 * ATT_TILE_BYTES + ATT_MAX_S * 4 + 64 + 1024;
 
 constexpr int ATT_FWD_SMEM = 5 * ATT_TILE_BYTES + ATT_T * 4 + 64 + 1024;
@@ -791,6 +964,29 @@ B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void
     e = cudaFuncSetAttribute(attn_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_MULTI_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
+  }
+  if (S > ATT_T && S <= 3 * ATT_T) {      // ViT lengths: score tiles stay in TMEM, one pass
+    const int nt = ceil_div(S, ATT_T);
+    const int items = B * H * nt;
+    static bool configured_tmem = false;
+    if (!configured_tmem) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tmem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           att_fwd_tmem_smem<2>());
+      if (e != cudaSuccess) return static_cast<int>(e);
+      e = cudaFuncSetAttribute(attn_fwd_tmem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               att_fwd_tmem_smem<3>());
+      if (e != cudaSuccess) return static_cast<int>(e);
+      configured_tmem = true;
+    }
+    if (nt == 2) {
+      const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
+      attn_fwd_tmem_kernel<2><<<grid, 128, att_fwd_tmem_smem<2>(), static_cast<cudaStream_t>(stream)>>>(tq, p);
+    } else {
+      const int grid = items < dev.num_sms ? items : dev.num_sms;
+      attn_fwd_tmem_kernel<3><<<grid, 128, att_fwd_tmem_smem<3>(), static_cast<cudaStream_t>(stream)>>>(tq, p);
+    }
+    B200MM_CHECK_LAUNCH();
+    return B200MM_OK;
   }
   if (S > ATT_T) {
     const int items = B * H * ceil_div(S, ATT_T);

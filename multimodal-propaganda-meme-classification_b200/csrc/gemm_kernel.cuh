@@ -409,7 +409,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(pass == 0 ? &tma_out : &tma_out2, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
+              if constexpr (EPI == EPI_STORE) {
+                // in-place residual (out += acc): the L2 performs the add, the SM never loads the residual
+                if (p.accumulate) tma_reduce_add_2d(&tma_out, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
+                else tma_store_2d(&tma_out, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
+              } else {
+                tma_store_2d(pass == 0 ? &tma_out : &tma_out2, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
+              }
               tma_store_commit();
             }
             if constexpr (EPI == EPI_STORE_STATS) {

@@ -40,6 +40,7 @@ struct GemmParams {
   __nv_bfloat16* out2;
   long long ld2;
   float* col_stats;  // EPI_STORE_STATS: fp32 [2N] accumulators (pre-zeroed by the caller)
+  int accumulate;    // EPI_STORE with residual == out: out += acc through TMA reduce-add stores (no residual loads)
   // EPI_STORE only: inverted dropout on (acc + bias) before the residual add, mask keyed by (seed, row * N + col)
   float p_drop;
   uint32_t drop_threshold;

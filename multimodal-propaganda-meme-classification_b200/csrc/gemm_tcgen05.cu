@@ -88,6 +88,10 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   p.bias = bias;
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.ldr = ldr;
+  // residual aliasing the output (same pointer and stride), plain store mode: accumulate in place with TMA reduce-add
+  p.accumulate = (epi == EPI_STORE && residual != nullptr && residual == out && ldr == ldc && p_drop == 0.f) ? 1 : 0;
+  if (p.accumulate) p.residual = nullptr;
+  else if (residual != nullptr && residual == out) return B200MM_ERR_BAD_ARG;   // aliasing is only defined for that case
   p.aux = static_cast<const __nv_bfloat16*>(aux);
   p.ld_aux = ld_aux;
   p.out = out;

@@ -323,7 +323,8 @@ class ImageTower:
             d_y1, _ = ops.batchnorm_bwd(d_a1, None, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True, beta=c1.b)
             ops.linear_wgrad(d_y1, x, c1.dw)
             if ds is None:
-                d_out = ops.linear_dgrad(d_y1, c1.w, residual=dz)          # identity branch folded into the epilogue
+                # identity branch: dz += d_y1 W1 in place (TMA reduce-add stores; the residual is never loaded)
+                d_out = ops.linear_dgrad(d_y1, c1.w, residual=dz, out=dz)
             else:
                 d_yd, _ = ops.batchnorm_bwd(dz, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=False)
                 ops.linear_wgrad(d_yd, xs, ds.dw)

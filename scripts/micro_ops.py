@@ -51,7 +51,8 @@ elif "gemm_res" in which:
 elif "gemmx" in which:
     shapes = [(32768, 3072, 768, 1, 0), (32768, 3072, 768, 0, 2), (32768, 3072, 768, 1, 2), (32768, 3072, 768, 0, 0),
               (32768, 3072, 768, 0, 1), (32768, 768, 768, 0, 0), (32768, 768, 768, 0, 7), (32768, 768, 3072, 0, 7),
-              (802816, 256, 64, 1, 0), (802816, 256, 64, 1, 7)]
+              (802816, 256, 64, 1, 0), (802816, 256, 64, 1, 7), (802816, 256, 64, 1, 8), (200704, 512, 128, 1, 7),
+              (200704, 512, 128, 1, 8), (50176, 1024, 256, 1, 7), (50176, 1024, 256, 1, 8)]
     which.append("gemm")
 elif "gemm1" in which:
     shapes = [(802816, 256, 64, 0, 0)]
@@ -62,14 +63,19 @@ elif "gemm" in which:
 if "gemm" in which or "gemm1" in which:
     for (M, N, K, b_mn, epi) in shapes:
         res = None
+        inplace = False
+        if epi == 8:     # plain store, residual aliasing the output (TMA reduce-add)
+            epi, inplace = 0, True
         if epi == 7:     # plain store + residual
             epi, res = 0, torch.randn(M, N, device=dev).to(bf)
         A = torch.randn(M, K, device=dev).to(bf)
         Bm = torch.randn(N, K, device=dev).to(bf) if not b_mn else torch.randn(K, N, device=dev).to(bf)
         out = torch.empty(M, N, device=dev, dtype=bf); out2 = torch.empty(M, N, device=dev, dtype=bf) if epi == 1 else None
+        if inplace:
+            out.zero_(); res = out
         aux = torch.randn(M, N, device=dev).to(bf) if epi == 2 else None
         bias = torch.zeros(N, device=dev) if epi != 2 else None   # dgrad epilogues carry no bias
-        timeit(f"gemm M{M} N{N} K{K} b_mn{b_mn} epi{epi}{'+res' if res is not None else ''}", lambda: ops.gemm_raw(A, False, Bm, bool(b_mn), M, N, K, out, epi=epi, bias=bias, aux=aux, out2=out2, residual=res),
+        timeit(f"gemm M{M} N{N} K{K} b_mn{b_mn} epi{epi}{'+res' if res is not None else ''}{' (in place)' if inplace else ''}", lambda: ops.gemm_raw(A, False, Bm, bool(b_mn), M, N, K, out, epi=epi, bias=bias, aux=aux, out2=out2, residual=res),
                flops=2.0 * M * N * K, bytes_=2.0 * (M * K + N * K + M * N * (2 if epi == 1 else 1) + (M * N if epi == 2 else 0)))
 if "attn" in which:
     for (B, H, S) in [(256, 12, 128), (256, 12, 197)]:

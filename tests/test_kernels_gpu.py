@@ -48,6 +48,9 @@ def test_gemm_dgrad_wgrad(ops, cuda_device, M, N, K):
     res = torch.randn(M, K, device=cuda_device).to(bf16)
     assert rel(ops.linear_dgrad(dy, w), dy.float() @ w.float()) < 1e-2
     assert rel(ops.linear_dgrad(dy, w, residual=res), dy.float() @ w.float() + res.float()) < 1e-2
+    acc = res.clone()                                            # residual aliasing the output: in-place reduce-add
+    got = ops.linear_dgrad(dy, w, residual=acc, out=acc)
+    assert got.data_ptr() == acc.data_ptr() and rel(acc, dy.float() @ w.float() + res.float()) < 1e-2
     z = torch.randn(M, K, device=cuda_device).to(bf16)
     zf = z.float().requires_grad_(True)
     F.gelu(zf).sum().backward()
@@ -94,7 +97,7 @@ def _attn_ref(qkv, key_bias, B, H, S):
 
 
 @pytest.mark.parametrize("B,H,S", [(2, 2, 128), (3, 12, 128), (2, 4, 64), (2, 3, 100), (2, 2, 256), (2, 3, 197),
-                                   (1, 4, 512), (2, 2, 300)])
+                                   (1, 4, 512), (2, 2, 300), (3, 2, 257), (2, 2, 384), (5, 12, 197)])
 def test_attention_fwd_bwd(ops, cuda_device, B, H, S):
     torch.manual_seed(3)
     D = H * 64
