@@ -916,6 +916,241 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     tmem_dealloc<TMEM_COLS>(tmem);
   }
 }
+// ------------------------------------------------------------------------------------------ 128 < S <= 256, backward
+// One CTA (256 threads) owns a whole (batch, head): Q, K, V, dO of both 128-row tiles are loaded ONCE (128 KB), and all
+// five gradient accumulators live in TMEM next to the score tiles: S | dP | dK_j dV_j | dQ_0 dQ_1 = 512 columns.  For
+// each of the four (query tile i, key tile j) pairs: S = Q_i K_j^T and dP = dO_i V_j^T on the tensor core, P and dS in
+// registers (two warps per TMEM lane quarter split the 128 key columns -- the backward needs no row reductions: LSE
+// and delta = rowsum(dO o O) are per-row scalars), then dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j.  Every
+// S / dP tile is computed once (the two-kind kernel above computes each twice and reloads its operands per pair:
+// 924 us -> see profiles/ for the measured time at B=256, H=12, S=197).
+constexpr int ATT_BWD2_THREADS = 256;
+constexpr int ATT_BWD2_SMEM = 12 * ATT_TILE_BYTES + 2 * ATT_T * 4 + 64 + 1024;
+__global__ void __launch_bounds__(ATT_BWD2_THREADS, 1)
+attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                     const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // 2 tiles each: [tile][128 x 64]
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + 2 * ATT_TILE_BYTES;
+  uint8_t* sdO = sV + 2 * ATT_TILE_BYTES;
+  uint8_t* sP = sdO + 2 * ATT_TILE_BYTES;           // 32 KB
+  uint8_t* sdS = sP + 2 * ATT_TILE_BYTES;           // 32 KB
+  float* sBias = reinterpret_cast<float*>(sdS + 2 * ATT_TILE_BYTES);   // [256]
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + 2 * ATT_T);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;   // row of a 128-row tile this thread owns (TMEM lane)
+  const int half = warp >> 2;               // which 64 of a tile's 128 key columns / which accumulator it drains
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_S = tmem, t_dP = tmem + 128, t_dK = tmem + 256, t_dV = tmem + 320, t_dQ = tmem + 384;  // dQ_i at +64 i
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);
+  const uint32_t idesc_nt = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+  constexpr int s_pad = 2 * ATT_T;
+
+  auto issue_scores = [&](int i, int j) {   // S = Q_i K_j^T, dP = dO_i V_j^T   (single thread)
+    const uint32_t q = smem_u32(sQ + i * ATT_TILE_BYTES), k = smem_u32(sK + j * ATT_TILE_BYTES);
+    const uint32_t g = smem_u32(sdO + i * ATT_TILE_BYTES), v = smem_u32(sV + j * ATT_TILE_BYTES);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16(t_S, umma_desc_sw128(q + kk * 32, 16, 1024), umma_desc_sw128(k + kk * 32, 16, 1024), idesc_s, kk > 0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16(t_dP, umma_desc_sw128(g + kk * 32, 16, 1024), umma_desc_sw128(v + kk * 32, 16, 1024), idesc_s, kk > 0);
+    umma_commit(bar_mma);
+  };
+
+  uint32_t ph_load = 0, ph_mma = 0;
+  const int items = p.B * p.H;
+  for (int bh = blockIdx.x; bh < items; bh += gridDim.x) {
+    const int b = bh / p.H, h = bh - b * p.H;
+    tc_fence_before_sync();
+    __syncthreads();   // previous head: all shared-memory / TMEM readers are done
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, 8 * ATT_TILE_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        tma_load_3d(sQ + t * ATT_TILE_BYTES, &tma_qkv, bar_load, h * ATT_D, t * ATT_T, b);
+        tma_load_3d(sK + t * ATT_TILE_BYTES, &tma_qkv, bar_load, p.D + h * ATT_D, t * ATT_T, b);
+        tma_load_3d(sV + t * ATT_TILE_BYTES, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, t * ATT_T, b);
+        tma_load_3d(sdO + t * ATT_TILE_BYTES, &tma_do, bar_load, h * ATT_D, t * ATT_T, b);
+      }
+    }
+    sBias[tid] = tid < p.S ? (p.key_bias ? p.key_bias[b * p.S + tid] * LOG2E : 0.f) : -INFINITY;
+    // per-row scalars of this thread's row in both query tiles: delta = sum_d dO o O, log2-domain LSE
+    float delta[2] = {0.f, 0.f}, lse_l2[2] = {INFINITY, INFINITY};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int qrow = i * ATT_T + row;
+      if (qrow < p.S) {
+        const long long off = (static_cast<long long>(b) * p.S + qrow) * p.D + h * ATT_D;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float a[8], g[8];
+          load8(p.o_in + off + q * 8, a);
+          load8(p.do_in + off + q * 8, g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) delta[i] = fmaf(a[e], g[e], delta[i]);
+        }
+        lse_l2[i] = p.lse[static_cast<long long>(bh) * p.S + qrow] * LOG2E;
+      }
+    }
+    __syncthreads();   // sBias visible
+    if (tid == 0) {
+      mbar_wait(bar_load, ph_load);
+      tc_fence_after_sync();
+      issue_scores(0, 0);
+    }
+    ph_load ^= 1;
+
+#pragma unroll 1
+    for (int pair = 0; pair < 4; ++pair) {
+      const int j = pair >> 1, i = pair & 1;     // key tile outer, query tile inner
+      mbar_wait(bar_mma, ph_mma);                // S / dP of this pair are ready (and every earlier MMA has retired)
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;             // 32-column chunk of the 128 key columns
+        uint32_t vs[32], vp[32];
+        tmem_ld32(t_S + lane_addr + c * 32, vs);
+        tmem_ld32(t_dP + lane_addr + c * 32, vp);
+        tmem_ld_wait();
+        float pd[32], ds[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          pd[e] = fast_exp2(fmaf(__uint_as_float(vs[e]), p.scale_log2, sBias[j * ATT_T + c * 32 + e]) - lse_l2[i]);
+          ds[e] = __uint_as_float(vp[e]);
+        }
+        if (use_drop) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t keep = dropout_keep4(
+                p.seed, drop_group(bh, s_pad, i * ATT_T + row, j * ATT_T + c * 32 + g * 4), p.drop_threshold);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float m = (keep >> e) & 1 ? p.inv_keep : 0.f;
+              const float prob = pd[g * 4 + e];
+              pd[g * 4 + e] = prob * m;
+              ds[g * 4 + e] = prob * (ds[g * 4 + e] * m - delta[i]) * p.scale;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ds[e] = pd[e] * (ds[e] - delta[i]) * p.scale;
+        }
+        store_row32_sw128(sP, row, c * 32, pd);
+        store_row32_sw128(sdS, row, c * 32, ds);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();   // P / dS complete; S / dP fully read
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t q = smem_u32(sQ + i * ATT_TILE_BYTES), k = smem_u32(sK + j * ATT_TILE_BYTES);
+        const uint32_t g = smem_u32(sdO + i * ATT_TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dV_j (+)= P^T dO_i   (first query tile overwrites)
+          umma_bf16(t_dV, umma_desc_sw128(smem_u32(sP) + kk * 2048, ATT_TILE_BYTES, 1024),
+                    umma_desc_sw128(g + kk * 2048, 8192, 1024), idesc_tt, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dK_j (+)= dS^T Q_i
+          umma_bf16(t_dK, umma_desc_sw128(smem_u32(sdS) + kk * 2048, ATT_TILE_BYTES, 1024),
+                    umma_desc_sw128(q + kk * 2048, 8192, 1024), idesc_tt, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dQ_i (+)= dS K_j     (first key tile overwrites)
+          umma_bf16(t_dQ + i * 64,
+                    umma_desc_sw128(smem_u32(sdS) + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                    umma_desc_sw128(k + kk * 2048, 8192, 1024), idesc_nt, (j > 0 || kk > 0) ? 1u : 0u);
+        // the next pair's scores go in right behind (S / dP columns are free, the tensor core runs in order) --
+        // except across a key-tile boundary, where dK_j / dV_j must first be drained by the epilogue below
+        if (pair == 0 || pair == 2) issue_scores(1, j);
+        else umma_commit(bar_mma);
+      }
+      if (i == 1) {
+        // ---- key tile j finished: drain dK_j (half 0) / dV_j (half 1) -> dqkv rows j*128 + row
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after_sync();
+        const int krow = j * ATT_T + row;
+        const uint32_t t_src = half == 0 ? t_dK : t_dV;
+        __nv_bfloat16* grow = p.dqkv + (static_cast<long long>(b) * p.S + krow) * (3 * p.D) + (1 + half) * p.D + h * ATT_D;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_src + lane_addr + c * 32, v);
+          tmem_ld_wait();
+          if (krow < p.S) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+              o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+              o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+              *reinterpret_cast<uint4*>(grow + c * 32 + q * 8) = o;
+            }
+          }
+        }
+        if (j == 0) {
+          tc_fence_before_sync();
+          __syncthreads();   // dK_0 / dV_0 drained by everybody before the tensor core may overwrite them
+          if (tid == 0) {
+            tc_fence_after_sync();
+            issue_scores(0, 1);
+          }
+        }
+      }
+    }
+    // ---- dQ_0 (half 0) / dQ_1 (half 1): the drain above already waited for the last MMA group
+    {
+      const int qrow = half * ATT_T + row;
+      __nv_bfloat16* grow = p.dqkv + (static_cast<long long>(b) * p.S + qrow) * (3 * p.D) + h * ATT_D;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_dQ + half * 64 + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (qrow < p.S) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(grow + c * 32 + q * 8) = o;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 template <int NT>
 constexpr int att_fwd_tmem_smem() { return (2 + 2 * NT) * ATT_TILE_BYTES + NT * ATT_T * 4 + 64 + 1024; }
 
@@ -1030,6 +1265,20 @@ B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, cons
     e = cudaFuncSetAttribute(attn_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
+  }
+  if (S > ATT_T && S <= 2 * ATT_T) {     // whole head per CTA, every accumulator resident in TMEM
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ATT_BWD2_SMEM);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      configured2 = true;
+    }
+    const int items = B * H;
+    const int grid = items < dev.num_sms ? items : dev.num_sms;
+    attn_bwd_tmem_kernel<<<grid, ATT_BWD2_THREADS, ATT_BWD2_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
+    B200MM_CHECK_LAUNCH();
+    return B200MM_OK;
   }
   if (S > ATT_T) {
     const int items = 2 * B * H * ceil_div(S, ATT_T);
