@@ -1151,6 +1151,230 @@ attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------ S <= 128, backward (v2)
+// Same idea for one-tile sequences (the text towers at 128 tokens): 256 threads so that two warps per TMEM lane quarter
+// split the key columns of P / dS and the three output tiles, and a two-stage shared-memory ring so the next head's
+// Q / K / V / dO arrive while the current head computes (the first version above is single-buffered, 128 threads,
+// one CTA per SM: every TMA / MMA latency was exposed: 199 us at B=256, H=12, S=128).
+constexpr int ATT_BWD1_SMEM = 12 * ATT_TILE_BYTES + 2 * ATT_T * 4 + 64 + 1024;
+__global__ void __launch_bounds__(256, 1)
+attn_bwd1_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                 const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sIn = smem;                              // [2 stages][Q | K | V | dO], 64 KB per stage
+  uint8_t* sP = sIn + 8 * ATT_TILE_BYTES;           // 32 KB
+  uint8_t* sdS = sP + 2 * ATT_TILE_BYTES;           // 32 KB
+  float* sBias = reinterpret_cast<float*>(sdS + 2 * ATT_TILE_BYTES);   // [2][128]
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + 2 * ATT_T); // [2]
+  uint64_t* bar_s = bar_load + 2;      // scores (S, dP) of a head are in TMEM
+  uint64_t* bar_g = bar_s + 1;         // gradient MMAs of a head have retired
+  // (two barriers: the scores of head n+1 are committed right behind the gradients of head n, and a single barrier
+  //  could complete two phases before a slow thread has observed the first)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_g + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+    mbar_init(&bar_load[0], 1);
+    mbar_init(&bar_load[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_g, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_S = tmem, t_dP = tmem + 128, t_dK = tmem + 256, t_dV = tmem + 320, t_dQ = tmem + 384;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);
+  const uint32_t idesc_nt = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+  const int items = p.B * p.H;
+
+  auto issue_loads = [&](int item, int stage) {   // single thread
+    const int b = item / p.H, h = item - b * p.H;
+    uint8_t* base = sIn + stage * 4 * ATT_TILE_BYTES;
+    mbar_expect_tx(&bar_load[stage], 4 * ATT_TILE_BYTES);
+    tma_load_3d(base, &tma_qkv, &bar_load[stage], h * ATT_D, 0, b);
+    tma_load_3d(base + ATT_TILE_BYTES, &tma_qkv, &bar_load[stage], p.D + h * ATT_D, 0, b);
+    tma_load_3d(base + 2 * ATT_TILE_BYTES, &tma_qkv, &bar_load[stage], 2 * p.D + h * ATT_D, 0, b);
+    tma_load_3d(base + 3 * ATT_TILE_BYTES, &tma_do, &bar_load[stage], h * ATT_D, 0, b);
+  };
+
+  auto issue_scores = [&](int stage) {            // single thread: S = Q K^T, dP = dO V^T
+    const uint32_t q = smem_u32(sIn + stage * 4 * ATT_TILE_BYTES), k = q + ATT_TILE_BYTES, v = k + ATT_TILE_BYTES,
+                   g = v + ATT_TILE_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16(t_S, umma_desc_sw128(q + kk * 32, 16, 1024), umma_desc_sw128(k + kk * 32, 16, 1024), idesc_s, kk > 0);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16(t_dP, umma_desc_sw128(g + kk * 32, 16, 1024), umma_desc_sw128(v + kk * 32, 16, 1024), idesc_s, kk > 0);
+    umma_commit(bar_s);
+  };
+  // per-row inputs of delta = rowsum(dO o O) and the LSE, fetched one head AHEAD (they sit on the critical path
+  // otherwise: 25 % of the stall samples of the first version)
+  uint4 ro[8], rg[8];
+  float lse_raw = INFINITY;
+  auto prefetch_rows = [&](int item) {
+    const int b = item / p.H, h = item - b * p.H;
+    if (row < p.S) {
+      const long long off = (static_cast<long long>(b) * p.S + row) * p.D + h * ATT_D;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ro[q] = __ldg(reinterpret_cast<const uint4*>(p.o_in + off + q * 8));
+        rg[q] = __ldg(reinterpret_cast<const uint4*>(p.do_in + off + q * 8));
+      }
+      lse_raw = __ldg(p.lse + static_cast<long long>(item) * p.S + row);
+    }
+  };
+  auto write_bias = [&](int item, int stage) {
+    const int b = item / p.H;
+    if (tid < ATT_T)
+      sBias[stage * ATT_T + tid] = tid < p.S ? (p.key_bias ? p.key_bias[b * p.S + tid] * LOG2E : 0.f) : -INFINITY;
+  };
+
+  uint32_t ph_s = 0, ph_g = 0;
+  if (static_cast<int>(blockIdx.x) < items) {
+    if (tid == 0) {
+      issue_loads(blockIdx.x, 0);
+      mbar_wait(&bar_load[0], 0);
+      tc_fence_after_sync();
+      issue_scores(0);
+    }
+    prefetch_rows(blockIdx.x);
+    write_bias(blockIdx.x, 0);
+  }
+  int n = 0;
+  for (int item = blockIdx.x; item < items; item += gridDim.x, ++n) {
+    const int stage = n & 1;
+    const int next = item + static_cast<int>(gridDim.x);
+    const int b = item / p.H, h = item - b * p.H;
+    uint8_t* sQ = sIn + stage * 4 * ATT_TILE_BYTES;
+    uint8_t* sK = sQ + ATT_TILE_BYTES;
+    uint8_t* sdO = sK + 2 * ATT_TILE_BYTES;
+    const float* bias = sBias + stage * ATT_T;
+    // the other stage was last read by the previous head's MMAs, all retired (bar_g waited): refill it now
+    if (tid == 0 && next < items) issue_loads(next, stage ^ 1);
+    const bool row_ok = row < p.S;
+    float delta = 0.f, lse_l2 = INFINITY;
+    if (row_ok) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float a[8], g[8];
+        unpack8(ro[q], a);
+        unpack8(rg[q], g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) delta = fmaf(a[e], g[e], delta);
+      }
+      lse_l2 = lse_raw * LOG2E;
+    }
+    __syncthreads();   // this head's bias (written one iteration ago) is visible
+    mbar_wait(bar_s, ph_s);   // S / dP of this head (issued one iteration ago)
+    ph_s ^= 1;
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
+      uint32_t vs[32], vp[32];
+      tmem_ld32(t_S + lane_addr + c * 32, vs);
+      tmem_ld32(t_dP + lane_addr + c * 32, vp);
+      tmem_ld_wait();
+      float pd[32], ds[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        pd[e] = fast_exp2(fmaf(__uint_as_float(vs[e]), p.scale_log2, bias[c * 32 + e]) - lse_l2);
+        ds[e] = __uint_as_float(vp[e]);
+      }
+      if (use_drop) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint64_t gidx = (static_cast<uint64_t>(item) * ATT_T + row) * 32 + c * 8 + g;   // as the forward
+          const uint32_t keep = dropout_keep4(p.seed, gidx, p.drop_threshold);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float m = (keep >> e) & 1 ? p.inv_keep : 0.f;
+            const float prob = pd[g * 4 + e];
+            pd[g * 4 + e] = prob * m;
+            ds[g * 4 + e] = prob * (ds[g * 4 + e] * m - delta) * p.scale;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ds[e] = pd[e] * (ds[e] - delta) * p.scale;
+      }
+      store_row32_sw128(sP, row, c * 32, pd);
+      store_row32_sw128(sdS, row, c * 32, ds);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();   // P / dS complete, S / dP fully read
+    if (tid == 0) {
+      tc_fence_after_sync();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(t_dV, umma_desc_sw128(smem_u32(sP) + k * 2048, ATT_TILE_BYTES, 1024),
+                  umma_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024), idesc_tt, k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(t_dK, umma_desc_sw128(smem_u32(sdS) + k * 2048, ATT_TILE_BYTES, 1024),
+                  umma_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024), idesc_tt, k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(t_dQ, umma_desc_sw128(smem_u32(sdS) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  umma_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_nt, k > 0);
+      umma_commit(bar_g);
+      // the next head's scores go in right behind (in-order tensor pipe; S / dP are free, its tiles were prefetched)
+      if (next < items) {
+        mbar_wait(&bar_load[stage ^ 1], ((n + 1) >> 1) & 1);
+        tc_fence_after_sync();
+        issue_scores(stage ^ 1);
+      }
+    }
+    if (next < items) {   // next head's per-row inputs and key bias travel while the gradient MMAs run
+      prefetch_rows(next);
+      write_bias(next, stage ^ 1);
+    }
+    mbar_wait(bar_g, ph_g);   // dV / dK / dQ of this head
+    ph_g ^= 1;
+    tc_fence_after_sync();
+    // ---- drain: half 0 -> dQ (64 cols) + dK cols 0..31 ; half 1 -> dV (64 cols) + dK cols 32..63
+    __nv_bfloat16* grow = p.dqkv + (static_cast<long long>(b) * p.S + row) * (3 * p.D) + h * ATT_D;
+#pragma unroll 1
+    for (int piece = 0; piece < 3; ++piece) {
+      const uint32_t t_src = piece < 2 ? ((half == 0 ? t_dQ : t_dV) + piece * 32) : (t_dK + half * 32);
+      const int col = piece < 2 ? ((half == 0 ? 0 : 2 * p.D) + piece * 32) : (p.D + half * 32);
+      uint32_t v[32];
+      tmem_ld32(t_src + lane_addr, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+          *reinterpret_cast<uint4*>(grow + col + q * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 template <int NT>
 constexpr int att_fwd_tmem_smem() { return (2 + 2 * NT) * ATT_TILE_BYTES + NT * ATT_T * 4 + 64 + 1024; }
 
@@ -1289,7 +1513,13 @@ B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, cons
   }
   const int items = B * H;
   const int grid = items < dev.num_sms ? items : dev.num_sms;
-  attn_bwd_kernel<<<grid, 128, ATT_BWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
+  static bool configured1 = false;
+  if (!configured1) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD1_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured1 = true;
+  }
+  attn_bwd1_kernel<<<grid, 256, ATT_BWD1_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, p);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
