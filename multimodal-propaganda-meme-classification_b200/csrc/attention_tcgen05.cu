@@ -149,13 +149,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
         sum += x[i];
       }
       if (use_drop) {
+        const uint32_t keep = dropout_keep32(p.seed, (static_cast<uint64_t>(item) * ATT_T + tid) * 4 + c,
+                                             p.drop_threshold >> 16);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint64_t gidx = (static_cast<uint64_t>(item) * ATT_T + tid) * 32 + c * 8 + g;
-          const uint32_t keep = dropout_keep4(p.seed, gidx, p.drop_threshold);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) x[g * 4 + i] = (keep >> i) & 1 ? x[g * 4 + i] * p.inv_keep : 0.f;
-        }
+        for (int i = 0; i < 32; ++i) x[i] = (keep >> i) & 1 ? x[i] * p.inv_keep : 0.f;
       }
       store_row32_sw128(sP, tid, c * 32, x);
     }
@@ -304,17 +301,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
         ds[i] = __uint_as_float(vp[i]);
       }
       if (use_drop) {
+        const uint32_t keep = dropout_keep32(p.seed, (static_cast<uint64_t>(item) * ATT_T + tid) * 4 + c,
+                                             p.drop_threshold >> 16);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint64_t gidx = (static_cast<uint64_t>(item) * ATT_T + tid) * 32 + c * 8 + g;
-          const uint32_t keep = dropout_keep4(p.seed, gidx, p.drop_threshold);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float m = (keep >> i) & 1 ? p.inv_keep : 0.f;
-            const float prob = pd[g * 4 + i];
-            pd[g * 4 + i] = prob * m;                                         // dropped probs (for dV)
-            ds[g * 4 + i] = prob * (ds[g * 4 + i] * m - delta) * p.scale;     // dS
-          }
+        for (int i = 0; i < 32; ++i) {
+          const float m = (keep >> i) & 1 ? p.inv_keep : 0.f;
+          const float prob = pd[i];
+          pd[i] = prob * m;                                   // dropped probs (for dV)
+          ds[i] = prob * (ds[i] * m - delta) * p.scale;       // dS
         }
       } else {
 #pragma unroll
@@ -388,8 +382,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_consta
 // over the query tiles in TMEM, another owns a query tile and accumulates dQ over the key tiles: no atomics.
 constexpr int ATT_MAX_S = 512;
 
-__device__ __forceinline__ uint64_t drop_group(int bh, int s_pad, int qrow, int key) {
-  return ((static_cast<uint64_t>(bh) * s_pad + qrow) * s_pad + key) >> 2;
+// index of the 32-key chunk starting at `key` (multiple of 32) of query row `qrow`, for dropout_keep32
+__device__ __forceinline__ uint64_t drop_chunk(int bh, int s_pad, int qrow, int key) {
+  return ((static_cast<uint64_t>(bh) * s_pad + qrow) * s_pad + key) >> 5;
 }
 
 __global__ void __launch_bounds__(128, 2)
@@ -505,13 +500,10 @@ attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPar
           sum += x[i];
         }
         if (use_drop) {
+          const uint32_t keep = dropout_keep32(p.seed, drop_chunk(bh, s_pad, q0 + tid, j * ATT_T + c * 32),
+                                               p.drop_threshold >> 16);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t keep = dropout_keep4(p.seed, drop_group(bh, s_pad, q0 + tid, j * ATT_T + c * 32 + g * 4),
-                                                p.drop_threshold);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[g * 4 + i] = (keep >> i) & 1 ? x[g * 4 + i] * p.inv_keep : 0.f;
-          }
+          for (int i = 0; i < 32; ++i) x[i] = (keep >> i) & 1 ? x[i] * p.inv_keep : 0.f;
         }
         store_row32_sw128(sP, tid, c * 32, x);
       }
@@ -668,17 +660,14 @@ attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
           ds[i] = __uint_as_float(vp[i]);
         }
         if (use_drop) {
+          const uint32_t keep =
+              dropout_keep32(p.seed, drop_chunk(bh, s_pad, q0 + tid, k0 + c * 32), p.drop_threshold >> 16);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t keep =
-                dropout_keep4(p.seed, drop_group(bh, s_pad, q0 + tid, k0 + c * 32 + g * 4), p.drop_threshold);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float m = (keep >> i) & 1 ? p.inv_keep : 0.f;
-              const float prob = pd[g * 4 + i];
-              pd[g * 4 + i] = prob * m;
-              ds[g * 4 + i] = prob * (ds[g * 4 + i] * m - delta) * p.scale;
-            }
+          for (int i = 0; i < 32; ++i) {
+            const float m = (keep >> i) & 1 ? p.inv_keep : 0.f;
+            const float prob = pd[i];
+            pd[i] = prob * m;
+            ds[i] = prob * (ds[i] * m - delta) * p.scale;
           }
         } else {
 #pragma unroll
@@ -859,13 +848,10 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           sum += x[i];
         }
         if (use_drop) {
+          const uint32_t keep = dropout_keep32(p.seed, drop_chunk(bh, s_pad, q0 + tid, j * ATT_T + c * 32),
+                                               p.drop_threshold >> 16);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t keep = dropout_keep4(p.seed, drop_group(bh, s_pad, q0 + tid, j * ATT_T + c * 32 + g * 4),
-                                                p.drop_threshold);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[g * 4 + i] = (keep >> i) & 1 ? x[g * 4 + i] * p.inv_keep : 0.f;
-          }
+          for (int i = 0; i < 32; ++i) x[i] = (keep >> i) & 1 ? x[i] * p.inv_keep : 0.f;
         }
         store_row32_sw128(sQP, tid, c * 32, x);
       }
@@ -1040,17 +1026,14 @@ attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
           ds[e] = __uint_as_float(vp[e]);
         }
         if (use_drop) {
+          const uint32_t keep = dropout_keep32(p.seed, drop_chunk(bh, s_pad, i * ATT_T + row, j * ATT_T + c * 32),
+                                               p.drop_threshold >> 16);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t keep = dropout_keep4(
-                p.seed, drop_group(bh, s_pad, i * ATT_T + row, j * ATT_T + c * 32 + g * 4), p.drop_threshold);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float m = (keep >> e) & 1 ? p.inv_keep : 0.f;
-              const float prob = pd[g * 4 + e];
-              pd[g * 4 + e] = prob * m;
-              ds[g * 4 + e] = prob * (ds[g * 4 + e] * m - delta[i]) * p.scale;
-            }
+          for (int e = 0; e < 32; ++e) {
+            const float m = (keep >> e) & 1 ? p.inv_keep : 0.f;
+            const float prob = pd[e];
+            pd[e] = prob * m;
+            ds[e] = prob * (ds[e] * m - delta[i]) * p.scale;
           }
         } else {
 #pragma unroll
@@ -1307,17 +1290,14 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
         ds[e] = __uint_as_float(vp[e]);
       }
       if (use_drop) {
+        const uint32_t keep = dropout_keep32(p.seed, (static_cast<uint64_t>(item) * ATT_T + row) * 4 + c,
+                                             p.drop_threshold >> 16);   // as the forward
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint64_t gidx = (static_cast<uint64_t>(item) * ATT_T + row) * 32 + c * 8 + g;   // as the forward
-          const uint32_t keep = dropout_keep4(p.seed, gidx, p.drop_threshold);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float m = (keep >> e) & 1 ? p.inv_keep : 0.f;
-            const float prob = pd[g * 4 + e];
-            pd[g * 4 + e] = prob * m;
-            ds[g * 4 + e] = prob * (ds[g * 4 + e] * m - delta) * p.scale;
-          }
+        for (int e = 0; e < 32; ++e) {
+          const float m = (keep >> e) & 1 ? p.inv_keep : 0.f;
+          const float prob = pd[e];
+          pd[e] = prob * m;
+          ds[e] = prob * (ds[e] * m - delta) * p.scale;
         }
       } else {
 #pragma unroll

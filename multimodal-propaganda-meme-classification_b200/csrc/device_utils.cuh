@@ -35,6 +35,41 @@ __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
   }
   return make_uint4(c0, c1, c2, c3);
 }
+// Same generator with a compile-time round count (7 rounds already pass BigCrush, Salmon et al. 2011; the attention
+// kernels draw 128 x 128 Bernoulli variables per head and were spending more instructions on the generator than on the
+// softmax) and 16-bit fields: one call yields 8 keep decisions.
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32_r(uint64_t seed, uint64_t ctr) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = 0x1BD11BDAu, c3 = 0x5851F42Du;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// 32 keep bits (bit i set = element i kept) for one 32-element chunk; thr16 = p_drop * 2^16.
+__device__ __forceinline__ uint32_t dropout_keep32(uint64_t seed, uint64_t chunk_idx, uint32_t thr16) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 r = philox4x32_r<7>(seed, chunk_idx * 4 + q);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bits |= ((w[i] & 0xFFFFu) >= thr16 ? 1u : 0u) << (q * 8 + 2 * i);
+      bits |= ((w[i] >> 16) >= thr16 ? 1u : 0u) << (q * 8 + 2 * i + 1);
+    }
+  }
+  return bits;
+}
 // keep-mask for 4 consecutive elements: bit i set = element kept. threshold = p_drop * 2^32.
 __device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t group_idx, uint32_t threshold) {
   const uint4 r = philox4x32(seed, group_idx);
