@@ -355,9 +355,19 @@ def run_engine(args):
     gemm_ms, gemm_flops, n_gemm, det = ops.profile_gemm(step_resident, steps=2, ridge=ridge)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     t, h = det["tensor"], det["hbm"]
+    # DRAM traffic of the same kernel from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum, average
+    # per launch over every GEMM launch of a step, cold caches under ncu): profiles/ncu_traffic_r01.json
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if args.config == 2 and os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)["gemm"]["dram_bytes_per_launch"]
+        traffic_src = "profiles/ncu_traffic_r01.json (ncu, cold cache, mean over the GEMM launches of one step)"
+    algo_bytes_per_launch = (t["bytes"] + h["bytes"]) / max(n_gemm, 1)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05+TMA; linear layers and implicit-GEMM convolutions)",
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
+                "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": algo_bytes_per_launch, "peak_source": pk["source"],
                 "note": "all launches of the kernel; it is HBM-bound on the short-K convolution shapes, split below",
                 "launches_per_step": n_gemm, "gemm_ms_per_step": gemm_ms,
                 "gemm_share_of_step": gemm_ms / ms_step,

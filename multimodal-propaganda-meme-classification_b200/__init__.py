@@ -24,6 +24,7 @@ _LAZY = {
     "test": ("loop", "test"),
     "evaluate": ("loop", "evaluate"),
     "predict": ("loop", "predict"),
+    "get_features": ("loop", "get_features"),
     "seed_everything": ("loop_head", "seed_everything"),
     "stratified_kfold": ("loop_head", "stratified_kfold"),
     "get_params": ("loop_head", "get_params"),

@@ -187,3 +187,25 @@ def evaluate(model, test_loader, device, out_path="task2C_TeamName.tsv", run_id=
     labels = [ID2L[int(i)] for i in logits.argmax(1).tolist()]
     write_label_tsv(out_path, ids, labels, run_id)
     return list(zip(ids, labels))
+
+
+def get_features(model, loader, device):
+    """Feature extraction for the SVM baseline (baselines/extract_feat.py:52-67 ``get_features``):
+    eval-mode towers -> one image feature vector and one text feature vector per id, returned as the two
+    ``{id: [float, ...]}`` dicts that script dumps to JSON for baselines/subtask_2c.py:74-95.  The towers are the
+    engine's own (image: the tower's output vector -- 1000-d ResNet logits, or the ViT CLS feature; text: the pooled
+    token the classifier head reads), not the script's ConvNeXt / AraBERT pooler."""
+    model.eval()
+    img_feats, text_feats = {}, {}
+    with torch.no_grad():
+        for text, image, mask, _, data in DevicePrefetcher(loader, device):
+            B, S = text.shape
+            model._prep() if hasattr(model, "_prep") else model.store.refresh_shadow()
+            h = model.text.forward(text, mask, training=False)
+            off = S - 1 if getattr(model, "pooling", "cls") == "last" else 0
+            t = ops.gather_rows(h, B, S, off).float().cpu()
+            v = model.img.forward(image, training=False).float().cpu()
+            for k, i in enumerate(data["id"]):
+                img_feats[i] = v[k].tolist()
+                text_feats[i] = t[k].tolist()
+    return img_feats, text_feats

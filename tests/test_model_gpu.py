@@ -583,3 +583,44 @@ def test_head_three_tower_loop_api(cuda_device, tmp_path):
     out = eng(d["text"][:8], d["image"][:8], d["text_mask"][:8], d["caption_text"][:8], d["caption_text_mask"][:8])
     crit(out, d["label"][:8]).backward()
     assert torch.isfinite(eng.store.grad).all() and eng.store.grad.abs().sum() > 0
+
+
+def test_feature_extraction_and_odd_shapes(cuda_device):
+    """get_features (baselines/extract_feat.py contract: {id: vector} per modality) and shapes that are no multiple of
+    any tile: batch 3, 17 tokens, one sample with a single real token."""
+    import b200mm
+    oracle, eng, _, cfg = _pair(cuda_device)
+    from oracle import reference_model as R
+    data = R.synthetic_batch(3, 17, cfg, seed=99)
+    data["text_mask"][1, 1:] = 0
+    data["text"][1, 1:] = 0
+    d = _dev(data, cuda_device)
+    oracle.eval()
+    eng.eval()
+    ref = oracle(data["text"], data["image"], data["text_mask"]).detach()
+    assert rel(eng(d["text"], d["image"], d["text_mask"]), ref) < 2e-2
+    oracle.train()
+    eng.train()
+    crit = nn.CrossEntropyLoss()
+    loss_ref = crit(oracle(data["text"], data["image"], data["text_mask"]), data["label"])
+    eng.zero_grad()
+    _, loss, _ = eng.train_step_fused(d["text"], d["image"], d["text_mask"], d["label"])
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 2e-2 and torch.isfinite(eng.store.grad).all()
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 3
+
+        def __getitem__(self, i):
+            return {"id": f"img_{i}", "text": data["text"][i], "text_mask": data["text_mask"][i],
+                    "image": data["image"][i], "label": data["label"][i]}
+
+    img_f, txt_f = b200mm.get_features(eng, torch.utils.data.DataLoader(DS(), batch_size=2), cuda_device)
+    assert sorted(img_f) == sorted(txt_f) == ["img_0", "img_1", "img_2"]
+    assert len(img_f["img_0"]) == 1000 and len(txt_f["img_0"]) == cfg.dim
+    oracle.eval()
+    with torch.no_grad():
+        h = oracle.bert(data["text"], attention_mask=data["text_mask"])[0][:, -1]
+        r = oracle.resnet(data["image"])
+    assert rel(torch.tensor([txt_f[f"img_{i}"] for i in range(3)]), h) < 2e-2
+    assert rel(torch.tensor([img_f[f"img_{i}"] for i in range(3)]), r) < 3e-2
