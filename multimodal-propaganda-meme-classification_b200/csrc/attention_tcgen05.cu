@@ -202,178 +202,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p)
   }
 }
 
-// ------------------------------------------------------------------------------------------ backward
-__global__ void __launch_bounds__(128, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
-                const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;
-  uint8_t* sV = sK + ATT_TILE_BYTES;
-  uint8_t* sdO = sV + ATT_TILE_BYTES;
-  uint8_t* sP = sdO + ATT_TILE_BYTES;       // 32 KB, P (dropped) as bf16
-  uint8_t* sdS = sP + 2 * ATT_TILE_BYTES;   // 32 KB, dS * scale as bf16
-  float* sBias = reinterpret_cast<float*>(sdS + 2 * ATT_TILE_BYTES);
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + ATT_T);
-  uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid == 0) {
-    tma_prefetch_desc(&tma_qkv);
-    tma_prefetch_desc(&tma_do);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_mma, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t t_S = tmem, t_dP = tmem + 128;               // phase 1
-  const uint32_t t_dV = tmem, t_dK = tmem + 64, t_dQ = tmem + 128;  // phase 2 (reuses the columns)
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-
-  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-  const uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);  // A^T (MN-major) x B (MN-major)
-  const uint32_t idesc_nt = umma_idesc_bf16(128, 64, 0, 1);
-  const bool use_drop = p.p_drop > 0.f;
-
-  uint32_t load_phase = 0;
-  const int items = p.B * p.H;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int b = item / p.H, h = item - b * p.H;
-    if (tid == 0) {
-      mbar_expect_tx(bar_load, 4 * ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tma_qkv, bar_load, h * ATT_D, 0, b);
-      tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, 0, b);
-      tma_load_3d(sV, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, 0, b);
-      tma_load_3d(sdO, &tma_do, bar_load, h * ATT_D, 0, b);
-    }
-    sBias[tid] = tid < p.S ? (p.key_bias ? p.key_bias[b * p.S + tid] * LOG2E : 0.f) : -INFINITY;
-    // delta_r = sum_d dO[r,d] * O[r,d]; lse of this query row (rows beyond S contribute nothing)
-    const bool row_ok = tid < p.S;
-    float delta = 0.f, lse_l2 = INFINITY;
-    if (row_ok) {
-      const long long off = (static_cast<long long>(b) * p.S + tid) * p.D + h * ATT_D;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float a[8], g[8];
-        load8(p.o_in + off + q * 8, a);
-        load8(p.do_in + off + q * 8, g);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) delta = fmaf(a[i], g[i], delta);
-      }
-      lse_l2 = p.lse[static_cast<long long>(item) * p.S + tid] * LOG2E;
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(bar_load, load_phase);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(t_S, umma_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024), umma_desc_sw128(smem_u32(sK) + k * 32, 16, 1024),
-                  idesc_s, k > 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(t_dP, umma_desc_sw128(smem_u32(sdO) + k * 32, 16, 1024),
-                  umma_desc_sw128(smem_u32(sV) + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(bar_mma);
-    }
-    load_phase ^= 1;
-    mbar_wait(bar_mma, 0);
-    tc_fence_after_sync();
-
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t vs[32], vp[32];
-      tmem_ld32(t_S + lane_addr + c * 32, vs);
-      tmem_ld32(t_dP + lane_addr + c * 32, vp);
-      tmem_ld_wait();
-      float pd[32], ds[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float prob = exp2f(fmaf(__uint_as_float(vs[i]), p.scale_log2, sBias[c * 32 + i]) - lse_l2);
-        pd[i] = prob;
-        ds[i] = __uint_as_float(vp[i]);
-      }
-      if (use_drop) {
-        const uint32_t keep = dropout_keep32(p.seed, (static_cast<uint64_t>(item) * ATT_T + tid) * 4 + c,
-                                             p.drop_threshold >> 16);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float m = (keep >> i) & 1 ? p.inv_keep : 0.f;
-          const float prob = pd[i];
-          pd[i] = prob * m;                                   // dropped probs (for dV)
-          ds[i] = prob * (ds[i] * m - delta) * p.scale;       // dS
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ds[i] = pd[i] * (ds[i] - delta) * p.scale;
-      }
-      store_row32_sw128(sP, tid, c * 32, pd);
-      store_row32_sw128(sdS, tid, c * 32, ds);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after_sync();
-      // dV[key, d] = sum_q P[q, key] dO[q, d]     A = P^T: MN-major (64-key atoms = the two blocks), K = query rows
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(t_dV, umma_desc_sw128(smem_u32(sP) + k * 2048, ATT_TILE_BYTES, 1024),
-                  umma_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024), idesc_tt, k > 0);
-      // dK[key, d] = sum_q dS[q, key] Q[q, d]
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(t_dK, umma_desc_sw128(smem_u32(sdS) + k * 2048, ATT_TILE_BYTES, 1024),
-                  umma_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024), idesc_tt, k > 0);
-      // dQ[q, d] = sum_key dS[q, key] K[key, d]   A = dS K-major, B = K MN-major
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(t_dQ, umma_desc_sw128(smem_u32(sdS) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
-                  umma_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_nt, k > 0);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 1);
-    tc_fence_after_sync();
-
-    __nv_bfloat16* grow = p.dqkv + (static_cast<long long>(b) * p.S + tid) * (3 * p.D) + h * ATT_D;
-#pragma unroll 1
-    for (int which = 0; which < 3; ++which) {
-      const uint32_t t_src = which == 0 ? t_dQ : (which == 1 ? t_dK : t_dV);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_src + lane_addr + c * 32, v);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-            o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-            o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-            o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-            *reinterpret_cast<uint4*>(grow + which * p.D + c * 32 + q * 8) = o;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after_sync();
-    tmem_dealloc<256>(tmem);
-  }
-}
-
 // ------------------------------------------------------------------------------------------ S > 128
 // Longer sequences (the reference pads to 512 tokens, example_scripts/Multimodal_example_task2C.txt:14) run the same
 // tile maths over several 128-key tiles.  Forward: two passes over the key tiles (pass 1: row maxima; pass 2:
@@ -1146,10 +974,13 @@ attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------ S <= 128, backward (v2)
-// Same idea for one-tile sequences (the text towers at 128 tokens): 256 threads so that two warps per TMEM lane quarter
-// split the key columns of P / dS and the three output tiles, and a two-stage shared-memory ring so the next head's
-// Q / K / V / dO arrive while the current head computes (the first version above is single-buffered, 128 threads,
-// one CTA per SM: every TMA / MMA latency was exposed: 199 us at B=256, H=12, S=128).
+// One-tile sequences (the text towers at 128 tokens): recompute S and dP = dO V^T on the tensor core, P = exp(S - LSE),
+// dS = P o (dP - delta), then dV = P^T dO, dK = dS^T Q, dQ = dS K -- the transposed operands are the SAME smem tiles
+// read through MN-major UMMA descriptors.  256 threads so that two warps per TMEM lane quarter split the key columns of
+// P / dS and the three output tiles; a two-stage shared-memory ring so the next head's Q / K / V / dO arrive while the
+// current head computes; the next head's score MMAs are issued right behind this head's gradient MMAs; gradient tiles
+// leave through swizzled staging + TMA stores.  (The first version -- 128 threads, single-buffered, per-thread row
+// stores -- exposed every TMA / MMA latency: 199 us at B=256, H=12, S=128; this one: 150 us.)
 constexpr int ATT_BWD1_SMEM = 12 * ATT_TILE_BYTES + 2 * ATT_T * 4 + 64 + 1024;
 __global__ void __launch_bounds__(256, 1)
 attn_bwd1_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
@@ -1493,9 +1324,7 @@ B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, cons
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    e = cudaFuncSetAttribute(attn_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
