@@ -24,10 +24,13 @@
 
 namespace b200 {
 
-template <int BN>
+// CTAS = 2: a CTA pair (cluster of two, cta_group::2) computes a 256 x BN tile with ONE MMA stream -- each CTA stages its
+// own 128 rows of A and only HALF of the B tile, so the tensor core's shared-memory reads per FLOP drop by a third
+// (the single-CTA 128 x 256 tile needs 96 B/clk of the 128 B/clk shared-memory port at full MMA rate).
+template <int BN, int CTAS = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // ring depth that fits next to `nbuf` staging boxes per epilogue warp and the barrier block
@@ -38,12 +41,14 @@ struct GemmCfg {
   }
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
+  constexpr bool PAIR = CTAS == 2;
+  const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   const int STAGES = p.num_stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -66,29 +71,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], CTAS * GEMM_EPI_WARPS);   // pair: the leader's copy collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // both CTAs' barriers exist before anything may signal them remotely
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = p.m_tiles * p.n_tiles;
+  // work units: output tiles (single CTA) or pairs of vertically adjacent tiles (CTA pair: rank r takes tile 2u + r)
+  const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int tiles_mn = m_units * p.n_tiles;
   const int num_work = tiles_mn * p.splits;
+  const int w_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int w_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = w_first; w < num_work; w += w_step) {
         const int split = w / tiles_mn;
         const int t = w - split * tiles_mn;
-        const int m_blk = t / p.n_tiles;
-        const int n_blk = t - m_blk * p.n_tiles;
+        const int m_unit = t / p.n_tiles;
+        const int n_blk = t - m_unit * p.n_tiles;
+        const int m_blk = PAIR ? 2 * m_unit + cta_rank : m_unit;
         const int k_begin = split * p.k_iters_per_split;
         const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
         int a_n0 = 0, a_p0 = 0, a_q0 = 0;   // first output pixel of this M tile (im2col A operand)
@@ -109,8 +123,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             int atoms = (p.N - n_blk * BN + 63) / 64;
             atoms = atoms > BN / 64 ? BN / 64 : atoms;
             mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + atoms * 8192);
-          } else {
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          } else if (!PAIR || cta_rank == 0) {
+            mbar_expect_tx(&full_bar[stage], CTAS * Cfg::STAGE_BYTES);   // pair: both CTAs' loads count on the leader
+          }
+          if constexpr (PAIR) {
+            // (matrix operands only: the convolution shapes stay on the single-CTA kernel)
+            const int n0 = n_blk * BN + cta_rank * (BN / 2);
+            if (!p.a_mn) {
+              tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+            } else {
+#pragma unroll
+              for (int j = 0; j < GEMM_BM / 64; ++j)
+                tma_load_2d_pair(sa + j * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + j * 64, kb * GEMM_BK);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_pair(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_2d_pair(sb + j * 8192, &tma_b, &full_bar[stage], n0 + j * 64, kb * GEMM_BK);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
           }
           if (p.a_im2col) {
             const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
@@ -154,8 +188,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, p.a_mn, p.b_mn);
+    if (lane == 0 && cta_rank == 0) {     // pair: only the leader issues (and commits to both CTAs' barriers)
+      const uint32_t idesc = umma_idesc_bf16(CTAS * GEMM_BM, BN, p.a_mn, p.b_mn);
       // K-major: 16-element k step = 32 B inside the swizzle row; 8-row groups 1024 B apart.
       // MN-major: 16-element k step = two 8-k-row groups = 2048 B; 64-wide MN atoms one 8 KB box apart.
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
@@ -164,7 +198,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = w_first; w < num_work; w += w_step) {
         const int split = w / tiles_mn;
         const int k_begin = split * p.k_iters_per_split;
         const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
@@ -180,12 +214,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
             const uint64_t da = umma_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = umma_desc_sw128(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_bf16_pair(d_tmem, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -227,12 +264,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint4 sv[SIDE_REGS];
     // tile coordinates advance by a constant (gridDim.x tiles) per round: no integer divisions on the prefetch path
     // (side inputs exist only for the bf16 store modes, which never split K: tile index == w)
-    const int step_m = static_cast<int>(gridDim.x) / p.n_tiles, step_n = static_cast<int>(gridDim.x) % p.n_tiles;
-    auto advance = [&](int& mb, int& nb) {
-      mb += step_m;
+    const int step_m = w_step / p.n_tiles, step_n = w_step % p.n_tiles;
+    auto advance = [&](int& mu, int& nb) {   // in work units (a unit = one tile, or one tile pair)
+      mu += step_m;
       nb += step_n;
-      if (nb >= p.n_tiles) { nb -= p.n_tiles; ++mb; }
+      if (nb >= p.n_tiles) { nb -= p.n_tiles; ++mu; }
     };
+    auto tile_row = [&](int mu) { return PAIR ? 2 * mu + cta_rank : mu; };
     auto side_fetch = [&](int mb, int nb, int b) {
       const int col = nb * BN + half * HALF_COLS + b * BOX_W + (lane % CPR) * 8;
       const long long r0 = static_cast<long long>(mb) * GEMM_BM + quarter * 32 + lane / CPR;
@@ -262,11 +300,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         st_s[b][0] = st_s[b][1] = st_q[b][0] = st_q[b][1] = 0.f;
       }
     };
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = w_first; w < num_work; w += w_step) {
       const int split = w / tiles_mn;
       const int t = w - split * tiles_mn;
-      const int m_blk = t / p.n_tiles;
-      const int n_blk = t - m_blk * p.n_tiles;
+      const int m_unit = t / p.n_tiles;
+      const int n_blk = t - m_unit * p.n_tiles;
+      const int m_blk = tile_row(m_unit);
       if constexpr (EPI == EPI_STORE_STATS) {
         if (n_blk != st_nblk) { stats_flush(); st_nblk = n_blk; }
       }
@@ -309,21 +348,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 // next box of this tile, or the first box of this CTA's next tile
                 const bool more = b + 1 < BOXES && n_blk * BN + half * HALF_COLS + (b + 1) * BOX_W < p.N;
-                int m1 = m_blk, n1 = n_blk;
+                int m1 = m_unit, n1 = n_blk;
                 advance(m1, n1);
                 {
                   // ... and pull this box of the tile two rounds ahead into L2 (one 128-byte line per lane = one
                   // box row): the register prefetch above then hits L2 instead of waiting ~2 us on HBM.
                   int m2 = m1, n2 = n1;
                   advance(m2, n2);
-                  const long long r = static_cast<long long>(m2) * GEMM_BM + quarter * 32 + lane;
+                  const long long r = static_cast<long long>(tile_row(m2)) * GEMM_BM + quarter * 32 + lane;
                   const int col = n2 * BN + box_col_in_tile;
-                  if (w + 2 * static_cast<int>(gridDim.x) < num_work && r < p.M && col < p.N)
+                  if (w + 2 * w_step < num_work && r < p.M && col < p.N)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(side + r * side_ld + col));
                 }
                 if (more) { side_fetch(m_blk, n_blk, b + 1); sv_tile = w; sv_box = b + 1; }
-                else if (w + static_cast<int>(gridDim.x) < num_work) {
-                  side_fetch(m1, n1, 0); sv_tile = w + gridDim.x; sv_box = 0;
+                else if (w + w_step < num_work) {
+                  side_fetch(tile_row(m1), n1, 0); sv_tile = w + w_step; sv_box = 0;
                 }
                 __syncwarp();
               }
@@ -493,7 +532,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if constexpr (EPI == EPI_STORE_STATS) stats_flush();
@@ -503,22 +544,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // no CTA may retire while its peer can still signal / read it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
 
-// Launch one (BN, EPI) instantiation.  Shared memory split: `stages` ring slots + `nbuf` staging boxes per epilogue warp.
-template <int BN, int EPI>
+// Launch one (BN, EPI, CTAS) instantiation.  Shared memory split: `stages` ring slots + `nbuf` staging boxes per
+// epilogue warp.  CTAS == 2 launches clusters of two CTAs (cudaLaunchKernelEx, cluster dimension 2).
+template <int BN, int EPI, int CTAS = 1>
 static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                             GemmParams p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GEMM_SMEM_TOTAL + 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
@@ -527,10 +571,42 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
   const int k_per_tile = p.k_iters_per_split;
   p.nbuf = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 0 : (k_per_tile >= 8 ? 1 : 2);   // fp32 modes do not stage
   p.num_stages = Cfg::stages_for(p.nbuf);
-  static_assert(GemmCfg<BN>::stages_for(2) >= 2, "ring too shallow");
-  gemm_bf16_kernel<BN, EPI><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL + 1024, stream>>>(ta, tb, to, to2, p);
+  static_assert(GemmCfg<BN, CTAS>::stages_for(2) >= 2, "ring too shallow");
+  if constexpr (CTAS == 1) {
+    gemm_bf16_kernel<BN, EPI, 1><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL + 1024, stream>>>(ta, tb, to, to2, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid & ~1), 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL + 1024;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, 2>, ta, tb, to, to2, p);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? B200MM_OK : static_cast<int>(e);
+}
+
+// CTA-pair instantiations (BN = 256 only; matrix operands, the text / ViT tower shapes)
+template <int BN>
+int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
+                     const GemmParams& p, int grid, cudaStream_t stream) {
+  switch (p.epi) {
+    case EPI_STORE:
+      if (p.p_drop > 0.f) return launch_gemm_inst<BN, EPI_STORE_DROP, 2>(ta, tb, to, to2, p, grid, stream);
+      return launch_gemm_inst<BN, EPI_STORE, 2>(ta, tb, to, to2, p, grid, stream);
+    case EPI_GELU: return launch_gemm_inst<BN, EPI_GELU, 2>(ta, tb, to, to2, p, grid, stream);
+    case EPI_DGELU: return launch_gemm_inst<BN, EPI_DGELU, 2>(ta, tb, to, to2, p, grid, stream);
+    case EPI_F32_ATOMIC: return launch_gemm_inst<BN, EPI_F32_ATOMIC, 2>(ta, tb, to, to2, p, grid, stream);
+    default: return B200MM_ERR_BAD_ARG;
+  }
 }
 
 template <int BN>

@@ -18,6 +18,7 @@
 // example_scripts/Multimodal_example_task2C.txt:172-197.
 #include "gemm_params.cuh"
 #include "device_utils.cuh"
+#include <cstdlib>
 
 namespace b200 {
 // one translation unit per tile width (gemm_bn64.cu / gemm_bn128.cu / gemm_bn256.cu) so they compile in parallel
@@ -27,6 +28,8 @@ int launch_gemm_bn128(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&
                       const GemmParams&, int, cudaStream_t);
 int launch_gemm_bn256(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
                       const GemmParams&, int, cudaStream_t);
+int launch_gemm_bn256_pair(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&,
+                           const GemmParams&, int, cudaStream_t);
 }  // namespace b200
 
 
@@ -105,6 +108,15 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   p.inv_keep = 1.f / (1.f - p_drop);
   p.seed = seed;
 
+  // CTA-pair (cta_group::2) kernel: 256 x 256 tile per cluster of two CTAs, for the big matrix-operand shapes of the
+  // text / ViT towers (B200MM_GEMM_PAIR=0 switches it off)
+  static const bool pair_enabled = [] {
+    const char* e = std::getenv("B200MM_GEMM_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool pair = pair_enabled && bn == 256 && !A.im2col && !B.im2col && col_stats == nullptr && !p.accumulate &&
+                    (epi == EPI_STORE || epi == EPI_GELU || epi == EPI_DGELU || epi == EPI_F32_ATOMIC) &&
+                    p.m_tiles >= 2 && p.k_iters_per_split >= 8 && (dev.num_sms & 1) == 0;
   CUtensorMap ta, tb;
   int rc;
   if (A.im2col)   rc = make_tmap_im2col_bf16(&ta, A.ptr, cg.N, cg.H, cg.W, cg.C, cg.ksize, cg.stride, cg.pad, GEMM_BM);
@@ -112,7 +124,7 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   else            rc = make_tmap_2d_bf16(&ta, A.ptr, M, K, A.ld * 2, 64, GEMM_BK);
   if (rc) return rc;
   if (B.im2col)   rc = make_tmap_im2col_bf16(&tb, B.ptr, cg.N, cg.H, cg.W, cg.C, cg.ksize, cg.stride, cg.pad, GEMM_BK);
-  else if (!B.mn) rc = make_tmap_2d_bf16(&tb, B.ptr, K, N, B.ld * 2, GEMM_BK, bn);
+  else if (!B.mn) rc = make_tmap_2d_bf16(&tb, B.ptr, K, N, B.ld * 2, GEMM_BK, pair ? bn / 2 : bn);
   else            rc = make_tmap_2d_bf16(&tb, B.ptr, N, K, B.ld * 2, 64, GEMM_BK);
   if (rc) return rc;
 
@@ -129,9 +141,14 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
     }
   }
 
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pair) {
+    const int units = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+    const int pgrid = 2 * units < dev.num_sms ? 2 * units : dev.num_sms;
+    return launch_gemm_bn256_pair(ta, tb, to, to2, p, pgrid, s);
+  }
   const int num_work = p.m_tiles * p.n_tiles * p.splits;
   const int grid = num_work < dev.num_sms ? num_work : dev.num_sms;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (bn) {
     case 64: return launch_gemm_bn64(ta, tb, to, to2, p, grid, s);
     case 128: return launch_gemm_bn128(ta, tb, to, to2, p, grid, s);

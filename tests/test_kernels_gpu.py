@@ -664,3 +664,35 @@ def test_head_bn_focal(ops, cuda_device, B):
     lg2, loss2, _, _ = ops.head_bn_focal(feat, W, bias, g, be, rm2, rv2, labels, train=False, bn_train=False)
     y2 = F.batch_norm(feat.float() @ W.t() + bias, rm2, rv2, g, be, False, 0.1, 1e-5).squeeze(1)
     assert rel(lg2, y2) < 1e-4
+
+
+# ------------------------------------------------------------------ CTA-pair (cta_group::2) GEMM
+@pytest.mark.parametrize("M,N,K", [(2048, 768, 768), (1157, 768, 1024), (4096, 3072, 768), (3000, 2304, 768)])
+def test_gemm_cta_pair_shapes(ops, cuda_device, M, N, K):
+    """Shapes big enough for the 256 x 256 CTA-pair kernel (incl. an odd number of 128-row tiles: the second CTA of
+    the last pair works on a phantom tile): every operand layout and epilogue it serves, vs fp32 torch."""
+    torch.manual_seed(17)
+    dev = cuda_device
+    x = torch.randn(M, K, device=dev).to(bf16)
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).to(bf16)
+    b = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev).to(bf16)
+    ref = x.float() @ w.float().t() + b
+    assert rel(ops.linear_fwd(x, w, b), ref) < 1e-2
+    assert rel(ops.linear_fwd(x, w, b, residual=r), ref + r.float()) < 1e-2
+    assert rel(ops.linear_fwd(x, w, b, residual=r, p_drop=0.0), ref + r.float()) < 1e-2
+    z, a = ops.linear_gelu_fwd(x, w, b)
+    assert rel(z, ref) < 1e-2 and rel(a, F.gelu(ref)) < 1e-2
+    dy = torch.randn(M, N, device=dev).to(bf16)
+    assert rel(ops.linear_dgrad(dy, w), dy.float() @ w.float()) < 1e-2
+    zz = torch.randn(M, K, device=dev).to(bf16)
+    zf = zz.float().requires_grad_(True)
+    F.gelu(zf).sum().backward()
+    assert rel(ops.linear_dgrad(dy, w, gelu_z=zz), (dy.float() @ w.float()) * zf.grad) < 1e-2
+    dw = torch.zeros(N, K, device=dev)
+    ops.linear_wgrad(dy, x, dw)
+    assert rel(dw, dy.float().t() @ x.float()) < 1e-3
+    # dropout epilogue keeps the expected scale
+    yd = ops.linear_fwd(x, w, b, p_drop=0.25, seed=3)
+    kept = (yd != 0).float().mean().item()
+    assert abs(kept - 0.75) < 0.02
