@@ -25,11 +25,21 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int M, int N, i
   const long long r1 = min(r0 + rows_per_cta, static_cast<long long>(M));
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (col < N) {
-    for (long long r = r0 + ty; r < r1; r += 8) {
-      float v[8];
-      load8(x + r * ld + col, v);
+    constexpr int U = 8;   // independent 16-byte loads in flight per thread (a single one left the loop latency-bound)
+    for (long long r = r0 + ty; r < r1; r += 8 * U) {
+      uint4 raw[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + 8 * u;
+        raw[u] = rr < r1 ? __ldg(reinterpret_cast<const uint4*>(x + rr * ld + col)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
     }
   }
 #pragma unroll
