@@ -99,6 +99,7 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long M, int C, int row
 
 // out = act(x * scale + shift (+ residual)); CTA 0 also records mean / rstd and updates the running statistics
 // (momentum update with the unbiased variance, as nn.BatchNorm2d does).
+template <bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual, long long M, int C,
                 int rows_per_cta, const float* __restrict__ sum, const float* __restrict__ sumsq,
@@ -129,7 +130,9 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread and stream (the loop is latency-bound otherwise)
+  // independent 16-byte loads in flight per thread: 8 on the single input stream, 4 + 4 with a residual (what is
+  // outstanding per SM sets the bandwidth of this pass: 65 KB gave 4.4 TB/s)
+  constexpr int U = HAS_RES ? 4 : 8;
   for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
     uint4 rx[U], rr[U];
 #pragma unroll
@@ -137,8 +140,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
       const long long row = r + static_cast<long long>(u) * rpp;
       const bool ok = row < r1;
       rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + row * C + g * 8)) : make_uint4(0, 0, 0, 0);
-      rr[u] = (ok && residual != nullptr) ? __ldg(reinterpret_cast<const uint4*>(residual + row * C + g * 8))
-                                          : make_uint4(0, 0, 0, 0);
+      rr[u] = (HAS_RES && ok) ? __ldg(reinterpret_cast<const uint4*>(residual + row * C + g * 8))
+                              : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -165,6 +168,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 }
 
 // eval-mode BN: running statistics instead of batch statistics
+template <bool HAS_RES>
 __global__ void __launch_bounds__(256)
 bn_eval_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual, long long M, int C,
                int rows_per_cta, const float* __restrict__ running_mean, const float* __restrict__ running_var,
@@ -181,7 +185,9 @@ bn_eval_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = min(r0 + rows_per_cta, M);
-  constexpr int U = 4;  // independent 16-byte loads in flight per thread and stream (the loop is latency-bound otherwise)
+  // independent 16-byte loads in flight per thread: 8 on the single input stream, 4 + 4 with a residual (what is
+  // outstanding per SM sets the bandwidth of this pass: 65 KB gave 4.4 TB/s)
+  constexpr int U = HAS_RES ? 4 : 8;
   for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
     uint4 rx[U], rr[U];
 #pragma unroll
@@ -189,8 +195,8 @@ bn_eval_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
       const long long row = r + static_cast<long long>(u) * rpp;
       const bool ok = row < r1;
       rx[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + row * C + g * 8)) : make_uint4(0, 0, 0, 0);
-      rr[u] = (ok && residual != nullptr) ? __ldg(reinterpret_cast<const uint4*>(residual + row * C + g * 8))
-                                          : make_uint4(0, 0, 0, 0);
+      rr[u] = (HAS_RES && ok) ? __ldg(reinterpret_cast<const uint4*>(residual + row * C + g * 8))
+                              : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -709,10 +715,16 @@ B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long lo
   const float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;
   bn_stats_kernel<<<rgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), M, C, rrows, scratch);
   B200MM_CHECK_LAUNCH();
-  bn_apply_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
-                                       static_cast<const __nv_bfloat16*>(residual), M, C, rows, fin, fin + C,
-                                       gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out,
-                                       rstd_out, running_mean, running_var, nullptr);
+  if (residual != nullptr)
+    bn_apply_kernel<true><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+                                               static_cast<const __nv_bfloat16*>(residual), M, C, rows, fin, fin + C,
+                                               gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out),
+                                               mean_out, rstd_out, running_mean, running_var, nullptr);
+  else
+    bn_apply_kernel<false><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), nullptr, M, C, rows, fin,
+                                                fin + C, gamma, beta, eps, momentum, relu,
+                                                static_cast<__nv_bfloat16*>(out), mean_out, rstd_out, running_mean,
+                                                running_var, nullptr);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -727,10 +739,15 @@ B200MM_API int b200mm_batchnorm_fwd_stats(const void* x, const void* residual, l
   if (!bn_shape_ok(M, C) || col_stats == nullptr) return B200MM_ERR_BAD_ARG;
   int grid;
   const int rows = bn_rows_per_cta(M, C, &grid);
-  bn_apply_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, col_stats,
-      col_stats + C, gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out, rstd_out,
-      running_mean, running_var, relu_mask);
+  if (residual != nullptr)
+    bn_apply_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, col_stats,
+        col_stats + C, gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out, rstd_out,
+        running_mean, running_var, relu_mask);
+  else
+    bn_apply_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), nullptr, M, C, rows, col_stats, col_stats + C, gamma, beta, eps,
+        momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out, rstd_out, running_mean, running_var, relu_mask);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -741,9 +758,14 @@ B200MM_API int b200mm_batchnorm_eval(const void* x, const void* residual, long l
   if (!bn_shape_ok(M, C)) return B200MM_ERR_BAD_ARG;
   int grid;
   const int rows = bn_rows_per_cta(M, C, &grid);
-  bn_eval_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, running_mean,
-      running_var, gamma, beta, eps, relu, static_cast<__nv_bfloat16*>(out));
+  if (residual != nullptr)
+    bn_eval_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, running_mean,
+        running_var, gamma, beta, eps, relu, static_cast<__nv_bfloat16*>(out));
+  else
+    bn_eval_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), nullptr, M, C, rows, running_mean, running_var, gamma, beta, eps, relu,
+        static_cast<__nv_bfloat16*>(out));
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
