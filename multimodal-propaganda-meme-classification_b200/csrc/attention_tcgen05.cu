@@ -973,6 +973,260 @@ attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
   }
 }
 
+// ------------------------------------------------------------------------------------------ 256 < S <= 384, backward
+// Three 128-row tiles (ViT-L/14: 257 tokens).  Same whole-head-per-CTA scheme, but 3 dQ accumulators + dK_j + dV_j +
+// S + dP would need 576 TMEM columns and P + dS next to 12 operand tiles 256 KB of shared memory, so each (i, j)
+// pair runs in two tensor-core phases that SHARE storage:  S -> P (kept packed in registers, staged for dV) | then dP
+// into S's columns and dS into P's buffer.   TMEM: S/dP 128 | dK_j dV_j 128 | dQ_0..2 192 = 448 columns;
+// shared memory: 12 operand tiles + one 32 KB P/dS buffer = 224 KB.
+constexpr int ATT_BWD3_SMEM = 14 * ATT_TILE_BYTES + 3 * ATT_T * 4 + 64 + 1024;
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_tmem3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
+                      const __grid_constant__ CUtensorMap tma_dqkv, const AttnParams p) {
+  constexpr int NT = 3;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // NT tiles each
+  uint8_t* sK = sQ + NT * ATT_TILE_BYTES;
+  uint8_t* sV = sK + NT * ATT_TILE_BYTES;
+  uint8_t* sdO = sV + NT * ATT_TILE_BYTES;
+  uint8_t* sP = sdO + NT * ATT_TILE_BYTES;           // 32 KB: P, then dS (in place), then the staged dK_j | dV_j
+  float* sBias = reinterpret_cast<float*>(sP + 2 * ATT_TILE_BYTES);   // [NT * 128]
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + NT * ATT_T);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+  if (tid == 0) {
+    tma_prefetch_desc(&tma_qkv);
+    tma_prefetch_desc(&tma_do);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_S = tmem, t_dK = tmem + 128, t_dV = tmem + 192, t_dQ = tmem + 256;   // dQ_i at + 64 i
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_tt = umma_idesc_bf16(128, 64, 1, 1);
+  const uint32_t idesc_nt = umma_idesc_bf16(128, 64, 0, 1);
+  const bool use_drop = p.p_drop > 0.f;
+  constexpr int s_pad = NT * ATT_T;
+
+  auto issue_s = [&](int i, int j) {   // S = Q_i K_j^T (single thread; no commit)
+    const uint32_t q = smem_u32(sQ + i * ATT_TILE_BYTES), k = smem_u32(sK + j * ATT_TILE_BYTES);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      umma_bf16(t_S, umma_desc_sw128(q + kk * 32, 16, 1024), umma_desc_sw128(k + kk * 32, 16, 1024), idesc_s, kk > 0);
+  };
+
+  uint32_t ph_load = 0, ph_mma = 0;
+  const int items = p.B * p.H;
+  for (int bh = blockIdx.x; bh < items; bh += gridDim.x) {
+    const int b = bh / p.H, h = bh - b * p.H;
+    tc_fence_before_sync();
+    __syncthreads();   // previous head: all shared-memory / TMEM readers are done
+    if (tid == 0) {
+      tma_store_wait_read<0>();   // its dQ tiles (staged in the Q region) have left shared memory
+      mbar_expect_tx(bar_load, 4 * NT * ATT_TILE_BYTES);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        tma_load_3d(sQ + t * ATT_TILE_BYTES, &tma_qkv, bar_load, h * ATT_D, t * ATT_T, b);
+        tma_load_3d(sK + t * ATT_TILE_BYTES, &tma_qkv, bar_load, p.D + h * ATT_D, t * ATT_T, b);
+        tma_load_3d(sV + t * ATT_TILE_BYTES, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, t * ATT_T, b);
+        tma_load_3d(sdO + t * ATT_TILE_BYTES, &tma_do, bar_load, h * ATT_D, t * ATT_T, b);
+      }
+    }
+    for (int k = tid; k < NT * ATT_T; k += 256)
+      sBias[k] = k < p.S ? (p.key_bias ? p.key_bias[b * p.S + k] * LOG2E : 0.f) : -INFINITY;
+    float delta[NT], lse_l2[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      delta[i] = 0.f;
+      lse_l2[i] = INFINITY;
+      const int qrow = i * ATT_T + row;
+      if (qrow < p.S) {
+        const long long off = (static_cast<long long>(b) * p.S + qrow) * p.D + h * ATT_D;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float a[8], g[8];
+          load8(p.o_in + off + q * 8, a);
+          load8(p.do_in + off + q * 8, g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) delta[i] = fmaf(a[e], g[e], delta[i]);
+        }
+        lse_l2[i] = p.lse[static_cast<long long>(bh) * p.S + qrow] * LOG2E;
+      }
+    }
+    __syncthreads();   // sBias visible
+    if (tid == 0) {
+      mbar_wait(bar_load, ph_load);
+      tc_fence_after_sync();
+      issue_s(0, 0);
+      umma_commit(bar_mma);
+    }
+    ph_load ^= 1;
+
+#pragma unroll 1
+    for (int pair = 0; pair < NT * NT; ++pair) {
+      const int j = pair / NT, i = pair - j * NT;   // key tile outer, query tile inner
+      const float dl = i == 0 ? delta[0] : (i == 1 ? delta[1] : delta[2]);
+      const float ll = i == 0 ? lse_l2[0] : (i == 1 ? lse_l2[1] : lse_l2[2]);
+      // ---- phase 1: S ready -> P (packed copy stays in registers for phase 2), staged for dV
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+      uint32_t prob_pk[2][16];   // undropped probabilities of this thread's 64 key columns, bf16x2
+      uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        uint32_t vs[32];
+        tmem_ld32(t_S + lane_addr + c * 32, vs);
+        tmem_ld_wait();
+        float pd[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          pd[e] = fast_exp2(fmaf(__uint_as_float(vs[e]), p.scale_log2, sBias[j * ATT_T + c * 32 + e]) - ll);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) prob_pk[cc][e] = pack_bf16x2(pd[2 * e], pd[2 * e + 1]);
+        if (use_drop) {
+          keep[cc] = dropout_keep32(p.seed, drop_chunk(bh, s_pad, i * ATT_T + row, j * ATT_T + c * 32),
+                                    p.drop_threshold >> 16);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) pd[e] = (keep[cc] >> e) & 1 ? pd[e] * p.inv_keep : 0.f;
+        }
+        store_row32_sw128(sP, row, c * 32, pd);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();   // P staged; S fully read (its columns may take dP now)
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t g = smem_u32(sdO + i * ATT_TILE_BYTES), v = smem_u32(sV + j * ATT_TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)   // dP = dO_i V_j^T into S's columns
+          umma_bf16(t_S, umma_desc_sw128(g + kk * 32, 16, 1024), umma_desc_sw128(v + kk * 32, 16, 1024), idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dV_j (+)= P^T dO_i
+          umma_bf16(t_dV, umma_desc_sw128(smem_u32(sP) + kk * 2048, ATT_TILE_BYTES, 1024),
+                    umma_desc_sw128(g + kk * 2048, 8192, 1024), idesc_tt, (i > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(bar_mma);
+      }
+      // ---- phase 2: dP ready (and P consumed) -> dS in place of P
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after_sync();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
+        uint32_t vp[32];
+        tmem_ld32(t_S + lane_addr + c * 32, vp);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float2 pr = unpack_bf16x2(prob_pk[cc][e]);
+          const float m0 = (keep[cc] >> (2 * e)) & 1 ? (use_drop ? p.inv_keep : 1.f) : 0.f;
+          const float m1 = (keep[cc] >> (2 * e + 1)) & 1 ? (use_drop ? p.inv_keep : 1.f) : 0.f;
+          ds[2 * e] = pr.x * (__uint_as_float(vp[2 * e]) * m0 - dl) * p.scale;
+          ds[2 * e + 1] = pr.y * (__uint_as_float(vp[2 * e + 1]) * m1 - dl) * p.scale;
+        }
+        store_row32_sw128(sP, row, c * 32, ds);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();   // dS staged; dP fully read
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t q = smem_u32(sQ + i * ATT_TILE_BYTES), k = smem_u32(sK + j * ATT_TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dK_j (+)= dS^T Q_i
+          umma_bf16(t_dK, umma_desc_sw128(smem_u32(sP) + kk * 2048, ATT_TILE_BYTES, 1024),
+                    umma_desc_sw128(q + kk * 2048, 8192, 1024), idesc_tt, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // dQ_i (+)= dS K_j
+          umma_bf16(t_dQ + i * 64,
+                    umma_desc_sw128(smem_u32(sP) + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                    umma_desc_sw128(k + kk * 2048, 8192, 1024), idesc_nt, (j > 0 || kk > 0) ? 1u : 0u);
+        // next pair's scores right behind (S / dP columns are free; in-order tensor pipe)
+        if (pair + 1 < NT * NT) issue_s((pair + 1) % NT, (pair + 1) / NT);
+        umma_commit(bar_mma);
+      }
+      if (i == NT - 1) {
+        // ---- key tile j finished: drain dK_j (half 0) / dV_j (half 1) through the P buffer
+        mbar_wait(bar_mma, ph_mma);     // (also the next pair's S; NOT consumed twice: see below)
+        tc_fence_after_sync();
+        const uint32_t t_src = half == 0 ? t_dK : t_dV;
+        uint8_t* dst = sP + half * ATT_TILE_BYTES;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_src + lane_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(dst + sw128_off(row, c * 4 + q)) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          tma_store_3d(&tma_dqkv, sP, p.D + h * ATT_D, j * ATT_T, b);
+          tma_store_3d(&tma_dqkv, sP + ATT_TILE_BYTES, 2 * p.D + h * ATT_D, j * ATT_T, b);
+          tma_store_commit();
+          tma_store_wait_read<0>();   // the P buffer is rewritten by the next pair's phase 1
+        }
+        __syncthreads();
+      }
+    }
+    // ---- dQ_0..2: staged in the (now idle) Q tiles, three TMA stores; the last drain waited for every MMA
+    ph_mma ^= 1;   // consume the phase observed (not toggled) by the last drain's wait
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) {
+      uint32_t v[32];
+      tmem_ld32(t_dQ + t * 64 + lane_addr + half * 32, v);
+      tmem_ld_wait();
+      uint8_t* dst = sQ + t * ATT_TILE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+        o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+        o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+        o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+        *reinterpret_cast<uint4*>(dst + sw128_off(row, half * 4 + q)) = o;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) tma_store_3d(&tma_dqkv, sQ + t * ATT_TILE_BYTES, h * ATT_D, t * ATT_T, b);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) tma_store_wait<0>();
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ S <= 128, backward (v2)
 // One-tile sequences (the text towers at 128 tokens): recompute S and dP = dO V^T on the tensor core, P = exp(S - LSE),
 // dS = P o (dP - delta), then dV = P^T dO, dK = dS^T Q, dQ = dS K -- the transposed operands are the SAME smem tiles
@@ -1342,6 +1596,23 @@ B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, cons
     rc = make_tmap_3d_bf16(&tdq2, dqkv, 3 * p.D, S, B, row, row * S, ATT_D, ATT_T);
     if (rc) return rc;
     attn_bwd_tmem_kernel<<<grid, ATT_BWD2_THREADS, ATT_BWD2_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, tdq2, p);
+    B200MM_CHECK_LAUNCH();
+    return B200MM_OK;
+  }
+  if (S > 2 * ATT_T && S <= 3 * ATT_T) {     // three tiles (ViT-L/14): whole head per CTA, two-phase pairs
+    static bool configured3 = false;
+    if (!configured3) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_tmem3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ATT_BWD3_SMEM);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      configured3 = true;
+    }
+    CUtensorMap tdq3;
+    rc = make_tmap_3d_bf16(&tdq3, dqkv, 3 * p.D, S, B, row, row * S, ATT_D, ATT_T);
+    if (rc) return rc;
+    const int items = B * H;
+    const int grid = items < dev.num_sms ? items : dev.num_sms;
+    attn_bwd_tmem3_kernel<<<grid, 256, ATT_BWD3_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, tdq3, p);
     B200MM_CHECK_LAUNCH();
     return B200MM_OK;
   }

@@ -99,7 +99,7 @@ def _attn_ref(qkv, key_bias, B, H, S):
 @pytest.mark.parametrize("B,H,S", [(2, 2, 128), (3, 12, 128), (2, 4, 64), (2, 3, 100), (2, 2, 256), (2, 3, 197),
                                    (1, 4, 512), (2, 2, 300), (3, 2, 257), (2, 2, 384), (5, 12, 197),
                                    # more (batch, head) items than CTAs: the persistent / cross-head pipelined paths
-                                   (40, 12, 128), (30, 12, 197), (26, 12, 64)])
+                                   (40, 12, 128), (30, 12, 197), (26, 12, 64), (20, 16, 257), (2, 2, 300)])
 def test_attention_fwd_bwd(ops, cuda_device, B, H, S):
     torch.manual_seed(3)
     D = H * 64
