@@ -1,17 +1,20 @@
 // Fused multi-head self-attention (head_dim 64, S <= 512) forward and backward on tcgen05 + TMA.
 //
-// One CTA (128 threads) handles one (batch, head) at a time, persistently:
-//   forward :  S = Q K^T (tcgen05.mma, fp32 in TMEM) -> scale + additive key-padding bias -> softmax in
-//              registers (thread r owns query row r: TMEM lane r) -> Philox dropout -> P (bf16) staged in
-//              128B-swizzled smem -> O = P V (tcgen05.mma) -> 1/rowsum -> global.  LSE kept for backward.
+// Persistent CTAs of 256 threads; thread (row, half) owns query row `row` (its TMEM lane) and half of the key columns:
+//   forward :  S = Q K^T for every key tile (tcgen05.mma, fp32 in TMEM) -> scale + additive key-padding bias -> exact
+//              row maximum over all tiles -> P = exp2(S - max) -> Philox dropout -> P (bf16) staged in 128B-swizzled
+//              smem -> O += P V (tcgen05.mma) -> 1/rowsum -> staged tile -> TMA store.  LSE kept for backward.
 //   backward:  recompute S and dP = dO V^T on the tensor core, P = exp(S - LSE), dS = P o (dP - delta),
 //              then dV = P^T dO, dK = dS^T Q, dQ = dS K -- the transposed operands are the SAME smem tiles
 //              read through MN-major UMMA descriptors, nothing is transposed in memory.
+// Kernels by length: forward S <= 384 (all score tiles resident in TMEM) / longer (two-pass); backward S <= 128
+// (pipelined across heads), <= 256 and <= 384 (whole head per CTA, every accumulator in TMEM), longer (two-kind).
 // Q/K/V are read straight out of the fused-QKV projection output [B*S, 3*D] (and dQ/dK/dV written into
 // the matching [B*S, 3*D] gradient) with 3-D TMA boxes, so no head-major re-layout pass exists.
 //
 // Replaces: transformers/models/distilbert/modeling_distilbert.py:126-151
 // (eager_attention_forward: softmax(QK^T * d^-1/2 + mask) -> dropout -> @V) and its autograd backward.
+#include <cstdlib>
 #include "common.cuh"
 #include "device_utils.cuh"
 #include "ptx.cuh"
@@ -63,142 +66,6 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c0, 
     o.z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
     o.w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
     *reinterpret_cast<uint4*>(blk + sw128_off(r, chunk0 + q)) = o;
-  }
-}
-
-// ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(128, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;
-  uint8_t* sV = sK + ATT_TILE_BYTES;
-  uint8_t* sP = sV + ATT_TILE_BYTES;  // 32 KB
-  float* sBias = reinterpret_cast<float*>(sP + 2 * ATT_TILE_BYTES);
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + ATT_T);
-  uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid == 0) {
-    tma_prefetch_desc(&tma_qkv);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_mma, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t t_S = tmem, t_O = tmem + 128;
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-
-  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-  const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-  const bool use_drop = p.p_drop > 0.f;
-
-  uint32_t load_phase = 0;
-  const int items = p.B * p.H;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int b = item / p.H, h = item - b * p.H;
-    if (tid == 0) {
-      mbar_expect_tx(bar_load, 3 * ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tma_qkv, bar_load, h * ATT_D, 0, b);
-      tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, 0, b);
-      tma_load_3d(sV, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, 0, b);
-    }
-    sBias[tid] = tid < p.S ? (p.key_bias ? p.key_bias[b * p.S + tid] * LOG2E : 0.f) : -INFINITY;
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(bar_load, load_phase);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(t_S, umma_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024), umma_desc_sw128(smem_u32(sK) + k * 32, 16, 1024),
-                  idesc_s, k > 0);
-      umma_commit(bar_mma);
-    }
-    load_phase ^= 1;
-    mbar_wait(bar_mma, 0);
-    tc_fence_after_sync();
-
-    // ---- softmax over the 128 key columns of this thread's query row
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_S + lane_addr + c * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[c * 32 + i]));
-    }
-    if (mx == -INFINITY) mx = 0.f;
-    float sum = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_S + lane_addr + c * 32, v);
-      tmem_ld_wait();
-      float x[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        x[i] = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[c * 32 + i]) - mx);
-        sum += x[i];
-      }
-      if (use_drop) {
-        const uint32_t keep = dropout_keep32(p.seed, (static_cast<uint64_t>(item) * ATT_T + tid) * 4 + c,
-                                             p.drop_threshold >> 16);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = (keep >> i) & 1 ? x[i] * p.inv_keep : 0.f;
-      }
-      store_row32_sw128(sP, tid, c * 32, x);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after_sync();
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(t_O,
-                  umma_desc_sw128(smem_u32(sP) + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
-                  umma_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 1);
-    tc_fence_after_sync();
-
-    const float inv_sum = 1.f / sum;
-    const bool row_ok = tid < p.S;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.S + tid) * p.D + h * ATT_D;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_O + lane_addr + c * 32, v);
-      tmem_ld_wait();
-      if (row_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv_sum, __uint_as_float(v[q * 8 + 1]) * inv_sum);
-          o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv_sum, __uint_as_float(v[q * 8 + 3]) * inv_sum);
-          o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv_sum, __uint_as_float(v[q * 8 + 5]) * inv_sum);
-          o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv_sum, __uint_as_float(v[q * 8 + 7]) * inv_sum);
-          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = o;
-        }
-      }
-    }
-    if (row_ok && p.lse) p.lse[static_cast<long long>(item) * p.S + tid] = (mx + log2f(sum)) * LN2;
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after_sync();
-    tmem_dealloc<256>(tmem);
   }
 }
 
@@ -570,7 +437,7 @@ attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
   }
 }
 
-// ------------------------------------------------------------------------------------------ 128 < S <= 384, forward
+// ------------------------------------------------------------------------------------------ S <= 384, forward
 // All score tiles of a query tile stay in TMEM (NT x 128 columns; NT = ceil(S / 128) <= 3), so the forward is ONE pass:
 // Q, every K tile and every V tile arrive with one TMA wave, S_j = Q K_j^T for all j is issued back to back, the exact
 // row maximum is taken over the NT x 128 columns, then P_j = exp2(S_j - max) and O += P_j V_j per key tile.  O
@@ -579,20 +446,24 @@ attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
 // lengths (197, 257 -> NT = 2, 3).  Replaces the two-pass kernel above for these lengths (that one recomputed Q K^T
 // and reloaded K per pass: 299 us -> see profiles/ for the measured time at B=256, H=12, S=197).
 template <int NT>
-__global__ void __launch_bounds__(128, NT <= 2 ? 2 : 1)
-attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
+__global__ void __launch_bounds__(256, NT <= 2 ? 2 : 1)
+attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_out,
+                     const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQP = smem;                              // Q [128 x 64] first, then P [128 x 128] (two swizzled blocks)
+  uint8_t* sQP = smem;                              // Q [128 x 64] first, then P [128 x 128], then the staged O tile
   uint8_t* sK = sQP + 2 * ATT_TILE_BYTES;           // NT tiles
   uint8_t* sV = sK + NT * ATT_TILE_BYTES;           // NT tiles
   float* sBias = reinterpret_cast<float*>(sV + NT * ATT_TILE_BYTES);   // [NT * 128]
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sBias + NT * ATT_T);
+  float* sRed = sBias + NT * ATT_T;                 // [2][128]: row maxima / row sums exchanged between the two halves
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sRed + 2 * ATT_T);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
   constexpr int TMEM_COLS = NT == 1 ? 128 : (NT == 2 ? 256 : 512);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  // 256 threads: two warps per TMEM lane quarter; thread (row, half) owns 64 of every tile's 128 key columns
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(bar_load, 1);
@@ -605,7 +476,7 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_O = tmem;   // aliases columns 0..63 of S_0
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
   const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
   const bool use_drop = p.p_drop > 0.f;
@@ -619,8 +490,9 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     const int b = bh / p.H, h = bh - b * p.H;
     const int q0 = qi * ATT_T;
     tc_fence_before_sync();
-    __syncthreads();   // previous item: everybody has read O / sBias, the tensor core is done with sQP / sK / sV
+    __syncthreads();   // previous item: everybody has read O / sBias / sRed, the tensor core is done with the tiles
     if (tid == 0) {
+      tma_store_wait_read<0>();   // the previous O tile has left sQP
       mbar_expect_tx(bar_load, (1 + 2 * NT) * ATT_TILE_BYTES);
       tma_load_3d(sQP, &tma_qkv, bar_load, h * ATT_D, q0, b);
 #pragma unroll
@@ -629,7 +501,7 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
         tma_load_3d(sV + j * ATT_TILE_BYTES, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, j * ATT_T, b);
       }
     }
-    for (int k = tid; k < NT * ATT_T; k += 128)
+    for (int k = tid; k < NT * ATT_T; k += 256)
       sBias[k] = k < p.S ? (p.key_bias ? p.key_bias[b * p.S + k] * LOG2E : 0.f) : -INFINITY;
     __syncthreads();
     if (tid == 0) {
@@ -648,16 +520,20 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     ph_mma ^= 1;
     tc_fence_after_sync();
 
-    // ---- exact row maximum over all NT x 128 key columns (TMEM reads only)
+    // ---- exact row maximum over all NT x 128 key columns: own 64 columns of every tile, then the partner's maximum
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < NT * 4; ++c) {
+    for (int jc = 0; jc < NT * 2; ++jc) {
+      const int col = (jc >> 1) * ATT_T + half * 64 + (jc & 1) * 32;
       uint32_t v[32];
-      tmem_ld32(tmem + lane_addr + c * 32, v);
+      tmem_ld32(tmem + lane_addr + col, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[c * 32 + i]));
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, sBias[col + i]));
     }
+    sRed[half * ATT_T + row] = mx;
+    __syncthreads();
+    mx = fmaxf(mx, sRed[(half ^ 1) * ATT_T + row]);
     if (mx == -INFINITY) mx = 0.f;
 
     // ---- P_j = exp2(S_j - max) -> shared memory -> O += P_j V_j
@@ -665,7 +541,8 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
 #pragma unroll 1
     for (int j = 0; j < NT; ++j) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + j * ATT_T + c * 32, v);
         tmem_ld_wait();
@@ -676,12 +553,12 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           sum += x[i];
         }
         if (use_drop) {
-          const uint32_t keep = dropout_keep32(p.seed, drop_chunk(bh, s_pad, q0 + tid, j * ATT_T + c * 32),
+          const uint32_t keep = dropout_keep32(p.seed, drop_chunk(bh, s_pad, q0 + row, j * ATT_T + c * 32),
                                                p.drop_threshold >> 16);
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = (keep >> i) & 1 ? x[i] * p.inv_keep : 0.f;
         }
-        store_row32_sw128(sQP, tid, c * 32, x);
+        store_row32_sw128(sQP, row, c * 32, x);
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -700,28 +577,35 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
       tc_fence_after_sync();
     }
 
+    // ---- row sums of the two halves, then O / sum -> staged tile -> one TMA store (rows >= S clipped by the map)
+    __syncthreads();               // everybody is past its read of the partner's maximum
+    sRed[half * ATT_T + row] = sum;
+    __syncthreads();
+    sum += sRed[(half ^ 1) * ATT_T + row];
     const float inv_sum = 1.f / sum;
-    const bool row_ok = q0 + tid < p.S;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.S + q0 + tid) * p.D + h * ATT_D;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld32(t_O + lane_addr + c * 32, v);
+      tmem_ld32(t_O + lane_addr + half * 32, v);
       tmem_ld_wait();
-      if (row_ok) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv_sum, __uint_as_float(v[q * 8 + 1]) * inv_sum);
-          o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv_sum, __uint_as_float(v[q * 8 + 3]) * inv_sum);
-          o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv_sum, __uint_as_float(v[q * 8 + 5]) * inv_sum);
-          o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv_sum, __uint_as_float(v[q * 8 + 7]) * inv_sum);
-          *reinterpret_cast<uint4*>(orow + c * 32 + q * 8) = o;
-        }
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[q * 8 + 0]) * inv_sum, __uint_as_float(v[q * 8 + 1]) * inv_sum);
+        o.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) * inv_sum, __uint_as_float(v[q * 8 + 3]) * inv_sum);
+        o.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) * inv_sum, __uint_as_float(v[q * 8 + 5]) * inv_sum);
+        o.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) * inv_sum, __uint_as_float(v[q * 8 + 7]) * inv_sum);
+        *reinterpret_cast<uint4*>(sQP + sw128_off(row, half * 4 + q)) = o;
       }
     }
-    if (row_ok && p.lse) p.lse[static_cast<long long>(bh) * p.S + q0 + tid] = (mx + log2f(sum)) * LN2;
+    if (half == 0 && q0 + row < p.S && p.lse) p.lse[static_cast<long long>(bh) * p.S + q0 + row] = (mx + log2f(sum)) * LN2;
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_3d(&tma_out, sQP, h * ATT_D, q0, b);
+      tma_store_commit();
+    }
   }
+  if (tid == 0) tma_store_wait<0>();
 
   tc_fence_before_sync();
   __syncthreads();
@@ -730,6 +614,7 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     tmem_dealloc<TMEM_COLS>(tmem);
   }
 }
+
 // ------------------------------------------------------------------------------------------ 128 < S <= 256, backward
 // One CTA (256 threads) owns a whole (batch, head): Q, K, V, dO of both 128-row tiles are loaded ONCE (128 KB), and all
 // five gradient accumulators live in TMEM next to the score tiles: S | dP | dK_j dV_j | dQ_0 dQ_1 = 512 columns.  For
@@ -1470,11 +1355,10 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
 }
 
 template <int NT>
-constexpr int att_fwd_tmem_smem() { return (2 + 2 * NT) * ATT_TILE_BYTES + NT * ATT_T * 4 + 64 + 1024; }
+constexpr int att_fwd_tmem_smem() { return (2 + 2 * NT) * ATT_TILE_BYTES + (NT + 2) * ATT_T * 4 + 64 + 1024; }
 
 constexpr int ATT_FWD_MULTI_SMEM = 5 * ATT_TILE_BYTES + ATT_MAX_S * 4 + 64 + 1024;
 
-constexpr int ATT_FWD_SMEM = 5 * ATT_TILE_BYTES + ATT_T * 4 + 64 + 1024;
 constexpr int ATT_BWD_SMEM = 8 * ATT_TILE_BYTES + ATT_T * 4 + 64 + 1024;
 
 static int fill_params(AttnParams& p, int B, int H, int S, float p_drop, unsigned long long seed,
@@ -1512,13 +1396,11 @@ B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    e = cudaFuncSetAttribute(attn_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_MULTI_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_MULTI_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  if (S > ATT_T && S <= 3 * ATT_T) {      // ViT lengths: score tiles stay in TMEM, one pass
+  if (S <= 3 * ATT_T) {      // up to three key tiles: all score tiles stay in TMEM, one pass
     const int nt = ceil_div(S, ATT_T);
     const int items = B * H * nt;
     static bool configured_tmem = false;
@@ -1526,17 +1408,27 @@ B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void
       cudaError_t e = cudaFuncSetAttribute(attn_fwd_tmem_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            att_fwd_tmem_smem<2>());
       if (e != cudaSuccess) return static_cast<int>(e);
+      e = cudaFuncSetAttribute(attn_fwd_tmem_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               att_fwd_tmem_smem<1>());
+      if (e != cudaSuccess) return static_cast<int>(e);
       e = cudaFuncSetAttribute(attn_fwd_tmem_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                att_fwd_tmem_smem<3>());
       if (e != cudaSuccess) return static_cast<int>(e);
       configured_tmem = true;
     }
-    if (nt == 2) {
+    CUtensorMap to;
+    const uint64_t orow = static_cast<uint64_t>(p.D) * 2;
+    rc = make_tmap_3d_bf16(&to, out, p.D, S, B, orow, orow * S, ATT_D, ATT_T);
+    if (rc) return rc;
+    if (nt == 1) {
       const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
-      attn_fwd_tmem_kernel<2><<<grid, 128, att_fwd_tmem_smem<2>(), static_cast<cudaStream_t>(stream)>>>(tq, p);
+      attn_fwd_tmem_kernel<1><<<grid, 256, att_fwd_tmem_smem<1>(), static_cast<cudaStream_t>(stream)>>>(tq, to, p);
+    } else if (nt == 2) {
+      const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
+      attn_fwd_tmem_kernel<2><<<grid, 256, att_fwd_tmem_smem<2>(), static_cast<cudaStream_t>(stream)>>>(tq, to, p);
     } else {
       const int grid = items < dev.num_sms ? items : dev.num_sms;
-      attn_fwd_tmem_kernel<3><<<grid, 128, att_fwd_tmem_smem<3>(), static_cast<cudaStream_t>(stream)>>>(tq, p);
+      attn_fwd_tmem_kernel<3><<<grid, 256, att_fwd_tmem_smem<3>(), static_cast<cudaStream_t>(stream)>>>(tq, to, p);
     }
     B200MM_CHECK_LAUNCH();
     return B200MM_OK;
@@ -1548,11 +1440,7 @@ B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void
     B200MM_CHECK_LAUNCH();
     return B200MM_OK;
   }
-  const int items = B * H;
-  const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
-  attn_fwd_kernel<<<grid, 128, ATT_FWD_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, p);
-  B200MM_CHECK_LAUNCH();
-  return B200MM_OK;
+  return B200MM_ERR_BAD_ARG;   // unreachable: every S <= 512 is served above
 }
 
 // dqkv [B*S, 3*H*64] <- gradients of Q, K, V given dO, using O and the saved LSE.
