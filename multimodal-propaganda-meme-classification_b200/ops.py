@@ -142,10 +142,24 @@ def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None):
 
 
 def _wgrad_splits(n_out, k_out, m_red):
-    tiles = ((n_out + 127) // 128) * ((k_out + 255) // 256)
+    """Split-K factor of a weight-gradient GEMM (dw[n_out, k_out], reduction over m_red rows): the one that minimises
+    (waves of work units over the SMs) x (k iterations per unit), with a small charge per split for the fp32
+    red.add traffic of the partial sums.  Work units follow the kernel's own geometry: 128 x 256 tiles on 148 CTAs, or
+    256 x 256 tile pairs on 74 clusters where the CTA-pair kernel applies (see b200mm_gemm_bf16)."""
+    m_tiles = (n_out + 127) // 128
+    bn = 256 if (k_out % 256 == 0 or k_out > 512) else (128 if k_out > 64 else 64)
+    n_tiles = (k_out + bn - 1) // bn
     k_iters = (m_red + 63) // 64
-    want = max(1, (2 * num_sms() + tiles - 1) // tiles)
-    return max(1, min(want, k_iters // 4 if k_iters >= 8 else 1))
+    pair = bn == 256 and m_tiles >= 2 and num_sms() % 2 == 0
+    units = ((m_tiles + 1) // 2 if pair else m_tiles) * n_tiles
+    slots = num_sms() // 2 if pair else num_sms()
+    best, best_cost = 1, None
+    for s in range(1, max(1, min(k_iters // 8, 4 * slots)) + 1):
+        waves = (units * s + slots - 1) // slots
+        cost = waves * ((k_iters + s - 1) // s + 6) + 0.5 * s      # + pipeline fill per unit, + partial-sum traffic
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s, cost
+    return best
 
 
 def linear_wgrad(dy, x, dw):
