@@ -129,6 +129,14 @@ int b200mm_col2im_nhwc(const void* dcols, const void* addend, int N, int H, int 
                        int pad, void* dx, void* stream);
 int b200mm_im2col_nchw_f32(const float* img, int N, int Cin, int H, int W, int KH, int KW, int stride, int pad,
                            int Kp, void* cols, void* stream);
+/* ResNet stem (torchvision/models/resnet.py:197 conv1, 7x7 / 2 / pad 3, 3 -> 64) computed from the fp32 NCHW image
+ * without an im2col matrix: forward (+ optional BatchNorm column statistics, accumulated into col_stats[128]) and the
+ * weight gradient (dw fp32 [64,152] accumulated).  B200MM_ERR_BAD_ARG for any other stem shape (Cin != 3, Cout != 64,
+ * Kp != 152, W > 226 or Wo > 128): the caller then lowers through b200mm_im2col_nchw_f32 + b200mm_gemm_bf16. */
+int b200mm_stem_conv_fwd(const float* img, int N, int Cin, int H, int W, const void* w, int Cout, int Kp, void* out,
+                         float* col_stats, void* stream);
+int b200mm_stem_conv_wgrad(const float* img, int N, int Cin, int H, int W, const void* dy, int Cout, int Kp,
+                           float* dw, void* stream);
 int b200mm_subsample_nhwc(const void* x, int N, int H, int W, int C, int stride, void* out, void* stream);
 int b200mm_upsample_add_nhwc(const void* dsub, const void* addend, int N, int H, int W, int C, int stride, void* dx,
                              void* stream);

@@ -137,6 +137,8 @@ declare("b200mm_im2col_nhwc", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, 
 declare("b200mm_col2im_nhwc", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_im2col_nchw_f32", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr,
                                    c_ptr])
+declare("b200mm_stem_conv_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr, c_ptr])
+declare("b200mm_stem_conv_wgrad", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_subsample_nhwc", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_upsample_add_nhwc", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_bn1d_fwd", [c_ptr, c_int, c_longlong, c_int, c_int, c_ptr, c_ptr, c_float, c_float, c_int, c_int, c_ptr,

@@ -207,12 +207,17 @@ class ImageTower:
         sv = {"N": N, "blocks": []} if training else None
         st = self.stem
         self._stats_begin(training)
-        cols, H1, W1 = ops.im2col_nchw_f32(image, 7, 2, 3, STEM_KP)
-        c0 = ops.linear_fwd(cols, st.w, col_stats=self._stats_of(st))
+        direct = ops.stem_conv_supported(image, st.w)
+        if direct:   # csrc/stem_conv.cu: patches gathered on the fly, no [N*Ho*Wo, 152] matrix
+            c0, H1, W1 = ops.stem_conv_fwd(image, st.w, col_stats=self._stats_of(st))
+            cols = image
+        else:        # other stem widths / very wide images: explicit lowering
+            cols, H1, W1 = ops.im2col_nchw_f32(image, 7, 2, 3, STEM_KP)
+            c0 = ops.linear_fwd(cols, st.w, col_stats=self._stats_of(st))
         a0, m0, r0 = self._bn(st, c0, training)
         x, arg, H2, W2 = ops.maxpool_fwd(a0, N, H1, W1, st.cout)
         if training:
-            sv["stem"] = (cols, c0, a0, m0, r0, arg, H1, W1)
+            sv["stem"] = (cols, direct, c0, a0, m0, r0, arg, H1, W1)
         Hc, Wc = H2, W2
         for blk in self.blocks:
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
@@ -334,9 +339,12 @@ class ImageTower:
                 else:
                     d_xs = ops.linear_dgrad(d_yd, ds.w)
                     d_out = ops.upsample_add(d_xs, d_x1, N, Hi, Wi, ds.cin, stride)
-        cols, c0, a0, m0, r0, arg, H1, W1 = sv["stem"]
+        cols, direct, c0, a0, m0, r0, arg, H1, W1 = sv["stem"]
         st = self.stem
         d_a0 = ops.maxpool_bwd(d_out, arg, N, H1, W1, st.cout)
         d_c0, _ = ops.batchnorm_bwd(d_a0, None, c0, m0, r0, st.g, st.dg, st.db, relu=True, beta=st.b)
-        ops.linear_wgrad(d_c0, cols, st.dw)
+        if direct:
+            ops.stem_conv_wgrad(cols, d_c0, st.dw)
+        else:
+            ops.linear_wgrad(d_c0, cols, st.dw)
         self._saved = None

@@ -535,6 +535,36 @@ def im2col_nchw_f32(img, k, stride, pad, Kp):
     return cols, Ho, Wo
 
 
+def stem_conv_supported(img, w) -> bool:
+    """Shapes the direct stem kernels are specialised for (csrc/stem_conv.cu: 7x7/2/3, 3 -> 64, K padded to 152)."""
+    N, Cin, H, W = img.shape
+    return Cin == 3 and tuple(w.shape) == (64, 152) and W <= 226 and 8 <= (W - 1) // 2 + 1 <= 128 and H >= 7
+
+
+def stem_conv_fwd(img, w, col_stats=None):
+    """conv1 (7x7 / 2 / pad 3) of the fp32 NCHW image -> bf16 NHWC [N*Ho*Wo, 64], no im2col matrix
+    (torchvision/models/resnet.py:197).  col_stats: fp32 [128] accumulator of column sum / sum of squares."""
+    _chk(img, f32, "pixel_values")
+    _chk(w, bf16, "conv1.weight")
+    img = img.contiguous()
+    N, Cin, H, W = img.shape
+    Ho, Wo = conv_out_hw(H, W, 7, 2, 3)
+    out = torch.empty(N * Ho * Wo, w.shape[0], device=img.device, dtype=bf16)
+    _lib.call("b200mm_stem_conv_fwd", _p(img), N, Cin, H, W, _p(w), w.shape[0], w.shape[1], _p(out),
+              _p(col_stats) if col_stats is not None else None, _s())
+    return out, Ho, Wo
+
+
+def stem_conv_wgrad(img, dy, dw):
+    """dw[64,152] (fp32) += dy^T . patches(img) for conv1, patches gathered on the fly."""
+    _chk(img, f32, "pixel_values")
+    _chk(dy, bf16, "dy")
+    _chk(dw, f32, "dw")
+    img = img.contiguous()
+    N, Cin, H, W = img.shape
+    _lib.call("b200mm_stem_conv_wgrad", _p(img), N, Cin, H, W, _p(dy), dw.shape[0], dw.shape[1], _p(dw), _s())
+
+
 def subsample(x, N, H, W, C, stride):
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     out = torch.empty(N * Ho * Wo, C, device=x.device, dtype=bf16)

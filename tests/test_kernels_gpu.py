@@ -377,6 +377,35 @@ def test_stem_lowering_and_subsample(ops, cuda_device):
     assert rel(_nchw(up, N, 8, 8), ref_up) < 1e-2
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 32, 32), (3, 64, 48), (2, 224, 224), (40, 224, 224)])
+def test_stem_direct_conv(ops, cuda_device, N, H, W):
+    """csrc/stem_conv.cu against F.conv2d (same bf16-rounded operands) and against the im2col lowering it replaces;
+    N = 40 at 224 x 224 gives 4480 output rows > 2 x 148 CTAs, so every CTA loops over several rows."""
+    torch.manual_seed(21)
+    img = torch.randn(N, 3, H, W, device=cuda_device)
+    w = (torch.randn(64, 3, 7, 7, device=cuda_device) * 0.05).to(bf16).float()
+    wp = torch.zeros(64, 152, device=cuda_device, dtype=bf16)
+    wp[:, :147] = w.permute(0, 2, 3, 1).reshape(64, 147).to(bf16)
+    assert ops.stem_conv_supported(img, wp)
+    ref = F.conv2d(img.to(bf16).float(), w, None, 2, 3)
+    stats = torch.zeros(128, device=cuda_device)
+    y, Ho, Wo = ops.stem_conv_fwd(img, wp, col_stats=stats)
+    assert (Ho, Wo) == tuple(ref.shape[2:])
+    assert rel(_nchw(y, N, Ho, Wo), ref) < 1e-2
+    cols, _, _ = ops.im2col_nchw_f32(img, 7, 2, 3, 152)
+    y_low = ops.linear_fwd(cols, wp)
+    assert rel(y, y_low) < 5e-3
+    yf = y.float()
+    assert rel(stats[:64], yf.sum(0)) < 1e-3 and rel(stats[64:], (yf * yf).sum(0)) < 1e-3
+    # weight gradient, accumulated on top of an existing value
+    dy = torch.randn(N * Ho * Wo, 64, device=cuda_device).to(bf16)
+    dw = torch.full((64, 152), 0.5, device=cuda_device)
+    ops.stem_conv_wgrad(img, dy, dw)
+    ref_dw = dy.float().t() @ cols.float() + 0.5
+    assert rel(dw, ref_dw) < 1e-3
+    assert torch.equal(dw[:, 147:], torch.full((64, 5), 0.5, device=cuda_device))
+
+
 # ------------------------------------------------------------------------------------------------- head / loss / optimizer
 def test_head_cross_entropy(ops, cuda_device):
     torch.manual_seed(12)
