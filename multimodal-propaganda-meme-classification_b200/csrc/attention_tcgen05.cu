@@ -135,7 +135,7 @@ attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPar
     // ---- pass 1: row maxima over all key tiles
     float mx = -INFINITY;
     for (int j = 0; j < nt; ++j) {
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         mbar_expect_tx(bar_load, ATT_TILE_BYTES);
         tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, j * ATT_T, b);
         mbar_wait(bar_load, ph_load);
@@ -167,7 +167,7 @@ attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPar
     // ---- pass 2: P = exp2(S - max), O += P V
     float sum = 0.f;
     for (int j = 0; j < nt; ++j) {
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         mbar_expect_tx(bar_load, 2 * ATT_TILE_BYTES);
         tma_load_3d(sK, &tma_qkv, bar_load, p.D + h * ATT_D, j * ATT_T, b);
         tma_load_3d(sV, &tma_qkv, bar_load, 2 * p.D + h * ATT_D, j * ATT_T, b);
@@ -205,7 +205,7 @@ attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPar
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -325,7 +325,7 @@ attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
       }
       tc_fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         mbar_wait(bar_load, ph_load);
         tc_fence_after_sync();
 #pragma unroll
@@ -374,7 +374,7 @@ attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         tc_fence_after_sync();
         const uint32_t accum = it > 0 ? 1u : 0u;
         if (kind == 0) {
@@ -504,7 +504,7 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
     for (int k = tid; k < NT * ATT_T; k += 256)
       sBias[k] = k < p.S ? (p.key_bias ? p.key_bias[b * p.S + k] * LOG2E : 0.f) : -INFINITY;
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
       mbar_wait(bar_load, ph_load);
       tc_fence_after_sync();
 #pragma unroll
@@ -563,7 +563,7 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncthreads();   // P_j complete in shared memory; every thread has finished reading S_j from TMEM
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -758,7 +758,7 @@ attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncthreads();   // P / dS complete; S / dP fully read
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         tc_fence_after_sync();
         const uint32_t q = smem_u32(sQ + i * ATT_TILE_BYTES), k = smem_u32(sK + j * ATT_TILE_BYTES);
         const uint32_t g = smem_u32(sdO + i * ATT_TILE_BYTES);
@@ -991,7 +991,7 @@ attn_bwd_tmem3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncthreads();   // P staged; S fully read (its columns may take dP now)
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         tc_fence_after_sync();
         const uint32_t g = smem_u32(sdO + i * ATT_TILE_BYTES), v = smem_u32(sV + j * ATT_TILE_BYTES);
 #pragma unroll
@@ -1027,7 +1027,7 @@ attn_bwd_tmem3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
       fence_proxy_async_smem();
       tc_fence_before_sync();
       __syncthreads();   // dS staged; dP fully read
-      if (tid == 0) {
+      if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
         tc_fence_after_sync();
         const uint32_t q = smem_u32(sQ + i * ATT_TILE_BYTES), k = smem_u32(sK + j * ATT_TILE_BYTES);
 #pragma unroll
@@ -1279,7 +1279,7 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();   // P / dS complete, S / dP fully read
-    if (tid == 0) {
+    if (tid < 32 && elect_one()) {   // one thread of warp 0 issues (ptx.cuh: elect_one)
       tc_fence_after_sync();
 #pragma unroll
       for (int k = 0; k < 8; ++k)

@@ -113,6 +113,25 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d
   return r == CUDA_SUCCESS ? B200MM_OK : B200MM_ERR_TENSORMAP;
 }
 
+int make_tmap_nhwc_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W, int C, uint32_t box_c, uint32_t box_w,
+                        uint32_t box_h) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return B200MM_ERR_NO_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (C & 7) || box_c * 2 > 128 || box_w > 256 || box_h > 256 ||
+      box_w == 0 || box_h == 0)
+    return B200MM_ERR_BAD_ARG;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? B200MM_OK : B200MM_ERR_TENSORMAP;
+}
+
 }  // namespace b200
 
 B200MM_API int b200mm_version() { return 100; }

@@ -43,6 +43,11 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 int make_tmap_3d_bf16(CUtensorMap* map, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1);
 
+// tiled 4-D bf16 tensor map over an NHWC activation [N][H][W][C] addressed (c, w, h, n): box = box_c x box_w x box_h x 1,
+// SWIZZLE_128B, zero OOB fill (halo loads start at w = -1, h = -1).
+int make_tmap_nhwc_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W, int C, uint32_t box_c, uint32_t box_w,
+                        uint32_t box_h);
+
 // im2col-mode bf16 tensor map over an NHWC activation [N][H][W][C]: square k x k window, symmetric padding,
 // traversal stride `stride`; each load delivers pixels_per_column pixels x 64 channels, SWIZZLE_128B.
 int make_tmap_im2col_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W, int C, int ksize, int stride, int pad,

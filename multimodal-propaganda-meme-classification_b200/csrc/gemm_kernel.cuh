@@ -188,7 +188,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {     // pair: only the leader issues (and commits to both CTAs' barriers)
+    // pair: only the leader issues (and commits to both CTAs' barriers).  elect_one(), not lane == 0: see ptx.cuh
+    if (cta_rank == 0 && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(CTAS * GEMM_BM, BN, p.a_mn, p.b_mn);
       // K-major: 16-element k step = 32 B inside the swizzle row; 8-row groups 1024 B apart.
       // MN-major: 16-element k step = two 8-k-row groups = 2048 B; 64-wide MN atoms one 8 KB box apart.

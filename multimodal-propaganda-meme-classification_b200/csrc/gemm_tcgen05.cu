@@ -193,6 +193,20 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
                   block_n, p_drop, seed, col_stats, stream);
 }
 
+namespace b200 {
+// conv3x3_c64.cu: halo-resident 3x3 / stride 1 / 64 -> 64 channel kernels (B200MM_HALO_CONV=0 falls back to im2col loads)
+bool conv3x3_c64_supported(int N, int H, int W);
+int conv3x3_c64_fwd(const void* x, int N, int H, int W, const void* w, void* out, float* col_stats, cudaStream_t stream);
+int conv3x3_c64_wgrad(const void* dy, const void* x, int N, int H, int W, float* dw, cudaStream_t stream);
+}  // namespace b200
+static bool halo_conv_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200MM_HALO_CONV");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // Implicit-GEMM convolution forward (square k x k window, symmetric padding): out[N*P*Q, Cout] = conv(x, w) with
 // x an NHWC bf16 activation [N,H,W,C] (C % 64 == 0) gathered by TMA im2col loads -- no im2col matrix in memory --
 // and w the OHWI-flattened weight [Cout, k*k*C].  epi / bias / residual as in b200mm_gemm_bf16 (bf16 output modes).
@@ -203,6 +217,9 @@ B200MM_API int b200mm_conv_fwd(const void* x, int N, int H, int W, int C, const 
                                void* out, long long ldc, float* col_stats, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || ksize <= 0 || stride <= 0 || pad < 0)
     return B200MM_ERR_BAD_ARG;
+  if (halo_conv_enabled() && ksize == 3 && stride == 1 && pad == 1 && C == 64 && Cout == 64 && epi == EPI_STORE &&
+      bias == nullptr && residual == nullptr && ldc == 64 && conv3x3_c64_supported(N, H, W))
+    return conv3x3_c64_fwd(x, N, H, W, w, out, col_stats, static_cast<cudaStream_t>(stream));
   ConvGeom cg;
   cg.N = N; cg.H = H; cg.W = W; cg.C = C; cg.ksize = ksize; cg.stride = stride; cg.pad = pad;
   cg.P = (H + 2 * pad - ksize) / stride + 1;
@@ -222,6 +239,9 @@ B200MM_API int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x,
                                  int ksize, int stride, int pad, float* dw, int splits, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || ksize <= 0 || stride <= 0 || pad < 0)
     return B200MM_ERR_BAD_ARG;
+  if (halo_conv_enabled() && ksize == 3 && stride == 1 && pad == 1 && C == 64 && Cout == 64 && ld_dy == 64 &&
+      conv3x3_c64_supported(N, H, W))
+    return conv3x3_c64_wgrad(dy, x, N, H, W, dw, static_cast<cudaStream_t>(stream));
   ConvGeom cg;
   cg.N = N; cg.H = H; cg.W = W; cg.C = C; cg.ksize = ksize; cg.stride = stride; cg.pad = pad;
   cg.P = (H + 2 * pad - ksize) / stride + 1;

@@ -201,7 +201,7 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant
     have_prev = true;
     fence_proxy_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
       tc_fence_after_sync();
 #pragma unroll
@@ -211,8 +211,8 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant
           umma_bf16(tmem, umma_desc_sw128(sA_u + kb * 16384 + k * 32, 16, 1024),
                     umma_desc_sw128(sW_u + kb * 8192 + k * 32, 16, 1024), idesc, (kb | k) ? 1u : 0u);
       umma_commit(bar_mma);
-      tma_store_wait_read<0>();   // previous tile's output box has left sOut
     }
+    if (threadIdx.x == 0) tma_store_wait_read<0>();   // previous tile's output box has left sOut (same thread stores)
     mbar_wait(bar_mma, phase);
     phase ^= 1;
     tc_fence_after_sync();
@@ -317,7 +317,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tma_dy, StemArgs a) {
     build_patches(a.Wo, sIn, sA);
     fence_proxy_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       mbar_wait(bar_dy, ph_dy);
       tc_fence_after_sync();
 #pragma unroll

@@ -377,6 +377,37 @@ def test_stem_lowering_and_subsample(ops, cuda_device):
     assert rel(_nchw(up, N, 8, 8), ref_up) < 1e-2
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 8, 8), (3, 10, 12), (2, 7, 30), (2, 56, 56), (12, 56, 56), (3, 33, 62)])
+def test_conv3x3_c64_halo_resident(ops, cuda_device, N, H, W):
+    """csrc/conv3x3_c64.cu (taken by conv_fwd / conv_wgrad for 3x3 / 1 / 1, 64 -> 64): forward + BN statistics, data
+    gradient through the rotated weights, weight gradient -- against autograd on the same bf16-rounded operands.
+    (12, 56, 56) is 336 row groups > 148 CTAs (several tiles per CTA, ring and TMEM double buffer wrap); (3, 10, 12),
+    (2, 7, 30) and (3, 33, 62) have a partial last row group / a row count R that does not divide H."""
+    torch.manual_seed(31)
+    C = 64
+    x = torch.randn(N, C, H, W, device=cuda_device).to(bf16).float()
+    w = (torch.randn(C, C, 3, 3, device=cuda_device) * 0.05).to(bf16).float()
+    xf, wf = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = F.conv2d(xf, wf, None, 1, 1)
+    w_ohwi = w.permute(0, 2, 3, 1).reshape(C, 9 * C).to(bf16).contiguous()
+    xn = _nhwc(x)
+    stats = torch.zeros(2 * C, device=cuda_device)
+    y, P, Q = ops.conv_fwd(xn, N, H, W, C, w_ohwi, 3, 1, 1, col_stats=stats)
+    assert (P, Q) == (H, W)
+    assert rel(_nchw(y, N, H, W), ref) < 1e-2
+    yf = y.float()
+    assert rel(stats[:C], yf.sum(0)) < 2e-3 and rel(stats[C:], (yf * yf).sum(0)) < 2e-3
+    dy = torch.randn_like(ref).to(bf16).float()
+    ref.backward(dy)
+    dyn = _nhwc(dy)
+    dw = torch.full((C, 9 * C), 0.25, device=cuda_device)
+    ops.conv_wgrad(dyn, xn, N, H, W, C, 3, 1, 1, dw)
+    assert rel((dw - 0.25).view(C, 3, 3, C).permute(0, 3, 1, 2), wf.grad) < 1e-2
+    w_rot = ops.conv_weight_rotate(w_ohwi, C, C, 3)
+    dx, _, _ = ops.conv_fwd(dyn, N, H, W, C, w_rot, 3, 1, 1)
+    assert rel(_nchw(dx, N, H, W), xf.grad) < 1e-2
+
+
 @pytest.mark.parametrize("N,H,W", [(2, 32, 32), (3, 64, 48), (2, 224, 224), (40, 224, 224)])
 def test_stem_direct_conv(ops, cuda_device, N, H, W):
     """csrc/stem_conv.cu against F.conv2d (same bf16-rounded operands) and against the im2col lowering it replaces;
