@@ -684,7 +684,16 @@ static bool bn_shape_ok(long long M, int C) {
 }
 // floats of scratch a BatchNorm launch needs: replicas + final row + ticket (rounded up)
 static size_t bn_scratch_floats(int C) { return static_cast<size_t>(BN_REPLICAS + 1) * 2 * C + 32; }
-static int bn_rows_per_cta(long long M, int C, int* grid, int ctas_per_sm = 8) {
+// resident 256-thread CTAs per SM of a kernel (register-limited: 2..3 for the apply kernels).  Grids are sized to ONE
+// wave of resident CTAs: with more, a [12544 x 512] tensor paid the per-CTA prologue and a DRAM round trip 3.5 times
+// (20 us for 26 MB of traffic).
+template <typename Kernel>
+static int bn_occupancy(Kernel kernel) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+static int bn_rows_per_cta(long long M, int C, int* grid, int ctas_per_sm) {
   const DeviceInfo& dev = device_info();
   const int rpp = 256 / (C >> 3);
   const long long target = static_cast<long long>(dev.num_sms > 0 ? dev.num_sms : 148) * ctas_per_sm;
@@ -710,7 +719,8 @@ B200MM_API int b200mm_batchnorm_fwd(const void* x, const void* residual, long lo
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * bn_scratch_floats(C), s);
   if (e != cudaSuccess) return static_cast<int>(e);
   int grid, rgrid;
-  const int rows = bn_rows_per_cta(M, C, &grid);
+  static const int occ_res = bn_occupancy(bn_apply_kernel<true>), occ_plain = bn_occupancy(bn_apply_kernel<false>);
+  const int rows = bn_rows_per_cta(M, C, &grid, residual != nullptr ? occ_res : occ_plain);
   const int rrows = bn_rows_per_cta(M, C, &rgrid, 3);   // reductions: fewer, fatter CTAs (8 loads in flight / thread)
   const float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;
   bn_stats_kernel<<<rgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), M, C, rrows, scratch);
@@ -738,7 +748,8 @@ B200MM_API int b200mm_batchnorm_fwd_stats(const void* x, const void* residual, l
                                           void* stream) {
   if (!bn_shape_ok(M, C) || col_stats == nullptr) return B200MM_ERR_BAD_ARG;
   int grid;
-  const int rows = bn_rows_per_cta(M, C, &grid);
+  static const int occ_res = bn_occupancy(bn_apply_kernel<true>), occ_plain = bn_occupancy(bn_apply_kernel<false>);
+  const int rows = bn_rows_per_cta(M, C, &grid, residual != nullptr ? occ_res : occ_plain);
   if (residual != nullptr)
     bn_apply_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, col_stats,
@@ -757,7 +768,8 @@ B200MM_API int b200mm_batchnorm_eval(const void* x, const void* residual, long l
                                      int relu, void* out, void* stream) {
   if (!bn_shape_ok(M, C)) return B200MM_ERR_BAD_ARG;
   int grid;
-  const int rows = bn_rows_per_cta(M, C, &grid);
+  static const int occ_res = bn_occupancy(bn_eval_kernel<true>), occ_plain = bn_occupancy(bn_eval_kernel<false>);
+  const int rows = bn_rows_per_cta(M, C, &grid, residual != nullptr ? occ_res : occ_plain);
   if (residual != nullptr)
     bn_eval_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, running_mean,
@@ -784,7 +796,10 @@ B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const voi
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * bn_scratch_floats(C), s);
   if (e != cudaSuccess) return static_cast<int>(e);
   int grid, rgrid;
-  const int rows = bn_rows_per_cta(M, C, &grid);
+  static const int occ_apply[3] = {bn_occupancy(bn_bwd_apply_kernel<0>), bn_occupancy(bn_bwd_apply_kernel<1>),
+                                   bn_occupancy(bn_bwd_apply_kernel<2>)};
+  const int src = (relu && relu_mask != nullptr) ? 2 : (relu && out != nullptr) ? 1 : 0;
+  const int rows = bn_rows_per_cta(M, C, &grid, occ_apply[src]);
   const int rrows = bn_rows_per_cta(M, C, &rgrid, 2);
   const float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;
   const __nv_bfloat16* dout_ = static_cast<const __nv_bfloat16*>(dout);
@@ -801,8 +816,8 @@ B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const voi
                                                   relu, fin, fin + C, dx_, dz_, dgamma, dbeta);                     \
     B200MM_CHECK_LAUNCH();                                                                                          \
   } while (0)
-  if (relu && relu_mask != nullptr) BN_BWD(2);
-  else if (relu && out != nullptr) BN_BWD(1);
+  if (src == 2) BN_BWD(2);
+  else if (src == 1) BN_BWD(1);
   else BN_BWD(0);
 #undef BN_BWD
   return B200MM_OK;

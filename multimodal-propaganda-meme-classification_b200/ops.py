@@ -454,7 +454,7 @@ def batchnorm_fwd(x, gamma, beta, running_mean, running_var, *, residual=None, r
         mask = torch.empty(M, C // 8, device=x.device, dtype=torch.uint8) if (want_mask and relu) else None
         _lib.call("b200mm_batchnorm_fwd_stats", _p(x), _p(residual), M, C, _p(col_stats), _p(gamma), _p(beta),
                   float(eps), float(momentum), int(relu), _p(out), _p(mean), _p(rstd), _p(running_mean),
-                  _p(running_var), _p(mask), _s())
+                  _p(running_var), _p(mask), _s(), key=("bn_fwd", M, C, int(residual is not None), int(mask is not None)))
         return (out, mean, rstd, mask) if want_mask else (out, mean, rstd)
     _lib.call("b200mm_batchnorm_fwd", _p(x), _p(residual), M, C, _p(gamma), _p(beta), float(eps), float(momentum),
               int(relu), _p(out), _p(mean), _p(rstd), _p(running_mean), _p(running_var),
@@ -478,7 +478,8 @@ def batchnorm_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=True, 
     dz = torch.empty_like(x) if need_dz else None
     _lib.call("b200mm_batchnorm_bwd", _p(dout), _p(out), _p(x), M, C, _p(mean), _p(rstd), _p(gamma), _p(beta),
               _p(mask), int(relu),
-              _p(dx), _p(dz), _p(dgamma), _p(dbeta), _p(BNScratch.get(x.device, C)), _s())
+              _p(dx), _p(dz), _p(dgamma), _p(dbeta), _p(BNScratch.get(x.device, C)), _s(),
+              key=("bn_bwd", M, C, int(need_dz), 0 if mask is None else 1))
     return dx, dz
 
 

@@ -42,7 +42,13 @@ for k, v in sorted(by_fn.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k:32s} n={v[0]//STEPS:4d} {v[1]/STEPS:8.3f} ms")
     rep["ops"][k] = {"calls": v[0] // STEPS, "ms": v[1] / STEPS}
 print("GEMM by shape (M,N,K,a_mn,b_mn,epi,splits):")
-for k, v in sorted(by_gemm.items(), key=lambda kv: -kv[1][1])[:60]:
+for k, v in sorted(by_gemm.items(), key=lambda kv: -kv[1][1])[:90]:
+    if isinstance(k[0], str) and k[0].startswith("bn_"):
+        M, C = k[1:3]
+        by = (4.0 + 2.0 * k[3]) * M * C if k[0] == "bn_fwd" else (10.0 + 2.0 * k[3]) * M * C
+        print(f"  {str(k):46s} n={v[0]//STEPS:3d} {v[1]/STEPS:7.3f} ms  {by*v[0]/v[1]/1e6:7.0f} GB/s (algorithmic)")
+        rep["gemm"].append({"key": list(k), "calls": v[0] // STEPS, "ms": v[1] / STEPS, "gbs": by * v[0] / v[1] / 1e6})
+        continue
     if isinstance(k[0], str):
         M, N, K = k[1:4]
         by = 2.0 * (M * N + N * K + M * K / 9.0) if k[0] == "conv_fwd" else 2.0 * (K * M + K * N / 9.0 + 2 * M * N)
