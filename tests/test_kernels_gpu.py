@@ -307,9 +307,10 @@ def _nchw(x, N, H, W):
     return x.float().view(N, H, W, -1).permute(0, 3, 1, 2)
 
 
-def test_pools(ops, cuda_device):
+@pytest.mark.parametrize("H,W", [(18, 18), (17, 21), (112, 112)])
+def test_pools(ops, cuda_device, H, W):
     torch.manual_seed(9)
-    N, C, H, W = 3, 64, 18, 18
+    N, C = 3, 64
     x = torch.randn(N, C, H, W, device=cuda_device).to(bf16).float()
     out, arg, Ho, Wo = ops.maxpool_fwd(_nhwc(x), N, H, W, C)
     xf = x.clone().requires_grad_(True)
