@@ -546,16 +546,13 @@ template <int STRIDE>
 __global__ void __launch_bounds__(256, 3)
 col2im3x3_kernel(const __nv_bfloat16* __restrict__ dcols, const __nv_bfloat16* __restrict__ addend, int N, int H,
                  int W, int C, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  // blockIdx.x = input row (n, hi); blockIdx.y * blockDim.x + threadIdx.x = wi * G + g (32-bit index math only)
   const int G = C >> 3;
-  const long long total = static_cast<long long>(N) * H * W * G;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % G);
-    long long t = i / G;
-    const long long pix = t;
-    const int wi = static_cast<int>(t % W); t /= W;
-    const int hi = static_cast<int>(t % H);
-    const int n = static_cast<int>(t / H);
+  const int col = blockIdx.y * blockDim.x + threadIdx.x;
+  if (col < W * G) {
+    const int wi = col / G, g = col - wi * G;
+    const int n = blockIdx.x / H, hi = blockIdx.x - n * H;
+    const long long pix = static_cast<long long>(blockIdx.x) * W + wi;
     const long long img_base = static_cast<long long>(n) * Ho * Wo;
     uint4 v[9];
 #pragma unroll
@@ -686,24 +683,24 @@ subsample_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C
 __global__ void __launch_bounds__(256)
 upsample_add_kernel(const __nv_bfloat16* __restrict__ dsub, const __nv_bfloat16* __restrict__ addend, int N, int H,
                     int W, int C, int stride, int Ho, int Wo, __nv_bfloat16* __restrict__ dx) {
+  // blockIdx.x = input row (n, hi); blockIdx.y * blockDim.x + threadIdx.x = wi * G + g; both loads issued together
   const int G = C >> 3;
-  const long long total = static_cast<long long>(N) * H * W * G;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % G);
-    long long t = i / G;
-    const int wi = static_cast<int>(t % W); t /= W;
-    const int hi = static_cast<int>(t % H);
-    const int n = static_cast<int>(t / H);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (addend != nullptr) load8(addend + (i / G) * C + g * 8, acc);
-    if (hi % stride == 0 && wi % stride == 0 && hi / stride < Ho && wi / stride < Wo) {
-      float v[8];
-      load8(dsub + ((static_cast<long long>(n) * Ho + hi / stride) * Wo + wi / stride) * C + g * 8, v);
+  const int col = blockIdx.y * blockDim.x + threadIdx.x;
+  if (col < W * G) {
+    const int wi = col / G, g = col - wi * G;
+    const int n = blockIdx.x / H, hi = blockIdx.x - n * H;
+    const long long off = (static_cast<long long>(blockIdx.x) * W + wi) * C + g * 8;
+    const bool on_grid = hi % stride == 0 && wi % stride == 0 && hi / stride < Ho && wi / stride < Wo;
+    const uint4 ra = addend != nullptr ? __ldg(reinterpret_cast<const uint4*>(addend + off)) : make_uint4(0, 0, 0, 0);
+    const uint4 rs = on_grid ? __ldg(reinterpret_cast<const uint4*>(
+                                   dsub + ((static_cast<long long>(n) * Ho + hi / stride) * Wo + wi / stride) * C + g * 8))
+                             : make_uint4(0, 0, 0, 0);
+    float acc[8], v[8];
+    unpack8(ra, acc);
+    unpack8(rs, v);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += v[k];
-    }
-    store8(dx + (i / G) * C + g * 8, acc);
+    for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    store8(dx + off, acc);
   }
 }
 
@@ -913,10 +910,12 @@ B200MM_API int b200mm_col2im_nhwc(const void* dcols, const void* addend, int N, 
   const __nv_bfloat16* dc = static_cast<const __nv_bfloat16*>(dcols);
   const __nv_bfloat16* ad = static_cast<const __nv_bfloat16*>(addend);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dx);
+  const dim3 grid2(N * H, (W * (C >> 3) + 255) / 256);
+  if (static_cast<long long>(N) * H > 0x7fffffffLL) return B200MM_ERR_BAD_ARG;
   if (KH == 3 && KW == 3 && pad == 1 && stride == 1)
-    col2im3x3_kernel<1><<<grid, 256, 0, s>>>(dc, ad, N, H, W, C, Ho, Wo, o);
+    col2im3x3_kernel<1><<<grid2, 256, 0, s>>>(dc, ad, N, H, W, C, Ho, Wo, o);
   else if (KH == 3 && KW == 3 && pad == 1 && stride == 2)
-    col2im3x3_kernel<2><<<grid, 256, 0, s>>>(dc, ad, N, H, W, C, Ho, Wo, o);
+    col2im3x3_kernel<2><<<grid2, 256, 0, s>>>(dc, ad, N, H, W, C, Ho, Wo, o);
   else
     col2im_kernel<<<grid, 256, 0, s>>>(dc, ad, N, H, W, C, KH, KW, stride, pad, Ho, Wo, o);
   B200MM_CHECK_LAUNCH();
@@ -948,8 +947,8 @@ B200MM_API int b200mm_upsample_add_nhwc(const void* dsub, const void* addend, in
                                         void* dx, void* stream) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || stride <= 0) return B200MM_ERR_BAD_ARG;
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  upsample_add_kernel<<<grid_for(static_cast<long long>(N) * H * W * (C >> 3), 256), 256, 0,
-                        static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dsub),
+  if (static_cast<long long>(N) * H > 0x7fffffffLL) return B200MM_ERR_BAD_ARG;
+  upsample_add_kernel<<<dim3(N * H, (W * (C >> 3) + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(dsub),
                                                              static_cast<const __nv_bfloat16*>(addend), N, H, W, C,
                                                              stride, Ho, Wo, static_cast<__nv_bfloat16*>(dx));
   B200MM_CHECK_LAUNCH();
