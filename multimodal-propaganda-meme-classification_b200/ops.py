@@ -6,6 +6,8 @@ a CUDA device and libb200mm.so must load, otherwise these raise.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -169,6 +171,18 @@ def linear_wgrad(dy, x, dw):
     return gemm_raw(dy, True, x, True, N, K, M, dw, epi=EPI_F32_ATOMIC, splits=_wgrad_splits(N, K, M))
 
 
+def _halo_conv_taken(H, W, C, Cout, ksize, stride, pad) -> bool:
+    """Mirror of the dispatch in b200mm_conv_fwd / b200mm_conv_wgrad (csrc/gemm_tcgen05.cu, csrc/conv3x3_c64.cu
+    c3_geometry): those launches run conv3x3_c64_*_kernel, not gemm_bf16_kernel, and are kept out of the GEMM
+    kernel's roofline profile."""
+    if os.environ.get("B200MM_HALO_CONV", "1").startswith("0"):
+        return False
+    if not (ksize == 3 and stride == 1 and pad == 1 and C == 64 and Cout == 64 and 6 <= W <= 61):
+        return False
+    R = min(128 // (W + 2), H)
+    return (R + 2) * (W + 2) <= 256
+
+
 def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False, out=None, col_stats=None):
     """Implicit-GEMM convolution: x NHWC bf16 [N*H*W, C] (C % 64 == 0), w [Cout, k*k*C] -> ([N*P*Q, Cout], P, Q)."""
     Cout = w.shape[0]
@@ -176,6 +190,9 @@ def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False,
     if out is None:
         out = torch.empty(N * P * Q, Cout, device=x.device, dtype=bf16)
     prof = _gemm_profile
+    if prof is not None and residual is None and not relu and out.stride(0) == 64 and \
+            _halo_conv_taken(H, W, C, Cout, ksize, stride, pad):
+        prof = None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -194,6 +211,8 @@ def conv_wgrad(dy, x, N, H, W, C, ksize, stride, pad, dw):
     Cout = dy.shape[1]
     pixels = dy.shape[0]
     prof = _gemm_profile
+    if prof is not None and dy.stride(0) == 64 and _halo_conv_taken(H, W, C, Cout, ksize, stride, pad):
+        prof = None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
