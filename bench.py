@@ -210,12 +210,14 @@ def run_ensemble(args, dev, world, rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -309,26 +311,40 @@ def run_engine(args):
         while True:
             yield host
 
+    from b200mm.loop import StepReadback
     e2e_iter = iter(DevicePrefetcher(endless(), dev))
+    readback = StepReadback(dev)
+    e2e_results = []
 
     def step_e2e():
         opt.zero_grad()
         t, i, m, l, _ = next(e2e_iter)
         _, loss, ok = model.train_step_fused(t, i, m, l)
         opt.step()
-        return loss.item(), ok.item()        # the reference's per-step D2H reads (.txt:218-220)
+        # the reference's per-step loss / accuracy D2H reads (.txt:218-220) as b200mm.train() does them: this step's
+        # two scalars are copied to pinned host memory asynchronously and consumed while the next step runs
+        done = readback.push(loss, ok)
+        if done is not None:
+            e2e_results.append(done)
+
+    def finish_e2e():                        # the last step's result, still inside the timed region
+        done = readback.flush()
+        if done is not None:
+            e2e_results.append(done)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -386,9 +402,14 @@ def run_engine(args):
     if not args.no_e2e:
         for _ in range(2):
             step_e2e()
-        ms_e = timed(step_e2e, args.steps) / args.steps
+        finish_e2e()
+        e2e_results.clear()
+        ms_e = timed(step_e2e, args.steps, finish=finish_e2e) / args.steps
+        assert len(e2e_results) == args.steps, "every timed step's loss / correct count must have reached the host"
         e2e = {"value": world * B / (ms_e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e}
+               "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e,
+               "readback": "loss + correct count of every step, asynchronous to pinned memory, consumed one step later",
+               "last_loss": e2e_results[-1][0]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:

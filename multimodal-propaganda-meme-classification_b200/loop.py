@@ -106,6 +106,46 @@ class DevicePrefetcher:
         return len(self.loader)
 
 
+class StepReadback:
+    """Per-step loss / correct-count readback without draining the launch queue.  The reference reads ``loss.item()``
+    right after ``optimizer.step()`` (.txt:218-220), which blocks the host until the whole step has run and leaves the
+    GPU idle while the next step's first kernels are being launched (about 1 ms of a 33 ms step here).  ``push`` queues
+    an asynchronous copy of this step's two scalars into pinned host memory and hands back the PREVIOUS step's values
+    (already complete by then); ``flush`` returns the last ones.  Every step's result still crosses to the host."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.host = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.dev = [torch.zeros(2, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.pending = None
+        self.i = 0
+
+    def _take(self):
+        if self.pending is None:
+            return None
+        slot = self.pending
+        self.events[slot].synchronize()
+        self.pending = None
+        return float(self.host[slot][0]), int(round(float(self.host[slot][1])))
+
+    def push(self, loss, ok):
+        prev = self._take()
+        slot = self.i & 1
+        self.i += 1
+        self.dev[slot][0].copy_(loss.reshape(()), non_blocking=True)
+        self.dev[slot][1].copy_(ok.reshape(()), non_blocking=True)
+        self.host[slot].copy_(self.dev[slot], non_blocking=True)
+        self.events[slot].record(torch.cuda.current_stream(self.device))
+        self.pending = slot
+        return prev
+
+    def flush(self):
+        return self._take()
+
+    bytes_per_step = 8
+
+
 def _fused(criterion):
     return isinstance(criterion, (CrossEntropyLoss, SigmoidFocalLoss))
 
@@ -116,13 +156,31 @@ def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_
     correct = 0
     n = 0
     fused = _fused(criterion) and hasattr(model, "train_step_fused")
+    readback = StepReadback(device) if fused else None
+    prev_bs = 0
+
+    def account(done, bs):
+        nonlocal train_loss, correct
+        train_loss += done[0] * bs
+        correct += done[1]
+        if on_step is not None:
+            on_step(done[0], bs)
+
     for text, image, mask, labels, data in DevicePrefetcher(train_loader, device):
         optimizer.zero_grad()
         if fused:
             _, loss, ok = model.train_step_fused(text, image, mask, labels, loss_kind=criterion.loss_kind,
                                                  alpha=criterion.alpha, gamma=criterion.gamma)
             optimizer.step()
-            loss_v, ok_v = loss.item(), ok.item()     # the reference's two per-step D2H syncs (.txt:218-220)
+            if scheduler is not None:
+                scheduler.step()
+            # the reference's per-step loss / accuracy reads (.txt:218-220), one step late so the host never waits
+            done = readback.push(loss, ok)
+            if done is not None:
+                account(done, prev_bs)
+            prev_bs = labels.size(0)
+            n += prev_bs
+            continue
         else:
             output = model(text, image, mask)
             loss = criterion(output, labels)
@@ -139,6 +197,10 @@ def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_
         n += bs
         if on_step is not None:
             on_step(loss_v, bs)
+    if readback is not None:
+        done = readback.flush()
+        if done is not None:
+            account(done, prev_bs)
     denom = len(train_loader.dataset) if hasattr(train_loader, "dataset") else n
     return train_loss / denom, correct / denom
 
