@@ -94,7 +94,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = w_first; w < num_work; w += w_step) {
@@ -106,6 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int k_begin = split * p.k_iters_per_split;
         const int k_end = min(k_begin + p.k_iters_per_split, p.k_iters);
         int a_n0 = 0, a_p0 = 0, a_q0 = 0;   // first output pixel of this M tile (im2col A operand)
+        int a_cb = 0, a_kw = 0, a_kh = 0;   // channel slab / filter tap of the current reduction block
         if (p.a_im2col) {
           const int pq = p.conv_P * p.conv_Q;
           const int m0 = m_blk * GEMM_BM;
@@ -113,6 +114,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const int r0 = m0 - a_n0 * pq;
           a_p0 = r0 / p.conv_Q;
           a_q0 = r0 - a_p0 * p.conv_Q;
+          const int tap = k_begin / p.conv_cblocks;
+          a_cb = k_begin - tap * p.conv_cblocks;
+          a_kh = tap / p.conv_KW;
+          a_kw = tap - a_kh * p.conv_KW;
+        }
+        // im2col B operand (implicit-GEMM weight gradient): the (tap, channel) of each 64-column atom is fixed for the
+        // work unit and the pixel coordinates of the reduction block advance by 64 per iteration -- no divisions in
+        // the k loop (with ten of them per iteration this thread, not the tensor pipe, paced the layer 2-4 wgrads)
+        int b_c0[BN / 64], b_kw[BN / 64], b_kh[BN / 64], b_atoms = 0;
+        int b_n0 = 0, b_p0 = 0, b_q0 = 0;
+        if (p.b_im2col) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) {
+            const int col = n_blk * BN + j * 64;
+            const int tap = col / p.conv_C;
+            b_c0[j] = col - tap * p.conv_C;
+            b_kh[j] = tap / p.conv_KW;
+            b_kw[j] = tap - b_kh[j] * p.conv_KW;
+            if (col < p.N) b_atoms = j + 1;
+          }
+          const int pq = p.conv_P * p.conv_Q;
+          const int pix = k_begin * GEMM_BK;
+          b_n0 = pix / pq;
+          const int r0 = pix - b_n0 * pq;
+          b_p0 = r0 / p.conv_Q;
+          b_q0 = r0 - b_p0 * p.conv_Q;
         }
         for (int kb = k_begin; kb < k_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -120,9 +147,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (p.b_im2col) {
             // wgrad: only the 64-column atoms that exist (N = taps * C may end inside the tile) are loaded
-            int atoms = (p.N - n_blk * BN + 63) / 64;
-            atoms = atoms > BN / 64 ? BN / 64 : atoms;
-            mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + atoms * 8192);
+            mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + b_atoms * 8192);
           } else if (!PAIR || cta_rank == 0) {
             mbar_expect_tx(&full_bar[stage], CTAS * Cfg::STAGE_BYTES);   // pair: both CTAs' loads count on the leader
           }
@@ -147,11 +172,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             continue;
           }
           if (p.a_im2col) {
-            const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
-            const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
-            tma_load_im2col_4d(sa, &tma_a, &full_bar[stage], cb * 64, a_q0 * p.conv_stride - p.conv_pad,
-                               a_p0 * p.conv_stride - p.conv_pad, a_n0, static_cast<uint16_t>(kw),
-                               static_cast<uint16_t>(kh));
+            tma_load_im2col_4d(sa, &tma_a, &full_bar[stage], a_cb * 64, a_q0 * p.conv_stride - p.conv_pad,
+                               a_p0 * p.conv_stride - p.conv_pad, a_n0, static_cast<uint16_t>(a_kw),
+                               static_cast<uint16_t>(a_kh));
+            if (++a_cb == p.conv_cblocks) {               // next reduction block: next channel slab, then next tap
+              a_cb = 0;
+              if (++a_kw == p.conv_KW) { a_kw = 0; ++a_kh; }
+            }
           } else if (!p.a_mn) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
           } else {
@@ -160,21 +187,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + j * 64, kb * GEMM_BK);
           }
           if (p.b_im2col) {
-            const int pq = p.conv_P * p.conv_Q;
-            const int pix = kb * GEMM_BK;                 // first output pixel of this reduction block
-            const int n0 = pix / pq, r0 = pix - n0 * pq;
-            const int p0 = r0 / p.conv_Q, q0 = r0 - p0 * p.conv_Q;
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
-              const int col = n_blk * BN + j * 64;
-              if (col < p.N) {
-                const int tap = col / p.conv_C, c0 = col - tap * p.conv_C;
-                const int kh = tap / p.conv_KW, kw = tap - kh * p.conv_KW;
-                tma_load_im2col_4d(sb + j * 8192, &tma_b, &full_bar[stage], c0, q0 * p.conv_stride - p.conv_pad,
-                                   p0 * p.conv_stride - p.conv_pad, n0, static_cast<uint16_t>(kw),
-                                   static_cast<uint16_t>(kh));
-              }
+              if (j < b_atoms)
+                tma_load_im2col_4d(sb + j * 8192, &tma_b, &full_bar[stage], b_c0[j],
+                                   b_q0 * p.conv_stride - p.conv_pad, b_p0 * p.conv_stride - p.conv_pad, b_n0,
+                                   static_cast<uint16_t>(b_kw[j]), static_cast<uint16_t>(b_kh[j]));
             }
+            b_q0 += GEMM_BK;                              // first output pixel of the next reduction block
+            while (b_q0 >= p.conv_Q) { b_q0 -= p.conv_Q; ++b_p0; }
+            while (b_p0 >= p.conv_P) { b_p0 -= p.conv_P; ++b_n0; }
           } else if (!p.b_mn) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           } else {
