@@ -15,7 +15,7 @@ namespace b200 {
 namespace {
 
 constexpr int ST_KH = 7, ST_KW = 7, ST_CIN = 3, ST_STRIDE = 2, ST_PAD = 3;
-constexpr int ST_K = ST_KH * ST_KW * ST_CIN;   // 147
+static_assert(ST_KH * ST_KW * ST_CIN == 147, "patch rows are 147 taps padded to ST_KP");
 constexpr int ST_KP = 152;                     // padded K of the weight / gradient rows
 constexpr int ST_COUT = 64;
 constexpr int ST_THREADS = 256;

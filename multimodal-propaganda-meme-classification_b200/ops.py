@@ -187,6 +187,8 @@ def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False,
     """Implicit-GEMM convolution: x NHWC bf16 [N*H*W, C] (C % 64 == 0), w [Cout, k*k*C] -> ([N*P*Q, Cout], P, Q)."""
     Cout = w.shape[0]
     P, Q = conv_out_hw(H, W, ksize, stride, pad)
+    if not (x.is_contiguous() and w.is_contiguous()):
+        raise ValueError("conv_fwd: x must be a contiguous NHWC [N*H*W, C] tensor and w a contiguous [Cout, k*k*C] one")
     if out is None:
         out = torch.empty(N * P * Q, Cout, device=x.device, dtype=bf16)
     prof = _gemm_profile
@@ -210,6 +212,8 @@ def conv_wgrad(dy, x, N, H, W, C, ksize, stride, pad, dw):
     """dw[Cout, k*k*C] (fp32) += dy[N*P*Q, Cout]^T im2col(x)  -- im2col operand gathered by TMA."""
     Cout = dy.shape[1]
     pixels = dy.shape[0]
+    if not x.is_contiguous() or dy.stride(1) != 1:
+        raise ValueError("conv_wgrad: x must be contiguous NHWC and dy row-major")
     prof = _gemm_profile
     if prof is not None and dy.stride(0) == 64 and _halo_conv_taken(H, W, C, Cout, ksize, stride, pad):
         prof = None
