@@ -70,6 +70,22 @@ __device__ __forceinline__ uint32_t dropout_keep32(uint64_t seed, uint64_t chunk
   }
   return bits;
 }
+// keep-mask for 8 consecutive elements (bit i set = element i kept) from ONE Philox4x32-7 call (16-bit fields);
+// group8_idx = flat element index / 8, threshold = p_drop * 2^32 (the upper 16 bits are compared).  Every elementwise
+// dropout of the engine (GEMM epilogue, LayerNorm / embedding kernels, pooled-feature gather / scatter) draws its mask
+// here, forward and backward alike -- two 10-round calls per 8 elements made the LayerNorm backward ALU-bound.
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t group8_idx, uint32_t threshold) {
+  const uint32_t thr16 = threshold >> 16;
+  const uint4 r = philox4x32_r<7>(seed, group8_idx);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bits |= ((w[i] & 0xFFFFu) >= thr16 ? 1u : 0u) << (2 * i);
+    bits |= ((w[i] >> 16) >= thr16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;
+}
 // keep-mask for 4 consecutive elements: bit i set = element kept. threshold = p_drop * 2^32.
 __device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t group_idx, uint32_t threshold) {
   const uint4 r = philox4x32(seed, group_idx);

@@ -412,14 +412,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP) {
                   if constexpr (EPI == EPI_STORE_DROP) {
-                    const uint64_t gi = static_cast<uint64_t>(row * p.N + col) >> 2;
-                    const uint32_t k0 = dropout_keep4(p.seed, gi, p.drop_threshold);
-                    const uint32_t k1 = dropout_keep4(p.seed, gi + 1, p.drop_threshold);
+                    const uint32_t keep =
+                        dropout_keep8(p.seed, static_cast<uint64_t>(row * p.N + col) >> 3, p.drop_threshold);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                      x[i] = (k0 >> i) & 1 ? x[i] * p.inv_keep : 0.f;
-                      x[4 + i] = (k1 >> i) & 1 ? x[4 + i] * p.inv_keep : 0.f;
-                    }
+                    for (int i = 0; i < 8; ++i) x[i] = (keep >> i) & 1 ? x[i] * p.inv_keep : 0.f;
                   }
                   if (res_row != nullptr && col_ok) {
                     // (row-strided per lane: relies on L1 to serve the other 16-byte pieces of each 128-byte line)

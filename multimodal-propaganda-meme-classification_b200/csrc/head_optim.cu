@@ -257,13 +257,9 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
     float v[8];
     load8(x + (r * stride_rows + offset_rows) * D + c, v);
     if (p_drop > 0.f) {
-      const uint64_t gi = static_cast<uint64_t>(r * D + c) >> 2;
-      const uint32_t k0 = dropout_keep4(seed, gi, threshold), k1 = dropout_keep4(seed, gi + 1, threshold);
+      const uint32_t keep = dropout_keep8(seed, static_cast<uint64_t>(r * D + c) >> 3, threshold);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        v[k] = (k0 >> k) & 1 ? v[k] * inv_keep : 0.f;
-        v[4 + k] = (k1 >> k) & 1 ? v[4 + k] * inv_keep : 0.f;
-      }
+      for (int k = 0; k < 8; ++k) v[k] = (keep >> k) & 1 ? v[k] * inv_keep : 0.f;
     }
     store8(out + r * D + c, v);
   }
@@ -285,13 +281,9 @@ scatter_rows_kernel(const __nv_bfloat16* __restrict__ dpooled, __nv_bfloat16* __
       const long long r = rel / stride_rows;
       load8(dpooled + r * D + c, v);
       if (p_drop > 0.f) {
-        const uint64_t gi = static_cast<uint64_t>(r * D + c) >> 2;
-        const uint32_t k0 = dropout_keep4(seed, gi, threshold), k1 = dropout_keep4(seed, gi + 1, threshold);
+        const uint32_t keep = dropout_keep8(seed, static_cast<uint64_t>(r * D + c) >> 3, threshold);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          v[k] = (k0 >> k) & 1 ? v[k] * inv_keep : 0.f;
-          v[4 + k] = (k1 >> k) & 1 ? v[4 + k] * inv_keep : 0.f;
-        }
+        for (int k = 0; k < 8; ++k) v[k] = (keep >> k) & 1 ? v[k] * inv_keep : 0.f;
       }
     }
     store8(dx + row * D + c, v);

@@ -29,13 +29,9 @@ static DropSpec make_drop(float p, unsigned long long seed) {
 }
 // keep-scale for the 8 consecutive elements starting at flat index `idx` (idx % 8 == 0)
 __device__ __forceinline__ void drop_scale8(const DropSpec& d, long long idx, float (&s)[8]) {
-  const uint32_t k0 = dropout_keep4(d.seed, static_cast<uint64_t>(idx >> 2), d.threshold);
-  const uint32_t k1 = dropout_keep4(d.seed, static_cast<uint64_t>(idx >> 2) + 1, d.threshold);
+  const uint32_t k = dropout_keep8(d.seed, static_cast<uint64_t>(idx >> 3), d.threshold);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    s[i] = (k0 >> i) & 1 ? d.inv_keep : 0.f;
-    s[4 + i] = (k1 >> i) & 1 ? d.inv_keep : 0.f;
-  }
+  for (int i = 0; i < 8; ++i) s[i] = (k >> i) & 1 ? d.inv_keep : 0.f;
 }
 
 // y = LN(x) * gamma + beta, optional dropout on y.  Stats saved for the backward.
