@@ -7,6 +7,7 @@
 // and their autograd backward passes.
 #include "common.cuh"
 #include "device_utils.cuh"
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -133,6 +134,10 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
 // in the forward) and optional second output dx2 = dropout-masked dx (out_drop: the mask that was applied to the
 // GEMM branch feeding this LN's input).  dgamma/dbeta are accumulated with fp32 atomics (pre-zeroed by caller
 // or holding the gradient to accumulate onto).
+// Rows reach the warps through a per-warp ring of LN_DEPTH shared-memory slots filled by 1-D bulk copies
+// (cp.async.bulk + mbarrier): the prefetch depth no longer costs registers (holding even one extra row of dy / x in
+// registers spilled, and with a single row in flight per warp the pass ran at 2.5 TB/s).
+constexpr int ln_depth(int nc) { return nc <= 4 ? 3 : 2; }   // D = 2048 with an addend: 2 x 3 rows x 4 KB x 8 warps
 template <int NC>
 __global__ void __launch_bounds__(LN_WARPS * 32, NC <= 3 ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
@@ -140,9 +145,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ addend,
                      __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx2, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int M, int D, int rows_per_cta, DropSpec in_drop, DropSpec out_drop) {
-  extern __shared__ float red[];  // [LN_WARPS][2][D]
+  // [LN_WARPS][LN_DEPTH][dy row | x row] bf16 while rows stream; reused as float [LN_WARPS][2][D] for the column sums
+  constexpr int LN_DEPTH = ln_depth(NC);
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  __shared__ uint64_t bars[LN_WARPS][LN_DEPTH];
+  float* red = reinterpret_cast<float*>(ln_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = D >> 3;
+  const uint32_t row_bytes = static_cast<uint32_t>(D) * 2;
+  const uint32_t slot_rows = addend != nullptr ? 3u : 2u;   // dy | x (| addend)
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * LN_DEPTH * slot_rows * row_bytes;
   float ag[NC][8], ab[NC][8];
 #pragma unroll
   for (int j = 0; j < NC; ++j)
@@ -151,25 +163,41 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 
   const long long row_begin = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long row_end = min(row_begin + rows_per_cta, static_cast<long long>(M));
-  // software pipeline: the next row's dy / x are in flight while this row's two warp reductions run
-  uint4 nd[NC], nx[NC];
-  auto fetch = [&](long long r) {
+  if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      const int c = lane + j * 32;
-      if (c < chunks) {
-        nd[j] = __ldg(reinterpret_cast<const uint4*>(dy + r * D + c * 8));
-        nx[j] = __ldg(reinterpret_cast<const uint4*>(x + r * D + c * 8));
-      }
-    }
+    for (int s = 0; s < LN_DEPTH; ++s) mbar_init(&bars[warp][s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  auto issue = [&](long long r, int s) {   // lane 0: both rows of slot s
+    uint8_t* dst = ring + static_cast<size_t>(s) * slot_rows * row_bytes;
+    mbar_expect_tx(&bars[warp][s], slot_rows * row_bytes);
+    bulk_load_1d(dst, dy + r * D, row_bytes, &bars[warp][s]);
+    bulk_load_1d(dst + row_bytes, x + r * D, row_bytes, &bars[warp][s]);
+    if (addend != nullptr) bulk_load_1d(dst + 2 * row_bytes, addend + r * D, row_bytes, &bars[warp][s]);
   };
-  if (row_begin + warp < row_end) fetch(row_begin + warp);
-  for (long long row = row_begin + warp; row < row_end; row += LN_WARPS) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    uint4 cd[NC], cx[NC];
+  if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < NC; ++j) { cd[j] = nd[j]; cx[j] = nx[j]; }
-    if (row + LN_WARPS < row_end) fetch(row + LN_WARPS);
+    for (int s = 0; s < LN_DEPTH; ++s) {
+      const long long r = row_begin + warp + static_cast<long long>(s) * LN_WARPS;
+      if (r < row_end) issue(r, s);
+    }
+  }
+  // per-row statistics: lane l holds those of the warp's (32 k + l)-th row, handed out by shuffle (a dependent
+  // scalar load at the top of every row cost a DRAM round trip per row)
+  float lane_mean = 0.f, lane_rstd = 0.f;
+  int it = 0;
+  for (long long row = row_begin + warp; row < row_end; row += LN_WARPS, ++it) {
+    const int slot = it % LN_DEPTH;
+    if ((it & 31) == 0) {
+      const long long r = row + static_cast<long long>(lane) * LN_WARPS;
+      lane_mean = r < row_end ? mean_in[r] : 0.f;
+      lane_rstd = r < row_end ? rstd_in[r] : 0.f;
+    }
+    const float mean = __shfl_sync(0xffffffffu, lane_mean, it & 31);
+    const float rstd = __shfl_sync(0xffffffffu, lane_rstd, it & 31);
+    mbar_wait(&bars[warp][slot], (it / LN_DEPTH) & 1);
+    const uint8_t* src = ring + static_cast<size_t>(slot) * slot_rows * row_bytes;
     float g_dy[NC][8], xh[NC][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -177,8 +205,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       const int c = lane + j * 32;
       if (c < chunks) {
         float d[8], xv[8];
-        unpack8(cd[j], d);
-        unpack8(cx[j], xv);
+        unpack8(*reinterpret_cast<const uint4*>(src + c * 16), d);
+        unpack8(*reinterpret_cast<const uint4*>(src + row_bytes + c * 16), xv);
         if (in_drop.p > 0.f) {
           float s[8];
           drop_scale8(in_drop, row * D + c * 8, s);
@@ -212,7 +240,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         for (int i = 0; i < 8; ++i) o[i] = rstd * (g_dy[j][i] - s1 - xh[j][i] * s2);
         if (addend != nullptr) {   // pre-LN blocks: the residual stream's gradient joins here (dx2 stays LN-only)
           float a[8], t[8];
-          load8(addend + row * D + c * 8, a);
+          unpack8(*reinterpret_cast<const uint4*>(src + 2 * row_bytes + c * 16), a);
 #pragma unroll
           for (int i = 0; i < 8; ++i) t[i] = o[i] + a[i];
           store8(dx + row * D + c * 8, t);
@@ -228,8 +256,15 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
       }
     }
+    // all of this row's slot reads are complete (their values were stored above): refill the slot LN_DEPTH rows ahead
+    __syncwarp();
+    if (lane == 0) {
+      const long long nr = row + static_cast<long long>(LN_DEPTH) * LN_WARPS;
+      if (nr < row_end) issue(nr, slot);
+    }
   }
   // cross-warp reduction of the column sums, then one atomic per column per CTA
+  __syncthreads();   // every warp is done with its ring slots: the buffer turns into the float staging area
   float* rg = red + warp * 2 * D;
   float* rb = rg + D;
 #pragma unroll
@@ -431,23 +466,29 @@ B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* 
                                     void* stream) {
   if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
   const DeviceInfo& dev = device_info();
-  // two resident CTAs per SM, one wave: every CTA ends with 2*D fp32 atomics onto the same 2*D addresses, so the
-  // CTA count is kept at the residency limit (4x fewer atomics than 4 CTAs/SM, same bandwidth)
-  const int target_ctas = dev.num_sms > 0 ? dev.num_sms * 2 : 296;
-  int rows_per_cta = ceil_div(M, target_ctas);
-  rows_per_cta = ceil_div(rows_per_cta, LN_WARPS) * LN_WARPS;
-  const int grid = ceil_div(M, rows_per_cta);
-  const size_t smem = static_cast<size_t>(LN_WARPS) * 2 * D * sizeof(float);
   const int nc = ceil_div(D, 256);
+  const int nc_inst = nc <= 4 ? nc : 8;
+  // ring: LN_WARPS x depth x (dy row + x row (+ addend row)) bf16; >= the 8 D bytes per warp of the float staging
+  const size_t smem =
+      static_cast<size_t>(LN_WARPS) * ln_depth(nc_inst) * (addend != nullptr ? 3 : 2) * D * sizeof(__nv_bfloat16);
+  // one wave of resident CTAs (every CTA ends with 2*D fp32 atomics onto the same 2*D addresses)
 #define LAUNCH_LN_BWD(NC)                                                                                          \
   do {                                                                                                             \
     static bool configured = false;                                                                                \
     if (!configured) {                                                                                             \
       cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                           LN_WARPS * 2 * NC * 256 * 4);                                           \
+                                           LN_WARPS * ln_depth(NC) * 3 * NC * 256 * 2);                            \
       if (e != cudaSuccess) return static_cast<int>(e);                                                            \
       configured = true;                                                                                           \
     }                                                                                                              \
+    int resident = 1;                                                                                              \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, layernorm_bwd_kernel<NC>, LN_WARPS * 32, smem) != \
+            cudaSuccess || resident < 1)                                                                           \
+      resident = 1;                                                                                                \
+    const int target_ctas = (dev.num_sms > 0 ? dev.num_sms : 148) * resident;                                      \
+    int rows_per_cta = ceil_div(M, target_ctas);                                                                   \
+    rows_per_cta = ceil_div(rows_per_cta, LN_WARPS) * LN_WARPS;                                                    \
+    const int grid = ceil_div(M, rows_per_cta);                                                                    \
     layernorm_bwd_kernel<NC><<<grid, LN_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                    \
         static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd, gamma,            \
         static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(dx),                                \

@@ -610,10 +610,11 @@ def test_embedding_variants_fwd_bwd(ops, cuda_device):
     assert rel(dword, dword_ref) < 1e-5 and rel(dpos, dpos_ref) < 1e-5
 
 
-def test_layernorm_bwd_addend(ops, cuda_device):
-    """pre-LN residual: dx = LN_bwd(dy) + addend."""
+@pytest.mark.parametrize("M,D", [(300, 256), (20000, 768), (1100, 1024), (96, 2048)])
+def test_layernorm_bwd_addend(ops, cuda_device, M, D):
+    """pre-LN residual: dx = LN_bwd(dy) + addend.  (20000 rows: > 32 rows per warp, the per-lane row statistics are
+    reloaded; 2048: the two-slot ring.)"""
     g = torch.Generator().manual_seed(9)
-    M, D = 300, 256
     dev = cuda_device
     x = torch.randn(M, D, generator=g).to(dev).to(torch.bfloat16)
     dy = torch.randn(M, D, generator=g).to(dev).to(torch.bfloat16)
