@@ -1,8 +1,10 @@
 """Image tower: torchvision-style ResNet (Bottleneck, v1.5) with explicit forward / backward on the sm_100a
-kernels.  Activations are NHWC bf16 token matrices [N*H*W, C]; every convolution is the tcgen05 GEMM
-(1x1: directly on the activation matrix; 3x3: implicit GEMM, the activation operand gathered by im2col-mode TMA
-loads; 7x7 stem and the three stride-2 data gradients: explicit im2col / col2im); BatchNorm runs in training mode
-with per-replica batch statistics exactly like the reference.
+kernels.  Activations are NHWC bf16 token matrices [N*H*W, C]; every convolution runs on tcgen05
+(1x1: the GEMM directly on the activation matrix; 3x3: implicit GEMM, the activation operand gathered by im2col-mode
+TMA loads -- at 64 channels the halo-resident kernels of csrc/conv3x3_c64.cu, picked inside b200mm_conv_fwd /
+b200mm_conv_wgrad; 7x7 stem: csrc/stem_conv.cu straight from the fp32 image, no im2col matrix; the three stride-2
+data gradients: explicit col2im); BatchNorm runs in training mode with per-replica batch statistics exactly like the
+reference.
 
 Mirrors ``self.resnet(image)`` of example_scripts/Multimodal_example_task2C.txt:164, :183 ->
 torchvision/models/resnet.py:108-163 (Bottleneck), :197-213 (stem, init), :266-280 (_forward_impl).
