@@ -63,6 +63,19 @@ def test_gemm_dgrad_wgrad(ops, cuda_device, M, N, K):
     assert rel(db, dy.float().sum(0)) < 1e-3
 
 
+@pytest.mark.parametrize("M,N,ld", [(5000, 768, 768), (4100, 2304, 2304), (8192, 3072, 3072), (4097, 264, 264),
+                                    (6000, 768, 2304), (300, 768, 768), (20000, 64, 64)])
+def test_colsum_shapes(ops, cuda_device, M, N, ld):
+    """bias-gradient column sums: tall / wide / narrow shapes, strided rows (a column slice of a wider matrix),
+    accumulation onto an existing value."""
+    torch.manual_seed(3)
+    full = torch.randn(M, ld, device=cuda_device).to(bf16)
+    x = full[:, :N]
+    out = torch.full((N,), 2.0, device=cuda_device)
+    ops.colsum(x, out)
+    assert rel(out, x.float().sum(0) + 2.0) < 1e-3
+
+
 def test_gemm_dropout_epilogue(ops, cuda_device):
     torch.manual_seed(2)
     M, N, K = 512, 768, 256
