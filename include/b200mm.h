@@ -185,6 +185,13 @@ int b200mm_adam_step(float* p, const float* g, float* m, float* v, void* shadow_
                      float beta1, float beta2, float eps, float weight_decay, int step, const float* gradsq,
                      float max_norm, float grad_scale, void* stream);
 int b200mm_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+/* Data-parallel gradient payload in bf16 ("bf16 payload -> fp32 master update"): pack a gradient range
+ * pre-scaled by 1 / world size, and the optimizer / clip-norm variants that read the all-reduced bf16 buffer. */
+int b200mm_scale_cast_f32_to_bf16(const float* x, void* y, long long n, float scale, void* stream);
+int b200mm_sumsq_bf16(const void* g_bf16, long long n, float* out, void* stream);
+int b200mm_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, long long n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, int step, const float* gradsq,
+                         float max_norm, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,10 @@ def _nvcc() -> str:
     return exe
 
 
+def have_nvcc() -> bool:
+    return os.path.exists(shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc")
+
+
 def _sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

@@ -160,17 +160,31 @@ head_loss_kernel(const __nv_bfloat16* __restrict__ feat, const float* __restrict
 
 // ------------------------------------------------------------------ optimizer
 // sum of squares of a flat fp32 buffer -> *out (accumulate)
+// four consecutive gradient elements as fp32, from an fp32 or a bf16 buffer (the data-parallel payload is bf16)
+__device__ __forceinline__ float4 load_grad4(const float* g, long long i) {
+  return __ldg(reinterpret_cast<const float4*>(g) + i);
+}
+__device__ __forceinline__ float4 load_grad4(const __nv_bfloat16* g, long long i) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(g) + i);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float grad_as_float(float x) { return x; }
+__device__ __forceinline__ float grad_as_float(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename G>
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+sumsq_kernel(const G* __restrict__ g, long long n, float* __restrict__ out) {
   float s = 0.f;
   const long long n4 = n >> 2;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 v = load_grad4(g, i);
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (long long i = n4 << 2; i < n; ++i) s += g[i] * g[i];
+    for (long long i = n4 << 2; i < n; ++i) s += grad_as_float(g[i]) * grad_as_float(g[i]);
   __shared__ float red[8];
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -189,8 +203,9 @@ sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) 
 //   p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
 // clip = min(1, max_norm / (sqrt(*gradsq) + 1e-6)) when gradsq != nullptr (torch.nn.utils.clip_grad_norm_).
 // Also refreshes the bf16 shadow copy the GEMMs read (shadow may be nullptr).
+template <typename G>
 __global__ void __launch_bounds__(256)
-adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adam_kernel(float* __restrict__ p, const G* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __nv_bfloat16* __restrict__ shadow, long long n, float step_size, float inv_sqrt_bc2, float b1, float b2,
             float eps, float weight_decay, const float* __restrict__ gradsq, float max_norm, float grad_scale) {
   float clip = grad_scale;
@@ -202,7 +217,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    const float4 gg = load_grad4(g, i);
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float pa[4] = {pp.x, pp.y, pp.z, pp.w};
@@ -230,14 +245,14 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 __global__ void __launch_bounds__(256)
-cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n, float scale) {
   const long long n4 = n >> 2;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     uint2 o;
-    o.x = pack_bf16x2_dev(v.x, v.y);
-    o.y = pack_bf16x2_dev(v.z, v.w);
+    o.x = pack_bf16x2_dev(v.x * scale, v.y * scale);
+    o.y = pack_bf16x2_dev(v.z * scale, v.w * scale);
     reinterpret_cast<uint2*>(y)[i] = o;
   }
 }
@@ -334,7 +349,15 @@ B200MM_API int b200mm_head_loss(const void* feat, const float* W, const float* b
 
 B200MM_API int b200mm_sumsq_f32(const float* g, long long n, float* out, void* stream) {
   if (n <= 0) return B200MM_ERR_BAD_ARG;
-  sumsq_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+  sumsq_kernel<float><<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+// same over a bf16 buffer (the all-reduced data-parallel gradient payload)
+B200MM_API int b200mm_sumsq_bf16(const void* g, long long n, float* out, void* stream) {
+  if (n <= 0) return B200MM_ERR_BAD_ARG;
+  sumsq_kernel<__nv_bfloat16><<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(g), n, out);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -346,9 +369,24 @@ B200MM_API int b200mm_adam_step(float* p, const float* g, float* m, float* v, vo
   if (n <= 0 || (n & 3) || step < 1) return B200MM_ERR_BAD_ARG;
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-  adam_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  adam_kernel<float><<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, static_cast<float>(lr / bc1),
       static_cast<float>(1.0 / sqrt(bc2)), beta1, beta2, eps, weight_decay, gradsq, max_norm, grad_scale);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+// The same step reading the gradient from a bf16 buffer: under data parallelism the all-reduced payload is bf16
+// (half the NVLink bytes) while parameters and both moments stay fp32 -- 28 B / parameter instead of 30.
+B200MM_API int b200mm_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, long long n,
+                                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                    const float* gradsq, float max_norm, float grad_scale, void* stream) {
+  if (n <= 0 || (n & 3) || step < 1) return B200MM_ERR_BAD_ARG;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adam_kernel<__nv_bfloat16><<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, static_cast<const __nv_bfloat16*>(g_bf16), m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n,
+      static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)), beta1, beta2, eps, weight_decay, gradsq,
+      max_norm, grad_scale);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -356,7 +394,16 @@ B200MM_API int b200mm_adam_step(float* p, const float* g, float* m, float* v, vo
 B200MM_API int b200mm_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
   if (n <= 0 || (n & 3)) return B200MM_ERR_BAD_ARG;
   cast_f32_bf16_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<__nv_bfloat16*>(y), n);
+      x, static_cast<__nv_bfloat16*>(y), n, 1.f);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+// y = bf16(x * scale): packs a gradient range for the data-parallel all-reduce (scale = 1 / world size, applied
+// BEFORE the sum so the bf16 partial sums stay in range)
+B200MM_API int b200mm_scale_cast_f32_to_bf16(const float* x, void* y, long long n, float scale, void* stream) {
+  if (n <= 0 || (n & 3)) return B200MM_ERR_BAD_ARG;
+  cast_f32_bf16_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n, scale);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

@@ -141,11 +141,11 @@ class MultimodalClassifierHEAD(MultimodalClassifier):
         return [{"params": groups[0], "lr": lr}, {"params": groups[1], "lr": lr * 0.8},
                 {"params": groups[2], "lr": lr * 0.8}]
 
-    def enable_data_parallel(self, group=None, bucket_elems: int = 64 * 1024 * 1024):
+    def enable_data_parallel(self, group=None, bucket_elems: int = 64 * 1024 * 1024, payload: str = "bf16"):
         from .ddp import GradSync
         is_text = lambda n: n.startswith("text_model.") or n.startswith("caption_text_model.")   # noqa: E731
-        self.grad_sync = GradSync(self.store, group, bucket_elems,
-                                  phase_predicates={"text": is_text, "rest": lambda n: not is_text(n)})
+        self.grad_sync = GradSync(self.store, group, bucket_elems, payload=payload,
+                                  phases=[("text", is_text)] + self.img.grad_phases() + [("rest", lambda n: True)])
         bufs = [self.img.buffers] + [t for pair in self.bn_buffers.values() for t in pair]
         self.grad_sync.broadcast_parameters(bufs)
         self.store.refresh_shadow()
@@ -264,9 +264,12 @@ class MultimodalClassifierHEAD(MultimodalClassifier):
         d_f1 = ops.relu_bwd(d_f1, f1)
         ops.linear_wgrad(d_f1, feat, st.g("image_model.fine_tune.0.weight"))
         ops.colsum(d_f1, st.g("image_model.fine_tune.0.bias"))
-        self.img.backward(ops.linear_dgrad(d_f1, st.s("image_model.fine_tune.0.weight")))
+        self.img.backward(ops.linear_dgrad(d_f1, st.s("image_model.fine_tune.0.weight")),
+                          on_grads_ready=sync.ready if sync is not None else None)
         if sync is not None:
             sync.ready("rest")
+            if not getattr(self, "_defer_grad_sync", False):
+                sync.finish_into_grad()
         self._saved = None
         self._attach_grads()
 

@@ -269,9 +269,26 @@ class ImageTower:
         self._saved = sv
         return logits
 
+    # ------------------------------------------------------------------ data-parallel gradient phases
+    def grad_phases(self):
+        """Ordered (tag, predicate) list for ddp.GradSync: the convolution weights of layer4 (+ fc), layer3, layer2,
+        layer1 -- the order the backward finishes them.  The stem and the BatchNorm affine parameters (tiny, and stored
+        in the shadow-less prefix of the flat buffer) fall to the model's catch-all last phase."""
+        pre = self.cfg.prefix
+        n_stage = len(self.cfg.layers)
+        out = []
+        for li in reversed(range(n_stage)):
+            stem = f"{pre}.layer{li + 1}."
+            fc = f"{pre}.fc.weight" if li == n_stage - 1 else None
+            out.append((f"{pre}.layer{li + 1}",
+                        lambda n, stem=stem, fc=fc: (n.startswith(stem) and n.endswith(".weight")
+                                                     and (".conv" in n or ".downsample.0." in n)) or n == fc))
+        return out
+
     # ------------------------------------------------------------------ backward
-    def backward(self, dlogits: torch.Tensor):
-        """dlogits: bf16 [N, 1000]. Accumulates parameter gradients (the image itself needs none)."""
+    def backward(self, dlogits: torch.Tensor, on_grads_ready=None):
+        """dlogits: bf16 [N, 1000]. Accumulates parameter gradients (the image itself needs none).
+        on_grads_ready(tag): called as soon as every gradient of a ``grad_phases`` group is final."""
         sv = self._saved
         assert sv is not None, "backward() without a training-mode forward()"
         N = sv["N"]
@@ -283,7 +300,10 @@ class ImageTower:
         else:
             dpooled = dlogits.contiguous()
         d_out = ops.avgpool_bwd(dpooled, N, Hc * Wc, self.feat_dim)
-        for blk, s in zip(reversed(self.blocks), reversed(sv["blocks"])):
+        stage_of = [li for li, nb in enumerate(self.cfg.layers) for _ in range(nb)]
+        for bi, blk, s in zip(reversed(range(len(self.blocks))), reversed(self.blocks), reversed(sv["blocks"])):
+            if on_grads_ready is not None and bi + 1 < len(self.blocks) and stage_of[bi + 1] != stage_of[bi]:
+                on_grads_ready(f"{self.cfg.prefix}.layer{stage_of[bi + 1] + 1}")     # the stage above is complete
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
             if self.basic:
                 x, y1, a1, m1, r1, y2, m2, r2, xs, yd, md, rd, msk, Hi, Wi, Ho, Wo = s
@@ -341,6 +361,8 @@ class ImageTower:
                 else:
                     d_xs = ops.linear_dgrad(d_yd, ds.w)
                     d_out = ops.upsample_add(d_xs, d_x1, N, Hi, Wi, ds.cin, stride)
+        if on_grads_ready is not None:
+            on_grads_ready(f"{self.cfg.prefix}.layer1")
         cols, direct, c0, a0, m0, r0, arg, H1, W1 = sv["stem"]
         st = self.stem
         d_a0 = ops.maxpool_bwd(d_out, arg, N, H1, W1, st.cout)

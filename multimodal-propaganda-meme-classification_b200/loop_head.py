@@ -14,8 +14,10 @@ with a single-logit head + sigmoid focal loss (``MultimodalClassifier(num_classe
 also carry ``caption_text`` / ``caption_text_mask``, :293-303).
 
 What is deliberately NOT reproduced: clipping before un-scaling under AMP (:712-717) --
-the engine is bf16 with fp32 master weights and needs no loss scaling, so ``scaler`` is accepted and ignored and the
-fp32 branch's clip threshold (10.0, :728-730) is the default.
+the engine is bf16 with fp32 master weights and needs no loss scaling, so ``scaler`` is accepted and ignored; the
+fp32 branch's ``clip_grad_norm_(model.parameters(), 10.0)`` (:728-730) is ENFORCED by ``train`` on every step: a
+``FusedAdam`` without a clip threshold gets ``max_grad_norm = 10.0`` (the clip is folded into the Adam kernel), any
+other optimizer is preceded by ``torch.nn.utils.clip_grad_norm_``.
 """
 from __future__ import annotations
 
@@ -28,6 +30,9 @@ import torch
 from . import ensemble
 from .loop import ID2L, SigmoidFocalLoss, _extra_inputs, _fused, _to_device
 from .tsv import write_label_tsv, write_prob_tsv
+
+
+CLIP_NORM = 10.0   # clip_grad_norm_(model.parameters(), 10.0), Multimodal_example_task2C.py:713-715, 728-730
 
 
 def seed_everything(seed: int = 42) -> None:
@@ -144,6 +149,9 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
     check_interval = max(total_batches // 2, 1)
     batch_losses = []
     fused = _fused(criterion) and hasattr(model, "train_step_fused")
+    fused_optim = hasattr(optimizer, "max_grad_norm")
+    if fused_optim and optimizer.max_grad_norm is None:
+        optimizer.max_grad_norm = CLIP_NORM              # reference: clip_grad_norm_(..., 10.0) on every step
     for batch_idx, data in enumerate(train_loader, 1):
         optimizer.zero_grad()
         text, image, mask, labels = _to_device(data, device)
@@ -151,12 +159,16 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
         if fused:
             output, loss, ok = model.train_step_fused(text, image, mask, *extra, labels, loss_kind=criterion.loss_kind,
                                                       alpha=criterion.alpha, gamma=criterion.gamma)
+            if not fused_optim:
+                grad_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), CLIP_NORM)
             optimizer.step()
             loss_v, ok_v = loss.item(), ok.item()
         else:
             output = model(text, image, mask, *extra)
             loss = criterion(output, labels.float() if output.dim() == 1 else labels)
             loss.backward()
+            if not fused_optim:
+                grad_norm = torch.nn.utils.clip_grad_norm_(model.parameters(), CLIP_NORM)     # :728-730
             optimizer.step()
             loss_v = loss.item()
             pred = (_probs(output) > 0.5).float() if output.dim() == 1 or output.shape[-1] == 1 else output.argmax(1)
@@ -169,7 +181,7 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
         n += bs
         if batch_idx % 10 == 0:
             gn = getattr(optimizer, "last_grad_norm", None)
-            gn = float(gn.sqrt().item()) if gn is not None else float("nan")
+            gn = float(gn.sqrt().item()) if gn is not None else (float(grad_norm) if not fused_optim else float("nan"))
             log(f"TRAIN | Epoch [{epoch}] | Batch [{batch_idx}/{total_batches}] | "
                 f"Loss: {sum(batch_losses) / len(batch_losses):.4f} | LR: {scheduler.get_last_lr()[0]} | "
                 f"Grad Norm: {gn:.4f} |")

@@ -239,13 +239,16 @@ class MultimodalClassifier(nn.Module):
         d_pooled = ops.linear_dgrad(d_t, st.s("bert_fc.weight"))
         d_r1000 = ops.linear_dgrad(d_r, st.s("resnet_fc.weight"))
         dh = ops.scatter_rows(d_pooled, B * S, S, off, p_drop=pd, seed=s_head)
-        self.text.backward(dh)
+        # data parallel: the towers announce each parameter group whose gradients are final (ddp.GradSync.ready), so
+        # its all-reduce runs on NCCL's stream under the rest of the backward
         sync = getattr(self, "grad_sync", None)
-        if sync is not None:
-            sync.ready("text")          # text-tower gradients are final: all-reduce them under the image backward
-        self.img.backward(d_r1000)
+        cb = sync.ready if sync is not None else None
+        self.text.backward(dh, on_grads_ready=cb)
+        self.img.backward(d_r1000, on_grads_ready=cb)
         if sync is not None:
             sync.ready("rest")
+            if not getattr(self, "_defer_grad_sync", False):
+                sync.finish_into_grad()      # an optimizer that reads param.grad (torch.optim.*) needs the mean NOW
         self._saved = None
         self._attach_grads()
 
@@ -258,10 +261,12 @@ class MultimodalClassifier(nn.Module):
                                             dbias=st.g("output_fc.bias"), dlogits=dlogits.float())
             self._backward_from_dfused(dfused)
 
-    def enable_data_parallel(self, group=None, bucket_elems: int = 64 * 1024 * 1024):
-        """One process per GPU: broadcast rank 0's parameters / BN buffers and all-reduce gradients every step."""
+    def enable_data_parallel(self, group=None, bucket_elems: int = 64 * 1024 * 1024, payload: str = "bf16"):
+        """One process per GPU: broadcast rank 0's parameters / BN buffers and all-reduce gradients every step, in
+        phases that follow the order in which the backward finishes them (ddp.py)."""
         from .ddp import GradSync
-        self.grad_sync = GradSync(self.store, group, bucket_elems)
+        phases = self.text.grad_phases() + self.img.grad_phases() + [("rest", lambda n: True)]
+        self.grad_sync = GradSync(self.store, group, bucket_elems, phases=phases, payload=payload)
         self.grad_sync.broadcast_parameters([self.img.buffers] if self.img.buffers is not None else [])
         self.store.refresh_shadow()
         return self.grad_sync

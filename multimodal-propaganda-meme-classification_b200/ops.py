@@ -433,19 +433,24 @@ def head_bn_focal(feat, W, bias, bn_g, bn_b, running_mean, running_var, labels, 
 
 
 def sumsq(g, out):
-    _lib.call("b200mm_sumsq_f32", _p(g), g.numel(), _p(out), _s())
+    """out[0] += sum(g^2); g fp32 or bf16 (the all-reduced data-parallel payload)."""
+    _lib.call("b200mm_sumsq_bf16" if g.dtype == bf16 else "b200mm_sumsq_f32", _p(g), g.numel(), _p(out), _s())
     return out
 
 
 def adam_step(p, g, m, v, shadow, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1, gradsq=None,
               max_norm=0.0, grad_scale=1.0):
-    _lib.call("b200mm_adam_step", _p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), float(lr), float(beta1),
+    _lib.call("b200mm_adam_step_g16" if g.dtype == bf16 else "b200mm_adam_step",
+              _p(p), _p(g), _p(m), _p(v), _p(shadow), p.numel(), float(lr), float(beta1),
               float(beta2), float(eps), float(weight_decay), int(step), _p(gradsq), float(max_norm),
               float(grad_scale), _s())
 
 
-def cast_to_bf16(x, y):
-    _lib.call("b200mm_cast_f32_to_bf16", _p(x), _p(y), x.numel(), _s())
+def cast_to_bf16(x, y, scale: float = 1.0):
+    if scale == 1.0:
+        _lib.call("b200mm_cast_f32_to_bf16", _p(x), _p(y), x.numel(), _s())
+    else:
+        _lib.call("b200mm_scale_cast_f32_to_bf16", _p(x), _p(y), x.numel(), float(scale), _s())
     return y
 
 

@@ -23,6 +23,10 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("FusedAdam drives the parameters of exactly one b200mm model")
         self.store = next(iter(stores.values()))
         self.model = self.store.owner
+        # data parallel: this optimizer finishes the gradient all-reduce itself (inside step(), so the exchange overlaps
+        # whatever the host does between backward and step); without this flag the model finishes it at the end of
+        # backward so that ANY optimizer reading param.grad sees averaged gradients (ddp.GradSync.finish_into_grad)
+        self.model._defer_grad_sync = True
         n = self.store.numel
         self.exp_avg = torch.zeros(n, device=self.store.device, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(n, device=self.store.device, dtype=torch.float32)
@@ -50,14 +54,17 @@ class FusedAdam(torch.optim.Optimizer):
         st = self.store
         self._step += 1
         sync = getattr(self.model, "grad_sync", None)
-        if sync is not None:
-            grad_scale = grad_scale * sync.finish()     # summed gradients -> mean, folded into the Adam kernel
+        grad = st.grad
+        if sync is not None and sync.world > 1:
+            grad_scale = grad_scale * sync.finish()     # fp32 payload: summed -> mean, folded into the Adam kernel
+            grad = sync.grad_buffer()                   # bf16 payload: the averaged gradients live in the comm buffer
         gradsq = None
         if self.max_grad_norm is not None:
             self._gradsq.zero_()
-            ops.sumsq(st.grad, self._gradsq)
+            ops.sumsq(grad, self._gradsq)
             gradsq = self._gradsq
-            self.last_grad_norm = self._gradsq   # device scalar (squared norm); .sqrt().item() when logging
+            # device scalar: SQUARED norm of the mean gradient (.sqrt().item() when logging)
+            self.last_grad_norm = self._gradsq if grad_scale == 1.0 else self._gradsq * (grad_scale * grad_scale)
         s0 = st.shadow_start
         for g, ranges in zip(self.param_groups, self._ranges):
             b1, b2 = g["betas"]
@@ -66,11 +73,27 @@ class FusedAdam(torch.optim.Optimizer):
                 for lo, hi, sh in ((a, min(b, s0), False), (max(a, s0), b, True)):
                     if hi <= lo:
                         continue
-                    ops.adam_step(st.master[lo:hi], st.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                    ops.adam_step(st.master[lo:hi], grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
                                   st.shadow[lo:hi] if sh else None, lr=g["lr"], beta1=b1, beta2=b2, eps=g["eps"],
                                   weight_decay=g["weight_decay"], step=self._step, gradsq=gradsq,
                                   max_norm=self.max_grad_norm or 0.0, grad_scale=grad_scale)
         self.model._shadow_fresh = True
+
+    # ---- checkpoint / resume: the moments and the step count live outside Optimizer.state (flat buffers)
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["b200mm"] = {"exp_avg": self.exp_avg.detach().cpu(), "exp_avg_sq": self.exp_avg_sq.detach().cpu(),
+                        "step": self._step, "max_grad_norm": self.max_grad_norm}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        extra = state_dict.get("b200mm")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "b200mm"})
+        if extra is not None:
+            self.exp_avg.copy_(extra["exp_avg"])
+            self.exp_avg_sq.copy_(extra["exp_avg_sq"])
+            self._step = int(extra["step"])
+            self.max_grad_norm = extra.get("max_grad_norm", self.max_grad_norm)
 
 
 def get_linear_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, last_epoch=-1):

@@ -223,9 +223,32 @@ class TextTower:
         self._saved = saved
         return x
 
+    # ------------------------------------------------------------------ data-parallel gradient phases
+    GRAD_GROUPS = 3
+
+    def _layer_stem(self, i: int) -> str:
+        mid = "transformer" if self.cfg.arch == "distilbert" else "encoder"
+        return f"{self.cfg.prefix}.{mid}.layer.{i}."
+
+    def _group_of(self, li: int) -> int:
+        per = -(-self.cfg.n_layers // self.GRAD_GROUPS)
+        return li // per
+
+    def grad_phases(self):
+        """Ordered (tag, predicate) list for ddp.GradSync: encoder layers in GRAD_GROUPS groups, top group first (the
+        order the backward finishes them), then everything else of this tower (embedding tables, embedding LN)."""
+        pre = self.cfg.prefix
+        out = []
+        for g in reversed(range(self._group_of(self.cfg.n_layers - 1) + 1)):
+            stems = tuple(self._layer_stem(i) for i in range(self.cfg.n_layers) if self._group_of(i) == g)
+            out.append((f"{pre}.g{g}", lambda n, stems=stems: n.startswith(stems)))
+        out.append((f"{pre}.tail", lambda n, pre=pre: n.startswith(pre + ".")))
+        return out
+
     # ------------------------------------------------------------------ backward
-    def backward(self, dh: torch.Tensor):
-        """dh: gradient w.r.t. the returned token matrix, bf16 [B*S, D]. Accumulates into the store's grad buffer."""
+    def backward(self, dh: torch.Tensor, on_grads_ready=None):
+        """dh: gradient w.r.t. the returned token matrix, bf16 [B*S, D]. Accumulates into the store's grad buffer.
+        on_grads_ready(tag): called as soon as every gradient of a ``grad_phases`` group is final."""
         sv = self._saved
         assert sv is not None, "backward() without a training-mode forward()"
         B, S, H = sv["B"], sv["S"], self.cfg.n_heads
@@ -256,6 +279,8 @@ class TextTower:
             ops.linear_wgrad(dqkv, x, L["dwqkv"])
             ops.colsum(dqkv, L["dbqkv"])
             d_out = ops.linear_dgrad(dqkv, L["wqkv"], residual=d_ypre)     # + residual path of LN1's input
+            if on_grads_ready is not None and (li == 0 or self._group_of(li - 1) != self._group_of(li)):
+                on_grads_ready(f"{self.cfg.prefix}.g{self._group_of(li)}")
         x_emb, e_mean, e_rstd, pd, s_emb = sv["emb"]
         d_emb, _ = ops.layernorm_bwd(d_out, x_emb, e_mean, e_rstd, self.eg, self.deg, self.deb, p_in=pd, seed_in=s_emb)
         roberta = self.cfg.arch == "roberta"
@@ -263,4 +288,6 @@ class TextTower:
                           pos_ids=sv["pos_ids"], pos_padding_idx=self.cfg.pad_token_id if roberta else -1)
         if self.dtype0 is not None:
             ops.colsum(d_emb, self.dtype0)      # every token has segment id 0
+        if on_grads_ready is not None:
+            on_grads_ready(f"{self.cfg.prefix}.tail")
         self._saved = None

@@ -217,9 +217,27 @@ class ViTTower:
         self._saved = sv
         return feat
 
+    # ------------------------------------------------------------------ data-parallel gradient phases
+    GRAD_GROUPS = 4
+
+    def _group_of(self, li: int) -> int:
+        per = -(-self.cfg.n_layers // self.GRAD_GROUPS)
+        return li // per
+
+    def grad_phases(self):
+        """Ordered (tag, predicate) list for ddp.GradSync: encoder layers in GRAD_GROUPS groups, top group first; the
+        patch embedding, cls / position tables and the final LayerNorm fall to the model's catch-all last phase."""
+        pre = self.cfg.prefix
+        out = []
+        for g in reversed(range(self._group_of(self.cfg.n_layers - 1) + 1)):
+            stems = tuple(f"{pre}.encoder.layer.{i}." for i in range(self.cfg.n_layers) if self._group_of(i) == g)
+            out.append((f"{pre}.g{g}", lambda n, stems=stems: n.startswith(stems)))
+        return out
+
     # ------------------------------------------------------------------ backward
-    def backward(self, dfeat: torch.Tensor):
-        """dfeat: bf16 [B, dim]. Accumulates parameter gradients (the image itself needs none)."""
+    def backward(self, dfeat: torch.Tensor, on_grads_ready=None):
+        """dfeat: bf16 [B, dim]. Accumulates parameter gradients (the image itself needs none).
+        on_grads_ready(tag): called as soon as every gradient of a ``grad_phases`` group is final."""
         sv = self._saved
         assert sv is not None, "backward() without a training-mode forward()"
         c = self.cfg
@@ -247,6 +265,8 @@ class ViTTower:
             ops.colsum(dqkv, L["dbqkv"])
             dh1 = ops.linear_dgrad(dqkv, L["wqkv"])
             dx, _ = ops.layernorm_bwd(dh1, x, m1, r1, L["g1"], L["dg1"], L["dbe1"], addend=dx2)
+            if on_grads_ready is not None and (li == 0 or self._group_of(li - 1) != self._group_of(li)):
+                on_grads_ready(f"{c.prefix}.g{self._group_of(li)}")
         dpatch = ops.vit_assemble_bwd(dx, self.dcls, self.dpos, B, P)
         ops.linear_wgrad(dpatch, sv["cols"], self.dwp)
         ops.colsum(dpatch, self.dbp)

@@ -227,29 +227,45 @@ def test_param_store_layout_and_bucket_plan():
     assert not any(a <= spec["resnet.conv1.weight"].offset < b for a, b in text)
 
 
+def _torch_pack(x, y, scale=1.0):
+    """CPU stand-in for ops.cast_to_bf16 (the CUDA packer) so the bucket / phase logic can run under gloo."""
+    y.copy_(x * scale)
+
+
 def _dp_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from b200mm.ddp import GradSync
-    st = _fake_store()
-    torch.manual_seed(100 + rank)
-    st.master.normal_()
-    gs = GradSync(st, bucket_elems=10000)
-    gs.broadcast_parameters()
-    torch.manual_seed(7 + rank)
-    st.grad.normal_()
-    local = st.grad.clone()
-    gs.ready("text")
-    gs.ready("rest")
-    scale = gs.finish()
-    gathered = [torch.zeros_like(local) for _ in range(world)]
-    dist.all_gather(gathered, local)
-    ok = torch.allclose(st.grad * scale, sum(gathered) / world, atol=1e-6)
-    ref = st.master.clone()
-    dist.broadcast(ref, src=0)
-    ok = ok and torch.equal(ref, st.master)
+    ok = True
+    for payload in ("fp32", "bf16"):
+        st = _fake_store()
+        torch.manual_seed(100 + rank)
+        st.master.normal_()
+        gs = GradSync(st, bucket_elems=10000, payload=payload, pack=_torch_pack)
+        gs.broadcast_parameters()
+        torch.manual_seed(7 + rank)
+        st.grad.normal_()
+        local = st.grad.clone()
+        gs.ready("text")
+        gs.ready("text")          # announcing a phase twice must not launch it twice
+        scale = gs.finish()       # launches the un-announced "rest" phase itself
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        mean = sum(gathered) / world
+        got = gs.grad_buffer().float() * scale
+        ok = ok and torch.allclose(got, mean, atol=1e-6 if payload == "fp32" else 3e-2, rtol=0 if payload == "fp32" else 2e-2)
+        ok = ok and (gs.grad_buffer().dtype == (torch.float32 if payload == "fp32" else torch.bfloat16))
+        # second step through the param.grad route (torch.optim.* optimizers): the MEAN ends up in store.grad
+        st.grad.copy_(local)
+        gs.ready("text")
+        gs.finish_into_grad()
+        ok = ok and torch.allclose(st.grad, mean, atol=1e-6 if payload == "fp32" else 3e-2, rtol=0 if payload == "fp32" else 2e-2)
+        ok = ok and not gs._pending and not gs._launched
+        ref = st.master.clone()
+        dist.broadcast(ref, src=0)
+        ok = ok and torch.equal(ref, st.master)
     if rank == 0:
         out.put(bool(ok))
     dist.destroy_process_group()
@@ -269,6 +285,51 @@ def test_gradient_allreduce_two_ranks_gloo():
     assert q.get(timeout=5) is True
 
 
+def test_tower_gradient_phases_cover_store_in_backward_order():
+    """The per-stage / per-layer-group phases the towers announce (ddp.py) partition the whole flat gradient buffer,
+    for every tower combination of BASELINE.json, and list the image stages in backward order."""
+    from b200mm.ddp import GradSync
+    from b200mm.image_tower import ImageConfig, ImageTower
+    from b200mm.params import ParamStore
+    from b200mm.text_tower import TextConfig, TextTower
+    from b200mm.vit_tower import ViTConfig, ViTTower
+    small = dict(vocab_size=64, max_position_embeddings=32, dim=64, n_heads=1, hidden_dim=128)
+    for tcfg, icfg in ((TextConfig(n_layers=6, **small), ImageConfig(layers=(1, 2, 1, 1))),
+                       (TextConfig(n_layers=4, arch="bert", **small), ViTConfig(image_size=32, dim=64, n_layers=5, n_heads=1, hidden_dim=128))):
+        st = ParamStore("cpu")
+        text = TextTower(tcfg, st)
+        img = ViTTower(icfg, st) if icfg.arch == "vit" else ImageTower(icfg, st)
+        text.register_noshadow(); img.register_noshadow()
+        st.add("output_fc.bias", (2,), shadow=False)
+        text.register_shadowed(); img.register_shadowed()
+        st.add("fusion_fc.weight", (512, 1024))
+        st.finalize()
+        phases = text.grad_phases() + img.grad_phases() + [("rest", lambda n: True)]
+        gs = GradSync(st, bucket_elems=1 << 20, phases=phases, payload="fp32")
+        cov = gs.covered()
+        assert cov[0][0] == 0 and cov[-1][1] == st.numel
+        assert all(a[1] == b[0] for a, b in zip(cov, cov[1:]))
+        tags = list(gs.phases)
+        assert tags[0] == "bert.g2" or tags[0] == "bert.g1"       # top layer group first
+        assert tags.index("bert.tail") < tags.index("rest")
+        q_top = st.specs[[n for n in st.names() if n.endswith(f"layer.{tcfg.n_layers - 1}.attention.q_lin.weight")
+                          or n.endswith(f"layer.{tcfg.n_layers - 1}.attention.self.query.weight")][0]].offset
+        assert any(a <= q_top < b for a, b in gs.phases[tags[0]])
+        emb = st.specs["bert.embeddings.word_embeddings.weight"].offset
+        assert any(a <= emb < b for a, b in gs.phases["bert.tail"])
+        if icfg.arch != "vit":
+            assert tags.index("resnet.layer4") < tags.index("resnet.layer3") < tags.index("resnet.layer1")
+            w = st.specs["resnet.layer3.0.conv2.weight"].offset
+            assert any(a <= w < b for a, b in gs.phases["resnet.layer3"])
+            fc = st.specs["resnet.fc.weight"].offset
+            assert any(a <= fc < b for a, b in gs.phases["resnet.layer4"])
+            stem = st.specs["resnet.conv1.weight"].offset
+            assert any(a <= stem < b for a, b in gs.phases["rest"])
+        else:
+            top = img._group_of(icfg.n_layers - 1)
+            assert top >= 1 and tags.index(f"resnet.g{top}") < tags.index("resnet.g0")
+
+
 def test_bench_reference_arm_contract():
     """bench.py --impl reference prints one JSON line with the keys the driver reads (tiny run)."""
     import subprocess
@@ -278,7 +339,7 @@ def test_bench_reference_arm_contract():
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
 
 
 # ------------------------------------------------------------------------------------------------- bf16 emulation oracle
