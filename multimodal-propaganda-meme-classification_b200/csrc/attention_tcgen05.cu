@@ -14,60 +14,9 @@
 //
 // Replaces: transformers/models/distilbert/modeling_distilbert.py:126-151
 // (eager_attention_forward: softmax(QK^T * d^-1/2 + mask) -> dropout -> @V) and its autograd backward.
-#include <cstdlib>
-#include "common.cuh"
-#include "device_utils.cuh"
-#include "ptx.cuh"
+#include "attention_common.cuh"
 
 namespace b200 {
-
-constexpr int ATT_T = 128;   // query / key tile (== max sequence length of this kernel)
-constexpr int ATT_D = 64;    // head dim
-constexpr int ATT_TILE_BYTES = ATT_T * ATT_D * 2;  // 16 KB: one [128 x 64] bf16 tile, 128B rows
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-
-struct AttnParams {
-  int B, H, S, D;  // D = H * 64
-  float scale_log2;      // head_dim^-1/2 * log2(e)
-  float scale;           // head_dim^-1/2
-  float p_drop;
-  uint32_t drop_threshold;
-  float inv_keep;
-  unsigned long long seed;
-  const float* key_bias;  // [B, S] additive bias (0 / -inf for padded keys) or nullptr
-  __nv_bfloat16* out;     // fwd: O [B*S, D]
-  float* lse;             // [B, H, S] natural-log LSE of the scaled+biased scores
-  const __nv_bfloat16* o_in;   // bwd: O
-  const __nv_bfloat16* do_in;  // bwd: dO [B*S, D]
-  __nv_bfloat16* dqkv;         // bwd: [B*S, 3D]
-};
-
-// exp2 on the special-function unit (inputs are <= 0 here; ex2.approx maps -inf to +0)
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// byte offset of 16-byte chunk `chunk` (0..7) of row `r` inside a [rows x 64] bf16 SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128_off(int r, int chunk) { return r * 128 + ((chunk ^ (r & 7)) << 4); }
-
-// write 32 consecutive bf16 of row r (columns c0..c0+31, c0 % 32 == 0) into a [128 x 128] tile stored as two
-// [128 x 64] swizzled blocks
-__device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c0, const float (&x)[32]) {
-  uint8_t* blk = tile + (c0 >> 6) * ATT_TILE_BYTES;
-  const int chunk0 = (c0 & 63) >> 3;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 o;
-    o.x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
-    o.y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
-    o.z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
-    o.w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
-    *reinterpret_cast<uint4*>(blk + sw128_off(r, chunk0 + q)) = o;
-  }
-}
 
 // ------------------------------------------------------------------------------------------ S > 128
 // Longer sequences (the reference pads to 512 tokens, example_scripts/Multimodal_example_task2C.txt:14) run the same
@@ -76,11 +25,6 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t* tile, int r, int c0, 
 // saved LSE makes every (query tile, key tile) pair independent, so one CTA owns a key tile and accumulates dK / dV
 // over the query tiles in TMEM, another owns a query tile and accumulates dQ over the key tiles: no atomics.
 constexpr int ATT_MAX_S = 512;
-
-// index of the 32-key chunk starting at `key` (multiple of 32) of query row `qrow`, for dropout_keep32
-__device__ __forceinline__ uint64_t drop_chunk(int bh, int s_pad, int qrow, int key) {
-  return ((static_cast<uint64_t>(bh) * s_pad + qrow) * s_pad + key) >> 5;
-}
 
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
@@ -1420,6 +1364,8 @@ B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void
     const uint64_t orow = static_cast<uint64_t>(p.D) * 2;
     rc = make_tmap_3d_bf16(&to, out, p.D, S, B, orow, orow * S, ATT_D, ATT_T);
     if (rc) return rc;
+    if (nt == 1 && attn_ws_enabled())      // warp-specialised pipeline, four heads in flight per SM (attention_ws.cu)
+      return launch_attn_fwd_ws(tq, to, p, dev.num_sms, static_cast<cudaStream_t>(stream));
     if (nt == 1) {
       const int grid = items < 2 * dev.num_sms ? items : 2 * dev.num_sms;
       attn_fwd_tmem_kernel<1><<<grid, 256, att_fwd_tmem_smem<1>(), static_cast<cudaStream_t>(stream)>>>(tq, to, p);
@@ -1522,6 +1468,8 @@ B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, cons
   CUtensorMap tdq;
   rc = make_tmap_3d_bf16(&tdq, dqkv, 3 * p.D, S, B, row, row * S, ATT_D, ATT_T);
   if (rc) return rc;
+  if (attn_ws_enabled())                   // warp-specialised pipeline, two heads in flight per SM (attention_ws.cu)
+    return launch_attn_bwd_ws(tq, td, tdq, p, dev.num_sms, static_cast<cudaStream_t>(stream));
   attn_bwd1_kernel<<<grid, 256, ATT_BWD1_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, tdq, p);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;

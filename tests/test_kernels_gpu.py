@@ -159,6 +159,52 @@ def test_attention_dropout_is_consistent(ops, cuda_device):
     assert abs(fd - an) / (abs(an) + 1e-6) < 0.1
 
 
+@pytest.mark.parametrize("B,H,S,p", [(3, 4, 128, 0.0), (40, 12, 128, 0.1), (5, 2, 77, 0.1), (700, 2, 128, 0.1)])
+def test_attention_warp_specialised_matches_single_role(ops, cuda_device, B, H, S, p):
+    """attention_ws.cu (TMA warp / MMA warp / softmax warpgroups, several heads in flight) against the single-role
+    kernels it replaces for one-tile sequences: same Philox stream and element indexing, so with the SAME seed the two
+    families produce the same dropout mask -- outputs, LSE and all three gradients agree to bf16 rounding, element by
+    element (max-abs, not only the L2 ratio: a wrong edge row or a bad last head would hide in a norm).  The last
+    shape gives every CTA 9-10 heads, i.e. several trips around the 4-slot / 2-slot rings."""
+    import os
+    torch.manual_seed(11)
+    D = H * 64
+    qkv = (torch.randn(B * S, 3 * D, device=cuda_device) * 0.7).to(bf16)
+    lengths = torch.randint(3, S + 1, (B,), device=cuda_device)
+    lengths[0] = S
+    bias = ops.mask_to_bias((torch.arange(S, device=cuda_device)[None] < lengths[:, None]).long())
+    dout = torch.randn(B * S, D, device=cuda_device).to(bf16)
+    res = {}
+    try:
+        for ws in ("0", "1"):
+            os.environ["B200MM_ATTN_WS"] = ws
+            out, lse = ops.attention_fwd(qkv, bias, B, H, S, p_drop=p, seed=99)
+            dqkv = ops.attention_bwd(qkv, bias, out, dout, lse, B, H, S, p_drop=p, seed=99)
+            res[ws] = (out.float(), lse.clone(), dqkv.float())
+        # mixed: warp-specialised backward on the single-role forward's output / LSE
+        os.environ["B200MM_ATTN_WS"] = "1"
+        dq_mixed = ops.attention_bwd(qkv, bias, res["0"][0].to(bf16), dout, res["0"][1], B, H, S, p_drop=p, seed=99).float()
+    finally:
+        os.environ["B200MM_ATTN_WS"] = "1"
+    o0, l0, g0 = res["0"]
+    o1, l1, g1 = res["1"]
+    assert torch.isfinite(o1).all() and torch.isfinite(g1).all()
+    assert rel(o1, o0) < 4e-3 and (o1 - o0).abs().max().item() < 2e-2 * o0.abs().max().item() + 1e-3
+    assert (l1 - l0).abs().max().item() < 1e-4
+    for name, a, b in (("ws", g1, g0), ("mixed", dq_mixed, g0)):
+        assert rel(a, b) < 1e-2, name
+        assert (a - b).abs().max().item() < 3e-2 * b.abs().max().item() + 1e-3, name
+        # per-row check of the last query row of the last head and of the rows past a short sequence's end
+        last = slice((B - 1) * S, B * S)
+        assert rel(a[last, -64:], b[last, -64:]) < 2e-2, name
+    if p == 0.0:
+        qf = qkv.float().requires_grad_(True)
+        ref = _attn_ref(qf, bias, B, H, S)
+        assert rel(o1, ref) < 1e-2
+        ref.backward(dout.float())
+        assert rel(g1, qf.grad) < 2e-2
+
+
 # ------------------------------------------------------------------------------------------------- LayerNorm / embeddings
 @pytest.mark.parametrize("M,D", [(64, 128), (1000, 768), (300, 1024), (96, 2048)])
 def test_layernorm_fwd_bwd(ops, cuda_device, M, D):
