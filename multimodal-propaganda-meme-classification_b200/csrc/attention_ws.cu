@@ -37,15 +37,14 @@ namespace b200 {
 // like ptx.cuh's bounded mbar_wait.
 struct PollWatchdog {
   long long t0;
-  __device__ __forceinline__ PollWatchdog() : t0(clock64()) {}
-  __device__ __forceinline__ void progress() { t0 = clock64(); }
-  __device__ __forceinline__ void check(const char* role) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("b200mm: attention %s stalled, block %d\n", role, blockIdx.x);
-      __trap();
-    }
-  }
 };
+__device__ __forceinline__ void dog_progress(PollWatchdog& d) { d.t0 = clock64(); }
+__device__ __forceinline__ void dog_check(const PollWatchdog& d, const char* role) {
+  if (clock64() - d.t0 > 4000000000LL) {
+    printf("b200mm: attention %s stalled, block %d\n", role, blockIdx.x);
+    __trap();
+  }
+}
 
 bool attn_ws_enabled() {
   const char* e = std::getenv("B200MM_ATTN_WS");
@@ -99,8 +98,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     if (elect_one()) {
       int nl = 0, nst = 0;
       PollWatchdog dog;
+      dog_progress(dog);
       while (nst < n_local) {
-        dog.check("fwd TMA warp");
+        dog_check(dog, "fwd TMA warp");
         if (nl < n_local && nl - WSF_SLOTS < nst) {       // the slot's previous tile has left shared memory
           const int s = nl & (WSF_SLOTS - 1);
           const int item = blockIdx.x + nl * gridDim.x;
@@ -111,7 +111,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
           tma_load_3d(base + ATT_TILE_BYTES, &tma_qkv, &bar_full[s], p.D + h * ATT_D, 0, b);
           tma_load_3d(base + 2 * ATT_TILE_BYTES, &tma_qkv, &bar_full[s], 2 * p.D + h * ATT_D, 0, b);
           ++nl;
-          dog.progress();
+          dog_progress(dog);
         }
         if (nst < nl) {
           const int s = nst & (WSF_SLOTS - 1);
@@ -122,7 +122,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             tma_store_commit();
             tma_store_wait_read<0>();
             ++nst;
-            dog.progress();
+            dog_progress(dog);
           }
         }
       }
@@ -135,8 +135,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
       const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       int nq = 0, np = 0;
       PollWatchdog dog;
+      dog_progress(dog);
       while (np < n_local) {
-        dog.check("fwd MMA warp");
+        dog_check(dog, "fwd MMA warp");
         if (nq < n_local) {
           const int s = nq & (WSF_SLOTS - 1);
           if (mbar_try_wait(&bar_full[s], (nq >> 2) & 1)) {
@@ -148,7 +149,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                         idesc_s, kk > 0);
             umma_commit(&bar_s[s]);
             ++nq;
-            dog.progress();
+            dog_progress(dog);
           }
         }
         if (np < nq) {
@@ -162,7 +163,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                         umma_desc_sw128(v + kk * 2048, 8192, 1024), idesc_o, kk > 0);
             umma_commit(&bar_o[s]);
             ++np;
-            dog.progress();
+            dog_progress(dog);
           }
         }
       }
@@ -309,8 +310,9 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
     if (elect_one()) {
       int nl = 0, nst = 0;
       PollWatchdog dog;
+      dog_progress(dog);
       while (nst < n_local) {
-        dog.check("bwd TMA warp");
+        dog_check(dog, "bwd TMA warp");
         if (nl < n_local) {
           const int s = nl & 1, k = nl >> 1;
           // operand tiles (and P, which overlays V) of the slot's previous head are free once its gradient MMAs retired
@@ -324,7 +326,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             tma_load_3d(base + 2 * ATT_TILE_BYTES, &tma_do, &bar_full[s], h * ATT_D, 0, b);
             tma_load_3d(base + 3 * ATT_TILE_BYTES, &tma_qkv, &bar_full[s], 2 * p.D + h * ATT_D, 0, b);
             ++nl;
-            dog.progress();
+            dog_progress(dog);
           }
         }
         if (nst < nl) {
@@ -339,7 +341,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
             tma_store_wait_read<0>();
             mbar_arrive(&bar_xfree[s]);
             ++nst;
-            dog.progress();
+            dog_progress(dog);
           }
         }
       }
@@ -353,8 +355,9 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
       const uint32_t idesc_nt = umma_idesc_bf16(128, 64, 0, 1);
       int nq = 0, ng = 0;
       PollWatchdog dog;
+      dog_progress(dog);
       while (ng < n_local) {
-        dog.check("bwd MMA warp");
+        dog_check(dog, "bwd MMA warp");
         if (nq < n_local) {
           const int s = nq & 1, k = nq >> 1;
           // operands landed AND the slot's TMEM (dV / dK / dQ of its previous head) has been drained
@@ -373,7 +376,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                         kk > 0);
             umma_commit(&bar_sc[s]);
             ++nq;
-            dog.progress();
+            dog_progress(dog);
           }
         }
         if (ng < nq) {
@@ -397,7 +400,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
                         umma_desc_sw128(kk_ + kk * 2048, 8192, 1024), idesc_nt, kk > 0);
             umma_commit(&bar_gd[s]);
             ++ng;
-            dog.progress();
+            dog_progress(dog);
           }
         }
       }
