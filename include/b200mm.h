@@ -146,6 +146,15 @@ int b200mm_upsample_add_nhwc(const void* dsub, const void* addend, int N, int H,
  * pointers; mean3/std3: HOST arrays of 3 floats. */
 int b200mm_preprocess_u8(const void* images, const int* heights, const int* widths, int n, int resize, int crop,
                          const float* mean3, const float* std3, float* out, void* stream);
+/* Same transform over a PACKED batch (one byte buffer + device tables of offsets / heights / widths: two H2D copies per
+ * batch whatever its size); square = 1 selects Resize((crop, crop)) of the HEAD script
+ * (example_scripts/Multimodal_example_task2C.py:222-235), flip = per-image RandomHorizontalFlip flags or NULL. */
+int b200mm_preprocess_u8_packed(const void* packed, const long long* offsets, const int* heights, const int* widths,
+                                const void* flip, int n, int resize, int crop, int square, const float* mean3,
+                                const float* std3, float* out, void* stream);
+/* Batch already at network resolution: [n, H, W, 3] uint8 -> ToTensor -> Normalize -> fp32 NCHW (W % 4 == 0). */
+int b200mm_u8_normalize_nchw(const void* src, const void* flip, int n, int H, int W, const float* mean3,
+                             const float* std3, float* out, void* stream);
 
 /* ---- head + loss, optimizer --------------------------------------------------------------------------------------
  * output layer fused with the loss: example_scripts/Multimodal_example_task2C.txt:195 (output_fc) + :214, :248

@@ -105,6 +105,9 @@ declare("b200mm_conv_wgrad", [c_ptr, c_longlong, c_ptr, c_int, c_int, c_int, c_i
                               c_int, c_ptr])
 declare("b200mm_conv_weight_rotate", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr])
 declare("b200mm_preprocess_u8", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr])
+declare("b200mm_preprocess_u8_packed", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                        c_ptr])
+declare("b200mm_u8_normalize_nchw", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_attention_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float, c_ulonglong, c_ptr])
 declare("b200mm_attention_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float,
                                  c_ulonglong, c_ptr])
