@@ -46,9 +46,27 @@ class SigmoidFocalLoss:
                                   reduction="mean")
 
 
+_EVAL_TRANSFORM = None
+
+
+def _image_to_device(data, device):
+    """fp32 pixels are copied as they are; uint8 pixels (fixed-size or packed, data.collate_packed) take the GPU
+    transform in its deterministic evaluation form."""
+    global _EVAL_TRANSFORM
+    if "image_packed" in data or data["image"].dtype == torch.uint8:
+        if _EVAL_TRANSFORM is None:
+            from .data import GpuImageTransform
+            _EVAL_TRANSFORM = GpuImageTransform("center_crop")
+        if "image_packed" in data:
+            return _EVAL_TRANSFORM.packed(data["image_packed"].to(device, non_blocking=True),
+                                          data["image_table"].to(device, non_blocking=True))
+        return _EVAL_TRANSFORM.fixed(data["image"].to(device, non_blocking=True))
+    return data["image"].to(device, non_blocking=True)
+
+
 def _to_device(data, device):
     text = data["text"].to(device, non_blocking=True)
-    image = data["image"].to(device, non_blocking=True)
+    image = _image_to_device(data, device)
     mask = data["text_mask"].to(device, non_blocking=True)
     labels = data["label"].to(device, non_blocking=True) if "label" in data else None
     return text, image, mask, labels
@@ -66,21 +84,41 @@ class DevicePrefetcher:
     """Iterates a loader of the reference's batch dicts and yields (text, image, mask, labels, batch) already on the
     device, copying batch i+1 on a side stream while step i computes (the reference does the copy synchronously at
     the top of every step, .txt:206-211; its loop is input-bound).  The overlap needs pinned host
-    tensors (``DataLoader(pin_memory=True)``); pageable ones are copied the way the reference copies them."""
+    tensors (``DataLoader(pin_memory=True)`` / ``data.collate_packed``); pageable ones are copied the way the
+    reference copies them.
 
-    def __init__(self, loader, device, pin: bool = False):
+    ``image`` may arrive in three forms: fp32 [B, 3, H, W] (what the reference's CPU transform produces -- copied as
+    is), uint8 [B, H, W, 3] at network resolution, or a packed variable-size batch (``image_packed`` +
+    ``image_table``, data.collate_packed).  The uint8 forms cross PCIe at a quarter of the bytes and are turned into
+    the normalised fp32 tensor by ONE kernel on the copy stream (``image_transform``, a data.GpuImageTransform;
+    default: the organiser script's Resize(256) / CenterCrop(224) / Normalize)."""
+
+    KEYS = ("text", "image", "text_mask", "label", "caption_text", "caption_text_mask", "image_packed", "image_table")
+
+    def __init__(self, loader, device, pin: bool = False, image_transform=None):
         self.loader, self.device, self.pin = loader, torch.device(device), pin
         self.stream = torch.cuda.Stream(device=self.device)
+        self.image_transform = image_transform
+
+    def _transform(self):
+        if self.image_transform is None:
+            from .data import GpuImageTransform
+            self.image_transform = GpuImageTransform("center_crop")
+        return self.image_transform
 
     def _stage(self, data):
         out = {}
         with torch.cuda.stream(self.stream):
-            for k in ("text", "image", "text_mask", "label"):
+            for k in self.KEYS:
                 if k in data:
                     t = data[k]
                     if self.pin and not t.is_cuda and not t.is_pinned():
                         t = t.pin_memory()
                     out[k] = t.to(self.device, non_blocking=True)
+            if "image_packed" in out:
+                out["image"] = self._transform().packed(out.pop("image_packed"), out.pop("image_table"))
+            elif "image" in out and out["image"].dtype == torch.uint8:
+                out["image"] = self._transform().fixed(out["image"])
         ev = torch.cuda.Event()
         ev.record(self.stream)
         return out, ev, data
@@ -100,6 +138,8 @@ class DevicePrefetcher:
             torch.cuda.current_stream(self.device).wait_event(ev)
             for t in cur.values():
                 t.record_stream(torch.cuda.current_stream(self.device))
+            if "caption_text" in cur:            # HEAD-script batches: hand the device copies to _extra_inputs
+                raw = dict(raw, caption_text=cur["caption_text"], caption_text_mask=cur["caption_text_mask"])
             yield cur["text"], cur["image"], cur["text_mask"], cur.get("label"), raw
 
     def __len__(self):
@@ -150,7 +190,7 @@ def _fused(criterion):
     return isinstance(criterion, (CrossEntropyLoss, SigmoidFocalLoss))
 
 
-def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_step=None):
+def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_step=None, image_transform=None):
     model.train()
     train_loss = 0.0
     correct = 0
@@ -166,7 +206,7 @@ def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_
         if on_step is not None:
             on_step(done[0], bs)
 
-    for text, image, mask, labels, data in DevicePrefetcher(train_loader, device):
+    for text, image, mask, labels, data in DevicePrefetcher(train_loader, device, image_transform=image_transform):
         optimizer.zero_grad()
         if fused:
             _, loss, ok = model.train_step_fused(text, image, mask, labels, loss_kind=criterion.loss_kind,

@@ -612,10 +612,62 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
+def _c3(v):
+    import ctypes
+    return ctypes.cast((ctypes.c_float * 3)(*v), ctypes.c_void_p)
+
+
+def pack_images(images, pin: bool = True):
+    """Host side of the packed image batch: a list of uint8 CPU tensors [H, W, 3] (decoded, any size) -> ONE uint8
+    buffer (pinned) + an int64 table [3, n] = (byte offset | height | width), so a batch crosses PCIe in two copies."""
+    n = len(images)
+    table = torch.empty(3, n, dtype=torch.int64)
+    off = 0
+    for i, im in enumerate(images):
+        if im.dtype != torch.uint8 or im.dim() != 3 or im.shape[2] != 3:
+            raise ValueError("images must be [H, W, 3] uint8")
+        table[0, i], table[1, i], table[2, i] = off, im.shape[0], im.shape[1]
+        off += (im.numel() + 15) // 16 * 16
+    buf = torch.empty(off, dtype=torch.uint8, pin_memory=pin)
+    for i, im in enumerate(images):
+        o = int(table[0, i])
+        buf[o:o + im.numel()].copy_(im.reshape(-1))
+    if pin:
+        table = table.pin_memory()
+    return buf, table
+
+
+def preprocess_u8_packed(packed, table, *, resize=256, crop=224, square=False, flip=None, mean=IMAGENET_MEAN,
+                         std=IMAGENET_STD):
+    """packed: uint8 CUDA buffer, table: int64 CUDA [3, n] (offset | height | width) from ``pack_images``.
+    Returns fp32 [n, 3, crop, crop]: Resize(resize) -> CenterCrop(crop) (square=False, .txt:37-41) or
+    Resize((crop, crop)) (square=True, HEAD script :224), optional per-image horizontal flip (uint8 flags [n]),
+    then ToTensor -> Normalize -- antialiased bilinear like torchvision's tensor path."""
+    _chk(packed, torch.uint8, "packed images")
+    n = table.shape[1]
+    hw = table[1:3].to(torch.int32).contiguous()            # [2, n] int32 heights | widths (tiny device op)
+    out = torch.empty(n, 3, crop, crop, device=packed.device, dtype=f32)
+    _lib.call("b200mm_preprocess_u8_packed", _p(packed), _p(table[0]), _p(hw[0]), _p(hw[1]), _p(flip), n, int(resize),
+              int(crop), int(square), _c3(mean), _c3(std), _p(out), _s())
+    return out
+
+
+def u8_normalize(images, *, flip=None, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """images: uint8 CUDA [n, H, W, 3] already at network resolution -> fp32 [n, 3, H, W] = Normalize(ToTensor(img)),
+    optional per-image horizontal flip (uint8 flags [n])."""
+    _chk(images, torch.uint8, "images")
+    if images.dim() != 4 or images.shape[3] != 3 or not images.is_contiguous():
+        raise ValueError("images must be a contiguous [n, H, W, 3] uint8 tensor")
+    n, H, W, _ = images.shape
+    out = torch.empty(n, 3, H, W, device=images.device, dtype=f32)
+    _lib.call("b200mm_u8_normalize_nchw", _p(images), _p(flip), n, H, W, _c3(mean), _c3(std), _p(out), _s())
+    return out
+
+
 def preprocess_u8(images, *, resize=256, crop=224, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     """images: list of uint8 CUDA tensors [H, W, 3] (decoded, any size).  Returns fp32 [n, 3, crop, crop] exactly as
-    Resize(resize) -> CenterCrop(crop) -> ToTensor -> Normalize(mean, std) would (antialiased bilinear)."""
-    import ctypes
+    Resize(resize) -> CenterCrop(crop) -> ToTensor -> Normalize(mean, std) would (antialiased bilinear).
+    (Device-resident inputs; a loader that starts from host images uses pack_images + preprocess_u8_packed.)"""
     n = len(images)
     dev = images[0].device
     imgs = [im.contiguous() for im in images]
@@ -623,13 +675,12 @@ def preprocess_u8(images, *, resize=256, crop=224, mean=IMAGENET_MEAN, std=IMAGE
         _chk(im, torch.uint8, "image")
         if im.dim() != 3 or im.shape[2] != 3:
             raise ValueError("images must be [H, W, 3] uint8")
-    ptrs = torch.tensor([im.data_ptr() for im in imgs], dtype=torch.int64).to(dev)
-    hs = torch.tensor([im.shape[0] for im in imgs], dtype=torch.int32).to(dev)
-    ws = torch.tensor([im.shape[1] for im in imgs], dtype=torch.int32).to(dev)
+    # one pinned table [3, n] (pointer | height | width) and one asynchronous copy instead of three pageable ones
+    table = torch.tensor([[im.data_ptr() for im in imgs], [im.shape[0] for im in imgs], [im.shape[1] for im in imgs]],
+                         dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+    hw = table[1:3].to(torch.int32).contiguous()
     out = torch.empty(n, 3, crop, crop, device=dev, dtype=f32)
-    m = (ctypes.c_float * 3)(*mean)
-    s = (ctypes.c_float * 3)(*std)
-    _lib.call("b200mm_preprocess_u8", _p(ptrs), _p(hs), _p(ws), n, resize, crop, ctypes.cast(m, ctypes.c_void_p),
-              ctypes.cast(s, ctypes.c_void_p), _p(out), _s())
-    out._keepalive = imgs
+    _lib.call("b200mm_preprocess_u8", _p(table[0]), _p(hw[0]), _p(hw[1]), n, resize, crop, _c3(mean), _c3(std),
+              _p(out), _s())
+    out._keepalive = (imgs, table)
     return out

@@ -405,3 +405,45 @@ def test_warmup_schedule_matches_transformers():
             cur.append(sch.get_last_lr()[0])
         lrs.append(cur)
     assert np.allclose(lrs[0], lrs[1], rtol=0, atol=1e-15)
+
+
+def test_host_input_pipeline_token_cache_and_packing(tmp_path):
+    """data.py host side (no CUDA): the JSON reader, one-time tokenisation, the reference's batch-dict keys
+    (Multimodal_example_task2C.txt:46-71; .py:262-304) and the packed uint8 image batch."""
+    import json
+    from b200mm import data as D, ops
+    rows = [{"id": f"i{k}", "img_path": f"p{k}.jpg", "text": "w " * (k + 1), "class_label": ["propaganda", "not_propaganda"][k & 1]}
+            for k in range(5)]
+    f = tmp_path / "train.json"
+    f.write_text(json.dumps(rows))
+    d = D.read_data(str(f))
+    assert d["id"] == [r["id"] for r in rows] and d["label"][0] == "propaganda"
+    assert "label" not in D.read_data(str(f), is_test=True)
+    calls = []
+
+    def tok(t):
+        calls.append(t)
+        n = len(t.split())
+        return list(range(5, 5 + n)), [1] * n
+
+    sizes = [(30, 40), (64, 48), (17, 90), (33, 33), (50, 20)]
+    imgs = {f"p{k}.jpg": torch.randint(0, 256, (h, w, 3), dtype=torch.uint8) for k, (h, w) in enumerate(sizes)}
+    ds = D.MemeDataset(d["id"], d["text"], d["image"], d["label"], tokenizer=tok, max_len=4, pad_id=9,
+                       image_loader=lambda p: imgs[p])
+    assert len(calls) == 5                                    # tokenised once, not per __getitem__
+    s = ds[2]
+    assert len(calls) == 5 and set(s) == {"id", "text", "text_mask", "image", "label"}
+    assert s["text"].tolist() == [5, 6, 7, 9] and s["text_mask"].tolist() == [1, 1, 1, 0] and int(s["label"]) == 1
+    assert ds[4]["text"].tolist() == [5, 6, 7, 8]             # truncated to max_len
+    batch = D.collate_packed([ds[i] for i in range(5)], pin=False)
+    assert batch["text"].shape == (5, 4) and batch["label"].tolist() == [1, 0, 1, 0, 1]
+    buf, table = batch["image_packed"], batch["image_table"]
+    assert table.shape == (3, 5) and table.dtype == torch.int64
+    for k, (h, w) in enumerate(sizes):
+        off = int(table[0, k])
+        assert off % 16 == 0 and (int(table[1, k]), int(table[2, k])) == (h, w)
+        assert torch.equal(buf[off:off + h * w * 3].view(h, w, 3), imgs[f"p{k}.jpg"])
+    same = [dict(ds[0], image=torch.zeros(8, 12, 3, dtype=torch.uint8)) for _ in range(3)]
+    assert D.collate_packed(same, pin=False)["image"].shape == (3, 8, 12, 3)   # equal sizes: stacked fast path
+    with pytest.raises(ValueError):
+        ops.pack_images([torch.zeros(3, 8, 8, dtype=torch.uint8)], pin=False)

@@ -623,6 +623,89 @@ def test_preprocess_u8_matches_torch_transforms(ops, cuda_device):
         assert (out[k] - ref).abs().max().item() < 2e-4, (k, (out[k] - ref).abs().max().item())
 
 
+def _torch_transform(im, *, resize=256, crop=224, square=False, flip=False):
+    """fp32 torch restatement of the reference's tensor transform for one uint8 [H, W, 3] image (on its device)."""
+    from b200mm import ops as O
+    h, w = im.shape[:2]
+    mean = torch.tensor(O.IMAGENET_MEAN, device=im.device).view(3, 1, 1)
+    std = torch.tensor(O.IMAGENET_STD, device=im.device).view(3, 1, 1)
+    x = im.permute(2, 0, 1).float().unsqueeze(0)
+    if square:
+        r = F.interpolate(x, size=(crop, crop), mode="bilinear", antialias=True, align_corners=False)[0]
+    else:
+        nh, nw = (resize, int(resize * w / h)) if h <= w else (int(resize * h / w), resize)
+        r = F.interpolate(x, size=(nh, nw), mode="bilinear", antialias=True, align_corners=False)[0]
+        top, left = int(round((nh - crop) / 2.0)), int(round((nw - crop) / 2.0))
+        r = r[:, top:top + crop, left:left + crop]
+    if flip:
+        r = r.flip(-1)
+    return (r / 255.0 - mean) / std
+
+
+@pytest.mark.parametrize("square", [False, True])
+def test_preprocess_u8_packed_flip_square(ops, cuda_device, square):
+    """One pinned byte buffer + offset/height/width table -> the whole transform in one kernel; Resize(256)+CenterCrop
+    (.txt:37-41) and Resize((224, 224)) + RandomHorizontalFlip (HEAD script :222-235) variants."""
+    torch.manual_seed(31)
+    sizes = [(300, 400), (640, 480), (224, 224), (97, 1001), (513, 259), (256, 256)]
+    imgs = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8) for h, w in sizes]
+    buf, table = ops.pack_images(imgs)
+    assert buf.is_pinned() and table.shape == (3, len(sizes)) and int(table[0, 1]) % 16 == 0
+    flip = torch.tensor([0, 1, 1, 0, 1, 0], dtype=torch.uint8, device=cuda_device)
+    out = ops.preprocess_u8_packed(buf.to(cuda_device), table.to(cuda_device), square=square, flip=flip)
+    assert out.shape == (len(sizes), 3, 224, 224)
+    for k, im in enumerate(imgs):
+        ref = _torch_transform(im.to(cuda_device), square=square, flip=bool(flip[k]))
+        err = (out[k] - ref).abs().max().item()
+        assert err < 2e-4, (k, square, err)
+
+
+def test_u8_normalize_is_exact_and_flips(ops, cuda_device):
+    """uint8 [n, H, W, 3] at network resolution -> fp32 NCHW (ToTensor + Normalize), per-image horizontal flip."""
+    torch.manual_seed(32)
+    x = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, device=cuda_device)
+    flip = torch.tensor([1, 0, 1, 0, 0], dtype=torch.uint8, device=cuda_device)
+    mean = torch.tensor(ops.IMAGENET_MEAN, device=cuda_device).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD, device=cuda_device).view(1, 3, 1, 1)
+    ref = (x.permute(0, 3, 1, 2).float() / 255.0 - mean) / std
+    got = ops.u8_normalize(x)
+    assert (got - ref).abs().max().item() < 2e-6
+    got = ops.u8_normalize(x, flip=flip)
+    ref_f = torch.where(flip.view(-1, 1, 1, 1).bool(), ref.flip(-1), ref)
+    assert (got - ref_f).abs().max().item() < 2e-6
+    with pytest.raises(ValueError):
+        ops.u8_normalize(x[:, :, :222].contiguous().permute(0, 2, 1, 3))      # not contiguous HWC
+
+
+def test_prefetcher_runs_gpu_transform_on_uint8_batches(cuda_device):
+    """loop.DevicePrefetcher: uint8 batches (fixed-size and packed) come out as the fp32 tensor the reference's CPU
+    transform would have produced; fp32 batches pass through untouched."""
+    from b200mm import data as D
+    from b200mm.loop import DevicePrefetcher
+    torch.manual_seed(33)
+    S = 16
+
+    def sample(i, h, w):
+        return {"id": f"img_{i}", "text": torch.randint(0, 100, (S,)), "text_mask": torch.ones(S, dtype=torch.long),
+                "image": torch.randint(0, 256, (h, w, 3), dtype=torch.uint8), "label": torch.tensor(i & 1)}
+
+    fixed = [sample(i, 224, 224) for i in range(4)]
+    ragged = [sample(i, 200 + 37 * i, 300 - 11 * i) for i in range(4)]
+    batches = [D.collate_packed(fixed), D.collate_packed(ragged)]
+    assert "image" in batches[0] and batches[0]["image"].dtype == torch.uint8 and batches[0]["image"].is_pinned()
+    assert "image_packed" in batches[1] and batches[1]["image_table"].shape == (3, 4)
+    got = list(DevicePrefetcher(batches, cuda_device))
+    assert len(got) == 2
+    for (text, image, mask, labels, raw), src in zip(got, (fixed, ragged)):
+        assert image.dtype == torch.float32 and image.shape == (4, 3, 224, 224) and image.is_cuda
+        assert torch.equal(text.cpu(), torch.stack([s["text"] for s in src]))
+        assert raw["id"] == [s["id"] for s in src]
+        for k, s in enumerate(src):
+            im = s["image"].to(cuda_device)
+            ref = _torch_transform(im) if im.shape[0] != 224 else _torch_transform(im, resize=224, crop=224)
+            assert (image[k] - ref).abs().max().item() < 2e-4
+
+
 # ------------------------------------------------------------------ BERT / RoBERTa / ViT support kernels
 def test_position_ids_match_transformers(ops, cuda_device):
     """RoBERTa / XLM-R position ids: cumsum(ids != pad) * (ids != pad) + pad
