@@ -7,6 +7,7 @@ reference repository and is not a valid Python identifier).  Public surface = th
     train / test / evaluate                       ...txt:200-242, 259-280
     CrossEntropyLoss, FusedAdam                   ...txt:248-249
     ensemble.*                                    example_scripts/combine_preds.py
+    setup(k) / run_folds / combine_folds          example_scripts/Multimodal_example_task2C.py:50-192, 882-885
 """
 __version__ = "0.1.0"
 
@@ -28,6 +29,9 @@ _LAZY = {
     "seed_everything": ("loop_head", "seed_everything"),
     "stratified_kfold": ("loop_head", "stratified_kfold"),
     "get_params": ("loop_head", "get_params"),
+    "setup": ("folds", "setup"),
+    "run_folds": ("folds", "run_folds"),
+    "combine_folds": ("folds", "combine_folds"),
 }
 
 

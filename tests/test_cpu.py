@@ -447,3 +447,16 @@ def test_host_input_pipeline_token_cache_and_packing(tmp_path):
     assert D.collate_packed(same, pin=False)["image"].shape == (3, 8, 12, 3)   # equal sizes: stacked fast path
     with pytest.raises(ValueError):
         ops.pack_images([torch.zeros(3, 8, 8, dtype=torch.uint8)], pin=False)
+
+
+def test_fold_driver_class_weights_and_split_sizes():
+    """folds.balanced_class_weights == sklearn compute_class_weight('balanced') (Multimodal_example_task2C.py:137-138);
+    the fold driver's constants are the script's (:68-73, 116-117, 171-173)."""
+    from sklearn.utils.class_weight import compute_class_weight
+    from b200mm import folds
+    rng = np.random.RandomState(0)
+    y = (rng.rand(2143) < 603 / 2143).astype(int)
+    ref = compute_class_weight(class_weight="balanced", classes=np.unique(y), y=y)
+    assert np.allclose(folds.balanced_class_weights(y), ref, rtol=0, atol=1e-12)
+    assert (folds.N_SPLITS, folds.SPLIT_SEED, folds.BATCH_SIZE, folds.NUM_EPOCHS) == (5, 42, 16, 8)
+    assert folds.LEARNING_RATE == 1e-5 and folds.WARMUP_RATIO == 0.1

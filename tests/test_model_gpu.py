@@ -4,6 +4,7 @@ on identical synthetic inputs and identical random-init weights.
 Tolerances follow BASELINE.json north_star: activations / logits within 2e-2 relative error (bf16 engine vs fp32
 reference), loss trajectory within 1 %, argmax agreement >= 99.5 %.
 """
+import numpy as np
 import pytest
 import torch
 import torch.nn as nn
@@ -359,6 +360,63 @@ def test_head_style_loop_api(cuda_device, tmp_path):
     assert tsv.check_label_tsv(str(f_lab))
     ids, labels, probs, _ = tsv.read_prob_tsv(str(f_prob))
     assert len(ids) == len(va) and all(0.0 <= p <= 1.0 for p in probs)
+
+
+def test_fold_driver_setup_and_ensemble_tail(cuda_device, tmp_path):
+    """``for k in range(5): setup(k)`` (Multimodal_example_task2C.py:50-192, 882-885) on a tiny model and corpus, then
+    the combine_preds tail over the five probability TSVs the folds wrote."""
+    import b200mm
+    from b200mm import folds, tsv
+    from oracle import reference_model as R
+    cfg = R.TowerConfig.tiny()
+    tcfg = b200mm.TextConfig(vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings,
+                             dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, hidden_dim=cfg.hidden_dim)
+    n_train, n_test, S = 40, 12, 32
+    data = R.synthetic_batch(n_train + n_test, S, cfg)
+    lab = ["propaganda" if int(l) else "not_propaganda" for l in data["label"]]
+    lab[:4] = ["propaganda", "not_propaganda"] * 2
+    rec = lambda lo, hi: {"id": [f"data/x/img_{i}.jpg" for i in range(lo, hi)], "text": list(range(lo, hi)),
+                          "image": list(range(lo, hi)), "label": lab[lo:hi]}
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, r):
+            self.r = r
+
+        def __len__(self):
+            return len(self.r["id"])
+
+        def __getitem__(self, k):
+            i = self.r["text"][k]
+            return {"id": self.r["id"][k], "text": data["text"][i], "text_mask": data["text_mask"][i],
+                    "image": data["image"][i], "label": torch.tensor(self.r["label"][k])}
+
+    def factory():
+        return b200mm.MultimodalClassifier(1, text_config=tcfg, image_config=b200mm.ImageConfig(layers=cfg.resnet_layers),
+                                           device=cuda_device, squeeze_output=True, pooling="cls")
+
+    lines = []
+    runs = b200mm.run_folds(train_records=rec(0, n_train), test_records=rec(n_train, n_train + n_test),
+                            model_factory=factory, make_dataset=DS, device=cuda_device, batch_size=8, num_epochs=2,
+                            out_dir=str(tmp_path), log=lines.append)
+    assert [r.fold for r in runs] == [0, 1, 2, 3, 4]
+    assert [l for l in lines if l.startswith("training for fold")] == [f"training for fold: {k}" for k in range(5)]
+    assert sum(l.startswith("  ALL | Epoch") for l in lines) == 5 * 2 * 2
+    val_ids = set()
+    for r in runs:
+        assert len(r.train_loader.dataset) + len(r.val_loader.dataset) == n_train and len(r.val_loader.dataset) == 8
+        assert r.total_steps == 2 * len(r.train_loader) and r.warmup_steps == int(0.1 * r.total_steps)
+        assert len(r.history) == 2 and r.prob_tsv is not None and r.best_macro_f1 > 0
+        ids, _, probs, _ = tsv.read_prob_tsv(r.prob_tsv)
+        assert sorted(ids) == sorted(rec(n_train, n_train + n_test)["id"]) and all(0 <= p <= 1 for p in probs)
+        val_ids |= set(r.val_loader.dataset.r["id"])
+    assert len(val_ids) == n_train                       # the five validation folds partition the training set
+    gold = dict(zip(rec(n_train, n_train + n_test)["id"], lab[n_train:]))
+    out = tmp_path / "task2C_ensemble.tsv"
+    ids, mean_prob, labels, thr, f1 = b200mm.combine_folds([r.prob_tsv for r in runs], gold, out_path=str(out),
+                                                           log=lines.append)
+    assert len(ids) == n_test and 0 <= thr <= 1 and 0 <= f1 <= 1 and tsv.check_label_tsv(str(out))
+    one = tsv.read_prob_tsv(runs[0].prob_tsv)
+    assert abs(mean_prob[0] - np.mean([dict(zip(*tsv.read_prob_tsv(r.prob_tsv)[0:3:2]))[ids[0]] for r in runs])) < 1e-12
 
 
 # ------------------------------------------------------------------ BASELINE configs 3-5: ViT + BERT / XLM-R towers
