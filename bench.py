@@ -197,13 +197,44 @@ def run_ensemble(args, dev, world, rank):
     def step_resident():
         forward_all(devd)
 
+    # multi-GPU tail: every rank's per-fold logits are gathered on rank 0, which averages the folds'
+    # probabilities per id (combine_preds.py:29-31) and, after the run, writes the five per-fold probability TSVs
+    # (Multimodal_example_task2C.py:869-879) and the ensembled submission through b200mm.combine_folds
+    gathered = torch.empty(world, folds, B, device=dev, dtype=torch.float32) if rank == 0 else None
+    gathered_host = torch.empty(world, folds, B, dtype=torch.float32).pin_memory() if rank == 0 else None
+    all_ids = [f"data/synth/img_{r}_{i}.jpg" for r in range(world) for i in range(B)]
+    kept = {}
+
     def step_e2e():
         d = {k: host[k].to(dev, non_blocking=True) for k in ("text", "text_mask", "image")}
         forward_all(d)
-        logits_host.copy_(logits_dev, non_blocking=False)
-        probs = 1.0 / (1.0 + np.exp(-logits_host.numpy().astype(np.float64)))
-        _, mean_prob = ensemble.average_probability([ids] * folds, list(probs))
+        if world > 1:
+            dist.gather(logits_dev, gather_list=list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+        elif rank == 0:
+            gathered[0].copy_(logits_dev)
+        if rank != 0:
+            return 0
+        gathered_host.copy_(gathered, non_blocking=False)
+        probs = 1.0 / (1.0 + np.exp(-gathered_host.numpy().astype(np.float64)))     # [world, folds, B]
+        per_fold = [probs[:, k, :].reshape(-1) for k in range(folds)]
+        _, mean_prob = ensemble.average_probability([all_ids] * folds, per_fold)
+        kept["per_fold"] = per_fold
         return int((mean_prob > 0.5).sum())
+
+    def write_tail(out_dir):
+        """rank 0, after the timed region: per-fold prob TSVs of the last batch + the ensembled label TSV."""
+        from b200mm import combine_folds, tsv
+        t0 = time.perf_counter()
+        paths = []
+        for k, p in enumerate(kept["per_fold"]):
+            path = os.path.join(out_dir, f"task2C_bench_probs_fold_{k}.tsv")
+            labels = ["propaganda" if x > 0.5 else "not_propaganda" for x in p]
+            tsv.write_prob_tsv(path, all_ids, labels, p, "bench_vit-b16_bert-base")
+            paths.append(path)
+        out = os.path.join(out_dir, "task2C_bench_ensemble.tsv")
+        ids, mean_prob, labels, _, _ = combine_folds(paths, None, out_path=out, log=lambda *_: None)
+        assert len(ids) == world * B and tsv.check_label_tsv(out)
+        return {"rows": len(ids), "files": len(paths) + 1, "seconds": time.perf_counter() - t0}
 
     def barrier():
         if world > 1:
@@ -248,7 +279,13 @@ def run_ensemble(args, dev, world, rank):
             step_e2e()
         ms_e = timed(step_e2e, args.steps) / args.steps
         e2e = {"value": world * B / (ms_e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": folds * B * 4 * world, "ms_per_step": ms_e}
+               "d2h_bytes_per_step": folds * B * 4 * world, "ms_per_step": ms_e,
+               "path": "per-rank forward of 5 resident fold models, logits gathered on rank 0 (NCCL gather), "
+                       "sigmoid + per-id mean over folds on the host every step"}
+        if rank == 0:
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                e2e["tsv_tail"] = write_tail(td)
     if rank == 0:
         print(json.dumps({
             "metric": "ensembled inference samples/s (5 folds, 224px img + 128-tok text)", "value": value,
@@ -339,12 +376,16 @@ def run_engine(args):
         def __iter__(self):
             return itertools.islice(self.it, self.k)
 
-    e2e_warm = 2
+    e2e_warm = int(os.environ.get("B200MM_E2E_WARM", "4"))
     e2e_log = []
 
     def make_e2e_loader():
         shm_free = shutil.disk_usage("/dev/shm").free if os.path.isdir("/dev/shm") else 0
-        workers = min(4, max(1, (os.cpu_count() or 2) // (2 * world))) if shm_free > (4 << 30) else 0
+        # two loader processes keep up with a 31 ms step; more of them take cores from the thread that launches the
+        # step's ~500 kernels (measured on a 16-core box: 0 / 2 / 4 / 8 workers -> 33.1 / 32.2 / 36.7 / 36.4 ms per
+        # step against 31.2 resident, gpurun_out/e2e_probe.log -> profiles/e2e_probe_r02.log)
+        workers = max(1, min(2, (os.cpu_count() or 2) // (4 * world))) if shm_free > (4 << 30) else 0
+        workers = int(os.environ.get("B200MM_E2E_WORKERS", workers))
         kw = dict(prefetch_factor=2, persistent_workers=False) if workers else {}
         dl = DataLoader(SyntheticMemes((e2e_warm + args.steps) * B), batch_size=B, shuffle=False, drop_last=True,
                         num_workers=workers, pin_memory=True, **kw)
