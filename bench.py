@@ -322,7 +322,7 @@ def run_engine(args):
     if args.config == 5:
         return run_ensemble(args, dev, world, rank)
     model, synth_kw = build_model(args.config, dev)
-    if world > 1:
+    if world > 1 and not os.environ.get("B200MM_NO_SYNC"):   # B200MM_NO_SYNC=1: N independent replicas (diagnostic only)
         model.enable_data_parallel()
     model.train()
     crit = b200mm.CrossEntropyLoss()
@@ -426,6 +426,15 @@ def run_engine(args):
     clocks = sampler.stop()
     ms_step = ms / args.steps
     value = world * B / (ms_step * 1e-3)
+    sync_info = None
+    gs = getattr(model, "grad_sync", None)
+    if world > 1 and gs is not None:
+        # exposed tail of the gradient exchange: device time the compute stream waited in GradSync.finish() (inside
+        # FusedAdam.step) during the LAST timed step, max over ranks
+        w = torch.tensor([gs.exposed_wait_ms()], device=dev)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        sync_info = {"payload": gs.payload, "bytes_per_step_per_rank": gs.bytes_per_step,
+                     "phases": {k: len(v) for k, v in gs.phases.items()}, "exposed_wait_ms_last_step": w.item()}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events on the launching stream
     pk = peaks()
@@ -493,6 +502,7 @@ def run_engine(args):
                        "parallelism": f"dp{world}", "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                        "dropout": "on (0.1 / 0.1 / 0.3, Philox)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "grad_sync": sync_info,
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -339,7 +339,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if constexpr (BF16_OUT) {
         constexpr int CHUNKS_PER_BOX = BOX_W / 32;
-        constexpr int PASSES = EPI == EPI_GELU ? 2 : 1;
+        constexpr int PASSES = 1;
         uint8_t* stage_base = staging + ew * (p.nbuf * GEMM_BOX_BYTES);
         const __nv_bfloat16* res_row = nullptr;
         if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP)
@@ -356,10 +356,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           for (int pass = 0; pass < PASSES; ++pass) {
             // the store issued from this buffer `nbuf` boxes ago has left shared memory
             if (lane == 0) {
-              if (p.nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+              if (EPI != EPI_GELU && p.nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
             }
             __syncwarp();
-            uint8_t* stage_buf = stage_base + buf * GEMM_BOX_BYTES;
+            // EPI_GELU: both boxes of the warp per output box (z -> box 0, gelu(z) -> box 1), filled from ONE read of
+            // the accumulator and stored by one bulk group
+            uint8_t* stage_buf = stage_base + (EPI == EPI_GELU ? 0 : buf) * GEMM_BOX_BYTES;
             if constexpr (HAS_SIDE) {
               if (side != nullptr) {
 #pragma unroll
@@ -392,6 +394,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
 #pragma unroll 1
             for (int c = 0; c < CHUNKS_PER_BOX; ++c) {
+              // residual of this lane's row for the whole 32-column chunk: four independent 16-byte loads issued
+              // BEFORE the accumulator read, so their latency overlaps it and each other (one load per 8 columns
+              // right before its use serialised four L2 round trips per chunk: 86 vs 40 us at [32768 x 768 x 768])
+              uint4 rres[4];
+              if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP) {
+                if (res_row != nullptr) {
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) {
+                    const int col = box_col0 + c * 32 + g * 8;
+                    rres[g] = col < p.N ? __ldg(reinterpret_cast<const uint4*>(res_row + col)) : make_uint4(0u, 0u, 0u, 0u);
+                  }
+                }
+              }
               uint32_t v[32];
               tmem_ld32(t_base + box_col_in_tile + c * 32, v);
               tmem_ld_wait();
@@ -406,8 +421,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   if (has_bias && col_ok) {
                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                     const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                    x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                    x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                    const float2 s0 = fadd2(make_float2(x[0], x[1]), make_float2(b0.x, b0.y));
+                    const float2 s1 = fadd2(make_float2(x[2], x[3]), make_float2(b0.z, b0.w));
+                    const float2 s2 = fadd2(make_float2(x[4], x[5]), make_float2(b1.x, b1.y));
+                    const float2 s3 = fadd2(make_float2(x[6], x[7]), make_float2(b1.z, b1.w));
+                    x[0] = s0.x; x[1] = s0.y; x[2] = s1.x; x[3] = s1.y;
+                    x[4] = s2.x; x[5] = s2.y; x[6] = s3.x; x[7] = s3.y;
                   }
                 }
                 if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP) {
@@ -419,11 +438,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   }
                   if (res_row != nullptr && col_ok) {
                     // (row-strided per lane: relies on L1 to serve the other 16-byte pieces of each 128-byte line)
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(res_row + col));
-                    const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y), r2 = unpack_bf16x2(r.z),
-                                 r3 = unpack_bf16x2(r.w);
-                    x[0] += r0.x; x[1] += r0.y; x[2] += r1.x; x[3] += r1.y;
-                    x[4] += r2.x; x[5] += r2.y; x[6] += r3.x; x[7] += r3.y;
+                    const uint4 r = rres[g];
+                    const float2 s0 = fadd2(make_float2(x[0], x[1]), unpack_bf16x2(r.x));
+                    const float2 s1 = fadd2(make_float2(x[2], x[3]), unpack_bf16x2(r.y));
+                    const float2 s2 = fadd2(make_float2(x[4], x[5]), unpack_bf16x2(r.z));
+                    const float2 s3 = fadd2(make_float2(x[6], x[7]), unpack_bf16x2(r.w));
+                    x[0] = s0.x; x[1] = s0.y; x[2] = s1.x; x[3] = s1.y;
+                    x[4] = s2.x; x[5] = s2.y; x[6] = s3.x; x[7] = s3.y;
                   }
                   if constexpr (EPI == EPI_RELU) {
 #pragma unroll
@@ -436,32 +457,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     const uint4 r = *reinterpret_cast<const uint4*>(
                         stage_buf + (BOX_W == 64 ? lane * 128 + ((scc ^ (lane & 7)) << 4)
                                                  : lane * 64 + ((scc ^ ((lane >> 1) & 3)) << 4)));
-                    const float2 z0 = unpack_bf16x2(r.x), z1 = unpack_bf16x2(r.y), z2 = unpack_bf16x2(r.z),
-                                 z3 = unpack_bf16x2(r.w);
-                    x[0] *= gelu_erf_grad(z0.x); x[1] *= gelu_erf_grad(z0.y);
-                    x[2] *= gelu_erf_grad(z1.x); x[3] *= gelu_erf_grad(z1.y);
-                    x[4] *= gelu_erf_grad(z2.x); x[5] *= gelu_erf_grad(z2.y);
-                    x[6] *= gelu_erf_grad(z3.x); x[7] *= gelu_erf_grad(z3.y);
+                    const float2 g0 = fmul2(make_float2(x[0], x[1]), gelu_erf_grad2(unpack_bf16x2(r.x)));
+                    const float2 g1 = fmul2(make_float2(x[2], x[3]), gelu_erf_grad2(unpack_bf16x2(r.y)));
+                    const float2 g2 = fmul2(make_float2(x[4], x[5]), gelu_erf_grad2(unpack_bf16x2(r.z)));
+                    const float2 g3 = fmul2(make_float2(x[6], x[7]), gelu_erf_grad2(unpack_bf16x2(r.w)));
+                    x[0] = g0.x; x[1] = g0.y; x[2] = g1.x; x[3] = g1.y;
+                    x[4] = g2.x; x[5] = g2.y; x[6] = g3.x; x[7] = g3.y;
                   }
                 }
                 uint4 o;
                 o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
                 o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-                if constexpr (EPI == EPI_GELU) {
-                  if (pass == 1) {
-                    // activation of the STORED (bf16-rounded) pre-activation: forward and backward see the same z
-                    const float2 z0 = unpack_bf16x2(o.x), z1 = unpack_bf16x2(o.y), z2 = unpack_bf16x2(o.z),
-                                 z3 = unpack_bf16x2(o.w);
-                    o.x = pack_bf16x2(gelu_erf(z0.x), gelu_erf(z0.y));
-                    o.y = pack_bf16x2(gelu_erf(z1.x), gelu_erf(z1.y));
-                    o.z = pack_bf16x2(gelu_erf(z2.x), gelu_erf(z2.y));
-                    o.w = pack_bf16x2(gelu_erf(z3.x), gelu_erf(z3.y));
-                  }
-                }
                 const int cc = c * 4 + g;  // 16-byte chunk index inside the staged row
                 const uint32_t off = BOX_W == 64 ? lane * 128 + ((cc ^ (lane & 7)) << 4)
                                                  : lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4);
                 *reinterpret_cast<uint4*>(stage_buf + off) = o;
+                if constexpr (EPI == EPI_GELU) {
+                  // activation of the STORED (bf16-rounded) pre-activation: forward and backward see the same z
+                  const float2 a0 = gelu_erf2(unpack_bf16x2(o.x)), a1 = gelu_erf2(unpack_bf16x2(o.y)),
+                               a2 = gelu_erf2(unpack_bf16x2(o.z)), a3 = gelu_erf2(unpack_bf16x2(o.w));
+                  uint4 a;
+                  a.x = pack_bf16x2(a0.x, a0.y); a.y = pack_bf16x2(a1.x, a1.y);
+                  a.z = pack_bf16x2(a2.x, a2.y); a.w = pack_bf16x2(a3.x, a3.y);
+                  *reinterpret_cast<uint4*>(stage_buf + GEMM_BOX_BYTES + off) = a;
+                }
               }
             }
             fence_proxy_async_smem();
@@ -472,7 +491,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 if (p.accumulate) tma_reduce_add_2d(&tma_out, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
                 else tma_store_2d(&tma_out, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
               } else {
-                tma_store_2d(pass == 0 ? &tma_out : &tma_out2, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
+                tma_store_2d(&tma_out, stage_buf, box_col0, m_blk * GEMM_BM + quarter * 32);
+                if constexpr (EPI == EPI_GELU)
+                  tma_store_2d(&tma_out2, stage_buf + GEMM_BOX_BYTES, box_col0, m_blk * GEMM_BM + quarter * 32);
               }
               tma_store_commit();
             }
@@ -588,7 +609,7 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
   }
   // long-K tiles live in the main loop: deepest ring, one staging box; short-K tiles are store-bound: two boxes
   const int k_per_tile = p.k_iters_per_split;
-  p.nbuf = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 0 : (k_per_tile >= 8 ? 1 : 2);   // fp32 modes do not stage
+  p.nbuf = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 0 : (EPI == EPI_GELU || k_per_tile < 8 ? 2 : 1);   // fp32 modes do not stage
   p.num_stages = Cfg::stages_for(p.nbuf);
   static_assert(GemmCfg<BN, CTAS>::stages_for(2) >= 2, "ring too shallow");
   if constexpr (CTAS == 1) {
