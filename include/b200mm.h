@@ -202,6 +202,16 @@ int b200mm_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void*
                          float beta1, float beta2, float eps, float weight_decay, int step, const float* gradsq,
                          float max_norm, float grad_scale, void* stream);
 
+/* CUDA-graph support for the whole train step (small-batch regime: the reference's batch 16 / 8 is launch-bound).
+ * A captured graph freezes by-value launch parameters, so the three per-step host values move to device memory:
+ * the dropout seed salt (added to every dropout seed by the kernels), the Adam step count and the learning rate.
+ * Reference loop being captured: example_scripts/Multimodal_example_task2C.txt:204-217. */
+int b200mm_set_step_salt_ptr(const unsigned long long* salt_dev);
+int b200mm_adam_step_dyn(float* p, const void* g, int g_is_bf16, float* m, float* v, void* shadow_bf16, long long n,
+                         const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                         const int* step_dev, const float* gradsq, float max_norm, float grad_scale, void* stream);
+int b200mm_step_advance(unsigned long long* salt_dev, int* adam_step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ _LAZY = {
     "seed_everything": ("loop_head", "seed_everything"),
     "stratified_kfold": ("loop_head", "stratified_kfold"),
     "get_params": ("loop_head", "get_params"),
+    "GraphedTrainStep": ("graph", "GraphedTrainStep"),
     "setup": ("folds", "setup"),
     "run_folds": ("folds", "run_folds"),
     "combine_folds": ("folds", "combine_folds"),

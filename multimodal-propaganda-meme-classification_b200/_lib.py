@@ -64,7 +64,8 @@ def load(build_if_needed: bool = True) -> ctypes.CDLL:
 
 # kernels launched through this module since the counter was last reset (bench.py's gpu_launches)
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0}
+_KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0,
+                     "b200mm_set_step_salt_ptr": 0}
 
 
 # optional per-call CUDA-event profile of a real (pipelined, warm-L2) run: PROFILE = [] enables it;
@@ -134,6 +135,10 @@ declare("b200mm_scale_cast_f32_to_bf16", [c_ptr, c_ptr, c_longlong, c_float, c_p
 declare("b200mm_sumsq_bf16", [c_ptr, c_longlong, c_ptr, c_ptr])
 declare("b200mm_adam_step_g16", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_longlong, c_float, c_float, c_float, c_float,
                                  c_float, c_int, c_ptr, c_float, c_float, c_ptr])
+declare("b200mm_set_step_salt_ptr", [c_ptr])
+declare("b200mm_adam_step_dyn", [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_longlong, c_ptr, c_float, c_float, c_float,
+                                 c_float, c_ptr, c_ptr, c_float, c_float, c_ptr])
+declare("b200mm_step_advance", [c_ptr, c_ptr, c_ptr])
 declare("b200mm_gather_rows", [c_ptr, c_ptr, c_int, c_int, c_longlong, c_longlong, c_float, c_ulonglong, c_ptr])
 declare("b200mm_scatter_rows", [c_ptr, c_ptr, c_longlong, c_int, c_longlong, c_longlong, c_float, c_ulonglong,
                                 c_ptr])

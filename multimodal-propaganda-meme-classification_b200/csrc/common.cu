@@ -134,6 +134,27 @@ int make_tmap_nhwc_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W, 
 
 }  // namespace b200
 
+namespace b200 {
+namespace {
+constexpr int MAX_SALT_SETTERS = 32;
+int (*g_salt_setters[MAX_SALT_SETTERS])(const unsigned long long*);
+int g_num_salt_setters = 0;
+}  // namespace
+void register_step_salt_setter(int (*setter)(const unsigned long long*)) {
+  if (g_num_salt_setters < MAX_SALT_SETTERS) g_salt_setters[g_num_salt_setters++] = setter;
+}
+}  // namespace b200
+
+// Point every translation unit's dropout seed salt (device_utils.cuh) at `salt` (device memory, one uint64; nullptr
+// = no salt).  Synchronous (cudaMemcpyToSymbol): call outside stream capture.
+B200MM_API int b200mm_set_step_salt_ptr(const unsigned long long* salt) {
+  for (int i = 0; i < b200::g_num_salt_setters; ++i) {
+    const int rc = b200::g_salt_setters[i](salt);
+    if (rc != 0) return rc;
+  }
+  return B200MM_OK;
+}
+
 B200MM_API int b200mm_version() { return 100; }
 
 // Number of SMs of the current device (0 if no usable device): lets the host side size grids.

@@ -2,6 +2,7 @@
 // 16-byte vector <-> bf16x8 conversion.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_runtime.h>
 #include <cstdint>
 
 namespace b200 {
@@ -15,6 +16,26 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Per-step salt of every dropout seed, read from DEVICE memory.  The host derives one seed per dropout site from
+// (model seed, step, layer, site) and passes it by value; a CUDA graph freezes those values at capture, so a graphed
+// train step additionally adds *c_step_salt -- a device counter its last node advances -- and every replay draws fresh
+// masks (forward and backward of one replay read the same value).  nullptr (eager mode): seeds are used as passed.
+// One copy of the pointer per translation unit (no relocatable device code in this build): each unit registers a
+// setter, b200mm_set_step_salt_ptr (common.cu) calls them all.
+static __constant__ const unsigned long long* c_step_salt = nullptr;
+void register_step_salt_setter(int (*setter)(const unsigned long long*));
+static int set_step_salt_this_unit(const unsigned long long* ptr) {
+  return static_cast<int>(cudaMemcpyToSymbol(c_step_salt, &ptr, sizeof(ptr)));
+}
+struct StepSaltRegistration {
+  explicit StepSaltRegistration(int (*setter)(const unsigned long long*)) { register_step_salt_setter(setter); }
+};
+static StepSaltRegistration step_salt_registration(&set_step_salt_this_unit);
+__device__ __forceinline__ uint64_t step_seed(uint64_t seed) {
+  const unsigned long long* sp = c_step_salt;
+  return sp != nullptr ? seed + __ldg(sp) : seed;
 }
 
 // Philox4x32-10: stateless counter RNG so that forward and backward (and every data-parallel replica,
@@ -57,6 +78,7 @@ __device__ __forceinline__ uint4 philox4x32_r(uint64_t seed, uint64_t ctr) {
 }
 // 32 keep bits (bit i set = element i kept) for one 32-element chunk; thr16 = p_drop * 2^16.
 __device__ __forceinline__ uint32_t dropout_keep32(uint64_t seed, uint64_t chunk_idx, uint32_t thr16) {
+  seed = step_seed(seed);
   uint32_t bits = 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -76,7 +98,7 @@ __device__ __forceinline__ uint32_t dropout_keep32(uint64_t seed, uint64_t chunk
 // here, forward and backward alike -- two 10-round calls per 8 elements made the LayerNorm backward ALU-bound.
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t group8_idx, uint32_t threshold) {
   const uint32_t thr16 = threshold >> 16;
-  const uint4 r = philox4x32_r<7>(seed, group8_idx);
+  const uint4 r = philox4x32_r<7>(step_seed(seed), group8_idx);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
   uint32_t bits = 0;
 #pragma unroll
@@ -88,7 +110,7 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t group8
 }
 // keep-mask for 4 consecutive elements: bit i set = element kept. threshold = p_drop * 2^32.
 __device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t group_idx, uint32_t threshold) {
-  const uint4 r = philox4x32(seed, group_idx);
+  const uint4 r = philox4x32(step_seed(seed), group_idx);
   return (r.x >= threshold ? 1u : 0u) | (r.y >= threshold ? 2u : 0u) | (r.z >= threshold ? 4u : 0u) |
          (r.w >= threshold ? 8u : 0u);
 }

@@ -207,7 +207,16 @@ template <typename G>
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const G* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __nv_bfloat16* __restrict__ shadow, long long n, float step_size, float inv_sqrt_bc2, float b1, float b2,
-            float eps, float weight_decay, const float* __restrict__ gradsq, float max_norm, float grad_scale) {
+            float eps, float weight_decay, const float* __restrict__ gradsq, float max_norm, float grad_scale,
+            const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    // graph-captured step: learning rate and step count live in device memory (the launch parameters are frozen at
+    // capture).  bias corrections 1 - beta^t through expm1 (no cancellation at small t).
+    const float t = static_cast<float>(*step_dev);
+    const float bc1 = -expm1f(t * logf(b1)), bc2 = -expm1f(t * logf(b2));
+    step_size = *lr_dev / bc1;
+    inv_sqrt_bc2 = rsqrtf(bc2);
+  }
   float clip = grad_scale;
   if (gradsq != nullptr) {
     const float norm = sqrtf(*gradsq) * grad_scale;
@@ -305,6 +314,14 @@ scatter_rows_kernel(const __nv_bfloat16* __restrict__ dpooled, __nv_bfloat16* __
   }
 }
 
+// last node of a captured train step: the next replay sees a new dropout salt and Adam step count
+__global__ void step_advance_kernel(unsigned long long* salt, int* adam_step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (salt != nullptr) *salt += 0x9E3779B97F4A7C15ull;
+    if (adam_step != nullptr) *adam_step += 1;
+  }
+}
+
 static int grid_for(long long work_items, int threads) {
   const DeviceInfo& dev = device_info();
   const long long max_ctas = static_cast<long long>(dev.num_sms > 0 ? dev.num_sms : 148) * 8;
@@ -371,7 +388,8 @@ B200MM_API int b200mm_adam_step(float* p, const float* g, float* m, float* v, vo
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   adam_kernel<float><<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, static_cast<float>(lr / bc1),
-      static_cast<float>(1.0 / sqrt(bc2)), beta1, beta2, eps, weight_decay, gradsq, max_norm, grad_scale);
+      static_cast<float>(1.0 / sqrt(bc2)), beta1, beta2, eps, weight_decay, gradsq, max_norm, grad_scale, nullptr,
+      nullptr);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -386,7 +404,35 @@ B200MM_API int b200mm_adam_step_g16(float* p, const void* g_bf16, float* m, floa
   adam_kernel<__nv_bfloat16><<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       p, static_cast<const __nv_bfloat16*>(g_bf16), m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n,
       static_cast<float>(lr / bc1), static_cast<float>(1.0 / sqrt(bc2)), beta1, beta2, eps, weight_decay, gradsq,
-      max_norm, grad_scale);
+      max_norm, grad_scale, nullptr, nullptr);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// Capturable Adam step: learning rate (*lr_dev) and step count (*step_dev, >= 1) are read on the device, so ONE captured
+// launch serves every replay of a CUDA graph (the scheduler rewrites *lr_dev, b200mm_step_advance increments *step_dev).
+// g_is_bf16: the gradient buffer is the bf16 data-parallel payload.
+B200MM_API int b200mm_adam_step_dyn(float* p, const void* g, int g_is_bf16, float* m, float* v, void* shadow_bf16,
+                                    long long n, const float* lr_dev, float beta1, float beta2, float eps,
+                                    float weight_decay, const int* step_dev, const float* gradsq, float max_norm,
+                                    float grad_scale, void* stream) {
+  if (n <= 0 || (n & 3) || !lr_dev || !step_dev) return B200MM_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_is_bf16)
+    adam_kernel<__nv_bfloat16><<<grid_for(n >> 2, 256), 256, 0, st>>>(
+        p, static_cast<const __nv_bfloat16*>(g), m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, 0.f, 1.f, beta1,
+        beta2, eps, weight_decay, gradsq, max_norm, grad_scale, lr_dev, step_dev);
+  else
+    adam_kernel<float><<<grid_for(n >> 2, 256), 256, 0, st>>>(
+        p, static_cast<const float*>(g), m, v, static_cast<__nv_bfloat16*>(shadow_bf16), n, 0.f, 1.f, beta1, beta2, eps,
+        weight_decay, gradsq, max_norm, grad_scale, lr_dev, step_dev);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// salt += odd constant, adam_step += 1 (either may be nullptr): the last node of a captured step.
+B200MM_API int b200mm_step_advance(unsigned long long* salt, int* adam_step, void* stream) {
+  step_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(salt, adam_step);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

@@ -190,7 +190,11 @@ def _fused(criterion):
     return isinstance(criterion, (CrossEntropyLoss, SigmoidFocalLoss))
 
 
-def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_step=None, image_transform=None):
+def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_step=None, image_transform=None,
+          graph=None):
+    """One epoch (.txt:200-223).  ``graph``: a ``b200mm.GraphedTrainStep`` built over (model, optimizer, criterion) --
+    the loop body then runs as one CUDA-graph replay per step (the small-batch regime, where launching the step's
+    ~500 kernels is what bounds it); batches whose shape differs from the captured one take the eager step."""
     model.train()
     train_loss = 0.0
     correct = 0
@@ -198,6 +202,8 @@ def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_
     fused = _fused(criterion) and hasattr(model, "train_step_fused")
     readback = StepReadback(device) if fused else None
     prev_bs = 0
+    if graph is not None and not fused:
+        raise ValueError("graph= needs the fused criterion (b200mm.CrossEntropyLoss / SigmoidFocalLoss)")
 
     def account(done, bs):
         nonlocal train_loss, correct
@@ -207,6 +213,16 @@ def train(model, train_loader, criterion, optimizer, device, scheduler=None, on_
             on_step(done[0], bs)
 
     for text, image, mask, labels, data in DevicePrefetcher(train_loader, device, image_transform=image_transform):
+        if graph is not None:
+            _, loss, ok = graph(text, image, mask, labels)
+            if scheduler is not None:
+                scheduler.step()
+            done = readback.push(loss, ok)
+            if done is not None:
+                account(done, prev_bs)
+            prev_bs = labels.size(0)
+            n += prev_bs
+            continue
         optimizer.zero_grad()
         if fused:
             _, loss, ok = model.train_step_fused(text, image, mask, labels, loss_kind=criterion.loss_kind,

@@ -446,6 +446,24 @@ def adam_step(p, g, m, v, shadow, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weigh
               float(grad_scale), _s())
 
 
+def adam_step_dyn(p, g, m, v, shadow, *, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
+                  gradsq=None, max_norm=0.0, grad_scale=1.0):
+    """adam_step with the learning rate (fp32 device scalar) and step count (int32 device scalar) read on the device:
+    the launch can be captured in a CUDA graph and replayed while both change."""
+    _lib.call("b200mm_adam_step_dyn", _p(p), _p(g), int(g.dtype == bf16), _p(m), _p(v), _p(shadow), p.numel(),
+              _p(lr_dev), float(beta1), float(beta2), float(eps), float(weight_decay), _p(step_dev), _p(gradsq),
+              float(max_norm), float(grad_scale), _s())
+
+
+def set_step_salt(salt):
+    """salt: uint64-sized device tensor (int64 [1]) added to every dropout seed by the kernels, or None."""
+    _lib.call("b200mm_set_step_salt_ptr", _p(salt))
+
+
+def step_advance(salt, adam_step):
+    _lib.call("b200mm_step_advance", _p(salt), _p(adam_step), _s())
+
+
 def cast_to_bf16(x, y, scale: float = 1.0):
     if scale == 1.0:
         _lib.call("b200mm_cast_f32_to_bf16", _p(x), _p(y), x.numel(), _s())

@@ -33,6 +33,10 @@ class FusedAdam(torch.optim.Optimizer):
         self._gradsq = torch.zeros(1, device=self.store.device, dtype=torch.float32)
         self._step = 0
         self.last_grad_norm = None
+        # capturable mode (graph.GraphedTrainStep): step count and per-group learning rates in device memory
+        self._step_dev = None
+        self._lr_dev = None
+        self._lr_host = None
         # contiguous element ranges per param group (alignment padding between parameters is all-zero: safe to sweep)
         self._ranges = []
         for gi, g in enumerate(self.param_groups):
@@ -66,18 +70,45 @@ class FusedAdam(torch.optim.Optimizer):
             # device scalar: SQUARED norm of the mean gradient (.sqrt().item() when logging)
             self.last_grad_norm = self._gradsq if grad_scale == 1.0 else self._gradsq * (grad_scale * grad_scale)
         s0 = st.shadow_start
-        for g, ranges in zip(self.param_groups, self._ranges):
+        for gi, (g, ranges) in enumerate(zip(self.param_groups, self._ranges)):
             b1, b2 = g["betas"]
             for a, b in ranges:
                 # split at the shadow boundary: embedding tables / norm params have no bf16 shadow
                 for lo, hi, sh in ((a, min(b, s0), False), (max(a, s0), b, True)):
                     if hi <= lo:
                         continue
+                    if self._step_dev is not None:
+                        ops.adam_step_dyn(st.master[lo:hi], grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                                          st.shadow[lo:hi] if sh else None, lr_dev=self._lr_dev[gi:gi + 1],
+                                          step_dev=self._step_dev, beta1=b1, beta2=b2, eps=g["eps"],
+                                          weight_decay=g["weight_decay"], gradsq=gradsq,
+                                          max_norm=self.max_grad_norm or 0.0, grad_scale=grad_scale)
+                        continue
                     ops.adam_step(st.master[lo:hi], grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
                                   st.shadow[lo:hi] if sh else None, lr=g["lr"], beta1=b1, beta2=b2, eps=g["eps"],
                                   weight_decay=g["weight_decay"], step=self._step, gradsq=gradsq,
                                   max_norm=self.max_grad_norm or 0.0, grad_scale=grad_scale)
         self.model._shadow_fresh = True
+
+    # ---- CUDA-graph support (graph.GraphedTrainStep)
+    def make_capturable(self):
+        """Move the step count and the learning rates to device memory (read by b200mm_adam_step_dyn): a captured
+        ``step()`` then serves every replay.  ``_step_dev`` holds the count the NEXT step uses; the graph's last node
+        (ops.step_advance) increments it, ``sync_lr()`` pushes the param groups' current learning rates."""
+        dev = self.store.device
+        self._step_dev = torch.full((1,), self._step + 1, device=dev, dtype=torch.int32)
+        self._lr_host = [float(g["lr"]) for g in self.param_groups]
+        self._lr_dev = torch.tensor(self._lr_host, device=dev, dtype=torch.float32)
+        return self
+
+    def sync_lr(self):
+        """Push learning rates a scheduler changed since the last call (one fill kernel per changed group: the value
+        travels in the launch, so nothing on the host must outlive the call)."""
+        for gi, g in enumerate(self.param_groups):
+            lr = float(g["lr"])
+            if lr != self._lr_host[gi]:
+                self._lr_dev[gi:gi + 1].fill_(lr)
+                self._lr_host[gi] = lr
 
     # ---- checkpoint / resume: the moments and the step count live outside Optimizer.state (flat buffers)
     def state_dict(self):

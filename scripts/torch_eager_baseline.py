@@ -1,7 +1,7 @@
 """Stock PyTorch on the same B200 ("the bar on the GPU box is the stock PyTorch eager/SDPA path running
 the same module"): the oracle module (transformers DistilBERT + torchvision ResNet-50, the reference's own libraries) in
 bf16 autocast with SDPA attention, channels_last convolutions (cuDNN), torch.optim.Adam(fused=True), batch 256.
-A reported baseline only; writes profiles/torch_eager_baseline_r01.json."""
+A reported baseline only; PB=<batch> selects the batch; writes gpurun_out/torch_eager_baseline_b<batch>.json."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn as nn
@@ -42,5 +42,4 @@ rep = {"what": "stock PyTorch %s eager, bf16 autocast, SDPA, channels_last, fuse
        "batch": B, "seq_len": S, "ms_per_step": ms, "samples_per_s": B / ms * 1e3}
 print(json.dumps(rep))
 os.makedirs("profiles", exist_ok=True); os.makedirs("gpurun_out", exist_ok=True)
-json.dump(rep, open("profiles/torch_eager_baseline_r01.json", "w"), indent=1)
-json.dump(rep, open("gpurun_out/torch_eager_baseline_r01.json", "w"), indent=1)
+json.dump(rep, open(f"gpurun_out/torch_eager_baseline_b{B}.json", "w"), indent=1)

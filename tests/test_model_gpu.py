@@ -362,6 +362,79 @@ def test_head_style_loop_api(cuda_device, tmp_path):
     assert len(ids) == len(va) and all(0.0 <= p <= 1.0 for p in probs)
 
 
+def _tiny_engine(cuda_device, dropout, seed=42):
+    import b200mm
+    from oracle import reference_model as R
+    cfg = R.TowerConfig.tiny()
+    tcfg = b200mm.TextConfig(vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings,
+                             dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, hidden_dim=cfg.hidden_dim,
+                             dropout=dropout, attention_dropout=dropout)
+    eng = b200mm.MultimodalClassifier(2, text_config=tcfg, image_config=b200mm.ImageConfig(layers=cfg.resnet_layers),
+                                      head_dropout=dropout, device=cuda_device, seed=seed)
+    return eng, cfg
+
+
+def test_cuda_graph_step_matches_eager_step(cuda_device):
+    """GraphedTrainStep == zero_grad / train_step_fused / FusedAdam.step, replay after replay (dropout off so both
+    routes are deterministic): same losses, same parameters, same Adam state, same BatchNorm buffers -- including
+    through a learning-rate schedule and with the capture's warm-up steps undone."""
+    import b200mm
+    from oracle import reference_model as R
+    eng_e, cfg = _tiny_engine(cuda_device, 0.0)
+    eng_g, _ = _tiny_engine(cuda_device, 0.0)
+    eng_g.load_reference_state_dict(eng_e.reference_state_dict())
+    batches = [_dev(R.synthetic_batch(8, 32, cfg, seed=100 + i), cuda_device) for i in range(5)]
+    crit = b200mm.CrossEntropyLoss()
+    opt_e = b200mm.FusedAdam(eng_e.parameters(), lr=1e-3, max_grad_norm=10.0)
+    opt_g = b200mm.FusedAdam(eng_g.parameters(), lr=1e-3, max_grad_norm=10.0)
+    sch_e = b200mm.get_linear_schedule_with_warmup(opt_e, 2, 10)
+    sch_g = b200mm.get_linear_schedule_with_warmup(opt_g, 2, 10)
+    step = b200mm.GraphedTrainStep(eng_g, opt_g, crit)
+    eng_e.train()
+    for d in batches:
+        opt_e.zero_grad()
+        _, loss_e, ok_e = eng_e.train_step_fused(d["text"], d["image"], d["text_mask"], d["label"])
+        opt_e.step()
+        sch_e.step()
+        _, loss_g, ok_g = step(d["text"], d["image"], d["text_mask"], d["label"])
+        sch_g.step()
+        assert abs(loss_e.item() - loss_g.item()) <= 2e-4 * abs(loss_e.item()), (loss_e.item(), loss_g.item())
+        assert int(ok_e.item()) == int(ok_g.item())
+    assert step.replays == len(batches) and opt_g._step == opt_e._step == len(batches)
+    assert rel(eng_g.store.master, eng_e.store.master) < 2e-5
+    assert rel(opt_g.exp_avg, opt_e.exp_avg) < 1e-3 and rel(opt_g.exp_avg_sq, opt_e.exp_avg_sq) < 1e-3
+    assert rel(eng_g.img.buffers, eng_e.img.buffers) < 1e-5
+    # a batch of another shape takes the eager route and keeps the device counters in step
+    odd = _dev(R.synthetic_batch(4, 32, cfg, seed=7), cuda_device)
+    step(odd["text"], odd["image"], odd["text_mask"], odd["label"])
+    assert step.replays == len(batches) and opt_g._step == len(batches) + 1
+    assert int(opt_g._step_dev.item()) == opt_g._step + 1
+    step.close()
+
+
+def test_cuda_graph_replays_draw_fresh_dropout_masks(cuda_device):
+    """The captured seeds are frozen; the device-side salt must still give every replay its own masks, and forward /
+    backward of one replay the same ones (a mismatch would wreck the gradient: checked through the loss going down
+    on a repeated batch)."""
+    import b200mm
+    from oracle import reference_model as R
+    eng, cfg = _tiny_engine(cuda_device, 0.3)
+    d = _dev(R.synthetic_batch(8, 32, cfg, seed=5), cuda_device)
+    opt = b200mm.FusedAdam(eng.parameters(), lr=0.0)          # lr 0: the model does not move, only the masks do
+    step = b200mm.GraphedTrainStep(eng, opt, b200mm.CrossEntropyLoss())
+    losses = [step(d["text"], d["image"], d["text_mask"], d["label"])[1].item() for _ in range(4)]
+    assert len({round(l, 6) for l in losses}) == 4, losses
+    assert int(step.salt.item()) != 0
+    for g in opt.param_groups:
+        g["lr"] = 2e-3
+    first = None
+    for _ in range(30):
+        loss = step(d["text"], d["image"], d["text_mask"], d["label"])[1].item()
+        first = loss if first is None else first
+    assert loss < first, (first, loss)
+    step.close()
+
+
 def test_fold_driver_setup_and_ensemble_tail(cuda_device, tmp_path):
     """``for k in range(5): setup(k)`` (Multimodal_example_task2C.py:50-192, 882-885) on a tiny model and corpus, then
     the combine_preds tail over the five probability TSVs the folds wrote."""
