@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the CPU reference step (BASELINE config 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the step's kernels one by one instead of replaying the captured CUDA graph (N = 1)")
     return ap.parse_args()
 
 
@@ -333,11 +335,22 @@ def run_engine(args):
     devd = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
-    def step_resident():
+    def step_eager():
         opt.zero_grad()
         _, loss, ok = model.train_step_fused(devd["text"], devd["image"], devd["text_mask"], devd["label"])
         opt.step()
         return loss
+
+    # one process: the loop body (zero_grad / forward / loss / backward / Adam) is captured once as a CUDA graph and
+    # replayed -- the same ~500 kernels, enqueued by one cudaGraphLaunch instead of 500 host calls (at batch 256 the
+    # host needs 30 of the step's 31 ms to enqueue them one by one: profiles/small_batch_r02.json).  Data parallel
+    # runs stay eager: the gradient exchange lives on NCCL's stream.
+    gstep = b200mm.GraphedTrainStep(model, opt, crit) if (world == 1 and not args.no_graph) else None
+
+    def step_resident():
+        if gstep is None:
+            return step_eager()
+        return gstep(devd["text"], devd["image"], devd["text_mask"], devd["label"])[1]
 
     # end-to-end: b200mm.train() ITSELF over a torch DataLoader(pin_memory=True), the call a user of the reference
     # makes (.txt:251-257).  The dataset hands out what a decoder produces -- uint8 HWC pixels at network resolution +
@@ -392,7 +405,8 @@ def run_engine(args):
         return Primed(dl), workers
 
     def e2e_train(primed, k):
-        return b200mm.train(model, primed.take(k), crit, opt, dev, on_step=lambda loss, bs: e2e_log.append(loss))
+        return b200mm.train(model, primed.take(k), crit, opt, dev, on_step=lambda loss, bs: e2e_log.append(loss),
+                            graph=gstep)
 
     def barrier():
         if world > 1:
@@ -422,7 +436,7 @@ def run_engine(args):
     sampler.start()
     _lib.LAUNCHES[0] = 0
     ms = timed(step_resident, args.steps)
-    launches = _lib.LAUNCHES[0]
+    launches = _lib.LAUNCHES[0] if gstep is None else gstep.launches_per_replay * args.steps
     clocks = sampler.stop()
     ms_step = ms / args.steps
     value = world * B / (ms_step * 1e-3)
@@ -439,7 +453,7 @@ def run_engine(args):
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events on the launching stream
     pk = peaks()
     ridge = pk["bf16_tflops_sustained"] * 1e12 / (pk["hbm_gbs"] * 1e9)        # FLOP per byte
-    gemm_ms, gemm_flops, n_gemm, det = ops.profile_gemm(step_resident, steps=2, ridge=ridge)
+    gemm_ms, gemm_flops, n_gemm, det = ops.profile_gemm(step_eager if gstep is None else (lambda: gstep.eager(devd["text"], devd["image"], devd["text_mask"], devd["label"])), steps=2, ridge=ridge)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     t, h = det["tensor"], det["hbm"]
     # DRAM traffic of the same kernel from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum, average
@@ -480,7 +494,7 @@ def run_engine(args):
         e2e = {"value": world * B / (ms_e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_e * world,
                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e,
                "path": "b200mm.train(model, DataLoader(pin_memory=True, num_workers=%d), CrossEntropyLoss, FusedAdam, "
-                       "device): uint8 HWC pixels + token ids from pinned memory, ToTensor/Normalize on the GPU copy "
+                       "device, graph=GraphedTrainStep when N = 1): uint8 HWC pixels + token ids from pinned memory, ToTensor/Normalize on the GPU copy "
                        "stream" % workers,
                "readback": "loss + correct count of every step, asynchronous to pinned memory, consumed one step later",
                "last_loss": e2e_log[-1]}
@@ -500,7 +514,8 @@ def run_engine(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "image": "3x224x224",
                        "parallelism": f"dp{world}", "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
-                       "dropout": "on (0.1 / 0.1 / 0.3, Philox)"},
+                       "dropout": "on (0.1 / 0.1 / 0.3, Philox)",
+                       "launch": "eager" if gstep is None else "cuda_graph (one replay per step)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "grad_sync": sync_info,
         }), flush=True)

@@ -48,6 +48,7 @@ class GraphedTrainStep:
         self.static_in = None
         self.static_out = None
         self.replays = 0
+        self.launches_per_replay = 0
 
     # ------------------------------------------------------------------ the loop body (eager)
     def _body(self, text, image, mask, labels):
@@ -78,9 +79,12 @@ class GraphedTrainStep:
         opt.make_capturable()
         ops.set_step_salt(self.salt)
         self.graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        before = _lib.LAUNCHES[0]
         with torch.cuda.graph(self.graph):
             self.static_out = self._body(*self.static_in)
             ops.step_advance(self.salt, opt._step_dev)
+        self.launches_per_replay = _lib.LAUNCHES[0] - before      # kernel nodes of ours in the graph
         # the capture only recorded work; the warm-up steps did run: restore parameters, moments, BatchNorm buffers
         # and the host / device step counters
         for dst, src in zip((st.master, opt.exp_avg, opt.exp_avg_sq, *bufs), snap):
