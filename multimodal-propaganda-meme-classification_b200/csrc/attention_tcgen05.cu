@@ -28,8 +28,11 @@ constexpr int ATT_MAX_S = 512;
 
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic ON the __shared__ array: the compiler keeps the
+  // address space and emits LDS / STS (the former round-up through uintptr_t turned every access of the tiles,
+  // the staging boxes and the bias rows into generic LD.E / ST.E, which queue with the global loads)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_TILE_BYTES;
   uint8_t* sV = sK + ATT_TILE_BYTES;
@@ -198,8 +201,8 @@ attn_fwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPar
 __global__ void __launch_bounds__(128, 1)
 attn_bwd_multi_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                       const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + ATT_TILE_BYTES;
   uint8_t* sV = sK + ATT_TILE_BYTES;
@@ -393,8 +396,8 @@ template <int NT>
 __global__ void __launch_bounds__(256, NT <= 2 ? 2 : 1)
 attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_out,
                      const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sQP = smem;                              // Q [128 x 64] first, then P [128 x 128], then the staged O tile
   uint8_t* sK = sQP + 2 * ATT_TILE_BYTES;           // NT tiles
   uint8_t* sV = sK + NT * ATT_TILE_BYTES;           // NT tiles
@@ -572,8 +575,8 @@ constexpr int ATT_BWD2_SMEM = 12 * ATT_TILE_BYTES + 2 * ATT_T * 4 + 64 + 1024;
 __global__ void __launch_bounds__(ATT_BWD2_THREADS, 1)
 attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                      const __grid_constant__ CUtensorMap tma_dqkv, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sQ = smem;                               // 2 tiles each: [tile][128 x 64]
   uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;
   uint8_t* sV = sK + 2 * ATT_TILE_BYTES;
@@ -813,8 +816,8 @@ __global__ void __launch_bounds__(256, 1)
 attn_bwd_tmem3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                       const __grid_constant__ CUtensorMap tma_dqkv, const AttnParams p) {
   constexpr int NT = 3;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sQ = smem;                                // NT tiles each
   uint8_t* sK = sQ + NT * ATT_TILE_BYTES;
   uint8_t* sV = sK + NT * ATT_TILE_BYTES;
@@ -1068,8 +1071,8 @@ constexpr int ATT_BWD1_SMEM = 12 * ATT_TILE_BYTES + 2 * ATT_T * 4 + 64 + 1024;
 __global__ void __launch_bounds__(256, 1)
 attn_bwd1_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                  const __grid_constant__ CUtensorMap tma_dqkv, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sIn = smem;                              // [2 stages][Q | K | V | dO], 64 KB per stage
   uint8_t* sP = sIn + 8 * ATT_TILE_BYTES;           // 32 KB
   uint8_t* sdS = sP + 2 * ATT_TILE_BYTES;           // 32 KB

@@ -60,8 +60,11 @@ constexpr int WSF_SMEM = WSF_SLOTS * WSF_SLOT_BYTES + WSF_SLOTS * ATT_T * 4 + 25
 __global__ void __launch_bounds__(WSF_THREADS, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_out,
                    const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic ON the __shared__ array: the compiler keeps the
+  // address space and emits LDS / STS (the former round-up through uintptr_t turned every access of the tiles,
+  // the staging boxes and the bias rows into generic LD.E / ST.E, which queue with the global loads)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* slots = smem;
   float* sBias = reinterpret_cast<float*>(slots + WSF_SLOTS * WSF_SLOT_BYTES);   // [SLOTS][128]
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(sBias + WSF_SLOTS * ATT_T);   // operands of the slot's head landed
@@ -269,8 +272,8 @@ static_assert(WSB_SMEM <= 232448, "backward slots must fit the 227 KB of opt-in 
 __global__ void __launch_bounds__(WSB_THREADS, 1)
 attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_constant__ CUtensorMap tma_do,
                    const __grid_constant__ CUtensorMap tma_dqkv, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* slots = smem;
   float* sBias = reinterpret_cast<float*>(slots + WSB_SLOTS * WSB_SLOT_BYTES);   // [SLOTS][128]
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(sBias + WSB_SLOTS * ATT_T);   // Q, K, V, dO landed

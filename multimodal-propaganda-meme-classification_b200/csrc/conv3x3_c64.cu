@@ -45,8 +45,11 @@ struct C3Args {
 __global__ void __launch_bounds__(C3_THREADS, 1)
 conv3x3_c64_fwd_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                        const __grid_constant__ CUtensorMap tma_out, C3Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic ON the __shared__ array: the compiler keeps the
+  // address space and emits LDS / STS (the former round-up through uintptr_t turned every access of the tiles,
+  // the staging boxes and the bias rows into generic LD.E / ST.E, which queue with the global loads)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem + C3Smem::W;
   uint8_t* sHalo = smem + C3Smem::HALO;
   uint8_t* sOut = smem + C3Smem::OUT;
@@ -213,8 +216,8 @@ constexpr int C3W_THREADS = 192;
 
 __global__ void __launch_bounds__(C3W_THREADS, 1)
 conv3x3_c64_wgrad_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_dy, C3Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sHalo = smem + C3WSmem::HALO;
   uint8_t* sDy = smem + C3WSmem::DY;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C3WSmem::BAR);

@@ -50,8 +50,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   constexpr bool PAIR = CTAS == 2;
   const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   const int STAGES = p.num_stages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic ON the __shared__ array: the compiler keeps the
+  // address space and emits LDS / STS (the former round-up through uintptr_t turned every access of the tiles,
+  // the staging boxes and the bias rows into generic LD.E / ST.E, which queue with the global loads)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (STAGE_BYTES is a multiple of 1024)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_WARPS * p.nbuf * GEMM_BOX_BYTES);
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;

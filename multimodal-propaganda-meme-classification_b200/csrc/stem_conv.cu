@@ -132,8 +132,11 @@ __device__ __forceinline__ void stem_prologue(uint8_t* smem) {
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_out, StemArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic ON the __shared__ array: the compiler keeps the
+  // address space and emits LDS / STS (the former round-up through uintptr_t turned every access of the tiles,
+  // the staging boxes and the bias rows into generic LD.E / ST.E, which queue with the global loads)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem + StemSmem::A;
   uint8_t* sW = smem + StemSmem::X;
   uint8_t* sOut = smem + StemSmem::OUT;
@@ -268,8 +271,8 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant
 // ------------------------------------------------------------------------------------------------ weight gradient
 __global__ void __launch_bounds__(ST_THREADS, 2)
 stem_wgrad_kernel(const __grid_constant__ CUtensorMap tma_dy, StemArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint8_t* sA = smem + StemSmem::A;
   uint8_t* sDy = smem + StemSmem::X;
   __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(smem + StemSmem::IN);
