@@ -202,6 +202,15 @@ int b200mm_adam_step_g16(float* p, const void* g_bf16, float* m, float* v, void*
                          float beta1, float beta2, float eps, float weight_decay, int step, const float* gradsq,
                          float max_norm, float grad_scale, void* stream);
 
+/* Attention with the dropout keep bits handed from the forward to the backward (one-tile sequences, S <= 128):
+ * drop_mask = [B*H][4][128] uint32 device buffer.  Same op as b200mm_attention_fwd / _bwd
+ * (transformers/models/distilbert/modeling_distilbert.py:126-151 and its autograd backward). */
+int b200mm_attention_fwd_mask(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
+                              float p_drop, unsigned long long seed, void* drop_mask, void* stream);
+int b200mm_attention_bwd_mask(const void* qkv, const float* key_bias, const void* out, const void* dout,
+                              const float* lse, void* dqkv, int B, int H, int S, float p_drop,
+                              unsigned long long seed, const void* drop_mask, void* stream);
+
 /* CUDA-graph support for the whole train step (small-batch regime: the reference's batch 16 / 8 is launch-bound).
  * A captured graph freezes by-value launch parameters, so the three per-step host values move to device memory:
  * the dropout seed salt (added to every dropout seed by the kernels), the Adam step count and the learning rate.

@@ -28,7 +28,28 @@ struct AttnParams {
   const __nv_bfloat16* o_in;   // bwd: O
   const __nv_bfloat16* do_in;  // bwd: dO [B*S, D]
   __nv_bfloat16* dqkv;         // bwd: [B*S, 3D]
+  // one-tile (warp-specialised) kernels: keep bits of the attention dropout, [B*H][4][128] words (word c of row r =
+  // keys 32c .. 32c+31, bit i = key 32c+i kept).  The forward writes them when non-null; the backward reads them
+  // instead of regenerating the Philox stream (which cost more instructions than the softmax gradient itself).
+  uint32_t* drop_mask;
+  // debugging aid (B200MM_ATTN_TRACE=1): CTA 0 records %globaltimer at the pipeline's hand-over points,
+  // [head][event] with 8 events per head; nullptr in normal operation
+  unsigned long long* trace;
 };
+
+__device__ __forceinline__ void trace_event(const AttnParams& p, int head, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[head * 8 + ev] = t;
+  }
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
 // exp2 on the special-function unit (inputs are <= 0 here; ex2.approx maps -inf to +0)
 __device__ __forceinline__ float fast_exp2(float x) {

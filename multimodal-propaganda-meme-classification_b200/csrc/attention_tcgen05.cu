@@ -1328,13 +1328,15 @@ using namespace b200;
 
 // O[B*S, H*64] = softmax(Q K^T / 8 + key_bias) (dropout) V, Q/K/V = column blocks of qkv [B*S, 3*H*64].
 // lse [B,H,S] (fp32) is written when non-null (required for the backward).  S <= 512 (multi-tile kernels above 128).
-B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
-                                    float p_drop, unsigned long long seed, void* stream) {
+static int attention_fwd_impl(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
+                              float p_drop, unsigned long long seed, void* drop_mask, void* stream) {
   const DeviceInfo& dev = device_info();
   if (!dev.ok || dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
   AttnParams p{};
   int rc = fill_params(p, B, H, S, p_drop, seed, key_bias);
   if (rc) return rc;
+  // the keep-bit exchange exists in the one-tile warp-specialised kernels only (forward writes, backward reads)
+  p.drop_mask = (S <= ATT_T && attn_ws_enabled() && p_drop > 0.f) ? static_cast<uint32_t*>(drop_mask) : nullptr;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
   CUtensorMap tq;
@@ -1392,15 +1394,28 @@ B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void
   return B200MM_ERR_BAD_ARG;   // unreachable: every S <= 512 is served above
 }
 
+B200MM_API int b200mm_attention_fwd(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H, int S,
+                                    float p_drop, unsigned long long seed, void* stream) {
+  return attention_fwd_impl(qkv, key_bias, out, lse, B, H, S, p_drop, seed, nullptr, stream);
+}
+// Same, and the keep bits of the attention dropout are written to drop_mask ([B*H][4][128] uint32, S <= 128 only;
+// ignored for longer sequences) for b200mm_attention_bwd_mask.
+B200MM_API int b200mm_attention_fwd_mask(const void* qkv, const float* key_bias, void* out, float* lse, int B, int H,
+                                         int S, float p_drop, unsigned long long seed, void* drop_mask, void* stream) {
+  return attention_fwd_impl(qkv, key_bias, out, lse, B, H, S, p_drop, seed, drop_mask, stream);
+}
+
 // dqkv [B*S, 3*H*64] <- gradients of Q, K, V given dO, using O and the saved LSE.
-B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, const void* out, const void* dout,
-                                    const float* lse, void* dqkv, int B, int H, int S, float p_drop,
-                                    unsigned long long seed, void* stream) {
+static int attention_bwd_impl(const void* qkv, const float* key_bias, const void* out, const void* dout,
+                              const float* lse, void* dqkv, int B, int H, int S, float p_drop,
+                              unsigned long long seed, const void* drop_mask, void* stream) {
   const DeviceInfo& dev = device_info();
   if (!dev.ok || dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
   AttnParams p{};
   int rc = fill_params(p, B, H, S, p_drop, seed, key_bias);
   if (rc) return rc;
+  p.drop_mask = (S <= ATT_T && attn_ws_enabled() && p_drop > 0.f)
+                    ? const_cast<uint32_t*>(static_cast<const uint32_t*>(drop_mask)) : nullptr;
   if (lse == nullptr) return B200MM_ERR_BAD_ARG;
   p.lse = const_cast<float*>(lse);
   p.o_in = static_cast<const __nv_bfloat16*>(out);
@@ -1476,4 +1491,16 @@ B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, cons
   attn_bwd1_kernel<<<grid, 256, ATT_BWD1_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, td, tdq, p);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
+}
+
+B200MM_API int b200mm_attention_bwd(const void* qkv, const float* key_bias, const void* out, const void* dout,
+                                    const float* lse, void* dqkv, int B, int H, int S, float p_drop,
+                                    unsigned long long seed, void* stream) {
+  return attention_bwd_impl(qkv, key_bias, out, dout, lse, dqkv, B, H, S, p_drop, seed, nullptr, stream);
+}
+// Same, reading the dropout keep bits b200mm_attention_fwd_mask saved (S <= 128; nullptr or longer: regenerated).
+B200MM_API int b200mm_attention_bwd_mask(const void* qkv, const float* key_bias, const void* out, const void* dout,
+                                         const float* lse, void* dqkv, int B, int H, int S, float p_drop,
+                                         unsigned long long seed, const void* drop_mask, void* stream) {
+  return attention_bwd_impl(qkv, key_bias, out, dout, lse, dqkv, B, H, S, p_drop, seed, drop_mask, stream);
 }

@@ -117,6 +117,10 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// producer side of a named barrier: counts towards `nthreads` without waiting (pair with named_bar_sync consumers)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // im2col-mode load (NHWC activation, rank 4): `pixels-per-column` consecutive output pixels starting at base pixel
 // (w, h, n) -- traversing W then H then N with the map's traversal strides -- x `channels-per-pixel` channels from c,
 // displaced by the filter offset (off_w, off_h); pixels falling outside the image are zero-filled.

@@ -254,15 +254,27 @@ def mask_to_bias(mask):
     return bias
 
 
-def attention_fwd(qkv, key_bias, B, H, S, *, p_drop=0.0, seed=0, need_lse=True):
+def attention_fwd(qkv, key_bias, B, H, S, *, p_drop=0.0, seed=0, need_lse=True, save_mask=False):
+    """save_mask (training, S <= 128, p_drop > 0): also returns the dropout keep bits ([B*H, 4, 128] int32) for
+    ``attention_bwd(..., drop_mask=)`` -- the backward then reads 2 KB per head instead of regenerating the Philox
+    stream.  Returns (out, lse) or (out, lse, mask)."""
     out = torch.empty(B * S, H * 64, device=qkv.device, dtype=bf16)
     lse = torch.empty(B, H, S, device=qkv.device, dtype=f32) if need_lse else None
+    if save_mask:
+        mask = torch.empty(B * H, 4, 128, device=qkv.device, dtype=torch.int32) if (S <= 128 and p_drop > 0) else None
+        _lib.call("b200mm_attention_fwd_mask", _p(qkv), _p(key_bias), _p(out), _p(lse), B, H, S, float(p_drop),
+                  int(seed), _p(mask), _s())
+        return out, lse, mask
     _lib.call("b200mm_attention_fwd", _p(qkv), _p(key_bias), _p(out), _p(lse), B, H, S, float(p_drop), int(seed), _s())
     return out, lse
 
 
-def attention_bwd(qkv, key_bias, out, dout, lse, B, H, S, *, p_drop=0.0, seed=0):
+def attention_bwd(qkv, key_bias, out, dout, lse, B, H, S, *, p_drop=0.0, seed=0, drop_mask=None):
     dqkv = torch.empty_like(qkv)
+    if drop_mask is not None:
+        _lib.call("b200mm_attention_bwd_mask", _p(qkv), _p(key_bias), _p(out), _p(dout), _p(lse), _p(dqkv), B, H, S,
+                  float(p_drop), int(seed), _p(drop_mask), _s())
+        return dqkv
     _lib.call("b200mm_attention_bwd", _p(qkv), _p(key_bias), _p(out), _p(dout), _p(lse), _p(dqkv), B, H, S,
               float(p_drop), int(seed), _s())
     return dqkv

@@ -208,7 +208,10 @@ class TextTower:
         for li, L in enumerate(self.layers):
             s_att, s_ffn, s_out = _mix(seed, step, li, 1), _mix(seed, step, li, 2), _mix(seed, step, li, 3)
             qkv = ops.linear_fwd(x, L["wqkv"], L["bqkv"])
-            ctx, lse = ops.attention_fwd(qkv, key_bias, B, H, S, p_drop=pa, seed=s_att, need_lse=training)
+            if training:   # the forward hands its dropout keep bits to the backward (one-tile sequences)
+                ctx, lse, amask = ops.attention_fwd(qkv, key_bias, B, H, S, p_drop=pa, seed=s_att, save_mask=True)
+            else:
+                (ctx, lse), amask = ops.attention_fwd(qkv, key_bias, B, H, S, p_drop=pa, seed=s_att, need_lse=False), None
             y_pre = ops.linear_fwd(ctx, L["wo"], L["bo"], residual=x, p_drop=p_out, seed=s_out)
             y, m1, r1 = ops.layernorm_fwd(y_pre, L["g1"], L["be1"], c.layer_norm_eps)
             z, a = ops.linear_gelu_fwd(y, L["w1"], L["b1"])
@@ -216,7 +219,7 @@ class TextTower:
             out, m2, r2 = ops.layernorm_fwd(o_pre, L["g2"], L["be2"], c.layer_norm_eps)
             if training:
                 saved["layers"].append((x, qkv, ctx, lse, y_pre, m1, r1, y, z, a, o_pre, m2, r2, pa, s_att, pd, s_ffn,
-                                        p_out, s_out))
+                                        p_out, s_out, amask))
             x = out
             if self.capture is not None:
                 self.capture.append(x)
@@ -256,7 +259,7 @@ class TextTower:
         d_out = dh
         for li in reversed(range(len(self.layers))):
             L = self.layers[li]
-            x, qkv, ctx, lse, y_pre, m1, r1, y, z, a, o_pre, m2, r2, pa, s_att, pd, s_ffn, p_out, s_out = \
+            x, qkv, ctx, lse, y_pre, m1, r1, y, z, a, o_pre, m2, r2, pa, s_att, pd, s_ffn, p_out, s_out, amask = \
                 sv["layers"][li]
             # out = LN2(o_pre);  o_pre = dropout(a W2^T + b2) + y
             d_opre, d_opre_m = ops.layernorm_bwd(d_out, o_pre, m2, r2, L["g2"], L["dg2"], L["dbe2"],
@@ -275,7 +278,7 @@ class TextTower:
             ops.linear_wgrad(d_o, ctx, L["dwo"])
             ops.colsum(d_o, L["dbo"])
             dctx = ops.linear_dgrad(d_o, L["wo"])
-            dqkv = ops.attention_bwd(qkv, kb, ctx, dctx, lse, B, H, S, p_drop=pa, seed=s_att)
+            dqkv = ops.attention_bwd(qkv, kb, ctx, dctx, lse, B, H, S, p_drop=pa, seed=s_att, drop_mask=amask)
             ops.linear_wgrad(dqkv, x, L["dwqkv"])
             ops.colsum(dqkv, L["dbqkv"])
             d_out = ops.linear_dgrad(dqkv, L["wqkv"], residual=d_ypre)     # + residual path of LN1's input

@@ -20,7 +20,7 @@ for B, H, S in shapes:
     for ws in ("1", "0"):
         os.environ["B200MM_ATTN_WS"] = ws
         for p in (0.0, 0.1):
-            out, lse = ops.attention_fwd(qkv, kb, B, H, S, p_drop=p, seed=7)
+            out, lse, dmask = ops.attention_fwd(qkv, kb, B, H, S, p_drop=p, seed=7, save_mask=True)   # as the towers call it
             dout = torch.randn_like(out)
             def timed(fn, n=10):
                 for _ in range(3):
@@ -32,8 +32,8 @@ for B, H, S in shapes:
                     fn()
                 e1.record(); torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / n * 1e3
-            tf = timed(lambda: ops.attention_fwd(qkv, kb, B, H, S, p_drop=p, seed=7))
-            tb = timed(lambda: ops.attention_bwd(qkv, kb, out, dout, lse, B, H, S, p_drop=p, seed=7))
+            tf = timed(lambda: ops.attention_fwd(qkv, kb, B, H, S, p_drop=p, seed=7, save_mask=True))
+            tb = timed(lambda: ops.attention_bwd(qkv, kb, out, dout, lse, B, H, S, p_drop=p, seed=7, drop_mask=dmask))
             heads = B * H
             fb = heads * (4 * S * 128 + 4 * S)
             bb = heads * (8 * S * 128 + 4 * S)

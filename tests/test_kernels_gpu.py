@@ -159,6 +159,31 @@ def test_attention_dropout_is_consistent(ops, cuda_device):
     assert abs(fd - an) / (abs(an) + 1e-6) < 0.1
 
 
+@pytest.mark.parametrize("B,H,S", [(40, 12, 128), (5, 2, 77), (300, 2, 128)])
+def test_attention_saved_dropout_mask_equals_regenerated(ops, cuda_device, B, H, S):
+    """The forward's saved keep bits ([B*H, 4, 128] words) are exactly the Philox decisions the backward would
+    regenerate: the gradient computed from the saved mask is bit-identical to the regenerated one, the bits'
+    density is 1 - p, and padded rows / keys carry no influence."""
+    torch.manual_seed(12)
+    D = H * 64
+    qkv = (torch.randn(B * S, 3 * D, device=cuda_device) * 0.7).to(bf16)
+    lengths = torch.randint(3, S + 1, (B,), device=cuda_device)
+    lengths[0] = S
+    bias = ops.mask_to_bias((torch.arange(S, device=cuda_device)[None] < lengths[:, None]).long())
+    dout = torch.randn(B * S, D, device=cuda_device).to(bf16)
+    out, lse, mask = ops.attention_fwd(qkv, bias, B, H, S, p_drop=0.1, seed=77, save_mask=True)
+    out_plain, lse_plain = ops.attention_fwd(qkv, bias, B, H, S, p_drop=0.1, seed=77)
+    assert mask is not None and mask.shape == (B * H, 4, 128)
+    assert torch.equal(out, out_plain) and torch.equal(lse, lse_plain)
+    g_saved = ops.attention_bwd(qkv, bias, out, dout, lse, B, H, S, p_drop=0.1, seed=77, drop_mask=mask)
+    g_regen = ops.attention_bwd(qkv, bias, out, dout, lse, B, H, S, p_drop=0.1, seed=77)
+    assert torch.equal(g_saved, g_regen)
+    bits = torch.stack([(mask >> i) & 1 for i in range(32)], -1).float()        # [BH, 4, 128 rows, 32]
+    assert abs(bits.mean().item() - 0.9) < 5e-3
+    # no mask is produced (or needed) without dropout or beyond one tile
+    assert ops.attention_fwd(qkv, bias, B, H, S, p_drop=0.0, save_mask=True)[2] is None
+
+
 @pytest.mark.parametrize("B,H,S,p", [(3, 4, 128, 0.0), (40, 12, 128, 0.1), (5, 2, 77, 0.1), (700, 2, 128, 0.1)])
 def test_attention_warp_specialised_matches_single_role(ops, cuda_device, B, H, S, p):
     """attention_ws.cu (TMA warp / MMA warp / softmax warpgroups, several heads in flight) against the single-role
