@@ -211,6 +211,12 @@ int b200mm_attention_bwd_mask(const void* qkv, const float* key_bias, const void
                               const float* lse, void* dqkv, int B, int H, int S, float p_drop,
                               unsigned long long seed, const void* drop_mask, void* stream);
 
+/* Feature-extraction path (baselines/extract_feat.py:52-67): ConvNeXt's depthwise 7x7 convolution
+ * (torchvision/models/convnext.py CNBlock; NHWC bf16, wt = [49][C] tap-major) and BertPooler's tanh. */
+int b200mm_dwconv7x7_nhwc(const void* x, const void* wt, const float* bias, void* y, int N, int H, int W, int C,
+                          void* stream);
+int b200mm_tanh_f32(float* x, long long n, void* stream);
+
 /* CUDA-graph support for the whole train step (small-batch regime: the reference's batch 16 / 8 is launch-bound).
  * A captured graph freezes by-value launch parameters, so the three per-step host values move to device memory:
  * the dropout seed salt (added to every dropout seed by the kernels), the Adam step count and the learning rate.

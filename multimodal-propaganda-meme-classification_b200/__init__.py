@@ -8,6 +8,7 @@ reference repository and is not a valid Python identifier).  Public surface = th
     CrossEntropyLoss, FusedAdam                   ...txt:248-249
     ensemble.*                                    example_scripts/combine_preds.py
     setup(k) / run_folds / combine_folds          example_scripts/Multimodal_example_task2C.py:50-192, 882-885
+    ConvNeXtTiny, BertPoolerModel, extract_features   baselines/extract_feat.py:52-67, 103-112
 """
 __version__ = "0.1.0"
 
@@ -30,6 +31,10 @@ _LAZY = {
     "stratified_kfold": ("loop_head", "stratified_kfold"),
     "get_params": ("loop_head", "get_params"),
     "GraphedTrainStep": ("graph", "GraphedTrainStep"),
+    "ConvNeXtTiny": ("features", "ConvNeXtTiny"),
+    "BertPoolerModel": ("features", "BertPoolerModel"),
+    "extract_features": ("features", "get_features"),
+    "write_features_json": ("features", "write_features_json"),
     "setup": ("folds", "setup"),
     "run_folds": ("folds", "run_folds"),
     "combine_folds": ("folds", "combine_folds"),

@@ -138,6 +138,8 @@ declare("b200mm_scale_cast_f32_to_bf16", [c_ptr, c_ptr, c_longlong, c_float, c_p
 declare("b200mm_sumsq_bf16", [c_ptr, c_longlong, c_ptr, c_ptr])
 declare("b200mm_adam_step_g16", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_longlong, c_float, c_float, c_float, c_float,
                                  c_float, c_int, c_ptr, c_float, c_float, c_ptr])
+declare("b200mm_dwconv7x7_nhwc", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr])
+declare("b200mm_tanh_f32", [c_ptr, c_longlong, c_ptr])
 declare("b200mm_set_step_salt_ptr", [c_ptr])
 declare("b200mm_adam_step_dyn", [c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_longlong, c_ptr, c_float, c_float, c_float,
                                  c_float, c_ptr, c_ptr, c_float, c_float, c_ptr])

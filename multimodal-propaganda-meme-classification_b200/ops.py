@@ -458,6 +458,20 @@ def adam_step(p, g, m, v, shadow, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weigh
               float(grad_scale), _s())
 
 
+def dwconv7x7(x, wt, bias, N, H, W, C):
+    """Depthwise 7x7 / pad 3 convolution on an NHWC bf16 activation [N*H*W, C]; wt bf16 [49, C], bias fp32 [C]."""
+    _chk(x, bf16, "x"); _chk(wt, bf16, "weight")
+    y = torch.empty_like(x)
+    _lib.call("b200mm_dwconv7x7_nhwc", _p(x), _p(wt), _p(bias), _p(y), N, H, W, C, _s())
+    return y
+
+
+def tanh_(x):
+    _chk(x, f32, "x")
+    _lib.call("b200mm_tanh_f32", _p(x), x.numel(), _s())
+    return x
+
+
 def adam_step_dyn(p, g, m, v, shadow, *, lr_dev, step_dev, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0,
                   gradsq=None, max_norm=0.0, grad_scale=1.0):
     """adam_step with the learning rate (fp32 device scalar) and step count (int32 device scalar) read on the device:

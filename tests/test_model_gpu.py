@@ -765,3 +765,98 @@ def test_feature_extraction_and_odd_shapes(cuda_device):
         r = oracle.resnet(data["image"])
     assert rel(torch.tensor([txt_f[f"img_{i}"] for i in range(3)]), h) < 2e-2
     assert rel(torch.tensor([img_f[f"img_{i}"] for i in range(3)]), r) < 3e-2
+
+
+# ------------------------------------------------------------------ feature extraction (baselines/extract_feat.py)
+def test_dwconv7x7_matches_torch(cuda_device):
+    from b200mm import ops
+    torch.manual_seed(21)
+    for N, H, W, C in ((2, 14, 14, 96), (1, 7, 9, 192), (3, 56, 56, 96), (2, 5, 3, 768)):
+        x = torch.randn(N, C, H, W, device=cuda_device).to(torch.bfloat16)
+        w = (torch.randn(C, 1, 7, 7, device=cuda_device) * 0.2).to(torch.bfloat16)
+        b = torch.randn(C, device=cuda_device)
+        ref = torch.nn.functional.conv2d(x.float(), w.float(), b, padding=3, groups=C)
+        xn = x.permute(0, 2, 3, 1).reshape(N * H * W, C).contiguous()
+        wt = w.reshape(C, 49).t().contiguous()
+        y = ops.dwconv7x7(xn, wt, b, N, H, W, C).view(N, H, W, C).permute(0, 3, 1, 2)
+        assert rel(y, ref) < 6e-3, (N, H, W, C)
+        assert (y.float() - ref).abs().max().item() < 3e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("size,batch", [(64, 3), (224, 2)])
+def test_convnext_tiny_features_match_torchvision(cuda_device, size, batch):
+    """img_model.avgpool(img_model.features(images)) of baselines/extract_feat.py:59 on the engine vs torchvision's
+    convnext_tiny (random init; layer scales raised from 1e-6 so that every block contributes)."""
+    import b200mm
+    from torchvision.models import convnext_tiny
+    torch.manual_seed(22)
+    ref = convnext_tiny(weights=None).to(cuda_device).eval()
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if n.endswith("layer_scale"):
+                p.fill_(0.5)
+            elif n.endswith(".bias"):
+                p.normal_(0.0, 0.05)
+    eng = b200mm.ConvNeXtTiny(device=cuda_device)
+    eng.load_state_dict(ref.state_dict())
+    x = torch.randn(batch, 3, size, size, device=cuda_device)
+    with torch.no_grad():
+        want = ref.avgpool(ref.features(x)).flatten(1)
+        feats = ref.features(x)
+    got_map, N, h, w = eng.features(x)
+    assert (N, h, w) == (batch, size // 32, size // 32)
+    assert rel(got_map.view(batch, h, w, 768).permute(0, 3, 1, 2), feats) < 2e-2
+    got = eng.avgpool((got_map, N, h, w))
+    assert got.shape == (batch, 768) and rel(got, want) < 2e-2
+
+
+def test_bert_pooler_output_matches_transformers(cuda_device):
+    """text_model(text_tokens).pooler_output (extract_feat.py:60) vs transformers' BertModel, small random config."""
+    import b200mm
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(23)
+    hc = BertConfig(vocab_size=300, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                    max_position_embeddings=64, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    ref = BertModel(hc).to(cuda_device).eval()
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if n.endswith(".bias"):
+                p.normal_(0.0, 0.05)
+    cfg = b200mm.TextConfig(vocab_size=300, max_position_embeddings=64, dim=128, n_layers=2, n_heads=2, hidden_dim=256,
+                            arch="bert", type_vocab_size=2, pad_token_id=0)
+    eng = b200mm.BertPoolerModel(cfg, device=cuda_device)
+    eng.load_state_dict(ref.state_dict())
+    ids = torch.randint(1, 300, (5, 32), device=cuda_device)
+    with torch.no_grad():
+        want = ref(ids)
+    got = eng(ids)
+    assert got.pooler_output.dtype == torch.float32 and got.pooler_output.shape == (5, 128)
+    assert rel(got.last_hidden_state, want.last_hidden_state) < 2e-2
+    assert rel(got.pooler_output, want.pooler_output) < 2e-2
+
+
+def test_extract_features_json_contract(cuda_device, tmp_path):
+    """get_features(loader, img_model, text_model) + the JSON the SVM baseline reads (extract_feat.py:52-67, 107-111;
+    subtask_2c.py:74-84): ids -> 768 image floats + D text floats, concatenated by the consumer."""
+    import json
+    import b200mm
+    from b200mm import features as F
+    cfg = b200mm.TextConfig(vocab_size=300, max_position_embeddings=64, dim=128, n_layers=1, n_heads=2, hidden_dim=256,
+                            arch="bert")
+    img_model, text_model = b200mm.ConvNeXtTiny(device=cuda_device), b200mm.BertPoolerModel(cfg, device=cuda_device)
+    g = torch.Generator().manual_seed(3)
+    items = [(f"data/x/img_{i}.jpg", torch.randn(3, 64, 64, generator=g), torch.randint(1, 300, (16,), generator=g))
+             for i in range(7)]
+    loader = torch.utils.data.DataLoader(items, batch_size=3, shuffle=True)
+    img_feats, text_feats = b200mm.extract_features(loader, img_model, text_model)
+    assert set(img_feats) == set(text_feats) == {it[0] for it in items}
+    assert all(len(v) == 768 for v in img_feats.values()) and all(len(v) == 128 for v in text_feats.values())
+    path = F.write_features_json(str(tmp_path / "features" / "train_feats.json"), img_feats, text_feats)
+    blob = json.load(open(path))
+    assert set(blob) == {"imgfeats", "textfeats"}
+    ids = [it[0] for it in items]
+    X = F.load_concat_features(path, ids)
+    assert X.shape == (7, 768 + 128) and np.isfinite(X).all()
+    # batch composition does not change a sample's features (eval-mode, no cross-sample statistics)
+    one = b200mm.extract_features([([items[2][0]], items[2][1][None], items[2][2][None])], img_model, text_model)
+    assert np.allclose(one[0][items[2][0]], img_feats[items[2][0]], rtol=0, atol=2e-2)
