@@ -343,9 +343,9 @@ def run_engine(args):
 
     # one process: the loop body (zero_grad / forward / loss / backward / Adam) is captured once as a CUDA graph and
     # replayed -- the same ~500 kernels, enqueued by one cudaGraphLaunch instead of 500 host calls (at batch 256 the
-    # host needs 30 of the step's 31 ms to enqueue them one by one: profiles/small_batch_r02.json).  Data parallel
-    # runs stay eager: the gradient exchange lives on NCCL's stream.
-    gstep = b200mm.GraphedTrainStep(model, opt, crit) if (world == 1 and not args.no_graph) else None
+    # host needs 30 of the step's 31 ms to enqueue them one by one: profiles/small_batch_r02.json).  Data parallel:
+    # the NCCL all-reduces of the gradient phases are captured with the step (forked / joined by events).
+    gstep = b200mm.GraphedTrainStep(model, opt, crit) if not args.no_graph else None
 
     def step_resident():
         if gstep is None:
@@ -448,7 +448,9 @@ def run_engine(args):
         w = torch.tensor([gs.exposed_wait_ms()], device=dev)
         dist.all_reduce(w, op=dist.ReduceOp.MAX)
         sync_info = {"payload": gs.payload, "bytes_per_step_per_rank": gs.bytes_per_step,
-                     "phases": {k: len(v) for k, v in gs.phases.items()}, "exposed_wait_ms_last_step": w.item()}
+                     "phases": {k: len(v) for k, v in gs.phases.items()}, "exposed_wait_ms_last_step": w.item() if gstep is None else None,
+                     "note": None if gstep is None else "captured in the step graph: no timing events inside a capture "
+                                                        "(run with --no-graph for the exposed-wait measurement)"}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events on the launching stream
     pk = peaks()
@@ -457,13 +459,13 @@ def run_engine(args):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     t, h = det["tensor"], det["hbm"]
     # DRAM traffic of the same kernel from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum, average
-    # per launch over every GEMM launch of a step, cold caches under ncu): profiles/ncu_traffic_r01.json
+    # per launch over every GEMM launch of a step, cold caches under ncu): profiles/ncu_traffic_r02.json
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
     if args.config == 2 and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)["gemm"]["dram_bytes_per_launch"]
-        traffic_src = "profiles/ncu_traffic_r01.json (ncu, cold cache, mean over the GEMM launches of one step)"
+        traffic_src = "profiles/ncu_traffic_r02.json (ncu, cold cache, mean over the GEMM launches of one step)"
     algo_bytes_per_launch = (t["bytes"] + h["bytes"]) / max(n_gemm, 1)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05+TMA; linear layers and implicit-GEMM convolutions)",
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -494,7 +496,7 @@ def run_engine(args):
         e2e = {"value": world * B / (ms_e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d_e * world,
                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e,
                "path": "b200mm.train(model, DataLoader(pin_memory=True, num_workers=%d), CrossEntropyLoss, FusedAdam, "
-                       "device, graph=GraphedTrainStep when N = 1): uint8 HWC pixels + token ids from pinned memory, ToTensor/Normalize on the GPU copy "
+                       "device, graph=GraphedTrainStep): uint8 HWC pixels + token ids from pinned memory, ToTensor/Normalize on the GPU copy "
                        "stream" % workers,
                "readback": "loss + correct count of every step, asynchronous to pinned memory, consumed one step later",
                "last_loss": e2e_log[-1]}
@@ -515,7 +517,7 @@ def run_engine(args):
             "config": {"workload": wl["name"], "per_gpu_batch": B, "global_batch": B * world, "seq_len": S, "image": "3x224x224",
                        "parallelism": f"dp{world}", "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)",
                        "dropout": "on (0.1 / 0.1 / 0.3, Philox)",
-                       "launch": "eager" if gstep is None else "cuda_graph (one replay per step)"},
+                       "launch": "eager" if gstep is None else "cuda_graph (one replay per step, NCCL all-reduces included)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "grad_sync": sync_info,
         }), flush=True)

@@ -17,7 +17,8 @@ What a capture freezes, and where the per-step values live instead:
   * the batch  -> copied into static input buffers on the replay stream.
 
 Shapes are static: one graph per (batch, sequence length); a different shape (the last, short batch of an epoch)
-falls back to the eager step.  Single process only -- the data-parallel exchange runs on NCCL's own stream.
+falls back to the eager step.  Under data parallelism (nccl) the gradient all-reduces are captured with the step: they
+are launches on NCCL's stream, forked from and joined to the capturing stream by events.
 """
 from __future__ import annotations
 
@@ -35,8 +36,15 @@ class GraphedTrainStep:
     def __init__(self, model, optimizer, criterion=None, warmup: int = 2):
         if not isinstance(optimizer, FusedAdam):
             raise TypeError("GraphedTrainStep needs b200mm.FusedAdam (its step is the capturable one)")
-        if getattr(model, "grad_sync", None) is not None and model.grad_sync.world > 1:
-            raise RuntimeError("GraphedTrainStep is single-process (the data-parallel exchange is not captured)")
+        sync = getattr(model, "grad_sync", None)
+        if sync is not None and sync.world > 1:
+            # data parallel: the phase all-reduces are NCCL launches on NCCL's stream, forked from / joined to the
+            # capturing stream by events -- all of it becomes part of the graph.  Needs the nccl backend (gloo has no
+            # stream semantics) and no timing events inside the captured region.
+            import torch.distributed as dist
+            if dist.get_backend(sync.group) != "nccl":
+                raise RuntimeError("GraphedTrainStep under data parallelism needs the nccl backend")
+            sync._ev = None
         self.model, self.optimizer, self.warmup = model, optimizer, warmup
         self.loss_kw = {}
         if criterion is not None:
