@@ -300,7 +300,27 @@ def run_ensemble(args, dev, world, rank):
             "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _shutdown(dist)
+
+
+def _shutdown(dist, gstep=None):
+    """Tear the process group down.  A captured graph that holds NCCL launches must die before its communicator
+    (destroying the group first hung the ranks); a watchdog ends the process if the teardown still blocks -- the
+    result line is already out."""
+    import gc
+    import torch
+    sys.stdout.flush()
+    killer = threading.Timer(20.0, lambda: os._exit(0))
+    killer.daemon = True
+    killer.start()
+    if gstep is not None:
+        gstep.close()
+        gstep.static_out = gstep.static_in = None
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    killer.cancel()
 
 
 # ------------------------------------------------------------------------------------------------- engine arm
@@ -522,7 +542,7 @@ def run_engine(args):
             "grad_sync": sync_info,
         }), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _shutdown(dist, gstep)
 
 
 if __name__ == "__main__":
