@@ -417,7 +417,7 @@ def run_engine(args):
         # two loader processes keep up with a 31 ms step; more of them take cores from the thread that launches the
         # step's ~500 kernels (measured on a 16-core box: 0 / 2 / 4 / 8 workers -> 33.1 / 32.2 / 36.7 / 36.4 ms per
         # step against 31.2 resident, gpurun_out/e2e_probe.log -> profiles/e2e_probe_r02.log)
-        workers = max(1, min(2, (os.cpu_count() or 2) // (4 * world))) if shm_free > (4 << 30) else 0
+        workers = (2 if (os.cpu_count() or 2) >= 4 * world else 1) if shm_free > (4 << 30) else 0
         workers = int(os.environ.get("B200MM_E2E_WORKERS", workers))
         kw = dict(prefetch_factor=2, persistent_workers=False) if workers else {}
         dl = DataLoader(SyntheticMemes((e2e_warm + args.steps) * B), batch_size=B, shuffle=False, drop_last=True,
