@@ -409,7 +409,7 @@ def run_engine(args):
         def __iter__(self):
             return itertools.islice(self.it, self.k)
 
-    e2e_warm = int(os.environ.get("B200MM_E2E_WARM", "4"))
+    e2e_warm = int(os.environ.get("B200MM_E2E_WARM", "8"))
     e2e_log = []
 
     def make_e2e_loader():

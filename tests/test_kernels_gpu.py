@@ -98,6 +98,35 @@ def test_gemm_dropout_epilogue(ops, cuda_device):
         ((dxm.float() != 0) == (kept & (dx.float() != 0))).all()
 
 
+def test_gelu_epilogue_tails(ops, cuda_device):
+    """The epilogue's GELU is erf evaluated as tanh(x(A + Bx^2)) with tanh.approx (a deliberate departure from erff,
+    |dPhi| < 4e-4): checked where the approximation is weakest relative to the value -- the tails |x| > 4 -- and across
+    the whole range, forward and derivative, through an identity weight so that z is exactly the input."""
+    torch.manual_seed(14)
+    M = N = K = 256
+    x = torch.cat([torch.linspace(-9, 9, M * K // 2), (torch.rand(M * K // 2) * 2 - 1) * 9]).view(M, K)
+    x = x.to(cuda_device).to(bf16)
+    eye = torch.eye(N, K, device=cuda_device).to(bf16)
+    zero = torch.zeros(N, device=cuda_device)
+    z, a = ops.linear_gelu_fwd(x, eye, zero)
+    xf = x.float()
+    assert torch.equal(z.float(), xf)
+    ref = F.gelu(xf)
+    err = (a.float() - ref).abs()
+    assert (err <= 4e-4 * xf.abs() + 2.0 ** -8 * ref.abs() + 1e-6).all(), err.max().item()
+    tail = xf.abs() > 4
+    assert (a.float()[tail & (xf < 0)].abs() < 2e-3).all()                 # gelu(x < -4) -> 0 (|exact| < 1.3e-4)
+    assert rel(a.float()[tail & (xf > 0)], ref[tail & (xf > 0)]) < 3e-3      # gelu(x > 4) -> x
+    # derivative: dz = (dy W) * gelu'(z) with dy = ones through the identity -> gelu'(z)
+    ones = torch.ones(M, N, device=cuda_device).to(bf16)
+    dz = ops.linear_dgrad(ones, eye, gelu_z=z)
+    xr = xf.clone().requires_grad_(True)
+    F.gelu(xr).sum().backward()
+    derr = (dz.float() - xr.grad).abs()
+    assert (derr <= 3e-3 + 2.0 ** -8 * xr.grad.abs()).all(), derr.max().item()
+    assert (dz.float()[tail & (xf < 0)].abs() < 3e-3).all() and rel(dz.float()[tail & (xf > 0)], xr.grad[tail & (xf > 0)]) < 5e-3
+
+
 # ------------------------------------------------------------------------------------------------- attention
 def _attn_ref(qkv, key_bias, B, H, S):
     D = H * 64
