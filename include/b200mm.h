@@ -47,6 +47,10 @@ int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int 
  * col_stats[N+n] += sum_m out[m,n]^2 over the STORED bf16 values -- the train-mode BatchNorm statistics of a
  * convolution output come out of the convolution's own epilogue (feeds b200mm_batchnorm_fwd_stats). */
 
+/* Micro-benchmark hook (A/B timing of dispatch decisions; the defaults are the measured optimum): knob 0 = smallest
+ * reduction depth in 64-wide k blocks the CTA-pair kernel takes (8), knob 1 = B-resident mode for short unsplit K (1). */
+int b200mm_gemm_tune(int knob, int value);
+
 /* Implicit-GEMM convolution on the same kernel: the activation operand is gathered from NHWC memory by im2col-mode
  * TMA loads (no im2col matrix exists).  x: bf16 [N,H,W,C], C % 64 == 0; w: bf16 OHWI-flattened [Cout, k*k*C].
  * conv_fwd also serves the stride-1 data gradient (call it on dY with the weight from conv_weight_rotate).

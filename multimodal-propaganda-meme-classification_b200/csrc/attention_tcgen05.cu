@@ -552,7 +552,7 @@ attn_fwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
       tma_store_commit();
     }
   }
-  if (tid == 0) tma_store_wait<0>();
+  if (tid == 0) tma_store_wait_read<0>();
 
   tc_fence_before_sync();
   __syncthreads();
@@ -795,7 +795,7 @@ attn_bwd_tmem_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_c
       }
     }
   }
-  if (tid == 0) tma_store_wait<0>();
+  if (tid == 0) tma_store_wait_read<0>();
 
   tc_fence_before_sync();
   __syncthreads();
@@ -1049,7 +1049,7 @@ attn_bwd_tmem3_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_
       tma_store_commit();
     }
   }
-  if (tid == 0) tma_store_wait<0>();
+  if (tid == 0) tma_store_wait_read<0>();
 
   tc_fence_before_sync();
   __syncthreads();
@@ -1291,7 +1291,7 @@ attn_bwd1_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_const
       }
     }
   }
-  if (tid == 0) tma_store_wait<0>();   // shared memory must outlive the last bulk store
+  if (tid == 0) tma_store_wait_read<0>();   // shared memory must outlive the last bulk store
 
   tc_fence_before_sync();
   __syncthreads();

@@ -75,6 +75,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_staged + WSF_SLOTS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();   // see launch_pdl (common.cuh): the set-up below overlaps the previous kernel's tail
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
     tma_prefetch_desc(&tma_out);
@@ -92,6 +93,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // first global-memory access comes after this point
 
   const int items = p.B * p.H;
   const int n_local = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -129,7 +131,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
           }
         }
       }
-      tma_store_wait<0>();
+      tma_store_wait_read<0>();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA warp
@@ -317,6 +319,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_xfree + WSB_SLOTS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();   // see launch_pdl (common.cuh): the set-up below overlaps the previous kernel's tail
   if (tid == 0) {
     tma_prefetch_desc(&tma_qkv);
     tma_prefetch_desc(&tma_do);
@@ -336,6 +339,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();   // first global-memory access comes after this point
 
   const int items = p.B * p.H;
   const int n_local = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -377,7 +381,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tma_qkv, const __grid_con
         trace_event(p, nst, 7);
         mbar_arrive(&bar_xfree[s]);
       }
-      tma_store_wait<0>();
+      tma_store_wait_read<0>();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA warp
@@ -626,7 +630,8 @@ int launch_attn_fwd_ws(const CUtensorMap& tma_qkv, const CUtensorMap& tma_out, c
   }
   const int items = p.B * p.H;
   const int grid = items < num_sms ? items : num_sms;
-  attn_fwd_ws_kernel<<<grid, WSF_THREADS, WSF_SMEM, stream>>>(tma_qkv, tma_out, p);
+  cudaError_t le = launch_pdl(attn_fwd_ws_kernel, dim3(grid), dim3(WSF_THREADS), WSF_SMEM, stream, tma_qkv, tma_out, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -671,7 +676,9 @@ int launch_attn_bwd_ws(const CUtensorMap& tma_qkv, const CUtensorMap& tma_do, co
   const int grid = items < num_sms ? items : num_sms;
   const char* tr = std::getenv("B200MM_ATTN_TRACE");
   if (tr && tr[0] == '1') return trace_bwd_launch(tma_qkv, tma_do, tma_dqkv, p, grid, stream);
-  attn_bwd_ws_kernel<<<grid, WSB_THREADS, WSB_SMEM, stream>>>(tma_qkv, tma_do, tma_dqkv, p);
+  cudaError_t le = launch_pdl(attn_bwd_ws_kernel, dim3(grid), dim3(WSB_THREADS), WSB_SMEM, stream, tma_qkv, tma_do,
+                              tma_dqkv, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

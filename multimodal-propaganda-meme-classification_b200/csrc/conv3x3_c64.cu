@@ -197,7 +197,7 @@ conv3x3_c64_fwd_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_c
         }
       }
     }
-    if (et == 0) tma_store_wait<0>();
+    if (et == 0) tma_store_wait_read<0>();
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -107,6 +107,8 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
                 __nv_bfloat16* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                 float* __restrict__ running_mean, float* __restrict__ running_var,
                 unsigned char* __restrict__ relu_mask) {
+  pdl_launch_dependents();   // see launch_pdl (common.cuh)
+  pdl_wait();
   const int G = C >> 3;
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
   float sc[8], sh[8];
@@ -224,6 +226,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
                      const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
                      const float* __restrict__ mean, const float* __restrict__ rstd, int relu,
                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scratch) {
+  pdl_launch_dependents();   // see launch_pdl (common.cuh)
+  pdl_wait();
   __shared__ float red[2][256][8];
   const int G = C >> 3;
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
@@ -298,6 +302,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
                     const float* __restrict__ dbeta_sum,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dgamma,
                     float* __restrict__ dbeta) {
+  pdl_launch_dependents();   // see launch_pdl (common.cuh)
+  pdl_wait();
   const int G = C >> 3;
   const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
   float mu[8], rs[8], k0[8], k1[8], k2[8], sh[8];
@@ -776,15 +782,20 @@ B200MM_API int b200mm_batchnorm_fwd_stats(const void* x, const void* residual, l
   int grid;
   static const int occ_res = bn_occupancy(bn_apply_kernel<true>), occ_plain = bn_occupancy(bn_apply_kernel<false>);
   const int rows = bn_rows_per_cta(M, C, &grid, residual != nullptr ? occ_res : occ_plain);
+  // launched as a programmatic dependent of the producing convolution: its CTAs are resident (waiting in
+  // griddepcontrol.wait) when the convolution's last tile retires
+  cudaError_t e;
   if (residual != nullptr)
-    bn_apply_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows, col_stats,
-        col_stats + C, gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out, rstd_out,
-        running_mean, running_var, relu_mask);
+    e = launch_pdl(bn_apply_kernel<true>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                   static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), M, C, rows,
+                   col_stats, col_stats + C, gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out),
+                   mean_out, rstd_out, running_mean, running_var, relu_mask);
   else
-    bn_apply_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), nullptr, M, C, rows, col_stats, col_stats + C, gamma, beta, eps,
-        momentum, relu, static_cast<__nv_bfloat16*>(out), mean_out, rstd_out, running_mean, running_var, relu_mask);
+    e = launch_pdl(bn_apply_kernel<false>, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                   static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(nullptr), M, C, rows,
+                   col_stats, col_stats + C, gamma, beta, eps, momentum, relu, static_cast<__nv_bfloat16*>(out),
+                   mean_out, rstd_out, running_mean, running_var, relu_mask);
+  if (e != cudaSuccess) return static_cast<int>(e);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }
@@ -838,8 +849,9 @@ B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const voi
     bn_bwd_reduce_kernel<SRC><<<rgrid, 256, 0, s>>>(dout_, out_, relu_mask, x_, M, C, rrows, mean, rstd, relu, gamma, \
                                                     beta, scratch);                                                 \
     B200MM_CHECK_LAUNCH();                                                                                          \
-    bn_bwd_apply_kernel<SRC><<<grid, 256, 0, s>>>(dout_, out_, relu_mask, x_, M, C, rows, mean, rstd, gamma, beta,   \
-                                                  relu, fin, fin + C, dx_, dz_, dgamma, dbeta);                     \
+    e = launch_pdl(bn_bwd_apply_kernel<SRC>, dim3(grid), dim3(256), 0, s, dout_, out_, relu_mask, x_, M, C, rows, mean, \
+                   rstd, gamma, beta, relu, fin, fin + C, dx_, dz_, dgamma, dbeta);                                 \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                               \
     B200MM_CHECK_LAUNCH();                                                                                          \
   } while (0)
   if (src == 2) BN_BWD(2);

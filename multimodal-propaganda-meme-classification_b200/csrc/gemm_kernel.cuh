@@ -27,26 +27,31 @@ namespace b200 {
 // CTAS = 2: a CTA pair (cluster of two, cta_group::2) computes a 256 x BN tile with ONE MMA stream -- each CTA stages its
 // own 128 rows of A and only HALF of the B tile, so the tensor core's shared-memory reads per FLOP drop by a third
 // (the single-CTA 128 x 256 tile needs 96 B/clk of the 128 B/clk shared-memory port at full MMA rate).
-template <int BN, int CTAS = 1>
+// EW = epilogue warps: 8 (two column halves per TMEM lane quarter), or 16 (four column quarters: one staged box per
+// warp and tile) for the short-K convolution shapes, whose tiles are bound by the epilogue's instruction latency --
+// measured on [50176 x 1024 x 256]: the MMA thread spends its time waiting for a free accumulator while the 8
+// epilogue warps (2 per scheduler) need ~3600 cycles per 128 x 256 tile against 2048 cycles of tensor time.
+template <int BN, int CTAS = 1, int EW = GEMM_EPI_WARPS>
 struct GemmCfg {
+  static constexpr int THREADS = 64 + EW * 32;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // ring depth that fits next to `nbuf` staging boxes per epilogue warp and the barrier block
   static constexpr int stages_for(int nbuf) {
-    const int avail = GEMM_SMEM_TOTAL - GEMM_EPI_WARPS * nbuf * GEMM_BOX_BYTES - 512;
+    const int avail = GEMM_SMEM_TOTAL - EW * nbuf * GEMM_BOX_BYTES - 512;
     const int s = avail / STAGE_BYTES;
     return s > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : s;
   }
 };
 
-template <int BN, int EPI, int CTAS = 1>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int EPI, int CTAS = 1, int EW = GEMM_EPI_WARPS>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, EW>;
   constexpr bool PAIR = CTAS == 2;
   const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
   const int STAGES = p.num_stages;
@@ -55,8 +60,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   // the staging boxes and the bias rows into generic LD.E / ST.E, which queue with the global loads)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (STAGE_BYTES is a multiple of 1024)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + GEMM_EPI_WARPS * p.nbuf * GEMM_BOX_BYTES);
+  // B-resident mode (single CTA, short unsplit K, every tile of this CTA in the same column block): the whole B tile
+  // [BN x K] is loaded ONCE into a resident area and the ring carries A only.  The short-K convolution GEMMs are bound
+  // by the SM's L2 port (~64 B/clk: 192 KB in + 64 KB out per 128 x 256 x 256 tile = 4096 cycles against 2048 cycles of
+  // tensor time; ring depth, CTA pairs, more epilogue warps and L2 prefetch all left them at ~4800 cycles per tile);
+  // with B resident a tile moves 64 KB in + 64 KB out.
+  const bool BRES = !PAIR && p.b_resident != 0;
+  const int stage_stride = BRES ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
+  uint8_t* ring = smem + (BRES ? p.k_iters * Cfg::B_BYTES : 0);
+  uint8_t* staging = ring + STAGES * stage_stride;  // 1024-aligned (A_BYTES / B_BYTES are multiples of 1024)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + EW * p.nbuf * GEMM_BOX_BYTES);
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -65,6 +78,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // programmatic dependent launch: the next kernel on the stream may be scheduled as this one drains, and this CTA's
+  // set-up (barriers, TMEM allocation) runs while the previous kernel drains; nothing below touches global memory
+  // before pdl_wait()
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -74,7 +91,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], CTAS * GEMM_EPI_WARPS);   // pair: the leader's copy collects both CTAs' epilogue warps
+      mbar_init(&tmem_empty[s], CTAS * EW);   // pair: the leader's copy collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
@@ -87,6 +104,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // the previous kernel's outputs (this kernel's operands, residual, statistics accumulators) are complete
 
   // work units: output tiles (single CTA) or pairs of vertically adjacent tiles (CTA pair: rank r takes tile 2u + r)
   const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;
@@ -144,15 +162,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           b_p0 = r0 / p.conv_Q;
           b_q0 = r0 - b_p0 * p.conv_Q;
         }
+        const bool load_b = !BRES || w == w_first;   // resident B: k block kb of the first tile fills slot kb
         for (int kb = k_begin; kb < k_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+          uint8_t* sa = ring + stage * stage_stride;
+          uint8_t* sb = BRES ? smem + kb * Cfg::B_BYTES : sa + Cfg::A_BYTES;
           if (p.b_im2col) {
             // wgrad: only the 64-column atoms that exist (N = taps * C may end inside the tile) are loaded
             mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + b_atoms * 8192);
-          } else if (!PAIR || cta_rank == 0) {
-            mbar_expect_tx(&full_bar[stage], CTAS * Cfg::STAGE_BYTES);   // pair: both CTAs' loads count on the leader
+          } else if (PAIR) {
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], CTAS * Cfg::STAGE_BYTES);   // both CTAs' loads count on the leader
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + (load_b ? Cfg::B_BYTES : 0));
           }
           if constexpr (PAIR) {
             // (matrix operands only: the convolution shapes stay on the single-CTA kernel)
@@ -200,6 +221,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             b_q0 += GEMM_BK;                              // first output pixel of the next reduction block
             while (b_q0 >= p.conv_Q) { b_q0 -= p.conv_Q; ++b_p0; }
             while (b_p0 >= p.conv_P) { b_p0 -= p.conv_P; ++b_n0; }
+          } else if (!load_b) {
+            // resident B already holds this k block
           } else if (!p.b_mn) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           } else {
@@ -234,8 +257,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = k_begin; kb < k_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t sa = smem_u32(ring + stage * stage_stride);
+          const uint32_t sb = BRES ? smem_u32(smem + kb * Cfg::B_BYTES) : sa + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
             const uint64_t da = umma_desc_sw128(sa + k * a_kstep, a_lbo, 1024);
@@ -261,8 +284,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // 4096 SASS instructions, missed the instruction cache and issue-bound the short-K convolution GEMMs).
     const int ew = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = ew >> 2;              // which half of the BN columns
-    constexpr int HALF_COLS = BN / 2;
+    const int half = ew >> 2;              // which column group (half, or quarter with 16 warps) of the BN columns
+    constexpr int HALF_COLS = BN / (EW / 4);
     constexpr bool BF16_OUT = EPI != EPI_F32 && EPI != EPI_F32_ATOMIC;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -326,11 +349,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         st_s[b][0] = st_s[b][1] = st_q[b][0] = st_q[b][1] = 0.f;
       }
     };
+    // (m_unit, n_blk) of the work unit advance incrementally: the two runtime divisions per tile were 12 % of the
+    // epilogue warps' samples on the short-K shapes (K split never changes the tile an epilogue warp addresses)
+    int m_unit, n_blk;
+    {
+      const int t0 = w_first % tiles_mn;
+      m_unit = t0 / p.n_tiles;
+      n_blk = t0 - m_unit * p.n_tiles;
+    }
     for (int w = w_first; w < num_work; w += w_step) {
-      const int split = w / tiles_mn;
-      const int t = w - split * tiles_mn;
-      const int m_unit = t / p.n_tiles;
-      const int n_blk = t - m_unit * p.n_tiles;
       const int m_blk = tile_row(m_unit);
       if constexpr (EPI == EPI_STORE_STATS) {
         if (n_blk != st_nblk) { stats_flush(); st_nblk = n_blk; }
@@ -506,13 +533,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
               if constexpr (BOX_W == 64) {
                 const uint32_t cc = lane >> 2, wo = (lane & 3) * 4;
+                // two independent packed (FADD2 / FFMA2) chains over the even and the odd rows
+                float2 sa = make_float2(0.f, 0.f), sb = sa, qa = sa, qb = sa;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
+                for (int r = 0; r < 32; r += 2) {
                   const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
                       stage_buf + r * 128 + ((cc ^ (r & 7)) << 4) + wo));
-                  s0 += f.x; s1 += f.y;
-                  q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+                  const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(
+                      stage_buf + (r + 1) * 128 + ((cc ^ ((r + 1) & 7)) << 4) + wo));
+                  sa = fadd2(sa, f); qa = ffma2(f, f, qa);
+                  sb = fadd2(sb, g); qb = ffma2(g, g, qb);
                 }
+                sa = fadd2(sa, sb); qa = fadd2(qa, qb);
+                s0 = sa.x; s1 = sa.y; q0 = qa.x; q1 = qa.y;
               } else {
                 const uint32_t w16 = lane & 15, cc = w16 >> 2, wo = (w16 & 3) * 4, rb = (lane >> 4) * 16;
 #pragma unroll
@@ -579,10 +612,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if constexpr (PAIR) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      advance(m_unit, n_blk);
+      while (m_unit >= m_units) m_unit -= m_units;   // next K split of the same tile grid
     }
     if constexpr (EPI == EPI_STORE_STATS) stats_flush();
     if constexpr (BF16_OUT) {
-      if (lane == 0) tma_store_wait<0>();   // smem must outlive the last bulk store
+      // shared memory must outlive the last bulk store's READ of it; the global writes themselves complete with the grid
+      // (waiting for them here cost ~1 us of every launch's tail)
+      if (lane == 0) tma_store_wait_read<0>();
     }
   }
 
@@ -599,38 +636,60 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
 // Launch one (BN, EPI, CTAS) instantiation.  Shared memory split: `stages` ring slots + `nbuf` staging boxes per
 // epilogue warp.  CTAS == 2 launches clusters of two CTAs (cudaLaunchKernelEx, cluster dimension 2).
-template <int BN, int EPI, int CTAS = 1>
+// ring depth of the B-resident mode: what is left next to the resident [BN x K] tile and the staging boxes
+static inline int b_resident_stages(int bn, int ew, int nbuf, int k_iters) {
+  const int avail = GEMM_SMEM_TOTAL - ew * nbuf * GEMM_BOX_BYTES - 512 - k_iters * bn * GEMM_BK * 2;
+  const int st = avail / (GEMM_BM * GEMM_BK * 2);
+  return st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : st;
+}
+
+template <int BN, int EPI, int CTAS = 1, int EW = GEMM_EPI_WARPS>
 static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& to2,
                             GemmParams p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CTAS>;
+  using Cfg = GemmCfg<BN, CTAS, EW>;
+  const int grid_in = grid;
+  if (p.b_resident && CTAS == 1) grid -= grid % p.n_tiles;   // every tile of a CTA in one column block
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, CTAS, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GEMM_SMEM_TOTAL + 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
   // long-K tiles live in the main loop: deepest ring, one staging box; short-K tiles are store-bound: two boxes
+  // (16 epilogue warps stage ONE box per tile each: a single buffer, free again long before the next tile)
   const int k_per_tile = p.k_iters_per_split;
-  p.nbuf = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 0 : (EPI == EPI_GELU || k_per_tile < 8 ? 2 : 1);   // fp32 modes do not stage
+  if (EW == 16) p.nbuf = 1;
+  else if (p.nbuf <= 0 || EPI == EPI_GELU || EPI == EPI_F32 || EPI == EPI_F32_ATOMIC)
+    p.nbuf = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 0 : (EPI == EPI_GELU || k_per_tile < 8 ? 2 : 1);   // fp32 modes do not stage
   p.num_stages = Cfg::stages_for(p.nbuf);
-  static_assert(GemmCfg<BN, CTAS>::stages_for(2) >= 2, "ring too shallow");
+  static_assert(Cfg::stages_for(2) >= 2, "ring too shallow");
+  if (p.b_resident) {
+    if (CTAS == 1 && EPI != EPI_GELU) p.nbuf = p.nbuf > 1 ? 1 : p.nbuf;
+    const int st = b_resident_stages(BN, EW, p.nbuf, p.k_iters);
+    if (CTAS == 1 && st >= 3) p.num_stages = st;
+    else { p.b_resident = 0; grid = grid_in; }
+  }
   if constexpr (CTAS == 1) {
-    gemm_bf16_kernel<BN, EPI, 1><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL + 1024, stream>>>(ta, tb, to, to2, p);
+    cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, EPI, 1, EW>, dim3(grid), dim3(Cfg::THREADS), GEMM_SMEM_TOTAL + 1024,
+                               stream, ta, tb, to, to2, p);
+    if (e != cudaSuccess) return static_cast<int>(e);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid & ~1), 1, 1);
-    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
     cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL + 1024;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, 2>, ta, tb, to, to2, p);
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, 2, EW>, ta, tb, to, to2, p);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   cudaError_t e = cudaGetLastError();
@@ -643,6 +702,7 @@ int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
                      const GemmParams& p, int grid, cudaStream_t stream) {
   switch (p.epi) {
     case EPI_STORE:
+      if (p.col_stats != nullptr) return launch_gemm_inst<BN, EPI_STORE_STATS, 2>(ta, tb, to, to2, p, grid, stream);
       if (p.p_drop > 0.f) return launch_gemm_inst<BN, EPI_STORE_DROP, 2>(ta, tb, to, to2, p, grid, stream);
       return launch_gemm_inst<BN, EPI_STORE, 2>(ta, tb, to, to2, p, grid, stream);
     case EPI_GELU: return launch_gemm_inst<BN, EPI_GELU, 2>(ta, tb, to, to2, p, grid, stream);

@@ -51,6 +51,7 @@ struct GemmParams {
   //   b_im2col: B atom = 64 pixels (reduction dim) x 64 channels of tap (col / conv_C)     (wgrad)
   int a_im2col, b_im2col;
   int conv_C, conv_KW, conv_stride, conv_pad, conv_P, conv_Q, conv_cblocks;
+  int b_resident;  // single CTA, unsplit short K: the [BN x K] B tile stays in shared memory for all tiles of the CTA
   int num_stages;  // smem ring depth (runtime: deep ring for long-K tiles, ...)
   int nbuf;        // ... or two epilogue staging boxes per warp for short-K, store-heavy tiles
 };

@@ -37,6 +37,11 @@ using namespace b200;
 
 namespace {
 
+// Tuning knobs (b200mm_gemm_tune; the defaults are the measured optimum, the setter exists for A/B micro-benchmarks):
+//   0: smallest reduction depth (k blocks of 64 per tile) the CTA-pair kernel takes
+//   1: 1 = B-resident mode for short unsplit K (see gemm_kernel.cuh)
+int g_tune[2] = {8, 1};
+
 // Where an operand comes from: a matrix (tiled TMA loads, K-major or MN-major) or an NHWC activation gathered with
 // im2col-mode TMA loads (implicit-GEMM convolution).
 struct Operand {
@@ -114,9 +119,13 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
     const char* e = std::getenv("B200MM_GEMM_PAIR");
     return e == nullptr || e[0] != '0';
   }();
-  const bool pair = pair_enabled && bn == 256 && !A.im2col && !B.im2col && col_stats == nullptr && !p.accumulate &&
+  // Short-K 1x1-convolution shapes included: at K <= 512 the single-CTA kernel is bound by L2 -> SM traffic, not by
+  // HBM (every 128 x 256 tile re-reads its whole 256-row B tile from L2: 205 MB per ResNet bottleneck GEMM whatever
+  // the layer, ~10 TB/s measured at the L2's limit); the pair halves the B traffic.
+  const bool pair = pair_enabled && bn == 256 && !A.im2col && !B.im2col &&
                     (epi == EPI_STORE || epi == EPI_GELU || epi == EPI_DGELU || epi == EPI_F32_ATOMIC) &&
-                    p.m_tiles >= 2 && p.k_iters_per_split >= 8 && (dev.num_sms & 1) == 0;
+                    p.m_tiles >= 2 && p.k_iters_per_split >= g_tune[0] && (dev.num_sms & 1) == 0;
+  p.nbuf = 0;
   CUtensorMap ta, tb;
   int rc;
   if (A.im2col)   rc = make_tmap_im2col_bf16(&ta, A.ptr, cg.N, cg.H, cg.W, cg.C, cg.ksize, cg.stride, cg.pad, GEMM_BM);
@@ -149,12 +158,29 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   }
   const int num_work = p.m_tiles * p.n_tiles * p.splits;
   const int grid = num_work < dev.num_sms ? num_work : dev.num_sms;
+  // B-resident mode: bf16 output, matrix B operand, unsplit K, several tiles per CTA, n_tiles small enough that a grid
+  // of a multiple of n_tiles CTAs keeps (nearly) every SM busy; the launcher checks that the tile and a >= 3-slot
+  // ring fit and falls back otherwise
+  p.b_resident = (g_tune[1] && !B.im2col && p.splits == 1 && epi != EPI_F32 && epi != EPI_F32_ATOMIC &&
+                  p.n_tiles <= 8 && num_work >= 2 * dev.num_sms &&
+                  static_cast<long long>(p.k_iters) * bn * GEMM_BK * 2 <= 128 * 1024) ? 1 : 0;
   switch (bn) {
     case 64: return launch_gemm_bn64(ta, tb, to, to2, p, grid, s);
     case 128: return launch_gemm_bn128(ta, tb, to, to2, p, grid, s);
     default: return launch_gemm_bn256(ta, tb, to, to2, p, grid, s);
   }
 }
+
+}  // namespace
+
+// Micro-benchmark hook: set tuning knob `knob` (see g_tune) to `value`.
+B200MM_API int b200mm_gemm_tune(int knob, int value) {
+  if (knob < 0 || knob >= 2) return B200MM_ERR_BAD_ARG;
+  g_tune[knob] = value;
+  return B200MM_OK;
+}
+
+namespace {
 
 // w_rot[ci][k-1-kh][k-1-kw][co] = w[co][kh][kw][ci]: the weight of the transposed (data-gradient) convolution
 __global__ void __launch_bounds__(256)

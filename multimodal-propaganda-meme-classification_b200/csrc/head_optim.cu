@@ -18,6 +18,8 @@ namespace b200 {
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int M, int N, int rows_per_cta,
               float* __restrict__ out) {
+  pdl_launch_dependents();   // see launch_pdl (common.cuh)
+  pdl_wait();
   __shared__ float red[8][256 + 8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + tx) * 8;
@@ -342,8 +344,8 @@ B200MM_API int b200mm_colsum_bf16(const void* x, long long ld, int M, int N, flo
   int rows_per_cta = ceil_div(M, gy);
   rows_per_cta = ceil_div(rows_per_cta, 8) * 8;
   gy = ceil_div(M, rows_per_cta);
-  colsum_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ld, M, N, rows_per_cta, out);
+  launch_pdl(colsum_kernel, dim3(gx, gy), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(x), ld, M, N, rows_per_cta, out);
   B200MM_CHECK_LAUNCH();
   return B200MM_OK;
 }

@@ -46,6 +46,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const long long* __res
                      __nv_bfloat16* __restrict__ x_saved, const float* __restrict__ gamma,
                      const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int M, int D, float eps, DropSpec drop) {
+  pdl_launch_dependents();   // see launch_pdl (common.cuh)
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp;
   if (row >= M) return;
@@ -154,6 +156,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ addend,
                      __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx2, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int M, int D, int rows_per_cta, DropSpec in_drop, DropSpec out_drop) {
+  pdl_launch_dependents();   // see launch_pdl (common.cuh)
+  pdl_wait();
   // [LN_WARPS][LN_DEPTH][dy row | x row] bf16 while rows stream; reused as float [LN_WARPS][2][D] for the column sums
   constexpr int LN_DEPTH = ln_depth(NC);
   extern __shared__ __align__(128) uint8_t ln_smem[];
@@ -440,9 +444,10 @@ B200MM_API int b200mm_layernorm_fwd(const void* x, const float* gamma, const flo
                                     void* stream) {
   if (!ln_shape_ok(M, D)) return B200MM_ERR_BAD_ARG;
 #define LAUNCH_LN_FWD(NC)                                                                                           \
-  layernorm_fwd_kernel<false, NC><<<ceil_div(M, LN_WARPS), LN_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(  \
-      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, nullptr, 1, 1, nullptr, gamma, beta, \
-      static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps, make_drop(p_drop, seed))
+  launch_pdl(layernorm_fwd_kernel<false, NC>, dim3(ceil_div(M, LN_WARPS)), dim3(LN_WARPS * 32), 0,                  \
+             static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr,      \
+             nullptr, nullptr, 1, 1, nullptr, gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, M, D, eps,     \
+             make_drop(p_drop, seed))
   const int nc = ceil_div(D, 256);
   if (nc <= 1) LAUNCH_LN_FWD(1);
   else if (nc == 2) LAUNCH_LN_FWD(2);
@@ -509,11 +514,11 @@ B200MM_API int b200mm_layernorm_bwd(const void* dy, const void* x, const float* 
     int rows_per_cta = ceil_div(M, target_ctas);                                                                   \
     rows_per_cta = ceil_div(rows_per_cta, LN_WARPS) * LN_WARPS;                                                    \
     const int grid = ceil_div(M, rows_per_cta);                                                                    \
-    layernorm_bwd_kernel<NC><<<grid, LN_WARPS * 32, smem, static_cast<cudaStream_t>(stream)>>>(                    \
-        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd, gamma,            \
-        static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(dx),                                \
-        static_cast<__nv_bfloat16*>(dx2), dgamma, dbeta, M, D, rows_per_cta,                                       \
-        make_drop(p_in, seed_in), make_drop(dx2 ? p_out : 0.f, seed_out));                                         \
+    launch_pdl(layernorm_bwd_kernel<NC>, dim3(grid), dim3(LN_WARPS * 32), smem, static_cast<cudaStream_t>(stream), \
+               static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd, gamma,     \
+               static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(dx),                         \
+               static_cast<__nv_bfloat16*>(dx2), dgamma, dbeta, M, D, rows_per_cta,                                \
+               make_drop(p_in, seed_in), make_drop(dx2 ? p_out : 0.f, seed_out));                                  \
   } while (0)
   if (nc <= 1) LAUNCH_LN_BWD(1);
   else if (nc == 2) LAUNCH_LN_BWD(2);

@@ -262,7 +262,7 @@ stem_fwd_kernel(const __grid_constant__ CUtensorMap tma_w, const __grid_constant
       }
     }
   }
-  if (threadIdx.x == 0) tma_store_wait<0>();
+  if (threadIdx.x == 0) tma_store_wait_read<0>();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<ST_COUT>(tmem);
