@@ -412,17 +412,32 @@ def run_engine(args):
     e2e_warm = int(os.environ.get("B200MM_E2E_WARM", "8"))
     e2e_log = []
 
-    def make_e2e_loader():
-        shm_free = shutil.disk_usage("/dev/shm").free if os.path.isdir("/dev/shm") else 0
-        # two loader processes keep up with a 31 ms step; more of them take cores from the thread that launches the
-        # step's ~500 kernels (measured on a 16-core box: 0 / 2 / 4 / 8 workers -> 33.1 / 32.2 / 36.7 / 36.4 ms per
-        # step against 31.2 resident, gpurun_out/e2e_probe.log -> profiles/e2e_probe_r02.log)
-        workers = (2 if (os.cpu_count() or 2) >= 4 * world else 1) if shm_free > (4 << 30) else 0
-        workers = int(os.environ.get("B200MM_E2E_WORKERS", workers))
+    def make_e2e_loader(workers, steps):
         kw = dict(prefetch_factor=2, persistent_workers=False) if workers else {}
-        dl = DataLoader(SyntheticMemes((e2e_warm + args.steps) * B), batch_size=B, shuffle=False, drop_last=True,
+        dl = DataLoader(SyntheticMemes(steps * B), batch_size=B, shuffle=False, drop_last=True,
                         num_workers=workers, pin_memory=True, **kw)
-        return Primed(dl), workers
+        return Primed(dl)
+
+    def pick_e2e_workers():
+        """DataLoader worker count from a short measurement on THIS host: with the step replayed as one CUDA graph the
+        launching thread is idle, and what decides is whether the loader processes keep up without fighting the
+        pin-memory thread for cores (16-core box, graph mode: 0 / 1 / 2 / 3 workers -> 31.7 / 30.6 / 38.7 / 34.7 ms per
+        step against 30.2 resident, profiles/e2e_workers_r02.log).  Every rank runs the same number of probe steps."""
+        if "B200MM_E2E_WORKERS" in os.environ:
+            return int(os.environ["B200MM_E2E_WORKERS"]), None
+        shm_free = shutil.disk_usage("/dev/shm").free if os.path.isdir("/dev/shm") else 0
+        cands = [1, 2, 0] if shm_free > (4 << 30) and (os.cpu_count() or 2) >= 4 * world else [0]
+        probe = {}
+        for w in cands:
+            primed = make_e2e_loader(w, 3 + 6)
+            e2e_train(primed, 3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_train(primed, 6)
+            torch.cuda.synchronize()
+            probe[w] = (time.perf_counter() - t0) / 6 * 1e3
+            del primed
+        return min(probe, key=probe.get), {str(k): round(v, 2) for k, v in probe.items()}
 
     def e2e_train(primed, k):
         return b200mm.train(model, primed.take(k), crit, opt, dev, on_step=lambda loss, bs: e2e_log.append(loss),
@@ -507,7 +522,8 @@ def run_engine(args):
 
     e2e = None
     if not args.no_e2e:
-        primed, workers = make_e2e_loader()
+        workers, worker_probe = pick_e2e_workers()
+        primed = make_e2e_loader(workers, e2e_warm + args.steps)
         e2e_train(primed, e2e_warm)
         e2e_log.clear()
         ms_e = timed(lambda: e2e_train(primed, args.steps), 1) / args.steps
@@ -519,7 +535,7 @@ def run_engine(args):
                        "device, graph=GraphedTrainStep): uint8 HWC pixels + token ids from pinned memory, ToTensor/Normalize on the GPU copy "
                        "stream" % workers,
                "readback": "loss + correct count of every step, asynchronous to pinned memory, consumed one step later",
-               "last_loss": e2e_log[-1]}
+               "loader_workers_probe_ms": worker_probe, "last_loss": e2e_log[-1]}
         del primed
 
     cpu = None

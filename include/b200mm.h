@@ -47,9 +47,19 @@ int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const void* B, int 
  * col_stats[N+n] += sum_m out[m,n]^2 over the STORED bf16 values -- the train-mode BatchNorm statistics of a
  * convolution output come out of the convolution's own epilogue (feeds b200mm_batchnorm_fwd_stats). */
 
-/* Micro-benchmark hook (A/B timing of dispatch decisions; the defaults are the measured optimum): knob 0 = smallest
- * reduction depth in 64-wide k blocks the CTA-pair kernel takes (8), knob 1 = B-resident mode for short unsplit K (1). */
-int b200mm_gemm_tune(int knob, int value);
+/* out = bf16(A x B + (mask bit ? residual : 0)): data gradient of a residual block's first convolution + the identity
+ * branch's gradient (dout o ReLU mask) in one epilogue; mask = the 1-bit-per-element [M, N/8] ReLU mask written by
+ * b200mm_batchnorm_fwd_stats.  Replaces autograd's add of the two branch gradients behind
+ * torchvision/models/resnet.py:155-161 (out += identity; relu).  N % 32 == 0. */
+int b200mm_gemm_bf16_maskres(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb, int M, int N,
+                             int K, const void* residual, long long ldr, const unsigned char* mask, long long ld_mask,
+                             void* out, long long ldc, void* stream);
+
+/* Dispatch knobs (the defaults are the measured optimum; for A/B micro-benchmarks and for tests that must reach both
+ * sides of a dispatch decision): 0 = smallest reduction depth in 64-wide k blocks the CTA-pair GEMM takes (8),
+ * 1 = B-resident GEMM mode for short unsplit K (1), 2 = largest tensor in MB whose BatchNorm backward runs as one
+ * cooperative launch (0 = never, the default: it measured 0.7 % slower on the config-2 step). */
+int b200mm_tune(int knob, int value);
 
 /* Implicit-GEMM convolution on the same kernel: the activation operand is gathered from NHWC memory by im2col-mode
  * TMA loads (no im2col matrix exists).  x: bf16 [N,H,W,C], C % 64 == 0; w: bf16 OHWI-flattened [Cout, k*k*C].

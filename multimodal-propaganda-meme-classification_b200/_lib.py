@@ -64,7 +64,7 @@ def load(build_if_needed: bool = True) -> ctypes.CDLL:
 
 # kernels launched through this module since the counter was last reset (bench.py's gpu_launches)
 LAUNCHES = [0]
-_KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0, "b200mm_gemm_tune": 0,
+_KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0, "b200mm_tune": 0,
                      "b200mm_set_step_salt_ptr": 0}
 
 
@@ -97,7 +97,9 @@ def exported_symbols() -> list[str]:
 # ------------------------------------------------------------------ signatures (mirror include/b200mm.h)
 declare("b200mm_version", [])
 declare("b200mm_num_sms", [])
-declare("b200mm_gemm_tune", [c_int, c_int])
+declare("b200mm_tune", [c_int, c_int])
+declare("b200mm_gemm_bf16_maskres", [c_ptr, c_int, c_longlong, c_ptr, c_int, c_longlong, c_int, c_int, c_int, c_ptr,
+                                     c_longlong, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr])
 declare("b200mm_gemm_bf16", [c_ptr, c_int, c_longlong, c_ptr, c_int, c_longlong, c_int, c_int, c_int, c_int,
                              c_ptr, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong, c_ptr, c_longlong,
                              c_int, c_int, c_float, c_ulonglong, c_ptr, c_ptr])

@@ -17,6 +17,8 @@ const DeviceInfo& device_info() {
   return info;
 }
 
+int g_tune[TUNE_KNOBS] = {8, 1, 0};
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("B200MM_PDL");
@@ -161,6 +163,13 @@ B200MM_API int b200mm_set_step_salt_ptr(const unsigned long long* salt) {
     const int rc = b200::g_salt_setters[i](salt);
     if (rc != 0) return rc;
   }
+  return B200MM_OK;
+}
+
+// Set dispatch knob `knob` (see g_tune in common.cuh) to `value`.
+B200MM_API int b200mm_tune(int knob, int value) {
+  if (knob < 0 || knob >= b200::TUNE_KNOBS) return B200MM_ERR_BAD_ARG;
+  b200::g_tune[knob] = value;
   return B200MM_OK;
 }
 

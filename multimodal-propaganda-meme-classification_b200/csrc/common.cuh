@@ -53,6 +53,15 @@ int make_tmap_nhwc_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W, 
 int make_tmap_im2col_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W, int C, int ksize, int stride, int pad,
                           uint32_t pixels_per_column);
 
+// Dispatch knobs (b200mm_tune; the defaults are the measured optimum, the setter exists for A/B micro-benchmarks and
+// for tests that must reach both sides of a dispatch decision):
+//   0: smallest reduction depth (k blocks of 64 per tile) the CTA-pair GEMM takes                          (8)
+//   1: B-resident GEMM mode for short unsplit K (gemm_kernel.cuh)                                           (1)
+//   2: largest tensor in MB whose BatchNorm backward runs as ONE cooperative launch (conv_support.cu); 0 = never (0:
+//      measured on config 2 at 52 MB -- ResNet layers 3-4 -- the step takes 30.28 ms against 30.06 ms with two kernels)
+constexpr int TUNE_KNOBS = 3;
+extern int g_tune[TUNE_KNOBS];
+
 // Programmatic dependent launch (PDL).  A kernel launched through launch_pdl may be scheduled while the kernel before
 // it on the stream is still draining (its CTAs start on SMs whose resources are already free and run their prologue);
 // it MUST execute pdl_wait() (griddepcontrol.wait: the preceding grid has completed and its writes are visible) before

@@ -6,6 +6,7 @@
 // :266-280 (_forward_impl) -- cuDNN convolution / batch-norm and ATen pooling -- and their backward passes.
 #include "common.cuh"
 #include "device_utils.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -360,6 +361,155 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16*
         unpack8(ro[u], o);
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = o[i] > 0.f ? d[i] : 0.f;
+      }
+      if (dz_out != nullptr) store8(dz_out + rr * C + g * 8, d);
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = k0[i] * (d[i] - k1[i] - (xv[i] - mu[i]) * rs[i] * k2[i]);
+      store8(dx + rr * C + g * 8, o);
+    }
+  }
+}
+
+// Both backward passes in ONE launch for tensors the L2 holds (dout + x <= ~100 MB: ResNet layers 3-4, the narrow
+// layer-2 tensors): every CTA reduces its rows, publishes its partial sums, waits on a grid-wide counter, then applies
+// to the SAME rows -- the second read of dout and x comes from L2 instead of DRAM, and one launch (plus the gap and
+// the cold start of a second kernel over a 13-50 MB tensor) disappears.  Launched cooperatively (all CTAs co-resident:
+// grid = SMs x occupancy).  scratch: the replica rows and the counter of column_reduce_finish, zeroed by the caller.
+template <int MASK_SRC>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, const unsigned char* __restrict__ relu_mask,
+                    const __nv_bfloat16* __restrict__ x, long long M, int C, int rows_per_cta,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int relu, float* __restrict__ scratch,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dz_out, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta) {
+  static_assert(MASK_SRC == 0 || MASK_SRC == 2, "mask from x (recomputed) / none, or the 1-bit mask");
+  __shared__ float red[2][256][8];
+  const int G = C >> 3;
+  const int g = threadIdx.x % G, ty = threadIdx.x / G, rpp = 256 / G;
+  const bool recompute = relu && MASK_SRC == 0;
+  float mu[8], rs[8], k0[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mu[i] = mean[g * 8 + i];
+    rs[i] = rstd[g * 8 + i];
+    k0[i] = gamma[g * 8 + i] * rs[i];
+    sh[i] = recompute ? fmaf(-mu[i], k0[i], beta[g * 8 + i]) : 0.f;
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = min(r0 + rows_per_cta, M);
+  // ---- pass 1: dbeta = sum dz, dgamma = sum dz * xhat over this CTA's rows
+  float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr int U = 6;
+  for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
+    uint4 rd[U], rx[U];
+    unsigned int rm[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * rpp;
+      const bool ok = rr < r1;
+      const long long off = rr * C + g * 8;
+      rd[u] = ok ? __ldcg(reinterpret_cast<const uint4*>(dout + off)) : make_uint4(0, 0, 0, 0);
+      rx[u] = ok ? __ldcg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
+      if constexpr (MASK_SRC == 2) rm[u] = ok ? __ldg(relu_mask + rr * G + g) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float d[8], xv[8];
+      unpack8(rd[u], d);
+      unpack8(rx[u], xv);
+      if constexpr (MASK_SRC == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = (rm[u] >> i) & 1u ? d[i] : 0.f;
+      } else if (recompute) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(xv[i], k0[i], sh[i]) > 0.f ? d[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sb[i] += d[i];
+        sg[i] = fmaf(d[i], (xv[i] - mu[i]) * rs[i], sg[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[0][threadIdx.x][i] = sg[i];
+    red[1][threadIdx.x][i] = sb[i];
+  }
+  __syncthreads();
+  if (ty == 0) {
+    for (int t = 1; t < rpp; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sg[i] += red[0][t * G + g][i];
+        sb[i] += red[1][t * G + g][i];
+      }
+    float* rep = scratch + static_cast<size_t>(blockIdx.x % BN_REPLICAS) * 2 * C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(rep + g * 8 + i, sg[i]);
+      atomicAdd(rep + C + g * 8 + i, sb[i]);
+    }
+  }
+  // ---- grid-wide barrier (all CTAs are co-resident: cooperative launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + static_cast<size_t>(BN_REPLICAS + 1) * 2 * C);
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen < gridDim.x) __nanosleep(64);
+    } while (seen < gridDim.x);
+  }
+  __syncthreads();
+  // ---- pass 2: dx = gamma * rstd * (dz - dbeta/M - xhat * dgamma/M) over the same rows (L2-resident now)
+  const float invM = 1.f / static_cast<float>(M);
+  float k1[8], k2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = g * 8 + i;
+    float dg = 0.f, db = 0.f;
+#pragma unroll
+    for (int r = 0; r < BN_REPLICAS; ++r) {
+      dg += __ldcg(scratch + static_cast<size_t>(r) * 2 * C + c);
+      db += __ldcg(scratch + static_cast<size_t>(r) * 2 * C + C + c);
+    }
+    k1[i] = db * invM;
+    k2[i] = dg * invM;
+    if (blockIdx.x == 0 && ty == 0) {
+      dgamma[c] += dg;
+      dbeta[c] += db;
+    }
+  }
+  for (long long r = r0 + ty; r < r1; r += static_cast<long long>(rpp) * U) {
+    uint4 rd[U], rx[U];
+    unsigned int rm[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * rpp;
+      const bool ok = rr < r1;
+      const long long off = rr * C + g * 8;
+      rd[u] = ok ? __ldcg(reinterpret_cast<const uint4*>(dout + off)) : make_uint4(0, 0, 0, 0);
+      rx[u] = ok ? __ldcg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0, 0, 0, 0);
+      if constexpr (MASK_SRC == 2) rm[u] = ok ? __ldg(relu_mask + rr * G + g) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + static_cast<long long>(u) * rpp;
+      if (rr >= r1) break;
+      float d[8], xv[8];
+      unpack8(rd[u], d);
+      unpack8(rx[u], xv);
+      if constexpr (MASK_SRC == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = (rm[u] >> i) & 1u ? d[i] : 0.f;
+      } else if (recompute) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(xv[i], k0[i], sh[i]) > 0.f ? d[i] : 0.f;
       }
       if (dz_out != nullptr) store8(dz_out + rr * C + g * 8, d);
       float o[8];
@@ -836,6 +986,36 @@ B200MM_API int b200mm_batchnorm_bwd(const void* dout, const void* out, const voi
   static const int occ_apply[3] = {bn_occupancy(bn_bwd_apply_kernel<0>), bn_occupancy(bn_bwd_apply_kernel<1>),
                                    bn_occupancy(bn_bwd_apply_kernel<2>)};
   const int src = (relu && relu_mask != nullptr) ? 2 : (relu && out != nullptr) ? 1 : 0;
+  // L2-resident tensors: one cooperative launch does both passes (b200mm_tune knob 2: largest tensor in MB, 0 = off)
+  const long long fused_bytes = static_cast<long long>(g_tune[2]) << 20;
+  if (src != 1 && M * C * 2 <= fused_bytes) {
+    static const int occ_fused[2] = {bn_occupancy(bn_bwd_fused_kernel<0>), bn_occupancy(bn_bwd_fused_kernel<2>)};
+    int fgrid;
+    const int frows = bn_rows_per_cta(M, C, &fgrid, occ_fused[src == 2 ? 1 : 0] < 2 ? occ_fused[src == 2 ? 1 : 0] : 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(fgrid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    static const bool coop = [] { const char* e = std::getenv("B200MM_BN_COOP"); return e == nullptr || e[0] != '0'; }();
+    cfg.numAttrs = coop ? 1 : 0;
+    const __nv_bfloat16* d_ = static_cast<const __nv_bfloat16*>(dout);
+    const __nv_bfloat16* xx = static_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* dxp = static_cast<__nv_bfloat16*>(dx);
+    __nv_bfloat16* dzp = static_cast<__nv_bfloat16*>(dz_out);
+    cudaError_t le = src == 2
+        ? cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel<2>, d_, relu_mask, xx, M, C, frows, mean, rstd, gamma, beta, relu,
+                             scratch, dxp, dzp, dgamma, dbeta)
+        : cudaLaunchKernelEx(&cfg, bn_bwd_fused_kernel<0>, d_, relu_mask, xx, M, C, frows, mean, rstd, gamma, beta, relu,
+                             scratch, dxp, dzp, dgamma, dbeta);
+    if (le != cudaSuccess) return static_cast<int>(le);
+    B200MM_CHECK_LAUNCH();
+    return B200MM_OK;
+  }
   const int rows = bn_rows_per_cta(M, C, &grid, occ_apply[src]);
   const int rrows = bn_rows_per_cta(M, C, &rgrid, 2);
   const float* fin = scratch + static_cast<size_t>(BN_REPLICAS) * 2 * C;

@@ -287,6 +287,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int half = ew >> 2;              // which column group (half, or quarter with 16 warps) of the BN columns
     constexpr int HALF_COLS = BN / (EW / 4);
     constexpr bool BF16_OUT = EPI != EPI_F32 && EPI != EPI_F32_ATOMIC;
+    // store modes that may add a residual: plain / ReLU / dropout, and the ReLU-masked residual of the identity branch
+    constexpr bool RES_EPI = EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP || EPI == EPI_STORE_MASKRES;
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
@@ -372,7 +374,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         constexpr int PASSES = 1;
         uint8_t* stage_base = staging + ew * (p.nbuf * GEMM_BOX_BYTES);
         const __nv_bfloat16* res_row = nullptr;
-        if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP)
+        if constexpr (RES_EPI)
           if (p.residual != nullptr && row_ok) res_row = p.residual + row * p.ldr;
         if constexpr (HAS_SIDE) {
           if (side != nullptr && (sv_tile != w || sv_box != 0)) { side_fetch(m_blk, n_blk, 0); sv_tile = w; sv_box = 0; }
@@ -428,7 +430,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               // BEFORE the accumulator read, so their latency overlaps it and each other (one load per 8 columns
               // right before its use serialised four L2 round trips per chunk: 86 vs 40 us at [32768 x 768 x 768])
               uint4 rres[4];
-              if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP) {
+              if constexpr (RES_EPI) {
                 if (res_row != nullptr) {
 #pragma unroll
                   for (int g = 0; g < 4; ++g) {
@@ -436,6 +438,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     rres[g] = col < p.N ? __ldg(reinterpret_cast<const uint4*>(res_row + col)) : make_uint4(0u, 0u, 0u, 0u);
                   }
                 }
+              }
+              // EPI_STORE_MASKRES: 1 bit per element of this lane's row (bit set = the ReLU behind the residual's
+              // producer passed): 32 columns = one 4-byte word
+              uint32_t rmask = 0xffffffffu;
+              if constexpr (EPI == EPI_STORE_MASKRES) {
+                const int col = box_col0 + c * 32;
+                rmask = (row_ok && col < p.N) ? __ldg(reinterpret_cast<const uint32_t*>(p.res_mask + row * p.ld_mask + (col >> 3)))
+                                              : 0u;
               }
               uint32_t v[32];
               tmem_ld32(t_base + box_col_in_tile + c * 32, v);
@@ -459,7 +469,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     x[4] = s2.x; x[5] = s2.y; x[6] = s3.x; x[7] = s3.y;
                   }
                 }
-                if constexpr (EPI == EPI_STORE || EPI == EPI_RELU || EPI == EPI_STORE_DROP) {
+                if constexpr (RES_EPI) {
                   if constexpr (EPI == EPI_STORE_DROP) {
                     const uint32_t keep =
                         dropout_keep8(p.seed, static_cast<uint64_t>(row * p.N + col) >> 3, p.drop_threshold);
@@ -468,7 +478,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   }
                   if (res_row != nullptr && col_ok) {
                     // (row-strided per lane: relies on L1 to serve the other 16-byte pieces of each 128-byte line)
-                    const uint4 r = rres[g];
+                    uint4 r = rres[g];
+                    if constexpr (EPI == EPI_STORE_MASKRES) {
+                      // keep the residual elements whose mask bit is set: bits 2j, 2j+1 select the halves of word j
+                      const uint32_t m8 = rmask >> (8 * g);
+                      r.x &= ((m8 & 1u) ? 0x0000ffffu : 0u) | ((m8 & 2u) ? 0xffff0000u : 0u);
+                      r.y &= ((m8 & 4u) ? 0x0000ffffu : 0u) | ((m8 & 8u) ? 0xffff0000u : 0u);
+                      r.z &= ((m8 & 16u) ? 0x0000ffffu : 0u) | ((m8 & 32u) ? 0xffff0000u : 0u);
+                      r.w &= ((m8 & 64u) ? 0x0000ffffu : 0u) | ((m8 & 128u) ? 0xffff0000u : 0u);
+                    }
                     const float2 s0 = fadd2(make_float2(x[0], x[1]), unpack_bf16x2(r.x));
                     const float2 s1 = fadd2(make_float2(x[2], x[3]), unpack_bf16x2(r.y));
                     const float2 s2 = fadd2(make_float2(x[4], x[5]), unpack_bf16x2(r.z));
@@ -717,6 +735,7 @@ int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
                    const GemmParams& p, int grid, cudaStream_t stream) {
   switch (p.epi) {
     case EPI_STORE:
+      if (p.res_mask != nullptr) return launch_gemm_inst<BN, EPI_STORE_MASKRES>(ta, tb, to, to2, p, grid, stream);
       if (p.col_stats != nullptr) return launch_gemm_inst<BN, EPI_STORE_STATS>(ta, tb, to, to2, p, grid, stream);
       if (p.p_drop > 0.f) return launch_gemm_inst<BN, EPI_STORE_DROP>(ta, tb, to, to2, p, grid, stream);
       return launch_gemm_inst<BN, EPI_STORE>(ta, tb, to, to2, p, grid, stream);

@@ -21,6 +21,8 @@ enum EpiMode : int {
   EPI_F32_ATOMIC = 4,  // out_f32 += acc        (split-K partial sums)
   EPI_RELU = 5,        // out = bf16(max(acc + bias + residual, 0))
   EPI_STORE_DROP = 6,  // internal: EPI_STORE with inverted dropout (own instantiation keeps EPI_STORE lean)
+  EPI_STORE_MASKRES = 8, // internal: out = bf16(acc + (mask bit ? residual : 0)) -- the identity-branch gradient of a
+                         // residual block joins the data gradient without ever being materialised
   EPI_STORE_STATS = 7, // internal: out = bf16(acc) and col_stats[n] += sum_m out, col_stats[N + n] += sum_m out^2
                        // (train-mode BatchNorm statistics of a convolution output, taken on the stored bf16 values)
 };
@@ -39,6 +41,8 @@ struct GemmParams {
   long long ldc;
   __nv_bfloat16* out2;
   long long ld2;
+  const unsigned char* res_mask;  // EPI_STORE_MASKRES: [M, N / 8] bytes, bit i of byte j = element 8 j + i
+  long long ld_mask;              // ... row stride in bytes
   float* col_stats;  // EPI_STORE_STATS: fp32 [2N] accumulators (pre-zeroed by the caller)
   int accumulate;    // EPI_STORE with residual == out: out += acc through TMA reduce-add stores (no residual loads)
   // EPI_STORE only: inverted dropout on (acc + bias) before the residual add, mask keyed by (seed, row * N + col)

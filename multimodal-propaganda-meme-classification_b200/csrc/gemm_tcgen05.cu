@@ -37,11 +37,6 @@ using namespace b200;
 
 namespace {
 
-// Tuning knobs (b200mm_gemm_tune; the defaults are the measured optimum, the setter exists for A/B micro-benchmarks):
-//   0: smallest reduction depth (k blocks of 64 per tile) the CTA-pair kernel takes
-//   1: 1 = B-resident mode for short unsplit K (see gemm_kernel.cuh)
-int g_tune[2] = {8, 1};
-
 // Where an operand comes from: a matrix (tiled TMA loads, K-major or MN-major) or an NHWC activation gathered with
 // im2col-mode TMA loads (implicit-GEMM convolution).
 struct Operand {
@@ -57,7 +52,7 @@ struct ConvGeom {
 int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int N, int K, int epi, const float* bias,
              const void* residual, long long ldr, const void* aux, long long ld_aux, void* out, long long ldc,
              void* out2, long long ld2, int splits, int block_n, float p_drop, unsigned long long seed,
-             float* col_stats, void* stream) {
+             float* col_stats, void* stream, const unsigned char* res_mask = nullptr, long long ld_mask = 0) {
   const DeviceInfo& dev = device_info();
   if (!dev.ok) return B200MM_ERR_NOT_SM100;
   if (dev.cc_major != 10) return B200MM_ERR_NOT_SM100;
@@ -73,6 +68,10 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   if (col_stats != nullptr && (epi != EPI_STORE || bias != nullptr || residual != nullptr || p_drop > 0.f))
     return B200MM_ERR_BAD_ARG;
   if ((A.im2col || B.im2col) && (cg.C % 64 != 0 || cg.ksize < 1)) return B200MM_ERR_BAD_ARG;
+  // masked residual (identity-branch gradient): plain store mode with a residual, 32 columns per mask word
+  if (res_mask != nullptr && (epi != EPI_STORE || residual == nullptr || residual == out || bias != nullptr || p_drop > 0.f ||
+                              col_stats != nullptr || (N & 31) || (ld_mask & 3) || (reinterpret_cast<uintptr_t>(res_mask) & 3)))
+    return B200MM_ERR_BAD_ARG;
 
   int bn = block_n;
   if (bn == 0) bn = (N % 256 == 0 || N > 512) ? 256 : (N > 64 ? 128 : 64);
@@ -107,6 +106,8 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   p.out2 = static_cast<__nv_bfloat16*>(out2);
   p.ld2 = ld2;
   p.col_stats = col_stats;
+  p.res_mask = res_mask;
+  p.ld_mask = ld_mask;
   if (p_drop < 0.f || p_drop >= 1.f) return B200MM_ERR_BAD_ARG;
   p.p_drop = (epi == EPI_STORE) ? p_drop : 0.f;
   p.drop_threshold = dropout_threshold(p_drop);
@@ -122,7 +123,7 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   // Short-K 1x1-convolution shapes included: at K <= 512 the single-CTA kernel is bound by L2 -> SM traffic, not by
   // HBM (every 128 x 256 tile re-reads its whole 256-row B tile from L2: 205 MB per ResNet bottleneck GEMM whatever
   // the layer, ~10 TB/s measured at the L2's limit); the pair halves the B traffic.
-  const bool pair = pair_enabled && bn == 256 && !A.im2col && !B.im2col &&
+  const bool pair = pair_enabled && bn == 256 && !A.im2col && !B.im2col && res_mask == nullptr &&
                     (epi == EPI_STORE || epi == EPI_GELU || epi == EPI_DGELU || epi == EPI_F32_ATOMIC) &&
                     p.m_tiles >= 2 && p.k_iters_per_split >= g_tune[0] && (dev.num_sms & 1) == 0;
   p.nbuf = 0;
@@ -173,13 +174,6 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
 
 }  // namespace
 
-// Micro-benchmark hook: set tuning knob `knob` (see g_tune) to `value`.
-B200MM_API int b200mm_gemm_tune(int knob, int value) {
-  if (knob < 0 || knob >= 2) return B200MM_ERR_BAD_ARG;
-  g_tune[knob] = value;
-  return B200MM_OK;
-}
-
 namespace {
 
 // w_rot[ci][k-1-kh][k-1-kw][co] = w[co][kh][kw][ci]: the weight of the transposed (data-gradient) convolution
@@ -217,6 +211,23 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
   b.ptr = B; b.mn = b_mn; b.ld = ldb;
   return run_gemm(a, b, ConvGeom{}, M, N, K, epi, bias, residual, ldr, aux, ld_aux, out, ldc, out2, ld2, splits,
                   block_n, p_drop, seed, col_stats, stream);
+}
+
+// out[M,N] = bf16(A x B + (mask bit ? residual : 0)): the data gradient of a residual block's first convolution joined
+// with the identity branch's gradient dz = dout o relu_mask WITHOUT materialising dz -- `residual` is the gradient
+// w.r.t. the block's output, `mask` the 1-bit-per-element ReLU mask b200mm_batchnorm_fwd_stats wrote ([M, N / 8]
+// bytes).  Saves one full write (and the read-modify-write of an in-place accumulate) per identity block; writes are
+// the expensive direction on this part (3.9 TB/s write-only against 6.55 TB/s for a 1:1 copy).  N % 32 == 0.
+B200MM_API int b200mm_gemm_bf16_maskres(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb,
+                                        int M, int N, int K, const void* residual, long long ldr,
+                                        const unsigned char* mask, long long ld_mask, void* out, long long ldc,
+                                        void* stream) {
+  if (mask == nullptr) return B200MM_ERR_BAD_ARG;
+  Operand a, b;
+  a.ptr = A; a.mn = a_mn; a.ld = lda;
+  b.ptr = B; b.mn = b_mn; b.ld = ldb;
+  return run_gemm(a, b, ConvGeom{}, M, N, K, EPI_STORE, nullptr, residual, ldr, nullptr, 0, out, ldc, nullptr, 0, 1, 0,
+                  0.f, 0, nullptr, stream, mask, ld_mask);
 }
 
 namespace b200 {

@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import os
+
 import torch
 
 from . import ops
@@ -21,6 +23,13 @@ from .params import ParamStore
 
 STEM_K = 7 * 7 * 3
 STEM_KP = 152  # K padded to a multiple of 8 elements (TMA row stride must be a multiple of 16 bytes)
+
+
+# B200MM_MASKRES=1: never materialise the identity-branch gradient dz -- the first convolution's data gradient adds
+# (mask ? d_out : 0) in its epilogue (b200mm_gemm_bf16_maskres).  Off by default: measured on config 2 the BatchNorm
+# backward gains 0.42 ms (one write less per block) but the residual-loading epilogue costs the short-K GEMMs 0.65 ms
+# against the TMA reduce-add accumulate it replaces (30.58 vs 30.34 ms per step, profiles/step_profile_r02_maskres*.json).
+_MASKRES = os.environ.get("B200MM_MASKRES", "0") == "1"
 
 
 @dataclass
@@ -333,9 +342,12 @@ class ImageTower:
                         d_out = ops.upsample_add(d_xs, d_x1, N, Hi, Wi, ds.cin, stride)
                 continue
             x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, msk, Hi, Wi, Ho, Wo = s
-            # out = relu(bn3(y3) + idn)
-            d_y3, dz = ops.batchnorm_bwd(d_out, None, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, need_dz=True,
-                                         mask=msk)
+            # out = relu(bn3(y3) + idn).  The gradient of the pre-activation sum, dz = d_out o relu_mask, is what both
+            # branches receive; it is never written out: the consumers below take (d_out, mask) instead (one full
+            # write + read of the block's output size saved per block; writes are the slow direction of HBM here)
+            fused_id = _MASKRES
+            d_y3, dz = ops.batchnorm_bwd(d_out, None, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, mask=msk,
+                                         need_dz=not fused_id)
             ops.linear_wgrad(d_y3, a2, c3.dw)
             d_a2 = ops.linear_dgrad(d_y3, c3.w)
             d_y2, _ = ops.batchnorm_bwd(d_a2, None, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, beta=c2.b)
@@ -350,10 +362,18 @@ class ImageTower:
             d_y1, _ = ops.batchnorm_bwd(d_a1, None, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True, beta=c1.b)
             ops.linear_wgrad(d_y1, x, c1.dw)
             if ds is None:
-                # identity branch: dz += d_y1 W1 in place (TMA reduce-add stores; the residual is never loaded)
-                d_out = ops.linear_dgrad(d_y1, c1.w, residual=dz, out=dz)
+                if fused_id:
+                    # identity branch joins the data gradient in the epilogue: d_out' = d_y1 W1 + (mask ? d_out : 0)
+                    d_out = ops.linear_dgrad(d_y1, c1.w, residual=d_out, residual_mask=msk)
+                else:
+                    # dz += d_y1 W1 in place (TMA reduce-add stores; the residual is never loaded)
+                    d_out = ops.linear_dgrad(d_y1, c1.w, residual=dz, out=dz)
             else:
-                d_yd, _ = ops.batchnorm_bwd(dz, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=False)
+                if fused_id:
+                    # downsample branch: its BatchNorm has no ReLU of its own, the block's mask turns d_out into dz on load
+                    d_yd, _ = ops.batchnorm_bwd(d_out, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=True, mask=msk)
+                else:
+                    d_yd, _ = ops.batchnorm_bwd(dz, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=False)
                 ops.linear_wgrad(d_yd, xs, ds.dw)
                 d_x1 = ops.linear_dgrad(d_y1, c1.w)
                 if stride == 1:

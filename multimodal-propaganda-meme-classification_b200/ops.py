@@ -132,14 +132,29 @@ def linear_gelu_fwd(x, w, bias):
     return z, a
 
 
-def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None):
-    """dx = dy @ w (+residual), or dx = (dy @ w) * gelu'(gelu_z).  dy [M,N], w [N,K] -> dx [M,K]."""
+def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None, residual_mask=None):
+    """dx = dy @ w (+residual), or dx = (dy @ w) * gelu'(gelu_z).  dy [M,N], w [N,K] -> dx [M,K].
+    residual_mask (uint8 [M, K/8], 1 bit per element, from batchnorm_fwd(want_mask=True)): only the residual elements
+    whose bit is set are added -- the identity-branch gradient dout o relu_mask of a residual block, never materialised."""
     M, N = dy.shape
     K = w.shape[1]
     if out is None:
         out = torch.empty(M, K, device=dy.device, dtype=bf16)
     if gelu_z is not None:
         return gemm_raw(dy, False, w, True, M, K, N, out, epi=EPI_DGELU, aux=gelu_z)
+    if residual_mask is not None:
+        assert residual is not None and residual.data_ptr() != out.data_ptr()
+        args = ("b200mm_gemm_bf16_maskres", _p(dy), 0, dy.stride(0), _p(w), 1, w.stride(0), M, K, N, _p(residual),
+                residual.stride(0), _p(residual_mask), residual_mask.stride(0), _p(out), out.stride(0), _s())
+        if _gemm_profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call(*args)
+            e1.record()
+            _gemm_profile.append((e0, e1, 2.0 * M * N * K, 2.0 * (M * N + N * K + 2 * M * K) + M * K / 8.0))
+        else:
+            _lib.call(*args, key=(M, K, N, 0, 1, "maskres", 1))
+        return out
     return gemm_raw(dy, False, w, True, M, K, N, out, epi=EPI_STORE, residual=residual)
 
 
@@ -542,12 +557,27 @@ def batchnorm_eval(x, gamma, beta, running_mean, running_var, *, residual=None, 
     return out
 
 
+BN_FUSED_MB = [0]     # mirror of b200mm_tune knob 2 (set both through set_bn_fused_mb)
+_bn_fused_env = [os.environ.get("B200MM_BN_FUSED_MB")]   # A/B switch, applied at the first call
+
+
+def set_bn_fused_mb(mb: int) -> None:
+    """Largest tensor (MB) whose BatchNorm backward runs as one cooperative launch; 0 = always the two-kernel path."""
+    _lib.load().b200mm_tune(2, int(mb))
+    BN_FUSED_MB[0] = int(mb)
+
+
 def batchnorm_bwd(dout, out, x, mean, rstd, gamma, dgamma, dbeta, *, relu=True, need_dz=False, beta=None, mask=None):
     """ReLU mask: ``mask`` (1 bit / element, from batchnorm_fwd(want_mask=True)), else ``out``, else recomputed from x
     (pass beta; only valid without a residual)."""
     M, C = x.shape
+    if _bn_fused_env[0] is not None:
+        set_bn_fused_mb(int(_bn_fused_env[0]))
+        _bn_fused_env[0] = None
     dx = torch.empty_like(x)
     dz = torch.empty_like(x) if need_dz else None
+    if (out is None or not relu or mask is not None) and M * C * 2 <= (BN_FUSED_MB[0] << 20):
+        _lib.LAUNCHES[0] -= 1      # one cooperative launch instead of reduce + apply (mirror of b200mm_batchnorm_bwd)
     _lib.call("b200mm_batchnorm_bwd", _p(dout), _p(out), _p(x), M, C, _p(mean), _p(rstd), _p(gamma), _p(beta),
               _p(mask), int(relu),
               _p(dx), _p(dz), _p(dgamma), _p(dbeta), _p(BNScratch.get(x.device, C)), _s(),

@@ -26,7 +26,7 @@ def timeit(fn, iters=8):
 
 
 def tune(knob, v):
-    assert lib.b200mm_gemm_tune(knob, v) == 0
+    assert lib.b200mm_tune(knob, v) == 0
 
 
 # (M, N, K, b_mn, mode): mode "stats" = forward conv (column statistics), "plain" = dgrad store, "acc" = dgrad accumulating

@@ -48,9 +48,9 @@ for (M, N, K, mode) in [(128 * 148, 256, 64, "plain"), (128 * 148, 256, 256, "pl
     te, tg = b2b(fn), graph_b2b(fn)
     extra = ""
     if "ab" in sys.argv:
-        lib.b200mm_gemm_tune(1, 0)
+        lib.b200mm_tune(1, 0)
         extra = f" | B-resident off {graph_b2b(fn):6.1f}"
-        lib.b200mm_gemm_tune(1, 1)
+        lib.b200mm_tune(1, 1)
     fl = 2.0 * M * N * K
     by = 2.0 * (M * K + N * K + M * N)
     print(f"[{M:7d} x{N:5d} x{K:5d}] {mode:5s} eager {te:7.1f} us  graph {tg:7.1f} us   ({fl / tg / 1e6:6.0f} TF/s, {by / tg / 1e3:6.0f} GB/s; "

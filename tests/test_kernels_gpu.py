@@ -386,6 +386,52 @@ def test_batchnorm_fwd_bwd(ops, cuda_device, M, C, relu, use_res):
     assert rel(ev, ref_ev) < 1e-2
 
 
+@pytest.mark.parametrize("M,C,mode", [(50176, 256, "recompute"), (12544, 512, "mask"), (3001, 64, "recompute"),
+                                      (777, 2048, "mask"), (20000, 128, "plain")])
+def test_batchnorm_bwd_single_launch_matches_two_pass(ops, cuda_device, M, C, mode):
+    """BatchNorm backward as ONE cooperative launch (reduce -> grid barrier -> apply, L2-resident tensors) against the
+    two-kernel path and against autograd: same dx / dz element for element up to the summation order of the column
+    sums, last rows included."""
+    torch.manual_seed(17)
+    x = (torch.randn(M, C, device=cuda_device) * 1.5 + 0.3).to(bf16)
+    g = torch.rand(C, device=cuda_device) + 0.5
+    b = torch.randn(C, device=cuda_device) * 0.3
+    res = torch.randn(M, C, device=cuda_device).to(bf16) if mode == "mask" else None
+    st = torch.zeros(2 * C, device=cuda_device)
+    st[:C], st[C:] = x.float().sum(0), (x.float() ** 2).sum(0)
+    rm, rv = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+    relu = mode != "plain"
+    out, mean, rstd, msk = ops.batchnorm_fwd(x, g, b, rm, rv, residual=res, relu=relu, col_stats=st, want_mask=True)
+    dout = torch.randn(M, C, device=cuda_device).to(bf16)
+    kw = dict(relu=relu, need_dz=mode == "mask", mask=msk if mode == "mask" else None,
+              beta=b if mode == "recompute" else None)
+    got = {}
+    try:
+        for name, mb in (("fused", 52), ("two_pass", 0)):
+            ops.set_bn_fused_mb(mb)
+            dg, db = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+            dx, dz = ops.batchnorm_bwd(dout, None, x, mean, rstd, g, dg, db, **kw)
+            got[name] = (dx, dz, dg, db)
+    finally:
+        ops.set_bn_fused_mb(0)
+    (dx, dz, dg, db), (dx2, dz2, dg2, db2) = got["fused"], got["two_pass"]
+    assert rel(dg, dg2) < 1e-5 and rel(db, db2) < 1e-5
+    assert rel(dx, dx2) < 1e-3 and (dx.float() - dx2.float()).abs().max().item() < 0.05
+    assert (dx[-1].float() - dx2[-1].float()).abs().max().item() < 0.05
+    if dz is not None:
+        assert torch.equal(dz, dz2)
+    # autograd reference
+    xf = x.float().requires_grad_(True)
+    gf, bff = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.batch_norm(xf, None, None, gf, bff, True, 0.1, 1e-5)
+    if res is not None:
+        y = y + res.float()
+    if relu:
+        y = torch.relu(y)
+    y.backward(dout.float())
+    assert rel(dx, xf.grad) < 2e-2 and rel(dg, gf.grad) < 2e-2 and rel(db, bff.grad) < 2e-2
+
+
 @pytest.mark.parametrize("M,N,K", [(4096, 64, 152), (3000, 256, 64), (1000, 512, 256), (777, 2048, 512), (5000, 128, 1152)])
 def test_gemm_column_statistics_feed_batchnorm(ops, cuda_device, M, N, K):
     """The convolution epilogue's column sums (over the stored bf16 outputs) and the one-pass BatchNorm they feed,
@@ -409,6 +455,32 @@ def test_gemm_column_statistics_feed_batchnorm(ops, cuda_device, M, N, K):
     assert rel(rm, rm2) < 1e-4 and rel(rv, rv2) < 1e-4
     ref = torch.relu(F.batch_norm(yf, None, None, g, b, True, 0.1, 1e-5))
     assert rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(3000, 256, 64), (1000, 512, 128), (20000, 1024, 256), (777, 2048, 512), (300, 64, 256)])
+def test_gemm_masked_residual_joins_identity_gradient(ops, cuda_device, M, N, K):
+    """dx = dy W + (ReLU-mask bit ? d_out : 0): the identity-branch gradient of a residual block is added in the data
+    gradient's epilogue from (d_out, 1-bit mask) -- exact element selection, checked on every element incl. the last
+    rows / columns, and against the two-step path (BatchNorm backward's dz, then the in-place accumulate)."""
+    torch.manual_seed(31)
+    dy = torch.randn(M, K, device=cuda_device).to(bf16)              # gradient w.r.t. the first convolution's output
+    w = (torch.randn(K, N, device=cuda_device) / K ** 0.5).to(bf16)   # its weight [Cout = K, Cin = N]
+    d_out = torch.randn(M, N, device=cuda_device).to(bf16)
+    keep = torch.rand(M, N, device=cuda_device) < 0.6
+    bits = keep.view(M, N // 8, 8).to(torch.uint8)
+    mask = (bits << torch.arange(8, device=cuda_device, dtype=torch.uint8)).sum(-1).to(torch.uint8).contiguous()
+    got = ops.linear_dgrad(dy, w, residual=d_out, residual_mask=mask)
+    ref = dy.float() @ w.float() + torch.where(keep, d_out.float(), torch.zeros((), device=cuda_device))
+    assert rel(got, ref) < 4e-3
+    err = (got.float() - ref).abs()
+    assert err.max().item() < 0.06 and err[-1].max().item() < 0.06 and err[:, -1].max().item() < 0.06
+    # where dy W is exactly representable (dy = 0) the selection itself is exact
+    got0 = ops.linear_dgrad(torch.zeros_like(dy), w, residual=d_out, residual_mask=mask)
+    assert torch.equal(got0, torch.where(keep, d_out, torch.zeros((), device=cuda_device, dtype=bf16)))
+    # the path it replaces: dz materialised, then accumulated into in place
+    dz = torch.where(keep, d_out, torch.zeros((), device=cuda_device, dtype=bf16)).contiguous()
+    two_step = ops.linear_dgrad(dy, w, residual=dz, out=dz)
+    assert rel(got, two_step) < 6e-3      # (the in-place path rounds acc to bf16 before the add in L2)
 
 
 def _nhwc(x):  # NCHW fp32 -> [N*H*W, C] bf16
