@@ -516,7 +516,8 @@ def run_engine(args):
                 "hbm_bound_launches": {"launches": h["launches"], "ms": h["ms"],
                                        "achieved_gbs": h["bytes"] / (h["ms"] * 1e-3) / 1e9 if h["ms"] else None,
                                        "frac_of_hbm_peak": (h["bytes"] / (h["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"])
-                                       if h["ms"] else None, "ridge_flop_per_byte": ridge},
+                                       if h["ms"] else None, "ridge_flop_per_byte": ridge,
+                                       "bytes_written_share": h["bytes_written"] / h["bytes"] if h["bytes"] else None},
                 "whole_step_tflops": value / world * wl["gflop"] / 1e3,
                 "whole_step_frac_of_peak": value / world * wl["gflop"] / 1e3 / pk["bf16_tflops_sustained"]}
 

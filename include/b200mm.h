@@ -134,6 +134,13 @@ int b200mm_batchnorm_bwd(const void* dout, const void* out, const void* x, long 
                          const float* rstd, const float* gamma, const float* beta, const unsigned char* relu_mask,
                          int relu, void* dx, void* dz_out, float* dgamma, float* dbeta, float* scratch, void* stream);
 int b200mm_maxpool3x3s2_fwd(const void* x, int N, int H, int W, int C, void* out, void* argmax, void* stream);
+/* Stem tail in one pass: out = maxpool3x3s2(relu(BN_train(x))) straight from the convolution output x [N,H,W,C] whose
+ * column statistics are in col_stats; the normalised activation is never materialised.  Bit-identical to
+ * b200mm_batchnorm_fwd_stats + b200mm_maxpool3x3s2_fwd.  Replaces bn1 / relu / maxpool of
+ * torchvision/models/resnet.py:268-271. */
+int b200mm_bn_relu_maxpool_fwd(const void* x, int N, int H, int W, int C, const float* col_stats, const float* gamma,
+                               const float* beta, float eps, float momentum, void* out, void* argmax, float* mean_out,
+                               float* rstd_out, float* running_mean, float* running_var, void* stream);
 int b200mm_maxpool3x3s2_bwd(const void* dout, const void* argmax, int N, int H, int W, int C, void* dx, void* stream);
 int b200mm_avgpool_fwd(const void* x, int N, int HW, int C, void* out, void* stream);
 int b200mm_avgpool_bwd(const void* dout, int N, int HW, int C, void* dx, void* stream);

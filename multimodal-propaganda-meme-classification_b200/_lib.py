@@ -160,6 +160,8 @@ declare("b200mm_batchnorm_bwd", [c_ptr, c_ptr, c_ptr, c_longlong, c_int, c_ptr, 
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_maxpool3x3s2_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr])
 declare("b200mm_maxpool3x3s2_bwd", [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_bn_relu_maxpool_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_float, c_float, c_ptr,
+                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_avgpool_fwd", [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_avgpool_bwd", [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr])
 declare("b200mm_im2col_nhwc", [c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr])

@@ -27,10 +27,9 @@ namespace b200 {
 // CTAS = 2: a CTA pair (cluster of two, cta_group::2) computes a 256 x BN tile with ONE MMA stream -- each CTA stages its
 // own 128 rows of A and only HALF of the B tile, so the tensor core's shared-memory reads per FLOP drop by a third
 // (the single-CTA 128 x 256 tile needs 96 B/clk of the 128 B/clk shared-memory port at full MMA rate).
-// EW = epilogue warps: 8 (two column halves per TMEM lane quarter), or 16 (four column quarters: one staged box per
-// warp and tile) for the short-K convolution shapes, whose tiles are bound by the epilogue's instruction latency --
-// measured on [50176 x 1024 x 256]: the MMA thread spends its time waiting for a free accumulator while the 8
-// epilogue warps (2 per scheduler) need ~3600 cycles per 128 x 256 tile against 2048 cycles of tensor time.
+// EW = epilogue warps: 8 (two column halves per TMEM lane quarter).  16 (four column quarters, one staged box per warp
+// and tile) was measured on the short-K convolution shapes and did not pay (-10 % at [200704 x 512 x 128], +15 % at
+// [50176 x 1024 x 256], profiles/gemm_launch_cost_r02.log): only the 8-warp form is instantiated.
 template <int BN, int CTAS = 1, int EW = GEMM_EPI_WARPS>
 struct GemmCfg {
   static constexpr int THREADS = 64 + EW * 32;
@@ -61,10 +60,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // B-resident mode (single CTA, short unsplit K, every tile of this CTA in the same column block): the whole B tile
-  // [BN x K] is loaded ONCE into a resident area and the ring carries A only.  The short-K convolution GEMMs are bound
-  // by the SM's L2 port (~64 B/clk: 192 KB in + 64 KB out per 128 x 256 x 256 tile = 4096 cycles against 2048 cycles of
-  // tensor time; ring depth, CTA pairs, more epilogue warps and L2 prefetch all left them at ~4800 cycles per tile);
-  // with B resident a tile moves 64 KB in + 64 KB out.
+  // [BN x K] is loaded ONCE into a resident area and the ring carries A only (a 128 x 256 x 256 tile then moves 64 KB
+  // in + 64 KB out instead of 192 KB in).  Measured on the ResNet 1x1-convolution shapes (L2 flushed): 39.9 -> 37.9 us
+  // at [50176 x 1024 x 256], 52.2 -> 38.9 us at the ragged [50000 x 1000 x 200], unchanged elsewhere
+  // (profiles/conv_gemm_variants_r02.log).  What paces these shapes is the epilogue / store side: with the epilogue
+  // switched off the same launches take 18 us instead of 33, with the MMAs switched off 29 us
+  // (profiles/gemm_launch_cost_r02.log); ring depth, CTA pairs, 16 epilogue warps and an L2 prefetch of the next A
+  // tile all left the time within 5 %.
   const bool BRES = !PAIR && p.b_resident != 0;
   const int stage_stride = BRES ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
   uint8_t* ring = smem + (BRES ? p.k_iters * Cfg::B_BYTES : 0);
@@ -336,6 +338,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const bool has_bias = p.bias != nullptr;
     // EPI_STORE_STATS: per-lane running column sums (two adjacent columns per staged box), flushed with fp32
     // reductions when the CTA moves to another column block and at the end
+    // EPI_DGELU with p.col_stats: column SUMS only, into col_stats[0..N) -- the bias gradient of the linear layer whose
+    // output gradient this GEMM produces (the separate column-sum pass re-read the whole [M, N] tensor)
+    constexpr bool COLSUM_EPI = EPI == EPI_STORE_STATS || EPI == EPI_DGELU;
+    const bool do_colsum = EPI == EPI_STORE_STATS || (EPI == EPI_DGELU && p.col_stats != nullptr);
     float st_s[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, st_q[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     int st_nblk = -1;
     auto stats_flush = [&]() {
@@ -346,7 +352,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int col = st_nblk * BN + half * HALF_COLS + b * BOX_W + 2 * (BOX_W == 64 ? lane : (lane & 15));
         if (col < p.N) {
           asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p.col_stats + col), "f"(st_s[b][0]), "f"(st_s[b][1]) : "memory");
-          asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p.col_stats + p.N + col), "f"(st_q[b][0]), "f"(st_q[b][1]) : "memory");
+          if constexpr (EPI == EPI_STORE_STATS)
+            asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p.col_stats + p.N + col), "f"(st_q[b][0]), "f"(st_q[b][1]) : "memory");
         }
         st_s[b][0] = st_s[b][1] = st_q[b][0] = st_q[b][1] = 0.f;
       }
@@ -361,8 +368,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int w = w_first; w < num_work; w += w_step) {
       const int m_blk = tile_row(m_unit);
-      if constexpr (EPI == EPI_STORE_STATS) {
-        if (n_blk != st_nblk) { stats_flush(); st_nblk = n_blk; }
+      if constexpr (COLSUM_EPI) {
+        if (do_colsum && n_blk != st_nblk) { stats_flush(); st_nblk = n_blk; }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after_sync();
@@ -545,7 +552,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               }
               tma_store_commit();
             }
-            if constexpr (EPI == EPI_STORE_STATS) {
+            if constexpr (COLSUM_EPI) if (do_colsum) {
               // column sums over the 32 staged rows: lane l owns the 4-byte word (2 columns) l of every row --
               // conflict-free under either swizzle; rows past M were zero-filled by TMA and add nothing
               float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -633,7 +640,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       advance(m_unit, n_blk);
       while (m_unit >= m_units) m_unit -= m_units;   // next K split of the same tile grid
     }
-    if constexpr (EPI == EPI_STORE_STATS) stats_flush();
+    if constexpr (COLSUM_EPI) {
+      if (do_colsum) stats_flush();
+    }
     if constexpr (BF16_OUT) {
       // shared memory must outlive the last bulk store's READ of it; the global writes themselves complete with the grid
       // (waiting for them here cost ~1 us of every launch's tail)

@@ -64,8 +64,10 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
   if (splits > 1 && epi != EPI_F32_ATOMIC) return B200MM_ERR_BAD_ARG;
   if (epi == EPI_GELU && out2 == nullptr) return B200MM_ERR_BAD_ARG;
   if (epi == EPI_DGELU && (aux == nullptr || bias != nullptr)) return B200MM_ERR_BAD_ARG;
-  // column statistics ride on the plain store epilogue only (convolution outputs: no bias, residual or dropout)
-  if (col_stats != nullptr && (epi != EPI_STORE || bias != nullptr || residual != nullptr || p_drop > 0.f))
+  // column statistics ride on the plain store epilogue (convolution outputs: no bias, residual or dropout); with the
+  // dGELU epilogue col_stats is fp32 [N] and receives the column sums only (bias gradient of the first FFN layer)
+  if (col_stats != nullptr && epi != EPI_DGELU &&
+      (epi != EPI_STORE || bias != nullptr || residual != nullptr || p_drop > 0.f))
     return B200MM_ERR_BAD_ARG;
   if ((A.im2col || B.im2col) && (cg.C % 64 != 0 || cg.ksize < 1)) return B200MM_ERR_BAD_ARG;
   // masked residual (identity-branch gradient): plain store mode with a residual, 32 columns per mask word
@@ -120,9 +122,8 @@ int run_gemm(const Operand& A, const Operand& B, const ConvGeom& cg, int M, int 
     const char* e = std::getenv("B200MM_GEMM_PAIR");
     return e == nullptr || e[0] != '0';
   }();
-  // Short-K 1x1-convolution shapes included: at K <= 512 the single-CTA kernel is bound by L2 -> SM traffic, not by
-  // HBM (every 128 x 256 tile re-reads its whole 256-row B tile from L2: 205 MB per ResNet bottleneck GEMM whatever
-  // the layer, ~10 TB/s measured at the L2's limit); the pair halves the B traffic.
+  // (the statistics / accumulate epilogues are served too; K < 512 stays on the single-CTA kernel: the pair measured
+  // within +-5 % of it on the short-K convolution shapes, profiles/conv_gemm_variants_r02.log)
   const bool pair = pair_enabled && bn == 256 && !A.im2col && !B.im2col && res_mask == nullptr &&
                     (epi == EPI_STORE || epi == EPI_GELU || epi == EPI_DGELU || epi == EPI_F32_ATOMIC) &&
                     p.m_tiles >= 2 && p.k_iters_per_split >= g_tune[0] && (dev.num_sms & 1) == 0;
@@ -216,8 +217,9 @@ B200MM_API int b200mm_gemm_bf16(const void* A, int a_mn, long long lda, const vo
 // out[M,N] = bf16(A x B + (mask bit ? residual : 0)): the data gradient of a residual block's first convolution joined
 // with the identity branch's gradient dz = dout o relu_mask WITHOUT materialising dz -- `residual` is the gradient
 // w.r.t. the block's output, `mask` the 1-bit-per-element ReLU mask b200mm_batchnorm_fwd_stats wrote ([M, N / 8]
-// bytes).  Saves one full write (and the read-modify-write of an in-place accumulate) per identity block; writes are
-// the expensive direction on this part (3.9 TB/s write-only against 6.55 TB/s for a 1:1 copy).  N % 32 == 0.
+// bytes).  Saves one full write (and the read-modify-write of an in-place accumulate) per identity block, but the
+// per-lane residual loads make the epilogue slower than the TMA reduce-add accumulate it replaces (see image_tower.py:
+// off by default).  N % 32 == 0.
 B200MM_API int b200mm_gemm_bf16_maskres(const void* A, int a_mn, long long lda, const void* B, int b_mn, long long ldb,
                                         int M, int N, int K, const void* residual, long long ldr,
                                         const unsigned char* mask, long long ld_mask, void* out, long long ldc,

@@ -225,10 +225,16 @@ class ImageTower:
         else:        # other stem widths / very wide images: explicit lowering
             cols, H1, W1 = ops.im2col_nchw_f32(image, 7, 2, 3, STEM_KP)
             c0 = ops.linear_fwd(cols, st.w, col_stats=self._stats_of(st))
-        a0, m0, r0 = self._bn(st, c0, training)
-        x, arg, H2, W2 = ops.maxpool_fwd(a0, N, H1, W1, st.cout)
         if training:
-            sv["stem"] = (cols, direct, c0, a0, m0, r0, arg, H1, W1)
+            # bn1 + relu + maxpool in one pass: the 112 x 112 activation between them is not needed again (the
+            # BatchNorm backward recomputes the ReLU mask from c0) and is never written
+            x, arg, H2, W2, m0, r0 = ops.bn_relu_maxpool_fwd(c0, N, H1, W1, st.cout, st.g, st.b, st.rm, st.rv,
+                                                             self._stats_of(st), eps=self.cfg.bn_eps,
+                                                             momentum=self.cfg.bn_momentum)
+            sv["stem"] = (cols, direct, c0, None, m0, r0, arg, H1, W1)
+        else:
+            a0, m0, r0 = self._bn(st, c0, training)
+            x, arg, H2, W2 = ops.maxpool_fwd(a0, N, H1, W1, st.cout)
         Hc, Wc = H2, W2
         for blk in self.blocks:
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
@@ -344,7 +350,7 @@ class ImageTower:
             x, y1, a1, m1, r1, y2, a2, m2, r2, y3, m3, r3, xs, yd, md, rd, msk, Hi, Wi, Ho, Wo = s
             # out = relu(bn3(y3) + idn).  The gradient of the pre-activation sum, dz = d_out o relu_mask, is what both
             # branches receive; it is never written out: the consumers below take (d_out, mask) instead (one full
-            # write + read of the block's output size saved per block; writes are the slow direction of HBM here)
+            # write + read of the block's output size saved per block)
             fused_id = _MASKRES
             d_y3, dz = ops.batchnorm_bwd(d_out, None, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, mask=msk,
                                          need_dz=not fused_id)

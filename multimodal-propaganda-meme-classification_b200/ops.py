@@ -63,17 +63,19 @@ def profile_gemm(step_fn, steps: int = 2, ridge: float = 208.0):
         rec = _gemm_profile
     finally:
         _gemm_profile = None
-    ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
-    fl = sum(f for _, _, f, _ in rec)
+    ms = sum(r[0].elapsed_time(r[1]) for r in rec)
+    fl = sum(r[2] for r in rec)
     # split by the roofline that bounds each launch: arithmetic intensity above / below the ridge point
-    split = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}
-    for a, b, f, by in rec:
+    split = {"tensor": [0.0, 0.0, 0.0, 0, 0.0], "hbm": [0.0, 0.0, 0.0, 0, 0.0]}
+    for a, b, f, by, wby in rec:
         k = "tensor" if f / by >= ridge else "hbm"
         split[k][0] += a.elapsed_time(b)
         split[k][1] += f
         split[k][2] += by
         split[k][3] += 1
-    detail = {k: {"ms": v[0] / steps, "flops": v[1] / steps, "bytes": v[2] / steps, "launches": v[3] // steps}
+        split[k][4] += wby
+    detail = {k: {"ms": v[0] / steps, "flops": v[1] / steps, "bytes": v[2] / steps, "launches": v[3] // steps,
+                  "bytes_written": v[4] / steps}
               for k, v in split.items()}
     return ms / steps, fl / steps, len(rec) // steps, detail
 
@@ -93,7 +95,8 @@ def gemm_raw(A, a_mn, B, b_mn, M, N, K, out, *, epi=EPI_STORE, bias=None, residu
         nbytes = 2.0 * (M * K + N * K) + M * N * (8.0 if epi in (EPI_F32, EPI_F32_ATOMIC) else (4.0 if epi == EPI_GELU else 2.0))
         if residual is not None or aux is not None:
             nbytes += 2.0 * M * N
-        _gemm_profile.append((e0, e1, 2.0 * M * N * K, nbytes))
+        _gemm_profile.append((e0, e1, 2.0 * M * N * K, nbytes,
+                              M * N * (8.0 if epi in (EPI_F32, EPI_F32_ATOMIC) else (4.0 if epi == EPI_GELU else 2.0))))
         return out
     _lib.call("b200mm_gemm_bf16", _p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, epi,
               _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
@@ -132,7 +135,10 @@ def linear_gelu_fwd(x, w, bias):
     return z, a
 
 
-def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None, residual_mask=None):
+FOLD_BIAS_GRAD = os.environ.get("B200MM_FOLD_BIAS_GRAD", "1") != "0"
+
+
+def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None, residual_mask=None, bias_grad=None):
     """dx = dy @ w (+residual), or dx = (dy @ w) * gelu'(gelu_z).  dy [M,N], w [N,K] -> dx [M,K].
     residual_mask (uint8 [M, K/8], 1 bit per element, from batchnorm_fwd(want_mask=True)): only the residual elements
     whose bit is set are added -- the identity-branch gradient dout o relu_mask of a residual block, never materialised."""
@@ -141,7 +147,13 @@ def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None, residual_mask=N
     if out is None:
         out = torch.empty(M, K, device=dy.device, dtype=bf16)
     if gelu_z is not None:
-        return gemm_raw(dy, False, w, True, M, K, N, out, epi=EPI_DGELU, aux=gelu_z)
+        # bias_grad (fp32 [K], accumulated): column sums of the result = the bias gradient of the layer that produced z
+        if bias_grad is not None and not FOLD_BIAS_GRAD:      # A/B switch: the separate column-sum pass
+            gemm_raw(dy, False, w, True, M, K, N, out, epi=EPI_DGELU, aux=gelu_z)
+            colsum(out, bias_grad)
+            return out
+        return gemm_raw(dy, False, w, True, M, K, N, out, epi=EPI_DGELU, aux=gelu_z, col_stats=bias_grad)
+    assert bias_grad is None
     if residual_mask is not None:
         assert residual is not None and residual.data_ptr() != out.data_ptr()
         args = ("b200mm_gemm_bf16_maskres", _p(dy), 0, dy.stride(0), _p(w), 1, w.stride(0), M, K, N, _p(residual),
@@ -151,7 +163,7 @@ def linear_dgrad(dy, w, *, residual=None, gelu_z=None, out=None, residual_mask=N
             e0.record()
             _lib.call(*args)
             e1.record()
-            _gemm_profile.append((e0, e1, 2.0 * M * N * K, 2.0 * (M * N + N * K + 2 * M * K) + M * K / 8.0))
+            _gemm_profile.append((e0, e1, 2.0 * M * N * K, 2.0 * (M * N + N * K + 2 * M * K) + M * K / 8.0, 2.0 * M * K))
         else:
             _lib.call(*args, key=(M, K, N, 0, 1, "maskres", 1))
         return out
@@ -219,7 +231,7 @@ def conv_fwd(x, N, H, W, C, w, ksize, stride, pad, *, residual=None, relu=False,
     if prof is not None:
         e1.record()
         M_, K_ = N * P * Q, ksize * ksize * C
-        prof.append((e0, e1, 2.0 * M_ * Cout * K_, 2.0 * (N * H * W * C + Cout * K_ + M_ * Cout)))
+        prof.append((e0, e1, 2.0 * M_ * Cout * K_, 2.0 * (N * H * W * C + Cout * K_ + M_ * Cout), 2.0 * M_ * Cout))
     return out, P, Q
 
 
@@ -241,7 +253,8 @@ def conv_wgrad(dy, x, N, H, W, C, ksize, stride, pad, dw):
     if prof is not None:
         e1.record()
         K_ = ksize * ksize * C
-        prof.append((e0, e1, 2.0 * pixels * Cout * K_, 2.0 * (pixels * Cout + N * H * W * C) + 8.0 * Cout * K_))
+        prof.append((e0, e1, 2.0 * pixels * Cout * K_, 2.0 * (pixels * Cout + N * H * W * C) + 8.0 * Cout * K_,
+                     8.0 * Cout * K_))
     return dw
 
 
@@ -591,6 +604,19 @@ def maxpool_fwd(x, N, H, W, C):
     arg = torch.empty(N * Ho * Wo, C, device=x.device, dtype=torch.uint8)
     _lib.call("b200mm_maxpool3x3s2_fwd", _p(x), N, H, W, C, _p(out), _p(arg), _s())
     return out, arg, Ho, Wo
+
+
+def bn_relu_maxpool_fwd(x, N, H, W, C, gamma, beta, running_mean, running_var, col_stats, *, eps=1e-5, momentum=0.1):
+    """maxpool3x3s2(relu(BN_train(x))) in one pass from the convolution output x [N*H*W, C] and its column statistics;
+    returns (pooled, argmax, Ho, Wo, mean, rstd) -- the normalised activation itself is never written."""
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(N * Ho * Wo, C, device=x.device, dtype=bf16)
+    arg = torch.empty(N * Ho * Wo, C, device=x.device, dtype=torch.uint8)
+    mean = torch.empty(C, device=x.device, dtype=f32)
+    rstd = torch.empty(C, device=x.device, dtype=f32)
+    _lib.call("b200mm_bn_relu_maxpool_fwd", _p(x), N, H, W, C, _p(col_stats), _p(gamma), _p(beta), float(eps),
+              float(momentum), _p(out), _p(arg), _p(mean), _p(rstd), _p(running_mean), _p(running_var), _s())
+    return out, arg, Ho, Wo, mean, rstd
 
 
 def maxpool_bwd(dout, arg, N, H, W, C):

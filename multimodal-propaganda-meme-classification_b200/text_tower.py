@@ -267,9 +267,9 @@ class TextTower:
             d_lin2 = d_opre_m if d_opre_m is not None else d_opre
             ops.linear_wgrad(d_lin2, a, L["dw2"])
             ops.colsum(d_lin2, L["db2"])
-            dz = ops.linear_dgrad(d_lin2, L["w2"], gelu_z=z)               # (d_lin2 W2) * gelu'(z)
+            # (d_lin2 W2) * gelu'(z); the epilogue also accumulates the result's column sums = lin1's bias gradient
+            dz = ops.linear_dgrad(d_lin2, L["w2"], gelu_z=z, bias_grad=L["db1"])
             ops.linear_wgrad(dz, y, L["dw1"])
-            ops.colsum(dz, L["db1"])
             dy = ops.linear_dgrad(dz, L["w1"], residual=d_opre)            # + residual path of LN2's input
             # y = LN1(y_pre);  y_pre = dropout(ctx Wo^T + bo) + x   (the dropout exists in BERT / RoBERTa only)
             d_ypre, d_ypre_m = ops.layernorm_bwd(dy, y_pre, m1, r1, L["g1"], L["dg1"], L["dbe1"],

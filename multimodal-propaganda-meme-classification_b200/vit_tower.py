@@ -251,9 +251,8 @@ class ViTTower:
             # x3 = a W2^T + b2 + x2
             ops.linear_wgrad(dx, a, L["dw2"])
             ops.colsum(dx, L["db2"])
-            dz = ops.linear_dgrad(dx, L["w2"], gelu_z=z)
+            dz = ops.linear_dgrad(dx, L["w2"], gelu_z=z, bias_grad=L["db1"])   # + column sums = fc1's bias gradient
             ops.linear_wgrad(dz, h2, L["dw1"])
-            ops.colsum(dz, L["db1"])
             dh2 = ops.linear_dgrad(dz, L["w1"])
             dx2, _ = ops.layernorm_bwd(dh2, x2, m2, r2, L["g2"], L["dg2"], L["dbe2"], addend=dx)
             # x2 = ctx Wo^T + bo + x

@@ -1,5 +1,7 @@
-"""HBM bandwidth by traffic mix on this GPU (CUDA-graph replays of 20 back-to-back kernels): write-only (fill), read-only
-(sum), copy (1:1), and 1 read : 4 writes (the traffic of a short-K convolution GEMM)."""
+"""HBM bandwidth by traffic mix on this GPU (CUDA-graph replays of 20 back-to-back torch kernels): fill, copy, sum.
+CAUTION when reading the numbers: torch's bf16 fill kernel stores 8 bytes per thread and reaches 3.9 TB/s, an fp32
+zero_() (16-byte stores) reaches 6.9 TB/s -- the low figure is that kernel's, not a write limit of the HBM (it was
+briefly mistaken for one; profiles/membw_r02.log)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,7 +27,8 @@ for mb in (103, 411, 1024):
     n = mb * 1024 * 1024 // 2
     a = torch.empty(n, device=dev, dtype=torch.bfloat16)
     b = torch.empty(n, device=dev, dtype=torch.bfloat16)
-    q = torch.empty(n // 4, device=dev, dtype=torch.bfloat16)
+    f32 = torch.empty(n // 2, device=dev, dtype=torch.float32)
+    t = graph_b2b(lambda: f32.zero_()); print(f"{mb:5d} MB fp32 zero_ (write only) {t:7.1f} us  {mb * 1.048576 / t * 1e3:6.0f} GB/s")
     t = graph_b2b(lambda: a.fill_(1.0)); print(f"{mb:5d} MB fill (write only)      {t:7.1f} us  {mb * 1.048576 / t * 1e3:6.0f} GB/s")
     t = graph_b2b(lambda: a.zero_()); print(f"{mb:5d} MB zero_ (write only)     {t:7.1f} us  {mb * 1.048576 / t * 1e3:6.0f} GB/s")
     t = graph_b2b(lambda: b.copy_(a)); print(f"{mb:5d} MB copy (1 read : 1 write) {t:7.1f} us  {2 * mb * 1.048576 / t * 1e3:6.0f} GB/s")

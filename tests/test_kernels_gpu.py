@@ -55,6 +55,12 @@ def test_gemm_dgrad_wgrad(ops, cuda_device, M, N, K):
     zf = z.float().requires_grad_(True)
     F.gelu(zf).sum().backward()
     assert rel(ops.linear_dgrad(dy, w, gelu_z=z), (dy.float() @ w.float()) * zf.grad) < 1e-2
+    # the same epilogue accumulating the bias gradient of the layer behind z: column sums of the STORED result
+    dbz = torch.full((K,), 0.5, device=cuda_device)
+    dz = ops.linear_dgrad(dy, w, gelu_z=z, bias_grad=dbz)
+    assert torch.equal(dz, ops.linear_dgrad(dy, w, gelu_z=z))
+    ref_db = dz.float().sum(0) + 0.5
+    assert rel(dbz, ref_db) < 1e-4 and (dbz - ref_db).abs().max().item() < 1e-3 * (1.0 + ref_db.abs().max().item())
     dw = torch.ones(N, K, device=cuda_device)
     ops.linear_wgrad(dy, x, dw)
     assert rel(dw, dy.float().t() @ x.float() + 1.0) < 1e-3
@@ -511,6 +517,27 @@ def test_pools(ops, cuda_device, H, W):
     d = torch.randn(N, C, device=cuda_device).to(bf16)
     da = ops.avgpool_bwd(d, N, H * W, C)
     assert rel(_nchw(da, N, H, W), (d.float() / (H * W))[:, :, None, None].expand(N, C, H, W)) < 1e-2
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 112, 112), (3, 17, 21), (1, 8, 8)])
+def test_stem_tail_bn_relu_maxpool_one_pass(ops, cuda_device, N, H, W):
+    """bn1 + relu + maxpool in one pass from the convolution output: bit-identical pooled values, argmax, statistics and
+    running-statistics update to the BatchNorm kernel followed by the pooling kernel."""
+    torch.manual_seed(23)
+    C = 64
+    x = (torch.randn(N * H * W, C, device=cuda_device) * 2.0 + 0.2).to(bf16)
+    g = torch.rand(C, device=cuda_device) + 0.5
+    b = torch.randn(C, device=cuda_device) * 0.5
+    st = torch.zeros(2 * C, device=cuda_device)
+    st[:C], st[C:] = x.float().sum(0), (x.float() ** 2).sum(0)
+    rm, rv = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+    rm2, rv2 = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+    a, mean, rstd = ops.batchnorm_fwd(x, g, b, rm, rv, relu=True, col_stats=st)
+    ref, ref_arg, Ho, Wo = ops.maxpool_fwd(a, N, H, W, C)
+    got, arg, Ho2, Wo2, mean2, rstd2 = ops.bn_relu_maxpool_fwd(x, N, H, W, C, g, b, rm2, rv2, st)
+    assert (Ho, Wo) == (Ho2, Wo2)
+    assert torch.equal(got, ref) and torch.equal(arg, ref_arg)
+    assert torch.equal(mean, mean2) and torch.equal(rstd, rstd2) and torch.equal(rm, rm2) and torch.equal(rv, rv2)
 
 
 @pytest.mark.parametrize("k,stride,pad,Cin,Cout,H", [(3, 1, 1, 64, 64, 14), (3, 2, 1, 128, 128, 16), (1, 1, 0, 64, 256, 8)])
