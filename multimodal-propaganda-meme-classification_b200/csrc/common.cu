@@ -17,7 +17,11 @@ const DeviceInfo& device_info() {
   return info;
 }
 
-int g_tune[TUNE_KNOBS] = {8, 1, 0};
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e != nullptr ? std::atoi(e) : dflt;
+}
+int g_tune[TUNE_KNOBS] = {8, 1, 0, env_int("B200MM_GEMM_SMEM_FREE_KB", 0)};
 
 bool pdl_enabled() {
   static const bool on = [] {

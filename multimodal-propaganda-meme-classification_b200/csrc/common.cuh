@@ -59,7 +59,9 @@ int make_tmap_im2col_bf16(CUtensorMap* map, const void* ptr, int N, int H, int W
 //   1: B-resident GEMM mode for short unsplit K (gemm_kernel.cuh)                                           (1)
 //   2: largest tensor in MB whose BatchNorm backward runs as ONE cooperative launch (conv_support.cu); 0 = never (0:
 //      measured on config 2 at 52 MB -- ResNet layers 3-4 -- the step takes 30.28 ms against 30.06 ms with two kernels)
-constexpr int TUNE_KNOBS = 3;
+//   3: KB of shared memory the GEMM leaves free per SM so that small kernels of a concurrent stream (BatchNorm, LayerNorm,
+//      column sums of the other tower) can be co-resident with its persistent CTAs (0; B200MM_GEMM_SMEM_FREE_KB)
+constexpr int TUNE_KNOBS = 4;
 extern int g_tune[TUNE_KNOBS];
 
 // Programmatic dependent launch (PDL).  A kernel launched through launch_pdl may be scheduled while the kernel before

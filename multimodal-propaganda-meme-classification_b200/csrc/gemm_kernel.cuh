@@ -38,8 +38,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // ring depth that fits next to `nbuf` staging boxes per epilogue warp and the barrier block
-  static constexpr int stages_for(int nbuf) {
-    const int avail = GEMM_SMEM_TOTAL - EW * nbuf * GEMM_BOX_BYTES - 512;
+  static constexpr int stages_for(int nbuf, int budget = GEMM_SMEM_TOTAL) {
+    const int avail = budget - EW * nbuf * GEMM_BOX_BYTES - 512;
     const int s = avail / STAGE_BYTES;
     return s > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : s;
   }
@@ -664,8 +664,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 // Launch one (BN, EPI, CTAS) instantiation.  Shared memory split: `stages` ring slots + `nbuf` staging boxes per
 // epilogue warp.  CTAS == 2 launches clusters of two CTAs (cudaLaunchKernelEx, cluster dimension 2).
 // ring depth of the B-resident mode: what is left next to the resident [BN x K] tile and the staging boxes
-static inline int b_resident_stages(int bn, int ew, int nbuf, int k_iters) {
-  const int avail = GEMM_SMEM_TOTAL - ew * nbuf * GEMM_BOX_BYTES - 512 - k_iters * bn * GEMM_BK * 2;
+static inline int b_resident_stages(int bn, int ew, int nbuf, int k_iters, int budget) {
+  const int avail = budget - ew * nbuf * GEMM_BOX_BYTES - 512 - k_iters * bn * GEMM_BK * 2;
   const int st = avail / (GEMM_BM * GEMM_BK * 2);
   return st > GEMM_MAX_STAGES ? GEMM_MAX_STAGES : st;
 }
@@ -689,23 +689,25 @@ static int launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const 
   if (EW == 16) p.nbuf = 1;
   else if (p.nbuf <= 0 || EPI == EPI_GELU || EPI == EPI_F32 || EPI == EPI_F32_ATOMIC)
     p.nbuf = (EPI == EPI_F32 || EPI == EPI_F32_ATOMIC) ? 0 : (EPI == EPI_GELU || k_per_tile < 8 ? 2 : 1);   // fp32 modes do not stage
-  p.num_stages = Cfg::stages_for(p.nbuf);
+  const int budget = GEMM_SMEM_TOTAL - (g_tune[3] > 0 && g_tune[3] <= 64 ? g_tune[3] * 1024 : 0);   // see common.cuh, knob 3
+  p.num_stages = Cfg::stages_for(p.nbuf, budget);
+  if (p.num_stages < 2) return B200MM_ERR_BAD_ARG;
   static_assert(Cfg::stages_for(2) >= 2, "ring too shallow");
   if (p.b_resident) {
     if (CTAS == 1 && EPI != EPI_GELU) p.nbuf = p.nbuf > 1 ? 1 : p.nbuf;
-    const int st = b_resident_stages(BN, EW, p.nbuf, p.k_iters);
+    const int st = b_resident_stages(BN, EW, p.nbuf, p.k_iters, budget);
     if (CTAS == 1 && st >= 3) p.num_stages = st;
     else { p.b_resident = 0; grid = grid_in; }
   }
   if constexpr (CTAS == 1) {
-    cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, EPI, 1, EW>, dim3(grid), dim3(Cfg::THREADS), GEMM_SMEM_TOTAL + 1024,
+    cudaError_t e = launch_pdl(gemm_bf16_kernel<BN, EPI, 1, EW>, dim3(grid), dim3(Cfg::THREADS), budget + 1024,
                                stream, ta, tb, to, to2, p);
     if (e != cudaSuccess) return static_cast<int>(e);
   } else {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid & ~1), 1, 1);
     cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL + 1024;
+    cfg.dynamicSmemBytes = budget + 1024;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;

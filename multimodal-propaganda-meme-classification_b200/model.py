@@ -16,6 +16,8 @@ There is no CPU path: constructing the model without a CUDA device, or with libb
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -27,6 +29,8 @@ from .vit_tower import ViTConfig, ViTTower
 
 POOL_LAST, POOL_CLS = "last", "cls"
 
+
+_TOWER_OVERLAP = os.environ.get("B200MM_TOWER_OVERLAP", "1") != "0"
 
 class _EngineFunction(torch.autograd.Function):
     """Single autograd node: forward = engine forward, backward = engine backward (grads written in place)."""
@@ -197,12 +201,25 @@ class MultimodalClassifier(nn.Module):
         """Towers + fusion layers up to the 512-d fused feature (input of output_fc)."""
         st, S = self.store, text.shape[1]
         B = text.shape[0]
+        # The two towers are independent until the concat: the image tower is issued on a side stream (a parallel branch
+        # of the step's CUDA graph), so its HBM-bound BatchNorm / pooling kernels share the SMs with the text tower's
+        # tensor-bound GEMMs instead of alternating with them (B200MM_TOWER_OVERLAP=0: one stream)
+        main, side = self._tower_streams()
+        if side is not None:
+            side.wait_stream(main)
+            image.record_stream(side)
+            with torch.cuda.stream(side):
+                r1000 = self.img.forward(image, training=training, seed=self.seed, step=self._step)
+            r1000.record_stream(main)
         h = self.text.forward(text, mask, training=training, seed=self.seed, step=self._step)      # [B*S, D]
         off = S - 1 if self.pooling == POOL_LAST else 0
         s_head = _mix(self.seed, self._step, 254, 0)
         pd = self.head_dropout if training else 0.0
         pooled = ops.gather_rows(h, B, S, off, p_drop=pd, seed=s_head)                             # bert_drop(h[:, -1])
-        r1000 = self.img.forward(image, training=training, seed=self.seed, step=self._step)        # [B, 1000 | dim]
+        if side is not None:
+            main.wait_stream(side)
+        else:
+            r1000 = self.img.forward(image, training=training, seed=self.seed, step=self._step)    # [B, 1000 | dim]
         cat = torch.empty(B, 1024, device=self.device, dtype=torch.bfloat16)
         ops.linear_fwd(pooled, st.s("bert_fc.weight"), st.p("bert_fc.bias"), out=cat[:, :512])      # .txt:179
         ops.linear_fwd(r1000, st.s("resnet_fc.weight"), st.p("resnet_fc.bias"), out=cat[:, 512:])   # .txt:184, 190
@@ -210,6 +227,16 @@ class MultimodalClassifier(nn.Module):
         if training:
             self._saved = (B, S, off, pd, s_head, pooled, r1000, cat, fused)
         return fused
+
+    def _tower_streams(self):
+        """(current stream, side stream for the image tower) -- side is None when the overlap is switched off."""
+        main = torch.cuda.current_stream(self.device)
+        if not _TOWER_OVERLAP:
+            return main, None
+        side = getattr(self, "_side_stream", None)
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream(device=self.device)
+        return main, side
 
     def _engine_forward(self, text, image, mask, training):
         st = self.store
@@ -243,8 +270,17 @@ class MultimodalClassifier(nn.Module):
         # its all-reduce runs on NCCL's stream under the rest of the backward
         sync = getattr(self, "grad_sync", None)
         cb = sync.ready if sync is not None else None
-        self.text.backward(dh, on_grads_ready=cb)
-        self.img.backward(d_r1000, on_grads_ready=cb)
+        main, side = self._tower_streams()
+        if side is not None:
+            side.wait_stream(main)
+            d_r1000.record_stream(side)
+            with torch.cuda.stream(side):
+                self.img.backward(d_r1000, on_grads_ready=cb)
+            self.text.backward(dh, on_grads_ready=cb)
+            main.wait_stream(side)
+        else:
+            self.text.backward(dh, on_grads_ready=cb)
+            self.img.backward(d_r1000, on_grads_ready=cb)
         if sync is not None:
             sync.ready("rest")
             if not getattr(self, "_defer_grad_sync", False):

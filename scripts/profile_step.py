@@ -3,6 +3,8 @@ Aggregates by C-ABI entry point, and by shape for the GEMM.  Writes profiles/ste
 import json, os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, b200mm
+import b200mm.model as _m
+_m._TOWER_OVERLAP = False     # per-op events need one stream (the two-stream tower overlap interleaves kernels)
 from b200mm import _lib
 from b200mm.synth import synthetic_batch
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
