@@ -316,8 +316,12 @@ class ImageTower:
             dpooled = dlogits.contiguous()
         d_out = ops.avgpool_bwd(dpooled, N, Hc * Wc, self.feat_dim)
         stage_of = [li for li, nb in enumerate(self.cfg.layers) for _ in range(nb)]
+        if getattr(self, "_wq", None) is None:
+            self._wq = ops.SideQueue(dlogits.device)
+        wq = self._wq       # weight gradients run beside the data-gradient chain (ops.SideQueue)
         for bi, blk, s in zip(reversed(range(len(self.blocks))), reversed(self.blocks), reversed(sv["blocks"])):
             if on_grads_ready is not None and bi + 1 < len(self.blocks) and stage_of[bi + 1] != stage_of[bi]:
+                wq.join()
                 on_grads_ready(f"{self.cfg.prefix}.layer{stage_of[bi + 1] + 1}")     # the stage above is complete
             c1, c2, c3, ds, stride = blk["c1"], blk["c2"], blk["c3"], blk["ds"], blk["stride"]
             if self.basic:
@@ -354,10 +358,10 @@ class ImageTower:
             fused_id = _MASKRES
             d_y3, dz = ops.batchnorm_bwd(d_out, None, y3, m3, r3, c3.g, c3.dg, c3.db, relu=True, mask=msk,
                                          need_dz=not fused_id)
-            ops.linear_wgrad(d_y3, a2, c3.dw)
+            wq.run(lambda: ops.linear_wgrad(d_y3, a2, c3.dw), d_y3, a2)
             d_a2 = ops.linear_dgrad(d_y3, c3.w)
             d_y2, _ = ops.batchnorm_bwd(d_a2, None, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, beta=c2.b)
-            ops.conv_wgrad(d_y2, a1, N, Hi, Wi, c2.cin, 3, stride, 1, c2.dw)
+            wq.run(lambda: ops.conv_wgrad(d_y2, a1, N, Hi, Wi, c2.cin, 3, stride, 1, c2.dw), d_y2, a1)
             if stride == 1:
                 # data gradient = the same implicit-GEMM convolution applied to dY with the rotated weight
                 w_rot = ops.conv_weight_rotate(c2.w, c2.cout, c2.cin, 3)
@@ -366,7 +370,7 @@ class ImageTower:
                 d_cols2 = ops.linear_dgrad(d_y2, c2.w)
                 d_a1 = ops.col2im(d_cols2, N, Hi, Wi, c2.cin, 3, stride, 1)
             d_y1, _ = ops.batchnorm_bwd(d_a1, None, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True, beta=c1.b)
-            ops.linear_wgrad(d_y1, x, c1.dw)
+            wq.run(lambda: ops.linear_wgrad(d_y1, x, c1.dw), d_y1, x)
             if ds is None:
                 if fused_id:
                     # identity branch joins the data gradient in the epilogue: d_out' = d_y1 W1 + (mask ? d_out : 0)
@@ -380,13 +384,14 @@ class ImageTower:
                     d_yd, _ = ops.batchnorm_bwd(d_out, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=True, mask=msk)
                 else:
                     d_yd, _ = ops.batchnorm_bwd(dz, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=False)
-                ops.linear_wgrad(d_yd, xs, ds.dw)
+                wq.run(lambda: ops.linear_wgrad(d_yd, xs, ds.dw), d_yd, xs)
                 d_x1 = ops.linear_dgrad(d_y1, c1.w)
                 if stride == 1:
                     d_out = ops.linear_dgrad(d_yd, ds.w, residual=d_x1)
                 else:
                     d_xs = ops.linear_dgrad(d_yd, ds.w)
                     d_out = ops.upsample_add(d_xs, d_x1, N, Hi, Wi, ds.cin, stride)
+        wq.join()
         if on_grads_ready is not None:
             on_grads_ready(f"{self.cfg.prefix}.layer1")
         cols, direct, c0, a0, m0, r0, arg, H1, W1 = sv["stem"]

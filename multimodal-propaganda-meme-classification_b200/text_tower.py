@@ -257,6 +257,9 @@ class TextTower:
         B, S, H = sv["B"], sv["S"], self.cfg.n_heads
         kb = sv["key_bias"]
         d_out = dh
+        if getattr(self, "_wq", None) is None:
+            self._wq = ops.SideQueue(dh.device)
+        wq = self._wq
         for li in reversed(range(len(self.layers))):
             L = self.layers[li]
             x, qkv, ctx, lse, y_pre, m1, r1, y, z, a, o_pre, m2, r2, pa, s_att, pd, s_ffn, p_out, s_out, amask = \
@@ -265,24 +268,22 @@ class TextTower:
             d_opre, d_opre_m = ops.layernorm_bwd(d_out, o_pre, m2, r2, L["g2"], L["dg2"], L["dbe2"],
                                                  p_out=pd, seed_out=s_ffn)
             d_lin2 = d_opre_m if d_opre_m is not None else d_opre
-            ops.linear_wgrad(d_lin2, a, L["dw2"])
-            ops.colsum(d_lin2, L["db2"])
+            wq.run(lambda: (ops.linear_wgrad(d_lin2, a, L["dw2"]), ops.colsum(d_lin2, L["db2"])), d_lin2, a)
             # (d_lin2 W2) * gelu'(z); the epilogue also accumulates the result's column sums = lin1's bias gradient
             dz = ops.linear_dgrad(d_lin2, L["w2"], gelu_z=z, bias_grad=L["db1"])
-            ops.linear_wgrad(dz, y, L["dw1"])
+            wq.run(lambda: ops.linear_wgrad(dz, y, L["dw1"]), dz, y)
             dy = ops.linear_dgrad(dz, L["w1"], residual=d_opre)            # + residual path of LN2's input
             # y = LN1(y_pre);  y_pre = dropout(ctx Wo^T + bo) + x   (the dropout exists in BERT / RoBERTa only)
             d_ypre, d_ypre_m = ops.layernorm_bwd(dy, y_pre, m1, r1, L["g1"], L["dg1"], L["dbe1"],
                                                  p_out=p_out, seed_out=s_out)
             d_o = d_ypre_m if d_ypre_m is not None else d_ypre
-            ops.linear_wgrad(d_o, ctx, L["dwo"])
-            ops.colsum(d_o, L["dbo"])
+            wq.run(lambda: (ops.linear_wgrad(d_o, ctx, L["dwo"]), ops.colsum(d_o, L["dbo"])), d_o, ctx)
             dctx = ops.linear_dgrad(d_o, L["wo"])
             dqkv = ops.attention_bwd(qkv, kb, ctx, dctx, lse, B, H, S, p_drop=pa, seed=s_att, drop_mask=amask)
-            ops.linear_wgrad(dqkv, x, L["dwqkv"])
-            ops.colsum(dqkv, L["dbqkv"])
+            wq.run(lambda: (ops.linear_wgrad(dqkv, x, L["dwqkv"]), ops.colsum(dqkv, L["dbqkv"])), dqkv, x)
             d_out = ops.linear_dgrad(dqkv, L["wqkv"], residual=d_ypre)     # + residual path of LN1's input
             if on_grads_ready is not None and (li == 0 or self._group_of(li - 1) != self._group_of(li)):
+                wq.join()
                 on_grads_ready(f"{self.cfg.prefix}.g{self._group_of(li)}")
         x_emb, e_mean, e_rstd, pd, s_emb = sv["emb"]
         d_emb, _ = ops.layernorm_bwd(d_out, x_emb, e_mean, e_rstd, self.eg, self.deg, self.deb, p_in=pd, seed_in=s_emb)
@@ -291,6 +292,7 @@ class TextTower:
                           pos_ids=sv["pos_ids"], pos_padding_idx=self.cfg.pad_token_id if roberta else -1)
         if self.dtype0 is not None:
             ops.colsum(d_emb, self.dtype0)      # every token has segment id 0
+        wq.join()
         if on_grads_ready is not None:
             on_grads_ready(f"{self.cfg.prefix}.tail")
         self._saved = None

@@ -245,28 +245,30 @@ class ViTTower:
         cls_rows, mf, rf = sv["tail"]
         d_cls, _ = ops.layernorm_bwd(dfeat, cls_rows, mf, rf, self.gf, self.dgf, self.dbf)
         dx = ops.scatter_rows(d_cls, B * T, T, 0)
+        if getattr(self, "_wq", None) is None:
+            self._wq = ops.SideQueue(dfeat.device)
+        wq = self._wq       # weight / bias gradients run beside the data-gradient chain (ops.SideQueue)
         for li in reversed(range(len(self.layers))):
             L = self.layers[li]
             x, m1, r1, h1, qkv, ctx, lse, x2, m2, r2, h2, z, a, pa, s_att = sv["layers"][li]
             # x3 = a W2^T + b2 + x2
-            ops.linear_wgrad(dx, a, L["dw2"])
-            ops.colsum(dx, L["db2"])
+            wq.run(lambda: (ops.linear_wgrad(dx, a, L["dw2"]), ops.colsum(dx, L["db2"])), dx, a)
             dz = ops.linear_dgrad(dx, L["w2"], gelu_z=z, bias_grad=L["db1"])   # + column sums = fc1's bias gradient
-            ops.linear_wgrad(dz, h2, L["dw1"])
+            wq.run(lambda: ops.linear_wgrad(dz, h2, L["dw1"]), dz, h2)
             dh2 = ops.linear_dgrad(dz, L["w1"])
             dx2, _ = ops.layernorm_bwd(dh2, x2, m2, r2, L["g2"], L["dg2"], L["dbe2"], addend=dx)
             # x2 = ctx Wo^T + bo + x
-            ops.linear_wgrad(dx2, ctx, L["dwo"])
-            ops.colsum(dx2, L["dbo"])
+            wq.run(lambda: (ops.linear_wgrad(dx2, ctx, L["dwo"]), ops.colsum(dx2, L["dbo"])), dx2, ctx)
             dctx = ops.linear_dgrad(dx2, L["wo"])
             dqkv = ops.attention_bwd(qkv, None, ctx, dctx, lse, B, H, T, p_drop=pa, seed=s_att)
-            ops.linear_wgrad(dqkv, h1, L["dwqkv"])
-            ops.colsum(dqkv, L["dbqkv"])
+            wq.run(lambda: (ops.linear_wgrad(dqkv, h1, L["dwqkv"]), ops.colsum(dqkv, L["dbqkv"])), dqkv, h1)
             dh1 = ops.linear_dgrad(dqkv, L["wqkv"])
             dx, _ = ops.layernorm_bwd(dh1, x, m1, r1, L["g1"], L["dg1"], L["dbe1"], addend=dx2)
             if on_grads_ready is not None and (li == 0 or self._group_of(li - 1) != self._group_of(li)):
+                wq.join()
                 on_grads_ready(f"{c.prefix}.g{self._group_of(li)}")
         dpatch = ops.vit_assemble_bwd(dx, self.dcls, self.dpos, B, P)
         ops.linear_wgrad(dpatch, sv["cols"], self.dwp)
         ops.colsum(dpatch, self.dbp)
+        wq.join()
         self._saved = None
