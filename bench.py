@@ -499,13 +499,13 @@ def run_engine(args):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     t, h = det["tensor"], det["hbm"]
     # DRAM traffic of the same kernel from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum, average
-    # per launch over every GEMM launch of a step, cold caches under ncu): profiles/ncu_traffic_r02.json
+    # per launch over every GEMM launch of a step, cold caches under ncu): profiles/ncu_traffic_r02b.json
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r02b.json")
     if args.config == 2 and os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)["gemm"]["dram_bytes_per_launch"]
-        traffic_src = "profiles/ncu_traffic_r02.json (ncu, cold cache, mean over the GEMM launches of one step)"
+        traffic_src = "profiles/ncu_traffic_r02b.json (ncu, cold cache, mean over the GEMM launches of one step)"
     algo_bytes_per_launch = (t["bytes"] + h["bytes"]) / max(n_gemm, 1)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05+TMA; linear layers and implicit-GEMM convolutions)",
                 "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
