@@ -8,7 +8,7 @@
 // (R + 2) x (W + 2) x 64 halo (zero-filled borders) into shared memory as rows of 128 B, and output position
 // r = hl * (W + 2) + w reads, for tap (kh, kw), halo row r + kh * (W + 2) + kw -- a constant row offset per tap, so the
 // nine taps are nine UMMA descriptors into the SAME tile (SWIZZLE_128B is a function of the absolute shared-memory
-// address: a descriptor may start at any 128-byte row, measured in scratch/desc_shift_test.cu).  Positions with
+// address: a descriptor may start at any 128-byte row, measured in scripts/desc_shift_test.cu).  Positions with
 // w >= W are computed and dropped (3.4 % at W = 56).
 //   forward : D[r, cout]       = sum_tap halo[r + off_tap, :] . W_tap[cout, :]^T          (36 MMAs of 128 x 64 x 16)
 //   wgrad   : D_pair[cin2, cout] += halo[r + off_tap, cin]^T . dy[r, cout]  (MN-major A whose two 64-channel atoms are
