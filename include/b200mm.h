@@ -71,6 +71,8 @@ int b200mm_conv_fwd(const void* x, int N, int H, int W, int C, const void* w, in
 int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x, int N, int H, int W, int C, int Cout, int ksize,
                       int stride, int pad, float* dw, int splits, void* stream);
 int b200mm_conv_weight_rotate(const void* w, void* w_rot, int Cout, int Cin, int ksize, void* stream);
+/* every rotation of a backward pass in one launch; table: DEVICE int64 [n][4] = {w, w_rot, Cout << 32 | Cin, ksize^2} */
+int b200mm_conv_weight_rotate_multi(const long long* table, int n, void* stream);
 
 /* ---- fused attention (head_dim 64, S <= 512) -------------------------------------------------------------------
  * out[B*S, H*64] = softmax(Q K^T / 8 + key_bias) (dropout) V with Q|K|V = column blocks of qkv [B*S, 3*H*64].

@@ -108,6 +108,7 @@ declare("b200mm_conv_fwd", [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_i
 declare("b200mm_conv_wgrad", [c_ptr, c_longlong, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr,
                               c_int, c_ptr])
 declare("b200mm_conv_weight_rotate", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr])
+declare("b200mm_conv_weight_rotate_multi", [c_ptr, c_int, c_ptr])
 declare("b200mm_preprocess_u8", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_preprocess_u8_packed", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
                                         c_ptr])

@@ -192,6 +192,24 @@ rotate_conv_weight_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __
   }
 }
 
+// all rotations of a step in one launch: blockIdx.y = table entry {w, w_rot, Cout << 32 | Cin, taps}
+__global__ void __launch_bounds__(256)
+rotate_conv_weight_multi_kernel(const long long* __restrict__ table) {
+  const long long* e = table + 4 * blockIdx.y;
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(e[0]);
+  __nv_bfloat16* w_rot = reinterpret_cast<__nv_bfloat16*>(e[1]);
+  const int Cout = static_cast<int>(e[2] >> 32), Cin = static_cast<int>(e[2] & 0xffffffffLL), taps = static_cast<int>(e[3]);
+  const long long total = static_cast<long long>(Cout) * taps * Cin;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % Cout);
+    long long t = i / Cout;
+    const int tap = static_cast<int>(t % taps);
+    const int ci = static_cast<int>(t / taps);
+    w_rot[i] = w[(static_cast<long long>(co) * taps + (taps - 1 - tap)) * Cin + ci];
+  }
+}
+
 }  // namespace
 
 // D[M,N] = A x B (+ epilogue), bf16 operands, fp32 accumulate.
@@ -293,6 +311,15 @@ B200MM_API int b200mm_conv_wgrad(const void* dy, long long ld_dy, const void* x,
   const int ncols = ksize * ksize * C;
   return run_gemm(a, b, cg, Cout, ncols, static_cast<int>(pixels), EPI_F32_ATOMIC, nullptr, nullptr, 0, nullptr, 0,
                   dw, ncols, nullptr, 0, splits, 0, 0.f, 0, nullptr, stream);
+}
+
+// Every rotation a backward pass needs in ONE launch (ResNet-50: 13 stride-1 3x3 convolutions, 13 launches of ~7 us
+// before).  table: DEVICE int64 [n][4] = {w pointer, w_rot pointer, Cout << 32 | Cin, ksize * ksize}.
+B200MM_API int b200mm_conv_weight_rotate_multi(const long long* table, int n, void* stream) {
+  if (table == nullptr || n <= 0 || n > 65535) return B200MM_ERR_BAD_ARG;
+  rotate_conv_weight_multi_kernel<<<dim3(96, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(table);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
 }
 
 // w [Cout, k, k, Cin] -> w_rot [Cin, k, k, Cout] with both spatial axes flipped (bf16)

@@ -300,6 +300,26 @@ class ImageTower:
                                                      and (".conv" in n or ".downsample.0." in n)) or n == fc))
         return out
 
+    def _rotate_weights(self):
+        """Rotated (transposed-convolution) copies of every stride-1 3x3 weight, refreshed from the bf16 shadow in ONE
+        launch at the top of the backward (they change once per optimizer step; 13 launches in ResNet-50 before)."""
+        convs = [c for c in self._convs if c.k == 3 and c.stride == 1 and c.cin != 3]
+        key = tuple(c.w.data_ptr() for c in convs)           # (the flat shadow buffer may have been re-created)
+        if getattr(self, "_rot_key", None) != key:
+            self._rot_key = key
+            total = sum(c.cin * 9 * c.cout for c in convs)
+            dev = self.store.device
+            self._rot_arena = torch.empty(max(total, 1), device=dev, dtype=torch.bfloat16)
+            rows, off = [], 0
+            for c in convs:
+                c.w_rot = self._rot_arena[off:off + c.cin * 9 * c.cout].view(c.cin, 9 * c.cout)
+                rows.append([c.w.data_ptr(), c.w_rot.data_ptr(), (c.cout << 32) | c.cin, 9])
+                off += c.cin * 9 * c.cout
+            self._rot_n = len(rows)
+            self._rot_table = torch.tensor(rows if rows else [[0, 0, 0, 0]], dtype=torch.int64).to(dev)
+        if self._rot_n:
+            ops.conv_weight_rotate_multi(self._rot_table, self._rot_n)
+
     # ------------------------------------------------------------------ backward
     def backward(self, dlogits: torch.Tensor, on_grads_ready=None):
         """dlogits: bf16 [N, 1000]. Accumulates parameter gradients (the image itself needs none).
@@ -316,6 +336,7 @@ class ImageTower:
             dpooled = dlogits.contiguous()
         d_out = ops.avgpool_bwd(dpooled, N, Hc * Wc, self.feat_dim)
         stage_of = [li for li, nb in enumerate(self.cfg.layers) for _ in range(nb)]
+        self._rotate_weights()
         if getattr(self, "_wq", None) is None:
             self._wq = ops.SideQueue(dlogits.device)
         wq = self._wq       # weight gradients run beside the data-gradient chain (ops.SideQueue)
@@ -330,20 +351,20 @@ class ImageTower:
                 d_y2, dz = ops.batchnorm_bwd(d_out, None, y2, m2, r2, c2.g, c2.dg, c2.db, relu=True, need_dz=True,
                                              mask=msk)
                 ops.conv_wgrad(d_y2, a1, N, Ho, Wo, c2.cin, 3, 1, 1, c2.dw)
-                d_a1, _, _ = ops.conv_fwd(d_y2, N, Ho, Wo, c2.cout, ops.conv_weight_rotate(c2.w, c2.cout, c2.cin, 3),
+                d_a1, _, _ = ops.conv_fwd(d_y2, N, Ho, Wo, c2.cout, c2.w_rot,
                                           3, 1, 1)
                 d_y1, _ = ops.batchnorm_bwd(d_a1, None, y1, m1, r1, c1.g, c1.dg, c1.db, relu=True, beta=c1.b)
                 ops.conv_wgrad(d_y1, x, N, Hi, Wi, c1.cin, 3, stride, 1, c1.dw)
                 if ds is None:      # stride 1: data gradient + identity branch in one epilogue
                     d_out, _, _ = ops.conv_fwd(d_y1, N, Ho, Wo, c1.cout,
-                                               ops.conv_weight_rotate(c1.w, c1.cout, c1.cin, 3), 3, 1, 1, residual=dz)
+                                               c1.w_rot, 3, 1, 1, residual=dz)
                 else:
                     d_yd, _ = ops.batchnorm_bwd(dz, None, yd, md, rd, ds.g, ds.dg, ds.db, relu=False)
                     ops.linear_wgrad(d_yd, xs, ds.dw)
                     d_xs = ops.linear_dgrad(d_yd, ds.w)
                     if stride == 1:
                         d_x1, _, _ = ops.conv_fwd(d_y1, N, Ho, Wo, c1.cout,
-                                                  ops.conv_weight_rotate(c1.w, c1.cout, c1.cin, 3), 3, 1, 1,
+                                                  c1.w_rot, 3, 1, 1,
                                                   residual=d_xs)
                         d_out = d_x1
                     else:
@@ -364,8 +385,7 @@ class ImageTower:
             wq.run(lambda: ops.conv_wgrad(d_y2, a1, N, Hi, Wi, c2.cin, 3, stride, 1, c2.dw), d_y2, a1)
             if stride == 1:
                 # data gradient = the same implicit-GEMM convolution applied to dY with the rotated weight
-                w_rot = ops.conv_weight_rotate(c2.w, c2.cout, c2.cin, 3)
-                d_a1, _, _ = ops.conv_fwd(d_y2, N, Ho, Wo, c2.cout, w_rot, 3, 1, 1)
+                d_a1, _, _ = ops.conv_fwd(d_y2, N, Ho, Wo, c2.cout, c2.w_rot, 3, 1, 1)
             else:
                 d_cols2 = ops.linear_dgrad(d_y2, c2.w)
                 d_a1 = ops.col2im(d_cols2, N, Hi, Wi, c2.cin, 3, stride, 1)

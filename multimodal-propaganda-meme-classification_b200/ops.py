@@ -288,6 +288,11 @@ def conv_wgrad(dy, x, N, H, W, C, ksize, stride, pad, dw):
     return dw
 
 
+def conv_weight_rotate_multi(table, n):
+    """All weight rotations of a backward pass in one launch; table: device int64 [n, 4] (see the C header)."""
+    _lib.call("b200mm_conv_weight_rotate_multi", _p(table), int(n), _s())
+
+
 def conv_weight_rotate(w, Cout, Cin, ksize, out=None):
     if out is None:
         out = torch.empty(Cin, ksize * ksize * Cout, device=w.device, dtype=bf16)

@@ -519,6 +519,21 @@ def test_pools(ops, cuda_device, H, W):
     assert rel(_nchw(da, N, H, W), (d.float() / (H * W))[:, :, None, None].expand(N, C, H, W)) < 1e-2
 
 
+def test_conv_weight_rotate_multi_matches_single(ops, cuda_device):
+    """All rotated (transposed-convolution) weights of a backward pass from one launch == one launch per weight."""
+    torch.manual_seed(5)
+    shapes = [(64, 64), (128, 128), (256, 192), (512, 512)]
+    ws = [torch.randn(co, 9 * ci, device=cuda_device).to(bf16) for co, ci in shapes]
+    outs = [torch.empty(ci, 9 * co, device=cuda_device, dtype=bf16) for co, ci in shapes]
+    table = torch.tensor([[w.data_ptr(), o.data_ptr(), (co << 32) | ci, 9] for w, o, (co, ci) in zip(ws, outs, shapes)],
+                         dtype=torch.int64).to(cuda_device)
+    ops.conv_weight_rotate_multi(table, len(shapes))
+    for w, o, (co, ci) in zip(ws, outs, shapes):
+        assert torch.equal(o, ops.conv_weight_rotate(w, co, ci, 3))
+        ref = w.view(co, 3, 3, ci).flip(1, 2).permute(3, 1, 2, 0).reshape(ci, 9 * co)
+        assert torch.equal(o, ref)
+
+
 @pytest.mark.parametrize("N,H,W", [(2, 112, 112), (3, 17, 21), (1, 8, 8)])
 def test_stem_tail_bn_relu_maxpool_one_pass(ops, cuda_device, N, H, W):
     """bn1 + relu + maxpool in one pass from the convolution output: bit-identical pooled values, argmax, statistics and
