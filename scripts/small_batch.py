@@ -1,5 +1,5 @@
 """Step latency at the batch sizes the reference actually trains with (16: .txt:18 / HEAD :73; 8; 32), config-2 model:
-eager launches vs the whole step as one CUDA graph (b200mm.GraphedTrainStep).  Writes gpurun_out/small_batch_r02.json."""
+eager launches vs the whole step as one CUDA graph (b200mm.GraphedTrainStep).  Writes gpurun_out/small_batch_r02b.json."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -47,4 +47,4 @@ for B in [int(a) for a in sys.argv[1:]] or [8, 16, 32, 256]:
         del model, opt
         torch.cuda.empty_cache()
 json.dump({"what": "config-2 train step (ResNet-50 + DistilBERT, seq 128, dropout on) at small batch: eager vs CUDA graph",
-           "rows": rows}, open("gpurun_out/small_batch_r02.json", "w"), indent=1)
+           "rows": rows}, open("gpurun_out/small_batch_r02b.json", "w"), indent=1)
