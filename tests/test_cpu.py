@@ -460,3 +460,17 @@ def test_fold_driver_class_weights_and_split_sizes():
     assert np.allclose(folds.balanced_class_weights(y), ref, rtol=0, atol=1e-12)
     assert (folds.N_SPLITS, folds.SPLIT_SEED, folds.BATCH_SIZE, folds.NUM_EPOCHS) == (5, 42, 16, 8)
     assert folds.LEARNING_RATE == 1e-5 and folds.WARMUP_RATIO == 0.1
+
+
+def test_dispatch_switch_defaults_and_side_queue_passthrough():
+    """The A/B switches of the last round-2 session default to the measured optimum, and a disabled
+    side queue runs its work inline (no stream, no CUDA call)."""
+    from b200mm import ops, model, image_tower
+    assert model._TOWER_OVERLAP is True and ops.FOLD_BIAS_GRAD is True
+    assert ops.WGRAD_OVERLAP is False and image_tower._MASKRES is False and ops.BN_FUSED_MB[0] == 0
+    ran = []
+    q = ops.SideQueue("cpu")
+    assert q.stream is None
+    q.run(lambda: ran.append(1))
+    q.join()
+    assert ran == [1]
