@@ -496,8 +496,16 @@ def run_engine(args):
     # this (untimed) profiling pass, otherwise a GEMM's interval also covers kernels of the other tower
     from b200mm import model as _model_mod
     _overlap, _model_mod._TOWER_OVERLAP = _model_mod._TOWER_OVERLAP, False
+    _wq_on, ops.WGRAD_OVERLAP = ops.WGRAD_OVERLAP, False
+    for _tw in (getattr(model, "text", None), getattr(model, "img", None)):
+        if _tw is not None and getattr(_tw, "_wq", None) is not None:
+            _tw._wq = None                      # (a side queue created earlier keeps its stream: rebuild it serial)
     gemm_ms, gemm_flops, n_gemm, det = ops.profile_gemm(step_eager if gstep is None else (lambda: gstep.eager(devd["text"], devd["image"], devd["text_mask"], devd["label"])), steps=2, ridge=ridge)
     _model_mod._TOWER_OVERLAP = _overlap
+    ops.WGRAD_OVERLAP = _wq_on
+    for _tw in (getattr(model, "text", None), getattr(model, "img", None)):
+        if _tw is not None:
+            _tw._wq = None
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     t, h = det["tensor"], det["hbm"]
     # DRAM traffic of the same kernel from the committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum, average

@@ -136,7 +136,7 @@ def linear_gelu_fwd(x, w, bias):
 
 
 FOLD_BIAS_GRAD = os.environ.get("B200MM_FOLD_BIAS_GRAD", "1") != "0"
-WGRAD_OVERLAP = os.environ.get("B200MM_WGRAD_OVERLAP", "1") != "0"
+WGRAD_OVERLAP = os.environ.get("B200MM_WGRAD_OVERLAP", "0") == "1"
 
 
 class SideQueue:
@@ -145,7 +145,9 @@ class SideQueue:
     worth depends on the batch: at the reference's batch 16 the graph replays in 5.30 instead of 5.62 ms (batch 8:
     4.56 vs 4.90, batch 32: 6.78 vs 7.05), at batch 256 it is neutral on top of the two-stream tower overlap (29.93 vs
     29.92 ms; config 3: 54.7 vs 54.5) -- every persistent GEMM CTA takes a whole SM's shared memory, so another branch
-    only ever fills kernel-boundary gaps.  B200MM_WGRAD_OVERLAP=0 switches it off.  ``run(fn, *tensors)`` orders ``fn`` after everything
+    only ever fills kernel-boundary gaps.  Opt-in (B200MM_WGRAD_OVERLAP=1): with it on by default one run of the full
+    GPU suite failed test_head_three_tower_model_matches_oracle (not reproduced in four reruns of that file, cause not
+    found before the GPU budget ran out), so the default stays the configuration every full run has passed with.  ``run(fn, *tensors)`` orders ``fn`` after everything
     issued so far on the current stream; ``tensors`` are the operands it reads (kept alive for the side stream);
     ``join()`` makes the current stream wait for all of it (before the gradients are announced / consumed)."""
 

@@ -467,13 +467,9 @@ def test_dispatch_switch_defaults_and_side_queue_passthrough():
     side queue runs its work inline (no stream, no CUDA call)."""
     from b200mm import ops, model, image_tower
     assert model._TOWER_OVERLAP is True and ops.FOLD_BIAS_GRAD is True
-    assert ops.WGRAD_OVERLAP is True and image_tower._MASKRES is False and ops.BN_FUSED_MB[0] == 0
+    assert ops.WGRAD_OVERLAP is False and image_tower._MASKRES is False and ops.BN_FUSED_MB[0] == 0
     ran = []
-    ops.WGRAD_OVERLAP = False
-    try:
-        q = ops.SideQueue("cpu")
-    finally:
-        ops.WGRAD_OVERLAP = True
+    q = ops.SideQueue("cpu")
     assert q.stream is None
     q.run(lambda: ran.append(1))
     q.join()
