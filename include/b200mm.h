@@ -178,6 +178,14 @@ int b200mm_preprocess_u8_packed(const void* packed, const long long* offsets, co
 /* Batch already at network resolution: [n, H, W, 3] uint8 -> ToTensor -> Normalize -> fp32 NCHW (W % 4 == 0). */
 int b200mm_u8_normalize_nchw(const void* src, const void* flip, int n, int H, int W, const float* mean3,
                              const float* std3, float* out, void* stream);
+/* Train-time augmentations of the HEAD script (example_scripts/Multimodal_example_task2C.py:224-233): ColorJitter (four
+ * operators in a per-image random order) + RandomRotation (nearest, zero fill) + Normalize over a batch already resized /
+ * flipped / scaled to [0, 1] (the two entry points above with mean 0, std 1).  img01, out: [n, 3, H, W] fp32 (out != img01);
+ * order [n] int: 2 bits per operator, first applied in the low bits (0 brightness, 1 contrast, 2 saturation, 3 hue);
+ * params [n, 8] fp32: brightness / contrast / saturation factors, hue shift, inverse rotation matrix m00 m01 m10 m11;
+ * gray_mean [n] fp32: scratch, holds each image's contrast mean afterwards.  Semantics: torchvision's float-tensor path. */
+int b200mm_augment_jitter_rotate(const float* img01, const int* order, const float* params, int n, int H, int W,
+                                 const float* mean3, const float* std3, float* gray_mean, float* out, void* stream);
 
 /* ---- head + loss, optimizer --------------------------------------------------------------------------------------
  * output layer fused with the loss: example_scripts/Multimodal_example_task2C.txt:195 (output_fc) + :214, :248

@@ -1,0 +1,99 @@
+// Train-time augmentations of the HEAD script on the GPU: ColorJitter + RandomRotation + Normalize over a batch that
+// is already resized to network resolution (example_scripts/Multimodal_example_task2C.py:224-233).
+//
+//   img01 [n, 3, H, W] fp32 in [0, 1]  (output of preprocess_kernel / u8_normalize_kernel with mean 0, std 1: Resize +
+//                                       RandomHorizontalFlip + ToTensor already applied)
+//   -> jitter_gray_mean_kernel            one CTA per image: grey mean of the image as the contrast operator sees it
+//                                         (after the operators that precede it in this image's random permutation)
+//   -> jitter_rotate_normalize_kernel     one thread per OUTPUT pixel: inverse-rotate to the source pixel (nearest, zero
+//                                         fill), apply the four colour operators in the drawn order, Normalize, store
+//
+// The colour operators are pointwise once the grey mean is known, so "jitter the image, then rotate it" equals "gather
+// the rotated source pixel, then jitter it": the jittered image is never materialised.  Both kernels are HBM-bound:
+// 12 B read per pixel by the first, 12 B gathered (rotation by <= 15 degrees keeps a warp's 32 sources within two or
+// three rows) + 12 B written by the second.  The arithmetic is csrc/augment_math.cuh (torchvision's tensor path).
+#include "common.cuh"
+#include "augment_math.cuh"
+
+namespace b200 {
+
+constexpr int kMeanThreads = 512;
+
+__global__ void __launch_bounds__(kMeanThreads)
+jitter_gray_mean_kernel(const float* __restrict__ img01, const int* __restrict__ order, const float* __restrict__ params,
+                        int H, int W, float* __restrict__ gray_mean) {
+  const int img = blockIdx.x;
+  const aug::Jitter j = aug::make_jitter(order[img], params + img * 8);
+  const int upto = aug::contrast_position(j.order);
+  const int plane = H * W;
+  const float* src = img01 + static_cast<long long>(img) * 3 * plane;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < plane; i += kMeanThreads) {
+    float r = __ldg(src + i), g = __ldg(src + plane + i), b = __ldg(src + 2 * plane + i);
+    aug::jitter_pixel(j, 0, upto, 0.f, r, g, b);
+    acc += aug::gray(r, g, b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[kMeanThreads / 32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kMeanThreads / 32 ? part[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) gray_mean[img] = v / static_cast<float>(plane);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+jitter_rotate_normalize_kernel(const float* __restrict__ img01, const int* __restrict__ order,
+                               const float* __restrict__ params, const float* __restrict__ gray_mean, int H, int W,
+                               float m0, float m1, float m2, float s0, float s1, float s2, float* __restrict__ out) {
+  const int img = blockIdx.z;
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= W || oy >= H) return;
+  const float* prm = params + img * 8;
+  const int plane = H * W;
+  float r = 0.f, g = 0.f, b = 0.f;   // RandomRotation's fill
+  int sx, sy;
+  if (aug::rotate_source(ox, oy, W, H, prm + 4, sx, sy)) {
+    const float* src = img01 + static_cast<long long>(img) * 3 * plane + sy * W + sx;
+    r = __ldg(src);
+    g = __ldg(src + plane);
+    b = __ldg(src + 2 * plane);
+    const aug::Jitter j = aug::make_jitter(order[img], prm);
+    aug::jitter_pixel(j, 0, 4, gray_mean[img], r, g, b);
+  }
+  float* o = out + static_cast<long long>(img) * 3 * plane + oy * W + ox;
+  o[0] = aug::div_rn(aug::sub_rn(r, m0), s0);
+  o[plane] = aug::div_rn(aug::sub_rn(g, m1), s1);
+  o[2 * plane] = aug::div_rn(aug::sub_rn(b, m2), s2);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// img01 [n, 3, H, W] fp32 in [0, 1]; order [n] int (2 bits per ColorJitter operator, first applied in the low bits);
+// params [n, 8] fp32 = brightness, contrast, saturation factors, hue shift, inverse rotation matrix m00 m01 m10 m11;
+// gray_mean [n] fp32 scratch (holds each image's contrast mean afterwards); out [n, 3, H, W] fp32 normalised.
+// mean3 / std3: HOST arrays.  All other pointers are device pointers.
+B200MM_API int b200mm_augment_jitter_rotate(const float* img01, const int* order, const float* params, int n, int H,
+                                            int W, const float* mean3, const float* std3, float* gray_mean, float* out,
+                                            void* stream) {
+  if (n <= 0 || H <= 0 || W <= 0 || !img01 || !order || !params || !mean3 || !std3 || !gray_mean || !out)
+    return B200MM_ERR_BAD_ARG;
+  if (img01 == out) return B200MM_ERR_BAD_ARG;   // the rotation gathers: not an in-place transform
+  for (int c = 0; c < 3; ++c)
+    if (std3[c] == 0.f) return B200MM_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  jitter_gray_mean_kernel<<<n, kMeanThreads, 0, st>>>(img01, order, params, H, W, gray_mean);
+  B200MM_CHECK_LAUNCH();
+  dim3 grid(ceil_div(W, 32), ceil_div(H, 8), n);
+  jitter_rotate_normalize_kernel<<<grid, 256, 0, st>>>(img01, order, params, gray_mean, H, W, mean3[0], mean3[1],
+                                                       mean3[2], std3[0], std3[1], std3[2], out);
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}

@@ -12,14 +12,18 @@ SURVEY.md §3.1).  Here the host only does what must stay there:
                           (ops.pack_images): two host->device copies per batch whatever its size, 4x fewer bytes than
                           fp32 pixels even before counting the resize;
   * ``GpuImageTransform`` Resize / CenterCrop (or Resize((224, 224))) / RandomHorizontalFlip / ToTensor / Normalize as ONE
-                          kernel on the copy stream (csrc/preprocess.cu), called by ``loop.DevicePrefetcher``.
+                          kernel on the copy stream (csrc/preprocess.cu), called by ``loop.DevicePrefetcher``; with
+                          ``augment=True`` the HEAD script's whole train transform (.py:222-235): + ColorJitter(.1, .1,
+                          .1, .1) + RandomRotation(15) as two more kernels (csrc/augment.cu).
 
-JPEG decode stays on the host (PIL, as in the reference); ColorJitter / RandomRotation of the HEAD script's train
-transform (.py:224-233) are not reproduced (documented in DESIGN.md; the parity runs use fixed inputs).
+JPEG decode stays on the host (PIL, as in the reference).  The augmentations follow torchvision's float-tensor
+operators with per-image parameters drawn as ``ColorJitter.get_params`` / ``RandomRotation.get_params`` draw them; the
+reference applies the same operators to PIL images (uint8 intermediates: up to 1/255 of rounding per operator).
 """
 from __future__ import annotations
 
 import json
+import math
 
 import torch
 from torch.utils.data import Dataset
@@ -122,18 +126,30 @@ def collate_packed(samples, pin: bool = True):
 
 
 class GpuImageTransform:
-    """The reference's image transform as one device kernel, applied to a batch that has just crossed PCIe.
+    """The reference's image transform as device kernels, applied to a batch that has just crossed PCIe.
 
     mode 'center_crop': Resize(256) -> CenterCrop(224) -> ToTensor -> Normalize          (.txt:37-41)
     mode 'square'     : Resize((224, 224)) [-> RandomHorizontalFlip] -> ToTensor -> Normalize   (.py:222-235)
-    ``train=True`` draws the flip flags (p = 0.5) from a seeded host generator, one per image."""
+    ``train=True`` draws the flip flags (p = 0.5) from a seeded host generator, one per image.
+    ``augment=True`` (with ``train=True``, mode 'square') completes the HEAD script's train transform (.py:224-233):
+    ColorJitter(brightness, contrast, saturation, hue) in a per-image random operator order and
+    RandomRotation(degrees) (nearest, zero fill) between the flip and ToTensor / Normalize."""
 
     def __init__(self, mode: str = "center_crop", *, resize: int = 256, crop: int = 224, train: bool = False,
-                 seed: int = 0, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD):
+                 seed: int = 0, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, augment: bool = False,
+                 brightness: float = 0.1, contrast: float = 0.1, saturation: float = 0.1, hue: float = 0.1,
+                 degrees: float = 15.0):
         if mode not in ("center_crop", "square"):
             raise ValueError(f"unknown image transform mode {mode!r}")
+        if augment and not (train and mode == "square"):
+            raise ValueError("augment=True is the HEAD script's TRAIN transform: it needs train=True and mode='square'")
+        if not 0.0 <= hue <= 0.5 or min(brightness, contrast, saturation, degrees) < 0.0:
+            raise ValueError("ColorJitter / RandomRotation ranges must be non-negative (hue <= 0.5)")
         self.mode, self.resize, self.crop, self.train = mode, resize, crop, train
         self.mean, self.std = tuple(mean), tuple(std)
+        self.augment = augment
+        self.jitter = (brightness, contrast, saturation, hue)
+        self.degrees = degrees
         self.gen = torch.Generator().manual_seed(seed)
 
     def _flip(self, n, device):
@@ -142,9 +158,51 @@ class GpuImageTransform:
         f = (torch.rand(n, generator=self.gen) < 0.5).to(torch.uint8)
         return f.pin_memory().to(device, non_blocking=True)
 
+    def draw_raw(self, n):
+        """Per-image draws of ColorJitter.get_params ($SP/torchvision/transforms/transforms.py:1237-1266: a permutation of
+        the four operators, factors ~ U[max(0, 1 - x), 1 + x], hue shift ~ U[-hue, hue]) and RandomRotation.get_params
+        (:1354-1361: angle ~ U[-degrees, degrees]): perm int64 [n, 4], factors fp32 [n, 4], angles fp64 [n] (degrees)."""
+        perm = torch.stack([torch.randperm(4, generator=self.gen) for _ in range(n)])
+        u = torch.rand(n, 5, generator=self.gen)
+        factors = torch.empty(n, 4)
+        for k, x in enumerate(self.jitter[:3]):
+            lo = max(0.0, 1.0 - x)
+            factors[:, k] = lo + u[:, k] * (1.0 + x - lo)
+        factors[:, 3] = (2.0 * u[:, 3] - 1.0) * self.jitter[3]
+        angles = ((2.0 * u[:, 4] - 1.0) * self.degrees).double()
+        return perm, factors, angles
+
+    @staticmethod
+    def pack_augment(perm, factors, angles):
+        """The kernel's parameter tables (csrc/augment.cu): order int32 [n] -- 2 bits per operator, first applied in the
+        low bits -- and params fp32 [n, 8] = factors | inverse rotation matrix.  torchvision's ``rotate`` hands -angle to
+        ``_get_inverse_affine_matrix`` (functional.py:1131); for a rotation about the centre that matrix is
+        [[cos t, sin t, 0], [-sin t, cos t, 0]] with t = radians(-angle), computed in double and rounded to fp32."""
+        order = (perm << torch.tensor([0, 2, 4, 6])).sum(1).to(torch.int32)
+        t = angles.double().neg() * (math.pi / 180.0)
+        rot = torch.stack([torch.cos(t), torch.sin(t), torch.sin(t).neg(), torch.cos(t)], dim=1).float()
+        return order, torch.cat([factors.float(), rot], dim=1).contiguous()
+
+    def draw_augment(self, n):
+        return self.pack_augment(*self.draw_raw(n))
+
+    def _finish(self, img01):
+        order, params = self.draw_augment(img01.shape[0])
+        order = order.pin_memory().to(img01.device, non_blocking=True)
+        params = params.pin_memory().to(img01.device, non_blocking=True)
+        return ops.augment_jitter_rotate(img01, order, params, mean=self.mean, std=self.std)[0]
+
     def packed(self, packed, table):
-        return ops.preprocess_u8_packed(packed, table, resize=self.resize, crop=self.crop, square=self.mode == "square",
-                                        flip=self._flip(table.shape[1], packed.device), mean=self.mean, std=self.std)
+        flip = self._flip(table.shape[1], packed.device)
+        square = self.mode == "square"
+        if self.augment:    # resize + flip + ToTensor to [0, 1] here, Normalize at the end of the augmentation kernel
+            return self._finish(ops.preprocess_u8_packed(packed, table, resize=self.resize, crop=self.crop, square=square,
+                                                         flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)))
+        return ops.preprocess_u8_packed(packed, table, resize=self.resize, crop=self.crop, square=square, flip=flip,
+                                        mean=self.mean, std=self.std)
 
     def fixed(self, images):
-        return ops.u8_normalize(images, flip=self._flip(images.shape[0], images.device), mean=self.mean, std=self.std)
+        flip = self._flip(images.shape[0], images.device)
+        if self.augment:
+            return self._finish(ops.u8_normalize(images, flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)))
+        return ops.u8_normalize(images, flip=flip, mean=self.mean, std=self.std)

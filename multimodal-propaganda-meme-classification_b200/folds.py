@@ -86,12 +86,15 @@ def setup(k: int, *, train_records: dict, test_records: dict, model_factory: Cal
           make_dataset: Callable[[dict], object], device, batch_size: int = BATCH_SIZE,
           learning_rate: float = LEARNING_RATE, num_epochs: int = NUM_EPOCHS, n_splits: int = N_SPLITS,
           out_dir: str = ".", team_name: str = "kevinmathew", run_id: str | None = None, num_workers: int = 0,
-          collate_fn=None, log=print) -> FoldRun:
+          collate_fn=None, image_transform=None, log=print) -> FoldRun:
     """One fold of the reference's ``setup(k)`` (Multimodal_example_task2C.py:50-192).
 
     train_records / test_records: ``data.read_data`` dicts (``id``, ``text``, ``image``, ``label`` lists).
     model_factory():              a fresh model for this fold (the script builds ``MultimodalClassifier(fusion_method)``).
-    make_dataset(records):        a Dataset yielding the reference's batch-dict keys for those records."""
+    make_dataset(records):        a Dataset yielding the reference's batch-dict keys for those records.
+    image_transform:              data.GpuImageTransform for loaders that ship uint8 pixels (data.collate_packed);
+                                  ``GpuImageTransform('square', train=True, augment=True)`` is the script's transform
+                                  (:222-235), which its train, validation and test datasets all share."""
     loop_head.seed_everything()
     labels = train_records["label"]
     splits = list(loop_head.stratified_kfold(labels, n_splits, SPLIT_SEED))
@@ -123,9 +126,11 @@ def setup(k: int, *, train_records: dict, test_records: dict, model_factory: Cal
     for epoch in range(num_epochs):
         train_loss, acc = loop_head.train(model, train_loader, criterion, optimizer, scheduler, device, epoch,
                                           test_loader=test_loader, val_loader=val_loader, state=state,
-                                          evaluate_kwargs=ev, log=log)
-        t_loss, t_acc, t_f1, t_thr = loop_head.test(model, test_loader, criterion, device, epoch, log)
-        v_loss, v_acc, v_f1, v_thr = loop_head.test(model, val_loader, criterion, device, epoch, log)
+                                          evaluate_kwargs=ev, log=log, image_transform=image_transform)
+        t_loss, t_acc, t_f1, t_thr = loop_head.test(model, test_loader, criterion, device, epoch, log,
+                                                    image_transform=image_transform)
+        v_loss, v_acc, v_f1, v_thr = loop_head.test(model, val_loader, criterion, device, epoch, log,
+                                                    image_transform=image_transform)
         log("  ALL | Epoch {}/{}: Train Loss = {:.4f}, Test Loss = {:.4f}, Train Accuracy = {:.4f}, Test Accuracy = "
             "{:.4f}, F1 = {:.4f}".format(epoch + 1, num_epochs, train_loss, t_loss, acc, t_acc, t_f1))
         log("  ALL | Epoch {}/{}: Train Loss = {:.4f}, Val Loss = {:.4f}, Train Accuracy = {:.4f}, Val Accuracy = "

@@ -49,24 +49,28 @@ class SigmoidFocalLoss:
 _EVAL_TRANSFORM = None
 
 
-def _image_to_device(data, device):
+def _image_to_device(data, device, image_transform=None):
     """fp32 pixels are copied as they are; uint8 pixels (fixed-size or packed, data.collate_packed) take the GPU
-    transform in its deterministic evaluation form."""
+    transform: ``image_transform`` (a data.GpuImageTransform) or, by default, the organiser script's deterministic
+    evaluation form (Resize(256) / CenterCrop(224) / Normalize)."""
     global _EVAL_TRANSFORM
     if "image_packed" in data or data["image"].dtype == torch.uint8:
-        if _EVAL_TRANSFORM is None:
-            from .data import GpuImageTransform
-            _EVAL_TRANSFORM = GpuImageTransform("center_crop")
+        tr = image_transform
+        if tr is None:
+            if _EVAL_TRANSFORM is None:
+                from .data import GpuImageTransform
+                _EVAL_TRANSFORM = GpuImageTransform("center_crop")
+            tr = _EVAL_TRANSFORM
         if "image_packed" in data:
-            return _EVAL_TRANSFORM.packed(data["image_packed"].to(device, non_blocking=True),
-                                          data["image_table"].to(device, non_blocking=True))
-        return _EVAL_TRANSFORM.fixed(data["image"].to(device, non_blocking=True))
+            return tr.packed(data["image_packed"].to(device, non_blocking=True),
+                             data["image_table"].to(device, non_blocking=True))
+        return tr.fixed(data["image"].to(device, non_blocking=True))
     return data["image"].to(device, non_blocking=True)
 
 
-def _to_device(data, device):
+def _to_device(data, device, image_transform=None):
     text = data["text"].to(device, non_blocking=True)
-    image = _image_to_device(data, device)
+    image = _image_to_device(data, device, image_transform)
     mask = data["text_mask"].to(device, non_blocking=True)
     labels = data["label"].to(device, non_blocking=True) if "label" in data else None
     return text, image, mask, labels

@@ -82,14 +82,16 @@ def _probs(output):
     return torch.sigmoid(output.float().reshape(-1))
 
 
-def test(model, test_loader, criterion, device, epoch=0, log=print):
+def test(model, test_loader, criterion, device, epoch=0, log=print, *, image_transform=None):
+    """``image_transform``: the data.GpuImageTransform applied to uint8 image batches (the script's Dataset uses ONE
+    transform object -- augmentations included -- for its train, validation and test datasets alike, :222-235)."""
     model.eval()
     test_loss, n = 0.0, 0
     true_labels, predicted_probs = [], []
     fused = _fused(criterion) and hasattr(model, "eval_step_fused")
     with torch.no_grad():
         for batch_idx, data in enumerate(test_loader, 1):
-            text, image, mask, labels = _to_device(data, device)
+            text, image, mask, labels = _to_device(data, device, image_transform)
             extra = _extra_inputs(data, device)
             if fused:
                 output, loss, _ = model.eval_step_fused(text, image, mask, *extra, labels, loss_kind=criterion.loss_kind,
@@ -119,14 +121,14 @@ def test(model, test_loader, criterion, device, epoch=0, log=print):
 
 
 def evaluate(model, test_loader, t_optimal_threshold, device, *, fold=0, team_name="kevinmathew",
-             run_id=None, out_dir="."):
+             run_id=None, out_dir=".", image_transform=None):
     """Writes ``task2C_<team>.tsv`` (id, label, run_id) and ``task2C_<team>_probs_fold_<fold>.tsv``
     (id, label, prob, run_id) -- the schemas of the reference's committed prediction files."""
     model.eval()
     ids, probs = [], []
     with torch.no_grad():
         for data in test_loader:
-            text, image, mask, _ = _to_device(data, device)
+            text, image, mask, _ = _to_device(data, device, image_transform)
             probs.append(_probs(model(text, image, mask, *_extra_inputs(data, device))).cpu())
             ids.extend(list(data["id"]))
     probs = torch.cat(probs).numpy() if probs else np.zeros(0, dtype=np.float32)
@@ -140,8 +142,12 @@ def evaluate(model, test_loader, t_optimal_threshold, device, *, fold=0, team_na
 
 
 def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0, scaler=None, *, test_loader=None,
-          val_loader=None, state=None, evaluate_kwargs=None, log=print):
-    """One epoch. ``state`` (dict) carries ``best_macro_f1`` across epochs like the script's global (:766-769)."""
+          val_loader=None, state=None, evaluate_kwargs=None, log=print, image_transform=None):
+    """One epoch. ``state`` (dict) carries ``best_macro_f1`` across epochs like the script's global (:766-769).
+    ``image_transform``: data.GpuImageTransform for uint8 image batches -- ``GpuImageTransform('square', train=True,
+    augment=True)`` is the script's transform (:222-235: Resize((224, 224)), flip, ColorJitter, RandomRotation,
+    Normalize), run on the device; it is also handed to the mid-epoch ``test`` / ``evaluate`` calls, as the script's
+    datasets all share that transform."""
     model.train()
     state = state if state is not None else {}
     train_loss, correct, n = 0.0, 0, 0
@@ -154,7 +160,7 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
         optimizer.max_grad_norm = CLIP_NORM              # reference: clip_grad_norm_(..., 10.0) on every step
     for batch_idx, data in enumerate(train_loader, 1):
         optimizer.zero_grad()
-        text, image, mask, labels = _to_device(data, device)
+        text, image, mask, labels = _to_device(data, device, image_transform)
         extra = _extra_inputs(data, device)
         if fused:
             output, loss, ok = model.train_step_fused(text, image, mask, *extra, labels, loss_kind=criterion.loss_kind,
@@ -187,16 +193,18 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
                 f"Grad Norm: {gn:.4f} |")
             batch_losses = []
         if test_loader is not None and (batch_idx % check_interval == 0 or batch_idx == total_batches):
-            t_loss, t_acc, t_f1, t_thr = test(model, test_loader, criterion, device, epoch, log)
+            t_loss, t_acc, t_f1, t_thr = test(model, test_loader, criterion, device, epoch, log,
+                                              image_transform=image_transform)
             if val_loader is not None:
-                v_loss, v_acc, v_f1, v_thr = test(model, val_loader, criterion, device, epoch, log)
+                v_loss, v_acc, v_f1, v_thr = test(model, val_loader, criterion, device, epoch, log,
+                                                  image_transform=image_transform)
                 log(f" VAL | Epoch [{epoch}] | Batch [{batch_idx}/{total_batches}] | Test Loss: {v_loss:.4f} | "
                     f"Acc: {v_acc:.4f} | F1: {v_f1:.4f} | thresh: {v_thr}")
             log(f" TEST | Epoch [{epoch}] | Batch [{batch_idx}/{total_batches}] | Test Loss: {t_loss:.4f} | "
                 f"Acc: {t_acc:.4f} | F1: {t_f1:.4f} | thresh: {t_thr}")
             if t_f1 > state.get("best_macro_f1", 0.0):
                 state["best_macro_f1"] = t_f1
-                evaluate(model, test_loader, t_thr, device, **(evaluate_kwargs or {}))
+                evaluate(model, test_loader, t_thr, device, image_transform=image_transform, **(evaluate_kwargs or {}))
             model.train()
     denom = len(train_loader.dataset) if hasattr(train_loader, "dataset") else n
     train_loss /= denom

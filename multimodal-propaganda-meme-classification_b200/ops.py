@@ -802,6 +802,27 @@ def u8_normalize(images, *, flip=None, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     return out
 
 
+def augment_jitter_rotate(img01, order, params, *, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """ColorJitter + RandomRotation + Normalize of the HEAD script's train transform (.py:224-233) over a batch already
+    resized / flipped / scaled to [0, 1].  img01: fp32 CUDA [n, 3, H, W]; order: int32 CUDA [n] (2 bits per operator,
+    first applied in the low bits; 0 brightness, 1 contrast, 2 saturation, 3 hue); params: fp32 CUDA [n, 8] (the three
+    factors, the hue shift, the inverse rotation matrix m00 m01 m10 m11).  Returns (normalised fp32 [n, 3, H, W],
+    per-image contrast means [n]).  torchvision's float-tensor semantics (csrc/augment_math.cuh)."""
+    _chk(img01, f32, "img01")
+    _chk(order, torch.int32, "order")
+    _chk(params, f32, "params")
+    if img01.dim() != 4 or img01.shape[1] != 3 or not img01.is_contiguous():
+        raise ValueError("img01 must be a contiguous [n, 3, H, W] fp32 tensor")
+    n, _, H, W = img01.shape
+    if tuple(order.shape) != (n,) or tuple(params.shape) != (n, 8) or not params.is_contiguous():
+        raise ValueError("order must be [n] and params a contiguous [n, 8]")
+    out = torch.empty_like(img01)
+    gray_mean = torch.empty(n, device=img01.device, dtype=f32)
+    _lib.call("b200mm_augment_jitter_rotate", _p(img01), _p(order), _p(params), n, H, W, _c3(mean), _c3(std),
+              _p(gray_mean), _p(out), _s())
+    return out, gray_mean
+
+
 def preprocess_u8(images, *, resize=256, crop=224, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     """images: list of uint8 CUDA tensors [H, W, 3] (decoded, any size).  Returns fp32 [n, 3, crop, crop] exactly as
     Resize(resize) -> CenterCrop(crop) -> ToTensor -> Normalize(mean, std) would (antialiased bilinear).

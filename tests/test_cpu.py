@@ -474,3 +474,47 @@ def test_dispatch_switch_defaults_and_side_queue_passthrough():
     q.run(lambda: ran.append(1))
     q.join()
     assert ran == [1]
+
+
+# ------------------------------------------------------------------------------------------------- augmentation math
+def test_augment_math_matches_torchvision_on_host(tmp_path):
+    """csrc/augment_math.cuh (the per-pixel arithmetic of augment.cu's kernels: ColorJitter in a random operator order
+    + RandomRotation + Normalize, HEAD script .py:224-233) compiled for the host agrees with torchvision's tensor path;
+    the draws come from data.GpuImageTransform, so the order encoding and the rotation matrices are covered too."""
+    import ctypes
+    from augment_ref import build_host_harness, torchvision_augment
+    from b200mm.data import GpuImageTransform
+    lib = ctypes.CDLL(build_host_harness(tmp_path))
+    torch.manual_seed(5)
+    n, H, W = 10, 96, 128
+    img = torch.rand(n, 3, H, W)
+    img[1, :, 20:60, 30:90] = 0.5                       # grey patch: the hue operator's max == min branch
+    img[2] = (img[2] * 255).round() / 255                # an image that really came from uint8 pixels
+    img[3] = 0.0
+    img[4] = 1.0
+    tr = GpuImageTransform("square", train=True, augment=True, seed=11)
+    perm, factors, angles = tr.draw_raw(n)
+    assert perm.sort(1).values.eq(torch.arange(4)).all()
+    assert factors[:, :3].min() >= 0.9 and factors[:, :3].max() <= 1.1 and factors[:, 3].abs().max() <= 0.1
+    assert angles.abs().max() <= 15.0
+    angles[5] = 0.0                                      # identity rotation: every source pixel in bounds
+    angles[6], angles[7] = 15.0, -15.0
+    order, params = tr.pack_augment(perm, factors, angles)
+    for i in range(n):                                   # low bits = first operator
+        assert [(int(order[i]) >> (2 * k)) & 3 for k in range(4)] == perm[i].tolist()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    ref = torchvision_augment(img, perm, factors, angles, mean, std)
+    out, gm = torch.empty_like(img), torch.empty(n)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    lib.host_augment_jitter_rotate(vp(img), vp(order), vp(params), n, H, W, (ctypes.c_float * 3)(*mean),
+                                   (ctypes.c_float * 3)(*std), vp(gm), vp(out))
+    d = (out - ref).abs()
+    # pointwise arithmetic is bit-faithful; only the contrast mean (summation order) moves the last bits
+    # (a source coordinate within an ulp of x.5 may round to the other neighbour under another BLAS: per-million events)
+    assert (d > 2e-5).any(dim=1).float().mean().item() < 1e-4, d.reshape(n, -1).max(1).values
+    assert d[5].max().item() < 2e-5 and d[3].max().item() < 2e-5 and d[4].max().item() < 2e-5
+    # the zero-filled corners of the rotated images are exactly Normalize(0)
+    corner = torch.tensor([(0 - m) / s for m, s in zip(mean, std)])
+    assert torch.allclose(out[6, :, 0, 0], corner, atol=1e-6) and torch.allclose(out[7, :, 0, -1], corner, atol=1e-6)
+    with pytest.raises(ValueError):
+        GpuImageTransform("center_crop", train=True, augment=True)

@@ -874,6 +874,92 @@ def test_prefetcher_runs_gpu_transform_on_uint8_batches(cuda_device):
             assert (image[k] - ref).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("H,W", [(224, 224), (96, 130)])
+def test_augment_jitter_rotate_matches_torchvision(ops, cuda_device, H, W):
+    """ColorJitter (random operator order) + RandomRotation(15) + Normalize of the HEAD script's train transform
+    (.py:224-233) as two kernels vs torchvision's tensor operators run on the same GPU with the same draws: element-wise,
+    every pixel (nearest-neighbour rotation: a wrong source pixel would be an O(1) error), partial tiles included."""
+    from augment_ref import torchvision_augment
+    from b200mm.data import GpuImageTransform
+    torch.manual_seed(40)
+    n = 9
+    img = torch.rand(n, 3, H, W, device=cuda_device)
+    img[1, :, 10:50, 20:80] = 0.5            # grey patch: hue's max == min branch
+    img[2] = (img[2] * 255).round() / 255
+    img[3] = 0.0
+    img[4] = 1.0
+    tr = GpuImageTransform("square", train=True, augment=True, seed=7)
+    perm, factors, angles = tr.draw_raw(n)
+    angles[5], angles[6], angles[7] = 0.0, 15.0, -15.0
+    order, params = tr.pack_augment(perm, factors, angles)
+    out, gm = ops.augment_jitter_rotate(img, order.to(cuda_device), params.to(cuda_device))
+    ref = torchvision_augment(img, perm, factors, angles, ops.IMAGENET_MEAN, ops.IMAGENET_STD)
+    d = (out - ref).abs()
+    # A source coordinate that lands within an ulp of x.5 may round to the other neighbour when the grid product is
+    # fused differently (cuBLAS bmm vs the kernel's one-rounding-per-op chain): a handful of pixels per million, each
+    # then off by a neighbouring pixel's value.  Everything else agrees to the contrast mean's last bits.
+    bad = (d > 2e-5).any(dim=1)
+    assert bad.float().mean().item() < 1e-4, bad.sum().item()
+    assert d[5].max().item() < 2e-5 and d[3].max().item() < 2e-5 and d[4].max().item() < 2e-5   # angle 0 / flat images
+    # last row / last column (partial 32 x 8 tiles at 96 x 130) and the zero-filled corners
+    assert (d[:, :, -1, :] > 2e-5).float().mean().item() < 5e-3 and (d[:, :, :, -1] > 2e-5).float().mean().item() < 5e-3
+    corner = torch.tensor([(0 - m) / s for m, s in zip(ops.IMAGENET_MEAN, ops.IMAGENET_STD)], device=cuda_device)
+    assert torch.allclose(out[6, :, 0, 0], corner, atol=1e-6) and torch.allclose(out[7, :, 0, -1], corner, atol=1e-6)
+    # the contrast mean is the grey mean of the image after the operators that precede contrast
+    for i in (0, 5):
+        x = img[i]
+        import torchvision.transforms.functional as TF
+        for fn in perm[i].tolist():
+            if fn == 1:
+                break
+            x = [lambda v: TF.adjust_brightness(v, float(factors[i, 0])), None,
+                 lambda v: TF.adjust_saturation(v, float(factors[i, 2])),
+                 lambda v: TF.adjust_hue(v, float(factors[i, 3]))][fn](x)
+        assert abs(gm[i].item() - TF.rgb_to_grayscale(x).mean().item()) < 1e-6
+    with pytest.raises(ValueError):
+        ops.augment_jitter_rotate(img, order.to(cuda_device)[:3], params.to(cuda_device))
+
+
+def test_gpu_transform_full_head_train_pipeline(cuda_device):
+    """data.GpuImageTransform(augment=True): Resize((224, 224)) + RandomHorizontalFlip + ColorJitter + RandomRotation +
+    ToTensor + Normalize on packed ragged uint8 images, against the torch restatement of every stage with the
+    transform's own draws (a second transform with the same seed replays them)."""
+    from augment_ref import torchvision_augment
+    from b200mm import ops as O
+    from b200mm.data import GpuImageTransform
+    torch.manual_seed(41)
+    sizes = [(300, 400), (640, 480), (224, 224), (97, 1001), (513, 259)]
+    imgs = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8) for h, w in sizes]
+    n = len(imgs)
+    buf, table = O.pack_images(imgs)
+    tr = GpuImageTransform("square", train=True, augment=True, seed=123)
+    out = tr.packed(buf.to(cuda_device), table.to(cuda_device))
+    assert out.shape == (n, 3, 224, 224) and out.dtype == torch.float32
+    replay = GpuImageTransform("square", train=True, augment=True, seed=123)
+    flip = torch.rand(n, generator=replay.gen) < 0.5
+    perm, factors, angles = replay.draw_raw(n)
+    mean = torch.tensor(O.IMAGENET_MEAN, device=cuda_device).view(3, 1, 1)
+    std = torch.tensor(O.IMAGENET_STD, device=cuda_device).view(3, 1, 1)
+    img01 = torch.stack([_torch_transform(im.to(cuda_device), square=True, flip=bool(flip[k])) * std + mean
+                         for k, im in enumerate(imgs)]).clamp(0, 1)
+    ref = torchvision_augment(img01, perm, factors, angles, O.IMAGENET_MEAN, O.IMAGENET_STD)
+    # the resize stage agrees to 2e-4 (test_preprocess_u8_packed_flip_square); the colour operators are 1.1-Lipschitz
+    # and the hue operator's slope is bounded by ~6, so a handful of pixels may move by a few 1e-3
+    d = (out - ref).abs()
+    assert d.max().item() < 2e-2 and d.mean().item() < 2e-4, (d.max().item(), d.mean().item())
+    # fixed-size batches take the u8_normalize route
+    x = torch.randint(0, 256, (4, 224, 224, 3), dtype=torch.uint8, device=cuda_device)
+    tr2 = GpuImageTransform("square", train=True, augment=True, seed=9)
+    out2 = tr2.fixed(x)
+    replay2 = GpuImageTransform("square", train=True, augment=True, seed=9)
+    flip2 = torch.rand(4, generator=replay2.gen) < 0.5
+    perm2, factors2, angles2 = replay2.draw_raw(4)
+    x01 = x.permute(0, 3, 1, 2).float() / 255.0
+    x01 = torch.where(flip2.view(-1, 1, 1, 1).to(cuda_device), x01.flip(-1), x01)
+    ref2 = torchvision_augment(x01, perm2, factors2, angles2, O.IMAGENET_MEAN, O.IMAGENET_STD)
+    assert (out2 - ref2).abs().max().item() < 1e-4
+
+
 # ------------------------------------------------------------------ BERT / RoBERTa / ViT support kernels
 def test_position_ids_match_transformers(ops, cuda_device):
     """RoBERTa / XLM-R position ids: cumsum(ids != pad) * (ids != pad) + pad

@@ -4,6 +4,8 @@ on identical synthetic inputs and identical random-init weights.
 Tolerances follow BASELINE.json north_star: activations / logits within 2e-2 relative error (bf16 engine vs fp32
 reference), loss trajectory within 1 %, argmax agreement >= 99.5 %.
 """
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -500,6 +502,55 @@ def test_fold_driver_setup_and_ensemble_tail(cuda_device, tmp_path):
     assert len(ids) == n_test and 0 <= thr <= 1 and 0 <= f1 <= 1 and tsv.check_label_tsv(str(out))
     one = tsv.read_prob_tsv(runs[0].prob_tsv)
     assert abs(mean_prob[0] - np.mean([dict(zip(*tsv.read_prob_tsv(r.prob_tsv)[0:3:2]))[ids[0]] for r in runs])) < 1e-12
+
+
+def test_fold_setup_with_device_side_train_transform(cuda_device, tmp_path):
+    """One ``setup(k)`` whose loaders ship DECODED uint8 images of ragged sizes (data.collate_packed) and whose image
+    transform -- the script's Resize / flip / ColorJitter / RandomRotation / Normalize, .py:222-235 -- runs on the device
+    (data.GpuImageTransform(augment=True)) for the train, validation and test loaders alike, as in the script."""
+    import b200mm
+    from b200mm import data as D, folds, tsv
+    from oracle import reference_model as R
+    cfg = R.TowerConfig.tiny()
+    tcfg = b200mm.TextConfig(vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings,
+                             dim=cfg.dim, n_layers=cfg.n_layers, n_heads=cfg.n_heads, hidden_dim=cfg.hidden_dim)
+    n_train, n_test, S = 20, 6, 32
+    data = R.synthetic_batch(n_train + n_test, S, cfg)
+    px = data["image"].shape[-1]
+    g = torch.Generator().manual_seed(3)
+    images = [torch.randint(0, 256, (px + 7 * (i % 5), px + 11 * (i % 3), 3), dtype=torch.uint8, generator=g)
+              for i in range(n_train + n_test)]
+    lab = ["propaganda" if i % 3 == 0 else "not_propaganda" for i in range(n_train + n_test)]
+    rec = lambda lo, hi: {"id": [f"img_{i}" for i in range(lo, hi)], "text": list(range(lo, hi)),
+                          "image": list(range(lo, hi)), "label": lab[lo:hi]}
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, r):
+            self.r = r
+
+        def __len__(self):
+            return len(self.r["id"])
+
+        def __getitem__(self, k):
+            i = self.r["text"][k]
+            return {"id": self.r["id"][k], "text": data["text"][i], "text_mask": data["text_mask"][i],
+                    "image": images[i], "label": torch.tensor(self.r["label"][k])}
+
+    def factory():
+        return b200mm.MultimodalClassifier(1, text_config=tcfg, image_config=b200mm.ImageConfig(layers=cfg.resnet_layers),
+                                           device=cuda_device, squeeze_output=True, pooling="cls")
+
+    tr = D.GpuImageTransform("square", crop=px, train=True, augment=True, seed=5)
+    lines = []
+    run = folds.setup(1, train_records=rec(0, n_train), test_records=rec(n_train, n_train + n_test),
+                      model_factory=factory, make_dataset=DS, device=cuda_device, batch_size=8, num_epochs=1,
+                      out_dir=str(tmp_path), collate_fn=D.collate_packed, image_transform=tr, log=lines.append)
+    h = run.history[0]
+    assert all(math.isfinite(h[k]) for k in ("train_loss", "test_loss", "val_loss")) and run.prob_tsv is not None
+    ids, _, probs, _ = tsv.read_prob_tsv(run.prob_tsv)
+    assert sorted(ids) == sorted(rec(n_train, n_train + n_test)["id"]) and all(0 <= p <= 1 for p in probs)
+    # the transform drew from its generator for every batch of every loader
+    assert tr.gen.get_state().ne(torch.Generator().manual_seed(5).get_state()).any()
 
 
 # ------------------------------------------------------------------ BASELINE configs 3-5: ViT + BERT / XLM-R towers
