@@ -134,10 +134,10 @@ class MultimodalClassifierHEAD(MultimodalClassifier):
 
     def get_params(self, lr):
         """Reference :645-664 (same substring rules, same group order)."""
+        from .loop_head import param_group_index
         groups = ([], [], [])
         for name, param in self.named_parameters():
-            k = 0 if "fusion_layer" in name else 1 if "text_model" in name else 2 if "image_model" in name else 0
-            groups[k].append(param)
+            groups[param_group_index(name)].append(param)
         return [{"params": groups[0], "lr": lr}, {"params": groups[1], "lr": lr * 0.8},
                 {"params": groups[2], "lr": lr * 0.8}]
 

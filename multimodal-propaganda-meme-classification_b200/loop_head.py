@@ -17,7 +17,8 @@ What is deliberately NOT reproduced: clipping before un
 the engine is bf16 with fp32 master weights and needs no loss scaling, so ``scaler`` is accepted and ignored; the
 fp32 branch's ``clip_grad_norm_(model.parameters(), 10.0)`` (:728-730) is ENFORCED by ``train`` on every step: a
 ``FusedAdam`` without a clip threshold gets ``max_grad_norm = 10.0`` (the clip is folded into the Adam kernel), any
-other optimizer is preceded by ``torch.nn.utils.clip_grad_norm_``.
+other optimizer is preceded by ``torch.nn.utils.clip_grad_norm_``; and the script's accidental switch to eval mode
+after its first mid-epoch check (``train(reference_eval_mode_quirk=True)`` reproduces it).
 """
 from __future__ import annotations
 
@@ -67,15 +68,28 @@ def stratified_kfold(labels, n_splits: int = 5, seed: int = 42):
         yield idx[test_folds != f], idx[test_folds == f]
 
 
+def param_group_index(name: str) -> int:
+    """The script's substring rules (:650-658), in its order: 'fusion_layer' -> group 0 (lr); 'text_model' -> group 1
+    (0.8 lr) -- which also captures ``caption_text_model.*``; 'image_model' -> group 2 (0.8 lr); anything else -> 0."""
+    return 0 if "fusion_layer" in name else 1 if "text_model" in name else 2 if "image_model" in name else 0
+
+
 def get_params(model, lr: float):
-    """Three param groups as in the HEAD script (:645-664): everything else @ lr, text tower @ 0.8 lr, image tower
-    @ 0.8 lr (engine names: ``bert.*`` is the text tower, ``resnet.*`` the image tower)."""
+    """Three param groups as in the HEAD script (:645-664): everything else @ lr, text tower(s) @ 0.8 lr, image tower
+    @ 0.8 lr.  A model with the script's attribute names (``text_model`` / ``image_model`` / ``fusion_layer``) is grouped
+    by the script's own substring rules; the two-tower engine model by its tower prefixes (``bert.*`` / ``resnet.*``)."""
     if hasattr(model, "get_params"):      # the three-tower HEAD model carries the reference's own method
         return model.get_params(lr)
-    text, image, other = [], [], []
-    for name, p in model.named_parameters():
-        (text if name.startswith("bert.") else image if name.startswith("resnet.") else other).append(p)
-    return [{"params": other, "lr": lr}, {"params": text, "lr": lr * 0.8}, {"params": image, "lr": lr * 0.8}]
+    named = list(model.named_parameters())
+    groups = ([], [], [])
+    if any("text_model" in n or "image_model" in n or "fusion_layer" in n for n, _ in named):
+        for name, p in named:
+            groups[param_group_index(name)].append(p)
+    else:
+        for name, p in named:
+            groups[1 if name.startswith("bert.") else 2 if name.startswith("resnet.") else 0].append(p)
+    return [{"params": groups[0], "lr": lr}, {"params": groups[1], "lr": lr * 0.8},
+            {"params": groups[2], "lr": lr * 0.8}]
 
 
 def _probs(output):
@@ -142,12 +156,21 @@ def evaluate(model, test_loader, t_optimal_threshold, device, *, fold=0, team_na
 
 
 def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0, scaler=None, *, test_loader=None,
-          val_loader=None, state=None, evaluate_kwargs=None, log=print, image_transform=None):
+          val_loader=None, state=None, evaluate_kwargs=None, log=print, image_transform=None,
+          reference_eval_mode_quirk: bool = False):
     """One epoch. ``state`` (dict) carries ``best_macro_f1`` across epochs like the script's global (:766-769).
     ``image_transform``: data.GpuImageTransform for uint8 image batches -- ``GpuImageTransform('square', train=True,
     augment=True)`` is the script's transform (:222-235: Resize((224, 224)), flip, ColorJitter, RandomRotation,
     Normalize), run on the device; it is also handed to the mid-epoch ``test`` / ``evaluate`` calls, as the script's
-    datasets all share that transform."""
+    datasets all share that transform.
+
+    ``reference_eval_mode_quirk``: the script's ``train`` never calls ``model.train()`` again after its mid-epoch
+    ``test`` / ``evaluate`` calls (:752-769 -> ``model.eval()`` at :780 / :838), so from the first check of every epoch
+    (batch ``total // 2``) to the epoch's end it keeps optimising in EVAL mode -- dropout off, BatchNorm normalising
+    with its running statistics.  By default this loop restores training mode after a check; ``True`` reproduces the
+    script to the letter (tests/test_cpu.py replays the script's own functions against it, tests/golden/
+    make_reference_golden.py), for a model whose backward supports eval-mode BatchNorm (any torch module; not the
+    fused engine step)."""
     model.train()
     state = state if state is not None else {}
     train_loss, correct, n = 0.0, 0, 0
@@ -156,6 +179,9 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
     batch_losses = []
     fused = _fused(criterion) and hasattr(model, "train_step_fused")
     fused_optim = hasattr(optimizer, "max_grad_norm")
+    if fused and reference_eval_mode_quirk:
+        raise ValueError("reference_eval_mode_quirk needs the generic (torch criterion) route: the fused engine step "
+                         "differentiates training-mode BatchNorm only")
     if fused_optim and optimizer.max_grad_norm is None:
         optimizer.max_grad_norm = CLIP_NORM              # reference: clip_grad_norm_(..., 10.0) on every step
     for batch_idx, data in enumerate(train_loader, 1):
@@ -205,7 +231,8 @@ def train(model, train_loader, criterion, optimizer, scheduler, device, epoch=0,
             if t_f1 > state.get("best_macro_f1", 0.0):
                 state["best_macro_f1"] = t_f1
                 evaluate(model, test_loader, t_thr, device, image_transform=image_transform, **(evaluate_kwargs or {}))
-            model.train()
+            if not reference_eval_mode_quirk:
+                model.train()
     denom = len(train_loader.dataset) if hasattr(train_loader, "dataset") else n
     train_loss /= denom
     accuracy = correct / denom

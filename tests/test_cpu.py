@@ -518,3 +518,121 @@ def test_augment_math_matches_torchvision_on_host(tmp_path):
     assert torch.allclose(out[6, :, 0, 0], corner, atol=1e-6) and torch.allclose(out[7, :, 0, -1], corner, atol=1e-6)
     with pytest.raises(ValueError):
         GpuImageTransform("center_crop", train=True, augment=True)
+
+
+# ------------------------------------------------------------------------------------------------- reference-run pinning
+def _refpin():
+    sys.path.insert(0, GOLD)
+    import refpin
+    return refpin, torch.load(os.path.join(GOLD, "reference_run_golden.pt"), weights_only=False)
+
+
+def _close(a, b, rel=2e-5):
+    return abs(a - b) <= rel * max(abs(a), abs(b), 1e-12)
+
+
+def test_oracle_reproduces_reference_classifier_run():
+    """tests/golden/reference_run_golden.pt holds what the REFERENCE'S OWN class and loop source
+    (Multimodal_example_task2C.txt:152-242, executed verbatim by tests/golden/make_reference_golden.py) produced; the
+    oracle -- same weights by name, same batches -- must reproduce it: state-dict layout, logits, loss, every parameter's
+    gradient norm, and a whole train() / test() pass with the script's dropout drawing from torch's generator."""
+    import torch.nn as nn
+    from oracle import reference_model as R
+    refpin, fx = _refpin()
+    fx = fx["organiser"]
+    torch.set_num_threads(1)
+    cfg = R.TowerConfig(vocab_size=refpin.VOCAB, max_position_embeddings=refpin.MAX_POS, n_layers=refpin.TEXT_LAYERS,
+                        hidden_dim=refpin.TEXT_FFN, resnet_layers=(1, 1, 1, 1), image_size=refpin.IMG)
+    torch.manual_seed(0)
+    m = refpin.reseed_by_name(R.MultimodalClassifier(2, cfg), seed=1)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == fx["state_keys"]
+    data = refpin.batches(4, 4, seed=11, captions=False)
+    R.zero_dropout(m).train()
+    b = data[0]
+    out = m(b["text"], b["image"], b["text_mask"])
+    loss = nn.CrossEntropyLoss()(out, b["label"])
+    loss.backward()
+    assert torch.allclose(out.detach(), fx["logits"], rtol=1e-4, atol=1e-5)
+    assert _close(loss.item(), fx["loss"].item())
+    assert torch.allclose(m.output_fc.weight.grad, fx["grad_output_fc"], rtol=1e-3, atol=1e-6)
+    assert torch.allclose(m.fusion_fc.bias.grad, fx["grad_fusion_bias"], rtol=1e-3, atol=1e-6)
+    got = refpin.param_norms(m, grads=True)
+    assert got.keys() == fx["grad_norms"].keys()
+    for k, v in fx["grad_norms"].items():
+        assert (v is None) == (got[k] is None) and (v is None or _close(got[k], v, 1e-3)), k
+    # the loops: the oracle's restatement of train() / test() against the script's own functions
+    m = refpin.reseed_by_name(R.MultimodalClassifier(2, cfg), seed=1)
+    opt = torch.optim.Adam(m.parameters(), lr=2e-5)
+    torch.manual_seed(123)
+    tr = R.train(m, refpin.ListLoader(data[:3]), nn.CrossEntropyLoss(), opt, torch.device("cpu"))
+    te = R.test(m, refpin.ListLoader(data[3:]), nn.CrossEntropyLoss(), torch.device("cpu"))
+    assert _close(tr[0], fx["train_return"][0], 1e-4) and tr[1] == fx["train_return"][1]
+    assert _close(te[0], fx["test_return"][0], 1e-4) and te[1] == fx["test_return"][1]
+    post = refpin.param_norms(m)
+    assert all(_close(post[k], v, 1e-5) for k, v in fx["post_train_norms"].items())
+
+
+def test_participant_model_and_loops_reproduce_reference_run(tmp_path):
+    """The participant script's classes and its train / test / evaluate functions
+    (Multimodal_example_task2C.py:307-392, 476-499, 562-685, 689-879, executed verbatim when the fixture was made) against
+    the oracle's three-tower model driven by THIS repo's host-side loops (b200mm.loop_head, generic route on the CPU):
+    parameter groups, forward / backward, the epoch's returned loss and accuracy, ROC threshold and macro-F1, and both TSVs
+    byte for byte."""
+    from oracle import reference_model as R
+    from b200mm import loop_head
+    from b200mm.loop import SigmoidFocalLoss
+    from torchvision.ops import sigmoid_focal_loss
+    from transformers import get_linear_schedule_with_warmup
+    refpin, fx = _refpin()
+    fx = fx["participant"]
+    torch.set_num_threads(1)
+    common = dict(vocab_size=refpin.VOCAB, max_position_embeddings=refpin.MAX_POS, n_layers=refpin.TEXT_LAYERS,
+                  hidden_dim=refpin.TEXT_FFN)
+    tcfg = R.TowerConfig(text_arch="bert", pad_token_id=0, layer_norm_eps=1e-12, type_vocab_size=2, **common)
+    ccfg = R.TowerConfig(text_arch="roberta", pad_token_id=1, layer_norm_eps=1e-5, type_vocab_size=1, **common)
+
+    def build():
+        torch.manual_seed(0)
+        return refpin.reseed_by_name(R.MultimodalClassifierHEAD(tcfg, ccfg, resnet_layers=(1, 1, 1, 1)), seed=2)
+
+    m = build()
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == fx["state_keys"]
+    groups = loop_head.get_params(m, 1e-5)
+    names = [sorted(n for n, p in m.named_parameters() if any(p is q for q in g["params"])) for g in groups]
+    assert names == fx["param_groups"] and [g["lr"] for g in groups] == fx["group_lrs"]
+    assert any(n.startswith("caption_text_model") for n in names[1])          # the substring quirk, from the script itself
+    data = refpin.batches(6, 6, seed=21, captions=True)
+    R.zero_dropout(m).train()
+    b = data[0]
+    out = m(b["text"], b["image"], b["text_mask"], b["caption_text"], b["caption_text_mask"])
+    loss = sigmoid_focal_loss(out, b["label"].float(), alpha=0.25, gamma=2.0, reduction="mean")
+    loss.backward()
+    assert torch.allclose(out.detach(), fx["logits"], rtol=1e-4, atol=1e-5)
+    assert _close(loss.item(), fx["loss"].item())
+    got = refpin.param_norms(m, grads=True)
+    for k, v in fx["grad_norms"].items():
+        assert (v is None) == (got[k] is None) and (v is None or _close(got[k], v, 1e-3)), k
+    # the script's epoch, replayed through b200mm.loop_head
+    m = build()
+    opt = torch.optim.Adam(loop_head.get_params(m, 1e-4))
+    sched = get_linear_schedule_with_warmup(opt, num_warmup_steps=1, num_training_steps=8)
+    test_loader, val_loader = refpin.ListLoader(data[4:5]), refpin.ListLoader(data[5:6])
+    ev = {"fold": 3, "out_dir": str(tmp_path), "run_id": "kevinmathew_resnet18_stub-text_stub-caption_concatenation.tsv"}
+    state, crit, cpu = {}, SigmoidFocalLoss(alpha=0.25, gamma=2.0), torch.device("cpu")
+    torch.manual_seed(321)
+    tr = loop_head.train(m, refpin.ListLoader(data[:4]), crit, opt, sched, cpu, 0, None, test_loader=test_loader,
+                         val_loader=val_loader, state=state, evaluate_kwargs=ev, log=lambda s: None,
+                         reference_eval_mode_quirk=True)
+    te = loop_head.test(m, test_loader, crit, cpu, 0, log=lambda s: None)
+    assert m.training is False and fx["training_flag_after_train"] is False     # the script leaves the model in eval mode
+    assert _close(tr[0], fx["train_return"][0], 1e-4) and _close(tr[1], fx["train_return"][1], 1e-9)
+    assert all(_close(a, b, 1e-4) for a, b in zip(te, fx["test_return"]))
+    assert _close(state["best_macro_f1"], fx["best_macro_f1"], 1e-9)
+    assert open(tmp_path / "task2C_kevinmathew.tsv").read() == fx["tsv_label"]
+    got_prob, want_prob = open(tmp_path / "task2C_kevinmathew_probs_fold_3.tsv").read(), fx["tsv_prob"]
+    assert [l.split("\t")[:2] + l.split("\t")[3:] for l in got_prob.splitlines()] == \
+        [l.split("\t")[:2] + l.split("\t")[3:] for l in want_prob.splitlines()]
+    for a, b in zip(got_prob.splitlines()[1:], want_prob.splitlines()[1:]):
+        assert _close(float(a.split("\t")[2]), float(b.split("\t")[2]), 1e-5)
+    post = refpin.param_norms(m)
+    assert all(_close(post[k], v, 1e-5) for k, v in fx["post_train_norms"].items())
