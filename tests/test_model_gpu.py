@@ -553,6 +553,112 @@ def test_fold_setup_with_device_side_train_transform(cuda_device, tmp_path):
     assert tr.gen.get_state().ne(torch.Generator().manual_seed(5).get_state()).any()
 
 
+# ------------------------------------------------------------------ vectors produced by the reference's own source
+def _reference_run_fixture():
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import refpin
+    return refpin, torch.load(os.path.join(gold, "reference_run_golden.pt"), weights_only=False)
+
+
+def _report_refrun(key, **values):
+    """measured numbers -> gpurun_out/parity_refrun_r02.json (committed copy under profiles/), pass or fail"""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
+                        "parity_refrun_r02.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[key] = values
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
+    print(key, json.dumps(values))
+
+
+def _norm_gaps(engine_grads, fixture_norms, skip=()):
+    """relative gap between the engine's gradient norms and the norms the reference run recorded (None = no gradient)."""
+    gaps = {}
+    for n, want in fixture_norms.items():
+        if want is None or want < 1e-6 or any(n.startswith(s) for s in skip):
+            continue
+        gaps[n] = abs(float(engine_grads[n].double().norm()) - want) / want
+    return gaps
+
+
+def test_engine_matches_reference_run_vectors(cuda_device):
+    """The CUDA path against tests/golden/reference_run_golden.pt -- logits, loss and gradient norms that the REFERENCE'S
+    OWN class source produced in the build container (tests/golden/make_reference_golden.py; .txt:152-197 and
+    .py:307-685 executed verbatim, fp32 CPU).  The oracle appears here only as the carrier of the name-keyed weights."""
+    import b200mm
+    from oracle import reference_model as R
+    refpin, fx = _reference_run_fixture()
+    # organiser model: DistilBERT (768 wide, 2 layers) + Bottleneck ResNet (1, 1, 1, 1), batch 4, S = 16, 64 px
+    o = fx["organiser"]
+    cfg = R.TowerConfig(vocab_size=refpin.VOCAB, max_position_embeddings=refpin.MAX_POS, n_layers=refpin.TEXT_LAYERS,
+                        hidden_dim=refpin.TEXT_FFN, resnet_layers=(1, 1, 1, 1), image_size=refpin.IMG)
+    torch.manual_seed(0)
+    carrier = refpin.reseed_by_name(R.MultimodalClassifier(2, cfg), seed=1)
+    tcfg = b200mm.TextConfig(vocab_size=cfg.vocab_size, max_position_embeddings=cfg.max_position_embeddings, dim=cfg.dim,
+                             n_layers=cfg.n_layers, n_heads=cfg.n_heads, hidden_dim=cfg.hidden_dim, dropout=0.0,
+                             attention_dropout=0.0)
+    eng = b200mm.MultimodalClassifier(2, text_config=tcfg, image_config=b200mm.ImageConfig(layers=cfg.resnet_layers),
+                                      head_dropout=0.0, device=cuda_device)
+    eng.load_reference_state_dict(carrier.state_dict())
+    b = _dev({k: v for k, v in refpin.batches(4, 4, seed=11, captions=False)[0].items() if k != "id"}, cuda_device)
+    eng.train()
+    eng.zero_grad()
+    logits, loss, _ = eng.train_step_fused(b["text"], b["image"], b["text_mask"], b["label"])
+    gaps = _norm_gaps(eng.reference_grad_dict(), o["grad_norms"], skip=("resnet.",))
+    img_gaps = _norm_gaps(eng.reference_grad_dict(), {k: v for k, v in o["grad_norms"].items() if k.startswith("resnet.")})
+    _report_refrun("organiser_model_vs_reference_run", logits_rel_err=rel(logits, o["logits"]),
+                   loss=loss.item(), loss_reference=o["loss"].item(), text_head_grad_norm_gap_max=max(gaps.values()),
+                   image_grad_norm_gap_median=sorted(img_gaps.values())[len(img_gaps) // 2],
+                   image_grad_norm_gap_max=max(img_gaps.values()))
+    assert rel(logits, o["logits"]) < 2e-2, rel(logits, o["logits"])
+    assert abs(loss.item() - o["loss"].item()) / o["loss"].item() < 1e-2
+    assert max(gaps.values()) < 6e-2, sorted(gaps.items(), key=lambda kv: -kv[1])[:5]
+    assert sorted(img_gaps.values())[len(img_gaps) // 2] < 6e-2, sorted(img_gaps.items(), key=lambda kv: -kv[1])[:5]
+    # participant model: BERT + RoBERTa caption tower (768 wide, 2 layers) + BasicBlock ResNet, batch 6
+    p = fx["participant"]
+    common = dict(vocab_size=refpin.VOCAB, max_position_embeddings=refpin.MAX_POS, n_layers=refpin.TEXT_LAYERS,
+                  hidden_dim=refpin.TEXT_FFN)
+    tc = R.TowerConfig(text_arch="bert", pad_token_id=0, layer_norm_eps=1e-12, type_vocab_size=2, **common)
+    cc = R.TowerConfig(text_arch="roberta", pad_token_id=1, layer_norm_eps=1e-5, type_vocab_size=1, **common)
+    torch.manual_seed(0)
+    carrier = refpin.reseed_by_name(R.MultimodalClassifierHEAD(tc, cc, resnet_layers=(1, 1, 1, 1)), seed=2)
+
+    def text_config(c, arch):
+        return b200mm.TextConfig(vocab_size=c.vocab_size, max_position_embeddings=c.max_position_embeddings, dim=c.dim,
+                                 n_layers=c.n_layers, n_heads=c.n_heads, hidden_dim=c.hidden_dim, dropout=0.0,
+                                 attention_dropout=0.0, layer_norm_eps=c.layer_norm_eps, pad_token_id=c.pad_token_id,
+                                 arch=arch, type_vocab_size=c.type_vocab_size)
+    eng = b200mm.MultimodalClassifierHEAD("concatenation", text_config=text_config(tc, "bert"),
+                                          caption_config=text_config(cc, "roberta"),
+                                          image_config=b200mm.ImageConfig(layers=(1, 1, 1, 1), block="basic",
+                                                                          num_outputs=0),
+                                          device=cuda_device, text_dropout=0.0, image_dropout=0.0)
+    eng.load_reference_state_dict(carrier.state_dict())
+    b = _dev({k: v for k, v in refpin.batches(6, 6, seed=21, captions=True)[0].items() if k != "id"}, cuda_device)
+    eng.train()
+    eng.zero_grad()
+    logits, loss, _ = eng.train_step_fused(b["text"], b["image"], b["text_mask"], b["caption_text"],
+                                           b["caption_text_mask"], b["label"])
+    _report_refrun("participant_model_vs_reference_run", logits_rel_err=rel(logits, p["logits"]), loss=loss.item(),
+                   loss_reference=p["loss"].item())
+    assert rel(logits, p["logits"]) < 3e-2, rel(logits, p["logits"])
+    assert abs(loss.item() - p["loss"].item()) / p["loss"].item() < 2e-2
+    names = {id(q): n for n, q in eng.named_parameters()}
+    # parameter groups as the script's own get_params formed them (the engine carries no unused pooler and may fuse
+    # projections, so membership is compared per top-level module)
+    assert [{names[id(q)].split(".")[0] for q in g["params"]} for g in eng.get_params(1e-5)] == \
+        [{n.split(".")[0] for n in g} for g in p["param_groups"]]
+
+
 # ------------------------------------------------------------------ BASELINE configs 3-5: ViT + BERT / XLM-R towers
 def _pair_vit(cuda_device, text_arch="bert", seq=32, batch=8, seed=7):
     """Engine / oracle pair of the config-3/4/5 graph (ViT image tower + BERT- or RoBERTa-style text tower, CLS
