@@ -183,7 +183,8 @@ int b200mm_u8_normalize_nchw(const void* src, const void* flip, int n, int H, in
  * flipped / scaled to [0, 1] (the two entry points above with mean 0, std 1).  img01, out: [n, 3, H, W] fp32 (out != img01);
  * order [n] int: 2 bits per operator, first applied in the low bits (0 brightness, 1 contrast, 2 saturation, 3 hue);
  * params [n, 8] fp32: brightness / contrast / saturation factors, hue shift, inverse rotation matrix m00 m01 m10 m11;
- * gray_mean [n] fp32: scratch, holds each image's contrast mean afterwards.  Semantics: torchvision's float-tensor path. */
+ * gray_mean [9 n] fp32: scratch; entries [0, n) hold each image's contrast mean afterwards.  Semantics: torchvision's
+ * float-tensor path. */
 int b200mm_augment_jitter_rotate(const float* img01, const int* order, const float* params, int n, int H, int W,
                                  const float* mean3, const float* std3, float* gray_mean, float* out, void* stream);
 

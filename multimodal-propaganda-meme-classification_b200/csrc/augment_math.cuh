@@ -5,7 +5,8 @@
 // Semantics = torchvision's float-tensor path ($SP/torchvision/transforms/_functional_tensor.py: _blend :258-261,
 // rgb_to_grayscale :148-168, _rgb2hsv :264-300, _hsv2rgb :303-321, adjust_hue :199-221; rotate = _gen_affine_grid
 // :579-602 + grid_sample(nearest, zeros, align_corners=False)), one rounding per torch op (no fused multiply-adds), so
-// that the kernel and torchvision agree to the last bit wherever the arithmetic is pointwise.  The reference runs the
+// that the kernel and torchvision agree to the last bit wherever the arithmetic is pointwise (Normalize's final
+// division is a multiplication by 1 / std: one ulp).  The reference runs the
 // same operators on PIL images, whose uint8 intermediates add up to 1/255 of rounding per operator.
 //
 // Host-compilable (plain C++ when __CUDACC__ is absent): tests/host/host_augment.cpp builds these functions for the CPU and
@@ -60,14 +61,13 @@ B200_HD float blend(float v, float other, float ratio, float one_minus) {
   return clamp01(add_rn(mul_rn(ratio, v), mul_rn(one_minus, other)));
 }
 
-// torch.remainder(x, 1.0) / torch.fmod for the value ranges that occur here
-B200_HD float remainder1(float x) {
-  float m = fmodf(x, 1.f);
-  if (m != 0.f && m < 0.f) m = add_rn(m, 1.f);
-  return m;
-}
+// torch.fmod(x, 1.0) for x >= 0 and torch.remainder(x, 1.0) for -1 < x: both equal x - floor(x) BIT FOR BIT in these
+// ranges (the subtraction is exact for x >= 0; for -1 < x < 0 it is the one rounding of x + 1 that remainder performs),
+// so the iterative fmodf is never needed.
+B200_HD float frac1(float x) { return sub_rn(x, floorf(x)); }
 
-// adjust_hue: rgb -> hsv, h = (h + shift) mod 1, hsv -> rgb
+// adjust_hue: rgb -> hsv, h = (h + shift) mod 1, hsv -> rgb.  _rgb2hsv evaluates three quotients (maxc - c) / cr and
+// multiplies two sums by zero; only the two quotients of the branch that survives are computed here -- same values.
 B200_HD void hue_shift(float& r, float& g, float& b, float shift) {
   const float maxc = fmaxf(fmaxf(r, g), b);
   const float minc = fminf(fminf(r, g), b);
@@ -75,15 +75,16 @@ B200_HD void hue_shift(float& r, float& g, float& b, float shift) {
   const float cr = sub_rn(maxc, minc);
   const float s = div_rn(cr, eqc ? 1.f : maxc);
   const float cd = eqc ? 1.f : cr;
-  const float rc = div_rn(sub_rn(maxc, r), cd);
-  const float gc = div_rn(sub_rn(maxc, g), cd);
-  const float bc = div_rn(sub_rn(maxc, b), cd);
-  const float hr = (maxc == r) ? sub_rn(bc, gc) : 0.f;
-  const float hg = (maxc == g && maxc != r) ? sub_rn(add_rn(2.f, rc), bc) : 0.f;
-  const float hb = (maxc != g && maxc != r) ? sub_rn(add_rn(4.f, gc), rc) : 0.f;
-  float h = add_rn(add_rn(hr, hg), hb);
-  h = fmodf(add_rn(div_rn(h, 6.f), 1.f), 1.f);
-  h = remainder1(add_rn(h, shift));
+  // maxc == r: h = bc - gc;  maxc == g (and != r): h = (2 + rc) - bc;  otherwise: h = (4 + gc) - rc
+  const bool is_r = maxc == r, is_g = maxc == g;
+  const float x1 = is_r ? b : is_g ? r : g;
+  const float x2 = is_r ? g : is_g ? b : r;
+  const float base = is_r ? 0.f : is_g ? 2.f : 4.f;
+  const float q1 = div_rn(sub_rn(maxc, x1), cd);
+  const float q2 = div_rn(sub_rn(maxc, x2), cd);
+  float h = sub_rn(add_rn(base, q1), q2);
+  h = frac1(add_rn(div_rn(h, 6.f), 1.f));          // torch.fmod(h / 6 + 1, 1)
+  h = frac1(add_rn(h, shift));                     // (h + hue_factor) % 1.0
   const float v = maxc;
   const float h6 = mul_rn(h, 6.f);
   const float fl = floorf(h6);
@@ -153,15 +154,20 @@ B200_HD void jitter_pixel(const Jitter& j, int first, int last, float mean, floa
   }
 }
 
-// RandomRotation(NEAREST, expand=False, fill=0): source pixel of output pixel (ox, oy).  m = the first two columns of
-// the inverse affine matrix [[m00, m01], [m10, m11]] (translation is zero for a rotation about the centre).  Follows
-// _gen_affine_grid + grid_sample's un-normalisation + nearbyint, each in fp32.  Returns false outside the image.
-B200_HD bool rotate_source(int ox, int oy, int W, int H, const float* m, int& sx, int& sy) {
+// RandomRotation(NEAREST, expand=False, fill=0).  m = the first two columns of the inverse affine matrix
+// [[m00, m01], [m10, m11]] (translation is zero for a rotation about the centre); _gen_affine_grid divides its rows by half
+// the width / height: t[k], the same for every pixel of an image (computed once per CTA, not per thread).
+B200_HD float rotate_scale(const float* m, int k, int W, int H) {
+  return div_rn(m[k], 0.5f * static_cast<float>(k < 2 ? W : H));
+}
+
+// Source pixel of output pixel (ox, oy): grid product, grid_sample's un-normalisation and nearbyint, each in fp32.
+// Returns false outside the image (zero fill).
+B200_HD bool rotate_source(int ox, int oy, int W, int H, const float* t, int& sx, int& sy) {
   const float bx = static_cast<float>(ox) + (0.5f - 0.5f * static_cast<float>(W));
   const float by = static_cast<float>(oy) + (0.5f - 0.5f * static_cast<float>(H));
-  const float hw = 0.5f * static_cast<float>(W), hh = 0.5f * static_cast<float>(H);
-  const float gx = add_rn(mul_rn(bx, div_rn(m[0], hw)), mul_rn(by, div_rn(m[1], hw)));
-  const float gy = add_rn(mul_rn(bx, div_rn(m[2], hh)), mul_rn(by, div_rn(m[3], hh)));
+  const float gx = add_rn(mul_rn(bx, t[0]), mul_rn(by, t[1]));
+  const float gy = add_rn(mul_rn(bx, t[2]), mul_rn(by, t[3]));
   const float ix = mul_rn(sub_rn(mul_rn(add_rn(gx, 1.f), static_cast<float>(W)), 1.f), 0.5f);
   const float iy = mul_rn(sub_rn(mul_rn(add_rn(gy, 1.f), static_cast<float>(H)), 1.f), 0.5f);
   const float rx = nearbyintf(ix), ry = nearbyintf(iy);
@@ -170,6 +176,9 @@ B200_HD bool rotate_source(int ox, int oy, int W, int H, const float* m, int& sx
   sy = static_cast<int>(ry);
   return true;
 }
+
+// Normalize: (v - mean) * (1 / std) -- within one ulp of torch's (v - mean) / std.
+B200_HD float normalize(float v, float mean, float inv_std) { return mul_rn(sub_rn(v, mean), inv_std); }
 
 }  // namespace aug
 }  // namespace b200

@@ -162,7 +162,7 @@ class GpuImageTransform:
         """Per-image draws of ColorJitter.get_params ($SP/torchvision/transforms/transforms.py:1237-1266: a permutation of
         the four operators, factors ~ U[max(0, 1 - x), 1 + x], hue shift ~ U[-hue, hue]) and RandomRotation.get_params
         (:1354-1361: angle ~ U[-degrees, degrees]): perm int64 [n, 4], factors fp32 [n, 4], angles fp64 [n] (degrees)."""
-        perm = torch.stack([torch.randperm(4, generator=self.gen) for _ in range(n)])
+        perm = torch.rand(n, 4, generator=self.gen).argsort(1)      # n uniform permutations of the four operators, one call
         u = torch.rand(n, 5, generator=self.gen)
         factors = torch.empty(n, 4)
         for k, x in enumerate(self.jitter[:3]):

@@ -817,10 +817,10 @@ def augment_jitter_rotate(img01, order, params, *, mean=IMAGENET_MEAN, std=IMAGE
     if tuple(order.shape) != (n,) or tuple(params.shape) != (n, 8) or not params.is_contiguous():
         raise ValueError("order must be [n] and params a contiguous [n, 8]")
     out = torch.empty_like(img01)
-    gray_mean = torch.empty(n, device=img01.device, dtype=f32)
+    scratch = torch.empty(9 * n, device=img01.device, dtype=f32)      # [n] means | [n, 8] partial sums
     _lib.call("b200mm_augment_jitter_rotate", _p(img01), _p(order), _p(params), n, H, W, _c3(mean), _c3(std),
-              _p(gray_mean), _p(out), _s())
-    return out, gray_mean
+              _p(scratch), _p(out), _s())
+    return out, scratch[:n]
 
 
 def preprocess_u8(images, *, resize=256, crop=224, mean=IMAGENET_MEAN, std=IMAGENET_STD):

@@ -23,19 +23,21 @@ extern "C" void host_augment_jitter_rotate(const float* img01, const int* order,
     }
     gray_mean[img] = static_cast<float>(acc / plane);
     float* dst = out + static_cast<long long>(img) * 3 * plane;
+    float t[4];
+    for (int k = 0; k < 4; ++k) t[k] = aug::rotate_scale(prm + 4, k, W, H);
     for (int oy = 0; oy < H; ++oy)
       for (int ox = 0; ox < W; ++ox) {
         float r = 0.f, g = 0.f, b = 0.f;
         int sx, sy;
-        if (aug::rotate_source(ox, oy, W, H, prm + 4, sx, sy)) {
+        if (aug::rotate_source(ox, oy, W, H, t, sx, sy)) {
           r = src[sy * W + sx];
           g = src[plane + sy * W + sx];
           b = src[2 * plane + sy * W + sx];
           aug::jitter_pixel(j, 0, 4, gray_mean[img], r, g, b);
         }
-        dst[oy * W + ox] = aug::div_rn(aug::sub_rn(r, mean3[0]), std3[0]);
-        dst[plane + oy * W + ox] = aug::div_rn(aug::sub_rn(g, mean3[1]), std3[1]);
-        dst[2 * plane + oy * W + ox] = aug::div_rn(aug::sub_rn(b, mean3[2]), std3[2]);
+        dst[oy * W + ox] = aug::normalize(r, mean3[0], 1.f / std3[0]);
+        dst[plane + oy * W + ox] = aug::normalize(g, mean3[1], 1.f / std3[1]);
+        dst[2 * plane + oy * W + ox] = aug::normalize(b, mean3[2], 1.f / std3[2]);
       }
   }
 }

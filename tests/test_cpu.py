@@ -636,3 +636,54 @@ def test_participant_model_and_loops_reproduce_reference_run(tmp_path):
         assert _close(float(a.split("\t")[2]), float(b.split("\t")[2]), 1e-5)
     post = refpin.param_norms(m)
     assert all(_close(post[k], v, 1e-5) for k, v in fx["post_train_norms"].items())
+
+
+def test_augment_semantics_against_the_scripts_pil_transform(tmp_path):
+    """The participant script runs its transform on PIL images (.py:222-235).  Same draws, same images: the float-tensor
+    semantics the kernels implement stay within PIL's own uint8 quantisation of it (every PIL operator truncates to
+    uint8, hue works at 1/255 resolution, its nearest-neighbour rotation picks a neighbouring source pixel here and
+    there): mean deviation below 3/255 of the pixel range, 99 % of the values within 12/255."""
+    import ctypes
+    import torch.nn.functional as F
+    import torchvision.transforms as T
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    from augment_ref import build_host_harness
+    from b200mm.data import GpuImageTransform
+    lib = ctypes.CDLL(build_host_harness(tmp_path))
+    torch.manual_seed(0)
+    n = 4
+    imgs = []
+    for i in range(n):                                     # smooth synthetic "photos" of different sizes
+        h, w = 300 + 40 * i, 420 - 30 * i
+        im = F.interpolate(torch.rand(1, 3, 12, 16), size=(h, w), mode="bicubic", align_corners=False).clamp(0, 1)[0]
+        imgs.append((im * 255).round().byte().permute(1, 2, 0).contiguous())
+    tr = GpuImageTransform("square", train=True, augment=True, seed=4)
+    flip = torch.rand(n, generator=tr.gen) < 0.5
+    perm, factors, angles = tr.draw_raw(n)
+    order, params = tr.pack_augment(perm, factors, angles)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    # this side: the resize the preprocessing kernel computes (torch's antialiased bilinear, test_preprocess_u8_*),
+    # the flip, then the augmentation arithmetic of csrc/augment_math.cuh
+    img01 = torch.stack([F.interpolate(im.permute(2, 0, 1).float()[None], size=(224, 224), mode="bilinear",
+                                       antialias=True, align_corners=False)[0] / 255.0 for im in imgs]).clamp(0, 1)
+    img01 = torch.where(flip.view(-1, 1, 1, 1), img01.flip(-1), img01).contiguous()
+    out, gm = torch.empty_like(img01), torch.empty(n)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    lib.host_augment_jitter_rotate(vp(img01), vp(order), vp(params), n, 224, 224, (ctypes.c_float * 3)(*mean),
+                                   (ctypes.c_float * 3)(*std), vp(gm), vp(out))
+    # the script's side: its Compose, operator by operator, on the PIL image
+    ref = torch.empty_like(out)
+    for i, im in enumerate(imgs):
+        x = T.Resize((224, 224))(Image.fromarray(im.numpy()))
+        if flip[i]:
+            x = TF.hflip(x)
+        b, c, s, h = (float(v) for v in factors[i])
+        for fn in perm[i].tolist():
+            x = [lambda v: TF.adjust_brightness(v, b), lambda v: TF.adjust_contrast(v, c),
+                 lambda v: TF.adjust_saturation(v, s), lambda v: TF.adjust_hue(v, h)][fn](x)
+        x = TF.rotate(x, float(angles[i]))                 # RandomRotation's defaults: NEAREST, expand=False, fill=0
+        ref[i] = TF.normalize(TF.to_tensor(x), mean, std)
+    d = (out - ref).abs() * torch.tensor(std).view(1, 3, 1, 1) * 255.0       # back to units of one uint8 step
+    assert d.mean().item() < 3.0 and d.flatten().quantile(0.99).item() < 12.0, (d.mean().item(),
+                                                                               d.flatten().quantile(0.99).item())

@@ -874,7 +874,7 @@ def test_prefetcher_runs_gpu_transform_on_uint8_batches(cuda_device):
             assert (image[k] - ref).abs().max().item() < 2e-4
 
 
-@pytest.mark.parametrize("H,W", [(224, 224), (96, 130)])
+@pytest.mark.parametrize("H,W", [(224, 224), (96, 130), (45, 67)])
 def test_augment_jitter_rotate_matches_torchvision(ops, cuda_device, H, W):
     """ColorJitter (random operator order) + RandomRotation(15) + Normalize of the HEAD script's train transform
     (.py:224-233) as two kernels vs torchvision's tensor operators run on the same GPU with the same draws: element-wise,
