@@ -188,6 +188,26 @@ int b200mm_u8_normalize_nchw(const void* src, const void* flip, int n, int H, in
 int b200mm_augment_jitter_rotate(const float* img01, const int* order, const float* params, int n, int H, int W,
                                  const float* mean3, const float* std3, float* gray_mean, float* out, void* stream);
 
+/* ---- JPEG decode, split for the GPU (the decode inside the reference's Dataset: `Image.open(path).convert("RGB")`,
+ * example_scripts/Multimodal_example_task2C.txt:50, Multimodal_example_task2C.py:270).  HOST functions (no CUDA call; meant
+ * for loader workers): marker parsing + Huffman decoding of 8-bit baseline / progressive files, grayscale or YCbCr with
+ * 4:4:4 / 4:2:2 / 4:2:0 sampling.  Return 0, B200MM_JPEG_UNSUPPORTED (-10: arithmetic coding, 12-bit, CMYK, RGB-coded,
+ * other sampling factors -- decode those with the caller's loader) or B200MM_JPEG_CORRUPT (-11, incl. truncated files).
+ * info: int[32] = width, height, components, progressive, hs, vs, blocks per row [3], block rows [3] (both padded to whole
+ * MCUs), real component width [3], height [3], first coefficient of each component [3], coefficients in total, restart
+ * interval.  coefs: info[21] int16, 64 per block in natural order; qtabs: [3][64] uint16, natural order. */
+int b200mm_jpeg_parse(const void* data, long long len, int* info);
+int b200mm_jpeg_entropy_decode(const void* data, long long len, short* coefs, unsigned short* qtabs, int* info);
+/* DEVICE: dequantisation + inverse DCT + chroma up-sampling + YCbCr -> RGB of a whole batch in two launches, bit-identical to
+ * libjpeg-turbo's default path (JDCT_ISLOW, fancy up-sampling), i.e. to Pillow's pixels.  coefs: the batch's coefficients;
+ * qtabs [n][3][64]; table: int64 [n][32] = width, height, components (0: skip, the caller supplies the pixels), hs, vs,
+ * blocks per row [3], block rows [3], component width [3], height [3], first coefficient in `coefs` [3] (int16 elements,
+ * multiples of 8), first byte of each component plane in `planes` [3] (multiples of 8), first byte of the image in `out`,
+ * blocks of the image in total.  out: packed uint8 RGB, image i = [height][width][3] -- the layout
+ * b200mm_preprocess_u8_packed reads.  max_blocks / max_w / max_h: maxima over the batch (grid sizing). */
+int b200mm_jpeg_reconstruct(const short* coefs, const unsigned short* qtabs, const long long* table, int n, int max_blocks,
+                            int max_w, int max_h, void* planes, void* out, void* stream);
+
 /* ---- head + loss, optimizer --------------------------------------------------------------------------------------
  * output layer fused with the loss: example_scripts/Multimodal_example_task2C.txt:195 (output_fc) + :214, :248
  * (nn.CrossEntropyLoss); loss_kind 1 = torchvision.ops.sigmoid_focal_loss (Multimodal_example_task2C.py:167);

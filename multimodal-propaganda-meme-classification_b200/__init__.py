@@ -9,6 +9,7 @@ reference repository and is not a valid Python identifier).  Public surface = th
     ensemble.*                                    example_scripts/combine_preds.py
     setup(k) / run_folds / combine_folds          example_scripts/Multimodal_example_task2C.py:50-192, 882-885
     ConvNeXtTiny, BertPoolerModel, extract_features   baselines/extract_feat.py:52-67, 103-112
+    decode_jpeg / collate_jpeg                    the Dataset's Image.open(path).convert("RGB") (.txt:50; .py:270), split host / GPU
 """
 __version__ = "0.1.0"
 
@@ -38,6 +39,8 @@ _LAZY = {
     "setup": ("folds", "setup"),
     "run_folds": ("folds", "run_folds"),
     "combine_folds": ("folds", "combine_folds"),
+    "decode_jpeg": ("jpeg", "decode_jpeg"),
+    "collate_jpeg": ("jpeg", "collate_jpeg"),
 }
 
 

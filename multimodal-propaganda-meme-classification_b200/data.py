@@ -11,12 +11,14 @@ SURVEY.md §3.1).  Here the host only does what must stay there:
   * ``collate_packed``    packs the batch's images into ONE pinned byte buffer + an offset / height / width table
                           (ops.pack_images): two host->device copies per batch whatever its size, 4x fewer bytes than
                           fp32 pixels even before counting the resize;
+  * ``file_bytes_loader`` + ``jpeg.collate_jpeg``   (optional) the worker only Huffman-decodes the JPEG; the rest of the
+                          decode runs on the GPU, bit-identical to Pillow (csrc/jpeg_decode.cu);
   * ``GpuImageTransform`` Resize / CenterCrop (or Resize((224, 224))) / RandomHorizontalFlip / ToTensor / Normalize as ONE
                           kernel on the copy stream (csrc/preprocess.cu), called by ``loop.DevicePrefetcher``; with
                           ``augment=True`` the HEAD script's whole train transform (.py:222-235): + ColorJitter(.1, .1,
                           .1, .1) + RandomRotation(15) as two more kernels (csrc/augment.cu).
 
-JPEG decode stays on the host (PIL, as in the reference).  The augmentations follow torchvision's float-tensor
+The augmentations follow torchvision's float-tensor
 operators with per-image parameters drawn as ``ColorJitter.get_params`` / ``RandomRotation.get_params`` draw them; the
 reference applies the same operators to PIL images (uint8 intermediates: up to 1/255 of rounding per operator).
 """
@@ -71,6 +73,13 @@ def pil_loader(path):
     from PIL import Image
     with Image.open(path) as im:
         return torch.from_numpy(np.asarray(im.convert("RGB"), dtype=np.uint8).copy())
+
+
+def file_bytes_loader(path):
+    """The image FILE as a uint8 1-D tensor: for ``collate_fn=jpeg.collate_jpeg``, which Huffman-decodes the batch in the
+    loader worker and leaves inverse DCT / up-sampling / colour conversion to the GPU (pixels equal ``pil_loader``'s)."""
+    with open(path, "rb") as f:
+        return torch.frombuffer(bytearray(f.read()), dtype=torch.uint8)
 
 
 class MemeDataset(Dataset):

@@ -54,6 +54,10 @@ def _image_to_device(data, device, image_transform=None):
     transform: ``image_transform`` (a data.GpuImageTransform) or, by default, the organiser script's deterministic
     evaluation form (Resize(256) / CenterCrop(224) / Normalize)."""
     global _EVAL_TRANSFORM
+    if "jpeg_coefs" in data:           # entropy-decoded JPEG batch (jpeg.collate_jpeg): finish the decode on the device
+        from .jpeg import reconstruct_batch
+        data = dict(data)
+        data["image_packed"], data["image_table"] = reconstruct_batch(data, device)
     if "image_packed" in data or data["image"].dtype == torch.uint8:
         tr = image_transform
         if tr is None:
@@ -91,7 +95,8 @@ class DevicePrefetcher:
     tensors (``DataLoader(pin_memory=True)`` / ``data.collate_packed``); pageable ones are copied the way the
     reference copies them.
 
-    ``image`` may arrive in three forms: fp32 [B, 3, H, W] (what the reference's CPU transform produces -- copied as
+    ``image`` may arrive in four forms (the fourth: ``jpeg_coefs`` / ``jpeg_qtabs`` / ``jpeg_table`` from
+    jpeg.collate_jpeg -- files entropy-decoded in the loader worker, reconstructed to pixels here on the device): fp32 [B, 3, H, W] (what the reference's CPU transform produces -- copied as
     is), uint8 [B, H, W, 3] at network resolution, or a packed variable-size batch (``image_packed`` +
     ``image_table``, data.collate_packed).  The uint8 forms cross PCIe at a quarter of the bytes and are turned into
     the normalised fp32 tensor by ONE kernel on the copy stream (``image_transform``, a data.GpuImageTransform;
@@ -119,6 +124,9 @@ class DevicePrefetcher:
                     if self.pin and not t.is_cuda and not t.is_pinned():
                         t = t.pin_memory()
                     out[k] = t.to(self.device, non_blocking=True)
+            if "jpeg_coefs" in data:   # coefficients cross PCIe; IDCT / up-sampling / colour conversion run here
+                from .jpeg import reconstruct_batch
+                out["image_packed"], out["image_table"] = reconstruct_batch(data, self.device)
             if "image_packed" in out:
                 out["image"] = self._transform().packed(out.pop("image_packed"), out.pop("image_table"))
             elif "image" in out and out["image"].dtype == torch.uint8:

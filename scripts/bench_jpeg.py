@@ -1,0 +1,105 @@
+"""Split JPEG decode (csrc/jpeg_decode.cu) at the headline batch: 256 files of ~500 x 600 px, 4:2:0, quality 85.
+Times, per batch: Pillow's full decode on the host (what the reference's Dataset does per sample), the host half of the
+split decoder (Huffman decoding into coefficients), and the device half (two launches; CUDA events on the launching
+stream; the batch's coefficients and planes exceed the 126 MB L2).  Writes gpurun_out/jpeg_bench_r02.json.
+
+    python scripts/bench_jpeg.py [--n 256] [--iters 10]
+"""
+import argparse
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import b200mm  # noqa: E402
+from b200mm import jpeg  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    rng = np.random.default_rng(0)
+    uniq = []
+    for i in range(32):
+        h, w = 440 + 8 * (i % 16), 560 + 12 * (i % 8)
+        base = torch.from_numpy(rng.random((1, 3, 14, 18), dtype=np.float32))
+        im = F.interpolate(base, size=(h, w), mode="bicubic", align_corners=False)[0]
+        im = im + 0.03 * torch.from_numpy(rng.standard_normal((3, h, w)).astype(np.float32))
+        b = io.BytesIO()
+        Image.fromarray((im.clamp(0, 1) * 255).byte().permute(1, 2, 0).numpy()).save(
+            b, "JPEG", quality=85, subsampling=2, progressive=bool(i & 1))
+        uniq.append(b.getvalue())
+    files = [uniq[i % len(uniq)] for i in range(a.n)]
+    t0 = time.perf_counter()
+    pixels = 0
+    for f in files:
+        px = np.asarray(Image.open(io.BytesIO(f)).convert("RGB"))
+        pixels += px.shape[0] * px.shape[1]
+    t_pil = time.perf_counter() - t0
+    dev = torch.device("cuda:0")
+    torch.zeros(1, device=dev)                            # CUDA context up before any pinned allocation is timed
+    jpeg.pack_jpeg_batch(files[:8])
+    t0 = time.perf_counter()
+    batch = jpeg.pack_jpeg_batch(files)
+    t_host = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for f in files:
+        jpeg.entropy_decode(f)
+    t_entropy = time.perf_counter() - t0
+    for _ in range(3):
+        jpeg.reconstruct_batch(batch, dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        jpeg.reconstruct_batch(batch, dev)               # H2D of the coefficients + both kernels, as the prefetcher runs it
+    e1.record()
+    torch.cuda.synchronize()
+    t_dev_with_copy = e0.elapsed_time(e1) / a.iters
+    # the two kernels alone, operands resident
+    from b200mm import _lib
+    coefs, qtabs, table = (batch[k].to(dev) for k in ("jpeg_coefs", "jpeg_qtabs", "jpeg_table"))
+    mb, mw, mh, pb, ob = (int(v) for v in batch["jpeg_meta"])
+    planes = torch.empty(pb, dtype=torch.uint8, device=dev)
+    rgb = torch.empty(ob, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    args = (coefs.data_ptr(), qtabs.data_ptr(), table.data_ptr(), a.n, mb, mw, mh, planes.data_ptr(), rgb.data_ptr(), st)
+    for _ in range(3):
+        _lib.call("b200mm_jpeg_reconstruct", *args)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.iters):
+        _lib.call("b200mm_jpeg_reconstruct", *args)
+    e1.record()
+    torch.cuda.synchronize()
+    t_dev = e0.elapsed_time(e1) / a.iters
+    coef_bytes = batch["jpeg_coefs"].numel() * 2
+    plane_bytes, out_bytes = int(batch["jpeg_meta"][3]), int(batch["jpeg_meta"][4])
+    out = {"images": a.n, "megapixels": pixels / 1e6, "file_bytes": sum(len(f) for f in files),
+           "pillow_full_decode_ms_per_batch_1thread": t_pil * 1e3,
+           "host_entropy_decode_ms_per_batch_1thread": t_entropy * 1e3,
+           "host_entropy_decode_and_pack_pinned_ms_per_batch_1thread": t_host * 1e3,
+           "host_work_offloaded_frac": 1.0 - t_entropy / t_pil,
+           "device_kernels_ms_per_batch": t_dev,
+           "device_with_h2d_ms_per_batch": t_dev_with_copy,
+           "device_algorithmic_bytes": coef_bytes + 2 * plane_bytes + out_bytes,
+           "device_gbs": (coef_bytes + 2 * plane_bytes + out_bytes) / t_dev / 1e6,
+           "h2d_bytes_coefficients": coef_bytes, "h2d_bytes_if_pixels": out_bytes,
+           "note": "device bytes: coefficients read + planes written + planes read + RGB written"}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "jpeg_bench_r02.json"), "w"), indent=1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

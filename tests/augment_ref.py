@@ -39,3 +39,53 @@ def build_host_harness(out_dir):
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", csrc,
                     os.path.join(ROOT, "tests", "host", "host_augment.cpp"), "-o", lib], check=True)
     return lib
+
+
+def build_host_jpeg_harness(out_dir):
+    """g++ build of tests/host/host_jpeg.cpp (csrc/jpeg_math.cuh -- the kernels' integer arithmetic -- for the CPU)."""
+    lib = os.path.join(str(out_dir), "libhost_jpeg.so")
+    csrc = os.path.join(ROOT, "multimodal-propaganda-meme-classification_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", csrc, os.path.join(ROOT, "tests", "host", "host_jpeg.cpp"),
+                    "-o", lib], check=True)
+    return lib
+
+
+def jpeg_cases(seed=0):
+    """(description, file bytes) over the supported set: baseline / progressive, 4:4:4 / 4:2:2 / 4:2:0 / grayscale,
+    optimised tables, restart intervals, sizes that are not multiples of the MCU, one-pixel images, extreme qualities."""
+    import io
+
+    import numpy as np
+    import torch.nn.functional as F
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+
+    def photo(h, w):
+        base = torch.from_numpy(rng.random((1, 3, 9, 11), dtype=np.float32))
+        im = F.interpolate(base, size=(h, w), mode="bicubic", align_corners=False)[0]
+        im = im + 0.08 * torch.from_numpy(rng.standard_normal((3, h, w)).astype(np.float32))
+        return (im.clamp(0, 1) * 255).byte().permute(1, 2, 0).numpy()
+
+    def enc(arr, gray=False, **kw):
+        b = io.BytesIO()
+        (Image.fromarray(arr).convert("L") if gray else Image.fromarray(arr)).save(b, "JPEG", **kw)
+        return b.getvalue()
+
+    cases = []
+    for (h, w) in [(64, 64), (37, 53), (1, 1), (8, 17), (200, 301), (2, 3), (33, 4), (5, 3)]:
+        for sub in (0, 1, 2):
+            for prog in (False, True):
+                q = (30, 75, 95)[(h + sub + prog) % 3]
+                cases.append((f"{h}x{w} sub{sub} prog{prog} q{q}", enc(photo(h, w), quality=q, subsampling=sub,
+                                                                       progressive=prog, optimize=bool((h + sub) & 1))))
+        cases.append((f"{h}x{w} gray", enc(photo(h, w), gray=True, quality=80)))
+        cases.append((f"{h}x{w} gray prog", enc(photo(h, w), gray=True, quality=60, progressive=True)))
+    noise = rng.integers(0, 256, (123, 211, 3), dtype=np.uint8)
+    for kw in (dict(quality=100, subsampling=0), dict(quality=1, subsampling=2),
+               dict(quality=100, subsampling=2, progressive=True), dict(quality=90, subsampling=2, restart_marker_blocks=3),
+               dict(quality=90, subsampling=1, restart_marker_rows=1),
+               dict(quality=85, subsampling=2, progressive=True, restart_marker_rows=2),
+               dict(quality=50, subsampling=0, restart_marker_blocks=1)):
+        cases.append((f"noise {kw}", enc(noise, **kw)))
+        cases.append((f"photo {kw}", enc(photo(240, 320), **kw)))
+    return cases

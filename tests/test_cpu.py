@@ -687,3 +687,67 @@ def test_augment_semantics_against_the_scripts_pil_transform(tmp_path):
     d = (out - ref).abs() * torch.tensor(std).view(1, 3, 1, 1) * 255.0       # back to units of one uint8 step
     assert d.mean().item() < 3.0 and d.flatten().quantile(0.99).item() < 12.0, (d.mean().item(),
                                                                                d.flatten().quantile(0.99).item())
+
+
+# ------------------------------------------------------------------------------------------------- JPEG decode (split host / GPU)
+def test_jpeg_split_decode_is_bit_identical_to_pillow_on_host(tmp_path):
+    """The product's host half (b200mm_jpeg_entropy_decode in libb200mm.so: marker parsing + Huffman decoding) followed by
+    the kernels' integer arithmetic compiled for the host (csrc/jpeg_math.cuh via tests/host/host_jpeg.cpp) reproduces
+    ``Image.open(...).convert("RGB")`` -- the reference's loader (.txt:50; .py:270) -- PIXEL FOR PIXEL over baseline and
+    progressive files of every supported sampling, restart intervals and awkward sizes."""
+    import ctypes
+    import io
+    from PIL import Image
+    from augment_ref import build_host_jpeg_harness, jpeg_cases
+    from b200mm import jpeg
+    host = ctypes.CDLL(build_host_jpeg_harness(tmp_path))
+    n_prog = n_dri = 0
+    for name, data in jpeg_cases():
+        ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        coefs, qtabs, info = jpeg.entropy_decode(data)
+        assert (info[0], info[1]) == (ref.shape[1], ref.shape[0]), name
+        out = np.empty_like(ref)
+        host.host_jpeg_reconstruct(ctypes.c_void_p(coefs.ctypes.data), ctypes.c_void_p(qtabs.ctypes.data),
+                                   ctypes.c_void_p(info.ctypes.data), ctypes.c_void_p(out.ctypes.data))
+        assert np.array_equal(out, ref), (name, int(np.abs(out.astype(int) - ref.astype(int)).max()))
+        n_prog += int(info[3])
+        n_dri += int(info[22] > 0)
+    assert n_prog > 20 and n_dri >= 8
+
+
+def test_jpeg_unsupported_and_corrupt_files_fail_loudly():
+    """CMYK and RGB-coded files are refused (B200MM_JPEG_UNSUPPORTED -> UnsupportedJpeg); truncated files and non-JPEG
+    bytes are errors like Pillow's OSError; 'pil' mode ships such files as pixels decoded by the reference's loader."""
+    import io
+    from PIL import Image
+    from b200mm import jpeg
+    rng = np.random.default_rng(1)
+    arr = rng.integers(0, 256, (40, 56, 3), dtype=np.uint8)
+
+    def enc(im, fmt="JPEG", **kw):
+        b = io.BytesIO()
+        im.save(b, fmt, **kw)
+        return b.getvalue()
+
+    good = enc(Image.fromarray(arr), quality=80)
+    cmyk = enc(Image.fromarray(arr).convert("CMYK"))
+    rgb_coded = enc(Image.fromarray(arr), keep_rgb=True)
+    png = enc(Image.fromarray(arr), "PNG")
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.entropy_decode(cmyk)
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.entropy_decode(rgb_coded)
+    with pytest.raises(OSError):
+        jpeg.entropy_decode(good[: len(good) // 2])
+    with pytest.raises(OSError):
+        jpeg.entropy_decode(png)
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.pack_jpeg_batch([good, cmyk], pin=False)
+    b = jpeg.pack_jpeg_batch([good, cmyk, png, rgb_coded], pin=False, unsupported="pil")
+    assert sorted(i for i, _ in b["jpeg_raw"]) == [1, 2, 3] and b["jpeg_table"][:, 2].tolist() == [3, 0, 0, 0]
+    for i, px in b["jpeg_raw"]:
+        assert px.shape == (40, 56, 3)
+    assert torch.equal(dict(b["jpeg_raw"])[2], torch.from_numpy(arr))          # the PNG's pixels, lossless
+    # geometry of the batch table: offsets are aligned and disjoint
+    t = b["jpeg_table"]
+    assert (t[:, 23] % 16 == 0).all() and t[1, 23] - t[0, 23] >= 40 * 56 * 3

@@ -960,6 +960,69 @@ def test_gpu_transform_full_head_train_pipeline(cuda_device):
     assert (out2 - ref2).abs().max().item() < 1e-4
 
 
+def test_jpeg_reconstruct_is_bit_identical_to_pillow(cuda_device):
+    """Host Huffman decode + the two device kernels (dequantise + IDCT, up-sampling + colour conversion) over a batch of
+    files of every supported coding = ``Image.open(...).convert("RGB")`` PIXEL FOR PIXEL (the reference's loader,
+    .txt:50; .py:270); one batch, ragged sizes, images one pixel wide included."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from augment_ref import jpeg_cases
+    from b200mm import jpeg
+    cases = jpeg_cases()
+    got = jpeg.decode_jpeg([d for _, d in cases], device=cuda_device)
+    torch.cuda.synchronize()
+    assert len(got) == len(cases)
+    for (name, data), g in zip(cases, got):
+        ref = torch.from_numpy(np.asarray(Image.open(io.BytesIO(data)).convert("RGB")).copy())
+        assert g.shape == ref.shape and g.dtype == torch.uint8, name
+        assert torch.equal(g.cpu(), ref), (name, (g.cpu().int() - ref.int()).abs().max().item())
+
+
+def test_jpeg_batches_through_the_prefetcher(cuda_device):
+    """jpeg.collate_jpeg batches (coefficients cross PCIe) come out of loop.DevicePrefetcher as the tensor the reference's
+    Dataset would have produced from Pillow's pixels; with unsupported='pil' a CMYK file and a PNG ride along."""
+    import functools
+    import io
+    import numpy as np
+    from PIL import Image
+    from b200mm import jpeg
+    from b200mm.loop import DevicePrefetcher
+    rng = np.random.default_rng(5)
+    S = 16
+
+    def enc(arr, fmt="JPEG", mode=None, **kw):
+        b = io.BytesIO()
+        im = Image.fromarray(arr)
+        (im.convert(mode) if mode else im).save(b, fmt, **kw)
+        return b.getvalue()
+
+    def picture(h, w):            # a gradient with mild noise (Pillow's encoder refuses incompressible progressive input)
+        g = np.linspace(0, 200, h * w * 3).reshape(h, w, 3) + rng.integers(0, 40, (h, w, 3))
+        return g.astype(np.uint8)
+
+    files = [enc(picture(300 + 31 * i, 280 + 17 * i), quality=70 + 5 * i, subsampling=i % 3, progressive=bool(i & 1))
+             for i in range(4)]
+    files.append(enc(picture(260, 300), mode="CMYK", quality=60))
+    files.append(enc(picture(270, 290), "PNG"))
+    samples = [{"id": f"img_{i}", "text": torch.randint(0, 100, (S,)), "text_mask": torch.ones(S, dtype=torch.long),
+                "image": torch.frombuffer(bytearray(f), dtype=torch.uint8), "label": torch.tensor(i & 1)}
+               for i, f in enumerate(files)]
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.collate_jpeg(samples)
+    strict = jpeg.collate_jpeg(samples[:4])
+    mixed = functools.partial(jpeg.collate_jpeg, unsupported="pil")(samples)
+    assert strict["jpeg_coefs"].is_pinned() and strict["jpeg_coefs"].dtype == torch.int16 and not strict["jpeg_raw"]
+    assert sorted(i for i, _ in mixed["jpeg_raw"]) == [4, 5]
+    got = list(DevicePrefetcher([strict, mixed], cuda_device))
+    for (text, image, mask, labels, raw), src in zip(got, (samples[:4], samples)):
+        assert image.shape == (len(src), 3, 224, 224) and image.dtype == torch.float32
+        for k, smp in enumerate(src):
+            px = np.asarray(Image.open(io.BytesIO(bytes(smp["image"].numpy()))).convert("RGB"))
+            ref = _torch_transform(torch.from_numpy(px.copy()).to(cuda_device))
+            assert (image[k] - ref).abs().max().item() < 2e-4, k
+
+
 # ------------------------------------------------------------------ BERT / RoBERTa / ViT support kernels
 def test_position_ids_match_transformers(ops, cuda_device):
     """RoBERTa / XLM-R position ids: cumsum(ids != pad) * (ids != pad) + pad
