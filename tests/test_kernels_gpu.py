@@ -1021,6 +1021,10 @@ def test_jpeg_batches_through_the_prefetcher(cuda_device):
             px = np.asarray(Image.open(io.BytesIO(bytes(smp["image"].numpy()))).convert("RGB"))
             ref = _torch_transform(torch.from_numpy(px.copy()).to(cuda_device))
             assert (image[k] - ref).abs().max().item() < 2e-4, k
+    # the synchronous route of the evaluation loops (loop._to_device) finishes the decode the same way
+    from b200mm.loop import _to_device
+    _, image2, _, _ = _to_device(strict, cuda_device)
+    assert torch.equal(image2, got[0][1])
 
 
 # ------------------------------------------------------------------ BERT / RoBERTa / ViT support kernels
