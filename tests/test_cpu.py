@@ -751,3 +751,12 @@ def test_jpeg_unsupported_and_corrupt_files_fail_loudly():
     # geometry of the batch table: offsets are aligned and disjoint
     t = b["jpeg_table"]
     assert (t[:, 23] % 16 == 0).all() and t[1, 23] - t[0, 23] >= 40 * 56 * 3
+    # concurrent decode of a batch's files and recycled coefficient buffers change nothing in the result
+    files = [good, enc(Image.fromarray(arr[:33, :21]), quality=50, progressive=True), good]
+    one = jpeg.pack_jpeg_batch(files, pin=False)
+    ring = jpeg.CoefRing(slots=2, pin=False)
+    for _ in range(3):
+        again = jpeg.pack_jpeg_batch(files, pin=False, threads=3, ring=ring)
+        assert torch.equal(one["jpeg_coefs"], again["jpeg_coefs"]) and torch.equal(one["jpeg_table"], again["jpeg_table"])
+        assert torch.equal(one["jpeg_qtabs"], again["jpeg_qtabs"])
+    assert ring._bufs[0] is not None and ring._bufs[1] is not None
