@@ -5,7 +5,7 @@
 What runs is the reference's source text, executed verbatim:
 
   organiser script  example_scripts/Multimodal_example_task2C.txt
-      class MultimodalClassifier (:152-197), def train (:200-223), def test (:225-242)
+      class MultimodalClassifier (:152-197), def train (:200-223), def test (:225-242), def evaluate (:259-280)
   participant script example_scripts/Multimodal_example_task2C.py
       class LLMWithClassificationHead (:307-392), ConcatAttention3 (:476-499), CustomDenseNet161 (:562-585),
       MultimodalClassifier incl. get_params (:587-685), def train (:689-776), test (:779-834), evaluate (:837-879)
@@ -51,7 +51,7 @@ def organiser_namespace():
           "AutoModel": types.SimpleNamespace(from_pretrained=lambda name: refpin.distilbert()),
           "models": types.SimpleNamespace(resnet50=lambda pretrained=True: refpin.resnet50_small())}
     spans = {}
-    for prefix in ("class MultimodalClassifier", "def train(", "def test("):
+    for prefix in ("class MultimodalClassifier", "def train(", "def test(", "def evaluate("):
         src, span = _top_level_block(lines, prefix)
         exec(compile(src, f"Multimodal_example_task2C.txt:{span[0]}", "exec"), ns)
         spans[prefix] = span
@@ -103,6 +103,15 @@ def run_organiser():
     tr = ns["train"](model, refpin.ListLoader(data[:3]), nn.CrossEntropyLoss(), opt, torch.device("cpu"))
     te = ns["test"](model, refpin.ListLoader(data[3:]), nn.CrossEntropyLoss(), torch.device("cpu"))
     fx.update(train_return=tr, test_return=te, post_train_norms=refpin.param_norms(model))
+    # the script's evaluate() (.txt:259-280) writes task2C_TeamName.tsv into the working directory
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            ns["evaluate"](model, refpin.ListLoader(data[2:]), torch.device("cpu"))
+            fx["tsv_label"] = open("task2C_TeamName.tsv").read()
+        finally:
+            os.chdir(cwd)
     return fx
 
 

@@ -531,7 +531,7 @@ def _close(a, b, rel=2e-5):
     return abs(a - b) <= rel * max(abs(a), abs(b), 1e-12)
 
 
-def test_oracle_reproduces_reference_classifier_run():
+def test_oracle_reproduces_reference_classifier_run(tmp_path):
     """tests/golden/reference_run_golden.pt holds what the REFERENCE'S OWN class and loop source
     (Multimodal_example_task2C.txt:152-242, executed verbatim by tests/golden/make_reference_golden.py) produced; the
     oracle -- same weights by name, same batches -- must reproduce it: state-dict layout, logits, loss, every parameter's
@@ -570,6 +570,14 @@ def test_oracle_reproduces_reference_classifier_run():
     assert _close(te[0], fx["test_return"][0], 1e-4) and te[1] == fx["test_return"][1]
     post = refpin.param_norms(m)
     assert all(_close(post[k], v, 1e-5) for k, v in fx["post_train_norms"].items())
+    # THIS repo's evaluation loops (generic route, CPU) on the same trained model: test() returns what the script's test()
+    # returned, evaluate() writes the script's TSV byte for byte (.txt:225-242, 259-280)
+    from b200mm import loop
+    te2 = loop.test(m, refpin.ListLoader(data[3:]), nn.CrossEntropyLoss(), torch.device("cpu"))
+    assert _close(te2[0], fx["test_return"][0], 1e-4) and te2[1] == fx["test_return"][1]
+    out = tmp_path / "task2C_TeamName.tsv"
+    loop.evaluate(m, refpin.ListLoader(data[2:]), torch.device("cpu"), out_path=str(out))
+    assert out.read_text() == fx["tsv_label"]
 
 
 def test_participant_model_and_loops_reproduce_reference_run(tmp_path):
