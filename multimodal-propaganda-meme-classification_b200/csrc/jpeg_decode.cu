@@ -50,7 +50,7 @@ struct HuffTable {
     for (int l = 1; l <= 16; ++l) {
       valoffset[l] = p - code;
       for (int i = 0; i < bits[l]; ++i, ++p, ++code) {
-        if (p >= 256) return false;
+        if (p >= 256 || code >= (1 << l)) return false;       // more codes of this length than the code space holds
         if (l <= 9) {
           const int first = code << (9 - l);
           for (int k = 0; k < (1 << (9 - l)); ++k) look[first + k] = static_cast<uint16_t>((l << 8) | vals[p]);
@@ -174,11 +174,10 @@ inline int decode_symbol_nofill(BitReader& br, const HuffTable& t) {
   }
   int32_t code = static_cast<int32_t>(pre >> 6);   // 10 bits
   int l = 10;
-  while (l <= 16 && code > t.maxcode[l]) {
-    ++l;
+  while (code > t.maxcode[l]) {
+    if (++l > 16) return -1;                       // no code of any length matches: corrupt data
     code = static_cast<int32_t>(pre >> (16 - l));
   }
-  if (l > 16) return -1;
   br.skip(l);
   const int idx = code + t.valoffset[l];
   return idx >= 0 && idx < 256 ? t.vals[idx] : -1;

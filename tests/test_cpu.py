@@ -768,3 +768,36 @@ def test_jpeg_unsupported_and_corrupt_files_fail_loudly():
         assert torch.equal(one["jpeg_coefs"], again["jpeg_coefs"]) and torch.equal(one["jpeg_table"], again["jpeg_table"])
         assert torch.equal(one["jpeg_qtabs"], again["jpeg_qtabs"])
     assert ring._bufs[0] is not None and ring._bufs[1] is not None
+
+
+def test_jpeg_host_decoder_survives_mutated_files():
+    """Random byte edits, deletions and insertions in valid files: the host decoder either decodes, or refuses with
+    UnsupportedJpeg / OSError -- never crashes, never writes outside the coefficient buffer (canaries on both sides).
+    (The same corpus was run once under AddressSanitizer + UBSan on the stand-alone host half.)"""
+    from augment_ref import jpeg_cases
+    from b200mm import jpeg
+    cases = [d for _, d in jpeg_cases()][:60:4]
+    rng = np.random.default_rng(11)
+    outcomes = {"ok": 0, "unsupported": 0, "corrupt": 0}
+    for it in range(400):
+        base = bytearray(cases[it % len(cases)])
+        for _ in range(int(rng.integers(1, 6))):
+            kind, pos = int(rng.integers(0, 3)), int(rng.integers(2, len(base)))
+            if kind == 0:
+                base[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                del base[pos:pos + int(rng.integers(1, 20))]
+            else:
+                base[pos:pos] = bytes(rng.integers(0, 256, int(rng.integers(1, 8)), dtype=np.uint8))
+        data = bytes(base)
+        try:
+            n = int(jpeg.parse(data)[21])
+            guard = np.full(n + 128, 0x5A5A, dtype=np.int16)
+            jpeg.entropy_decode(data, out=guard[64:64 + n])
+            outcomes["ok"] += 1
+            assert (guard[:64] == 0x5A5A).all() and (guard[64 + n:] == 0x5A5A).all()
+        except jpeg.UnsupportedJpeg:
+            outcomes["unsupported"] += 1
+        except OSError:
+            outcomes["corrupt"] += 1
+    assert outcomes["ok"] > 20 and outcomes["corrupt"] > 100, outcomes
