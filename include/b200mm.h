@@ -207,6 +207,17 @@ int b200mm_jpeg_entropy_decode(const void* data, long long len, short* coefs, un
  * b200mm_preprocess_u8_packed reads.  max_blocks / max_w / max_h: maxima over the batch (grid sizing). */
 int b200mm_jpeg_reconstruct(const short* coefs, const unsigned short* qtabs, const long long* table, int n, int max_blocks,
                             int max_w, int max_h, void* planes, void* out, void* stream);
+/* The same pair with the coefficients delivered SPARSE (a typical file keeps 5-15 % of them; 3 B per non-zero + 4 B per
+ * block cross PCIe instead of 128 B per block).  HOST: scratch = info[21] int16 work space; block_off int32 [blocks + 1],
+ * idx uint8 [nnz] (position inside the block, natural order), val int16 [nnz]; capacity = entries idx / val can hold
+ * (info[21] always suffices); *nnz receives the count.  DEVICE: sp_off = the batch's block_off arrays concatenated with
+ * batch-wide entry offsets ([blocks of the batch + 1]); table columns 17..19 = first BLOCK of each component in the
+ * batch's block numbering. */
+int b200mm_jpeg_entropy_decode_sparse(const void* data, long long len, short* scratch, int* block_off, unsigned char* idx,
+                                      short* val, long long capacity, unsigned short* qtabs, int* info, long long* nnz);
+int b200mm_jpeg_reconstruct_sparse(const int* sp_off, const unsigned char* sp_idx, const short* sp_val,
+                                   const unsigned short* qtabs, const long long* table, int n, int max_blocks, int max_w,
+                                   int max_h, void* planes, void* out, void* stream);
 
 /* ---- head + loss, optimizer --------------------------------------------------------------------------------------
  * output layer fused with the loss: example_scripts/Multimodal_example_task2C.txt:195 (output_fc) + :214, :248

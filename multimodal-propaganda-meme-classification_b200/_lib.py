@@ -65,7 +65,7 @@ def load(build_if_needed: bool = True) -> ctypes.CDLL:
 # kernels launched through this module since the counter was last reset (bench.py's gpu_launches)
 LAUNCHES = [0]
 _KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_jpeg_parse": 0, "b200mm_jpeg_entropy_decode": 0,
-                     "b200mm_jpeg_reconstruct": 2, "b200mm_augment_jitter_rotate": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0, "b200mm_tune": 0,
+                     "b200mm_jpeg_reconstruct": 2, "b200mm_jpeg_entropy_decode_sparse": 0, "b200mm_jpeg_reconstruct_sparse": 2, "b200mm_augment_jitter_rotate": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0, "b200mm_tune": 0,
                      "b200mm_set_step_salt_ptr": 0}
 
 
@@ -117,6 +117,8 @@ declare("b200mm_u8_normalize_nchw", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c
 declare("b200mm_jpeg_parse", [c_ptr, c_longlong, c_ptr])
 declare("b200mm_jpeg_entropy_decode", [c_ptr, c_longlong, c_ptr, c_ptr, c_ptr])
 declare("b200mm_jpeg_reconstruct", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr])
+declare("b200mm_jpeg_entropy_decode_sparse", [c_ptr, c_longlong, c_ptr, c_ptr, c_ptr, c_ptr, c_longlong, c_ptr, c_ptr, c_ptr])
+declare("b200mm_jpeg_reconstruct_sparse", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr])
 declare("b200mm_augment_jitter_rotate", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_attention_fwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float, c_ulonglong, c_ptr])
 declare("b200mm_attention_bwd", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_float,

@@ -574,6 +574,43 @@ B200MM_API int b200mm_jpeg_entropy_decode(const void* data, long long len, short
   return B200MM_OK;
 }
 
+// The same decode, delivered SPARSE: after the dense decode into `scratch` (info[21] int16, caller-owned and reusable
+// across files) the non-zero coefficients are compacted block by block, in the dense layout's block order:
+//   block_off [blocks + 1] int32   entry range of block b = [block_off[b], block_off[b + 1])
+//   idx [nnz] uint8                position of the coefficient inside its block (natural order, 0..63)
+//   val [nnz] int16                its value
+// capacity: entries idx / val can hold (info[21] always suffices); *nnz receives the count.  A typical file keeps 5-15 % of
+// its coefficients, so the batch that crosses PCIe shrinks accordingly (3 B per non-zero + 4 B per block instead of
+// 128 B per block).  Returns B200MM_ERR_BAD_ARG when capacity is too small.
+B200MM_API int b200mm_jpeg_entropy_decode_sparse(const void* data, long long len, short* scratch, int* block_off,
+                                                 unsigned char* idx, short* val, long long capacity,
+                                                 unsigned short* qtabs, int* info, long long* nnz) {
+  if (!block_off || !idx || !val || !nnz || capacity < 0) return B200MM_ERR_BAD_ARG;
+  const int rc = b200mm_jpeg_entropy_decode(data, len, scratch, qtabs, info);
+  if (rc) return rc;
+  const long long blocks = info[21] / 64;
+  long long n = 0;
+  for (long long b = 0; b < blocks; ++b) {
+    block_off[b] = static_cast<int>(n);
+    const short* blk = scratch + b * 64;
+    for (int k = 0; k < 64; k += 4) {
+      uint64_t four;
+      std::memcpy(&four, blk + k, 8);
+      if (four == 0) continue;                       // most groups of four are empty
+      for (int j = 0; j < 4; ++j)
+        if (blk[k + j] != 0) {
+          if (n >= capacity) return B200MM_ERR_BAD_ARG;
+          idx[n] = static_cast<unsigned char>(k + j);
+          val[n] = blk[k + j];
+          ++n;
+        }
+    }
+  }
+  block_off[blocks] = static_cast<int>(n);
+  *nnz = n;
+  return B200MM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------- device side
 namespace b200 {
 
@@ -584,9 +621,19 @@ namespace b200 {
 //   in the packed RGB output, 24 blocks of the image in total
 constexpr int kJpegTableCols = 32;
 
-__global__ void __launch_bounds__(128)
-jpeg_idct_kernel(const int16_t* __restrict__ coefs, const uint16_t* __restrict__ qtabs, const long long* __restrict__ table,
-                 uint8_t* __restrict__ planes) {
+// SPARSE = false: coefs holds 64 int16 per block.  SPARSE = true: the batch ships only its non-zero coefficients
+// (sp_off [blocks of the batch + 1], sp_idx, sp_val; table columns 17..19 = first BLOCK of the component in the batch's
+// block numbering); a thread scatters its block's entries into its own row of a shared-memory tile (rows 33 words apart:
+// the same position in 32 different rows falls into 32 different banks) and reads the row back into registers.
+constexpr int kIdctThreads = 128;
+constexpr int kSparseRowWords = 33;
+
+template <bool SPARSE>
+__global__ void __launch_bounds__(kIdctThreads)
+jpeg_idct_kernel(const int16_t* __restrict__ coefs, const int* __restrict__ sp_off, const uint8_t* __restrict__ sp_idx,
+                 const int16_t* __restrict__ sp_val, const uint16_t* __restrict__ qtabs,
+                 const long long* __restrict__ table, uint8_t* __restrict__ planes) {
+  __shared__ uint32_t tile[SPARSE ? kIdctThreads * kSparseRowWords : 1];
   const int img = blockIdx.y;
   const long long* t = table + static_cast<long long>(img) * kJpegTableCols;
   const int total = static_cast<int>(t[24]);
@@ -600,23 +647,40 @@ jpeg_idct_kernel(const int16_t* __restrict__ coefs, const uint16_t* __restrict__
     }
     const int wb = static_cast<int>(t[5 + c]);
     const int by = idx / wb, bx = idx - by * wb;
-    // the block's 128 bytes as eight 16-byte loads, the result as eight 8-byte stores; everything in registers
-    const uint4* src = reinterpret_cast<const uint4*>(coefs + t[17 + c] + static_cast<long long>(idx) * 64);
     int16_t blk[64];
+    if (SPARSE) {
+      // private to this thread: no synchronisation needed; volatile because the row is written as halves and read as words
+      volatile uint32_t* row = tile + threadIdx.x * kSparseRowWords;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint4 v = __ldg(src + k);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      for (int k = 0; k < 32; ++k) row[k] = 0u;
+      volatile int16_t* row16 = reinterpret_cast<volatile int16_t*>(row);
+      const long long gb = t[17 + c] + idx;
+      const int e1 = sp_off[gb + 1];
+      for (int e = sp_off[gb]; e < e1; ++e) row16[sp_idx[e] & 63] = sp_val[e];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        blk[8 * k + 2 * j] = static_cast<int16_t>(w[j] & 0xffffu);
-        blk[8 * k + 2 * j + 1] = static_cast<int16_t>(w[j] >> 16);
+      for (int k = 0; k < 32; ++k) {
+        const uint32_t w = row[k];
+        blk[2 * k] = static_cast<int16_t>(w & 0xffffu);
+        blk[2 * k + 1] = static_cast<int16_t>(w >> 16);
+      }
+    } else {
+      // the block's 128 bytes as eight 16-byte loads; everything in registers
+      const uint4* src = reinterpret_cast<const uint4*>(coefs + t[17 + c] + static_cast<long long>(idx) * 64);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint4 v = __ldg(src + k);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          blk[8 * k + 2 * j] = static_cast<int16_t>(w[j] & 0xffffu);
+          blk[8 * k + 2 * j + 1] = static_cast<int16_t>(w[j] >> 16);
+        }
       }
     }
     uint8_t px[64];
     jpeg::idct_islow_block(blk, qtabs + (static_cast<long long>(img) * 3 + c) * 64, px, 8);
     const int stride = wb * 8;
-    uint8_t* dst = planes + t[20 + c] + static_cast<long long>(by) * 8 * stride + bx * 8;
+    uint8_t* dst = planes + t[20 + c] + static_cast<long long>(by) * 8 * stride + bx * 8;   // eight 8-byte stores
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       uint2 o;
@@ -677,8 +741,33 @@ B200MM_API int b200mm_jpeg_reconstruct(const short* coefs, const unsigned short*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int gx = ceil_div(max_blocks, 128);
   if (gx > 4096) gx = 4096;
-  jpeg_idct_kernel<<<dim3(gx, n), 128, 0, st>>>(reinterpret_cast<const int16_t*>(coefs), qtabs, table,
-                                                static_cast<uint8_t*>(planes));
+  jpeg_idct_kernel<false><<<dim3(gx, n), kIdctThreads, 0, st>>>(reinterpret_cast<const int16_t*>(coefs), nullptr, nullptr,
+                                                                nullptr, qtabs, table, static_cast<uint8_t*>(planes));
+  B200MM_CHECK_LAUNCH();
+  int cx = ceil_div(max_w, 32), cy = ceil_div(max_h, 8);
+  if (cx > 64) cx = 64;
+  if (cy > 256) cy = 256;
+  jpeg_upsample_color_kernel<<<dim3(cx, cy, n), 256, 0, st>>>(static_cast<const uint8_t*>(planes), table,
+                                                              static_cast<uint8_t*>(out));
+  B200MM_CHECK_LAUNCH();
+  return B200MM_OK;
+}
+
+// The same reconstruction from the SPARSE batch (b200mm_jpeg_entropy_decode_sparse): sp_off int32 [blocks of the batch + 1]
+// (entry offsets made batch-wide by the caller), sp_idx uint8 [nnz], sp_val int16 [nnz]; table columns 17..19 hold the
+// first BLOCK of each component in the batch's block numbering instead of a coefficient offset.
+B200MM_API int b200mm_jpeg_reconstruct_sparse(const int* sp_off, const unsigned char* sp_idx, const short* sp_val,
+                                              const unsigned short* qtabs, const long long* table, int n, int max_blocks,
+                                              int max_w, int max_h, void* planes, void* out, void* stream) {
+  if (!sp_off || !sp_idx || !sp_val || !qtabs || !table || !planes || !out || n <= 0 || n > 65535 || max_blocks <= 0 ||
+      max_w <= 0 || max_h <= 0)
+    return B200MM_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(planes) & 7) return B200MM_ERR_BAD_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int gx = ceil_div(max_blocks, kIdctThreads);
+  if (gx > 4096) gx = 4096;
+  jpeg_idct_kernel<true><<<dim3(gx, n), kIdctThreads, 0, st>>>(nullptr, sp_off, sp_idx, reinterpret_cast<const int16_t*>(sp_val),
+                                                               qtabs, table, static_cast<uint8_t*>(planes));
   B200MM_CHECK_LAUNCH();
   int cx = ceil_div(max_w, 32), cy = ceil_div(max_h, 8);
   if (cx > 64) cx = 64;

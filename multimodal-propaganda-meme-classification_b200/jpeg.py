@@ -19,6 +19,7 @@ pixels beside the coefficients, so that a real dataset with a stray CMYK or PNG 
 from __future__ import annotations
 
 import io
+import threading
 
 import numpy as np
 import torch
@@ -79,6 +80,46 @@ def entropy_decode(data, out: np.ndarray | None = None):
     return coefs, qtabs, info
 
 
+class _Scratch:
+    """Per-thread reusable work space of ``entropy_decode_sparse`` (dense coefficients + worst-case entry arrays)."""
+
+    def __init__(self):
+        self.dense = np.empty(0, dtype=np.int16)
+        self.idx = np.empty(0, dtype=np.uint8)
+        self.val = np.empty(0, dtype=np.int16)
+
+    def fit(self, n):
+        if self.dense.size < n:
+            self.dense, self.idx, self.val = (np.empty(n, dtype=np.int16), np.empty(n, dtype=np.uint8),
+                                              np.empty(n, dtype=np.int16))
+
+
+_TLS = threading.local()
+
+
+def entropy_decode_sparse(data):
+    """``entropy_decode`` with the result compacted to its non-zero coefficients (a typical file keeps 5-15 % of them).
+    Returns (block_off int32 [blocks + 1], idx uint8 [nnz], val int16 [nnz], qtabs uint16 [3, 64], info): entries
+    [block_off[b], block_off[b + 1]) belong to block b (blocks in the dense layout's order), ``idx`` = position inside
+    the block in natural order."""
+    a = _as_bytes(data)
+    info = parse(a)
+    n = int(info[21])
+    sc = getattr(_TLS, "scratch", None)
+    if sc is None:
+        sc = _TLS.scratch = _Scratch()
+    sc.fit(n)
+    block_off = np.empty(n // 64 + 1, dtype=np.int32)
+    qtabs = np.zeros((3, 64), dtype=np.uint16)
+    nnz = np.zeros(1, dtype=np.int64)
+    _check(_lib.load().b200mm_jpeg_entropy_decode_sparse(a.ctypes.data, a.size, sc.dense.ctypes.data,
+                                                         block_off.ctypes.data, sc.idx.ctypes.data, sc.val.ctypes.data, n,
+                                                         qtabs.ctypes.data, info.ctypes.data, nnz.ctypes.data),
+           "b200mm_jpeg_entropy_decode_sparse")
+    k = int(nnz[0])
+    return block_off, sc.idx[:k].copy(), sc.val[:k].copy(), qtabs, info
+
+
 def _pil_pixels(data) -> torch.Tensor:
     from PIL import Image
     with Image.open(io.BytesIO(_as_bytes(data).tobytes())) as im:
@@ -104,13 +145,17 @@ class CoefRing:
 
 
 def pack_jpeg_batch(files, pin: bool = True, unsupported: str = "raise", threads: int = 1,
-                    ring: CoefRing | None = None) -> dict:
+                    ring: CoefRing | None = None, sparse: bool = False) -> dict:
     """files: the raw bytes of the batch's image files.  ``unsupported``: 'raise' (default) or 'pil' -- what to do with a
     file outside the split decoder's set (module docstring).  ``threads`` > 1 Huffman-decodes the files of the batch
     concurrently (the C call releases the GIL; every file writes its own slice of the batch buffer).  ``pin``: allocate
     the buffers in pinned memory here -- for a collate that runs in the training process; inside DataLoader WORKER
     processes pass ``pin=False`` and let ``DataLoader(pin_memory=True)`` pin (a worker must not create a CUDA context).
     ``ring``: a ``CoefRing`` whose recycled buffer receives the coefficients instead of a fresh allocation.
+    ``sparse=True`` ships only the non-zero coefficients: ``jpeg_coefs`` is replaced by ``jpeg_sp_off`` int32
+    [blocks of the batch + 1], ``jpeg_sp_idx`` uint8 [nnz], ``jpeg_sp_val`` int16 [nnz], and table columns 17..19 hold the
+    first BLOCK of each component in the batch's block numbering (3 B per non-zero + 4 B per block cross PCIe instead of
+    128 B per block).
     Returns the batch in the form that crosses PCIe:
 
       jpeg_coefs  int16 [total]       coefficients of every split-decoded image (pinned)
@@ -145,7 +190,7 @@ def pack_jpeg_batch(files, pin: bool = True, unsupported: str = "raise", threads
         for c in range(nc):
             wb, hb = int(info[6 + c]), int(info[9 + c])
             row[5 + c], row[8 + c], row[11 + c], row[14 + c] = wb, hb, int(info[12 + c]), int(info[15 + c])
-            row[17 + c] = coef_off + int(info[18 + c])
+            row[17 + c] = (coef_off + int(info[18 + c])) // 64 if sparse else coef_off + int(info[18 + c])
             row[20 + c] = plane_off + blocks * 64
             blocks += wb * hb
         row[23], row[24] = out_off, blocks
@@ -153,15 +198,27 @@ def pack_jpeg_batch(files, pin: bool = True, unsupported: str = "raise", threads
         plane_off += blocks * 64
         out_off += (w * h * 3 + 15) // 16 * 16
         max_blocks, max_w, max_h = max(max_blocks, blocks), max(max_w, w), max(max_h, h)
-    coefs = ring.take(coef_off) if ring is not None else torch.empty(max(coef_off, 8), dtype=torch.int16, pin_memory=pin)
     qtabs = torch.zeros(n, 3, 64, dtype=torch.int16, pin_memory=pin)
-    cnp, qnp = coefs.numpy(), qtabs.numpy().view(np.uint16)
+    qnp = qtabs.numpy().view(np.uint16)
     raw_idx = {i for i, _ in raw}
+    coef_start = [0] * n
+    acc = 0
+    for i, info in enumerate(infos):
+        coef_start[i] = acc
+        acc += int(info[21])
+    sparse_parts = [None] * n
+    if not sparse:
+        coefs = ring.take(coef_off) if ring is not None else torch.empty(max(coef_off, 8), dtype=torch.int16,
+                                                                         pin_memory=pin)
+        cnp = coefs.numpy()
 
     def decode_one(i):
-        start = int(table[i, 17])
         try:
-            _, q, _ = entropy_decode(files[i], out=cnp[start:start + int(infos[i][21])])
+            if sparse:
+                off, idx, val, q, _ = entropy_decode_sparse(files[i])
+                sparse_parts[i] = (off, idx, val)
+            else:
+                _, q, _ = entropy_decode(files[i], out=cnp[coef_start[i]:coef_start[i] + int(infos[i][21])])
         except UnsupportedJpeg:                          # found past the frame header (e.g. RGB-coded components)
             if unsupported == "raise":
                 raise
@@ -182,26 +239,60 @@ def pack_jpeg_batch(files, pin: bool = True, unsupported: str = "raise", threads
         else:
             qnp[i] = q
     meta = torch.tensor([max_blocks, max_w, max_h, max(plane_off, 8), max(out_off, 16)], dtype=torch.int64)
-    return {"jpeg_coefs": coefs, "jpeg_qtabs": qtabs, "jpeg_table": table.pin_memory() if pin else table,
-            "jpeg_meta": meta, "jpeg_raw": raw}
+    out = {"jpeg_qtabs": qtabs, "jpeg_table": table.pin_memory() if pin else table, "jpeg_meta": meta, "jpeg_raw": raw}
+    if not sparse:
+        out["jpeg_coefs"] = coefs
+        return out
+    # concatenate the files' entry lists; block offsets become batch-wide (a skipped / Pillow-decoded image keeps its
+    # block range with zero entries, so the block numbering stays the dense one)
+    total_blocks = coef_off // 64
+    nnz = sum(p[1].size for p in sparse_parts if p is not None)
+    sp_off = torch.empty(total_blocks + 1, dtype=torch.int32, pin_memory=pin)
+    sp_idx = torch.empty(max(nnz, 16), dtype=torch.uint8, pin_memory=pin)
+    sp_val = torch.empty(max(nnz, 16), dtype=torch.int16, pin_memory=pin)
+    onp, inp, vnp = sp_off.numpy(), sp_idx.numpy(), sp_val.numpy()
+    e = 0
+    for i in range(n):
+        b0, nb = coef_start[i] // 64, int(infos[i][21]) // 64
+        part = sparse_parts[i]
+        if part is None:
+            onp[b0:b0 + nb] = e
+            continue
+        off, idx, val = part
+        onp[b0:b0 + nb] = off[:nb] + e
+        inp[e:e + idx.size] = idx
+        vnp[e:e + val.size] = val
+        e += idx.size
+    onp[total_blocks] = e
+    out.update(jpeg_sp_off=sp_off, jpeg_sp_idx=sp_idx, jpeg_sp_val=sp_val)
+    return out
 
 
 def reconstruct_batch(batch: dict, device=None):
     """Device half: ``pack_jpeg_batch``'s tensors (host or already on the device) -> (packed uint8 RGB CUDA buffer,
     int64 CUDA table [3, n] = byte offset | height | width) -- what ``ops.preprocess_u8_packed`` /
     ``data.GpuImageTransform.packed`` take.  Runs on the current stream."""
-    dev = torch.device(device) if device is not None else batch["jpeg_coefs"].device
+    sparse = "jpeg_sp_off" in batch
+    dev = torch.device(device) if device is not None else batch["jpeg_qtabs"].device
     if dev.type != "cuda":
         raise _lib.B200MMError("reconstruct_batch needs a CUDA device (b200mm has no CPU path)")
-    coefs = batch["jpeg_coefs"].to(dev, non_blocking=True)
+    if sparse:
+        sp_off, sp_idx, sp_val = (batch[k].to(dev, non_blocking=True) for k in ("jpeg_sp_off", "jpeg_sp_idx", "jpeg_sp_val"))
+    else:
+        coefs = batch["jpeg_coefs"].to(dev, non_blocking=True)
     qtabs = batch["jpeg_qtabs"].to(dev, non_blocking=True)
     table = batch["jpeg_table"].to(dev, non_blocking=True)
     max_blocks, max_w, max_h, plane_bytes, out_bytes = (int(v) for v in batch["jpeg_meta"])
     n = table.shape[0]
     planes = torch.empty(plane_bytes, dtype=torch.uint8, device=dev)
     out = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
-    _lib.call("b200mm_jpeg_reconstruct", coefs.data_ptr(), qtabs.data_ptr(), table.data_ptr(), n, max_blocks, max_w,
-              max_h, planes.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.current_stream().cuda_stream
+    if sparse:
+        _lib.call("b200mm_jpeg_reconstruct_sparse", sp_off.data_ptr(), sp_idx.data_ptr(), sp_val.data_ptr(),
+                  qtabs.data_ptr(), table.data_ptr(), n, max_blocks, max_w, max_h, planes.data_ptr(), out.data_ptr(), stream)
+    else:
+        _lib.call("b200mm_jpeg_reconstruct", coefs.data_ptr(), qtabs.data_ptr(), table.data_ptr(), n, max_blocks, max_w,
+                  max_h, planes.data_ptr(), out.data_ptr(), stream)
     host_table = batch["jpeg_table"]
     for i, px in batch.get("jpeg_raw", ()):              # images the reference's loader decoded: their pixels are copied in
         o = int(host_table[i, 23])
@@ -210,16 +301,17 @@ def reconstruct_batch(batch: dict, device=None):
     return out, image_table
 
 
-def decode_jpeg(files, device=None, unsupported: str = "raise"):
+def decode_jpeg(files, device=None, unsupported: str = "raise", sparse: bool = False):
     """Convenience: list of file bytes -> list of uint8 CUDA tensors [H, W, 3] (views of one packed buffer)."""
-    batch = pack_jpeg_batch(files, unsupported=unsupported)
+    batch = pack_jpeg_batch(files, unsupported=unsupported, sparse=sparse)
     out, _ = reconstruct_batch(batch, device or "cuda")
     t = batch["jpeg_table"]
     return [out[int(t[i, 23]):int(t[i, 23]) + int(t[i, 0]) * int(t[i, 1]) * 3].view(int(t[i, 1]), int(t[i, 0]), 3)
             for i in range(t.shape[0])]
 
 
-def collate_jpeg(samples, pin: bool = True, unsupported: str = "raise", threads: int = 1, ring: CoefRing | None = None):
+def collate_jpeg(samples, pin: bool = True, unsupported: str = "raise", threads: int = 1, ring: CoefRing | None = None,
+                 sparse: bool = False):
     """DataLoader ``collate_fn`` for datasets whose ``image`` is the FILE CONTENT (bytes / uint8 1-D tensor, see
     ``data.file_bytes_loader``): stacks the token tensors / labels and entropy-decodes the batch's files in the worker
     (``pack_jpeg_batch``; ``functools.partial(collate_jpeg, unsupported="pil")`` for datasets with stray non-JPEG / CMYK
@@ -230,5 +322,5 @@ def collate_jpeg(samples, pin: bool = True, unsupported: str = "raise", threads:
             t = torch.stack([s[k] for s in samples])
             out[k] = t.pin_memory() if pin else t
     out.update(pack_jpeg_batch([s["image"] for s in samples], pin=pin, unsupported=unsupported, threads=threads,
-                               ring=ring))
+                               ring=ring, sparse=sparse))
     return out

@@ -54,7 +54,7 @@ def _image_to_device(data, device, image_transform=None):
     transform: ``image_transform`` (a data.GpuImageTransform) or, by default, the organiser script's deterministic
     evaluation form (Resize(256) / CenterCrop(224) / Normalize)."""
     global _EVAL_TRANSFORM
-    if "jpeg_coefs" in data:           # entropy-decoded JPEG batch (jpeg.collate_jpeg): finish the decode on the device
+    if "jpeg_table" in data:           # entropy-decoded JPEG batch (jpeg.collate_jpeg): finish the decode on the device
         from .jpeg import reconstruct_batch
         data = dict(data)
         data["image_packed"], data["image_table"] = reconstruct_batch(data, device)
@@ -124,7 +124,7 @@ class DevicePrefetcher:
                     if self.pin and not t.is_cuda and not t.is_pinned():
                         t = t.pin_memory()
                     out[k] = t.to(self.device, non_blocking=True)
-            if "jpeg_coefs" in data:   # coefficients cross PCIe; IDCT / up-sampling / colour conversion run here
+            if "jpeg_table" in data:   # coefficients cross PCIe; IDCT / up-sampling / colour conversion run here
                 from .jpeg import reconstruct_batch
                 out["image_packed"], out["image_table"] = reconstruct_batch(data, self.device)
             if "image_packed" in out:

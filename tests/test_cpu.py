@@ -768,6 +768,18 @@ def test_jpeg_unsupported_and_corrupt_files_fail_loudly():
         assert torch.equal(one["jpeg_coefs"], again["jpeg_coefs"]) and torch.equal(one["jpeg_table"], again["jpeg_table"])
         assert torch.equal(one["jpeg_qtabs"], again["jpeg_qtabs"])
     assert ring._bufs[0] is not None and ring._bufs[1] is not None
+    # the sparse form (non-zero coefficients only) expands to exactly the dense batch, block numbering included
+    sp = jpeg.pack_jpeg_batch(files + [cmyk], pin=False, sparse=True, threads=2, unsupported="pil")
+    dn = jpeg.pack_jpeg_batch(files + [cmyk], pin=False, unsupported="pil")
+    off, idx, val = sp["jpeg_sp_off"].numpy(), sp["jpeg_sp_idx"].numpy(), sp["jpeg_sp_val"].numpy()
+    blocks, nnz = off.size - 1, int(off[-1])
+    assert (np.diff(off) >= 0).all() and (np.diff(off) <= 64).all()
+    dense = np.zeros(blocks * 64, dtype=np.int16)
+    dense[np.repeat(np.arange(blocks), np.diff(off)) * 64 + idx[:nnz]] = val[:nnz]
+    want = dn["jpeg_coefs"].numpy()[:blocks * 64]                # (the Pillow-decoded CMYK file owns no blocks)
+    assert np.array_equal(dense, want) and (val[:nnz] != 0).all() and int(sp["jpeg_table"][3, 24]) == 0
+    assert torch.equal(sp["jpeg_table"][:3, 17:20] * 64, dn["jpeg_table"][:3, 17:20])
+    assert torch.equal(sp["jpeg_table"][:, 20:], dn["jpeg_table"][:, 20:])
 
 
 def test_jpeg_host_decoder_survives_mutated_files():

@@ -964,7 +964,8 @@ def test_gpu_transform_full_head_train_pipeline(cuda_device):
     assert (d2 > 1e-4).any(dim=1).float().mean().item() < 1e-4 and d2.mean().item() < 1e-5
 
 
-def test_jpeg_reconstruct_is_bit_identical_to_pillow(cuda_device):
+@pytest.mark.parametrize("sparse", [False, True])
+def test_jpeg_reconstruct_is_bit_identical_to_pillow(cuda_device, sparse):
     """Host Huffman decode + the two device kernels (dequantise + IDCT, up-sampling + colour conversion) over a batch of
     files of every supported coding = ``Image.open(...).convert("RGB")`` PIXEL FOR PIXEL (the reference's loader,
     .txt:50; .py:270); one batch, ragged sizes, images one pixel wide included."""
@@ -974,7 +975,7 @@ def test_jpeg_reconstruct_is_bit_identical_to_pillow(cuda_device):
     from augment_ref import jpeg_cases
     from b200mm import jpeg
     cases = jpeg_cases()
-    got = jpeg.decode_jpeg([d for _, d in cases], device=cuda_device)
+    got = jpeg.decode_jpeg([d for _, d in cases], device=cuda_device, sparse=sparse)   # sparse: only non-zero coefficients ship
     torch.cuda.synchronize()
     assert len(got) == len(cases)
     for (name, data), g in zip(cases, got):
@@ -1029,6 +1030,12 @@ def test_jpeg_batches_through_the_prefetcher(cuda_device):
     from b200mm.loop import _to_device
     _, image2, _, _ = _to_device(strict, cuda_device)
     assert torch.equal(image2, got[0][1])
+    # sparse batches (non-zero coefficients only) give the same tensors, Pillow-decoded stragglers included
+    for src, want in ((samples[:4], got[0][1]), (samples, got[1][1])):
+        sp = jpeg.collate_jpeg(src, unsupported="pil", sparse=True, threads=2)
+        assert "jpeg_coefs" not in sp and sp["jpeg_sp_off"].dtype == torch.int32 and sp["jpeg_sp_idx"].is_pinned()
+        _, image3, _, _ = _to_device(sp, cuda_device)
+        assert torch.equal(image3, want)
 
 
 # ------------------------------------------------------------------ BERT / RoBERTa / ViT support kernels
