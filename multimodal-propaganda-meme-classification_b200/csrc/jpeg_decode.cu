@@ -44,6 +44,22 @@ struct HuffTable {
   int32_t maxcode[18];
   int32_t valoffset[17];
   uint16_t look[512];
+  // AC tables only: when a code AND the value bits behind it fit into the 9-bit look-ahead, the whole coefficient comes out
+  // of one lookup: fast[prefix] = (value << 8) | (run << 4) | total bits   (0 = take the two-step path)
+  int16_t fast[512];
+  void build_fast() {
+    for (int i = 0; i < 512; ++i) {
+      fast[i] = 0;
+      const uint16_t e = look[i];
+      if (!e) continue;
+      const int l = e >> 8, run = (e >> 4) & 15, s = e & 15;
+      if (s == 0 || l + s > 9) continue;
+      const int v = ((i << l) & 511) >> (9 - s);
+      const int val = v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+      if (val < -128 || val > 127) continue;
+      fast[i] = static_cast<int16_t>(val * 256 + run * 16 + (l + s));
+    }
+  }
   bool build() {
     int32_t code = 0, p = 0;
     std::memset(look, 0, sizeof(look));
@@ -275,6 +291,7 @@ struct Decoder {
       std::memset(t.vals, 0, sizeof(t.vals));
       std::memcpy(t.vals, s + 17, count);
       if (!t.build()) return B200MM_JPEG_CORRUPT;
+      if (tc) t.build_fast();
       t.present = true;
       s += 17 + count;
       n -= 17 + count;
@@ -414,6 +431,14 @@ struct Decoder {
     const HuffTable& t = ac[c.ta];
     for (int k = 1; k < 64;) {
       br.need(32);
+      const int f = t.fast[br.acc >> 55];
+      if (f) {                             // run, size and value from one lookup
+        k += (f >> 4) & 15;
+        if (k > 63) return B200MM_JPEG_CORRUPT;
+        blk[kZigzag[k++]] = static_cast<int16_t>(f >> 8);
+        br.skip(f & 15);
+        continue;
+      }
       const int rs = decode_symbol_nofill(br, t);
       if (rs < 0) return B200MM_JPEG_CORRUPT;
       const int r = rs >> 4;
@@ -451,7 +476,16 @@ struct Decoder {
     }
     const HuffTable& t = ac[c.ta];
     for (int k = Ss; k <= Se; ++k) {
-      const int rs = decode_symbol(br, t);
+      br.need(32);
+      const int f = t.fast[br.acc >> 55];
+      if (f) {                             // run, size and value from one lookup
+        k += (f >> 4) & 15;
+        if (k > 63) return B200MM_JPEG_CORRUPT;
+        blk[kZigzag[k]] = static_cast<int16_t>((f >> 8) * (1 << Al));
+        br.skip(f & 15);
+        continue;
+      }
+      const int rs = decode_symbol_nofill(br, t);
       if (rs < 0) return B200MM_JPEG_CORRUPT;
       const int r = rs >> 4, s = rs & 15;
       if (s) {
