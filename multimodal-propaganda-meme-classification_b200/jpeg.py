@@ -166,6 +166,8 @@ def pack_jpeg_batch(files, pin: bool = True, unsupported: str = "raise", threads
     """
     if unsupported not in ("raise", "pil"):
         raise ValueError("unsupported must be 'raise' or 'pil'")
+    if sparse and ring is not None:
+        raise ValueError("ring= recycles the DENSE coefficient buffer; the sparse form allocates exact-size buffers")
     n = len(files)
     infos, raw = [], []
     for i, f in enumerate(files):
