@@ -23,6 +23,7 @@ import threading
 
 import numpy as np
 import torch
+import torch.utils.data
 
 from . import _lib
 
@@ -312,12 +313,15 @@ def decode_jpeg(files, device=None, unsupported: str = "raise", sparse: bool = F
             for i in range(t.shape[0])]
 
 
-def collate_jpeg(samples, pin: bool = True, unsupported: str = "raise", threads: int = 1, ring: CoefRing | None = None,
-                 sparse: bool = False):
+def collate_jpeg(samples, pin: bool | None = None, unsupported: str = "raise", threads: int = 1,
+                 ring: CoefRing | None = None, sparse: bool = False):
     """DataLoader ``collate_fn`` for datasets whose ``image`` is the FILE CONTENT (bytes / uint8 1-D tensor, see
     ``data.file_bytes_loader``): stacks the token tensors / labels and entropy-decodes the batch's files in the worker
     (``pack_jpeg_batch``; ``functools.partial(collate_jpeg, unsupported="pil")`` for datasets with stray non-JPEG / CMYK
-    files, ``pin=False`` when the collate runs in worker processes, ``threads=k`` to decode a batch's files concurrently).  ``loop.DevicePrefetcher`` finishes the decode on the device and runs the image transform."""
+    files, ``threads=k`` to decode a batch's files concurrently).  ``pin=None`` pins the buffers when the collate runs in
+    the training process and leaves pinning to ``DataLoader(pin_memory=True)`` inside worker processes.  ``loop.DevicePrefetcher`` finishes the decode on the device and runs the image transform."""
+    if pin is None:     # pin here only in the training process: a DataLoader worker must not create a CUDA context
+        pin = torch.utils.data.get_worker_info() is None and torch.cuda.is_available()
     out = {"id": [s["id"] for s in samples]}
     for k in ("text", "text_mask", "caption_text", "caption_text_mask", "label"):
         if k in samples[0]:

@@ -813,3 +813,32 @@ def test_jpeg_host_decoder_survives_mutated_files():
         except OSError:
             outcomes["corrupt"] += 1
     assert outcomes["ok"] > 20 and outcomes["corrupt"] > 100, outcomes
+
+
+def test_jpeg_collate_in_dataloader_workers(tmp_path):
+    """data.file_bytes_loader + jpeg.collate_jpeg under a DataLoader with worker processes: the workers Huffman-decode
+    (and do not pin: they must not touch CUDA), the batches carry everything the device half needs, and the coefficients
+    equal the in-process result."""
+    import io
+    from PIL import Image
+    from torch.utils.data import DataLoader
+    from b200mm import data as D, jpeg
+    rng = np.random.default_rng(3)
+    paths = []
+    for i in range(6):
+        arr = (np.linspace(0, 200, (40 + i) * 52 * 3).reshape(40 + i, 52, 3) + rng.integers(0, 30, (40 + i, 52, 3))).astype(np.uint8)
+        p = tmp_path / f"img_{i}.jpg"
+        Image.fromarray(arr).save(p, "JPEG", quality=80, progressive=bool(i & 1))
+        paths.append(str(p))
+    tok = lambda t: ([1, 2, 3], [1, 1, 1])
+    ds = D.MemeDataset([f"id{i}" for i in range(6)], ["x"] * 6, paths, ["propaganda", "not_propaganda"] * 3, tokenizer=tok,
+                       max_len=8, image_loader=D.file_bytes_loader)
+    assert ds[0]["image"].dtype == torch.uint8 and ds[0]["image"].dim() == 1
+    batches = list(DataLoader(ds, batch_size=3, num_workers=2, collate_fn=jpeg.collate_jpeg))
+    assert len(batches) == 2
+    for b, lo in zip(batches, (0, 3)):
+        assert b["id"] == [f"id{i}" for i in range(lo, lo + 3)] and b["text"].shape == (3, 8)
+        assert not b["jpeg_coefs"].is_pinned()
+        want = jpeg.pack_jpeg_batch([open(p, "rb").read() for p in paths[lo:lo + 3]], pin=False)
+        assert torch.equal(b["jpeg_coefs"], want["jpeg_coefs"]) and torch.equal(b["jpeg_table"], want["jpeg_table"])
+        assert b["jpeg_meta"].tolist() == want["jpeg_meta"].tolist() and b["jpeg_raw"] == []
