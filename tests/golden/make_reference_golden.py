@@ -5,7 +5,8 @@
 What runs is the reference's source text, executed verbatim:
 
   organiser script  example_scripts/Multimodal_example_task2C.txt
-      class MultimodalClassifier (:152-197), def train (:200-223), def test (:225-242), def evaluate (:259-280)
+      class MultimodalDataset (:28-72), class MultimodalClassifier (:152-197), def train (:200-223), def test (:225-242),
+      def evaluate (:259-280)
   participant script example_scripts/Multimodal_example_task2C.py
       class LLMWithClassificationHead (:307-392), ConcatAttention3 (:476-499), CustomDenseNet161 (:562-585),
       MultimodalClassifier incl. get_params (:587-685), def train (:689-776), test (:779-834), evaluate (:837-879)
@@ -115,6 +116,38 @@ def run_organiser():
     return fx
 
 
+def run_dataset():
+    """The organiser script's own ``MultimodalDataset`` (.txt:28-72), executed verbatim on three JPEG files: what
+    ``__getitem__`` hands the loop -- token ids / mask at the script's max length 512, label, and the image after the
+    script's Resize(256) / CenterCrop(224) / ToTensor / Normalize on the PIL image.  The files themselves travel in the
+    fixture (their encoder's output is not guaranteed to be reproducible elsewhere); the image tensors are stored as the
+    uint8 pixel values they were computed from ((x * std + mean) * 255 is integral up to rounding noise)."""
+    from PIL import Image
+    from torch.utils.data import DataLoader, Dataset
+    from torchvision import transforms
+    lines = open(os.path.join(REF, "Multimodal_example_task2C.txt"), encoding="utf-8").readlines()
+    with tempfile.TemporaryDirectory() as tmp:
+        tok = refpin.EncodePlusTokenizer(tmp)
+        ns = {"torch": torch, "Dataset": Dataset, "Image": Image, "transforms": transforms, "train_max_seq_len": 512,
+              "AutoTokenizer": types.SimpleNamespace(from_pretrained=lambda name: tok)}
+        src, span = _top_level_block(lines, "class MultimodalDataset")
+        exec(compile(src, f"Multimodal_example_task2C.txt:{span[0]}", "exec"), ns)
+        files = refpin.dataset_jpegs()
+        paths = []
+        for i, f in enumerate(files):
+            paths.append(os.path.join(tmp, f"img_{i}.jpg"))
+            open(paths[-1], "wb").write(f)
+        ids = [f"data/x/img_{i}.jpg" for i in range(len(files))]
+        ds = ns["MultimodalDataset"](ids, refpin.DATASET_TEXTS, paths, refpin.DATASET_LABELS)
+        batch = next(iter(DataLoader(ds, batch_size=len(files), shuffle=False)))
+    mean = torch.tensor((0.485, 0.456, 0.406)).view(1, 3, 1, 1)
+    std = torch.tensor((0.229, 0.224, 0.225)).view(1, 3, 1, 1)
+    px = (batch["image"] * std + mean) * 255.0
+    assert (px - px.round()).abs().max() < 1e-3
+    return {"span": span, "files": files, "id": list(batch["id"]), "text": batch["text"], "text_mask": batch["text_mask"],
+            "label": batch["label"], "image_u8": px.round().to(torch.uint8), "keys": sorted(batch.keys())}
+
+
 def run_participant():
     from transformers import get_linear_schedule_with_warmup
     with tempfile.TemporaryDirectory() as tmp:
@@ -163,7 +196,7 @@ def run_participant():
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     torch.set_num_threads(1)
-    fx = {"organiser": run_organiser(), "participant": run_participant(),
+    fx = {"organiser": run_organiser(), "participant": run_participant(), "dataset": run_dataset(),
           "versions": {"torch": torch.__version__, "transformers": __import__("transformers").__version__,
                        "torchvision": __import__("torchvision").__version__}}
     out = os.path.join(HERE, "reference_run_golden.pt")

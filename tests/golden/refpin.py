@@ -124,3 +124,49 @@ def param_norms(model: nn.Module, grads: bool = False):
         t = p.grad if grads else p.detach()
         return None if t is None else float(t.double().norm())
     return {n: norm(p) for n, p in model.named_parameters()}
+
+
+# ------------------------------------------------------------------------------------------------- Dataset run
+DATASET_TEXTS = ["the memes! هذا ميم propaganda", "propaganda? the meme.", "ميم"]
+DATASET_LABELS = [1, 0, 1]
+DATASET_SIZES = [(300, 400), (420, 310), (256, 256)]          # (height, width) of the synthetic JPEG files
+
+
+class EncodePlusTokenizer:
+    """A tokenizer built offline from a 130-entry WordPiece vocabulary, with the ``encode_plus`` entry point the reference's
+    Dataset calls (.txt:54-56; transformers 5.x dropped the name: for one text it is ``__call__``)."""
+
+    def __init__(self, workdir):
+        import os
+        from transformers import DistilBertTokenizer
+        ar = list("ابتثجحخدذرزسشصضطظعغفقكلمنهوي")
+        lat = list("abcdefghijklmnopqrstuvwxyz")
+        vocab = (["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + lat + ["##" + c for c in lat] +
+                 ["meme", "propaganda", "the", "##s", "!", "?", "."] + ar + ["##" + c for c in ar])
+        path = os.path.join(str(workdir), "vocab.txt")
+        with open(path, "w", encoding="utf-8") as f:
+            f.write("\n".join(vocab))
+        self.tok = DistilBertTokenizer(path, do_lower_case=False)
+
+    def encode_plus(self, text, **kw):
+        return self.tok(text, **kw)
+
+
+def dataset_jpegs():
+    """The Dataset run's image files: deterministic photo-like content, encoded by Pillow (baseline, progressive, 4:4:4)."""
+    import io
+
+    import numpy as np
+    import torch.nn.functional as F
+    from PIL import Image
+    rng = np.random.default_rng(2024)
+    files = []
+    for i, (h, w) in enumerate(DATASET_SIZES):
+        base = torch.from_numpy(rng.random((1, 3, 7, 9), dtype=np.float32))
+        im = F.interpolate(base, size=(h, w), mode="bicubic", align_corners=False)[0]
+        im = im + 0.04 * torch.from_numpy(rng.standard_normal((3, h, w)).astype(np.float32))
+        b = io.BytesIO()
+        Image.fromarray((im.clamp(0, 1) * 255).byte().permute(1, 2, 0).numpy()).save(
+            b, "JPEG", quality=(85, 70, 92)[i], subsampling=(2, 1, 0)[i], progressive=(i == 1))
+        files.append(b.getvalue())
+    return files

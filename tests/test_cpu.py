@@ -842,3 +842,59 @@ def test_jpeg_collate_in_dataloader_workers(tmp_path):
         want = jpeg.pack_jpeg_batch([open(p, "rb").read() for p in paths[lo:lo + 3]], pin=False)
         assert torch.equal(b["jpeg_coefs"], want["jpeg_coefs"]) and torch.equal(b["jpeg_table"], want["jpeg_table"])
         assert b["jpeg_meta"].tolist() == want["jpeg_meta"].tolist() and b["jpeg_raw"] == []
+
+
+# ------------------------------------------------------------------------------------------------- Dataset contract
+def _reference_dataset_fixture(tmp_path):
+    refpin, fx = _refpin()
+    fx = fx["dataset"]
+    paths = []
+    for i, f in enumerate(fx["files"]):
+        p = tmp_path / f"img_{i}.jpg"
+        p.write_bytes(f)
+        paths.append(str(p))
+    tok = refpin.EncodePlusTokenizer(tmp_path)
+
+    def tokenize(text):
+        e = tok.tok(text, add_special_tokens=True)
+        return e["input_ids"], e["attention_mask"]
+    return refpin, fx, paths, tokenize
+
+
+def test_dataset_contract_matches_reference_dataset_run(tmp_path):
+    """The organiser script's own ``MultimodalDataset`` (.txt:28-72, executed verbatim when the fixture was made) against
+    data.MemeDataset: same keys, ids, token ids / mask at the script's length 512, labels; the decoded pixels are Pillow's
+    (directly, and through the split JPEG decode); and the tensor-path transform the GPU kernel implements stays within
+    ONE uint8 step of the script's PIL transform (PIL rounds the resized image to uint8, twice; the kernel does not)."""
+    import ctypes
+    import io
+    import torch.nn.functional as F
+    from PIL import Image
+    from augment_ref import build_host_jpeg_harness
+    from b200mm import data as D, jpeg
+    refpin, fx, paths, tokenize = _reference_dataset_fixture(tmp_path)
+    ds = D.MemeDataset(fx["id"], refpin.DATASET_TEXTS, paths, refpin.DATASET_LABELS, tokenizer=tokenize, max_len=512)
+    batch = D.collate_packed([ds[i] for i in range(len(ds))], pin=False)
+    assert sorted({"image" if k.startswith("image") else k for k in batch}) == sorted(fx["keys"])
+    assert batch["id"] == fx["id"] and torch.equal(batch["text"], fx["text"]) and batch["text"].dtype == torch.int64
+    assert torch.equal(batch["text_mask"], fx["text_mask"]) and torch.equal(batch["label"], fx["label"])
+    host = ctypes.CDLL(build_host_jpeg_harness(tmp_path))
+    mean = torch.tensor((0.485, 0.456, 0.406)).view(3, 1, 1)
+    std = torch.tensor((0.229, 0.224, 0.225)).view(3, 1, 1)
+    for k, f in enumerate(fx["files"]):
+        px = ds[k]["image"]
+        assert torch.equal(px, torch.from_numpy(np.asarray(Image.open(io.BytesIO(f)).convert("RGB")).copy()))
+        coefs, qtabs, info = jpeg.entropy_decode(D.file_bytes_loader(paths[k]))
+        out = np.empty(tuple(px.shape), dtype=np.uint8)
+        host.host_jpeg_reconstruct(ctypes.c_void_p(coefs.ctypes.data), ctypes.c_void_p(qtabs.ctypes.data),
+                                   ctypes.c_void_p(info.ctypes.data), ctypes.c_void_p(out.ctypes.data))
+        assert np.array_equal(out, px.numpy())
+        h, w = px.shape[:2]
+        nh, nw = (256, int(256 * w / h)) if h <= w else (int(256 * h / w), 256)
+        r = F.interpolate(px.permute(2, 0, 1).float()[None], size=(nh, nw), mode="bilinear", antialias=True,
+                          align_corners=False)[0]
+        top, left = int(round((nh - 224) / 2.0)), int(round((nw - 224) / 2.0))
+        ours = (r[:, top:top + 224, left:left + 224] / 255.0 - mean) / std
+        steps = (ours - (fx["image_u8"][k].float() / 255.0 - mean) / std).abs() * std * 255.0    # in uint8 steps
+        assert steps.max().item() < 1.05 and steps.mean().item() < 0.35, (k, steps.max().item(), steps.mean().item())
+    assert steps.max().item() < 1e-3           # the 256 x 256 file needs no resize: only Normalize, exact
