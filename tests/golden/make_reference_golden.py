@@ -8,7 +8,7 @@ What runs is the reference's source text, executed verbatim:
       class MultimodalDataset (:28-72), class MultimodalClassifier (:152-197), def train (:200-223), def test (:225-242),
       def evaluate (:259-280)
   participant script example_scripts/Multimodal_example_task2C.py
-      class LLMWithClassificationHead (:307-392), ConcatAttention3 (:476-499), CustomDenseNet161 (:562-585),
+      class MultimodalDataset (:206-304), LLMWithClassificationHead (:307-392), ConcatAttention3 (:476-499), CustomDenseNet161 (:562-585),
       MultimodalClassifier incl. get_params (:587-685), def train (:689-776), test (:779-834), evaluate (:837-879)
 
 with the names they look up at run time bound to the stock libraries -- except the three network-bound constructors,
@@ -148,6 +148,52 @@ def run_dataset():
             "label": batch["label"], "image_u8": px.round().to(torch.uint8), "keys": sorted(batch.keys())}
 
 
+def run_participant_dataset():
+    """The participant script's ``MultimodalDataset`` (.py:206-304), executed verbatim: its Compose -- Resize((224, 224)),
+    RandomHorizontalFlip, ColorJitter(.1, .1, .1, .1), RandomRotation(15), ToTensor, Normalize -- on the PIL image, with
+    torch's generator seeded before every ``__getitem__`` so that the draws can be replayed without the reference
+    (torch.rand(1) for the flip, ColorJitter.get_params, RandomRotation.get_params, in that order); BLIP captioning
+    (:195-204, CUDA + a download) is a stub that returns fixed strings."""
+    from PIL import Image
+    from torch.utils.data import Dataset
+    from torchvision import transforms
+    path = os.path.join(REF, "Multimodal_example_task2C.py")
+    src = open(path, encoding="utf-8").read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "MultimodalDataset")
+
+    class ImageCaptioning:
+        def generate_caption(self, images, texts):
+            return [f"{t} the propaganda" for t in texts]
+
+    with tempfile.TemporaryDirectory() as tmp:
+        tok = refpin.EncodePlusTokenizer(tmp)
+        ns = {"torch": torch, "Dataset": Dataset, "Image": Image, "transforms": transforms, "tqdm": lambda it: it,
+              "train_max_seq_len": 512, "text_model": "stub-text", "english_text_model": "stub-caption",
+              "AutoTokenizer": types.SimpleNamespace(from_pretrained=lambda name: tok),
+              "ImageCaptioning": ImageCaptioning}
+        exec(compile(ast.get_source_segment(src, node), f"Multimodal_example_task2C.py:{node.lineno}", "exec"), ns)
+        files = refpin.dataset_jpegs()[:2]
+        paths = []
+        for i, f in enumerate(files):
+            paths.append(os.path.join(tmp, f"img_{i}.jpg"))
+            open(paths[-1], "wb").write(f)
+        ids = [f"data/x/img_{i}.jpg" for i in range(len(files))]
+        ds = ns["MultimodalDataset"](ids, refpin.DATASET_TEXTS[:2], paths, refpin.DATASET_LABELS[:2])
+        items = []
+        for i in range(len(files)):
+            torch.manual_seed(refpin.DATASET_AUG_SEED + i)
+            items.append(ds[i])
+    mean = torch.tensor((0.485, 0.456, 0.406)).view(3, 1, 1)
+    std = torch.tensor((0.229, 0.224, 0.225)).view(3, 1, 1)
+    px = torch.stack([(it["image"] * std + mean) * 255.0 for it in items])
+    assert (px - px.round()).abs().max() < 1e-3
+    return {"line": node.lineno, "keys": sorted(items[0].keys()), "captions": list(ds.precalculated_captions),
+            "text": torch.stack([it["text"] for it in items]), "text_mask": torch.stack([it["text_mask"] for it in items]),
+            "caption_text": torch.stack([it["caption_text"] for it in items]),
+            "caption_text_mask": torch.stack([it["caption_text_mask"] for it in items]),
+            "label": torch.stack([it["label"] for it in items]), "image_u8": px.round().to(torch.uint8)}
+
+
 def run_participant():
     from transformers import get_linear_schedule_with_warmup
     with tempfile.TemporaryDirectory() as tmp:
@@ -197,6 +243,7 @@ if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     torch.set_num_threads(1)
     fx = {"organiser": run_organiser(), "participant": run_participant(), "dataset": run_dataset(),
+          "participant_dataset": run_participant_dataset(),
           "versions": {"torch": torch.__version__, "transformers": __import__("transformers").__version__,
                        "torchvision": __import__("torchvision").__version__}}
     out = os.path.join(HERE, "reference_run_golden.pt")

@@ -130,6 +130,7 @@ def param_norms(model: nn.Module, grads: bool = False):
 DATASET_TEXTS = ["the memes! هذا ميم propaganda", "propaganda? the meme.", "ميم"]
 DATASET_LABELS = [1, 0, 1]
 DATASET_SIZES = [(300, 400), (420, 310), (256, 256)]          # (height, width) of the synthetic JPEG files
+DATASET_AUG_SEED = 77                                        # torch.manual_seed(DATASET_AUG_SEED + i) before sample i of the participant Dataset
 
 
 class EncodePlusTokenizer:

@@ -898,3 +898,62 @@ def test_dataset_contract_matches_reference_dataset_run(tmp_path):
         steps = (ours - (fx["image_u8"][k].float() / 255.0 - mean) / std).abs() * std * 255.0    # in uint8 steps
         assert steps.max().item() < 1.05 and steps.mean().item() < 0.35, (k, steps.max().item(), steps.mean().item())
     assert steps.max().item() < 1e-3           # the 256 x 256 file needs no resize: only Normalize, exact
+
+
+def test_train_transform_matches_participant_dataset_run(tmp_path):
+    """The participant script's own ``MultimodalDataset`` (.py:206-304, executed verbatim with torch's generator seeded per
+    sample when the fixture was made): its keys and token tensors against data.MemeDataset with captions, and its
+    augmented image -- Resize((224, 224)) / flip / ColorJitter / RandomRotation / ToTensor / Normalize on the PIL image --
+    against the kernels' arithmetic fed with the SAME draws, replayed here from the seed in the order the script's Compose
+    consumes them.  A wrong operator order, range or rotation direction would be an O(1) error; what remains is PIL's uint8
+    quantisation (test_augment_semantics_against_the_scripts_pil_transform)."""
+    import ctypes
+    import io
+    import torch.nn.functional as F
+    import torchvision.transforms as T
+    from PIL import Image
+    from augment_ref import build_host_harness
+    from b200mm import data as D
+    refpin, fx, paths, tokenize = _reference_dataset_fixture(tmp_path)
+    fx = _refpin()[1]["participant_dataset"]
+    n = fx["image_u8"].shape[0]
+    ds = D.MemeDataset([f"data/x/img_{i}.jpg" for i in range(n)], refpin.DATASET_TEXTS[:n], paths[:n],
+                       refpin.DATASET_LABELS[:n], tokenizer=tokenize, max_len=512, captions=fx["captions"],
+                       caption_tokenizer=tokenize, caption_pad_id=0)
+    batch = D.collate_packed([ds[i] for i in range(n)], pin=False)
+    assert sorted({"image" if k.startswith("image") else k for k in batch}) == sorted(fx["keys"])
+    for k in ("text", "text_mask", "caption_text", "caption_text_mask", "label"):
+        assert torch.equal(batch[k], fx[k]), k
+    # replay the draws of the script's Compose: RandomHorizontalFlip, ColorJitter.get_params, RandomRotation.get_params
+    flips, perms, factors, angles = [], [], [], []
+    for i in range(n):
+        torch.manual_seed(refpin.DATASET_AUG_SEED + i)
+        flips.append(bool(torch.rand(1) < 0.5))
+        fn_idx, b, c, s, h = T.ColorJitter.get_params([0.9, 1.1], [0.9, 1.1], [0.9, 1.1], [-0.1, 0.1])
+        perms.append(fn_idx)
+        factors.append([b, c, s, h])
+        angles.append(T.RandomRotation.get_params([-15.0, 15.0]))
+    order, params = D.GpuImageTransform.pack_augment(torch.stack(perms), torch.tensor(factors),
+                                                     torch.tensor(angles, dtype=torch.float64))
+    img01 = torch.stack([F.interpolate(ds[i]["image"].permute(2, 0, 1).float()[None], size=(224, 224), mode="bilinear",
+                                       antialias=True, align_corners=False)[0] / 255.0 for i in range(n)]).clamp(0, 1)
+    img01 = torch.where(torch.tensor(flips).view(-1, 1, 1, 1), img01.flip(-1), img01).contiguous()
+    lib = ctypes.CDLL(build_host_harness(tmp_path))
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    out, gm = torch.empty_like(img01), torch.empty(n)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    lib.host_augment_jitter_rotate(vp(img01), vp(order), vp(params), n, 224, 224, (ctypes.c_float * 3)(*mean),
+                                   (ctypes.c_float * 3)(*std), vp(gm), vp(out))
+    stdv, meanv = torch.tensor(std).view(1, 3, 1, 1), torch.tensor(mean).view(1, 3, 1, 1)
+    ref = (fx["image_u8"].float() / 255.0 - meanv) / stdv
+    steps = (out - ref).abs() * stdv * 255.0                       # in uint8 steps
+    print("participant Dataset run vs kernel arithmetic, uint8 steps: mean %.2f, p99 %.2f" % (
+        steps.mean().item(), steps.flatten().quantile(0.99).item()))
+    assert steps.mean().item() < 3.0 and steps.flatten().quantile(0.99).item() < 12.0, (
+        steps.mean().item(), steps.flatten().quantile(0.99).item())
+    # the pin discriminates: with the rotation direction reversed the images no longer agree
+    _, wrong = D.GpuImageTransform.pack_augment(torch.stack(perms), torch.tensor(factors),
+                                                torch.tensor(angles, dtype=torch.float64).neg())
+    lib.host_augment_jitter_rotate(vp(img01), vp(order), vp(wrong), n, 224, 224, (ctypes.c_float * 3)(*mean),
+                                   (ctypes.c_float * 3)(*std), vp(gm), vp(out))
+    assert ((out - ref).abs() * stdv * 255.0).mean().item() > 8.0
