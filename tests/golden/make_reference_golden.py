@@ -11,6 +11,9 @@ What runs is the reference's source text, executed verbatim:
       class MultimodalDataset (:206-304), LLMWithClassificationHead (:307-392), ConcatAttention3 (:476-499), CustomDenseNet161 (:562-585),
       MultimodalClassifier incl. get_params (:587-685), def train (:689-776), test (:779-834), evaluate (:837-879)
 
+  SVM baseline       baselines/subtask_2c.py
+      def run_imgbert_baseline (:74-95), fed with feature files written by this repo's write_features_json
+
 with the names they look up at run time bound to the stock libraries -- except the three network-bound constructors,
 which return from-config modules (tests/golden/refpin.py).  Weights are set by name (refpin.reseed_by_name), inputs are
 refpin.batches: both are reproducible without the reference, so tests/test_cpu.py can demand that the oracle
@@ -194,6 +197,31 @@ def run_participant_dataset():
             "label": torch.stack([it["label"] for it in items]), "image_u8": px.round().to(torch.uint8)}
 
 
+def run_svm_consumer():
+    """The consumer of the feature-extraction contract, ``run_imgbert_baseline`` (baselines/subtask_2c.py:74-95), executed
+    verbatim on feature files written by THIS repo's ``write_features_json``: the results TSV it produces."""
+    import json
+    from os.path import join
+    from sklearn.svm import SVC
+    sys.path.insert(0, ROOT)
+    from b200mm.features import write_features_json
+    path = "/root/reference/baselines/subtask_2c.py"
+    src = open(path, encoding="utf-8").read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "run_imgbert_baseline")
+    ns = {"json": json, "join": join, "np": np, "SVC": SVC}
+    exec(compile(ast.get_source_segment(src, node), f"subtask_2c.py:{node.lineno}", "exec"), ns)
+    corpus = refpin.svm_feature_corpus()
+    with tempfile.TemporaryDirectory() as tmp:
+        for split in ("train", "dev"):
+            c = corpus[split]
+            write_features_json(os.path.join(tmp, "features", f"{split}_feats.json"), c["imgfeats"], c["textfeats"])
+            json.dump([{"id": i, "class_label": l} for i, l in zip(c["id"], c["class_label"])],
+                      open(os.path.join(tmp, f"{split}.json"), "w"))
+        out = os.path.join(tmp, "results.tsv")
+        ns["run_imgbert_baseline"](tmp, "dev", "train.json", "dev.json", out)
+        return {"line": node.lineno, "results_tsv": open(out).read()}
+
+
 def run_participant():
     from transformers import get_linear_schedule_with_warmup
     with tempfile.TemporaryDirectory() as tmp:
@@ -243,7 +271,7 @@ if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     torch.set_num_threads(1)
     fx = {"organiser": run_organiser(), "participant": run_participant(), "dataset": run_dataset(),
-          "participant_dataset": run_participant_dataset(),
+          "participant_dataset": run_participant_dataset(), "svm_consumer": run_svm_consumer(),
           "versions": {"torch": torch.__version__, "transformers": __import__("transformers").__version__,
                        "torchvision": __import__("torchvision").__version__}}
     out = os.path.join(HERE, "reference_run_golden.pt")

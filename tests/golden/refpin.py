@@ -171,3 +171,21 @@ def dataset_jpegs():
             b, "JPEG", quality=(85, 70, 92)[i], subsampling=(2, 1, 0)[i], progressive=(i == 1))
         files.append(b.getvalue())
     return files
+
+
+# ------------------------------------------------------------------------------------------------- SVM-baseline consumer run
+def svm_feature_corpus():
+    """Synthetic ids / labels / feature vectors of the feature-extraction contract (baselines/extract_feat.py:52-67 ->
+    baselines/subtask_2c.py:74-95): 40 train + 12 dev items, 8-d image and 6-d text features with a weak class signal."""
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    for split, n in (("train", 40), ("dev", 12)):
+        ids = [f"data/x/{split}_{i}.jpg" for i in range(n)]
+        y = (torch.rand(n, generator=g) < 0.4).long()
+        y[0], y[1] = 1, 0
+        img = torch.randn(n, 8, generator=g) + 0.8 * y[:, None]
+        txt = torch.randn(n, 6, generator=g) - 0.5 * y[:, None]
+        out[split] = {"id": ids, "class_label": ["propaganda" if v else "not_propaganda" for v in y.tolist()],
+                      "imgfeats": {i: img[k].tolist() for k, i in enumerate(ids)},
+                      "textfeats": {i: txt[k].tolist() for k, i in enumerate(ids)}}
+    return out

@@ -957,3 +957,25 @@ def test_train_transform_matches_participant_dataset_run(tmp_path):
     lib.host_augment_jitter_rotate(vp(img01), vp(order), vp(wrong), n, 224, 224, (ctypes.c_float * 3)(*mean),
                                    (ctypes.c_float * 3)(*std), vp(gm), vp(out))
     assert ((out - ref).abs() * stdv * 255.0).mean().item() > 8.0
+
+
+def test_feature_json_runs_the_reference_svm_consumer(tmp_path):
+    """The feature-extraction contract end to end on the host: files written by ``write_features_json`` were consumed by
+    the reference's own ``run_imgbert_baseline`` (baselines/subtask_2c.py:74-95, executed verbatim when the fixture was
+    made); the same files, read back through ``load_concat_features`` into the consumer's SVC, give its results TSV."""
+    from sklearn.svm import SVC
+    from b200mm.features import load_concat_features, write_features_json
+    refpin, fx = _refpin()
+    fx = fx["svm_consumer"]
+    corpus = refpin.svm_feature_corpus()
+    files = {}
+    for split in ("train", "dev"):
+        c = corpus[split]
+        files[split] = write_features_json(str(tmp_path / "features" / f"{split}_feats.json"), c["imgfeats"], c["textfeats"])
+        feats = json.load(open(files[split]))
+        assert sorted(feats) == ["imgfeats", "textfeats"] and len(feats["imgfeats"]) == len(c["id"])
+    clf = SVC(C=1, kernel="linear", random_state=0)                         # subtask_2c.py:85
+    clf.fit(load_concat_features(files["train"], corpus["train"]["id"]), corpus["train"]["class_label"])
+    pred = clf.predict(load_concat_features(files["dev"], corpus["dev"]["id"]))
+    tsv = "id\tclass_label\trun_id\n" + "".join(f"{i}\t{l}\timgbert\n" for i, l in zip(corpus["dev"]["id"], pred))
+    assert tsv == fx["results_tsv"]
