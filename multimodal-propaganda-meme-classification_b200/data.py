@@ -142,16 +142,23 @@ class GpuImageTransform:
     ``train=True`` draws the flip flags (p = 0.5) from a seeded host generator, one per image.
     ``augment=True`` (with ``train=True``, mode 'square') completes the HEAD script's train transform (.py:224-233):
     ColorJitter(brightness, contrast, saturation, hue) in a per-image random operator order and
-    RandomRotation(degrees) (nearest, zero fill) between the flip and ToTensor / Normalize."""
+    RandomRotation(degrees) (nearest, zero fill) between the flip and ToTensor / Normalize.
+    ``rng='batched'`` (default) draws a batch's parameters in a few vectorised calls from the transform's own seeded
+    generator; ``rng='torchvision'`` draws them image by image from torch's GLOBAL generator with the very calls and in
+    the very order the script's Compose makes them (``torch.rand(1)`` for the flip, ``ColorJitter.get_params``,
+    ``RandomRotation.get_params``), so that after the same ``torch.manual_seed`` the device transform takes the decisions
+    the script's Dataset would take for those samples (tests/test_cpu.py replays a run of the script's own Dataset)."""
 
     def __init__(self, mode: str = "center_crop", *, resize: int = 256, crop: int = 224, train: bool = False,
                  seed: int = 0, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, augment: bool = False,
                  brightness: float = 0.1, contrast: float = 0.1, saturation: float = 0.1, hue: float = 0.1,
-                 degrees: float = 15.0):
+                 degrees: float = 15.0, rng: str = "batched"):
         if mode not in ("center_crop", "square"):
             raise ValueError(f"unknown image transform mode {mode!r}")
         if augment and not (train and mode == "square"):
             raise ValueError("augment=True is the HEAD script's TRAIN transform: it needs train=True and mode='square'")
+        if rng not in ("batched", "torchvision"):
+            raise ValueError("rng must be 'batched' or 'torchvision'")
         if not 0.0 <= hue <= 0.5 or min(brightness, contrast, saturation, degrees) < 0.0:
             raise ValueError("ColorJitter / RandomRotation ranges must be non-negative (hue <= 0.5)")
         self.mode, self.resize, self.crop, self.train = mode, resize, crop, train
@@ -160,6 +167,7 @@ class GpuImageTransform:
         self.jitter = (brightness, contrast, saturation, hue)
         self.degrees = degrees
         self.gen = torch.Generator().manual_seed(seed)
+        self.rng = rng
 
     def _flip(self, n, device):
         if not (self.train and self.mode == "square"):
@@ -195,23 +203,46 @@ class GpuImageTransform:
     def draw_augment(self, n):
         return self.pack_augment(*self.draw_raw(n))
 
-    def _finish(self, img01):
-        order, params = self.draw_augment(img01.shape[0])
+    def draw_torchvision(self, n):
+        """flips bool [n], perm, factors, angles (as ``draw_raw``) from torch's global generator, per image, in the order
+        of the script's Compose (.py:222-233): RandomHorizontalFlip.forward, ColorJitter.forward, RandomRotation.forward."""
+        import torchvision.transforms as T
+        b, c, s, h = self.jitter
+        rng = lambda x: [max(0.0, 1.0 - x), 1.0 + x]          # noqa: E731  (ColorJitter._check_input)
+        flips, perms, factors, angles = [], [], [], []
+        for _ in range(n):
+            flips.append(bool(torch.rand(1) < 0.5))
+            fn_idx, fb, fc, fs, fh = T.ColorJitter.get_params(rng(b), rng(c), rng(s), [-h, h])
+            perms.append(fn_idx)
+            factors.append([fb, fc, fs, fh])
+            angles.append(T.RandomRotation.get_params([-float(self.degrees), float(self.degrees)]))
+        return (torch.tensor(flips), torch.stack(perms), torch.tensor(factors, dtype=torch.float32),
+                torch.tensor(angles, dtype=torch.float64))
+
+    def _draws(self, n, device):
+        """(flip flags on the device or None, (order, params) host tensors or None) for a batch of n images."""
+        if self.augment and self.rng == "torchvision":
+            flips, perm, factors, angles = self.draw_torchvision(n)
+            return flips.to(torch.uint8).pin_memory().to(device, non_blocking=True), self.pack_augment(perm, factors, angles)
+        return self._flip(n, device), None
+
+    def _finish(self, img01, drawn=None):
+        order, params = drawn if drawn is not None else self.draw_augment(img01.shape[0])
         order = order.pin_memory().to(img01.device, non_blocking=True)
         params = params.pin_memory().to(img01.device, non_blocking=True)
         return ops.augment_jitter_rotate(img01, order, params, mean=self.mean, std=self.std)[0]
 
     def packed(self, packed, table):
-        flip = self._flip(table.shape[1], packed.device)
+        flip, drawn = self._draws(table.shape[1], packed.device)
         square = self.mode == "square"
         if self.augment:    # resize + flip + ToTensor to [0, 1] here, Normalize at the end of the augmentation kernel
             return self._finish(ops.preprocess_u8_packed(packed, table, resize=self.resize, crop=self.crop, square=square,
-                                                         flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)))
+                                                         flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)), drawn)
         return ops.preprocess_u8_packed(packed, table, resize=self.resize, crop=self.crop, square=square, flip=flip,
                                         mean=self.mean, std=self.std)
 
     def fixed(self, images):
-        flip = self._flip(images.shape[0], images.device)
+        flip, drawn = self._draws(images.shape[0], images.device)
         if self.augment:
-            return self._finish(ops.u8_normalize(images, flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)))
+            return self._finish(ops.u8_normalize(images, flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)), drawn)
         return ops.u8_normalize(images, flip=flip, mean=self.mean, std=self.std)

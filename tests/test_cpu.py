@@ -925,14 +925,16 @@ def test_train_transform_matches_participant_dataset_run(tmp_path):
     for k in ("text", "text_mask", "caption_text", "caption_text_mask", "label"):
         assert torch.equal(batch[k], fx[k]), k
     # replay the draws of the script's Compose: RandomHorizontalFlip, ColorJitter.get_params, RandomRotation.get_params
+    # (GpuImageTransform(rng="torchvision") does exactly that from torch's global generator)
+    tr = D.GpuImageTransform("square", train=True, augment=True, rng="torchvision")
     flips, perms, factors, angles = [], [], [], []
     for i in range(n):
         torch.manual_seed(refpin.DATASET_AUG_SEED + i)
-        flips.append(bool(torch.rand(1) < 0.5))
-        fn_idx, b, c, s, h = T.ColorJitter.get_params([0.9, 1.1], [0.9, 1.1], [0.9, 1.1], [-0.1, 0.1])
-        perms.append(fn_idx)
-        factors.append([b, c, s, h])
-        angles.append(T.RandomRotation.get_params([-15.0, 15.0]))
+        f, pm, fa, an = tr.draw_torchvision(1)
+        flips.append(bool(f[0]))
+        perms.append(pm[0])
+        factors.append(fa[0].tolist())
+        angles.append(float(an[0]))
     order, params = D.GpuImageTransform.pack_augment(torch.stack(perms), torch.tensor(factors),
                                                      torch.tensor(angles, dtype=torch.float64))
     img01 = torch.stack([F.interpolate(ds[i]["image"].permute(2, 0, 1).float()[None], size=(224, 224), mode="bilinear",
