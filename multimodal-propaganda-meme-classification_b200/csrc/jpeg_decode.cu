@@ -18,6 +18,10 @@
 // components, 4:4:0 and exotic sampling factors) returns B200MM_JPEG_UNSUPPORTED and is left to the caller's loader.
 #include <cstring>
 #include <vector>
+#if defined(__SSE2__) && !defined(__CUDA_ARCH__)
+#include <emmintrin.h>
+#define B200_JPEG_SSE2 1
+#endif
 
 #include "common.cuh"
 #include "jpeg_math.cuh"
@@ -35,6 +39,49 @@ constexpr int kInfoInts = 32;
 const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
                              41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                              30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// Bit i of the result: coefficient i (natural order) of the block is non-zero.
+inline uint64_t nonzero_mask_natural(const int16_t* blk) {
+  uint64_t m = 0;
+#ifdef B200_JPEG_SSE2
+  const __m128i zero = _mm_setzero_si128();
+  for (int i = 0; i < 4; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i + 8));
+    const __m128i z = _mm_packs_epi16(_mm_cmpeq_epi16(a, zero), _mm_cmpeq_epi16(b, zero));   // 0xFF where the value is 0
+    m |= static_cast<uint64_t>(static_cast<uint16_t>(~_mm_movemask_epi8(z))) << (16 * i);
+  }
+#else
+  for (int i = 0; i < 64; ++i) m |= static_cast<uint64_t>(blk[i] != 0) << i;
+#endif
+  return m;
+}
+
+// Natural-order bit mask -> zigzag-order bit mask, one table look-up per byte of the mask.
+struct ZigzagMaskTable {
+  uint64_t t[8][256];
+  ZigzagMaskTable() {
+    uint8_t pos_of_natural[64];
+    for (int k = 0; k < 64; ++k) pos_of_natural[kZigzag[k]] = static_cast<uint8_t>(k);
+    for (int b = 0; b < 8; ++b)
+      for (int v = 0; v < 256; ++v) {
+        uint64_t m = 0;
+        for (int i = 0; i < 8; ++i)
+          if (v & (1 << i)) m |= 1ULL << pos_of_natural[8 * b + i];
+        t[b][v] = m;
+      }
+  }
+  uint64_t zigzag(uint64_t natural) const {
+    uint64_t m = 0;
+    for (int b = 0; b < 8; ++b) m |= t[b][(natural >> (8 * b)) & 0xFF];
+    return m;
+  }
+};
+
+inline const ZigzagMaskTable& zigzag_mask_table() {
+  static const ZigzagMaskTable table;
+  return table;
+}
 
 struct HuffTable {
   bool present = false;
@@ -504,12 +551,32 @@ struct Decoder {
     return 0;
   }
 
+  // One correction bit for every coefficient of `seg` (zigzag positions, ascending): |coefficient| grows by 1 << Al when
+  // the bit is set and that bit of the magnitude is still clear (ITU T.81 G.1.2.3).
+  static inline void refine_nonzeros(BitReader& br, int16_t* blk, uint64_t seg, int p1) {
+    while (seg) {
+      const int pos = __builtin_ctzll(seg);
+      seg &= seg - 1;
+      int16_t* coef = blk + kZigzag[pos];
+      const int v = *coef;
+      const int grow = br.bit() & static_cast<int>((v & p1) == 0);
+      *coef = static_cast<int16_t>(v + (v >= 0 ? grow * p1 : -(grow * p1)));
+    }
+  }
+
+  // Successive-approximation refinement of an AC band -- the hot loop of progressive files (four such scans per file as
+  // Pillow writes them).  The reference formulation walks every position of the band and asks "non-zero?" (a branch that
+  // mispredicts on textured images); here the block's non-zero positions are one 64-bit mask in zigzag order, a run of r
+  // zeros is found with r + 1 count-trailing-zero steps and only the non-zero coefficients in between are visited.
   int block_ac_refine(BitReader& br, Component& c, int16_t* blk, int Ss, int Se, int Al, int& eobrun) {
     const int p1 = 1 << Al, m1 = -(1 << Al);
     const HuffTable& t = ac[c.ta];
+    const uint64_t upto_se = Se == 63 ? ~0ULL : (1ULL << (Se + 1)) - 1;
+    const uint64_t band = upto_se & ~((1ULL << Ss) - 1);
+    const uint64_t nz = zigzag_mask_table().zigzag(nonzero_mask_natural(blk)) & band;   // as the block is on entry
     int k = Ss;
     if (eobrun == 0) {
-      for (; k <= Se; ++k) {
+      while (k <= Se) {
         const int rs = decode_symbol(br, t);
         if (rs < 0) return B200MM_JPEG_CORRUPT;
         int r = rs >> 4, s = rs & 15;
@@ -520,27 +587,26 @@ struct Decoder {
           if (r) eobrun += static_cast<int>(br.get(r));
           break;                           // end of band: the rest of this block is handled below
         }
-        // skip r still-zero coefficients, refining every already non-zero one on the way
-        do {
-          int16_t* coef = blk + kZigzag[k];
-          if (*coef != 0) {
-            if (br.bit() && (*coef & p1) == 0) *coef = static_cast<int16_t>(*coef + (*coef >= 0 ? p1 : m1));
-          } else if (--r < 0) {
-            break;
-          }
-          ++k;
-        } while (k <= Se);
-        if (s) {
-          if (k > 63) return B200MM_JPEG_CORRUPT;
-          blk[kZigzag[k]] = static_cast<int16_t>(s);
+        // the (r + 1)-th still-zero position at or after k (Se + 1 when the band has fewer): where the new coefficient
+        // goes (or, for a zero run of 16, the last position skipped); coefficients placed earlier in this call lie below k
+        const uint64_t from_k = ~((1ULL << k) - 1);
+        uint64_t zeros = ~nz & band & from_k;
+        int target = Se + 1;
+        for (int i = 0; i <= r && zeros; ++i) {
+          if (i == r) target = __builtin_ctzll(zeros);
+          zeros &= zeros - 1;
         }
+        const uint64_t below_target = target >= 64 ? ~0ULL : (1ULL << target) - 1;
+        refine_nonzeros(br, blk, nz & from_k & below_target, p1);
+        if (s) {
+          if (target > 63) return B200MM_JPEG_CORRUPT;
+          blk[kZigzag[target]] = static_cast<int16_t>(s);
+        }
+        k = target + 1;
       }
     }
     if (eobrun > 0) {
-      for (; k <= Se; ++k) {
-        int16_t* coef = blk + kZigzag[k];
-        if (*coef != 0 && br.bit() && (*coef & p1) == 0) *coef = static_cast<int16_t>(*coef + (*coef >= 0 ? p1 : m1));
-      }
+      if (k <= Se) refine_nonzeros(br, blk, nz & ~((1ULL << k) - 1), p1);
       --eobrun;
     }
     return 0;
