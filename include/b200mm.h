@@ -26,6 +26,8 @@ extern "C" {
 #define B200MM_ERR_NO_DRIVER (-2) /* cuTensorMapEncodeTiled could not be resolved */
 #define B200MM_ERR_TENSORMAP (-3) /* the driver rejected a TMA tensor map */
 #define B200MM_ERR_NOT_SM100 (-4) /* current device is not compute capability 10.x */
+#define B200MM_JPEG_UNSUPPORTED (-10) /* a valid JPEG whose coding the split decoder does not handle */
+#define B200MM_JPEG_CORRUPT (-11)     /* not a JPEG, damaged or truncated */
 
 int b200mm_version(void);
 int b200mm_num_sms(void);

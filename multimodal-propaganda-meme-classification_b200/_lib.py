@@ -28,7 +28,8 @@ class B200MMError(RuntimeError):
 
 
 _ERRORS = {-1: "bad argument (shape/alignment contract)", -2: "CUDA driver entry point unavailable",
-           -3: "tensor map rejected by the driver", -4: "device is not sm_100 (B200)"}
+           -3: "tensor map rejected by the driver", -4: "device is not sm_100 (B200)",
+           -10: "JPEG coding not handled by the split decoder", -11: "not a JPEG, or damaged / truncated"}
 
 
 def load(build_if_needed: bool = True) -> ctypes.CDLL:
