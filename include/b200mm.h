@@ -177,6 +177,13 @@ int b200mm_preprocess_u8(const void* images, const int* heights, const int* widt
 int b200mm_preprocess_u8_packed(const void* packed, const long long* offsets, const int* heights, const int* widths,
                                 const void* flip, int n, int resize, int crop, int square, const float* mean3,
                                 const float* std3, float* out, void* stream);
+/* Same contract, PILLOW-EXACT: the resize is Pillow's 8-bit two-pass bilinear (22-bit fixed-point coefficients, uint8
+ * between the passes; src/libImaging/Resample.c restated in csrc/resample_math.cuh), ToTensor / Normalize with torch's
+ * roundings -- the output equals the tensor the reference's Dataset builds from the PIL image bit for bit
+ * (example_scripts/Multimodal_example_task2C.txt:37-41, :50).  Sides that shrink by more than 31x are not supported. */
+int b200mm_preprocess_u8_packed_pil(const void* packed, const long long* offsets, const int* heights, const int* widths,
+                                    const void* flip, int n, int resize, int crop, int square, const float* mean3,
+                                    const float* std3, float* out, void* stream);
 /* Batch already at network resolution: [n, H, W, 3] uint8 -> ToTensor -> Normalize -> fp32 NCHW (W % 4 == 0). */
 int b200mm_u8_normalize_nchw(const void* src, const void* flip, int n, int H, int W, const float* mean3,
                              const float* std3, float* out, void* stream);

@@ -114,6 +114,8 @@ declare("b200mm_conv_weight_rotate_multi", [c_ptr, c_int, c_ptr])
 declare("b200mm_preprocess_u8", [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_preprocess_u8_packed", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
                                         c_ptr])
+declare("b200mm_preprocess_u8_packed_pil", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                        c_ptr])
 declare("b200mm_u8_normalize_nchw", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_jpeg_parse", [c_ptr, c_longlong, c_ptr])
 declare("b200mm_jpeg_entropy_decode", [c_ptr, c_longlong, c_ptr, c_ptr, c_ptr])

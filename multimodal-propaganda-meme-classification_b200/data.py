@@ -147,18 +147,24 @@ class GpuImageTransform:
     generator; ``rng='torchvision'`` draws them image by image from torch's GLOBAL generator with the very calls and in
     the very order the script's Compose makes them (``torch.rand(1)`` for the flip, ``ColorJitter.get_params``,
     ``RandomRotation.get_params``), so that after the same ``torch.manual_seed`` the device transform takes the decisions
-    the script's Dataset would take for those samples (tests/test_cpu.py replays a run of the script's own Dataset)."""
+    the script's Dataset would take for those samples (tests/test_cpu.py replays a run of the script's own Dataset).
+    ``resample='pillow'`` (packed batches) resizes with Pillow's own 8-bit two-pass arithmetic instead of the float
+    kernel: the tensor equals the one the script's Dataset builds from the PIL image bit for bit (csrc/preprocess_pil.cu;
+    verified on the host build against Pillow and a run of the script's Dataset, not yet timed on a GPU)."""
 
     def __init__(self, mode: str = "center_crop", *, resize: int = 256, crop: int = 224, train: bool = False,
                  seed: int = 0, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, augment: bool = False,
                  brightness: float = 0.1, contrast: float = 0.1, saturation: float = 0.1, hue: float = 0.1,
-                 degrees: float = 15.0, rng: str = "batched"):
+                 degrees: float = 15.0, rng: str = "batched", resample: str = "float"):
         if mode not in ("center_crop", "square"):
             raise ValueError(f"unknown image transform mode {mode!r}")
         if augment and not (train and mode == "square"):
             raise ValueError("augment=True is the HEAD script's TRAIN transform: it needs train=True and mode='square'")
         if rng not in ("batched", "torchvision"):
             raise ValueError("rng must be 'batched' or 'torchvision'")
+        if resample not in ("float", "pillow"):
+            raise ValueError("resample must be 'float' or 'pillow'")
+        self.resample = resample
         if not 0.0 <= hue <= 0.5 or min(brightness, contrast, saturation, degrees) < 0.0:
             raise ValueError("ColorJitter / RandomRotation ranges must be non-negative (hue <= 0.5)")
         self.mode, self.resize, self.crop, self.train = mode, resize, crop, train
@@ -237,9 +243,10 @@ class GpuImageTransform:
         square = self.mode == "square"
         if self.augment:    # resize + flip + ToTensor to [0, 1] here, Normalize at the end of the augmentation kernel
             return self._finish(ops.preprocess_u8_packed(packed, table, resize=self.resize, crop=self.crop, square=square,
-                                                         flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)), drawn)
+                                                         flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0),
+                                                         resample=self.resample), drawn)
         return ops.preprocess_u8_packed(packed, table, resize=self.resize, crop=self.crop, square=square, flip=flip,
-                                        mean=self.mean, std=self.std)
+                                        mean=self.mean, std=self.std, resample=self.resample)
 
     def fixed(self, images):
         flip, drawn = self._draws(images.shape[0], images.device)

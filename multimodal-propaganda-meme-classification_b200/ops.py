@@ -776,16 +776,21 @@ def pack_images(images, pin: bool = True):
 
 
 def preprocess_u8_packed(packed, table, *, resize=256, crop=224, square=False, flip=None, mean=IMAGENET_MEAN,
-                         std=IMAGENET_STD):
+                         std=IMAGENET_STD, resample="float"):
     """packed: uint8 CUDA buffer, table: int64 CUDA [3, n] (offset | height | width) from ``pack_images``.
     Returns fp32 [n, 3, crop, crop]: Resize(resize) -> CenterCrop(crop) (square=False, .txt:37-41) or
     Resize((crop, crop)) (square=True, HEAD script :224), optional per-image horizontal flip (uint8 flags [n]),
-    then ToTensor -> Normalize -- antialiased bilinear like torchvision's tensor path."""
+    then ToTensor -> Normalize -- antialiased bilinear like torchvision's tensor path (``resample='float'``), or with
+    Pillow's own 8-bit two-pass arithmetic (``resample='pillow'``: bit-identical to what the reference's Dataset computes
+    on the PIL image; sides shrinking by more than 31x are not supported)."""
+    if resample not in ("float", "pillow"):
+        raise ValueError("resample must be 'float' or 'pillow'")
     _chk(packed, torch.uint8, "packed images")
     n = table.shape[1]
     hw = table[1:3].to(torch.int32).contiguous()            # [2, n] int32 heights | widths (tiny device op)
     out = torch.empty(n, 3, crop, crop, device=packed.device, dtype=f32)
-    _lib.call("b200mm_preprocess_u8_packed", _p(packed), _p(table[0]), _p(hw[0]), _p(hw[1]), _p(flip), n, int(resize),
+    entry = "b200mm_preprocess_u8_packed_pil" if resample == "pillow" else "b200mm_preprocess_u8_packed"
+    _lib.call(entry, _p(packed), _p(table[0]), _p(hw[0]), _p(hw[1]), _p(flip), n, int(resize),
               int(crop), int(square), _c3(mean), _c3(std), _p(out), _s())
     return out
 

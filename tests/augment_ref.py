@@ -89,3 +89,12 @@ def jpeg_cases(seed=0):
         cases.append((f"noise {kw}", enc(noise, **kw)))
         cases.append((f"photo {kw}", enc(photo(240, 320), **kw)))
     return cases
+
+
+def build_host_resample_harness(out_dir):
+    """g++ build of tests/host/host_resample.cpp (csrc/resample_math.cuh -- Pillow's 8-bit resize restated -- for the CPU)."""
+    lib = os.path.join(str(out_dir), "libhost_resample.so")
+    csrc = os.path.join(ROOT, "multimodal-propaganda-meme-classification_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", csrc,
+                    os.path.join(ROOT, "tests", "host", "host_resample.cpp"), "-o", lib], check=True)
+    return lib

@@ -981,3 +981,51 @@ def test_feature_json_runs_the_reference_svm_consumer(tmp_path):
     pred = clf.predict(load_concat_features(files["dev"], corpus["dev"]["id"]))
     tsv = "id\tclass_label\trun_id\n" + "".join(f"{i}\t{l}\timgbert\n" for i, l in zip(corpus["dev"]["id"], pred))
     assert tsv == fx["results_tsv"]
+
+
+def test_pillow_exact_resize_arithmetic_on_host(tmp_path):
+    """csrc/resample_math.cuh (the arithmetic of preprocess_pil.cu: Pillow's 8-bit two-pass bilinear resize restated)
+    compiled for the host: (a) equals ``Image.resize(..., BILINEAR)`` byte for byte over down- / up-scaling, identity and
+    extreme aspect ratios; (b) the per-pixel transform function the kernel calls equals torchvision's PIL Compose
+    (Resize(256) + CenterCrop(224), and Resize((224, 224)) + flip); (c) on the files of the reference-run fixture it
+    reproduces the pixels the organiser script's OWN Dataset produced, exactly -- with the split JPEG decode in front, the
+    step's whole input tensor is the reference's; (d) torch's ToTensor / Normalize are the three IEEE operations the kernel
+    applies (byte / 255, - mean, / std)."""
+    import ctypes
+    import io
+    import torchvision.transforms as T
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    from augment_ref import build_host_resample_harness
+    lib = ctypes.CDLL(build_host_resample_harness(tmp_path))
+    lib.host_pil_resize.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    lib.host_pil_preprocess.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p]
+    rng = np.random.default_rng(0)
+    for (h, w) in [(300, 400), (420, 310), (256, 256), (97, 1001), (1001, 97), (513, 259), (1200, 1000), (50, 70), (3, 5),
+                   (1, 1)]:
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for (nh, nw) in [(224, 224), (256, int(256 * w / h)) if h <= w else (int(256 * h / w), 256), (h, w), (300, 500)]:
+            out = np.empty((nh, nw, 3), dtype=np.uint8)
+            assert lib.host_pil_resize(src.ctypes.data, h, w, nh, nw, out.ctypes.data) == 0
+            assert np.array_equal(out, np.asarray(Image.fromarray(src).resize((nw, nh), Image.BILINEAR))), (h, w, nh, nw)
+    for (h, w) in [(300, 401), (419, 310), (257, 300), (640, 481), (97, 1001), (225, 224)]:
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        pil = Image.fromarray(src)
+        for square, flip in ((0, 0), (1, 0), (1, 1)):
+            want = T.Resize((224, 224))(pil) if square else T.CenterCrop(224)(T.Resize(256)(pil))
+            want = TF.hflip(want) if flip else want
+            out = np.empty((224, 224, 3), dtype=np.uint8)
+            assert lib.host_pil_preprocess(src.ctypes.data, h, w, 256, 224, square, flip, out.ctypes.data) == 0
+            assert np.array_equal(out, np.asarray(want)), (h, w, square, flip)
+    fx = _refpin()[1]["dataset"]
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    for k, f in enumerate(fx["files"]):
+        px = np.asarray(Image.open(io.BytesIO(f)).convert("RGB")).copy()
+        out = np.empty((224, 224, 3), dtype=np.uint8)
+        assert lib.host_pil_preprocess(px.ctypes.data, px.shape[0], px.shape[1], 256, 224, 0, 0, out.ctypes.data) == 0
+        assert np.array_equal(out, fx["image_u8"][k].permute(1, 2, 0).numpy()), k
+        u8 = torch.from_numpy(out).permute(2, 0, 1)
+        ours = (u8.float().div(255.0) - torch.tensor(mean).view(3, 1, 1)) / torch.tensor(std).view(3, 1, 1)
+        ref = TF.normalize(TF.to_tensor(T.CenterCrop(224)(T.Resize(256)(Image.fromarray(px)))), mean, std)
+        assert torch.equal(ours, ref)
+    assert lib.host_pil_resize(src.ctypes.data, h, w, 2, 2, out.ctypes.data) == -1        # 112x down: refused, not wrong

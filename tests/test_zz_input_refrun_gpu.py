@@ -51,3 +51,42 @@ def test_input_pipeline_against_reference_dataset_run(cuda_device, tmp_path):
         assert steps[2].max().item() < 0.02          # 256 x 256 file: centre crop + Normalize only
         images.append(image)
     assert torch.equal(images[0], images[1])         # pixels decoded on the GPU == Pillow's: identical tensors downstream
+
+
+def test_pillow_exact_input_tensor_equals_reference_dataset(cuda_device, tmp_path):
+    """GpuImageTransform(resample="pillow") behind the split JPEG decode: the tensor that reaches the training step equals
+    the one the organiser script's own Dataset produced (fixture) -- every pixel on the same uint8 value, floats within
+    rounding of torch's ToTensor / Normalize.  (The arithmetic was verified on the host build against Pillow and this
+    fixture, tests/test_cpu.py::test_pillow_exact_resize_arithmetic_on_host; this is the kernel's first run on a GPU.)"""
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import refpin
+    from b200mm import data as D, jpeg
+    from b200mm.loop import DevicePrefetcher
+    fx = torch.load(os.path.join(gold, "reference_run_golden.pt"), weights_only=False)["dataset"]
+    paths = []
+    for i, f in enumerate(fx["files"]):
+        p = tmp_path / f"img_{i}.jpg"
+        p.write_bytes(f)
+        paths.append(str(p))
+    tok = refpin.EncodePlusTokenizer(tmp_path)
+
+    def tokenize(text):
+        e = tok.tok(text, add_special_tokens=True)
+        return e["input_ids"], e["attention_mask"]
+
+    ds = D.MemeDataset(fx["id"], refpin.DATASET_TEXTS, paths, refpin.DATASET_LABELS, tokenizer=tokenize, max_len=512,
+                       image_loader=D.file_bytes_loader)
+    batch = jpeg.collate_jpeg([ds[i] for i in range(len(ds))])
+    tr = D.GpuImageTransform("center_crop", resample="pillow")
+    (text, image, mask, labels, raw), = list(DevicePrefetcher([batch], cuda_device, image_transform=tr))
+    mean = torch.tensor(D.ops.IMAGENET_MEAN, device=cuda_device).view(1, 3, 1, 1)
+    std = torch.tensor(D.ops.IMAGENET_STD, device=cuda_device).view(1, 3, 1, 1)
+    want_u8 = fx["image_u8"].to(cuda_device)
+    got_u8 = ((image * std + mean) * 255.0).round().to(torch.uint8)
+    assert torch.equal(got_u8, want_u8), (got_u8.int() - want_u8.int()).abs().max().item()
+    want = (want_u8.float() / 255.0 - mean) / std
+    assert (image - want).abs().max().item() < 1e-6
