@@ -184,6 +184,17 @@ int b200mm_preprocess_u8_packed(const void* packed, const long long* offsets, co
 int b200mm_preprocess_u8_packed_pil(const void* packed, const long long* offsets, const int* heights, const int* widths,
                                     const void* flip, int n, int resize, int crop, int square, const float* mean3,
                                     const float* std3, float* out, void* stream);
+/* The Pillow-exact Resize / CenterCrop / flip as uint8: out [n, crop, crop, 3] -- input of b200mm_augment_pil. */
+int b200mm_preprocess_u8_packed_pil_u8(const void* packed, const long long* offsets, const int* heights, const int* widths,
+                                       const void* flip, int n, int resize, int crop, int square, void* out, void* stream);
+/* ColorJitter + RandomRotation + ToTensor + Normalize of example_scripts/Multimodal_example_task2C.py:224-235 with Pillow's
+ * own uint8 arithmetic (ImageEnhance blends, convert("L") / ("HSV"), Image.rotate's 16.16 fixed-point affine; restated in
+ * csrc/augment_pil_math.cuh): img_u8 [n, H, W, 3]; order int [n] (2 bits per operator, first applied in the low bits);
+ * alpha fp32 [n, 3] = brightness / contrast / saturation factors; hue int [n] = uint8(hue_factor * 255); affine int [n, 6]
+ * = the rotation matrix in 16.16 fixed point as Pillow's affine_fixed prepares it; sums: n x uint64 scratch; out fp32
+ * [n, 3, H, W].  The output equals the tensor the script's Dataset builds for the same draws, bit for bit. */
+int b200mm_augment_pil(const void* img_u8, const int* order, const float* alpha, const int* hue, const int* affine, int n,
+                       int H, int W, const float* mean3, const float* std3, void* sums, float* out, void* stream);
 /* Batch already at network resolution: [n, H, W, 3] uint8 -> ToTensor -> Normalize -> fp32 NCHW (W % 4 == 0). */
 int b200mm_u8_normalize_nchw(const void* src, const void* flip, int n, int H, int W, const float* mean3,
                              const float* std3, float* out, void* stream);

@@ -66,7 +66,7 @@ def load(build_if_needed: bool = True) -> ctypes.CDLL:
 # kernels launched through this module since the counter was last reset (bench.py's gpu_launches)
 LAUNCHES = [0]
 _KERNELS_PER_CALL = {"b200mm_batchnorm_fwd": 2, "b200mm_jpeg_parse": 0, "b200mm_jpeg_entropy_decode": 0,
-                     "b200mm_jpeg_reconstruct": 2, "b200mm_jpeg_entropy_decode_sparse": 0, "b200mm_jpeg_reconstruct_sparse": 2, "b200mm_augment_jitter_rotate": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0, "b200mm_tune": 0,
+                     "b200mm_jpeg_reconstruct": 2, "b200mm_augment_pil": 2, "b200mm_jpeg_entropy_decode_sparse": 0, "b200mm_jpeg_reconstruct_sparse": 2, "b200mm_augment_jitter_rotate": 2, "b200mm_batchnorm_bwd": 2, "b200mm_version": 0, "b200mm_num_sms": 0, "b200mm_tune": 0,
                      "b200mm_set_step_salt_ptr": 0}
 
 
@@ -116,6 +116,8 @@ declare("b200mm_preprocess_u8_packed", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int
                                         c_ptr])
 declare("b200mm_preprocess_u8_packed_pil", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
                                         c_ptr])
+declare("b200mm_preprocess_u8_packed_pil_u8", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr])
+declare("b200mm_augment_pil", [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_u8_normalize_nchw", [c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr])
 declare("b200mm_jpeg_parse", [c_ptr, c_longlong, c_ptr])
 declare("b200mm_jpeg_entropy_decode", [c_ptr, c_longlong, c_ptr, c_ptr, c_ptr])

@@ -150,7 +150,9 @@ class GpuImageTransform:
     the script's Dataset would take for those samples (tests/test_cpu.py replays a run of the script's own Dataset).
     ``resample='pillow'`` (packed batches) resizes with Pillow's own 8-bit two-pass arithmetic instead of the float
     kernel: the tensor equals the one the script's Dataset builds from the PIL image bit for bit (csrc/preprocess_pil.cu;
-    verified on the host build against Pillow and a run of the script's Dataset, not yet timed on a GPU)."""
+    verified on the host build against Pillow and a run of the script's Dataset, not yet timed on a GPU).  With
+    ``augment=True`` the colour operators and the rotation switch to Pillow's uint8 arithmetic as well
+    (csrc/augment_pil.cu): for the same draws (``rng='torchvision'`` + the same seed) the tensor equals the script's."""
 
     def __init__(self, mode: str = "center_crop", *, resize: int = 256, crop: int = 224, train: bool = False,
                  seed: int = 0, mean=ops.IMAGENET_MEAN, std=ops.IMAGENET_STD, augment: bool = False,
@@ -209,6 +211,36 @@ class GpuImageTransform:
     def draw_augment(self, n):
         return self.pack_augment(*self.draw_raw(n))
 
+    @staticmethod
+    def pack_augment_pil(perm, factors, angles, width, height):
+        """The parameter tables of the Pillow-exact kernels (csrc/augment_pil.cu), built the way Pillow / torchvision's PIL
+        back end build theirs: alpha = the three factors as C floats; hue = ``np.array(hue_factor * 255).astype(np.uint8)``
+        (functional_pil.adjust_hue); affine = ``Image.rotate``'s matrix -- cos / sin rounded to 15 digits, centre
+        (w / 2, h / 2) -- converted to 16.16 fixed point with the half-pixel offsets of libImaging's affine_fixed."""
+        import numpy as np
+        order = (perm << torch.tensor([0, 2, 4, 6])).sum(1).to(torch.int32)
+        alpha = factors[:, :3].float().contiguous()
+        with np.errstate(invalid="ignore"):
+            hue = torch.tensor([int(np.array(float(h) * 255).astype(np.uint8)) for h in factors[:, 3].tolist()],
+                               dtype=torch.int32)
+
+        def fix(v):
+            v = v * 65536.0 + 0.5
+            return int(v) if v >= 0.0 else int(math.floor(v))
+
+        rows = []
+        for angle in angles.tolist():
+            a = -math.radians(angle % 360.0)
+            m = [round(math.cos(a), 15), round(math.sin(a), 15), 0.0, round(-math.sin(a), 15), round(math.cos(a), 15), 0.0]
+            cx, cy = width / 2, height / 2
+            m[2] = m[0] * (-cx) + m[1] * (-cy) + m[2]
+            m[5] = m[3] * (-cx) + m[4] * (-cy) + m[5]
+            m[2] += cx
+            m[5] += cy
+            rows.append([fix(m[0]), fix(m[1]), fix(m[2] + m[0] * 0.5 + m[1] * 0.5),
+                         fix(m[3]), fix(m[4]), fix(m[5] + m[3] * 0.5 + m[4] * 0.5)])
+        return order, alpha, hue, torch.tensor(rows, dtype=torch.int32)
+
     def draw_torchvision(self, n):
         """flips bool [n], perm, factors, angles (as ``draw_raw``) from torch's global generator, per image, in the order
         of the script's Compose (.py:222-233): RandomHorizontalFlip.forward, ColorJitter.forward, RandomRotation.forward."""
@@ -238,7 +270,23 @@ class GpuImageTransform:
         params = params.pin_memory().to(img01.device, non_blocking=True)
         return ops.augment_jitter_rotate(img01, order, params, mean=self.mean, std=self.std)[0]
 
+    def _packed_pil_augment(self, packed, table):
+        """resample='pillow' with augment: uint8 all the way, Pillow's arithmetic in every operator."""
+        n, dev = table.shape[1], packed.device
+        if self.rng == "torchvision":
+            flips, perm, factors, angles = self.draw_torchvision(n)
+            flip = flips.to(torch.uint8).pin_memory().to(dev, non_blocking=True)
+        else:
+            flip = self._flip(n, dev)
+            perm, factors, angles = self.draw_raw(n)
+        u8 = ops.preprocess_u8_packed_pil_u8(packed, table, resize=self.resize, crop=self.crop, square=True, flip=flip)
+        tables = self.pack_augment_pil(perm, factors, angles, self.crop, self.crop)
+        order, alpha, hue, affine = (t.pin_memory().to(dev, non_blocking=True) for t in tables)
+        return ops.augment_pil(u8, order, alpha, hue, affine, mean=self.mean, std=self.std)
+
     def packed(self, packed, table):
+        if self.augment and self.resample == "pillow":
+            return self._packed_pil_augment(packed, table)
         flip, drawn = self._draws(table.shape[1], packed.device)
         square = self.mode == "square"
         if self.augment:    # resize + flip + ToTensor to [0, 1] here, Normalize at the end of the augmentation kernel
@@ -249,6 +297,9 @@ class GpuImageTransform:
                                         mean=self.mean, std=self.std, resample=self.resample)
 
     def fixed(self, images):
+        if self.augment and self.resample == "pillow":
+            raise ValueError("resample='pillow' with augment=True takes packed batches (data.collate_packed / "
+                             "jpeg.collate_jpeg): the Pillow-exact path starts from the decoded image")
         flip, drawn = self._draws(images.shape[0], images.device)
         if self.augment:
             return self._finish(ops.u8_normalize(images, flip=flip, mean=(0.0, 0.0, 0.0), std=(1.0, 1.0, 1.0)), drawn)

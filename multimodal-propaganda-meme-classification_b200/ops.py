@@ -795,6 +795,40 @@ def preprocess_u8_packed(packed, table, *, resize=256, crop=224, square=False, f
     return out
 
 
+def preprocess_u8_packed_pil_u8(packed, table, *, resize=256, crop=224, square=False, flip=None):
+    """Pillow-exact Resize / CenterCrop (or square resize) / flip of a packed batch, kept as uint8 [n, crop, crop, 3] --
+    the PIL image as it enters the script's ColorJitter (``augment_pil``)."""
+    _chk(packed, torch.uint8, "packed images")
+    n = table.shape[1]
+    hw = table[1:3].to(torch.int32).contiguous()
+    out = torch.empty(n, crop, crop, 3, device=packed.device, dtype=torch.uint8)
+    _lib.call("b200mm_preprocess_u8_packed_pil_u8", _p(packed), _p(table[0]), _p(hw[0]), _p(hw[1]), _p(flip), n,
+              int(resize), int(crop), int(square), _p(out), _s())
+    return out
+
+
+def augment_pil(img_u8, order, alpha, hue, affine, *, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """ColorJitter + RandomRotation + ToTensor + Normalize with Pillow's own uint8 arithmetic (csrc/augment_pil.cu).
+    img_u8: uint8 CUDA [n, H, W, 3]; order int32 [n]; alpha fp32 [n, 3]; hue int32 [n]; affine int32 [n, 6]
+    (data.GpuImageTransform.pack_augment_pil builds the four tables).  Returns fp32 [n, 3, H, W]."""
+    _chk(img_u8, torch.uint8, "img_u8")
+    _chk(order, torch.int32, "order")
+    _chk(alpha, f32, "alpha")
+    _chk(hue, torch.int32, "hue")
+    _chk(affine, torch.int32, "affine")
+    if img_u8.dim() != 4 or img_u8.shape[3] != 3 or not img_u8.is_contiguous():
+        raise ValueError("img_u8 must be a contiguous [n, H, W, 3] uint8 tensor")
+    n, H, W, _ = img_u8.shape
+    if tuple(order.shape) != (n,) or tuple(alpha.shape) != (n, 3) or tuple(hue.shape) != (n,) or \
+            tuple(affine.shape) != (n, 6) or not alpha.is_contiguous() or not affine.is_contiguous():
+        raise ValueError("order / hue must be [n], alpha a contiguous [n, 3], affine a contiguous [n, 6]")
+    out = torch.empty(n, 3, H, W, device=img_u8.device, dtype=f32)
+    sums = torch.empty(n, device=img_u8.device, dtype=torch.int64)
+    _lib.call("b200mm_augment_pil", _p(img_u8), _p(order), _p(alpha), _p(hue), _p(affine), n, H, W, _c3(mean), _c3(std),
+              _p(sums), _p(out), _s())
+    return out
+
+
 def u8_normalize(images, *, flip=None, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     """images: uint8 CUDA [n, H, W, 3] already at network resolution -> fp32 [n, 3, H, W] = Normalize(ToTensor(img)),
     optional per-image horizontal flip (uint8 flags [n])."""

@@ -98,3 +98,12 @@ def build_host_resample_harness(out_dir):
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", csrc,
                     os.path.join(ROOT, "tests", "host", "host_resample.cpp"), "-o", lib], check=True)
     return lib
+
+
+def build_host_augment_pil_harness(out_dir):
+    """g++ build of tests/host/host_augment_pil.cpp (csrc/augment_pil_math.cuh -- Pillow's ColorJitter / rotate arithmetic)."""
+    lib = os.path.join(str(out_dir), "libhost_augment_pil.so")
+    csrc = os.path.join(ROOT, "multimodal-propaganda-meme-classification_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", csrc,
+                    os.path.join(ROOT, "tests", "host", "host_augment_pil.cpp"), "-o", lib], check=True)
+    return lib

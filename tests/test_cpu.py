@@ -1029,3 +1029,69 @@ def test_pillow_exact_resize_arithmetic_on_host(tmp_path):
         ref = TF.normalize(TF.to_tensor(T.CenterCrop(224)(T.Resize(256)(Image.fromarray(px)))), mean, std)
         assert torch.equal(ours, ref)
     assert lib.host_pil_resize(src.ctypes.data, h, w, 2, 2, out.ctypes.data) == -1        # 112x down: refused, not wrong
+
+
+def test_pillow_exact_augmentation_arithmetic_on_host(tmp_path):
+    """csrc/augment_pil_math.cuh (the arithmetic of augment_pil.cu) compiled for the host is BYTE-IDENTICAL to Pillow:
+    convert("L") / convert("HSV") / HSV -> RGB over a million values each; ColorJitter in all 24 operator orders followed by
+    the nearest-neighbour rotation against torchvision's PIL back end; and -- with the Pillow-exact resize in front and the
+    draws replayed from the seed -- the pixels the participant script's OWN Dataset produced (reference-run fixture)."""
+    import ctypes
+    import io
+    import itertools
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    from augment_ref import build_host_augment_pil_harness, build_host_resample_harness
+    from b200mm import data as D
+    aug = ctypes.CDLL(build_host_augment_pil_harness(tmp_path))
+    res = ctypes.CDLL(build_host_resample_harness(tmp_path))
+    P, I = ctypes.c_void_p, ctypes.c_int
+    aug.host_pil_convert.argtypes = [P, ctypes.c_longlong, I, P]
+    aug.host_pil_augment.argtypes = [P, I, I, I, P, P, P, P, P]
+    res.host_pil_preprocess.argtypes = [P] + [I] * 6 + [P]
+    rng = np.random.default_rng(0)
+    tri = rng.integers(0, 256, (1000, 1000, 3), dtype=np.uint8)
+    out = np.empty_like(tri)
+    aug.host_pil_convert(tri.ctypes.data, 1000 * 1000, 0, out.ctypes.data)
+    assert np.array_equal(out, np.asarray(Image.fromarray(tri).convert("HSV")))
+    aug.host_pil_convert(tri.ctypes.data, 1000 * 1000, 1, out.ctypes.data)
+    assert np.array_equal(out, np.asarray(Image.fromarray(tri, "HSV").convert("RGB")))
+    aug.host_pil_convert(tri.ctypes.data, 1000 * 1000, 2, out.ctypes.data)
+    assert np.array_equal(out[..., 0], np.asarray(Image.fromarray(tri).convert("L")))
+
+    def run(arr, perm, factors, angle):
+        H, W = arr.shape[:2]
+        order, alpha, hue, affine = (t.numpy() for t in D.GpuImageTransform.pack_augment_pil(
+            torch.tensor([perm]), torch.tensor([factors], dtype=torch.float32), torch.tensor([angle], dtype=torch.float64),
+            W, H))
+        o = np.empty_like(arr)
+        aug.host_pil_augment(arr.ctypes.data, 1, H, W, order.ctypes.data, alpha.ctypes.data, hue.ctypes.data,
+                             affine.ctypes.data, o.ctypes.data)
+        return o
+
+    for t, perm in enumerate(itertools.permutations(range(4))):
+        H, W = (224, 224) if t % 2 else (96, 130)
+        arr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        if t % 3 == 0:
+            arr[:40, :50] = rng.integers(0, 256, (40, 50, 1))              # grey patch: max == min in the hue operator
+        b, c, s = (float(np.float32(rng.uniform(0.9, 1.1))) for _ in range(3))
+        h, ang = float(np.float32(rng.uniform(-0.1, 0.1))), float(np.float32(rng.uniform(-15, 15)))
+        x = Image.fromarray(arr)
+        for fn in perm:
+            x = [lambda v: TF.adjust_brightness(v, b), lambda v: TF.adjust_contrast(v, c),
+                 lambda v: TF.adjust_saturation(v, s), lambda v: TF.adjust_hue(v, h)][fn](x)
+        want = np.asarray(TF.rotate(x, ang, fill=0))
+        assert np.array_equal(run(arr, list(perm), [b, c, s, h], ang), want), (t, perm)
+    # the participant script's own Dataset: decode -> Resize((224, 224)) -> flip -> ColorJitter -> RandomRotation, same seed
+    refpin, fx = _refpin()
+    files, pd = fx["dataset"]["files"], fx["participant_dataset"]
+    tr = D.GpuImageTransform("square", train=True, augment=True, rng="torchvision", resample="pillow")
+    for i in range(pd["image_u8"].shape[0]):
+        px = np.asarray(Image.open(io.BytesIO(files[i])).convert("RGB")).copy()
+        torch.manual_seed(refpin.DATASET_AUG_SEED + i)
+        flips, perm, factors, angles = tr.draw_torchvision(1)
+        u8 = np.empty((224, 224, 3), dtype=np.uint8)
+        assert res.host_pil_preprocess(px.ctypes.data, px.shape[0], px.shape[1], 256, 224, 1, int(flips[0]),
+                                       u8.ctypes.data) == 0
+        got = run(u8, perm[0].tolist(), factors[0].tolist(), float(angles[0]))
+        assert np.array_equal(got, pd["image_u8"][i].permute(1, 2, 0).numpy()), i

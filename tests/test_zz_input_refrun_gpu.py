@@ -90,3 +90,31 @@ def test_pillow_exact_input_tensor_equals_reference_dataset(cuda_device, tmp_pat
     assert torch.equal(got_u8, want_u8), (got_u8.int() - want_u8.int()).abs().max().item()
     want = (want_u8.float() / 255.0 - mean) / std
     assert (image - want).abs().max().item() < 1e-6
+
+
+def test_pillow_exact_train_transform_equals_participant_dataset(cuda_device, tmp_path):
+    """GpuImageTransform("square", train=True, augment=True, rng="torchvision", resample="pillow") behind the split JPEG
+    decode, one sample at a time under the seeds of the fixture: the tensor equals the one the participant script's own
+    Dataset produced (Resize((224, 224)) / flip / ColorJitter / RandomRotation on the PIL image) -- every pixel on the same
+    uint8 value.  (Arithmetic verified on the host build, tests/test_cpu.py::test_pillow_exact_augmentation_arithmetic_on_host;
+    this is the kernels' first run on a GPU.)"""
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gold not in sys.path:
+        sys.path.insert(0, gold)
+    import refpin
+    from b200mm import data as D, jpeg
+    fx = torch.load(os.path.join(gold, "reference_run_golden.pt"), weights_only=False)
+    files, pd = fx["dataset"]["files"], fx["participant_dataset"]
+    tr = D.GpuImageTransform("square", train=True, augment=True, rng="torchvision", resample="pillow")
+    mean = torch.tensor(D.ops.IMAGENET_MEAN, device=cuda_device).view(1, 3, 1, 1)
+    std = torch.tensor(D.ops.IMAGENET_STD, device=cuda_device).view(1, 3, 1, 1)
+    for i in range(pd["image_u8"].shape[0]):
+        packed, table = jpeg.reconstruct_batch(jpeg.pack_jpeg_batch([files[i]]), cuda_device)
+        torch.manual_seed(refpin.DATASET_AUG_SEED + i)
+        image = tr.packed(packed, table)
+        got_u8 = ((image * std + mean) * 255.0).round().to(torch.uint8)
+        want_u8 = pd["image_u8"][i:i + 1].to(cuda_device)
+        assert torch.equal(got_u8, want_u8), (i, (got_u8.int() - want_u8.int()).abs().max().item())
+        assert (image - (want_u8.float() / 255.0 - mean) / std).abs().max().item() < 1e-6
