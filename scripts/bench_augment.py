@@ -46,6 +46,10 @@ def main():
     t_aug = timed(lambda: ops.augment_jitter_rotate(img, order, params))
     t_norm = timed(lambda: ops.u8_normalize(u8))
     t_full = timed(lambda: tr.fixed(u8))
+    # the Pillow-exact pair (uint8 operators, fixed-point rotation) on the same batch
+    perm, factors, angles = tr.draw_raw(n)
+    o2, alpha, hue, affine = (t.to(dev) for t in GpuImageTransform.pack_augment_pil(perm, factors, angles, W, H))
+    t_pil = timed(lambda: ops.augment_pil(u8, o2, alpha, hue, affine))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -56,7 +60,7 @@ def main():
            "augment_gbs": 36 * px / t_aug / 1e3,
            "note": "two kernels: grey-mean pass reads 12 B/pixel; gather pass reads 12 B/pixel and writes 12 B/pixel",
            "u8_normalize_us": t_norm, "u8_normalize_gbs": 15 * px / t_norm / 1e3,
-           "full_train_transform_fixed_us": t_full,
+           "full_train_transform_fixed_us": t_full, "augment_pil_us": t_pil,
            "full_note": "u8_normalize to [0, 1] + parameter draw on the host + two small H2D copies + the two kernels",
            "measured_peaks": peaks}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -40,6 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--resample", default="float", choices=("float", "pillow"), help="pillow: the Pillow-exact kernel")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
@@ -56,18 +57,18 @@ def main():
     packed, table = jpeg.reconstruct_batch(dbatch, dev)
     src_bytes = int((table[1] * table[2] * 3).sum())
     out_bytes = a.n * 3 * 224 * 224 * 4
-    t_crop = timed(lambda: ops.preprocess_u8_packed(packed, table), a.iters)
-    t_square = timed(lambda: ops.preprocess_u8_packed(packed, table, square=True), a.iters)
-    tr = GpuImageTransform("center_crop")
+    t_crop = timed(lambda: ops.preprocess_u8_packed(packed, table, resample=a.resample), a.iters)
+    t_square = timed(lambda: ops.preprocess_u8_packed(packed, table, square=True, resample=a.resample), a.iters)
+    tr = GpuImageTransform("center_crop", resample=a.resample)
     t_path = timed(lambda: tr.packed(*jpeg.reconstruct_batch(dbatch, dev)), a.iters)
-    out = {"images": a.n, "source_megapixels": src_bytes / 3e6, "source_bytes": src_bytes, "output_bytes": out_bytes,
+    out = {"images": a.n, "resample": a.resample, "source_megapixels": src_bytes / 3e6, "source_bytes": src_bytes, "output_bytes": out_bytes,
            "resize256_centercrop224_normalize_ms": t_crop, "resize256_centercrop224_gbs": (src_bytes + out_bytes) / t_crop / 1e6,
            "resize224x224_normalize_ms": t_square, "resize224x224_gbs": (src_bytes + out_bytes) / t_square / 1e6,
            "jpeg_reconstruct_plus_resize_ms": t_path,
            "note": "GB/s = (decoded source bytes + fp32 NCHW output bytes) / time; the centre crop reads only the part of "
                    "the source under the crop window, so its true traffic is lower than the bytes counted"}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "preprocess_bench_r02.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"preprocess_bench_{a.resample}.json" if a.resample != "float" else "preprocess_bench_r02.json"), "w"), indent=1)
     print(json.dumps(out))
 
 
