@@ -107,3 +107,61 @@ def build_host_augment_pil_harness(out_dir):
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", csrc,
                     os.path.join(ROOT, "tests", "host", "host_augment_pil.cpp"), "-o", lib], check=True)
     return lib
+
+
+def build_emulated_pil_kernels(out_dir):
+    """The kernel functions of preprocess_pil.cu and augment_pil.cu (text between their `namespace b200 {` and the C-ABI
+    entry points) compiled for the host behind tests/host/cuda_emulation_shim.h, plus two drivers that run them thread by
+    thread over the same grids the entry points launch."""
+    csrc = os.path.join(ROOT, "multimodal-propaganda-meme-classification_b200", "csrc")
+
+    def kernels(name):
+        text = open(os.path.join(csrc, name)).read()
+        return text[text.index("namespace b200 {"):text.index("using namespace b200;")]
+
+    src = os.path.join(str(out_dir), "emulated_pil_kernels.cpp")
+    with open(src, "w") as f:
+        f.write('#include "cuda_emulation_shim.h"\n#include "resample_math.cuh"\n#include "augment_pil_math.cuh"\n')
+        f.write(kernels("preprocess_pil.cu"))
+        f.write(kernels("augment_pil.cu"))
+        f.write(r'''
+using namespace b200;
+static unsigned cdiv(int a, int b) { return static_cast<unsigned>((a + b - 1) / b); }
+extern "C" void emu_preprocess_pil(const unsigned char* packed, const long long* offsets, const int* heights,
+                                   const int* widths, const unsigned char* flip, int n, int resize, int crop, int square,
+                                   const float* mean3, const float* std3, float* out) {
+  PilPreprocParams p{};
+  p.packed = packed; p.offsets = offsets; p.flip = flip; p.heights = heights; p.widths = widths;
+  p.n = n; p.resize = resize; p.crop = crop; p.square = square; p.out = out;
+  for (int c = 0; c < 3; ++c) { p.mean[c] = mean3[c]; p.std[c] = std3[c]; }
+  emu_launch(preprocess_pil_kernel, cdiv(crop, 32), cdiv(crop, 8), n, 256, p);
+}
+extern "C" void emu_train_transform_pil(const unsigned char* packed, const long long* offsets, const int* heights,
+                                        const int* widths, const unsigned char* flip, int n, int resize, int crop,
+                                        const int* order, const float* alpha, const int* hue, const int* affine,
+                                        const float* mean3, const float* std3, unsigned char* u8, float* out) {
+  emu_launch(preprocess_pil_u8_kernel, cdiv(crop, 32), cdiv(crop, 8), n, 256, packed, offsets, heights, widths, flip, resize,
+             crop, 1, u8);
+  // the grey-level sums: the reduction kernel exchanges data between threads and is not emulated; its per-thread body is
+  // the same two calls
+  unsigned long long* sums = new unsigned long long[n];
+  for (int img = 0; img < n; ++img) {
+    pilaug::Jitter j = load_jitter(order, alpha, hue, img);
+    const int upto = pilaug::contrast_position(j.order);
+    sums[img] = 0;
+    for (long long i = 0; i < static_cast<long long>(crop) * crop; ++i) {
+      const unsigned char* q = u8 + (static_cast<long long>(img) * crop * crop + i) * 3;
+      int r = q[0], g = q[1], b = q[2];
+      pilaug::jitter_pixel(j, 0, upto, 0, r, g, b);
+      sums[img] += pilaug::luma(r, g, b);
+    }
+  }
+  emu_launch(pil_jitter_rotate_kernel, cdiv(crop, 32), cdiv(crop, 8), n, 256, u8, order, alpha, hue, affine, sums, crop, crop,
+             mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out);
+  delete[] sums;
+}
+''')
+    lib = os.path.join(str(out_dir), "libemulated_pil_kernels.so")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "host"),
+                    "-I", csrc, src, "-o", lib], check=True)
+    return lib

@@ -1095,3 +1095,55 @@ def test_pillow_exact_augmentation_arithmetic_on_host(tmp_path):
                                        u8.ctypes.data) == 0
         got = run(u8, perm[0].tolist(), factors[0].tolist(), float(angles[0]))
         assert np.array_equal(got, pd["image_u8"][i].permute(1, 2, 0).numpy()), i
+
+
+def test_pillow_exact_kernel_bodies_emulated_on_host(tmp_path):
+    """Beyond the arithmetic headers: the KERNEL FUNCTIONS of preprocess_pil.cu and augment_pil.cu themselves (their
+    indexing, strides, parameter tables) are compiled for the host behind a small CUDA-name shim and run thread by thread
+    over the grids their entry points launch, on packed batches built by the product's own ``ops.pack_images`` /
+    ``GpuImageTransform.pack_augment_pil``: the output tensors equal what the two reference Dataset runs produced."""
+    import ctypes
+    import io
+    from PIL import Image
+    from augment_ref import build_emulated_pil_kernels
+    from b200mm import data as D, ops
+    lib = ctypes.CDLL(build_emulated_pil_kernels(tmp_path))
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.emu_preprocess_pil.argtypes = [P, P, P, P, P, I, I, I, I, P, P, P]
+    lib.emu_train_transform_pil.argtypes = [P, P, P, P, P, I, I, I, P, P, P, P, P, P, P, P]
+    refpin, fx = _refpin()
+    files = fx["dataset"]["files"]
+    imgs = [torch.from_numpy(np.asarray(Image.open(io.BytesIO(f)).convert("RGB")).copy()) for f in files]
+    packed, table = ops.pack_images(imgs, pin=False)
+    offsets = table[0].contiguous()
+    heights, widths = table[1].to(torch.int32).contiguous(), table[2].to(torch.int32).contiguous()
+    mean = torch.tensor(ops.IMAGENET_MEAN)
+    std = torch.tensor(ops.IMAGENET_STD)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    # organiser transform: Resize(256) / CenterCrop(224) / ToTensor / Normalize
+    n = len(imgs)
+    out = torch.full((n, 3, 224, 224), float("nan"))
+    lib.emu_preprocess_pil(vp(packed), vp(offsets), vp(heights), vp(widths), None, n, 256, 224, 0, vp(mean), vp(std), vp(out))
+    want = (fx["dataset"]["image_u8"].float().div(255.0) - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)
+    assert torch.equal(out, want)
+    # participant transform: Resize((224, 224)) / flip / ColorJitter / RandomRotation / ToTensor / Normalize, seeded draws
+    pd = fx["participant_dataset"]
+    m = pd["image_u8"].shape[0]
+    tr = D.GpuImageTransform("square", train=True, augment=True, rng="torchvision", resample="pillow")
+    flips, perms, factors, angles = [], [], [], []
+    for i in range(m):
+        torch.manual_seed(refpin.DATASET_AUG_SEED + i)
+        f, pm, fa, an = tr.draw_torchvision(1)
+        flips.append(int(f[0]))
+        perms.append(pm[0])
+        factors.append(fa[0])
+        angles.append(an[0])
+    order, alpha, hue, affine = D.GpuImageTransform.pack_augment_pil(torch.stack(perms), torch.stack(factors),
+                                                                    torch.stack(angles), 224, 224)
+    flip = torch.tensor(flips, dtype=torch.uint8)
+    u8 = torch.zeros(m, 224, 224, 3, dtype=torch.uint8)
+    out2 = torch.full((m, 3, 224, 224), float("nan"))
+    lib.emu_train_transform_pil(vp(packed), vp(offsets), vp(heights), vp(widths), vp(flip), m, 256, 224, vp(order),
+                                vp(alpha), vp(hue), vp(affine), vp(mean), vp(std), vp(u8), vp(out2))
+    want2 = (pd["image_u8"].float().div(255.0) - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)
+    assert torch.equal(out2, want2)
