@@ -142,20 +142,8 @@ extern "C" void emu_train_transform_pil(const unsigned char* packed, const long 
                                         const float* mean3, const float* std3, unsigned char* u8, float* out) {
   emu_launch(preprocess_pil_u8_kernel, cdiv(crop, 32), cdiv(crop, 8), n, 256, packed, offsets, heights, widths, flip, resize,
              crop, 1, u8);
-  // the grey-level sums: the reduction kernel exchanges data between threads and is not emulated; its per-thread body is
-  // the same two calls
-  unsigned long long* sums = new unsigned long long[n];
-  for (int img = 0; img < n; ++img) {
-    pilaug::Jitter j = load_jitter(order, alpha, hue, img);
-    const int upto = pilaug::contrast_position(j.order);
-    sums[img] = 0;
-    for (long long i = 0; i < static_cast<long long>(crop) * crop; ++i) {
-      const unsigned char* q = u8 + (static_cast<long long>(img) * crop * crop + i) * 3;
-      int r = q[0], g = q[1], b = q[2];
-      pilaug::jitter_pixel(j, 0, upto, 0, r, g, b);
-      sums[img] += pilaug::luma(r, g, b);
-    }
-  }
+  unsigned long long* sums = new unsigned long long[n]();
+  emu_launch(pil_luma_sum_kernel, kLumaParts, n, 1, kLumaThreads, u8, order, alpha, hue, crop, crop, sums);
   emu_launch(pil_jitter_rotate_kernel, cdiv(crop, 32), cdiv(crop, 8), n, 256, u8, order, alpha, hue, affine, sums, crop, crop,
              mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out);
   delete[] sums;

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE: the handful of CUDA names a simple one-thread-per-element kernel uses, defined for a plain C++
 // compiler, so that the KERNEL BODIES of preprocess_pil.cu / augment_pil.cu (indexing included, not only their arithmetic
-// headers) can be executed thread by thread on the host by tests/test_cpu.py.  Kernels that exchange data between threads
-// (shuffles, shared memory, atomics) compile against the dummies below but are not run this way.
+// headers) can be executed thread by thread on the host by tests/test_cpu.py.  Only kernels whose threads do not exchange
+// data can run this way (integer atomicAdd is fine: sequential addition gives the same sum); the shuffle below is a dummy.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -22,7 +22,7 @@ static inline float __fsub_rn(float a, float b) { volatile float r = a - b; retu
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }                 // not executed
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { *p += v; return *p; }  // not executed
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
 
 // runs `kernel(args...)` for every thread of a (gx, gy, gz) grid of `threads` threads, one after the other
 template <typename K, typename... A>
