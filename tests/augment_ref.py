@@ -153,3 +153,41 @@ extern "C" void emu_train_transform_pil(const unsigned char* packed, const long 
     subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "host"),
                     "-I", csrc, src, "-o", lib], check=True)
     return lib
+
+
+def build_emulated_jpeg_kernels(out_dir):
+    """The device kernels of jpeg_decode.cu (dense and sparse IDCT, up-sampling + colour conversion) compiled for the host
+    behind tests/host/cuda_emulation_shim.h, with a driver that runs them thread by thread over the entry points' grids."""
+    csrc = os.path.join(ROOT, "multimodal-propaganda-meme-classification_b200", "csrc")
+    text = open(os.path.join(csrc, "jpeg_decode.cu")).read()
+    dev = text[text.index("// ---------------------------------------------------------------------------------------------------- device side"):]
+    dev = dev[dev.index("namespace b200 {"):dev.index("using namespace b200;")]
+    src = os.path.join(str(out_dir), "emulated_jpeg_kernels.cpp")
+    with open(src, "w") as f:
+        f.write('#include "cuda_emulation_shim.h"\n#include "jpeg_math.cuh"\n')
+        f.write(dev)
+        f.write(r"""
+using namespace b200;
+static unsigned cdiv(int a, int b) { return static_cast<unsigned>((a + b - 1) / b); }
+// sparse != 0: sp_off / sp_idx / sp_val carry the batch; else coefs does
+extern "C" void emu_jpeg_reconstruct(const short* coefs, const int* sp_off, const unsigned char* sp_idx, const short* sp_val,
+                                     int sparse, const unsigned short* qtabs, const long long* table, int n, int max_blocks,
+                                     int max_w, int max_h, unsigned char* planes, unsigned char* out) {
+  unsigned gx = cdiv(max_blocks, kIdctThreads);
+  if (gx > 4096) gx = 4096;
+  if (sparse)
+    emu_launch(jpeg_idct_kernel<true>, gx, n, 1, kIdctThreads, static_cast<const int16_t*>(nullptr), sp_off, sp_idx, sp_val,
+               qtabs, table, planes);
+  else
+    emu_launch(jpeg_idct_kernel<false>, gx, n, 1, kIdctThreads, coefs, static_cast<const int*>(nullptr),
+               static_cast<const uint8_t*>(nullptr), static_cast<const int16_t*>(nullptr), qtabs, table, planes);
+  unsigned cx = cdiv(max_w, 32), cy = cdiv(max_h, 8);
+  if (cx > 64) cx = 64;
+  if (cy > 256) cy = 256;
+  emu_launch(jpeg_upsample_color_kernel, cx, cy, n, 256, static_cast<const uint8_t*>(planes), table, out);
+}
+""")
+    lib = os.path.join(str(out_dir), "libemulated_jpeg_kernels.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "host"), "-I", csrc, src, "-o", lib],
+                   check=True)
+    return lib

@@ -17,6 +17,9 @@ static EmuDim3 blockIdx, threadIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __restrict__
 #define __ldg(p) (*(p))
+#define __shared__ static
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }

@@ -1147,3 +1147,39 @@ def test_pillow_exact_kernel_bodies_emulated_on_host(tmp_path):
                                 vp(alpha), vp(hue), vp(affine), vp(mean), vp(std), vp(u8), vp(out2))
     want2 = (pd["image_u8"].float().div(255.0) - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)
     assert torch.equal(out2, want2)
+
+
+def test_jpeg_device_kernels_emulated_on_host(tmp_path):
+    """The DEVICE kernels of jpeg_decode.cu -- dense and sparse inverse DCT, up-sampling + colour conversion -- compiled for
+    the host behind the CUDA-name shim and run thread by thread over the grids ``b200mm_jpeg_reconstruct[_sparse]`` launch,
+    on batches packed by ``jpeg.pack_jpeg_batch``: pixels equal Pillow's (the same check the GPU suite makes on a B200; here
+    it guards the kernels' indexing and the sparse scatter against regressions where no GPU is present)."""
+    import ctypes
+    import io
+    from PIL import Image
+    from augment_ref import build_emulated_jpeg_kernels, jpeg_cases
+    from b200mm import jpeg
+    lib = ctypes.CDLL(build_emulated_jpeg_kernels(tmp_path))
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.emu_jpeg_reconstruct.argtypes = [P, P, P, P, I, P, P, I, I, I, I, P, P]
+    cases = jpeg_cases()[::3]
+    files = [d for _, d in cases]
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    for sparse in (False, True):
+        b = jpeg.pack_jpeg_batch(files, pin=False, sparse=sparse)
+        max_blocks, max_w, max_h, plane_bytes, out_bytes = (int(v) for v in b["jpeg_meta"])
+        planes = torch.zeros(plane_bytes, dtype=torch.uint8)
+        out = torch.zeros(out_bytes, dtype=torch.uint8)
+        if sparse:
+            lib.emu_jpeg_reconstruct(None, vp(b["jpeg_sp_off"]), vp(b["jpeg_sp_idx"]), vp(b["jpeg_sp_val"]), 1,
+                                     vp(b["jpeg_qtabs"]), vp(b["jpeg_table"]), len(files), max_blocks, max_w, max_h,
+                                     vp(planes), vp(out))
+        else:
+            lib.emu_jpeg_reconstruct(vp(b["jpeg_coefs"]), None, None, None, 0, vp(b["jpeg_qtabs"]), vp(b["jpeg_table"]),
+                                     len(files), max_blocks, max_w, max_h, vp(planes), vp(out))
+        t = b["jpeg_table"]
+        for i, (name, data) in enumerate(cases):
+            ref = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+            o, h, w = int(t[i, 23]), int(t[i, 1]), int(t[i, 0])
+            got = out[o:o + h * w * 3].view(h, w, 3).numpy()
+            assert np.array_equal(got, ref), (sparse, name)
