@@ -100,8 +100,10 @@ def test_gemm_dropout_epilogue(ops, cuda_device):
     dg, db = torch.zeros_like(g), torch.zeros_like(g)
     dx, dxm = ops.layernorm_bwd(torch.randn(M, N, device=cuda_device).to(bf16), xin, mean, rstd, g, dg, db,
                                 p_out=0.25, seed_out=77)
-    assert torch.equal(dxm.float() != 0, kept | (dx.float() == 0) & (dxm.float() != 0)) or \
-        ((dxm.float() != 0) == (kept & (dx.float() != 0))).all()
+    # the masked gradient is non-zero exactly where the forward kept the element and the gradient itself is non-zero
+    # (the former two-way "or" of this assertion was implied by this predicate alone: where dx != 0 both said
+    # "dxm != 0 <=> kept", where dx == 0 the masked value is 0 and only this form holds)
+    assert ((dxm.float() != 0) == (kept & (dx.float() != 0))).all()
 
 
 def test_gelu_epilogue_tails(ops, cuda_device):
